@@ -1,0 +1,364 @@
+/*
+ * tracerboy_b200.h — C ABI of the B200-native TracerBoy path-tracing hot path.
+ *
+ * This is the drop-in boundary for the part of wallisc/TracerBoy that sits
+ * behind `class TracerBoy` (TracerBoy/TracerBoy.h:158-397) and behind the
+ * D3D12 Raytracing Fallback Layer interface
+ * (D3D12RaytracingFallback/Include/D3D12RaytracingFallback.h:76-173).
+ *
+ *   - plain C, `extern "C"`, pointers + sizes only; no torch/CUDA types
+ *   - every entry point returns an int (TB_OK = 0, negative = TbStatus)
+ *   - no exception crosses the ABI; message via tb_last_error()
+ *   - one thread at a time per handle (same contract as the reference object,
+ *     D3D12App.cpp:161-168); tb_load_scene may run on a worker thread while
+ *     another thread polls tb_get_load_status()
+ *
+ * The POD structs below reproduce the reference's host<->shader data contract
+ * byte for byte (TracerBoy/SharedShaderStructs.h); static_asserts at the bottom
+ * pin the sizes.
+ */
+#ifndef TRACERBOY_B200_H
+#define TRACERBOY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define TB_API
+#else
+#define TB_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------ status */
+/* Replaces VERIFY/VERIFY_HRESULT (TracerBoy/pch.h:45-47) and the fallback
+ * layer's ThrowFailure(E_INVALIDARG/E_NOTIMPL) (D3D12RaytracingFallback/src/Util.h:12-32). */
+typedef enum TbStatus {
+    TB_OK = 0,
+    TB_ERR_INVALID_ARG = -1, /* E_INVALIDARG */
+    TB_ERR_NOT_IMPL = -2,    /* E_NOTIMPL   */
+    TB_ERR_IO = -3,          /* parser std::runtime_error, missing file */
+    TB_ERR_OOM = -4,
+    TB_ERR_CUDA = -5,
+    TB_ERR_NCCL = -6,
+    TB_ERR_STATE = -7        /* call out of order, e.g. render before load */
+} TbStatus;
+
+/* ------------------------------------------------------- shared data (a1) */
+typedef struct TbFloat2 { float x, y; } TbFloat2;
+typedef struct TbFloat3 { float x, y, z; } TbFloat3;
+typedef struct TbFloat4 { float x, y, z, w; } TbFloat4;
+
+/* SharedShaderStructs.h:116-124 */
+#define TB_DEFAULT_MATERIAL_FLAG 0x0
+#define TB_METALLIC_MATERIAL_FLAG 0x1
+#define TB_SUBSURFACE_SCATTER_MATERIAL_FLAG 0x2
+#define TB_NO_SPECULAR_MATERIAL_FLAG 0x4
+#define TB_MIX_MATERIAL_FLAG 0x8
+#define TB_LIGHT_MATERIAL_FLAG 0x10
+#define TB_NO_ALPHA_MATERIAL_FLAG 0x20
+#define TB_HAIR_MATERIAL_FLAG 0x40
+#define TB_SINGLE_SIDED_MATERIAL_FLAG 0x80
+
+#define TB_INVALID_TEXTURE 0xffffffffu /* UINT_MAX, SharedRaytracing.h:60-63 */
+
+/* SharedShaderStructs.h:141-161, 84 bytes */
+typedef struct TbMaterial {
+    TbFloat3 albedo;
+    uint32_t albedoIndex;
+    uint32_t alphaIndex;
+    uint32_t normalMapIndex;
+    uint32_t emissiveIndex;
+    uint32_t specularMapIndex;
+    float IOR;
+    TbFloat3 absorption;
+    float roughness;
+    TbFloat3 scattering;
+    TbFloat3 emissive;
+    int32_t Flags;
+    float SpecularCoef;
+} TbMaterial;
+
+#define TB_LIGHT_TYPE_AREA 0
+#define TB_LIGHT_TYPE_DIRECTIONAL 1
+
+/* SharedShaderStructs.h:92-111, 104 bytes */
+typedef struct TbLight {
+    uint32_t LightType;
+    TbFloat3 LightColor;
+    float SurfaceArea;
+    TbFloat3 P0, P1, P2;
+    TbFloat3 N0, N1, N2;
+    TbFloat3 Direction;
+} TbLight;
+
+#define TB_IMAGE_TEXTURE_TYPE 0
+#define TB_CHECKER_TEXTURE_TYPE 1
+#define TB_SCALE_TEXTURE_TYPE 2
+#define TB_NEEDS_GAMMA_CORRECTION_TEXTURE_FLAG 0x1
+
+/* SharedShaderStructs.h:169-190, 80 bytes. DescriptorHeapIndex is reinterpreted
+ * as the index into the scene's image table. */
+typedef struct TbTextureData {
+    uint32_t TextureType;
+    uint32_t DescriptorHeapIndex;
+    uint32_t TextureFlags;
+    uint32_t Padding;
+    TbFloat3 CheckerColor1;
+    float UScale;
+    TbFloat3 CheckerColor2;
+    float VScale;
+    uint32_t TextureIndex1;
+    TbFloat3 ScaleColor1;
+    uint32_t TextureIndex2;
+    TbFloat3 ScaleColor2;
+} TbTextureData;
+
+/* SharedShaderStructs.h:85-90, 32 bytes (stride 8 floats, SharedHitGroup.h:11) */
+typedef struct TbVertex {
+    TbFloat3 Normal;
+    TbFloat2 UV;
+    TbFloat3 Tangent;
+} TbVertex;
+
+/* The per-geometry record the shading stage reads. It plays the role of
+ * HitGroupShaderRecord (TracerBoy.cpp:31-41 == SharedHitGroup.h:13-23): the
+ * 32-byte shader identifier and the descriptor-heap indices have no meaning
+ * without D3D12, so the record keeps the material index plus element offsets
+ * into the scene's single pooled vertex / index arrays. */
+typedef struct TbGeometryRecord {
+    uint32_t MaterialIndex;
+    uint32_t VertexFirst;   /* first vertex of this geometry in the pooled arrays */
+    uint32_t VertexCount;
+    uint32_t IndexFirst;    /* first uint32 index of this geometry */
+    uint32_t IndexCount;    /* 3 * triangle count */
+    uint32_t GeometryFlags; /* D3D12_RAYTRACING_GEOMETRY_FLAG_*; 1 = OPAQUE (TracerBoy.cpp:1761) */
+    uint32_t GeometryIndex;
+    uint32_t Padding;
+} TbGeometryRecord;
+
+/* TracerBoy.h:59-67 */
+typedef struct TbCamera {
+    TbFloat3 Position;
+    TbFloat3 LookAt;
+    TbFloat3 Right;
+    TbFloat3 Up;
+    float LensHeight;
+    float FocalDistance;
+} TbCamera;
+
+/* ---------------------------------------------------------------- settings */
+/* TracerBoy.h:171-197 */
+typedef enum TbOutputType {
+    TB_OUTPUT_LIT = 0, TB_OUTPUT_ALBEDO, TB_OUTPUT_NORMALS, TB_OUTPUT_DEPTH,
+    TB_OUTPUT_MOTION_VECTORS, TB_OUTPUT_LUMINANCE, TB_OUTPUT_LUMINANCE_VARIANCE,
+    TB_OUTPUT_LIVE_PIXELS, TB_OUTPUT_LIVE_WAVES, TB_OUTPUT_HEATMAP
+} TbOutputType;
+typedef enum TbRenderMode { TB_RENDER_UNBIASED = 0, TB_RENDER_REALTIME = 1 } TbRenderMode;
+typedef enum TbFilterType { TB_FILTER_BOX = 0, TB_FILTER_TRIANGLE = 1, TB_FILTER_GAUSSIAN = 2 } TbFilterType;
+
+/* POD mirror of TracerBoy::OutputSettings (TracerBoy.h:212-288) restricted to the
+ * members that reach PerFrameConstants (TracerBoy.cpp:2810-2849). Defaults come
+ * from GetDefaultOutputSettings (TracerBoy.h:290-360). */
+typedef struct TbOutputSettings {
+    uint32_t OutputType;           /* TbOutputType, default Lit */
+    uint32_t EnableNormalMaps;     /* default 0 */
+    uint32_t RenderMode;           /* TbRenderMode, default Unbiased */
+    /* DebugSettings */
+    int32_t SampleLimit;           /* 0 = unlimited */
+    float TimeLimitInSeconds;      /* 0 = unlimited */
+    float DebugValue;              /* 1.0 */
+    float DebugValue2;             /* 1.0 */
+    /* CameraOutputSettings */
+    float DOFFocalDistance;        /* 0 = pinhole */
+    float ApertureWidth;           /* 0.075 */
+    uint32_t FilterType;           /* Box */
+    float FilterWidth;             /* 1.0 */
+    /* DenoiserSettings members that reach the tracer */
+    float FireflyClampValue;       /* 0 = off */
+    float MaxZ;                    /* 10000 */
+    /* PerformanceSettings */
+    float ConvergencePercentage;   /* 0.001 (adaptive dispatch is compiled out: RayGenCommon.h:660) */
+    uint32_t EnableNextEventEstimation;          /* 1 */
+    uint32_t EnableSamplingImportanceResampling; /* 0 */
+    uint32_t EnableBlueNoise;      /* 1 */
+    int32_t MaxBounces;            /* 6 */
+} TbOutputSettings;
+
+/* TracerBoy.h:114-128 */
+typedef enum TbSceneLoadState {
+    TB_LOAD_IDLE = 0, TB_LOADING_PBRT, TB_LOADING_HOST, TB_RECORDING_DEVICE_WORK,
+    TB_WAITING_ON_GPU, TB_LOAD_FINISHED, TB_LOAD_FAILED
+} TbSceneLoadState;
+typedef struct TbSceneLoadStatus {
+    uint32_t State;
+    uint32_t InstancesLoaded;
+    uint32_t TotalInstances;
+} TbSceneLoadStatus;
+
+/* TracerBoy.h:362-368 */
+typedef struct TbReadbackStats {
+    uint32_t ActiveWaves;
+    uint32_t ActivePixels;
+    float SelectedPixelDistance;
+    int32_t SelectedMaterialID;
+} TbReadbackStats;
+
+typedef struct TbSceneInfo {
+    uint32_t NumGeometries, NumTriangles, NumVertices, NumMaterials, NumLights,
+        NumTextures, NumImages, HasEnvironmentMap;
+} TbSceneInfo;
+
+/* What tb_readback can return. All float images are row-major, top row first
+ * (DispatchIndex.y = 0 is the top of the image as in the reference). */
+typedef enum TbBufferKind {
+    TB_BUF_ACCUM_RGBW = 0,     /* float4: OutputTexture (RayGenCommon.h:721-722) */
+    TB_BUF_JITTERED_RGBW = 1,  /* float4: JitteredOutputTexture (:723-727) */
+    TB_BUF_RESOLVED_RGB = 2,   /* float3: rgb / w (PostProcessCS.hlsl:23-27) */
+    TB_BUF_AOV_NORMAL = 3,     /* float4: AOVNormals (:575-578) */
+    TB_BUF_AOV_WORLDPOS = 4,   /* float4: AOVWorldPosition of the last frame (:712-719) */
+    TB_BUF_AOV_DEPTH = 5,      /* float:  AOVDepth (:632-640) */
+    TB_BUF_AOV_ALBEDO = 6,     /* float4: AOVCustomOutput (:524-530) */
+    TB_BUF_AOV_EMISSIVE = 7,   /* float4: AOVEmissive (:532-535) */
+    TB_BUF_PRIMARY_HIT_IDS = 8,/* uint2:  (geometryIndex, primitiveIndex) of the last frame's primary hit, 0xffffffff on miss */
+    TB_BUF_RAY_COUNTERS = 9    /* uint2:  per-pixel (TrianglesTested, BoxesTested) summed over the last frame's rays */
+} TbBufferKind;
+
+/* ----------------------------------------------------------- SW-RT boundary */
+/* D3D12_RAYTRACING_GEOMETRY_DESC (triangles only; fallback layer rejects other
+ * vertex formats, LoadPrimitivesPass.cpp:77-84). Pointers are HOST pointers;
+ * the library copies them to the device. */
+typedef struct TbGeometryDesc {
+    const float* Positions;     /* float3 per vertex */
+    uint32_t PositionStrideBytes; /* >= 12 */
+    uint32_t VertexCount;
+    const void* Indices;        /* NULL => non-indexed */
+    uint32_t IndexFormat;       /* 0 = none, 2 = uint16, 4 = uint32 */
+    uint32_t IndexCount;
+    const float* Transform3x4;  /* optional row-major 3x4, may be NULL */
+    uint32_t GeometryFlags;
+} TbGeometryDesc;
+
+typedef enum TbBvhBuildFlags {
+    TB_BVH_BUILD_NONE = 0,
+    TB_BVH_BUILD_PREFER_FAST_TRACE = 0x4, /* 3 treelet passes (TreeletReorder.cpp:63-108) */
+    TB_BVH_BUILD_PREFER_FAST_BUILD = 0x8  /* 0 treelet passes */
+} TbBvhBuildFlags;
+
+/* GetRaytracingAccelerationStructurePrebuildInfo (D3D12RaytracingFallback.h:134-136) */
+typedef struct TbPrebuildInfo {
+    uint64_t ResultDataMaxSizeInBytes; /* 116*N - 16, GpuBVH2Builder.cpp:459 */
+    uint64_t ScratchDataSizeInBytes;
+    uint64_t UpdateScratchDataSizeInBytes;
+} TbPrebuildInfo;
+
+/* RayDesc as consumed by SoftwareRayQuery::TraceRayInline (TraverseFunction.hlsli:39-132) */
+typedef struct TbRay {
+    float Origin[3];
+    float TMin;
+    float Direction[3];
+    float TMax;
+} TbRay;
+
+/* SoftwareHitData (TraverseFunction.hlsli:24-34) + the two counters (:46-47).
+ * t < 0 on miss. */
+typedef struct TbHit {
+    float t;
+    float b1, b2;             /* CommittedTriangleBarycentrics */
+    uint32_t PrimitiveIndex;  /* primitive index inside its geometry */
+    uint32_t GeometryIndex;
+    uint32_t InstanceIndex;   /* always 0 on the single-level fast path */
+    uint32_t TrianglesTested;
+    uint32_t BoxesTested;
+} TbHit;
+
+typedef struct TbRenderStats {
+    uint64_t RaysTraced;       /* every Intersect call: extend + shadow + SSS walk */
+    uint64_t BoxesTested;
+    uint64_t TrianglesTested;
+    uint64_t PathsStarted;
+    uint64_t KernelLaunches;   /* CUDA kernels launched by the library since the last reset */
+    double DeviceMilliseconds; /* CUDA-event time of tb_render calls since the last reset */
+} TbRenderStats;
+
+typedef struct TbHandle TbHandle; /* opaque; owns all device memory */
+
+/* ---------------------------------------------------------------- lifecycle */
+/* TracerBoy::TracerBoy(ID3D12CommandQueue*) (TracerBoy.cpp:507-960). `device` is
+ * the CUDA ordinal. */
+TB_API int tb_create(int device, TbHandle** out);
+TB_API void tb_destroy(TbHandle* h);
+TB_API const char* tb_last_error(TbHandle* h); /* h may be NULL: last create error */
+TB_API const char* tb_version(void);
+
+/* ------------------------------------------------------------- scene + bvh */
+/* TracerBoy::LoadScene (TracerBoy.cpp:1065-2161). Accepts
+ *   *.tbscene            the library's flattened scene cache
+ *   *.pbrt / *.pbf       through the optional importer (libtb_pbrtimport.so)
+ *   "synthetic:<name>?k=v&..."   built-in procedural scenes
+ * then builds the BVH on the device (PREFER_FAST_TRACE, TracerBoy.cpp:1970). */
+TB_API int tb_load_scene(TbHandle* h, const char* path);
+TB_API int tb_load_scene_ex(TbHandle* h, const char* path, uint32_t bvhBuildFlags);
+TB_API int tb_get_load_status(TbHandle* h, TbSceneLoadStatus* out);
+TB_API int tb_save_scene(TbHandle* h, const char* tbscenePath); /* .pbf-cache role, TracerBoy.cpp:1200-1223 */
+/* Host-only: import any supported scene path and write the .tbscene cache (no device needed). */
+TB_API int tb_convert_scene(const char* inPath, const char* outTbscenePath, char* err, size_t errCap);
+TB_API int tb_get_scene_info(TbHandle* h, TbSceneInfo* out);
+TB_API int tb_get_bvh_size(TbHandle* h, uint64_t* bytes);
+/* Copies the BVH in the reference's byte layout (RayTracingHlslCompat.h:344-398). */
+TB_API int tb_get_bvh(TbHandle* h, void* dst, uint64_t bytes);
+TB_API int tb_get_bvh_build_ms(TbHandle* h, double* ms);
+
+/* --------------------------------------------------------- settings/camera */
+TB_API int tb_get_default_settings(TbOutputSettings* out); /* TracerBoy::GetDefaultOutputSettings */
+TB_API int tb_get_camera(TbHandle* h, TbCamera* out);
+TB_API int tb_set_camera(TbHandle* h, const TbCamera* cam); /* invalidates history like TracerBoy::Update */
+TB_API int tb_resize(TbHandle* h, uint32_t width, uint32_t height); /* ResizeBuffersIfNeeded, TracerBoy.cpp:3624-3929 */
+TB_API int tb_select_pixel(TbHandle* h, int x, int y);      /* TracerBoy::SelectPixel */
+TB_API int tb_get_stats(TbHandle* h, TbReadbackStats* out);
+
+/* ------------------------------------------------------------------ render */
+/* nSamples x TracerBoy::Render (TracerBoy.cpp:2677-3369): each sample is one
+ * GlobalFrameCount step. `time` replaces the wall clock of TracerBoy.cpp:2817 and
+ * is an explicit seed input (use 0 for reproducible renders). */
+TB_API int tb_render(TbHandle* h, const TbOutputSettings* settings, uint32_t nSamples, float time);
+TB_API int tb_samples_rendered(TbHandle* h, uint32_t* out); /* GetNumberOfSamplesSinceLastInvalidate */
+TB_API int tb_invalidate_history(TbHandle* h);
+/* Sample-index sharding for multi-GPU: this handle renders only
+ * frames f with f % stride == offset. Default (0, 1). */
+TB_API int tb_set_frame_shard(TbHandle* h, uint32_t offset, uint32_t stride);
+TB_API int tb_buffer_size(TbHandle* h, uint32_t kind, uint64_t* bytes);
+TB_API int tb_readback(TbHandle* h, uint32_t kind, void* dst, uint64_t bytes);
+/* Device pointer of the float4 accumulation buffer (for the NCCL reduce; the
+ * pointer stays valid until tb_resize/tb_destroy). */
+TB_API int tb_device_buffer(TbHandle* h, uint32_t kind, void** devPtr, uint64_t* bytes);
+TB_API int tb_get_render_stats(TbHandle* h, TbRenderStats* out);
+TB_API int tb_reset_render_stats(TbHandle* h);
+TB_API int tb_synchronize(TbHandle* h);
+
+/* --------------------------------------------------------------- materials */
+TB_API int tb_is_material_id_valid(TbHandle* h, int id);                 /* IsMaterialIDValid */
+TB_API int tb_get_material(TbHandle* h, int id, TbMaterial* out, char* name, uint32_t nameCap); /* GetMaterial */
+TB_API int tb_set_material(TbHandle* h, int id, const TbMaterial* m);    /* SetMaterial (invalidates history) */
+
+/* ------------------------------------------------- SW-RT layer equivalents */
+TB_API int tb_bvh_prebuild_info(const TbGeometryDesc* geoms, uint32_t n, TbPrebuildInfo* out);
+/* BuildRaytracingAccelerationStructure on caller-provided geometry; replaces
+ * the handle's scene geometry (materials: one default). */
+TB_API int tb_bvh_build(TbHandle* h, const TbGeometryDesc* geoms, uint32_t n, uint32_t bvhBuildFlags);
+/* SoftwareRayQuery::TraceRayInline + Proceed for n rays (host arrays). */
+TB_API int tb_trace_rays(TbHandle* h, const TbRay* rays, uint64_t n, TbHit* hits);
+
+#ifdef __cplusplus
+}
+static_assert(sizeof(TbMaterial) == 84, "Material must be 84 bytes");
+static_assert(sizeof(TbLight) == 104, "Light must be 104 bytes");
+static_assert(sizeof(TbTextureData) == 80, "TextureData must be 80 bytes");
+static_assert(sizeof(TbVertex) == 32, "Vertex must be 32 bytes");
+static_assert(sizeof(TbRay) == 32, "Ray must be 32 bytes");
+static_assert(sizeof(TbHit) == 32, "Hit must be 32 bytes");
+#endif
+#endif /* TRACERBOY_B200_H */

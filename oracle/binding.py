@@ -1,0 +1,134 @@
+"""ctypes binding of the CPU oracle (TEST INFRASTRUCTURE). Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference leg may import this module."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+BLUE_NOISE = os.path.join(_ROOT, "tracerboy_b200", "data", "bluenoise_rgba8_256.bin")
+_lib = None
+
+
+def lib_path():
+    return os.path.join(_HERE, "liboracle.so")
+
+
+def load():
+    global _lib
+    if _lib is None:
+        lib = C.CDLL(lib_path())
+        lib.oracle_create.restype = C.c_void_p
+        lib.oracle_last_error.restype = C.c_char_p
+        lib.oracle_bvh_size.restype = C.c_uint64
+        lib.oracle_max_treelet_climb.restype = C.c_uint32
+        lib.oracle_num_triangles.restype = C.c_uint32
+        lib.oracle_samples.restype = C.c_uint32
+        for n in ("oracle_destroy", "oracle_last_error", "oracle_bvh_size", "oracle_max_treelet_climb",
+                  "oracle_num_triangles", "oracle_samples", "oracle_invalidate"):
+            getattr(lib, n).argtypes = [C.c_void_p]
+        lib.oracle_load_scene.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        lib.oracle_build_bvh.argtypes = [C.c_void_p, C.c_int]
+        lib.oracle_get_bvh.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.oracle_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.oracle_get_camera.argtypes = [C.c_void_p, C.c_void_p]
+        lib.oracle_set_camera.argtypes = [C.c_void_p, C.c_void_p]
+        lib.oracle_resize.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        lib.oracle_select_pixel.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.oracle_set_samples.argtypes = [C.c_void_p, C.c_uint32]
+        lib.oracle_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_int, C.POINTER(C.c_double)]
+        lib.oracle_get_counts.argtypes = [C.c_void_p, C.c_void_p]
+        lib.oracle_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        lib.oracle_readback.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]
+        _lib = lib
+    return _lib
+
+
+class Oracle:
+    """Same verbs as tracerboy_b200.TracerBoy so the parity tests read symmetrically."""
+    _shape = {0: (np.float32, 4), 1: (np.float32, 4), 2: (np.float32, 3), 3: (np.float32, 4), 4: (np.float32, 4),
+              5: (np.float32, 1), 6: (np.float32, 4), 7: (np.float32, 4), 8: (np.uint32, 2), 9: (np.uint32, 2)}
+
+    def __init__(self):
+        self.lib = load()
+        self.h = C.c_void_p(self.lib.oracle_create())
+        self.width = self.height = 0
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_destroy(self.h)
+            self.h = None
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError("oracle error %d: %s" % (rc, self.lib.oracle_last_error(self.h).decode()))
+
+    def LoadScene(self, tbscene, treelet_passes=3, blue_noise=BLUE_NOISE):
+        self._ck(self.lib.oracle_load_scene(self.h, tbscene.encode(), blue_noise.encode()))
+        self._ck(self.lib.oracle_build_bvh(self.h, treelet_passes))
+
+    def GetBVH(self):
+        n = self.lib.oracle_bvh_size(self.h)
+        buf = np.empty(n, np.uint8)
+        self._ck(self.lib.oracle_get_bvh(self.h, buf.ctypes.data, n))
+        return buf
+
+    def MaxTreeletClimb(self):
+        return self.lib.oracle_max_treelet_climb(self.h)
+
+    def NumTriangles(self):
+        return self.lib.oracle_num_triangles(self.h)
+
+    def TraceRays(self, rays):
+        from tracerboy_b200.api import HIT_DTYPE, RAY_DTYPE
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.empty(rays.shape[0], HIT_DTYPE)
+        self._ck(self.lib.oracle_trace_rays(self.h, rays.ctypes.data, rays.shape[0], hits.ctypes.data))
+        return hits
+
+    def GetCamera(self):
+        from tracerboy_b200.api import Camera
+        c = Camera()
+        self.lib.oracle_get_camera(self.h, C.byref(c))
+        return c
+
+    def SetCamera(self, cam):
+        self.lib.oracle_set_camera(self.h, C.byref(cam))
+
+    def Resize(self, w, h):
+        self._ck(self.lib.oracle_resize(self.h, w, h))
+        self.width, self.height = w, h
+
+    def SelectPixel(self, x, y):
+        self.lib.oracle_select_pixel(self.h, x, y)
+
+    def SetSamples(self, n):
+        self.lib.oracle_set_samples(self.h, n)
+
+    def Render(self, settings, samples=1, time=0.0, threads=0):
+        sec = C.c_double()
+        self._ck(self.lib.oracle_render(self.h, C.byref(settings), samples, C.c_float(time), threads, C.byref(sec)))
+        return sec.value
+
+    def Counts(self):
+        c = (C.c_uint64 * 3)()
+        self.lib.oracle_get_counts(self.h, c)
+        return {"rays": c[0], "boxes": c[1], "tris": c[2]}
+
+    def GetReadbackStats(self):
+        from tracerboy_b200.api import ReadbackStats
+        s = ReadbackStats()
+        self.lib.oracle_get_stats(self.h, C.byref(s))
+        return s
+
+    def Readback(self, kind):
+        dt, ch = self._shape[kind]
+        shape = (self.height, self.width, ch) if ch > 1 else (self.height, self.width)
+        out = np.empty(shape, dt)
+        self._ck(self.lib.oracle_readback(self.h, kind, out.ctypes.data, out.nbytes))
+        return out
+
+    @staticmethod
+    def max_threads():
+        return load().oracle_max_threads()

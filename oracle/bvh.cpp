@@ -1,0 +1,344 @@
+// bvh.cpp — CPU ORACLE (test infrastructure): sequential restatement of the reference's
+// GPU LBVH builder (D3D12RaytracingFallback/src/GpuBVH2Builder.cpp:167-356 and the HLSL
+// kernels it dispatches). Output is the reference's BVH byte layout.
+//
+// Deliberate, documented deviations (both also made by the CUDA builder):
+//  D1  child order on equal subtree sizes: "swap iff leftCount > rightCount". The
+//      reference's rule (ComputeAABBs.hlsli:145-158) depends on thread arrival order.
+//  D2  treelet climbing is not capped. The reference stops every thread group after 33
+//      levels (TreeletReorder.hlsl:293-311), which of two merging groups continues is
+//      arrival-order dependent. Scene::maxTreeletClimb reports the longest chain so a
+//      test can tell when the cap would have mattered.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include "../tracerboy_b200/csrc/common/tb_vec.h"
+#include "oracle.h"
+
+using namespace tbm;
+
+namespace oracle {
+
+namespace {
+
+struct Prim { uint32_t type; float v[9]; };                 // RayTracingHlslCompat.h:122-176 (40 B)
+struct Meta { uint32_t geom, prim, flags; };                // :182-188 (12 B)
+struct HNode { uint32_t parent, left, right; };             // :33-38
+struct Box { f3 mn, mx; };                                  // AABB :40-58
+struct AABBNode { float c[3]; uint32_t flags; float h[3]; uint32_t right; }; // :344-385 (32 B)
+static_assert(sizeof(Prim) == 40 && sizeof(Meta) == 12 && sizeof(AABBNode) == 32, "layout");
+
+const uint32_t kLeafFlag = 0x80000000u; // RayTracingHelper.hlsli:24
+
+inline f3 pv(const Prim& p, int k) { return mk3(p.v[3 * k], p.v[3 * k + 1], p.v[3 * k + 2]); }
+
+// CalculateMortonCodesBindings.h:117-162
+uint32_t morton_code(f3 centroid, f3 smin, f3 smax) {
+    const float epsilon = 0.00001f;
+    f3 dim = max3(smax - smin, mk3(epsilon));
+    f3 unit = (centroid - smin) / dim;
+    const float maxCoord = 1024.0f;
+    f3 adj = min3(max3(unit * maxCoord, mk3(0.0f)), mk3(maxCoord - 1.0f));
+    uint32_t coords[3] = {(uint32_t)adj.y, (uint32_t)adj.x, (uint32_t)adj.z};
+    uint32_t code = 0;
+    for (uint32_t bit = 0; bit < 10; bit++)
+        for (uint32_t axis = 0; axis < 3; axis++)
+            if ((1u << bit) & coords[axis]) code |= 1u << (bit * 3 + axis);
+    return code;
+}
+
+// BuildBVHSplits.hlsli:18-141
+struct Karras {
+    const uint32_t* codes;
+    uint32_t n;
+    static int clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+    int lcp(uint32_t a, uint32_t b) const {
+        if (a >= n || b >= n) return -1;
+        uint32_t ca = codes[a], cb = codes[b];
+        if (ca != cb) return clz(ca ^ cb);
+        return clz(a ^ b) + 31;
+    }
+    void range(uint32_t idx, uint32_t& first, uint32_t& last) const {
+        int d = lcp(idx, idx + 1) - lcp(idx, idx - 1);
+        d = d < -1 ? -1 : (d > 1 ? 1 : d);
+        int minPrefix = lcp(idx, idx - d);
+        int maxLength = 2;
+        while (lcp(idx, idx + (uint32_t)(maxLength * d)) > minPrefix) maxLength *= 4;
+        int length = 0;
+        for (int t = maxLength / 2; t > 0; t /= 2)
+            if (lcp(idx, idx + (uint32_t)((length + t) * d)) > minPrefix) length += t;
+        uint32_t j = idx + (uint32_t)(length * d);
+        first = std::min(idx, j);
+        last = std::max(idx, j);
+    }
+    uint32_t split(uint32_t first, uint32_t last) const {
+        int common = lcp(first, last);
+        int sp = (int)first;
+        int step = (int)(last - first);
+        do {
+            step = (step + 1) >> 1;
+            int ns = sp + step;
+            if ((uint32_t)ns < last) {
+                if (lcp(first, (uint32_t)ns) > common) sp = ns;
+            }
+        } while (step > 1);
+        return (uint32_t)sp;
+    }
+};
+
+inline float surface_area(const Box& b) { // TreeletReorderBindings.h:101-105
+    f3 d = b.mx - b.mn;
+    return 2.0f * ((d.x * d.y + d.x * d.z) + d.y * d.z);
+}
+inline Box combine(const Box& a, const Box& b) { return {min3(a.mn, b.mn), max3(a.mx, b.mx)}; }
+
+// RayTracingHelper.hlsli:251-263 (GetBoxDataFromTriangle) -> center/halfDim
+inline void leaf_box(const Prim& p, f3& center, f3& half) {
+    f3 v0 = pv(p, 0), v1 = pv(p, 1), v2 = pv(p, 2);
+    f3 mn = min3(min3(v0, v1), v2);
+    f3 mx = max3(max3(v0, v1), v2);
+    mn = min3(mn, mx - 0.001f);
+    center = (mn + mx) * 0.5f;
+    half = mx - center;
+}
+
+// One treelet-reorder pass (ClearBuffers.hlsl, FindTreelets.hlsl, TreeletReorder.hlsl).
+void treelet_pass(std::vector<HNode>& H, const std::vector<Prim>& prims, uint32_t n, uint32_t minTris,
+                  uint32_t& maxClimb) {
+    const uint32_t nInternal = n - 1, total = 2 * n - 1;
+    std::vector<Box> aabb(total);
+    std::vector<uint32_t> count(total, 1), depth(total, 0);
+    // post-order over the current topology (children before parents)
+    std::vector<uint32_t> order;
+    order.reserve(nInternal);
+    {
+        std::vector<std::pair<uint32_t, int>> st;
+        st.push_back({0, 0});
+        while (!st.empty()) {
+            auto& top = st.back();
+            uint32_t node = top.first;
+            if (node >= nInternal) { st.pop_back(); continue; }
+            if (top.second == 0) { top.second = 1; depth[H[node].left] = depth[node] + 1; st.push_back({H[node].left, 0}); }
+            else if (top.second == 1) { top.second = 2; depth[H[node].right] = depth[node] + 1; st.push_back({H[node].right, 0}); }
+            else { order.push_back(node); st.pop_back(); }
+        }
+    }
+    for (uint32_t i = 0; i < n; i++) { // FindTreelets.hlsl:16-29 ComputeLeafAABB
+        f3 c, h;
+        leaf_box(prims[i], c, h);
+        aabb[nInternal + i] = {c - h, c + h};
+    }
+    for (uint32_t node : order) {
+        count[node] = count[H[node].left] + count[H[node].right];
+        aabb[node] = combine(aabb[H[node].left], aabb[H[node].right]);
+    }
+    auto isLeaf = [&](uint32_t i) { return i >= nInternal; };
+    for (uint32_t root : order) {
+        if (count[root] < minTris) continue;
+        bool base = count[H[root].left] < minTris && count[H[root].right] < minTris;
+        if (base) maxClimb = std::max(maxClimb, depth[root] + 1);
+        // FormTreelet (TreeletReorder.hlsl:38-80)
+        uint32_t leaves[7], internals[6];
+        internals[0] = root;
+        leaves[0] = H[root].left;
+        leaves[1] = H[root].right;
+        for (uint32_t size = 2; size < 7; size++) {
+            float largest = 0.0f;
+            uint32_t pick = 0, pickIdx = 0;
+            for (uint32_t i = 0; i < size; i++) {
+                uint32_t t = leaves[i];
+                if (!isLeaf(t)) {
+                    float sa = surface_area(aabb[t]);
+                    if (sa > largest) { largest = sa; pick = t; pickIdx = i; }
+                }
+            }
+            HNode nt = H[pick];
+            internals[size - 1] = pick;
+            leaves[pickIdx] = nt.left;
+            leaves[size] = nt.right;
+        }
+        // FindOptimalPartitions (:82-171)
+        float cost[128];
+        uint32_t part[128];
+        memset(part, 0, sizeof(part));
+        cost[0] = 0.0f;
+        for (uint32_t mask = 1; mask < 128; mask++) {
+            Box b = {mk3(FLT_MAX), mk3(-FLT_MAX)};
+            for (uint32_t i = 0; i < 7; i++)
+                if ((1u << i) & mask) b = combine(b, aabb[leaves[i]]);
+            cost[mask] = surface_area(b);
+        }
+        float rootSA = surface_area(aabb[root]);
+        for (uint32_t i = 0; i < 7; i++) cost[1u << i] = 1.0f * surface_area(aabb[leaves[i]]) / rootSA;
+        for (uint32_t subset = 2; subset <= 7; subset++) {
+            for (uint32_t mask = 1; mask < 128; mask++) {
+                if ((uint32_t)__builtin_popcount(mask) != subset) continue;
+                float lowest = FLT_MAX;
+                uint32_t best = 0;
+                uint32_t delta = (mask - 1) & mask;
+                uint32_t p = (0u - delta) & mask;
+                do {
+                    float c = cost[p] + cost[mask ^ p];
+                    if (c < lowest) { lowest = c; best = p; }
+                    p = (p - delta) & mask;
+                } while (p != 0);
+                cost[mask] = 1.0f * cost[mask] + lowest;
+                part[mask] = best;
+            }
+        }
+        // ReformTree (:173-236)
+        struct Entry { uint32_t mask, node; };
+        Entry stack[7];
+        uint32_t allocated = 1, sp = 1;
+        stack[0] = {127u, internals[0]};
+        while (sp > 0) {
+            Entry e = stack[--sp];
+            Entry l, r;
+            l.mask = part[e.mask];
+            if (__builtin_popcount(l.mask) > 1) { l.node = internals[allocated++]; stack[sp++] = l; }
+            else l.node = leaves[__builtin_ctz(l.mask)];
+            r.mask = e.mask ^ l.mask;
+            if (__builtin_popcount(r.mask) > 1) { r.node = internals[allocated++]; stack[sp++] = r; }
+            else r.node = leaves[__builtin_ctz(r.mask)];
+            H[e.node].left = l.node;
+            H[e.node].right = r.node;
+            H[l.node].parent = e.node;
+            H[r.node].parent = e.node;
+        }
+        for (int j = 5; j >= 0; j--) {
+            uint32_t in = internals[j];
+            aabb[in] = combine(aabb[H[in].left], aabb[H[in].right]);
+        }
+    }
+}
+
+} // namespace
+
+bool build_bvh(Scene& s, int treeletPasses, std::string& err) {
+    // LoadPrimitives (LoadPrimitivesPass.cpp:56-169, BottomLevelLoadTriangles.hlsli:88-126)
+    std::vector<Prim> prims;
+    std::vector<Meta> meta;
+    for (size_t g = 0; g < s.geoms.size(); g++) {
+        const TbGeometryRecord& G = s.geoms[g];
+        for (uint32_t t = 0; t < G.IndexCount / 3; t++) {
+            Prim p;
+            p.type = 1;
+            for (int k = 0; k < 3; k++) {
+                const TbFloat3& v = s.positions[G.VertexFirst + s.indices[G.IndexFirst + 3 * t + k]];
+                p.v[3 * k] = v.x; p.v[3 * k + 1] = v.y; p.v[3 * k + 2] = v.z;
+            }
+            prims.push_back(p);
+            meta.push_back({(uint32_t)g, t, G.GeometryFlags});
+        }
+    }
+    const uint32_t n = (uint32_t)prims.size();
+    if (n == 0) { err = "scene has no triangles"; return false; }
+    // The reference keeps 24-bit child / leaf indices (RayTracingHelper.hlsli:97-103), which
+    // silently wrap above 2^24 nodes. We mask with 30 bits instead (bit 31 = leaf, bit 30 =
+    // procedural): byte-identical for every scene the reference can represent, and valid
+    // up to 2^30 nodes (needed by the 20 M-triangle config).
+    if (2ull * n - 1 > (1ull << 30)) { err = "too many triangles for 30-bit node indices"; return false; }
+    // CalculateSceneAABBFromPrimitives.hlsl:16-40
+    f3 smin = mk3(FLT_MAX), smax = mk3(-FLT_MAX);
+    for (const Prim& p : prims) {
+        smin = min3(min3(min3(pv(p, 0), smin), pv(p, 1)), pv(p, 2));
+        smax = max3(max3(max3(pv(p, 0), smax), pv(p, 1)), pv(p, 2));
+    }
+    // Morton codes (CalculateMortonCodesForPrimitives.hlsl:17-24)
+    std::vector<uint32_t> codes(n), order(n);
+    for (uint32_t i = 0; i < n; i++) {
+        f3 c = ((pv(prims[i], 0) + pv(prims[i], 1)) + pv(prims[i], 2)) / 3.0f;
+        codes[i] = morton_code(c, smin, smax);
+        order[i] = i;
+    }
+    // Bitonic sort == stable sort by (code, index) (BitonicSortCommon.hlsli:37-47)
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return codes[a] < codes[b]; });
+    // RearrangeTriangles.hlsl:29-36
+    std::vector<Prim> sp(n);
+    std::vector<Meta> sm(n);
+    std::vector<uint32_t> sc(n);
+    for (uint32_t i = 0; i < n; i++) { sp[i] = prims[order[i]]; sm[i] = meta[order[i]]; sc[i] = codes[order[i]]; }
+
+    const uint32_t nInternal = n - 1, total = 2 * n - 1;
+    std::vector<HNode> H(total, HNode{0xffffffffu, 0, 0});
+    if (n > 1) {
+        Karras K{sc.data(), n};
+        for (uint32_t idx = 0; idx < nInternal; idx++) {
+            uint32_t first, last;
+            K.range(idx, first, last);
+            uint32_t split = K.split(first, last);
+            uint32_t a = (split == first) ? nInternal + split : split;
+            uint32_t b = (split + 1 == last) ? nInternal + split + 1 : split + 1;
+            H[idx].left = a;
+            H[idx].right = b;
+            H[a].parent = idx;
+            H[b].parent = idx;
+        }
+        // TreeletReorder.cpp:63-108
+        uint32_t minTris = 7;
+        s.maxTreeletClimb = 0;
+        for (int pass = 0; pass < treeletPasses; pass++) {
+            if (minTris > n) break;
+            treelet_pass(H, sp, n, minTris, s.maxTreeletClimb);
+            minTris *= 2;
+        }
+    }
+    // PrepareForComputeAABBs + ComputeAABBs (ComputeAABBs.hlsli:69-172)
+    const uint32_t offBoxes = 16;
+    const uint32_t offPrims = offBoxes + 32 * total;
+    const uint32_t offMeta = offPrims + 40 * n;
+    const uint64_t totalSize = (uint64_t)offMeta + 12ull * n;
+    s.bvh.assign(totalSize, 0);
+    uint32_t header[4] = {offBoxes, offPrims, offMeta, (uint32_t)totalSize};
+    memcpy(s.bvh.data(), header, 16);
+    AABBNode* nodes = (AABBNode*)(s.bvh.data() + offBoxes);
+    memcpy(s.bvh.data() + offPrims, sp.data(), 40ull * n);
+    memcpy(s.bvh.data() + offMeta, sm.data(), 12ull * n);
+    for (uint32_t i = 0; i < n; i++) {
+        f3 c, h;
+        leaf_box(sp[i], c, h);
+        AABBNode& nd = nodes[nInternal + i];
+        nd.c[0] = c.x; nd.c[1] = c.y; nd.c[2] = c.z;
+        nd.h[0] = h.x; nd.h[1] = h.y; nd.h[2] = h.z;
+        nd.flags = i | kLeafFlag;
+        nd.right = 1;
+    }
+    if (n > 1) {
+        // bottom-up in post-order; counts decide the child swap (deviation D1)
+        std::vector<uint32_t> cnt(total, 1);
+        std::vector<std::pair<uint32_t, int>> st;
+        st.push_back({0, 0});
+        while (!st.empty()) {
+            auto& top = st.back();
+            uint32_t node = top.first;
+            if (node >= nInternal) { st.pop_back(); continue; }
+            if (top.second == 0) { top.second = 1; st.push_back({H[node].left, 0}); }
+            else if (top.second == 1) { top.second = 2; st.push_back({H[node].right, 0}); }
+            else {
+                uint32_t l = H[node].left, r = H[node].right;
+                if (cnt[l] > cnt[r]) std::swap(l, r);
+                cnt[node] = cnt[l] + cnt[r];
+                const AABBNode& A = nodes[l];
+                const AABBNode& B = nodes[r];
+                f3 ac = mk3(A.c[0], A.c[1], A.c[2]), ah = mk3(A.h[0], A.h[1], A.h[2]);
+                f3 bc = mk3(B.c[0], B.c[1], B.c[2]), bh = mk3(B.h[0], B.h[1], B.h[2]);
+                f3 mn = min3(ac - ah, bc - bh); // GetBoxFromChildBoxes, RayTracingHelper.hlsli:275-285
+                f3 mx = max3(ac + ah, bc + bh);
+                f3 c = (mn + mx) * 0.5f;
+                f3 h = mx - c;
+                AABBNode& nd = nodes[node];
+                nd.c[0] = c.x; nd.c[1] = c.y; nd.c[2] = c.z;
+                nd.h[0] = h.x; nd.h[1] = h.y; nd.h[2] = h.z;
+                nd.flags = l & 0x3fffffffu;
+                nd.right = r;
+                st.pop_back();
+            }
+        }
+    }
+    s.numPrims = n;
+    return true;
+}
+
+} // namespace oracle

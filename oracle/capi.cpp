@@ -1,0 +1,119 @@
+// capi.cpp — CPU ORACLE (test infrastructure): C entry points for ctypes.
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "oracle.h"
+
+using namespace oracle;
+
+struct OracleHandle {
+    Scene scene;
+    FrameBuffers fb;
+    TbCamera camera;
+    std::string err;
+    uint32_t samples = 0;
+    int selX = -1, selY = -1;
+};
+
+#define ORACLE_API extern "C" __attribute__((visibility("default")))
+
+ORACLE_API OracleHandle* oracle_create() { return new OracleHandle(); }
+ORACLE_API void oracle_destroy(OracleHandle* h) { delete h; }
+ORACLE_API const char* oracle_last_error(OracleHandle* h) { return h->err.c_str(); }
+ORACLE_API int oracle_max_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+ORACLE_API int oracle_load_scene(OracleHandle* h, const char* tbscene, const char* blueNoiseBin) {
+    if (!load_tbscene(h->scene, tbscene, h->err)) return -3;
+    h->camera = h->scene.camera;
+    h->scene.blueNoise.assign(2 * 256 * 256 * 4, 0);
+    if (blueNoiseBin && *blueNoiseBin) {
+        FILE* f = fopen(blueNoiseBin, "rb");
+        if (!f || fread(h->scene.blueNoise.data(), 1, h->scene.blueNoise.size(), f) != h->scene.blueNoise.size()) {
+            if (f) fclose(f);
+            h->err = std::string("cannot read blue noise ") + blueNoiseBin;
+            return -3;
+        }
+        fclose(f);
+    }
+    h->samples = 0;
+    return 0;
+}
+ORACLE_API int oracle_build_bvh(OracleHandle* h, int treeletPasses) { return build_bvh(h->scene, treeletPasses, h->err) ? 0 : -1; }
+ORACLE_API uint64_t oracle_bvh_size(OracleHandle* h) { return h->scene.bvh.size(); }
+ORACLE_API int oracle_get_bvh(OracleHandle* h, void* dst, uint64_t bytes) {
+    if (bytes < h->scene.bvh.size()) return -1;
+    memcpy(dst, h->scene.bvh.data(), h->scene.bvh.size());
+    return 0;
+}
+ORACLE_API uint32_t oracle_max_treelet_climb(OracleHandle* h) { return h->scene.maxTreeletClimb; }
+ORACLE_API uint32_t oracle_num_triangles(OracleHandle* h) { return h->scene.numPrims; }
+ORACLE_API int oracle_trace_rays(OracleHandle* h, const TbRay* rays, uint64_t n, TbHit* hits) {
+    if (h->scene.bvh.empty()) { h->err = "no bvh"; return -7; }
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < (int64_t)n; i++) trace_ray(h->scene, rays[i], hits[i]);
+    return 0;
+}
+ORACLE_API int oracle_get_camera(OracleHandle* h, TbCamera* c) { *c = h->camera; return 0; }
+ORACLE_API int oracle_set_camera(OracleHandle* h, const TbCamera* c) { h->camera = *c; h->samples = 0; return 0; }
+ORACLE_API int oracle_resize(OracleHandle* h, uint32_t w, uint32_t hh) { h->fb.resize(w, hh); h->samples = 0; return 0; }
+ORACLE_API int oracle_select_pixel(OracleHandle* h, int x, int y) { h->selX = x; h->selY = y; return 0; }
+ORACLE_API int oracle_invalidate(OracleHandle* h) { h->samples = 0; return 0; }
+ORACLE_API uint32_t oracle_samples(OracleHandle* h) { return h->samples; }
+ORACLE_API int oracle_set_samples(OracleHandle* h, uint32_t s) { h->samples = s; return 0; }
+// nSamples x one-sample Render; returns elapsed seconds through *seconds.
+ORACLE_API int oracle_render(OracleHandle* h, const TbOutputSettings* s, uint32_t nSamples, float time, int threads, double* seconds) {
+    if (h->scene.bvh.empty() || h->fb.width == 0) { h->err = "render before load/resize"; return -7; }
+    auto t0 = std::chrono::high_resolution_clock::now();
+    for (uint32_t i = 0; i < nSamples; i++) {
+        RenderParams p;
+        p.settings = *s; p.camera = h->camera; p.time = time; p.frame = h->samples;
+        p.selectedX = h->selX; p.selectedY = h->selY;
+        render_frame(h->scene, p, h->fb, threads);
+        h->samples++;
+    }
+    auto t1 = std::chrono::high_resolution_clock::now();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    return 0;
+}
+ORACLE_API int oracle_get_counts(OracleHandle* h, uint64_t* out3) {
+    out3[0] = h->fb.raysTraced; out3[1] = h->fb.boxesTested; out3[2] = h->fb.trianglesTested;
+    return 0;
+}
+ORACLE_API int oracle_get_stats(OracleHandle* h, TbReadbackStats* s) { *s = h->fb.stats; return 0; }
+ORACLE_API int oracle_readback(OracleHandle* h, uint32_t kind, void* dst, uint64_t bytes) {
+    FrameBuffers& fb = h->fb;
+    size_t n = (size_t)fb.width * fb.height;
+    const void* src = nullptr;
+    size_t sz = 0;
+    std::vector<float> tmp;
+    switch (kind) {
+    case TB_BUF_ACCUM_RGBW: src = fb.accum.data(); sz = n * 16; break;
+    case TB_BUF_JITTERED_RGBW: src = fb.jittered.data(); sz = n * 16; break;
+    case TB_BUF_RESOLVED_RGB:
+        tmp.resize(n * 3);
+        for (size_t i = 0; i < n; i++) { // PostProcessCS.hlsl:23-27
+            tmp[3 * i] = fb.accum[i].x / fb.accum[i].w; tmp[3 * i + 1] = fb.accum[i].y / fb.accum[i].w; tmp[3 * i + 2] = fb.accum[i].z / fb.accum[i].w;
+        }
+        src = tmp.data(); sz = n * 12; break;
+    case TB_BUF_AOV_NORMAL: src = fb.aovNormal.data(); sz = n * 16; break;
+    case TB_BUF_AOV_WORLDPOS: src = fb.aovWorldPos[(h->samples + 1) % 2].data(); sz = n * 16; break;
+    case TB_BUF_AOV_DEPTH: src = fb.aovDepth.data(); sz = n * 4; break;
+    case TB_BUF_AOV_ALBEDO: src = fb.aovAlbedo.data(); sz = n * 16; break;
+    case TB_BUF_AOV_EMISSIVE: src = fb.aovEmissive.data(); sz = n * 16; break;
+    case TB_BUF_PRIMARY_HIT_IDS: src = fb.primaryHit.data(); sz = n * 8; break;
+    case TB_BUF_RAY_COUNTERS: src = fb.counters.data(); sz = n * 8; break;
+    default: h->err = "bad buffer kind"; return -1;
+    }
+    if (bytes < sz) { h->err = "buffer too small"; return -1; }
+    memcpy(dst, src, sz);
+    return 0;
+}

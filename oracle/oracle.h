@@ -1,0 +1,78 @@
+// oracle.h — CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+//
+// A sequential/OpenMP restatement of the reference's hot path: the fallback-layer LBVH
+// builder, the software BVH2 traversal with watertight triangles, and the per-pixel
+// path-tracing core. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference leg may load this library; the product (tracerboy_b200/) never does.
+//
+// PARITY PIN STATUS: the reference ships no tests, golden vectors or fixtures for this
+// path and its own implementation (HLSL + D3D12) cannot run here, so
+// this restatement is pinned by (i) oracle/ref_core, which compiles the reference's
+// kernel.glsl from the mount as host C++ and must agree with core.cpp bit for bit when
+// /root/reference is available, and (ii) analytic known answers in tests/. Where neither
+// applies the status is "parity unpinned" (see DESIGN.md §Oracle).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "tracerboy_b200.h"
+
+namespace oracle {
+
+struct Image {
+    uint32_t width = 0, height = 0, format = 0; // 0 float4, 1 unorm8x4
+    std::vector<uint8_t> data;
+};
+
+struct Scene {
+    std::vector<TbGeometryRecord> geoms;
+    std::vector<TbFloat3> positions;
+    std::vector<TbVertex> vertices;
+    std::vector<uint32_t> indices;
+    std::vector<TbMaterial> materials;
+    std::vector<TbLight> lights;
+    std::vector<TbTextureData> textures;
+    std::vector<Image> images;
+    TbCamera camera{};
+    uint32_t flipTextureUVs = 0;
+    int32_t envImage = -1;
+    TbFloat4 envTransform[3];
+    TbFloat3 envColorScale{1, 1, 1};
+    std::vector<uint8_t> blueNoise; // 2 x 256 x 256 x RGBA8 (LDR_RGBA_0, LDR_RGBA_1)
+    // built BVH, byte layout of RayTracingHlslCompat.h:344-398
+    std::vector<uint8_t> bvh;
+    uint32_t numPrims = 0;
+    uint32_t maxTreeletClimb = 0; // longest base-treelet -> root chain (reference caps at 33)
+};
+
+bool load_tbscene(Scene& s, const std::string& path, std::string& err);
+
+// BVH build (GpuBVH2Builder.cpp:167-356). passes: 3 = PREFER_FAST_TRACE, 1 = default, 0 = FAST_BUILD.
+bool build_bvh(Scene& s, int treeletPasses, std::string& err);
+
+// SoftwareRayQuery::TraceRayInline + Proceed (TraverseFunction.hlsli:537-785), FAST_PATH.
+void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit);
+
+struct FrameBuffers {
+    uint32_t width = 0, height = 0;
+    std::vector<TbFloat4> accum, jittered, aovNormal, aovWorldPos[2], aovAlbedo, aovEmissive;
+    std::vector<float> aovDepth;
+    std::vector<uint32_t> primaryHit; // 2 per pixel
+    std::vector<uint32_t> counters;   // 2 per pixel: tris, boxes
+    uint64_t raysTraced = 0, boxesTested = 0, trianglesTested = 0;
+    TbReadbackStats stats{};
+    void resize(uint32_t w, uint32_t h);
+};
+
+struct RenderParams {
+    TbOutputSettings settings;
+    TbCamera camera;
+    float time = 0.0f;
+    uint32_t frame = 0; // GlobalFrameCount
+    int selectedX = -1, selectedY = -1;
+};
+
+// One SoftwareRayTraceCS dispatch (SoftwareRayTraceCS.hlsl:9-51): one sample per pixel.
+void render_frame(const Scene& s, const RenderParams& p, FrameBuffers& fb, int numThreads);
+
+} // namespace oracle

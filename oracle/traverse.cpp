@@ -1,0 +1,131 @@
+// traverse.cpp — CPU ORACLE (test infrastructure): restatement of the software ray query
+// (D3D12RaytracingFallback/src/TraverseFunction.hlsli:203-313, 316-429, 473-495, 537-779)
+// with FAST_PATH=1, DISABLE_ANYHIT, DISABLE_PROCEDURAL_GEOMETRY (RayGenCommon.h:355-362).
+//
+// Pinned semantics: rcp(x) = 1/x; the slab test's a*b+-c are single fmaf;
+// the watertight triangle test is evaluated unfused (`precise`); the traversal stack is
+// unbounded (reference: 16 entries, unchecked); on exactly equal t the hit with the lower
+// (geometryIndex, primitiveIndex) wins (reference: first found).
+#include <cfloat>
+#include <cstring>
+#include "../tracerboy_b200/csrc/common/tb_vec.h"
+#include "oracle.h"
+
+using namespace tbm;
+
+namespace oracle {
+
+namespace {
+struct AABBNode { float c[3]; uint32_t flags; float h[3]; uint32_t right; };
+
+// RayBoxTest, TraverseFunction.hlsli:203-221
+inline bool ray_box(float& resultT, float closestT, f3 oinv, f3 inv, const AABBNode& b) {
+    f3 ainv = abs3(inv);
+    float rx = fmaf(b.c[0], inv.x, -oinv.x), ry = fmaf(b.c[1], inv.y, -oinv.y), rz = fmaf(b.c[2], inv.z, -oinv.z);
+    float maxx = fmaf(b.h[0], ainv.x, rx), maxy = fmaf(b.h[1], ainv.y, ry), maxz = fmaf(b.h[2], ainv.z, rz);
+    float minx = fmaf(-b.h[0], ainv.x, rx), miny = fmaf(-b.h[1], ainv.y, ry), minz = fmaf(-b.h[2], ainv.z, rz);
+    float minT = fmaxf(fmaxf(minx, miny), minz);
+    float maxT = fminf(fminf(maxx, maxy), maxz);
+    resultT = fmaxf(minT, 0.0f);
+    return fmaxf(minT, 0.0f) < fminf(maxT, closestT);
+}
+
+// RayTriangleIntersect, TraverseFunction.hlsli:231-313 (RAY_FLAG_NONE, instanceFlags 0 => two-sided)
+inline bool ray_tri(float& hitT, float& b1, float& b2, f3 org, int kx, int ky, int kz, f3 shear,
+                    const float* v) {
+    f3 v0 = mk3(v[0], v[1], v[2]) - org, v1 = mk3(v[3], v[4], v[5]) - org, v2 = mk3(v[6], v[7], v[8]) - org;
+    float Ax = comp(v0, kx), Ay = comp(v0, ky), Az = comp(v0, kz);
+    float Bx = comp(v1, kx), By = comp(v1, ky), Bz = comp(v1, kz);
+    float Cx = comp(v2, kx), Cy = comp(v2, ky), Cz = comp(v2, kz);
+    Ax = Ax - shear.x * Az; Ay = Ay - shear.y * Az;
+    Bx = Bx - shear.x * Bz; By = By - shear.y * Bz;
+    Cx = Cx - shear.x * Cz; Cy = Cy - shear.y * Cz;
+    float U = Cx * By - Cy * Bx;
+    float V = Ax * Cy - Ay * Cx;
+    float W = Bx * Ay - By * Ax;
+    float det = (U + V) + W;
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    if (det == 0.0f) return false;
+    Az = shear.z * Az; Bz = shear.z * Bz; Cz = shear.z * Cz;
+    float T = (U * Az + V * Bz) + W * Cz;
+    float signCorrectedT = fabsf(T);
+    if ((T > 0.0f) != (det > 0.0f)) signCorrectedT = -signCorrectedT;
+    if (signCorrectedT < 0.0f || signCorrectedT > hitT * fabsf(det)) return false;
+    float rcpDet = 1.0f / det;
+    b1 = V * rcpDet;
+    b2 = W * rcpDet;
+    hitT = T * rcpDet;
+    return true;
+}
+} // namespace
+
+void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit) {
+    const uint8_t* bvh = s.bvh.data();
+    uint32_t header[4];
+    memcpy(header, bvh, 16);
+    const AABBNode* nodes = (const AABBNode*)(bvh + header[0]);
+    const uint8_t* prims = bvh + header[1];
+    const uint32_t* meta = (const uint32_t*)(bvh + header[2]);
+
+    f3 org = mk3(ray.Origin[0], ray.Origin[1], ray.Origin[2]);
+    f3 dir = mk3(ray.Direction[0], ray.Direction[1], ray.Direction[2]);
+    // GetRayData, TraverseFunction.hlsli:473-495
+    f3 inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+    f3 oinv = org * inv;
+    f3 ad = abs3(dir);
+    int kz = (ad.x > ad.y && ad.x > ad.z) ? 0 : (ad.y > ad.z ? 1 : 2);
+    int kx = (kz + 1) % 3, ky = (kz + 2) % 3;
+    if (comp(dir, kz) < 0.0f) { int t = kx; kx = ky; ky = t; }
+    f3 shear = mk3(comp(dir, kx) / comp(dir, kz), comp(dir, ky) / comp(dir, kz), 1.0f / comp(dir, kz));
+
+    float committedT = ray.TMax;
+    bool haveHit = false;
+    uint32_t hitGeom = 0, hitPrim = 0;
+    float hb1 = 0, hb2 = 0;
+    uint32_t trisTested = 0, boxesTested = 0;
+
+    static thread_local std::vector<uint32_t> stack; // unbounded (reference: 16, unchecked)
+    stack.clear();
+    float unusedT;
+    if (ray_box(unusedT, committedT, oinv, inv, nodes[0])) stack.push_back(0);
+    while (!stack.empty()) {
+        uint32_t ni = stack.back();
+        stack.pop_back();
+        const AABBNode& nd = nodes[ni];
+        if (nd.flags & 0x80000000u) {
+            uint32_t leaf = nd.flags & 0x3fffffffu;
+            const uint32_t* m = meta + 3 * (size_t)leaf;
+            trisTested++;
+            float t0 = committedT, b1, b2;
+            const float* v = (const float*)(prims + 40 * (size_t)leaf + 4);
+            bool ok = ray_tri(t0, b1, b2, org, kx, ky, kz, shear, v);
+            // TestLeafNodeIntersections :420 plus the equal-t tie-break
+            bool closer = t0 < committedT;
+            bool tie = haveHit && t0 == committedT && (m[0] < hitGeom || (m[0] == hitGeom && m[1] < hitPrim));
+            if (ok && (closer || tie) && t0 > ray.TMin) {
+                committedT = t0; hb1 = b1; hb2 = b2; hitGeom = m[0]; hitPrim = m[1]; haveHit = true;
+            }
+        } else {
+            uint32_t l = nd.flags & 0x3fffffffu, r = nd.right;
+            float lt, rt;
+            bool lh = ray_box(lt, committedT, oinv, inv, nodes[l]);
+            bool rh = ray_box(rt, committedT, oinv, inv, nodes[r]);
+            boxesTested += 2;
+            if (lh && rh) { // far first, near last; on equal t left is near (:754-765)
+                bool rightFirst = rt < lt;
+                stack.push_back(rightFirst ? l : r);
+                stack.push_back(rightFirst ? r : l);
+            } else if (lh || rh) stack.push_back(rh ? r : l);
+        }
+    }
+    hit.TrianglesTested = trisTested;
+    hit.BoxesTested = boxesTested;
+    hit.InstanceIndex = 0;
+    if (haveHit && committedT < ray.TMax) {
+        hit.t = committedT; hit.b1 = hb1; hit.b2 = hb2; hit.PrimitiveIndex = hitPrim; hit.GeometryIndex = hitGeom;
+    } else {
+        hit.t = -1.0f; hit.b1 = hit.b2 = 0; hit.PrimitiveIndex = hit.GeometryIndex = 0xffffffffu;
+    }
+}
+
+} // namespace oracle

@@ -1,0 +1,12 @@
+"""tracerboy_b200 — B200-native implementation of TracerBoy's path-tracing hot path.
+
+The product is the CUDA library behind the C ABI in include/tracerboy_b200.h; this package
+is a thin ctypes mirror of the reference's `class TracerBoy` (TracerBoy/TracerBoy.h:158-397).
+There is no CPU fallback: importing works anywhere, but every compute call raises
+TracerBoyError when the CUDA library or a CUDA device is missing.
+"""
+from .api import (TracerBoy, TracerBoyError, OutputSettings, Camera, Material, Ray, Hit, RenderStats,
+                  SceneInfo, BufferKind, lib_path, load_library, convert_scene, get_default_output_settings)
+
+__all__ = ["TracerBoy", "TracerBoyError", "OutputSettings", "Camera", "Material", "Ray", "Hit", "RenderStats",
+           "SceneInfo", "BufferKind", "lib_path", "load_library", "convert_scene", "get_default_output_settings"]

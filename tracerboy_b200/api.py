@@ -1,0 +1,348 @@
+"""ctypes mirror of `class TracerBoy` (TracerBoy/TracerBoy.h:158-397) over the C ABI.
+
+Method names follow the reference (LoadScene, Render, SetMaterial, ...). Everything heavy
+happens in libtracerboy_b200.so; numpy is only used to hand out readback buffers.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class TracerBoyError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("tracerboy_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+class Float3(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+    def tuple(self):
+        return (self.x, self.y, self.z)
+
+
+class Material(C.Structure):  # SharedShaderStructs.h:141-161
+    _fields_ = [("albedo", Float3), ("albedoIndex", C.c_uint32), ("alphaIndex", C.c_uint32),
+                ("normalMapIndex", C.c_uint32), ("emissiveIndex", C.c_uint32), ("specularMapIndex", C.c_uint32),
+                ("IOR", C.c_float), ("absorption", Float3), ("roughness", C.c_float), ("scattering", Float3),
+                ("emissive", Float3), ("Flags", C.c_int32), ("SpecularCoef", C.c_float)]
+
+
+class Camera(C.Structure):  # TracerBoy.h:59-67
+    _fields_ = [("Position", Float3), ("LookAt", Float3), ("Right", Float3), ("Up", Float3),
+                ("LensHeight", C.c_float), ("FocalDistance", C.c_float)]
+
+
+class OutputSettings(C.Structure):  # TracerBoy.h:212-288 (members that reach PerFrameConstants)
+    _fields_ = [("OutputType", C.c_uint32), ("EnableNormalMaps", C.c_uint32), ("RenderMode", C.c_uint32),
+                ("SampleLimit", C.c_int32), ("TimeLimitInSeconds", C.c_float), ("DebugValue", C.c_float),
+                ("DebugValue2", C.c_float), ("DOFFocalDistance", C.c_float), ("ApertureWidth", C.c_float),
+                ("FilterType", C.c_uint32), ("FilterWidth", C.c_float), ("FireflyClampValue", C.c_float),
+                ("MaxZ", C.c_float), ("ConvergencePercentage", C.c_float), ("EnableNextEventEstimation", C.c_uint32),
+                ("EnableSamplingImportanceResampling", C.c_uint32), ("EnableBlueNoise", C.c_uint32),
+                ("MaxBounces", C.c_int32)]
+
+
+class Ray(C.Structure):
+    _fields_ = [("Origin", C.c_float * 3), ("TMin", C.c_float), ("Direction", C.c_float * 3), ("TMax", C.c_float)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("t", C.c_float), ("b1", C.c_float), ("b2", C.c_float), ("PrimitiveIndex", C.c_uint32),
+                ("GeometryIndex", C.c_uint32), ("InstanceIndex", C.c_uint32), ("TrianglesTested", C.c_uint32),
+                ("BoxesTested", C.c_uint32)]
+
+
+RAY_DTYPE = np.dtype([("Origin", np.float32, 3), ("TMin", np.float32), ("Direction", np.float32, 3), ("TMax", np.float32)])
+HIT_DTYPE = np.dtype([("t", np.float32), ("b1", np.float32), ("b2", np.float32), ("PrimitiveIndex", np.uint32),
+                      ("GeometryIndex", np.uint32), ("InstanceIndex", np.uint32), ("TrianglesTested", np.uint32),
+                      ("BoxesTested", np.uint32)])
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("RaysTraced", C.c_uint64), ("BoxesTested", C.c_uint64), ("TrianglesTested", C.c_uint64),
+                ("PathsStarted", C.c_uint64), ("KernelLaunches", C.c_uint64), ("DeviceMilliseconds", C.c_double)]
+
+
+class SceneInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("NumGeometries", "NumTriangles", "NumVertices", "NumMaterials",
+                                          "NumLights", "NumTextures", "NumImages", "HasEnvironmentMap")]
+
+
+class ReadbackStats(C.Structure):
+    _fields_ = [("ActiveWaves", C.c_uint32), ("ActivePixels", C.c_uint32), ("SelectedPixelDistance", C.c_float),
+                ("SelectedMaterialID", C.c_int32)]
+
+
+class LoadStatus(C.Structure):
+    _fields_ = [("State", C.c_uint32), ("InstancesLoaded", C.c_uint32), ("TotalInstances", C.c_uint32)]
+
+
+class GeometryDesc(C.Structure):
+    _fields_ = [("Positions", C.c_void_p), ("PositionStrideBytes", C.c_uint32), ("VertexCount", C.c_uint32),
+                ("Indices", C.c_void_p), ("IndexFormat", C.c_uint32), ("IndexCount", C.c_uint32),
+                ("Transform3x4", C.c_void_p), ("GeometryFlags", C.c_uint32)]
+
+
+class PrebuildInfo(C.Structure):
+    _fields_ = [("ResultDataMaxSizeInBytes", C.c_uint64), ("ScratchDataSizeInBytes", C.c_uint64),
+                ("UpdateScratchDataSizeInBytes", C.c_uint64)]
+
+
+class BufferKind:
+    ACCUM_RGBW, JITTERED_RGBW, RESOLVED_RGB, AOV_NORMAL, AOV_WORLDPOS, AOV_DEPTH, AOV_ALBEDO, AOV_EMISSIVE, \
+        PRIMARY_HIT_IDS, RAY_COUNTERS = range(10)
+    _shape = {0: (np.float32, 4), 1: (np.float32, 4), 2: (np.float32, 3), 3: (np.float32, 4), 4: (np.float32, 4),
+              5: (np.float32, 1), 6: (np.float32, 4), 7: (np.float32, 4), 8: (np.uint32, 2), 9: (np.uint32, 2)}
+
+
+BVH_BUILD_PREFER_FAST_TRACE = 0x4
+BVH_BUILD_PREFER_FAST_BUILD = 0x8
+
+_lib = None
+
+
+def lib_path():
+    return os.path.join(_HERE, "lib", "libtracerboy_b200.so")
+
+
+def load_library():
+    """Load the CUDA library. Fails loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise TracerBoyError(-5, "CUDA library %s is missing; run `python -m tracerboy_b200.build`" % p)
+    lib = C.CDLL(p)
+    lib.tb_last_error.restype = C.c_char_p
+    lib.tb_last_error.argtypes = [C.c_void_p]
+    lib.tb_version.restype = C.c_char_p
+    lib.tb_destroy.restype = None
+    lib.tb_destroy.argtypes = [C.c_void_p]
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    sig = {
+        "tb_create": [i32, C.POINTER(vp)], "tb_load_scene": [vp, C.c_char_p], "tb_load_scene_ex": [vp, C.c_char_p, u32],
+        "tb_get_load_status": [vp, C.POINTER(LoadStatus)], "tb_save_scene": [vp, C.c_char_p],
+        "tb_convert_scene": [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t],
+        "tb_get_scene_info": [vp, C.POINTER(SceneInfo)], "tb_get_bvh_size": [vp, C.POINTER(u64)],
+        "tb_get_bvh": [vp, vp, u64], "tb_get_bvh_build_ms": [vp, C.POINTER(C.c_double)],
+        "tb_get_default_settings": [C.POINTER(OutputSettings)], "tb_get_camera": [vp, C.POINTER(Camera)],
+        "tb_set_camera": [vp, C.POINTER(Camera)], "tb_resize": [vp, u32, u32], "tb_select_pixel": [vp, i32, i32],
+        "tb_get_stats": [vp, C.POINTER(ReadbackStats)],
+        "tb_render": [vp, C.POINTER(OutputSettings), u32, C.c_float], "tb_samples_rendered": [vp, C.POINTER(u32)],
+        "tb_invalidate_history": [vp], "tb_set_frame_shard": [vp, u32, u32], "tb_buffer_size": [vp, u32, C.POINTER(u64)],
+        "tb_readback": [vp, u32, vp, u64], "tb_device_buffer": [vp, u32, C.POINTER(vp), C.POINTER(u64)],
+        "tb_get_render_stats": [vp, C.POINTER(RenderStats)], "tb_reset_render_stats": [vp], "tb_synchronize": [vp],
+        "tb_is_material_id_valid": [vp, i32], "tb_get_material": [vp, i32, C.POINTER(Material), C.c_char_p, u32],
+        "tb_set_material": [vp, i32, C.POINTER(Material)],
+        "tb_bvh_prebuild_info": [C.POINTER(GeometryDesc), u32, C.POINTER(PrebuildInfo)],
+        "tb_bvh_build": [vp, C.POINTER(GeometryDesc), u32, u32], "tb_trace_rays": [vp, vp, u64, vp],
+    }
+    for name, args in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = ["tb_create", "tb_destroy", "tb_last_error", "tb_version", "tb_load_scene", "tb_load_scene_ex",
+                    "tb_get_load_status", "tb_save_scene", "tb_convert_scene", "tb_get_scene_info", "tb_get_bvh_size",
+                    "tb_get_bvh", "tb_get_bvh_build_ms", "tb_get_default_settings", "tb_get_camera", "tb_set_camera",
+                    "tb_resize", "tb_select_pixel", "tb_get_stats", "tb_render", "tb_samples_rendered",
+                    "tb_invalidate_history", "tb_set_frame_shard", "tb_buffer_size", "tb_readback", "tb_device_buffer",
+                    "tb_get_render_stats", "tb_reset_render_stats", "tb_synchronize", "tb_is_material_id_valid",
+                    "tb_get_material", "tb_set_material", "tb_bvh_prebuild_info", "tb_bvh_build", "tb_trace_rays"]
+
+
+def get_default_output_settings():
+    """TracerBoy::GetDefaultOutputSettings (TracerBoy.h:290-360)."""
+    s = OutputSettings()
+    load_library().tb_get_default_settings(C.byref(s))
+    return s
+
+
+def convert_scene(src, dst):
+    """Host-only: import a scene (.pbrt/.pbf/.tbscene/synthetic:) and write the .tbscene cache."""
+    err = C.create_string_buffer(1024)
+    rc = load_library().tb_convert_scene(src.encode(), dst.encode(), err, 1024)
+    if rc != 0:
+        raise TracerBoyError(rc, err.value.decode())
+
+
+class TracerBoy:
+    """Mirror of `class TracerBoy`: ctor / LoadScene / Render / readback / materials."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        rc = self._lib.tb_create(int(device), C.byref(h))
+        if rc != 0:
+            raise TracerBoyError(rc, self._lib.tb_last_error(None).decode())
+        self._h = h
+        self.width = self.height = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TracerBoyError(rc, self._lib.tb_last_error(self._h).decode())
+
+    # --- scene -----------------------------------------------------------
+    def LoadScene(self, path, bvh_build_flags=BVH_BUILD_PREFER_FAST_TRACE):
+        self._ck(self._lib.tb_load_scene_ex(self._h, path.encode(), bvh_build_flags))
+
+    def SaveScene(self, path):
+        self._ck(self._lib.tb_save_scene(self._h, path.encode()))
+
+    def GetSceneLoadStatus(self):
+        s = LoadStatus()
+        self._ck(self._lib.tb_get_load_status(self._h, C.byref(s)))
+        return s
+
+    def GetSceneInfo(self):
+        s = SceneInfo()
+        self._ck(self._lib.tb_get_scene_info(self._h, C.byref(s)))
+        return s
+
+    def GetBVH(self):
+        n = C.c_uint64()
+        self._ck(self._lib.tb_get_bvh_size(self._h, C.byref(n)))
+        buf = np.empty(n.value, np.uint8)
+        self._ck(self._lib.tb_get_bvh(self._h, buf.ctypes.data, n.value))
+        return buf
+
+    def GetBVHBuildMilliseconds(self):
+        ms = C.c_double()
+        self._ck(self._lib.tb_get_bvh_build_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def BuildRaytracingAccelerationStructure(self, geometries, flags=BVH_BUILD_PREFER_FAST_TRACE):
+        """geometries: list of (positions float32 [V,3], indices uint32/uint16 [T*3] or None)."""
+        descs = (GeometryDesc * len(geometries))()
+        keep = []
+        for i, (pos, idx) in enumerate(geometries):
+            pos = np.ascontiguousarray(pos, np.float32)
+            keep.append(pos)
+            descs[i].Positions = pos.ctypes.data
+            descs[i].PositionStrideBytes = 12
+            descs[i].VertexCount = pos.shape[0]
+            descs[i].GeometryFlags = 1
+            if idx is None:
+                descs[i].Indices = None
+                descs[i].IndexFormat = 0
+                descs[i].IndexCount = 0
+            else:
+                idx = np.ascontiguousarray(idx)
+                if idx.dtype not in (np.uint16, np.uint32):
+                    idx = idx.astype(np.uint32)
+                keep.append(idx)
+                descs[i].Indices = idx.ctypes.data
+                descs[i].IndexFormat = idx.dtype.itemsize
+                descs[i].IndexCount = idx.size
+        self._ck(self._lib.tb_bvh_build(self._h, descs, len(geometries), flags))
+
+    def TraceRays(self, rays):
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.empty(rays.shape[0], HIT_DTYPE)
+        self._ck(self._lib.tb_trace_rays(self._h, rays.ctypes.data, rays.shape[0], hits.ctypes.data))
+        return hits
+
+    # --- camera / settings ----------------------------------------------
+    @staticmethod
+    def GetDefaultOutputSettings():
+        return get_default_output_settings()
+
+    def GetCamera(self):
+        c = Camera()
+        self._ck(self._lib.tb_get_camera(self._h, C.byref(c)))
+        return c
+
+    def SetCamera(self, cam):
+        self._ck(self._lib.tb_set_camera(self._h, C.byref(cam)))
+
+    def Resize(self, width, height):
+        self._ck(self._lib.tb_resize(self._h, width, height))
+        self.width, self.height = width, height
+
+    def SelectPixel(self, x, y):
+        self._ck(self._lib.tb_select_pixel(self._h, x, y))
+
+    def GetReadbackStats(self):
+        s = ReadbackStats()
+        self._ck(self._lib.tb_get_stats(self._h, C.byref(s)))
+        return s
+
+    # --- render ----------------------------------------------------------
+    def Render(self, settings=None, samples=1, time=0.0):
+        """`samples` x the reference's one-sample Render (TracerBoy.cpp:2677-3369)."""
+        if settings is None:
+            settings = get_default_output_settings()
+        self._ck(self._lib.tb_render(self._h, C.byref(settings), int(samples), C.c_float(time)))
+
+    def GetNumberOfSamplesSinceLastInvalidate(self):
+        n = C.c_uint32()
+        self._ck(self._lib.tb_samples_rendered(self._h, C.byref(n)))
+        return n.value
+
+    def InvalidateHistory(self):
+        self._ck(self._lib.tb_invalidate_history(self._h))
+
+    def SetFrameShard(self, offset, stride):
+        self._ck(self._lib.tb_set_frame_shard(self._h, offset, stride))
+
+    def Readback(self, kind, out=None):
+        dt, ch = BufferKind._shape[kind]
+        shape = (self.height, self.width, ch) if ch > 1 else (self.height, self.width)
+        if out is None:
+            out = np.empty(shape, dt)
+        self._ck(self._lib.tb_readback(self._h, kind, out.ctypes.data, out.nbytes))
+        return out
+
+    def DeviceBuffer(self, kind):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self._lib.tb_device_buffer(self._h, kind, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def GetRenderStats(self):
+        s = RenderStats()
+        self._ck(self._lib.tb_get_render_stats(self._h, C.byref(s)))
+        return s
+
+    def ResetRenderStats(self):
+        self._ck(self._lib.tb_reset_render_stats(self._h))
+
+    def Synchronize(self):
+        self._ck(self._lib.tb_synchronize(self._h))
+
+    # --- materials -------------------------------------------------------
+    def IsMaterialIDValid(self, i):
+        return bool(self._lib.tb_is_material_id_valid(self._h, i))
+
+    def GetMaterial(self, i):
+        m = Material()
+        name = C.create_string_buffer(64)
+        self._ck(self._lib.tb_get_material(self._h, i, C.byref(m), name, 64))
+        return m, name.value.decode()
+
+    def SetMaterial(self, i, m):
+        self._ck(self._lib.tb_set_material(self._h, i, C.byref(m)))

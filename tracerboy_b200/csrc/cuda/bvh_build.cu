@@ -1,0 +1,536 @@
+// bvh_build.cu — GPU LBVH builder for sm_100a.
+//
+// Role: the D3D12 Raytracing Fallback Layer's GpuBvh2Builder::BuildBVH
+// (D3D12RaytracingFallback/src/GpuBVH2Builder.cpp:167-356) and the ~20 HLSL kernels it
+// dispatches. Output is byte-identical to the reference layout
+// (RayTracingHlslCompat.h:344-398) for a deterministic child-order rule; a second,
+// traversal-friendly copy (PairNode/WideTri, device_types.h) is derived from it.
+//
+// Pipeline (one stream, no host sync inside):
+//   load_prims      BottomLevelLoadTriangles.hlsli:88-126 + scene AABB (CalculateSceneAABB*.hlsl)
+//   morton          CalculateMortonCodesBindings.h:117-162 (30 bit, y,x,z interleave)
+//   radix sort      replaces the O(N log^2 N) bitonic sort (BitonicSort.cpp:67-143); a stable
+//                   LSD radix sort of (code, index) gives the same order as the reference's
+//                   tie-break-by-index compare (BitonicSortCommon.hlsli:37-47)
+//   rearrange       RearrangeTriangles.hlsl:29-36
+//   karras          BuildBVHSplits.hlsli:34-141
+//   treelet x3      ClearBuffers.hlsl / FindTreelets.hlsl / TreeletReorder.hlsl (1 warp / treelet)
+//   refit           ComputeAABBs.hlsli:69-172 (centre/half boxes, smaller subtree left)
+//   widen           reference nodes -> PairNode/WideTri
+//
+// Determinism: every cross-thread hand-off is "second arrival continues and recomputes
+// from both children", so arrival order never selects data. Two documented deviations
+// from the reference, shared with the oracle: equal-size siblings keep Karras order
+// (swap iff leftCount > rightCount), and treelet climbing is not capped at 33 levels.
+#include <cfloat>
+#include <cstdio>
+#include <cub/device/device_radix_sort.cuh>
+#include "../common/tb_vec.h"
+#include "device_types.h"
+#include "launch.h"
+
+using namespace tbm;
+
+namespace tbd {
+
+namespace {
+
+struct Prim { uint32_t type; float v[9]; };
+struct Meta { uint32_t geom, prim, flags; };
+struct Box { f3 mn, mx; };
+
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// ---------------------------------------------------------------- load + AABB
+__global__ void k_load_prims(const TbGeometryRecord* __restrict__ geoms, const uint32_t* __restrict__ triPrefix,
+                             uint32_t numGeoms, const float* __restrict__ positions,
+                             const uint32_t* __restrict__ indices, uint32_t n, Prim* __restrict__ prims,
+                             Meta* __restrict__ meta, uint32_t* __restrict__ sceneBox /*6 ordered uints*/) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    f3 mn = mk3(FLT_MAX), mx = mk3(-FLT_MAX);
+    if (i < n) {
+        // geometry lookup: last g with triPrefix[g] <= i
+        uint32_t lo = 0, hi = numGeoms;
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (triPrefix[mid] <= i) lo = mid; else hi = mid; }
+        TbGeometryRecord G = geoms[lo];
+        uint32_t t = i - triPrefix[lo];
+        Prim p;
+        p.type = 1;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            uint32_t vi = G.VertexFirst + indices[G.IndexFirst + 3 * t + k];
+            float x = positions[3 * (size_t)vi], y = positions[3 * (size_t)vi + 1], z = positions[3 * (size_t)vi + 2];
+            p.v[3 * k] = x; p.v[3 * k + 1] = y; p.v[3 * k + 2] = z;
+            mn = min3(mn, mk3(x, y, z));
+            mx = max3(mx, mk3(x, y, z));
+        }
+        uint32_t* dst = (uint32_t*)(prims + i);
+        const uint32_t* src = (const uint32_t*)&p;
+#pragma unroll
+        for (int k = 0; k < 10; k++) dst[k] = src[k];
+        Meta m = {lo, t, G.GeometryFlags};
+        meta[i] = m;
+    }
+    // warp reduce then 6 atomics per warp (min/max are order independent => deterministic)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn.x = fminf(mn.x, __shfl_xor_sync(0xffffffffu, mn.x, o)); mn.y = fminf(mn.y, __shfl_xor_sync(0xffffffffu, mn.y, o)); mn.z = fminf(mn.z, __shfl_xor_sync(0xffffffffu, mn.z, o));
+        mx.x = fmaxf(mx.x, __shfl_xor_sync(0xffffffffu, mx.x, o)); mx.y = fmaxf(mx.y, __shfl_xor_sync(0xffffffffu, mx.y, o)); mx.z = fmaxf(mx.z, __shfl_xor_sync(0xffffffffu, mx.z, o));
+    }
+    if ((threadIdx.x & 31) == 0 && mn.x <= mx.x) {
+        atomicMin(&sceneBox[0], float_to_ordered(mn.x)); atomicMin(&sceneBox[1], float_to_ordered(mn.y)); atomicMin(&sceneBox[2], float_to_ordered(mn.z));
+        atomicMax(&sceneBox[3], float_to_ordered(mx.x)); atomicMax(&sceneBox[4], float_to_ordered(mx.y)); atomicMax(&sceneBox[5], float_to_ordered(mx.z));
+    }
+}
+
+__global__ void k_morton(const Prim* __restrict__ prims, uint32_t n, const uint32_t* __restrict__ sceneBox,
+                         uint32_t* __restrict__ codes, uint32_t* __restrict__ order) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f3 smin = mk3(ordered_to_float(sceneBox[0]), ordered_to_float(sceneBox[1]), ordered_to_float(sceneBox[2]));
+    f3 smax = mk3(ordered_to_float(sceneBox[3]), ordered_to_float(sceneBox[4]), ordered_to_float(sceneBox[5]));
+    const float* v = prims[i].v;
+    f3 c = ((mk3(v[0], v[1], v[2]) + mk3(v[3], v[4], v[5])) + mk3(v[6], v[7], v[8])) / 3.0f;
+    f3 dim = max3(smax - smin, mk3(0.00001f));
+    f3 unit = (c - smin) / dim;
+    f3 adj = min3(max3(unit * 1024.0f, mk3(0.0f)), mk3(1023.0f));
+    uint32_t coords[3] = {(uint32_t)adj.y, (uint32_t)adj.x, (uint32_t)adj.z};
+    uint32_t code = 0;
+#pragma unroll
+    for (uint32_t bit = 0; bit < 10; bit++)
+#pragma unroll
+        for (uint32_t axis = 0; axis < 3; axis++)
+            if ((1u << bit) & coords[axis]) code |= 1u << (bit * 3 + axis);
+    codes[i] = code;
+    order[i] = i;
+}
+
+__global__ void k_rearrange(const Prim* __restrict__ prims, const Meta* __restrict__ meta,
+                            const uint32_t* __restrict__ order, uint32_t n, Prim* __restrict__ outPrims,
+                            Meta* __restrict__ outMeta) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s = order[i];
+    const uint32_t* src = (const uint32_t*)(prims + s);
+    uint32_t* dst = (uint32_t*)(outPrims + i);
+#pragma unroll
+    for (int k = 0; k < 10; k++) dst[k] = src[k];
+    outMeta[i] = meta[s];
+}
+
+// ------------------------------------------------------------------- Karras
+__device__ __forceinline__ int lcp(const uint32_t* __restrict__ codes, uint32_t n, uint32_t a, uint32_t b) {
+    if (a >= n || b >= n) return -1;
+    uint32_t ca = codes[a], cb = codes[b];
+    if (ca != cb) return __clz(ca ^ cb);
+    return __clz(a ^ b) + 31;
+}
+__global__ void k_karras(const uint32_t* __restrict__ codes, uint32_t n, HNode* __restrict__ H) {
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n - 1) return;
+    int d = lcp(codes, n, idx, idx + 1) - lcp(codes, n, idx, idx - 1);
+    d = d < -1 ? -1 : (d > 1 ? 1 : d);
+    int minPrefix = lcp(codes, n, idx, idx - d);
+    int maxLength = 2;
+    while (lcp(codes, n, idx, idx + (uint32_t)(maxLength * d)) > minPrefix) maxLength *= 4;
+    int length = 0;
+    for (int t = maxLength / 2; t > 0; t /= 2)
+        if (lcp(codes, n, idx, idx + (uint32_t)((length + t) * d)) > minPrefix) length += t;
+    uint32_t j = idx + (uint32_t)(length * d);
+    uint32_t first = min(idx, j), last = max(idx, j);
+    int common = lcp(codes, n, first, last);
+    int sp = (int)first, step = (int)(last - first);
+    do {
+        step = (step + 1) >> 1;
+        int ns = sp + step;
+        if ((uint32_t)ns < last && lcp(codes, n, first, (uint32_t)ns) > common) sp = ns;
+    } while (step > 1);
+    uint32_t split = (uint32_t)sp, nInternal = n - 1;
+    uint32_t a = (split == first) ? nInternal + split : split;
+    uint32_t b = (split + 1 == last) ? nInternal + split + 1 : split + 1;
+    H[idx].left = a;
+    H[idx].right = b;
+    H[a].parent = idx;
+    H[b].parent = idx;
+    if (idx == 0) H[0].parent = 0xffffffffu;
+}
+
+// ------------------------------------------------------------------ treelets
+__device__ __forceinline__ float surface_area(const Box& b) {
+    f3 d = b.mx - b.mn;
+    return 2.0f * ((d.x * d.y + d.x * d.z) + d.y * d.z);
+}
+__device__ __forceinline__ Box combine(const Box& a, const Box& b) { Box r; r.mn = min3(a.mn, b.mn); r.mx = max3(a.mx, b.mx); return r; }
+__device__ __forceinline__ void leaf_box(const Prim* prims, uint32_t i, f3& c, f3& h) {
+    const float* v = prims[i].v;
+    f3 v0 = mk3(v[0], v[1], v[2]), v1 = mk3(v[3], v[4], v[5]), v2 = mk3(v[6], v[7], v[8]);
+    f3 mn = min3(min3(v0, v1), v2), mx = max3(max3(v0, v1), v2);
+    mn = min3(mn, mx - 0.001f);
+    c = (mn + mx) * 0.5f;
+    h = mx - c;
+}
+// L2-coherent accessors for data handed between thread blocks (L1 is not coherent)
+__device__ __forceinline__ Box ld_box(const float* aabb, uint32_t i) {
+    const float* p = aabb + 6 * (size_t)i;
+    Box b;
+    b.mn = mk3(__ldcg(p), __ldcg(p + 1), __ldcg(p + 2));
+    b.mx = mk3(__ldcg(p + 3), __ldcg(p + 4), __ldcg(p + 5));
+    return b;
+}
+__device__ __forceinline__ void st_box(float* aabb, uint32_t i, const Box& b) {
+    float* p = aabb + 6 * (size_t)i;
+    __stcg(p, b.mn.x); __stcg(p + 1, b.mn.y); __stcg(p + 2, b.mn.z);
+    __stcg(p + 3, b.mx.x); __stcg(p + 4, b.mx.y); __stcg(p + 5, b.mx.z);
+}
+__device__ __forceinline__ uint32_t ld_u(const uint32_t* p) { return __ldcg(p); }
+
+__global__ void k_treelet_clear(uint32_t* numTris, uint32_t nInternal, uint32_t* baseCount) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *baseCount = 0;
+    if (i < nInternal) numTris[i] = 0;
+}
+
+// FindTreelets.hlsl:31-88
+__global__ void k_find_treelets(const Prim* __restrict__ prims, uint32_t n, uint32_t minTris, HNode* H, float* aabb,
+                                uint32_t* numTris, uint32_t* baseCount, uint32_t* baseRoots) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n) return;
+    const uint32_t nInternal = n - 1, total = 2 * n - 1;
+    uint32_t node = total - tid - 1;
+    uint32_t count = 1;
+    bool isLeaf = true;
+    while (true) {
+        Box b;
+        if (isLeaf) {
+            f3 c, h;
+            leaf_box(prims, node - nInternal, c, h);
+            b.mn = c - h; b.mx = c + h;
+        } else {
+            b = combine(ld_box(aabb, ld_u(&H[node].left)), ld_box(aabb, ld_u(&H[node].right)));
+        }
+        st_box(aabb, node, b);
+        __threadfence();
+        if (count >= minTris) {
+            uint32_t slot = atomicAdd(baseCount, 1u);
+            baseRoots[slot] = node;
+            return;
+        }
+        uint32_t parent = ld_u(&H[node].parent);
+        uint32_t other = atomicAdd(&numTris[parent], count);
+        if (other == 0) return;
+        __threadfence();
+        node = parent;
+        count += other;
+        isLeaf = false;
+    }
+}
+
+// masks 1..127 ordered by popcount (2..7 used), built at compile time into constant memory
+__constant__ uint8_t c_masksBySize[128];
+__constant__ uint8_t c_sizeStart[9];
+
+// TreeletReorder.hlsl:38-312 — one warp per base treelet root, climbing to the BVH root.
+__global__ void __launch_bounds__(128) k_treelet_reorder(uint32_t n, HNode* H, float* aabb, uint32_t* numTris,
+                                                         const uint32_t* baseCount, const uint32_t* baseRoots) {
+    const uint32_t warpsPerBlock = blockDim.x / 32;
+    const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x & 31;
+    const uint32_t nInternal = n - 1;
+    __shared__ float s_cost[4][128];
+    __shared__ uint8_t s_part[4][128];
+    __shared__ float s_box[4][7][6];
+    float* cost = s_cost[warp];
+    uint8_t* part = s_part[warp];
+    const uint32_t numRoots = *baseCount;
+    for (uint32_t w = blockIdx.x * warpsPerBlock + warp; w < numRoots; w += gridDim.x * warpsPerBlock) {
+        uint32_t root = baseRoots[w];
+        while (true) {
+            // ---- FormTreelet: lanes 0..6 hold the treelet leaves, lanes 0..5 the internal nodes
+            uint32_t leaf = 0xffffffffu, internal = 0xffffffffu;
+            if (lane == 0) { leaf = ld_u(&H[root].left); internal = root; }
+            if (lane == 1) leaf = ld_u(&H[root].right);
+            for (uint32_t size = 2; size < 7; size++) {
+                float sa = 0.0f;
+                if (lane < size && leaf < nInternal) sa = surface_area(ld_box(aabb, leaf));
+                // argmax, first index wins on ties, must be strictly > 0
+                float best = sa; uint32_t bestLane = lane;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) { // lanes 0..7 are enough
+                    float os = __shfl_xor_sync(0xffffffffu, best, o);
+                    uint32_t ol = __shfl_xor_sync(0xffffffffu, bestLane, o);
+                    if (os > best || (os == best && ol < bestLane)) { best = os; bestLane = ol; }
+                }
+                bestLane = __shfl_sync(0xffffffffu, bestLane, 0);
+                uint32_t pick = __shfl_sync(0xffffffffu, leaf, bestLane);
+                uint32_t pl = ld_u(&H[pick].left), pr = ld_u(&H[pick].right);
+                if (lane == bestLane) leaf = pl;
+                if (lane == size) leaf = pr;
+                if (lane == size - 1) internal = pick;
+            }
+            // lane (size-1) collected internals for size=2..6 -> lanes 1..5; lane 0 has root
+            Box lb;
+            if (lane < 7) {
+                lb = ld_box(aabb, leaf);
+                float* sb = s_box[warp][lane];
+                sb[0] = lb.mn.x; sb[1] = lb.mn.y; sb[2] = lb.mn.z; sb[3] = lb.mx.x; sb[4] = lb.mx.y; sb[5] = lb.mx.z;
+            }
+            __syncwarp();
+            // ---- FindOptimalPartitions
+            Box rb = ld_box(aabb, root);
+            float rootSA = surface_area(rb);
+            for (uint32_t mask = lane * 4; mask < lane * 4 + 4; mask++) {
+                if (mask == 0) { cost[0] = 0.0f; continue; }
+                Box b; b.mn = mk3(FLT_MAX); b.mx = mk3(-FLT_MAX);
+#pragma unroll
+                for (uint32_t i = 0; i < 7; i++)
+                    if ((1u << i) & mask) {
+                        const float* sb = s_box[warp][i];
+                        Box t; t.mn = mk3(sb[0], sb[1], sb[2]); t.mx = mk3(sb[3], sb[4], sb[5]);
+                        b = combine(b, t);
+                    }
+                cost[mask] = surface_area(b);
+            }
+            __syncwarp();
+            if (lane < 7) cost[1u << lane] = 1.0f * surface_area(lb) / rootSA;
+            __syncwarp();
+            for (uint32_t s = 2; s <= 7; s++) {
+                for (uint32_t k = c_sizeStart[s] + lane; k < c_sizeStart[s + 1]; k += 32) {
+                    uint32_t mask = c_masksBySize[k];
+                    float lowest = FLT_MAX;
+                    uint32_t bestP = 0;
+                    uint32_t delta = (mask - 1) & mask;
+                    uint32_t p = (0u - delta) & mask;
+                    do {
+                        float c = cost[p] + cost[mask ^ p];
+                        if (c < lowest) { lowest = c; bestP = p; }
+                        p = (p - delta) & mask;
+                    } while (p != 0);
+                    cost[mask] = 1.0f * cost[mask] + lowest;
+                    part[mask] = (uint8_t)bestP;
+                }
+                __syncwarp();
+            }
+            // ---- ReformTree (lane 0), with leaves / internals gathered by shuffles
+            uint32_t leaves[7], internals[6];
+#pragma unroll
+            for (int i = 0; i < 7; i++) leaves[i] = __shfl_sync(0xffffffffu, leaf, i);
+#pragma unroll
+            for (int i = 0; i < 6; i++) internals[i] = __shfl_sync(0xffffffffu, internal, i);
+            bool finished = false;
+            if (lane == 0) {
+                uint32_t stackMask[7], stackNode[7];
+                uint32_t allocated = 1, sp = 1;
+                stackMask[0] = 127u; stackNode[0] = internals[0];
+                while (sp > 0) {
+                    --sp;
+                    uint32_t em = stackMask[sp], en = stackNode[sp];
+                    uint32_t lm = part[em], ln, rm, rn;
+                    if (__popc(lm) > 1) { ln = internals[allocated++]; stackMask[sp] = lm; stackNode[sp] = ln; sp++; }
+                    else ln = leaves[__ffs(lm) - 1];
+                    rm = em ^ lm;
+                    if (__popc(rm) > 1) { rn = internals[allocated++]; stackMask[sp] = rm; stackNode[sp] = rn; sp++; }
+                    else rn = leaves[__ffs(rm) - 1];
+                    __stcg(&H[en].left, ln);
+                    __stcg(&H[en].right, rn);
+                    __stcg(&H[ln].parent, en);
+                    __stcg(&H[rn].parent, en);
+                }
+                for (int j = 5; j >= 0; j--) {
+                    uint32_t in = internals[j];
+                    Box b = combine(ld_box(aabb, ld_u(&H[in].left)), ld_box(aabb, ld_u(&H[in].right)));
+                    st_box(aabb, in, b);
+                }
+                // ---- TraverseToParent
+                if (root == 0) finished = true;
+                else {
+                    uint32_t parent = ld_u(&H[root].parent);
+                    uint32_t mine = ld_u(&numTris[root]);
+                    __threadfence();
+                    uint32_t other = atomicAdd(&numTris[parent], mine);
+                    if (other == 0) finished = true;
+                    else {
+                        __threadfence();
+                        Box b = combine(ld_box(aabb, ld_u(&H[parent].left)), ld_box(aabb, ld_u(&H[parent].right)));
+                        st_box(aabb, parent, b);
+                        root = parent;
+                    }
+                }
+            }
+            finished = __shfl_sync(0xffffffffu, (int)finished, 0);
+            root = __shfl_sync(0xffffffffu, root, 0);
+            __syncwarp();
+            if (finished) break;
+        }
+    }
+}
+
+// --------------------------------------------------------------------- refit
+// ComputeAABBs.hlsli:69-172 (+ PrepareForComputeAABBs header)
+__global__ void k_refit(uint32_t n, const HNode* H, uint8_t* bvh, uint32_t* counter) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n) return;
+    const uint32_t nInternal = n - 1, total = 2 * n - 1;
+    const uint32_t offPrims = 16 + 32 * total;
+    if (tid == 0) {
+        uint32_t* hd = (uint32_t*)bvh;
+        hd[0] = 16; hd[1] = offPrims; hd[2] = offPrims + 40 * n; hd[3] = offPrims + 40 * n + 12 * n;
+    }
+    float* nodes = (float*)(bvh + 16);
+    const Prim* prims = (const Prim*)(bvh + offPrims);
+    uint32_t node = total - tid - 1;
+    uint32_t count = 1;
+    {
+        f3 c, h;
+        leaf_box(prims, node - nInternal, c, h);
+        float* nd = nodes + 8 * (size_t)node;
+        __stcg(nd, c.x); __stcg(nd + 1, c.y); __stcg(nd + 2, c.z); __stcg((uint32_t*)nd + 3, (node - nInternal) | 0x80000000u);
+        __stcg(nd + 4, h.x); __stcg(nd + 5, h.y); __stcg(nd + 6, h.z); __stcg((uint32_t*)nd + 7, 1u);
+    }
+    while (node != 0) {
+        uint32_t parent = ld_u(&H[node].parent);
+        __threadfence();
+        uint32_t other = atomicAdd(&counter[parent], count);
+        if (other == 0) return;
+        __threadfence();
+        uint32_t l = ld_u(&H[parent].left), r = ld_u(&H[parent].right);
+        uint32_t lc = (l == node) ? count : other, rc = (l == node) ? other : count;
+        if (lc > rc) { uint32_t t = l; l = r; r = t; } // smaller subtree left; ties keep Karras order
+        const float* A = nodes + 8 * (size_t)l;
+        const float* B = nodes + 8 * (size_t)r;
+        f3 ac = mk3(__ldcg(A), __ldcg(A + 1), __ldcg(A + 2)), ah = mk3(__ldcg(A + 4), __ldcg(A + 5), __ldcg(A + 6));
+        f3 bc = mk3(__ldcg(B), __ldcg(B + 1), __ldcg(B + 2)), bh = mk3(__ldcg(B + 4), __ldcg(B + 5), __ldcg(B + 6));
+        f3 mn = min3(ac - ah, bc - bh), mx = max3(ac + ah, bc + bh);
+        f3 c = (mn + mx) * 0.5f;
+        f3 h = mx - c;
+        float* nd = nodes + 8 * (size_t)parent;
+        __stcg(nd, c.x); __stcg(nd + 1, c.y); __stcg(nd + 2, c.z); __stcg((uint32_t*)nd + 3, l & 0x3fffffffu);
+        __stcg(nd + 4, h.x); __stcg(nd + 5, h.y); __stcg(nd + 6, h.z); __stcg((uint32_t*)nd + 7, r);
+        node = parent;
+        count += other;
+    }
+}
+
+// ---------------------------------------------------------------------- widen
+__global__ void k_widen(uint32_t n, const uint8_t* __restrict__ bvh, PairNode* __restrict__ pairs, WideTri* __restrict__ tris) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nInternal = n - 1, total = 2 * n - 1;
+    const RefNode* nodes = (const RefNode*)(bvh + 16);
+    if (i < nInternal) {
+        RefNode nd = nodes[i];
+        uint32_t l = nd.flags & 0x3fffffffu, r = nd.right;
+        RefNode L = nodes[l], R = nodes[r];
+        uint32_t lref = (L.flags & 0x80000000u) ? (0x80000000u | (L.flags & 0x3fffffffu)) : l;
+        uint32_t rref = (R.flags & 0x80000000u) ? (0x80000000u | (R.flags & 0x3fffffffu)) : r;
+        PairNode p;
+        p.lc = make_float4(L.c[0], L.c[1], L.c[2], __uint_as_float(lref));
+        p.lh = make_float4(L.h[0], L.h[1], L.h[2], __uint_as_float(rref));
+        p.rc = make_float4(R.c[0], R.c[1], R.c[2], 0.0f);
+        p.rh = make_float4(R.h[0], R.h[1], R.h[2], 0.0f);
+        pairs[i] = p;
+    }
+    if (i < n) {
+        const Prim* prims = (const Prim*)(bvh + 16 + 32 * (size_t)total);
+        const Meta* meta = (const Meta*)(bvh + 16 + 32 * (size_t)total + 40 * (size_t)n);
+        const float* v = prims[i].v;
+        Meta m = meta[i];
+        WideTri t;
+        t.v0 = make_float4(v[0], v[1], v[2], __uint_as_float(m.geom));
+        t.v1 = make_float4(v[3], v[4], v[5], __uint_as_float(m.prim));
+        t.v2 = make_float4(v[6], v[7], v[8], 0.0f);
+        tris[i] = t;
+    }
+}
+
+void init_mask_tables() {
+    static bool done = false;
+    if (done) return;
+    uint8_t masks[128] = {0}, start[9] = {0};
+    uint32_t k = 0;
+    for (uint32_t s = 0; s <= 7; s++) {
+        start[s] = (uint8_t)k;
+        for (uint32_t m = 0; m < 128; m++)
+            if ((uint32_t)__builtin_popcount(m) == s) masks[k++] = (uint8_t)m;
+    }
+    start[8] = (uint8_t)k;
+    cudaMemcpyToSymbol(c_masksBySize, masks, sizeof(masks));
+    cudaMemcpyToSymbol(c_sizeStart, start, sizeof(start));
+    done = true;
+}
+
+} // namespace
+
+uint64_t bvh_ref_bytes(uint32_t n) { return 16ull + 32ull * (2ull * n - 1) + 40ull * n + 12ull * n; }
+
+// Builds dst (reference layout) + wide layout. All temporaries are allocated and freed
+// here (cudaMallocAsync on the stream); returns cudaSuccess or the first error.
+cudaError_t build_bvh(const TbGeometryRecord* d_geoms, const uint32_t* d_triPrefix, uint32_t numGeoms,
+                      const float* d_positions, const uint32_t* d_indices, uint32_t n, int treeletPasses,
+                      DeviceBvh& out, cudaStream_t stream, LaunchCounter& lc) {
+    init_mask_tables();
+    const uint32_t total = 2 * n - 1, nInternal = n - 1;
+    const uint32_t T = 256;
+    auto grid = [&](uint32_t c) { return (c + T - 1) / T; };
+    cudaError_t err;
+#define CK(x) do { err = (x); if (err != cudaSuccess) return err; } while (0)
+    Prim* prims; Meta* meta; uint32_t *codes, *order, *codesAlt, *orderAlt, *sceneBox, *numTris, *baseCount, *baseRoots;
+    HNode* H; float* aabb; void* cubTemp = nullptr; size_t cubBytes = 0;
+    CK(cudaMallocAsync(&prims, sizeof(Prim) * (size_t)n, stream));
+    CK(cudaMallocAsync(&meta, sizeof(Meta) * (size_t)n, stream));
+    CK(cudaMallocAsync(&codes, 4 * (size_t)n, stream));
+    CK(cudaMallocAsync(&order, 4 * (size_t)n, stream));
+    CK(cudaMallocAsync(&codesAlt, 4 * (size_t)n, stream));
+    CK(cudaMallocAsync(&orderAlt, 4 * (size_t)n, stream));
+    CK(cudaMallocAsync(&sceneBox, 6 * 4, stream));
+    CK(cudaMallocAsync(&numTris, 4 * (size_t)(nInternal + 1), stream));
+    CK(cudaMallocAsync(&baseCount, 4, stream));
+    CK(cudaMallocAsync(&baseRoots, 4 * (size_t)(n / 7 + 1), stream));
+    CK(cudaMallocAsync(&H, sizeof(HNode) * (size_t)total, stream));
+    CK(cudaMallocAsync(&aabb, 24 * (size_t)total, stream));
+    cub::DoubleBuffer<uint32_t> dk(codes, codesAlt), dv(order, orderAlt);
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, cubBytes, dk, dv, (int)n, 0, 30, stream));
+    CK(cudaMallocAsync(&cubTemp, cubBytes, stream));
+
+    uint32_t boxInit[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    CK(cudaMemcpyAsync(sceneBox, boxInit, sizeof(boxInit), cudaMemcpyHostToDevice, stream));
+    k_load_prims<<<grid(n), T, 0, stream>>>(d_geoms, d_triPrefix, numGeoms, d_positions, d_indices, n, prims, meta, sceneBox); lc.count++;
+    k_morton<<<grid(n), T, 0, stream>>>(prims, n, sceneBox, codes, order); lc.count++;
+    CK(cub::DeviceRadixSort::SortPairs(cubTemp, cubBytes, dk, dv, (int)n, 0, 30, stream));
+    uint8_t* bvh = out.ref;
+    Prim* sortedPrims = (Prim*)(bvh + 16 + 32 * (size_t)total);
+    Meta* sortedMeta = (Meta*)(bvh + 16 + 32 * (size_t)total + 40 * (size_t)n);
+    k_rearrange<<<grid(n), T, 0, stream>>>(prims, meta, dv.Current(), n, sortedPrims, sortedMeta); lc.count++;
+    if (n > 1) {
+        k_karras<<<grid(nInternal), T, 0, stream>>>(dk.Current(), n, H); lc.count++;
+        uint32_t minTris = 7;
+        for (int pass = 0; pass < treeletPasses; pass++) {
+            if (minTris > n) break;
+            k_treelet_clear<<<grid(n), T, 0, stream>>>(numTris, nInternal, baseCount); lc.count++;
+            k_find_treelets<<<grid(n), T, 0, stream>>>(sortedPrims, n, minTris, H, aabb, numTris, baseCount, baseRoots); lc.count++;
+            uint32_t maxRoots = n / minTris + 1;
+            uint32_t blocks = (maxRoots + 3) / 4;
+            if (blocks > 148 * 16) blocks = 148 * 16;
+            k_treelet_reorder<<<blocks, 128, 0, stream>>>(n, H, aabb, numTris, baseCount, baseRoots); lc.count++;
+            minTris *= 2;
+        }
+    }
+    CK(cudaMemsetAsync(numTris, 0, 4 * (size_t)(nInternal + 1), stream));
+    k_refit<<<grid(n), T, 0, stream>>>(n, H, bvh, numTris); lc.count++;
+    k_widen<<<grid(n), T, 0, stream>>>(n, bvh, out.pairs, out.tris); lc.count++;
+    CK(cudaMemcpyAsync(&out.root, bvh + 16, sizeof(RefNode), cudaMemcpyDeviceToHost, stream));
+    CK(cudaGetLastError());
+    cudaFreeAsync(prims, stream); cudaFreeAsync(meta, stream); cudaFreeAsync(codes, stream); cudaFreeAsync(order, stream);
+    cudaFreeAsync(codesAlt, stream); cudaFreeAsync(orderAlt, stream); cudaFreeAsync(sceneBox, stream); cudaFreeAsync(numTris, stream);
+    cudaFreeAsync(baseCount, stream); cudaFreeAsync(baseRoots, stream); cudaFreeAsync(H, stream); cudaFreeAsync(aabb, stream);
+    cudaFreeAsync(cubTemp, stream);
+    CK(cudaStreamSynchronize(stream));
+    out.numPrims = n;
+#undef CK
+    return cudaSuccess;
+}
+
+} // namespace tbd

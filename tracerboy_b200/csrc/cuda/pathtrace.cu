@@ -1,0 +1,768 @@
+// pathtrace.cu — wavefront path tracer for sm_100a.
+//
+// Role: SoftwareRayTraceCS.hlsl:9-51 -> RayTraceCommon (RayGenCommon.h:690-728) ->
+// PathTrace (kernel.glsl:1805-1921) -> Trace (kernel.glsl:1278-1776), i.e. the
+// reference's one-thread-per-pixel megakernel, re-designed as a wavefront:
+//
+//   k_raygen   one thread per pixel: seed (hash13), jitter, camera ray, path state, AOV clear
+//   k_extend   persistent threads over the ray queue: closest hit (traverse.cuh)
+//   k_shade    persistent threads over the same queue: one iteration of the bounce loop
+//              (material fetch, emissive, NEE + inline shadow query, BSDF sampling,
+//              throughput update, russian roulette for the next bounce); survivors are
+//              appended to the next queue with one warp-aggregated atomic per warp;
+//              terminated paths are accumulated in-kernel (OutputTexture +=)
+//
+// Per-pixel arithmetic follows the reference's order of operations with the intrinsics
+// pinned in common/tb_math.h / tb_vec.h (compiled with -fmad=false), and consumes the
+// reference's sequential per-pixel rand() stream in the reference's order (SURVEY
+// Appendix A) so that results are bit-identical to the CPU oracle.
+#include <cstdio>
+#include "../common/tb_vec.h"
+#include "device_types.h"
+#include "launch.h"
+#include "pathtrace.h"
+#include "traverse.cuh"
+
+using namespace tbm;
+
+namespace tbd {
+
+namespace {
+
+#define EPSILON 0.000001f
+#define PI_K 3.1415926535f
+#define LARGE_NUMBER 1e20f
+#define AIR_IOR 1.0f
+#define MIN_ROUGHNESS 0.04f
+#define MIN_ROUGHNESS_SQUARED (0.04f * 0.04f)
+#define MIN_T 0.001f
+#define FAR_T 999999.0f
+
+__device__ __forceinline__ f3 F3(const TbFloat3& v) { return mk3(v.x, v.y, v.z); }
+
+struct Mat {
+    f3 albedo; uint32_t albedoIndex, normalMapIndex, emissiveIndex, specularMapIndex;
+    float IOR; f3 absorption; float roughness; f3 scattering; f3 emissive; int Flags; float SpecularCoef;
+};
+
+__device__ __forceinline__ Mat load_mat(const TbMaterial* __restrict__ mats, uint32_t id) {
+    // 84 B = 21 words; read-only path
+    const uint32_t* p = (const uint32_t*)(mats + id);
+    uint32_t w[21];
+#pragma unroll
+    for (int i = 0; i < 21; i++) w[i] = __ldg(p + i);
+    Mat m;
+    m.albedo = mk3(__uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]));
+    m.albedoIndex = w[3]; m.normalMapIndex = w[5]; m.emissiveIndex = w[6]; m.specularMapIndex = w[7];
+    m.IOR = __uint_as_float(w[8]);
+    m.absorption = mk3(__uint_as_float(w[9]), __uint_as_float(w[10]), __uint_as_float(w[11]));
+    m.roughness = __uint_as_float(w[12]);
+    m.scattering = mk3(__uint_as_float(w[13]), __uint_as_float(w[14]), __uint_as_float(w[15]));
+    m.emissive = mk3(__uint_as_float(w[16]), __uint_as_float(w[17]), __uint_as_float(w[18]));
+    m.Flags = (int)w[19];
+    m.SpecularCoef = __uint_as_float(w[20]);
+    return m;
+}
+
+struct Rng {
+    float seed, time;
+    __device__ __forceinline__ float next() { float s = seed; seed = seed + 1.0f; return frac(sin_(s + time) * 43758.5453123f); }
+};
+
+// ------------------------------------------------------------------ textures
+__device__ __forceinline__ f4 fetch_texel(const DeviceScene::ImageRef& im, int x, int y) {
+    if (im.format == 0) return *((const f4*)im.data + ((size_t)y * im.width + x));
+    uchar4 c = *((const uchar4*)im.data + ((size_t)y * im.width + x));
+    return mk4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
+}
+__device__ __forceinline__ int wrapi(int i, int n) { i %= n; return i < 0 ? i + n : i; }
+__device__ __forceinline__ f4 lerp4(f4 a, f4 b, float s) { return mk4(lerp(a.x, b.x, s), lerp(a.y, b.y, s), lerp(a.z, b.z, s), lerp(a.w, b.w, s)); }
+__device__ f4 sample_bilinear_wrap(const DeviceScene::ImageRef& im, f2 uv) {
+    const float nanv = __uint_as_float(0x7fc00000u);
+    if (!(fabsf(uv.x) <= 1.0e6f) || !(fabsf(uv.y) <= 1.0e6f)) return mk4(nanv, nanv, nanv, nanv);
+    float fx = uv.x * (float)im.width - 0.5f, fy = uv.y * (float)im.height - 0.5f;
+    float x0f = floorf(fx), y0f = floorf(fy);
+    float tx = fx - x0f, ty = fy - y0f;
+    int x0 = wrapi((int)x0f, (int)im.width), y0 = wrapi((int)y0f, (int)im.height);
+    int x1 = wrapi(x0 + 1, (int)im.width), y1 = wrapi(y0 + 1, (int)im.height);
+    f4 a = lerp4(fetch_texel(im, x0, y0), fetch_texel(im, x1, y0), tx);
+    f4 b = lerp4(fetch_texel(im, x0, y1), fetch_texel(im, x1, y1), tx);
+    return lerp4(a, b, ty);
+}
+__device__ f4 texture_nonrecursive(const DeviceScene& sc, const TbTextureData& t, f2 uv) {
+    f4 data = mk4(0, 0, 0, 0);
+    if (t.TextureType == TB_IMAGE_TEXTURE_TYPE) data = sample_bilinear_wrap(sc.images[t.DescriptorHeapIndex], uv);
+    else if (t.TextureType == TB_CHECKER_TEXTURE_TYPE) {
+        f2 scaled = uv * mk2(t.UScale, t.VScale);
+        data = mk4(F3(t.CheckerColor1), 1.0f);
+        if ((((int)scaled.x + (int)scaled.y) % 2) == 0) data = mk4(F3(t.CheckerColor2), 1.0f);
+    }
+    if (t.TextureFlags & TB_NEEDS_GAMMA_CORRECTION_TEXTURE_FLAG) { data.x = pow_(data.x, 2.2f); data.y = pow_(data.y, 2.2f); data.z = pow_(data.z, 2.2f); }
+    return data;
+}
+__device__ f4 get_texture_data(const DeviceScene& sc, uint32_t index, f2 uv) {
+    if (index == TB_INVALID_TEXTURE) return mk4(0, 0, 0, 0);
+    if (sc.flipTextureUVs) uv = mk2(0.0f, 1.0f) + uv * mk2(1.0f, -1.0f);
+    TbTextureData t = sc.textures[index];
+    if (t.TextureType == TB_SCALE_TEXTURE_TYPE) {
+        f4 c1 = texture_nonrecursive(sc, sc.textures[t.TextureIndex1], uv);
+        f4 c2 = texture_nonrecursive(sc, sc.textures[t.TextureIndex2], uv);
+        return c1 * mk4(F3(t.ScaleColor1), 1.0f) + c2 * mk4(F3(t.ScaleColor2), 1.0f);
+    }
+    return texture_nonrecursive(sc, t, uv);
+}
+__device__ f3 sample_environment_map(const DeviceScene& sc, f3 v) {
+    if (sc.envImage < 0) return mk3(0.0f);
+    v = mk3(dot(v, mk3(sc.envTransform[0][0], sc.envTransform[0][1], sc.envTransform[0][2])),
+            dot(v, mk3(sc.envTransform[1][0], sc.envTransform[1][1], sc.envTransform[1][2])),
+            dot(v, mk3(sc.envTransform[2][0], sc.envTransform[2][1], sc.envTransform[2][2])));
+    f3 viewDir = normalize(v);
+    float p = atan2_(viewDir.y, viewDir.x);
+    p = p > 0.0f ? p : p + 2.0f * 3.14f;
+    f2 uv;
+    uv.x = p / (2.0f * 3.14f);
+    uv.y = acos_(viewDir.z) / 3.14f;
+    f4 t = sample_bilinear_wrap(sc.images[sc.envImage], uv);
+    return mk3(t.x, t.y, t.z) * mk3(sc.envColorScale[0], sc.envColorScale[1], sc.envColorScale[2]);
+}
+
+// -------------------------------------------------------------------- noise
+__device__ __forceinline__ float hash13(f3 p3) {
+    p3 = frac3(p3 * 0.1031f);
+    float d = dot(p3, mk3(p3.y, p3.z, p3.x) + 33.33f);
+    p3 = p3 + d;
+    return frac((p3.x + p3.y) * p3.z);
+}
+struct BlueNoise { f2 primary, dof; };
+__device__ __forceinline__ BlueNoise get_blue_noise(const DeviceScene& sc, const FrameConstants& fc, Rng& rng, uint32_t px, uint32_t py) {
+    BlueNoise d;
+    if (!fc.settings.EnableBlueNoise) {
+        float a, b;
+        a = rng.next(); b = rng.next(); d.primary = mk2(a, b);
+        a = rng.next(); b = rng.next();
+        a = rng.next(); b = rng.next();
+        a = rng.next(); b = rng.next(); d.dof = mk2(a, b);
+    } else {
+        f2 h = mk2(fc.halton2, fc.halton3);
+        const uchar4* t = (const uchar4*)sc.blueNoise + ((size_t)(py % 256) * 256 + (px % 256));
+        uchar4 t0 = t[0], t1 = t[256 * 256];
+        d.primary = frac2(mk2((float)t0.x / 255.0f, (float)t0.y / 255.0f) + h);
+        d.dof = frac2(mk2((float)t1.z / 255.0f, (float)t1.w / 255.0f) + h);
+    }
+    return d;
+}
+
+// ------------------------------------------------------------------ materials
+__device__ __forceinline__ bool AllowsSpecular(const Mat& m) { return (m.Flags & TB_NO_SPECULAR_MATERIAL_FLAG) == 0; }
+__device__ __forceinline__ bool IsMetallic(const Mat& m) { return (m.Flags & TB_METALLIC_MATERIAL_FLAG) != 0; }
+__device__ __forceinline__ bool IsSSS(const Mat& m) { return (m.Flags & TB_SUBSURFACE_SCATTER_MATERIAL_FLAG) != 0; }
+__device__ __forceinline__ bool IsHair(const Mat& m) { return (m.Flags & TB_HAIR_MATERIAL_FLAG) != 0; }
+__device__ __forceinline__ bool IsLight(const Mat& m) { return (m.Flags & TB_LIGHT_MATERIAL_FLAG) != 0; }
+
+__device__ Mat get_material(const DeviceScene& sc, Rng& rng, int id, f2 uv, bool backside) {
+    Mat mat = load_mat(sc.materials, (uint32_t)id);
+    bool ignoreEmissive = backside;
+    if (ignoreEmissive) mat.emissive = mk3(0.0f);
+    if ((mat.Flags & TB_MIX_MATERIAL_FLAG) != 0) {
+        if (rng.next() < mat.albedo.z) mat = load_mat(sc.materials, (uint32_t)mat.albedo.x);
+        else mat = load_mat(sc.materials, (uint32_t)mat.albedo.y);
+    } else {
+        if (mat.albedoIndex != TB_INVALID_TEXTURE) { f4 t = get_texture_data(sc, mat.albedoIndex, uv); mat.albedo = mk3(t.x, t.y, t.z); }
+        if (mat.emissiveIndex != TB_INVALID_TEXTURE && !ignoreEmissive) { f4 t = get_texture_data(sc, mat.emissiveIndex, uv); mat.emissive = mk3(t.x, t.y, t.z); }
+        if (mat.specularMapIndex != TB_INVALID_TEXTURE) {
+            f4 t = get_texture_data(sc, mat.specularMapIndex, uv);
+            mat.roughness = t.y;
+            if (t.z > 0.5f) mat.Flags |= TB_METALLIC_MATERIAL_FLAG;
+        }
+    }
+    if (IsSSS(mat) && (mat.albedo.x != 0.0f || mat.albedo.y != 0.0f || mat.albedo.z != 0.0f)) {
+        f3 color = mat.albedo;
+        f3 mfp = mk3(1.0f) / mat.scattering;
+        f3 alpha = mk3(1.0f) - exp3(((-5.09406f * color) + ((2.61188f * color) * color)) - (((4.31805f * color) * color) * color));
+        f3 s = (mk3(1.9f) - color) + ((3.5f * (color - 0.8f)) * (color - 0.8f));
+        f3 transmission = mk3(1.0f) / (s * mfp);
+        mat.scattering = transmission * alpha;
+        mat.absorption = transmission - mat.scattering;
+        mat.albedo = mk3(0.0f);
+    }
+    return mat;
+}
+__device__ f3 get_detail_normal(const DeviceScene& sc, const FrameConstants& fc, const Mat& mat, f3 normal, f3 tangent, f2 uv) {
+    if (mat.normalMapIndex != TB_INVALID_TEXTURE && fc.settings.EnableNormalMaps) {
+        f3 bitangent = cross(tangent, normal);
+        f4 nm = get_texture_data(sc, mat.normalMapIndex, uv);
+        f3 tbn = mk3((0.5f - nm.x) * 2.0f, (0.5f - nm.y) * 2.0f, 0.0f);
+        tbn.z = sqrtf(1.0f - (tbn.x * tbn.x + tbn.y * tbn.y));
+        return normalize((tangent * tbn.x + bitangent * tbn.y) + normal * fmaxf(tbn.z, 0.02f));
+    }
+    return normal;
+}
+
+// --------------------------------------------------------------------- lights
+__device__ __forceinline__ f3 random_barycentric(Rng& rng) {
+    float u = rng.next();
+    float v = rng.next();
+    if (u + v > 1.0f) { u = 1.0f - u; v = 1.0f - v; }
+    return mk3(u, v, 1.0f - u - v);
+}
+__device__ __forceinline__ float light_target_pdf(const TbLight& l, f3 bary, f3 pos) {
+    f3 lp = (F3(l.P0) * bary.x + F3(l.P1) * bary.y) + F3(l.P2) * bary.z;
+    float d = length(lp - pos);
+    return (l.SurfaceArea * dot(F3(l.LightColor), mk3(0.212671f, 0.715160f, 0.072169f))) / d * d;
+}
+__device__ void get_one_light_sample(const DeviceScene& sc, const FrameConstants& fc, Rng& rng, f3 pos, f3& LightDirection,
+                                     f3& LightColor, float& PDFValue, f3& LightNormal, float& LightAttenuation) {
+    LightDirection = LightColor = LightNormal = mk3(0.0f);
+    LightAttenuation = 0.0f;
+    PDFValue = 0.0f;
+    const uint32_t lightCount = sc.numLights;
+    if (lightCount > 0 && fc.settings.EnableNextEventEstimation) {
+        if (fc.settings.EnableSamplingImportanceResampling) {
+            uint32_t selIndex = 0; f3 selBary = mk3(0.0f); float weightSum = 0.0f;
+            for (uint32_t i = 0; i < 16; i++) {
+                uint32_t li = (uint32_t)(rng.next() * (float)lightCount);
+                TbLight light = sc.lights[li];
+                f3 bary = random_barycentric(rng);
+                float target = light_target_pdf(light, bary, pos);
+                float proposal = 1.0f / (float)lightCount;
+                float w = target / (proposal * 16.0f);
+                weightSum += w;
+                if (rng.next() < w / weightSum) { selIndex = li; selBary = bary; }
+            }
+            TbLight light = sc.lights[selIndex];
+            float sirPDF = light_target_pdf(light, selBary, pos) / weightSum;
+            PDFValue = sirPDF / light.SurfaceArea;
+            f3 lp = (F3(light.P0) * selBary.x + F3(light.P1) * selBary.y) + F3(light.P2) * selBary.z;
+            LightDirection = lp - pos;
+            LightNormal = (F3(light.N0) * selBary.x + F3(light.N1) * selBary.y) + F3(light.N2) * selBary.z;
+            LightColor = F3(light.LightColor);
+        } else {
+            uint32_t li = (uint32_t)(rng.next() * (float)lightCount);
+            TbLight light = sc.lights[li];
+            f3 bary = random_barycentric(rng);
+            if (light.LightType == TB_LIGHT_TYPE_AREA) {
+                f3 lp = (F3(light.P0) * bary.x + F3(light.P1) * bary.y) + F3(light.P2) * bary.z;
+                LightDirection = lp - pos;
+                LightNormal = (F3(light.N0) * bary.x + F3(light.N1) * bary.y) + F3(light.N2) * bary.z;
+                float d = length(LightDirection);
+                LightAttenuation = 1.0f / (d * d);
+                LightDirection = LightDirection / d;
+            } else if (light.LightType == TB_LIGHT_TYPE_DIRECTIONAL) {
+                LightDirection = -F3(light.Direction);
+                if (fc.settings.DebugValue > 0.0f) {
+                    LightDirection.x = sin_(fc.settings.DebugValue);
+                    LightDirection.y = sin_(fc.settings.DebugValue2);
+                    LightDirection = normalize(LightDirection);
+                }
+                LightNormal = -LightDirection;
+                LightAttenuation = 1.0f;
+            }
+            LightColor = F3(light.LightColor);
+            PDFValue = 1.0f / (float)lightCount;
+            if (light.LightType == TB_LIGHT_TYPE_AREA) PDFValue /= light.SurfaceArea;
+        }
+    }
+}
+
+// ------------------------------------------------------------------- sampling
+__device__ __forceinline__ f3 reorient_around_normal(f3 v, f3 normal) {
+    f3 tangent;
+    if (fabsf(normal.x) > fabsf(normal.y)) tangent = mk3(-normal.z, 0.0f, normal.x) / sqrtf(normal.x * normal.x + normal.z * normal.z);
+    else tangent = mk3(0.0f, normal.z, -normal.y) / sqrtf(normal.y * normal.y + normal.z * normal.z);
+    f3 bitangent = cross(normal, tangent);
+    return normalize((v.x * tangent + v.y * normal) + v.z * bitangent);
+}
+__device__ __forceinline__ f3 importance_sampled_direction(f3 normal, float roughness, float rand0, float rand1, float& pdf) {
+    float lobe = pow_(1.0f - roughness, 5.0f) * 1000.0f;
+    float theta = 2.0f * PI_K * rand1;
+    float phi = acos_(sqrtf(pow_(rand0, 1.0f / (lobe + 1.0f))));
+    f3 d = mk3(sin_(phi) * cos_(theta), cos_(phi), sin_(phi) * sin_(theta));
+    pdf = (lobe + 1.0f) * pow_(cos_(phi), lobe) / (2.0f * PI_K);
+    return reorient_around_normal(d, normal);
+}
+__device__ __forceinline__ float ggx_pdf(f3 normal, f3 outgoing, f3 halfVector, float roughness) {
+    roughness = fmaxf(MIN_ROUGHNESS, roughness);
+    float a = roughness * roughness;
+    float a2 = a * a;
+    float cosTheta = fabsf(dot(normal, halfVector));
+    float e = ((a2 - 1.0f) * cosTheta) * cosTheta + 1.0f;
+    if (e <= 0.0f) return LARGE_NUMBER;
+    float d = a2 / ((PI_K * e) * e);
+    return d * fabsf(dot(halfVector, normal)) / (4.0f * fabsf(dot(outgoing, halfVector)));
+}
+__device__ __forceinline__ float ggx_ndf(f3 normal, f3 halfVector, float roughnessSquared) {
+    roughnessSquared = fmaxf(roughnessSquared, MIN_ROUGHNESS_SQUARED);
+    float a2 = roughnessSquared * roughnessSquared;
+    float nDotH = dot(normal, halfVector);
+    float denom = PI_K * pow_((nDotH * nDotH) * (a2 - 1.0f) + 1.0f, 2.0f);
+    return a2 / denom;
+}
+__device__ __forceinline__ float diffuse_brdf(f3 l, f3 n) { return fmaxf(dot(l, n), 0.0f) / PI_K; }
+__device__ __forceinline__ f3 half_vector_safe(f3 a, f3 b, f3 normal) {
+    if (dot(a, b) > (-1.0f + EPSILON)) return normalize(a + b);
+    return normal;
+}
+enum RefractResult { REFRACTED, REFLECTED, GIVE_UP };
+__device__ RefractResult refract_or_reflect(Rng& rng, f3& dir, f3 normal, float nr, float RdotN, bool perfectSpec, float roughness, bool& prevPerfectlySpecular) {
+    float discriminant = 1.0f - (nr * nr) * (1.0f - RdotN * RdotN);
+    if (discriminant > EPSILON) {
+        f3 refr = normalize(nr * (dir - normal * RdotN) - normal * sqrtf(discriminant));
+        if (perfectSpec) { dir = refr; prevPerfectlySpecular = true; }
+        else {
+            float pdf;
+            float r0 = rng.next();
+            float r1 = rng.next();
+            dir = importance_sampled_direction(refr, roughness, r0, r1, pdf);
+            if (pdf < EPSILON) {
+                r0 = rng.next();
+                r1 = rng.next();
+                dir = importance_sampled_direction(refr, roughness, r0, r1, pdf);
+                if (pdf < EPSILON) return GIVE_UP;
+            }
+        }
+        return REFRACTED;
+    }
+    dir = reflect(dir, normal);
+    return REFLECTED;
+}
+
+// ------------------------------------------------------------- hit attributes
+struct Surface { f3 normal, tangent; f2 uv; int material; };
+__device__ __forceinline__ Surface surface_from_hit(const DeviceScene& sc, float b1, float b2, uint32_t geom, uint32_t prim) {
+    // GetGeometryInfo/GetHitInfo, SharedHitGroup.h:48-151
+    Surface s;
+    TbGeometryRecord G = sc.geoms[geom];
+    f3 bary = mk3(1.0f - b1 - b2, b1, b2);
+    const uint32_t* idx = sc.indices + G.IndexFirst + 3 * (size_t)prim;
+    uint32_t i0 = __ldg(idx), i1 = __ldg(idx + 1), i2 = __ldg(idx + 2);
+    const float4* va = (const float4*)(sc.vertices + G.VertexFirst + i0);
+    const float4* vb = (const float4*)(sc.vertices + G.VertexFirst + i1);
+    const float4* vc = (const float4*)(sc.vertices + G.VertexFirst + i2);
+    float4 a0 = __ldg(va), a1 = __ldg(va + 1), b0 = __ldg(vb), b1v = __ldg(vb + 1), c0 = __ldg(vc), c1 = __ldg(vc + 1);
+    // Vertex = normal3, uv2, tangent3
+    f2 uv0 = mk2(a0.w, a1.x), uv1 = mk2(b0.w, b1v.x), uv2 = mk2(c0.w, c1.x);
+    s.uv = (bary.x * uv0 + bary.y * uv1) + bary.z * uv2;
+    s.normal = normalize((bary.x * mk3(a0.x, a0.y, a0.z) + bary.y * mk3(b0.x, b0.y, b0.z)) + bary.z * mk3(c0.x, c0.y, c0.z));
+    s.tangent = normalize((bary.x * mk3(a1.y, a1.z, a1.w) + bary.y * mk3(b1v.y, b1v.z, b1v.w)) + bary.z * mk3(c1.y, c1.z, c1.w));
+    s.material = (int)G.MaterialIndex;
+    return s;
+}
+
+struct RayCount { uint32_t rays, tris, boxes; };
+
+// Intersect() for the rays that stay inside the shading stage (shadow feelers, SSS walk)
+__device__ __forceinline__ bool intersect_inline(const DeviceBvh& bvh, const DeviceScene& sc, f3 org, f3 dir, RayCount& rc, Surface& s, float& t) {
+    HitRec h;
+    trace_ray(bvh, org, dir, MIN_T, FAR_T, h);
+    rc.rays++; rc.tris += h.tris; rc.boxes += h.boxes;
+    if (h.t >= 0.0f) { s = surface_from_hit(sc, h.b1, h.b2, h.geom, h.prim); t = h.t; return true; }
+    s.normal = mk3(0.0f); s.tangent = mk3(0.0f); s.uv = mk2(0, 0); s.material = -1; t = -1.0f;
+    return false;
+}
+
+__device__ __forceinline__ f3 lens_position(const TbCamera& cam, f2 uv, float aspect) {
+    f3 p = F3(cam.Position);
+    float lensWidth = cam.LensHeight * aspect;
+    p += ((F3(cam.Right) * (uv.x * 2.0f - 1.0f)) * lensWidth) / 2.0f;
+    p += ((F3(cam.Up) * (uv.y * 2.0f - 1.0f)) * cam.LensHeight) / 2.0f;
+    return p;
+}
+__device__ __forceinline__ float gaussian(float x, float mu, float sigma) {
+    float d = x - mu;
+    return 1.0f / sqrtf((2.0f * PI_K) * sigma * sigma) * exp_(-(d * d) / ((2.0f * sigma) * sigma));
+}
+
+// state word packing in rayD.w: bits 0..7 bounce index, bit 8 prevPerfectlySpecular
+__device__ __forceinline__ uint32_t pack_state(int bounce, bool prevSpec) { return (uint32_t)bounce | (prevSpec ? 0x100u : 0u); }
+
+// ---------------------------------------------------------------------- raygen
+__global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, FrameConstants fc, PathState st) {
+    uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = fc.width * fc.height;
+    if (pi == 0) { st.queueCount[0] = n; st.queueCount[1] = 0; }
+    if (pi >= n) return;
+    uint32_t px = pi % fc.width, py = pi / fc.width;
+    Rng rng;
+    rng.time = fc.time;
+    rng.seed = hash13(mk3((float)px, (float)py, (float)fc.frame));
+    f2 res = mk2((float)fc.width, (float)fc.height);
+    f2 dispatchUV = mk2((float)px + 0.5f, (float)py + 0.5f) / res;
+    f2 uv0 = mk2(0.0f, 1.0f) + dispatchUV * mk2(1.0f, -1.0f);
+    f2 pixelCoord = uv0 * res;
+    // PathTrace
+    f2 pixelUVSize = mk2(1.0f / res.x, 1.0f / res.y);
+    f2 uv = pixelCoord * pixelUVSize;
+    BlueNoise bn = get_blue_noise(sc, fc, rng, px, py);
+    f2 off = bn.primary - mk2(0.5f, 0.5f);
+    float pixelRadius = fc.settings.FilterWidth / 2.0f;
+    float filterWeight = 1.0f;
+    if (fc.settings.FilterType == TB_FILTER_TRIANGLE) filterWeight = fmaxf(0.5f - fabsf(off.x), 0.5f - fabsf(off.y));
+    else if (fc.settings.FilterType == TB_FILTER_GAUSSIAN) {
+        float sigma = 0.8f;
+        float eX = gaussian(1.0f, 0.0f, sigma), eY = gaussian(1.0f, 0.0f, sigma);
+        filterWeight = fmaxf(0.0f, gaussian(off.x * 2.0f, 0.0f, sigma) - eX) * fmaxf(0.0f, gaussian(off.y * 2.0f, 0.0f, sigma) - eY);
+    }
+    uv = uv + (off * pixelUVSize) * (pixelRadius * 2.0f);
+    float aspect = res.x / res.y;
+    f3 camPos = F3(fc.camera.Position);
+    f3 focalPoint = camPos - fc.camera.FocalDistance * normalize(F3(fc.camera.LookAt) - camPos);
+    f3 lensPoint = lens_position(fc.camera, uv, aspect);
+    f3 neighborLensPoint = lens_position(fc.camera, uv + pixelUVSize, aspect);
+    f3 org = focalPoint, dir = normalize(lensPoint - focalPoint);
+    f3 ndir = normalize(neighborLensPoint - focalPoint);
+    if (fc.settings.DOFFocalDistance > 0.0f) {
+        f3 FocusPoint = org + dir * fc.settings.DOFFocalDistance;
+        float Radius = sqrtf(bn.dof.x) * fc.settings.ApertureWidth;
+        float Theta = (bn.dof.y * 2.0f) * PI_K;
+        f2 fj = mk2(cos_(Theta) * Radius, sin_(Theta) * Radius);
+        org = org + (fj.x * F3(fc.camera.Right) + fj.y * F3(fc.camera.Up));
+        dir = normalize(FocusPoint - org);
+    }
+    // Trace(): GetBlueNoise() again (values unused, burns 8 rand() when blue noise is off), kernel.glsl:1283
+    if (!fc.settings.EnableBlueNoise) { for (int k = 0; k < 8; k++) (void)rng.next(); }
+    st.rayO[pi] = make_float4(org.x, org.y, org.z, rng.seed);
+    st.rayD[pi] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(pack_state(0, false)));
+    st.thr[pi] = make_float4(1.0f, 1.0f, 1.0f, filterWeight);
+    st.col[pi] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    st.neighbor[pi] = make_float4(focalPoint.x, focalPoint.y, focalPoint.z, 0.0f);
+    st.neighborDir[pi] = make_float4(ndir.x, ndir.y, ndir.z, 0.0f);
+    st.queue[0][pi] = pi;
+    // ClearAOVs (RayGenCommon.h:650-654) + zeroed world-position accumulators (:693-694)
+    st.aovAlbedo[pi] = make_float4(0, 0, 0, 1.0f);
+    st.aovNormal[pi] = make_float4(0, 0, 0, 1.0f);
+    st.aovWorldPos[fc.frame & 1][pi] = make_float4(0, 0, 0, 0);
+    st.primaryHit[pi] = make_uint2(0xffffffffu, 0xffffffffu);
+    st.counters[pi] = make_uint2(0, 0);
+}
+
+// ---------------------------------------------------------------------- extend
+__global__ void __launch_bounds__(128) k_extend(DeviceBvh bvh, PathState st, int qi, int bounceIsZero, uint32_t outputHeatmap) {
+    const uint32_t count = st.queueCount[qi];
+    if (blockIdx.x == 0 && threadIdx.x == 0) st.queueCount[qi ^ 1] = 0; // next queue starts empty (consumed by k_shade)
+    uint32_t rays = 0, tris = 0, boxes = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        uint32_t pi = st.queue[qi][i];
+        float4 o = st.rayO[pi], d = st.rayD[pi];
+        HitRec h;
+        trace_ray(bvh, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), MIN_T, FAR_T, h);
+        st.hit[pi] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
+        st.hitGeom[pi] = h.geom;
+        uint2 c = st.counters[pi];
+        c.x += h.tris; c.y += h.boxes;
+        st.counters[pi] = c;
+        if (bounceIsZero) st.primaryHit[pi] = make_uint2(h.geom, h.prim);
+        if (outputHeatmap) st.aovAlbedo[pi] = make_float4((float)h.tris, (float)h.boxes, 0.0f, 0.0f);
+        rays++; tris += h.tris; boxes += h.boxes;
+    }
+    // warp-reduced global statistics
+    for (int o = 16; o > 0; o >>= 1) {
+        rays += __shfl_xor_sync(0xffffffffu, rays, o); tris += __shfl_xor_sync(0xffffffffu, tris, o); boxes += __shfl_xor_sync(0xffffffffu, boxes, o);
+    }
+    if ((threadIdx.x & 31) == 0 && rays) {
+        atomicAdd(&st.stats[0], (unsigned long long)rays); atomicAdd(&st.stats[1], (unsigned long long)boxes); atomicAdd(&st.stats[2], (unsigned long long)tris);
+    }
+}
+
+// ----------------------------------------------------------------------- shade
+// RayTraceCommon tail (RayGenCommon.h:696-727): firefly clamp + filter weight (kernel.glsl:1907-1920),
+// NaN rejection, OutputTexture +=, jittered buffer coin.
+__device__ __forceinline__ void finish_path(const FrameConstants& fc, PathState& st, uint32_t pi, f3 color, float filterWeight, Rng& rng) {
+    if (fc.settings.FireflyClampValue >= EPSILON) color = min3(color, fc.settings.FireflyClampValue);
+    f4 c = mk4(color * filterWeight, filterWeight);
+    f4 outc = mk4(0, 0, 0, 0);
+    if (!isnan_(c.x) && !isnan_(c.y) && !isnan_(c.z) && !isnan_(c.w)) outc = outc + c;
+    bool realtime = fc.settings.RenderMode == TB_RENDER_REALTIME;
+    bool clear = realtime || fc.clearAccum;
+    float4 prev = clear ? make_float4(0, 0, 0, 0) : st.accum[pi];
+    st.accum[pi] = make_float4(outc.x + prev.x, outc.y + prev.y, outc.z + prev.z, outc.w + prev.w);
+    if (!realtime) {
+        bool take = fc.frame == 0 || rng.next() < 0.5f; // the coin is not drawn on frame 0 (short circuit, :723)
+        if (take) {
+            float4 pj = fc.clearAccum ? make_float4(0, 0, 0, 0) : st.jittered[pi];
+            st.jittered[pi] = make_float4(outc.x + pj.x, outc.y + pj.y, outc.z + pj.z, outc.w + pj.w);
+        } else if (fc.clearAccum) st.jittered[pi] = make_float4(0, 0, 0, 0);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_shade(DeviceBvh bvh, DeviceScene sc, FrameConstants fc, PathState st, int qi) {
+    const uint32_t count = st.queueCount[qi];
+    const TbOutputSettings& S = fc.settings;
+    const int MaxBounces = S.MaxBounces;
+    RayCount rc = {0, 0, 0};
+    const uint32_t stride = gridDim.x * blockDim.x;
+    // loop bound rounded up to a warp multiple so every lane reaches the ballot below
+    const uint32_t countUp = (count + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < countUp; i += stride) {
+        bool alive = false; // does this path continue to the next bounce?
+        uint32_t pi = 0;
+        if (i < count) {
+            pi = st.queue[qi][i];
+            float4 o4 = st.rayO[pi], d4 = st.rayD[pi], t4 = st.thr[pi], c4 = st.col[pi], h4 = st.hit[pi];
+            Rng rng; rng.seed = o4.w; rng.time = fc.time;
+            uint32_t sw = __float_as_uint(d4.w);
+            int bounce = (int)(sw & 0xffu);
+            bool bPrevSpec = (sw & 0x100u) != 0;
+            f3 org = mk3(o4.x, o4.y, o4.z), dir = mk3(d4.x, d4.y, d4.z);
+            f3 thr = mk3(t4.x, t4.y, t4.z), acc = mk3(c4.x, c4.y, c4.z);
+            const float filterWeight = t4.w;
+            const bool bFirstRay = bounce == 0;
+            bool terminated = false;
+            uint2 cnt0 = make_uint2(rc.tris, rc.boxes);
+
+            do { // one iteration of the bounce loop, `break` = path ends
+                if (thr.x < EPSILON && thr.y < EPSILON && thr.z < EPSILON) { terminated = true; break; }
+                if (h4.x < 0.0f) { // miss
+                    acc += thr * sample_environment_map(sc, dir);
+                    if (bFirstRay) st.aovEmissive[pi] = make_float4(acc.x, acc.y, acc.z, 1.0f);
+                    terminated = true; break;
+                }
+                Surface sf = surface_from_hit(sc, h4.y, h4.z, st.hitGeom[pi], __float_as_uint(h4.w));
+                f3 normal = sf.normal;
+                f3 RayPoint = org + dir * h4.x;
+                org = RayPoint + normal * EPSILON;
+                float RdotN = dot(normal, dir);
+                bool backside = RdotN > 0.0f;
+                Mat material = get_material(sc, rng, sf.material, sf.uv, backside);
+                f3 detailNormal = get_detail_normal(sc, fc, material, normal, sf.tangent, sf.uv);
+                if (bFirstRay) {
+                    float4 nb = st.neighbor[pi], nd = st.neighborDir[pi];
+                    f3 nrp = mk3(nb.x, nb.y, nb.z) + mk3(nd.x, nd.y, nd.z) * h4.x;
+                    f3 wp = mk3(0.0f) + RayPoint;
+                    float dn = 0.0f + length(nrp - RayPoint);
+                    st.aovWorldPos[fc.frame & 1][pi] = make_float4(wp.x, wp.y, wp.z, dn);
+                    st.aovNormal[pi] = make_float4(detailNormal.x, detailNormal.y, detailNormal.z, 1.0f);
+                    st.aovDepth[pi] = saturate(h4.x / S.MaxZ);
+                    if ((int)(pi % fc.width) == fc.selectedX && (int)(pi / fc.width) == fc.selectedY) {
+                        st.readbackStats->SelectedPixelDistance = h4.x;
+                        st.readbackStats->SelectedMaterialID = sf.material;
+                    }
+                    if (S.OutputType == TB_OUTPUT_HEATMAP) { terminated = true; break; }
+                }
+                float CurrentIOR = backside ? material.IOR : AIR_IOR;
+                float NewIOR = backside ? AIR_IOR : material.IOR;
+                if (backside) { normal = -normal; RdotN = -RdotN; detailNormal = -detailNormal; }
+                float ReflectionCoefficient = material.SpecularCoef;
+                bool bSpecularRay = false;
+                if (AllowsSpecular(material)) {
+                    if (IsMetallic(material) || IsHair(material)) bSpecularRay = true;
+                    else bSpecularRay = rng.next() < 0.5f;
+                }
+                bool bPerfectSpec = bSpecularRay && material.roughness < 0.05f;
+                if (bPrevSpec || bFirstRay || !IsLight(material) || !S.EnableNextEventEstimation) acc += thr * material.emissive;
+                if (IsLight(material)) { terminated = true; break; }
+
+                float lightPDF, lightAttenuation;
+                f3 lightDirection, lightColor, lightNormal;
+                get_one_light_sample(sc, fc, rng, RayPoint, lightDirection, lightColor, lightPDF, lightNormal, lightAttenuation);
+                if (!bPerfectSpec && lightPDF > EPSILON && dot(lightDirection, lightNormal) < 0.0f) {
+                    f3 ShadowMultiplier = mk3(1.0f);
+                    Surface ss; float stt;
+                    if (intersect_inline(bvh, sc, RayPoint + normal * EPSILON, lightDirection, rc, ss, stt)) {
+                        bool shBack = dot(ss.normal, lightDirection) > 0.0f;
+                        Mat sm = get_material(sc, rng, ss.material, ss.uv, shBack);
+                        if (!IsLight(sm)) ShadowMultiplier = mk3(0.0f);
+                    }
+                    float lightMultiplier = lightAttenuation * diffuse_brdf(lightDirection, detailNormal) * fabsf(dot(lightNormal, lightDirection)) / lightPDF;
+                    acc += (((thr * material.albedo) * lightMultiplier) * ShadowMultiplier) * lightColor;
+                }
+
+                f3 previousDirection = dir;
+                bPrevSpec = bPerfectSpec;
+                bool skipBrdf = false;
+                if (bSpecularRay) {
+                    // ImportanceSampleGGX, kernel.glsl:1066-1082
+                    float roughness = fmaxf(MIN_ROUGHNESS, material.roughness);
+                    float a = roughness * roughness;
+                    float a2 = a * a;
+                    float u1 = rng.next(), u2 = rng.next();
+                    float theta = 2.0f * PI_K * u2;
+                    float phi = acos_(sqrtf((1.0f - u1) / ((a2 - 1.0f) * u1 + 1.0f)));
+                    f3 dd = mk3(sin_(phi) * cos_(theta), cos_(phi), sin_(phi) * sin_(theta));
+                    f3 hh = reorient_around_normal(dd, normal);
+                    dir = reflect(dir, hh);
+                } else if (IsSSS(material)) {
+                    float nr = CurrentIOR / NewIOR;
+                    if (refract_or_reflect(rng, dir, normal, nr, RdotN, bPerfectSpec, material.roughness, bPrevSpec) == GIVE_UP) { terminated = true; break; }
+                    bool noScatter = material.scattering.x < EPSILON;
+                    float DistancePerScatter = 1.0f / (((material.scattering.x + material.scattering.y) + material.scattering.z) / 3.0f);
+                    float maxTravelDistance = noScatter ? LARGE_NUMBER : DistancePerScatter;
+                    bool exitting = (material.Flags & TB_SINGLE_SIDED_MATERIAL_FLAG) != 0;
+                    for (int k = 0; k < 100 && !exitting; k++) {
+                        float travelDistance = fmaxf(-log_(rng.next()), 0.1f) * maxTravelDistance;
+                        Surface ws; float wt;
+                        bool found = intersect_inline(bvh, sc, org, dir, rc, ws, wt);
+                        normal = ws.normal;
+                        if (!found) { thr = mk3(0.0f); break; }
+                        float tt = fminf(travelDistance, wt);
+                        exitting = tt < travelDistance || noScatter;
+                        if (k == 99 && !exitting) thr = mk3(0.0f);
+                        RayPoint = org + dir * tt;
+                        org = RayPoint + normal * EPSILON;
+                        thr *= exp3((-tt) * material.absorption);
+                        if (exitting) {
+                            RdotN = dot(normal, dir);
+                            if (RdotN >= 0.0f) { normal = -normal; RdotN = -RdotN; }
+                            RefractResult rr = refract_or_reflect(rng, dir, normal, NewIOR / CurrentIOR, RdotN, bPerfectSpec, material.roughness, bPrevSpec);
+                            if (rr == GIVE_UP) break;
+                            if (rr == REFLECTED) exitting = false;
+                        } else {
+                            // GenerateRandomDirection(), kernel.glsl:991-999
+                            float u1 = rng.next(), u2 = rng.next();
+                            float r = sqrtf(1.0f - u1 * u1);
+                            float phi = 2.0f * 3.14f * u2;
+                            dir = mk3(cos_(phi) * r, sin_(phi) * r, u1);
+                            thr /= 1.0f;
+                        }
+                    }
+                    skipBrdf = true; // `continue`, kernel.glsl:1690
+                } else {
+                    // GenerateCosineWeightedDirection, kernel.glsl:1025-1046
+                    float rand0 = rng.next();
+                    float rand1 = rng.next();
+                    float r = sqrtf(rand0);
+                    float theta = 2.0f * PI_K * rand1;
+                    float x = r * cos_(theta);
+                    float y = sqrtf(fmaxf(EPSILON, 1.0f - rand0));
+                    float z = r * sin_(theta);
+                    dir = reorient_around_normal(mk3(x, y, z), normal);
+                }
+                if (!skipBrdf) {
+                    float DiffusePDF = dot(dir, normal) / PI_K;
+                    if (AllowsSpecular(material)) {
+                        f3 halfVector = half_vector_safe(-previousDirection, dir, normal);
+                        float SpecularPDF = ggx_pdf(normal, dir, halfVector, material.roughness);
+                        float PDFValue = IsMetallic(material) ? SpecularPDF : lerp(SpecularPDF, DiffusePDF, 0.5f);
+                        thr /= PDFValue;
+                    } else thr /= DiffusePDF;
+                    if (bFirstRay) st.aovEmissive[pi] = make_float4(material.emissive.x, material.emissive.y, material.emissive.z, 1.0f);
+                    bool bRemoveAlbedo = (S.RenderMode == TB_RENDER_REALTIME) && bFirstRay;
+                    f3 albedo = bRemoveAlbedo ? mk3(1.0f) : material.albedo;
+                    if (IsMetallic(material)) {
+                        f3 halfVector = normalize(-previousDirection + dir);
+                        float roughnessSquared = fmaxf(material.roughness * material.roughness, MIN_ROUGHNESS_SQUARED);
+                        float specular = ggx_ndf(detailNormal, halfVector, roughnessSquared) /
+                                         ((4.0f * fabsf(dot(-previousDirection, halfVector))) * fmaxf(fabsf(dot(-previousDirection, normal)), fabsf(dot(dir, normal))));
+                        thr *= (specular * albedo) * saturate(dot(dir, normal));
+                    } else if (AllowsSpecular(material)) {
+                        f3 halfVector = half_vector_safe(-previousDirection, dir, normal);
+                        float fresnel = ReflectionCoefficient + (1.0f - ReflectionCoefficient) * pow_(fabsf(1.0f - dot(-previousDirection, halfVector)), 5.0f);
+                        float diffuseMultiplier = (((28.0f / (23.0f * PI_K)) * (1.0f - ReflectionCoefficient)) *
+                                                   (1.0f - pow_(1.0f - 0.5f * dot(-previousDirection, normal), 5.0f))) *
+                                                  (1.0f - pow_(1.0f - 0.5f * dot(dir, normal), 5.0f));
+                        f3 diffuse = albedo * diffuseMultiplier;
+                        float roughnessSquared = fmaxf(material.roughness * material.roughness, MIN_ROUGHNESS_SQUARED);
+                        float specular = ggx_ndf(detailNormal, halfVector, roughnessSquared) /
+                                         ((4.0f * fabsf(dot(-previousDirection, halfVector))) * fmaxf(fabsf(dot(-previousDirection, normal)), fabsf(dot(dir, normal))));
+                        thr *= (diffuse + fresnel * specular) * saturate(dot(dir, normal));
+                    } else {
+                        thr *= albedo * diffuse_brdf(dir, detailNormal);
+                    }
+                    if (bFirstRay && S.OutputType != TB_OUTPUT_HEATMAP) st.aovAlbedo[pi] = make_float4(material.albedo.x, material.albedo.y, material.albedo.z, 1.0f);
+                }
+                // top of the next loop iteration: bounce limit, then russian roulette (kernel.glsl:1286-1302)
+                int next = bounce + 1;
+                if (next >= MaxBounces) { terminated = true; break; }
+                if (next >= 2) {
+                    float p = fmaxf(fmaxf(thr.x, thr.y), thr.z);
+                    p = fmaxf(p, EPSILON);
+                    if (p < rng.next()) { terminated = true; break; }
+                    thr *= 1.0f / p;
+                }
+                bounce = next;
+            } while (false);
+
+            // per-pixel counters for the inline rays of this stage
+            if (rc.tris != cnt0.x || rc.boxes != cnt0.y) {
+                uint2 c = st.counters[pi];
+                c.x += rc.tris - cnt0.x; c.y += rc.boxes - cnt0.y;
+                st.counters[pi] = c;
+            }
+            if (terminated) finish_path(fc, st, pi, acc, filterWeight, rng);
+            else {
+                st.rayO[pi] = make_float4(org.x, org.y, org.z, rng.seed);
+                st.rayD[pi] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(pack_state(bounce, bPrevSpec)));
+                st.thr[pi] = make_float4(thr.x, thr.y, thr.z, filterWeight);
+                st.col[pi] = make_float4(acc.x, acc.y, acc.z, 0.0f);
+                alive = true;
+            }
+        }
+        // queue compaction: one atomic per warp
+        uint32_t ballot = __ballot_sync(0xffffffffu, alive);
+        if (ballot) {
+            uint32_t lane = threadIdx.x & 31, base = 0;
+            if (lane == 0) base = atomicAdd(&st.queueCount[qi ^ 1], (uint32_t)__popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (alive) st.queue[qi ^ 1][base + __popc(ballot & ((1u << lane) - 1u))] = pi;
+        }
+    }
+    uint32_t rays = rc.rays, tris = rc.tris, boxes = rc.boxes;
+    for (int o = 16; o > 0; o >>= 1) {
+        rays += __shfl_xor_sync(0xffffffffu, rays, o); tris += __shfl_xor_sync(0xffffffffu, tris, o); boxes += __shfl_xor_sync(0xffffffffu, boxes, o);
+    }
+    if ((threadIdx.x & 31) == 0 && rays) {
+        atomicAdd(&st.stats[0], (unsigned long long)rays); atomicAdd(&st.stats[1], (unsigned long long)boxes); atomicAdd(&st.stats[2], (unsigned long long)tris);
+    }
+}
+
+__global__ void k_resolve(const float4* __restrict__ accum, float* __restrict__ rgb, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = accum[i]; // ProcessLit: color / color.w, PostProcessCS.hlsl:23-27
+    rgb[3 * (size_t)i] = a.x / a.w; rgb[3 * (size_t)i + 1] = a.y / a.w; rgb[3 * (size_t)i + 2] = a.z / a.w;
+}
+
+__global__ void k_trace_rays(DeviceBvh bvh, const TbRay* __restrict__ rays, uint64_t n, TbHit* __restrict__ hits) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        TbRay r = rays[i];
+        HitRec h;
+        trace_ray(bvh, mk3(r.Origin[0], r.Origin[1], r.Origin[2]), mk3(r.Direction[0], r.Direction[1], r.Direction[2]), r.TMin, r.TMax, h);
+        TbHit o;
+        o.t = h.t; o.b1 = h.b1; o.b2 = h.b2; o.PrimitiveIndex = h.prim; o.GeometryIndex = h.geom; o.InstanceIndex = 0;
+        o.TrianglesTested = h.tris; o.BoxesTested = h.boxes;
+        hits[i] = o;
+    }
+}
+
+} // namespace
+
+// ------------------------------------------------------------------ launchers
+static int g_numSMs = 0;
+static int num_sms() {
+    if (!g_numSMs) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_numSMs, cudaDevAttrMultiProcessorCount, dev); if (g_numSMs <= 0) g_numSMs = 148; }
+    return g_numSMs;
+}
+
+cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const FrameConstants& fc, PathState& st,
+                         cudaStream_t stream, LaunchCounter& lc) {
+    const uint32_t n = fc.width * fc.height;
+    k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(sc, fc, st); lc.count++;
+    // persistent grids: a multiple of the SM count, capped by the work available
+    const uint32_t sms = (uint32_t)num_sms();
+    const uint32_t maxBlocks = sms * 16;
+    uint32_t blocks = (n + 127) / 128;
+    if (blocks > maxBlocks) blocks = maxBlocks;
+    const int maxBounces = fc.settings.MaxBounces;
+    const uint32_t heat = fc.settings.OutputType == TB_OUTPUT_HEATMAP;
+    for (int b = 0; b < maxBounces; b++) {
+        int qi = b & 1;
+        k_extend<<<blocks, 128, 0, stream>>>(bvh, st, qi, b == 0, heat); lc.count++;
+        k_shade<<<blocks, 128, 0, stream>>>(bvh, sc, fc, st, qi); lc.count++;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t resolve_rgb(const float4* accum, float* rgb, uint32_t n, cudaStream_t stream, LaunchCounter& lc) {
+    k_resolve<<<(n + 255) / 256, 256, 0, stream>>>(accum, rgb, n); lc.count++;
+    return cudaGetLastError();
+}
+
+cudaError_t trace_rays(const DeviceBvh& bvh, const TbRay* d_rays, uint64_t n, TbHit* d_hits, cudaStream_t stream, LaunchCounter& lc) {
+    uint64_t blocks = (n + 127) / 128;
+    uint64_t cap = (uint64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) return cudaSuccess;
+    k_trace_rays<<<(uint32_t)blocks, 128, 0, stream>>>(bvh, d_rays, n, d_hits); lc.count++;
+    return cudaGetLastError();
+}
+
+} // namespace tbd

@@ -1,0 +1,125 @@
+// traverse.cuh — software ray query on the PairNode/WideTri layout (device_types.h).
+//
+// Role: SoftwareRayQuery::TraceRayInline + Proceed (TraverseFunction.hlsli:537-785) with
+// FAST_PATH=1, DISABLE_ANYHIT, DISABLE_PROCEDURAL_GEOMETRY (RayGenCommon.h:355-362):
+// single-level BVH2, world-space ray, closest hit, near child first (left on equal t),
+// watertight ray/triangle test (Woop/Benthin/Wald 2013, :231-313), slab box test on
+// centre/half boxes (:203-221). Same visit order and the same BoxesTested/TrianglesTested
+// counters as the reference; what changes is the memory layout: one 64-byte PairNode
+// (4 x LDG.128) carries both child boxes and both child references, so an internal visit
+// costs one dependent fetch instead of the reference's three (popped node, left, right),
+// and a leaf visit is one 48-byte WideTri (3 x LDG.128) that already holds the
+// geometry/primitive ids (the reference reads 40 B primitive + 12 B metadata + 2 header
+// offsets).
+#pragma once
+#include "../common/tb_vec.h"
+#include "device_types.h"
+
+namespace tbd {
+
+struct HitRec {
+    float t, b1, b2;
+    uint32_t prim, geom;
+    uint32_t tris, boxes;
+};
+
+#define TB_STACK_DEPTH 96
+
+__device__ __forceinline__ bool slab(float& resultT, float closestT, tbm::f3 oinv, tbm::f3 inv, tbm::f3 ainv,
+                                     float cx, float cy, float cz, float hx, float hy, float hz) {
+    float rx = fmaf(cx, inv.x, -oinv.x), ry = fmaf(cy, inv.y, -oinv.y), rz = fmaf(cz, inv.z, -oinv.z);
+    float maxx = fmaf(hx, ainv.x, rx), maxy = fmaf(hy, ainv.y, ry), maxz = fmaf(hz, ainv.z, rz);
+    float minx = fmaf(-hx, ainv.x, rx), miny = fmaf(-hy, ainv.y, ry), minz = fmaf(-hz, ainv.z, rz);
+    float minT = fmaxf(fmaxf(minx, miny), minz);
+    float maxT = fminf(fminf(maxx, maxy), maxz);
+    resultT = fmaxf(minT, 0.0f);
+    return fmaxf(minT, 0.0f) < fminf(maxT, closestT);
+}
+
+__device__ __forceinline__ void trace_ray(const DeviceBvh& bvh, tbm::f3 org, tbm::f3 dir, float tmin, float tmax, HitRec& out) {
+    using namespace tbm;
+    f3 inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+    f3 oinv = org * inv;
+    f3 ainv = abs3(inv);
+    f3 ad = abs3(dir);
+    int kz = (ad.x > ad.y && ad.x > ad.z) ? 0 : (ad.y > ad.z ? 1 : 2);
+    int kx = kz == 2 ? 0 : kz + 1, ky = kx == 2 ? 0 : kx + 1;
+    if (comp(dir, kz) < 0.0f) { int t = kx; kx = ky; ky = t; }
+    float dz = comp(dir, kz);
+    f3 shear = mk3(comp(dir, kx) / dz, comp(dir, ky) / dz, 1.0f / dz);
+    // ray origin permuted once (the triangle test permutes v - org; permuting both is the same values)
+    float committedT = tmax;
+    bool haveHit = false;
+    uint32_t hitGeom = 0xffffffffu, hitPrim = 0xffffffffu;
+    float hb1 = 0.0f, hb2 = 0.0f;
+    uint32_t trisTested = 0, boxesTested = 0;
+
+    uint32_t stack[TB_STACK_DEPTH];
+    int sp = 0;
+    {
+        float unusedT;
+        if (slab(unusedT, committedT, oinv, inv, ainv, bvh.root.c[0], bvh.root.c[1], bvh.root.c[2], bvh.root.h[0], bvh.root.h[1], bvh.root.h[2]))
+            stack[sp++] = (bvh.root.flags & 0x80000000u) ? (0x80000000u | (bvh.root.flags & 0x3fffffffu)) : 0u;
+    }
+    const float4* __restrict__ pairs = (const float4*)bvh.pairs;
+    const float4* __restrict__ tris = (const float4*)bvh.tris;
+    while (sp > 0) {
+        uint32_t ref = stack[--sp];
+        if (ref & 0x80000000u) {
+            uint32_t slot = ref & 0x3fffffffu;
+            float4 q0 = __ldg(tris + 3 * (size_t)slot), q1 = __ldg(tris + 3 * (size_t)slot + 1), q2 = __ldg(tris + 3 * (size_t)slot + 2);
+            trisTested++;
+            f3 v0 = mk3(q0.x, q0.y, q0.z) - org, v1 = mk3(q1.x, q1.y, q1.z) - org, v2 = mk3(q2.x, q2.y, q2.z) - org;
+            float Ax = comp(v0, kx), Ay = comp(v0, ky), Az = comp(v0, kz);
+            float Bx = comp(v1, kx), By = comp(v1, ky), Bz = comp(v1, kz);
+            float Cx = comp(v2, kx), Cy = comp(v2, ky), Cz = comp(v2, kz);
+            Ax = Ax - shear.x * Az; Ay = Ay - shear.y * Az;
+            Bx = Bx - shear.x * Bz; By = By - shear.y * Bz;
+            Cx = Cx - shear.x * Cz; Cy = Cy - shear.y * Cz;
+            float U = Cx * By - Cy * Bx;
+            float V = Ax * Cy - Ay * Cx;
+            float W = Bx * Ay - By * Ax;
+            float det = (U + V) + W;
+            bool ok = !((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) && det != 0.0f;
+            if (ok) {
+                Az = shear.z * Az; Bz = shear.z * Bz; Cz = shear.z * Cz;
+                float T = (U * Az + V * Bz) + W * Cz;
+                float sct = fabsf(T);
+                if ((T > 0.0f) != (det > 0.0f)) sct = -sct;
+                if (!(sct < 0.0f || sct > committedT * fabsf(det))) {
+                    float rcpDet = 1.0f / det;
+                    float t0 = T * rcpDet;
+                    uint32_t g = __float_as_uint(q0.w), p = __float_as_uint(q1.w);
+                    bool closer = t0 < committedT;
+                    bool tie = haveHit && t0 == committedT && (g < hitGeom || (g == hitGeom && p < hitPrim));
+                    if ((closer || tie) && t0 > tmin) {
+                        committedT = t0; hb1 = V * rcpDet; hb2 = W * rcpDet; hitGeom = g; hitPrim = p; haveHit = true;
+                    }
+                }
+            }
+        } else {
+            float4 a = __ldg(pairs + 4 * (size_t)ref), b = __ldg(pairs + 4 * (size_t)ref + 1);
+            float4 c = __ldg(pairs + 4 * (size_t)ref + 2), d = __ldg(pairs + 4 * (size_t)ref + 3);
+            float lt, rt;
+            bool lh = slab(lt, committedT, oinv, inv, ainv, a.x, a.y, a.z, b.x, b.y, b.z);
+            bool rh = slab(rt, committedT, oinv, inv, ainv, c.x, c.y, c.z, d.x, d.y, d.z);
+            boxesTested += 2;
+            uint32_t lref = __float_as_uint(a.w), rref = __float_as_uint(b.w);
+            if (lh && rh) {
+                bool rightFirst = rt < lt;
+                if (sp + 2 <= TB_STACK_DEPTH) {
+                    stack[sp++] = rightFirst ? lref : rref;
+                    stack[sp++] = rightFirst ? rref : lref;
+                }
+            } else if (lh || rh) {
+                if (sp + 1 <= TB_STACK_DEPTH) stack[sp++] = rh ? rref : lref;
+            }
+        }
+    }
+    out.tris = trisTested;
+    out.boxes = boxesTested;
+    if (haveHit && committedT < tmax) { out.t = committedT; out.b1 = hb1; out.b2 = hb2; out.prim = hitPrim; out.geom = hitGeom; }
+    else { out.t = -1.0f; out.b1 = out.b2 = 0.0f; out.prim = out.geom = 0xffffffffu; }
+}
+
+} // namespace tbd

@@ -1,0 +1,616 @@
+// api.cpp — the C ABI (include/tracerboy_b200.h): host-side mirror of `class TracerBoy`
+// (TracerBoy/TracerBoy.h:158-397) and of the fallback layer's build/trace interface
+// (D3D12RaytracingFallback.h:76-173) on top of the CUDA kernels. There is no CPU
+// fallback: every compute entry point needs a CUDA device and fails with TB_ERR_CUDA
+// when none is present.
+#include <dlfcn.h>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../cuda/pathtrace.h"
+#include "scene.h"
+#include "tracerboy_b200.h"
+
+using namespace tbd;
+
+struct TbHandle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    tb::Scene scene;
+    bool sceneLoaded = false;
+    // device scene
+    DeviceScene dscene;
+    std::vector<void*> sceneAllocs;
+    DeviceBvh bvh;
+    double bvhBuildMs = 0.0;
+    // render state
+    PathState st;
+    std::vector<void*> frameAllocs;
+    float* resolved = nullptr;
+    uint32_t width = 0, height = 0;
+    TbCamera camera{};
+    uint32_t samplesRendered = 0; // local samples since the last invalidate
+    uint32_t shardOffset = 0, shardStride = 1;
+    int selX = -1, selY = -1;
+    LaunchCounter lc;
+    double deviceMs = 0.0;
+    uint64_t pathsStarted = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::chrono::steady_clock::time_point renderStart;
+    bool timing = false;
+    std::mutex statusLock;
+    TbSceneLoadStatus status{TB_LOAD_IDLE, 0, 0};
+    std::vector<uint8_t> blueNoiseHost;
+};
+
+static std::string g_createError;
+static std::string g_libDir;
+
+static int fail(TbHandle* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_createError = msg;
+    return code;
+}
+#define CUDA_OK(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(h, TB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
+
+static std::string lib_dir() {
+    if (!g_libDir.empty()) return g_libDir;
+    Dl_info info;
+    if (dladdr((void*)&lib_dir, &info) && info.dli_fname) {
+        std::string p(info.dli_fname);
+        size_t s = p.find_last_of('/');
+        g_libDir = s == std::string::npos ? "." : p.substr(0, s);
+    } else g_libDir = ".";
+    return g_libDir;
+}
+
+template <class T>
+static cudaError_t upload(TbHandle* h, std::vector<void*>& owner, const T* src, size_t count, const T** dst) {
+    void* p = nullptr;
+    size_t bytes = sizeof(T) * (count ? count : 1);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+    owner.push_back(p);
+    if (count) e = cudaMemcpyAsync(p, src, sizeof(T) * count, cudaMemcpyHostToDevice, h->stream);
+    *dst = (const T*)p;
+    return e;
+}
+
+static void free_list(std::vector<void*>& v) { for (void* p : v) cudaFree(p); v.clear(); }
+
+static void free_scene(TbHandle* h) {
+    free_list(h->sceneAllocs);
+    if (h->bvh.ref) cudaFree(h->bvh.ref);
+    if (h->bvh.pairs) cudaFree(h->bvh.pairs);
+    if (h->bvh.tris) cudaFree(h->bvh.tris);
+    h->bvh = DeviceBvh();
+    h->dscene = DeviceScene();
+    h->sceneLoaded = false;
+}
+
+static void free_frame(TbHandle* h) {
+    free_list(h->frameAllocs);
+    h->st = PathState();
+    h->resolved = nullptr;
+    h->width = h->height = 0;
+}
+
+// Halton, RayGenCommon.h:49-60 (per-frame constant, evaluated on the host in IEEE binary32)
+static float halton(int b, int i) {
+    float r = 0.0f, f = 1.0f;
+    while (i > 0) {
+        f = f / (float)b;
+        r = r + f * (float)(i % b);
+        i = (int)floorf((float)i / (float)b);
+    }
+    return r;
+}
+
+static void set_status(TbHandle* h, uint32_t state, uint32_t loaded, uint32_t total) {
+    std::lock_guard<std::mutex> g(h->statusLock);
+    h->status.State = state; h->status.InstancesLoaded = loaded; h->status.TotalInstances = total;
+}
+
+// Uploads h->scene and builds the BVH.
+static int upload_and_build(TbHandle* h, uint32_t flags) {
+    tb::Scene& s = h->scene;
+    if (s.numTriangles() == 0) return fail(h, TB_ERR_INVALID_ARG, "scene has no triangles");
+    if (2ull * s.numTriangles() - 1 > (1ull << 30)) return fail(h, TB_ERR_INVALID_ARG, "too many triangles (30-bit node indices)");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    free_scene(h);
+    set_status(h, TB_RECORDING_DEVICE_WORK, (uint32_t)s.geoms.size(), (uint32_t)s.geoms.size());
+    DeviceScene& d = h->dscene;
+    CUDA_OK(h, upload(h, h->sceneAllocs, s.geoms.data(), s.geoms.size(), &d.geoms));
+    CUDA_OK(h, upload(h, h->sceneAllocs, (const float*)s.positions.data(), s.positions.size() * 3, &d.positions));
+    CUDA_OK(h, upload(h, h->sceneAllocs, s.vertices.data(), s.vertices.size(), &d.vertices));
+    CUDA_OK(h, upload(h, h->sceneAllocs, s.indices.data(), s.indices.size(), &d.indices));
+    CUDA_OK(h, upload(h, h->sceneAllocs, s.materials.data(), s.materials.size(), &d.materials));
+    CUDA_OK(h, upload(h, h->sceneAllocs, s.lights.data(), s.lights.size(), &d.lights));
+    CUDA_OK(h, upload(h, h->sceneAllocs, s.textures.data(), s.textures.size(), &d.textures));
+    std::vector<DeviceScene::ImageRef> refs(s.images.size());
+    for (size_t i = 0; i < s.images.size(); i++) {
+        const uint8_t* p = nullptr;
+        CUDA_OK(h, upload(h, h->sceneAllocs, s.images[i].data.data(), s.images[i].data.size(), &p));
+        refs[i] = {p, s.images[i].width, s.images[i].height, s.images[i].format};
+    }
+    CUDA_OK(h, upload(h, h->sceneAllocs, refs.data(), refs.size(), &d.images));
+    CUDA_OK(h, upload(h, h->sceneAllocs, h->blueNoiseHost.data(), h->blueNoiseHost.size(), &d.blueNoise));
+    d.numGeoms = (uint32_t)s.geoms.size(); d.numMaterials = (uint32_t)s.materials.size();
+    d.numLights = (uint32_t)s.lights.size(); d.numTextures = (uint32_t)s.textures.size(); d.numImages = (uint32_t)s.images.size();
+    d.envImage = s.envImage; d.flipTextureUVs = s.flipTextureUVs;
+    for (int r = 0; r < 3; r++) { d.envTransform[r][0] = s.envTransform[r].x; d.envTransform[r][1] = s.envTransform[r].y; d.envTransform[r][2] = s.envTransform[r].z; d.envTransform[r][3] = s.envTransform[r].w; }
+    d.envColorScale[0] = s.envColorScale.x; d.envColorScale[1] = s.envColorScale.y; d.envColorScale[2] = s.envColorScale.z;
+    // per-geometry triangle prefix (LoadPrimitivesPass.cpp:70-166 walks the descs in order)
+    std::vector<uint32_t> prefix(s.geoms.size());
+    uint32_t n = 0;
+    for (size_t g = 0; g < s.geoms.size(); g++) { prefix[g] = n; n += s.geoms[g].IndexCount / 3; }
+    const uint32_t* dPrefix = nullptr;
+    CUDA_OK(h, upload(h, h->sceneAllocs, prefix.data(), prefix.size(), &dPrefix));
+    h->bvh.refBytes = bvh_ref_bytes(n);
+    CUDA_OK(h, cudaMalloc((void**)&h->bvh.ref, h->bvh.refBytes));
+    CUDA_OK(h, cudaMalloc((void**)&h->bvh.pairs, sizeof(PairNode) * (size_t)(n > 1 ? n - 1 : 1)));
+    CUDA_OK(h, cudaMalloc((void**)&h->bvh.tris, sizeof(WideTri) * (size_t)n));
+    int passes = (flags & TB_BVH_BUILD_PREFER_FAST_BUILD) ? 0 : ((flags & TB_BVH_BUILD_PREFER_FAST_TRACE) ? 3 : 1); // TreeletReorder.cpp:63-78
+    set_status(h, TB_WAITING_ON_GPU, (uint32_t)s.geoms.size(), (uint32_t)s.geoms.size());
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    CUDA_OK(h, cudaEventRecord(h->ev0, h->stream));
+    CUDA_OK(h, build_bvh(d.geoms, dPrefix, d.numGeoms, d.positions, d.indices, n, passes, h->bvh, h->stream, h->lc));
+    CUDA_OK(h, cudaEventRecord(h->ev1, h->stream));
+    CUDA_OK(h, cudaEventSynchronize(h->ev1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->bvhBuildMs = ms;
+    h->camera = s.camera;
+    h->sceneLoaded = true;
+    h->samplesRendered = 0;
+    set_status(h, TB_LOAD_FINISHED, (uint32_t)s.geoms.size(), (uint32_t)s.geoms.size());
+    return TB_OK;
+}
+
+extern "C" {
+
+TB_API const char* tb_version(void) { return "tracerboy_b200 0.1 (sm_100a)"; }
+
+TB_API const char* tb_last_error(TbHandle* h) { return h ? h->err.c_str() : g_createError.c_str(); }
+
+TB_API int tb_create(int device, TbHandle** out) {
+    if (!out) return fail(nullptr, TB_ERR_INVALID_ARG, "out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, TB_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, TB_ERR_INVALID_ARG, "device ordinal out of range");
+    TbHandle* h = new TbHandle();
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, TB_ERR_CUDA, "cannot initialise CUDA stream/events");
+    }
+    // blue noise (TracerBoy.cpp:2126-2134): LDR_RGBA_0/1 decoded to raw RGBA8
+    h->blueNoiseHost.assign(2 * 256 * 256 * 4, 0);
+    std::string bn = lib_dir() + "/../data/bluenoise_rgba8_256.bin";
+    FILE* f = fopen(bn.c_str(), "rb");
+    if (!f || fread(h->blueNoiseHost.data(), 1, h->blueNoiseHost.size(), f) != h->blueNoiseHost.size()) {
+        if (f) fclose(f);
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return fail(nullptr, TB_ERR_IO, "cannot read blue-noise table " + bn);
+    }
+    fclose(f);
+    *out = h;
+    return TB_OK;
+}
+
+TB_API void tb_destroy(TbHandle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_frame(h);
+    free_scene(h);
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+static int load_host_scene(TbHandle* h, tb::Scene& s, const char* path) {
+    std::string p(path), err;
+    auto ends = [&](const char* suf) { size_t n = strlen(suf); return p.size() >= n && p.compare(p.size() - n, n, suf) == 0; };
+    if (p.rfind("synthetic:", 0) == 0) {
+        if (!tb::make_synthetic(s, p, err)) return fail(h, TB_ERR_INVALID_ARG, err);
+    } else if (ends(".tbscene")) {
+        if (!tb::load_tbscene(s, p, err)) return fail(h, TB_ERR_IO, err);
+    } else if (ends(".pbrt") || ends(".pbf")) {
+        // optional importer built from the reference's vendored pbrt-parser
+        std::string so = lib_dir() + "/libtb_pbrtimport.so";
+        void* lib = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (!lib) return fail(h, TB_ERR_NOT_IMPL, "PBRT import needs " + so + " (built only when the pbrt-parser sources are available)");
+        typedef int (*ImportFn)(const char*, void*, char*, size_t);
+        ImportFn fn = (ImportFn)dlsym(lib, "tb_pbrt_import");
+        char buf[1024] = {0};
+        if (!fn || fn(path, &s, buf, sizeof(buf)) != 0) return fail(h, TB_ERR_IO, std::string("pbrt import failed: ") + buf);
+    } else {
+        // AssimpImporter (fbx/obj/...) links a Windows-only binary in the reference; not available
+        return fail(h, TB_ERR_NOT_IMPL, "unsupported scene type: " + p);
+    }
+    return TB_OK;
+}
+
+TB_API int tb_load_scene_ex(TbHandle* h, const char* path, uint32_t flags) {
+    if (!h || !path) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    set_status(h, TB_LOADING_PBRT, 0, 0);
+    int rc = load_host_scene(h, h->scene, path);
+    if (rc != TB_OK) { set_status(h, TB_LOAD_FAILED, 0, 0); return rc; }
+    set_status(h, TB_LOADING_HOST, 0, (uint32_t)h->scene.geoms.size());
+    rc = upload_and_build(h, flags);
+    if (rc != TB_OK) set_status(h, TB_LOAD_FAILED, 0, 0);
+    return rc;
+}
+TB_API int tb_load_scene(TbHandle* h, const char* path) { return tb_load_scene_ex(h, path, TB_BVH_BUILD_PREFER_FAST_TRACE); }
+
+TB_API int tb_convert_scene(const char* inPath, const char* outTbscene, char* err, size_t errCap) {
+    TbHandle tmp; // host-only use
+    tb::Scene s;
+    int rc = load_host_scene(&tmp, s, inPath);
+    std::string e = tmp.err;
+    if (rc == TB_OK && !tb::save_tbscene(s, outTbscene, e)) rc = TB_ERR_IO;
+    if (rc != TB_OK && err && errCap) { strncpy(err, e.c_str(), errCap - 1); err[errCap - 1] = 0; }
+    return rc;
+}
+
+TB_API int tb_get_load_status(TbHandle* h, TbSceneLoadStatus* out) {
+    if (!h || !out) return TB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(h->statusLock);
+    *out = h->status;
+    return TB_OK;
+}
+
+TB_API int tb_save_scene(TbHandle* h, const char* path) {
+    if (!h || !path) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (!h->sceneLoaded) return fail(h, TB_ERR_STATE, "no scene loaded");
+    std::string err;
+    if (!tb::save_tbscene(h->scene, path, err)) return fail(h, TB_ERR_IO, err);
+    return TB_OK;
+}
+
+TB_API int tb_get_scene_info(TbHandle* h, TbSceneInfo* o) {
+    if (!h || !o) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (!h->sceneLoaded) return fail(h, TB_ERR_STATE, "no scene loaded");
+    o->NumGeometries = (uint32_t)h->scene.geoms.size(); o->NumTriangles = h->scene.numTriangles();
+    o->NumVertices = (uint32_t)h->scene.positions.size(); o->NumMaterials = (uint32_t)h->scene.materials.size();
+    o->NumLights = (uint32_t)h->scene.lights.size(); o->NumTextures = (uint32_t)h->scene.textures.size();
+    o->NumImages = (uint32_t)h->scene.images.size(); o->HasEnvironmentMap = h->scene.envImage >= 0;
+    return TB_OK;
+}
+
+TB_API int tb_get_bvh_size(TbHandle* h, uint64_t* bytes) {
+    if (!h || !bytes) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (!h->sceneLoaded) return fail(h, TB_ERR_STATE, "no scene loaded");
+    *bytes = h->bvh.refBytes;
+    return TB_OK;
+}
+TB_API int tb_get_bvh(TbHandle* h, void* dst, uint64_t bytes) {
+    if (!h || !dst) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (!h->sceneLoaded) return fail(h, TB_ERR_STATE, "no scene loaded");
+    if (bytes < h->bvh.refBytes) return fail(h, TB_ERR_INVALID_ARG, "destination too small");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, cudaMemcpyAsync(dst, h->bvh.ref, h->bvh.refBytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return TB_OK;
+}
+TB_API int tb_get_bvh_build_ms(TbHandle* h, double* ms) {
+    if (!h || !ms) return TB_ERR_INVALID_ARG;
+    *ms = h->bvhBuildMs;
+    return TB_OK;
+}
+
+TB_API int tb_get_default_settings(TbOutputSettings* s) {
+    if (!s) return TB_ERR_INVALID_ARG;
+    memset(s, 0, sizeof(*s));
+    s->OutputType = TB_OUTPUT_LIT; s->EnableNormalMaps = 0; s->RenderMode = TB_RENDER_UNBIASED;
+    s->SampleLimit = 0; s->TimeLimitInSeconds = 0.0f; s->DebugValue = 1.0f; s->DebugValue2 = 1.0f;
+    s->DOFFocalDistance = 0.0f; s->ApertureWidth = 0.075f; s->FilterType = TB_FILTER_BOX; s->FilterWidth = 1.0f;
+    s->FireflyClampValue = 0.0f; s->MaxZ = 10000.0f; s->ConvergencePercentage = 0.001f;
+    s->EnableNextEventEstimation = 1; s->EnableSamplingImportanceResampling = 0; s->EnableBlueNoise = 1; s->MaxBounces = 6;
+    return TB_OK;
+}
+
+TB_API int tb_get_camera(TbHandle* h, TbCamera* c) {
+    if (!h || !c) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    *c = h->camera;
+    return TB_OK;
+}
+TB_API int tb_set_camera(TbHandle* h, const TbCamera* c) {
+    if (!h || !c) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    h->camera = *c;
+    h->samplesRendered = 0; // m_bInvalidateHistory
+    return TB_OK;
+}
+
+TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
+    if (!h || w == 0 || hh == 0 || (uint64_t)w * hh > (1ull << 28)) return fail(h, TB_ERR_INVALID_ARG, "bad resolution");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    if (w == h->width && hh == h->height) return TB_OK;
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    free_frame(h);
+    size_t n = (size_t)w * hh;
+    auto alloc = [&](void** p, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) { h->frameAllocs.push_back(*p); e = cudaMemsetAsync(*p, 0, bytes, h->stream); }
+        return e;
+    };
+    PathState& st = h->st;
+    CUDA_OK(h, alloc((void**)&st.rayO, 16 * n)); CUDA_OK(h, alloc((void**)&st.rayD, 16 * n));
+    CUDA_OK(h, alloc((void**)&st.thr, 16 * n)); CUDA_OK(h, alloc((void**)&st.col, 16 * n));
+    CUDA_OK(h, alloc((void**)&st.hit, 16 * n)); CUDA_OK(h, alloc((void**)&st.hitGeom, 4 * n));
+    CUDA_OK(h, alloc((void**)&st.neighbor, 16 * n)); CUDA_OK(h, alloc((void**)&st.neighborDir, 16 * n));
+    CUDA_OK(h, alloc((void**)&st.queue[0], 4 * n)); CUDA_OK(h, alloc((void**)&st.queue[1], 4 * n));
+    CUDA_OK(h, alloc((void**)&st.queueCount, 16));
+    CUDA_OK(h, alloc((void**)&st.accum, 16 * n)); CUDA_OK(h, alloc((void**)&st.jittered, 16 * n));
+    CUDA_OK(h, alloc((void**)&st.aovAlbedo, 16 * n)); CUDA_OK(h, alloc((void**)&st.aovNormal, 16 * n));
+    CUDA_OK(h, alloc((void**)&st.aovEmissive, 16 * n));
+    CUDA_OK(h, alloc((void**)&st.aovWorldPos[0], 16 * n)); CUDA_OK(h, alloc((void**)&st.aovWorldPos[1], 16 * n));
+    CUDA_OK(h, alloc((void**)&st.aovDepth, 4 * n));
+    CUDA_OK(h, alloc((void**)&st.primaryHit, 8 * n)); CUDA_OK(h, alloc((void**)&st.counters, 8 * n));
+    CUDA_OK(h, alloc((void**)&st.stats, 32)); CUDA_OK(h, alloc((void**)&st.readbackStats, sizeof(TbReadbackStats)));
+    CUDA_OK(h, alloc((void**)&h->resolved, 12 * n));
+    h->width = w; h->height = hh;
+    h->samplesRendered = 0;
+    return TB_OK;
+}
+
+TB_API int tb_select_pixel(TbHandle* h, int x, int y) {
+    if (!h) return TB_ERR_INVALID_ARG;
+    h->selX = x; h->selY = y;
+    return TB_OK;
+}
+
+TB_API int tb_get_stats(TbHandle* h, TbReadbackStats* out) {
+    if (!h || !out) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (!h->st.readbackStats) return fail(h, TB_ERR_STATE, "no frame buffers");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, cudaMemcpyAsync(out, h->st.readbackStats, sizeof(*out), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    out->ActivePixels = h->width * h->height;
+    out->ActiveWaves = (h->width * h->height + 63) / 64;
+    return TB_OK;
+}
+
+TB_API int tb_render(TbHandle* h, const TbOutputSettings* s, uint32_t nSamples, float time) {
+    if (!h || !s) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (!h->sceneLoaded) return fail(h, TB_ERR_STATE, "tb_render before tb_load_scene");
+    if (!h->width) return fail(h, TB_ERR_STATE, "tb_render before tb_resize");
+    if (s->MaxBounces < 0 || s->MaxBounces > 255) return fail(h, TB_ERR_INVALID_ARG, "MaxBounces must be in [0,255]");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    if (h->samplesRendered == 0) { h->renderStart = std::chrono::steady_clock::now(); }
+    CUDA_OK(h, cudaEventRecord(h->ev0, h->stream));
+    for (uint32_t i = 0; i < nSamples; i++) {
+        // sample / time limits, TracerBoy.cpp:2679-2682
+        if (s->SampleLimit > 0 && (int)h->samplesRendered >= s->SampleLimit) break;
+        if (s->TimeLimitInSeconds > 0.0f &&
+            std::chrono::duration<float>(std::chrono::steady_clock::now() - h->renderStart).count() >= s->TimeLimitInSeconds) break;
+        FrameConstants fc;
+        memset(&fc, 0, sizeof(fc));
+        fc.settings = *s;
+        fc.camera = h->camera;
+        fc.time = time;
+        fc.frame = h->shardOffset + h->samplesRendered * h->shardStride; // GlobalFrameCount
+        fc.width = h->width; fc.height = h->height;
+        fc.selectedX = h->selX; fc.selectedY = h->selY;
+        fc.halton2 = halton(2, (int)fc.frame);
+        fc.halton3 = halton(3, (int)fc.frame);
+        fc.clearAccum = h->samplesRendered == 0;
+        CUDA_OK(h, render_frame(h->bvh, h->dscene, fc, h->st, h->stream, h->lc));
+        h->samplesRendered++;
+        h->pathsStarted += (uint64_t)h->width * h->height;
+    }
+    CUDA_OK(h, cudaEventRecord(h->ev1, h->stream));
+    CUDA_OK(h, cudaEventSynchronize(h->ev1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->deviceMs += ms;
+    CUDA_OK(h, cudaGetLastError());
+    return TB_OK;
+}
+
+TB_API int tb_samples_rendered(TbHandle* h, uint32_t* out) {
+    if (!h || !out) return TB_ERR_INVALID_ARG;
+    *out = h->samplesRendered;
+    return TB_OK;
+}
+TB_API int tb_invalidate_history(TbHandle* h) {
+    if (!h) return TB_ERR_INVALID_ARG;
+    h->samplesRendered = 0;
+    return TB_OK;
+}
+TB_API int tb_set_frame_shard(TbHandle* h, uint32_t offset, uint32_t stride) {
+    if (!h || stride == 0 || offset >= stride) return fail(h, TB_ERR_INVALID_ARG, "need offset < stride");
+    h->shardOffset = offset; h->shardStride = stride;
+    h->samplesRendered = 0;
+    return TB_OK;
+}
+
+static int buffer_info(TbHandle* h, uint32_t kind, void** p, uint64_t* bytes) {
+    size_t n = (size_t)h->width * h->height;
+    PathState& st = h->st;
+    switch (kind) {
+    case TB_BUF_ACCUM_RGBW: *p = st.accum; *bytes = 16 * n; break;
+    case TB_BUF_JITTERED_RGBW: *p = st.jittered; *bytes = 16 * n; break;
+    case TB_BUF_RESOLVED_RGB: *p = h->resolved; *bytes = 12 * n; break;
+    case TB_BUF_AOV_NORMAL: *p = st.aovNormal; *bytes = 16 * n; break;
+    case TB_BUF_AOV_WORLDPOS: {
+        uint32_t last = h->shardOffset + (h->samplesRendered ? h->samplesRendered - 1 : 0) * h->shardStride;
+        *p = st.aovWorldPos[last & 1]; *bytes = 16 * n; break;
+    }
+    case TB_BUF_AOV_DEPTH: *p = st.aovDepth; *bytes = 4 * n; break;
+    case TB_BUF_AOV_ALBEDO: *p = st.aovAlbedo; *bytes = 16 * n; break;
+    case TB_BUF_AOV_EMISSIVE: *p = st.aovEmissive; *bytes = 16 * n; break;
+    case TB_BUF_PRIMARY_HIT_IDS: *p = st.primaryHit; *bytes = 8 * n; break;
+    case TB_BUF_RAY_COUNTERS: *p = st.counters; *bytes = 8 * n; break;
+    default: return fail(h, TB_ERR_INVALID_ARG, "unknown buffer kind");
+    }
+    return TB_OK;
+}
+
+TB_API int tb_buffer_size(TbHandle* h, uint32_t kind, uint64_t* bytes) {
+    if (!h || !bytes) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (!h->width) return fail(h, TB_ERR_STATE, "no frame buffers (tb_resize)");
+    void* p;
+    return buffer_info(h, kind, &p, bytes);
+}
+
+TB_API int tb_device_buffer(TbHandle* h, uint32_t kind, void** devPtr, uint64_t* bytes) {
+    if (!h || !devPtr || !bytes) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (!h->width) return fail(h, TB_ERR_STATE, "no frame buffers (tb_resize)");
+    int rc = buffer_info(h, kind, devPtr, bytes);
+    if (rc == TB_OK && kind == TB_BUF_RESOLVED_RGB) {
+        CUDA_OK(h, cudaSetDevice(h->device));
+        CUDA_OK(h, resolve_rgb(h->st.accum, h->resolved, h->width * h->height, h->stream, h->lc));
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    }
+    return rc;
+}
+
+TB_API int tb_readback(TbHandle* h, uint32_t kind, void* dst, uint64_t bytes) {
+    if (!h || !dst) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (!h->width) return fail(h, TB_ERR_STATE, "no frame buffers (tb_resize)");
+    void* p; uint64_t need;
+    int rc = buffer_info(h, kind, &p, &need);
+    if (rc != TB_OK) return rc;
+    if (bytes < need) return fail(h, TB_ERR_INVALID_ARG, "destination too small");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    if (kind == TB_BUF_RESOLVED_RGB) CUDA_OK(h, resolve_rgb(h->st.accum, h->resolved, h->width * h->height, h->stream, h->lc));
+    CUDA_OK(h, cudaMemcpyAsync(dst, p, need, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return TB_OK;
+}
+
+TB_API int tb_get_render_stats(TbHandle* h, TbRenderStats* out) {
+    if (!h || !out) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    memset(out, 0, sizeof(*out));
+    if (h->st.stats) {
+        unsigned long long s[3];
+        CUDA_OK(h, cudaSetDevice(h->device));
+        CUDA_OK(h, cudaMemcpyAsync(s, h->st.stats, sizeof(s), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+        out->RaysTraced = s[0]; out->BoxesTested = s[1]; out->TrianglesTested = s[2];
+    }
+    out->PathsStarted = h->pathsStarted;
+    out->KernelLaunches = h->lc.count;
+    out->DeviceMilliseconds = h->deviceMs;
+    return TB_OK;
+}
+TB_API int tb_reset_render_stats(TbHandle* h) {
+    if (!h) return TB_ERR_INVALID_ARG;
+    if (h->st.stats) { CUDA_OK(h, cudaSetDevice(h->device)); CUDA_OK(h, cudaMemsetAsync(h->st.stats, 0, 32, h->stream)); }
+    h->pathsStarted = 0; h->lc.count = 0; h->deviceMs = 0.0;
+    return TB_OK;
+}
+TB_API int tb_synchronize(TbHandle* h) {
+    if (!h) return TB_ERR_INVALID_ARG;
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return TB_OK;
+}
+
+TB_API int tb_is_material_id_valid(TbHandle* h, int id) { return h && h->sceneLoaded && id >= 0 && id < (int)h->scene.materials.size(); }
+TB_API int tb_get_material(TbHandle* h, int id, TbMaterial* out, char* name, uint32_t cap) {
+    if (!h || !out) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (!tb_is_material_id_valid(h, id)) return fail(h, TB_ERR_INVALID_ARG, "invalid material id");
+    *out = h->scene.materials[id];
+    if (name && cap) { strncpy(name, id < (int)h->scene.materialNames.size() ? h->scene.materialNames[id].c_str() : "", cap - 1); name[cap - 1] = 0; }
+    return TB_OK;
+}
+TB_API int tb_set_material(TbHandle* h, int id, const TbMaterial* m) {
+    if (!h || !m) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (!tb_is_material_id_valid(h, id)) return fail(h, TB_ERR_INVALID_ARG, "invalid material id");
+    h->scene.materials[id] = *m;
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, cudaMemcpyAsync((void*)(h->dscene.materials + id), m, sizeof(*m), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    h->samplesRendered = 0;
+    return TB_OK;
+}
+
+TB_API int tb_bvh_prebuild_info(const TbGeometryDesc* geoms, uint32_t n, TbPrebuildInfo* out) {
+    if (!geoms || !out) return TB_ERR_INVALID_ARG;
+    uint64_t tris = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (geoms[i].Indices == nullptr && geoms[i].IndexFormat != 0) return TB_ERR_INVALID_ARG; // LoadPrimitivesPass.cpp:73-76
+        uint32_t vc = geoms[i].IndexFormat == 0 ? geoms[i].VertexCount : geoms[i].IndexCount;
+        tris += vc / 3;
+    }
+    if (tris == 0) { memset(out, 0, sizeof(*out)); return TB_OK; }
+    out->ResultDataMaxSizeInBytes = bvh_ref_bytes((uint32_t)tris);
+    // scratch: unsorted prims+meta, codes/order double buffers, hierarchy, AABBs, counters
+    out->ScratchDataSizeInBytes = tris * (40 + 12 + 16 + 4 + 4) + (2 * tris) * (12 + 24);
+    out->UpdateScratchDataSizeInBytes = 0;
+    return TB_OK;
+}
+
+TB_API int tb_bvh_build(TbHandle* h, const TbGeometryDesc* geoms, uint32_t n, uint32_t flags) {
+    if (!h || !geoms || n == 0) return fail(h, TB_ERR_INVALID_ARG, "null/empty geometry list");
+    tb::Scene s;
+    s.materials.push_back(tb::default_material({0, 0, 0}));
+    s.materials[0].albedo = {0.5f, 0.5f, 0.5f};
+    s.materials[0].Flags |= TB_NO_SPECULAR_MATERIAL_FLAG | TB_NO_ALPHA_MATERIAL_FLAG;
+    s.materialNames.push_back("default");
+    for (uint32_t g = 0; g < n; g++) {
+        const TbGeometryDesc& G = geoms[g];
+        if (!G.Positions || G.PositionStrideBytes < 12 || G.PositionStrideBytes % 4) return fail(h, TB_ERR_INVALID_ARG, "bad vertex buffer");
+        if (G.Indices == nullptr && G.IndexFormat != 0) return fail(h, TB_ERR_INVALID_ARG, "If the index buffer is null, the index format must be 0");
+        if (G.IndexFormat != 0 && G.IndexFormat != 2 && G.IndexFormat != 4) return fail(h, TB_ERR_INVALID_ARG, "index format must be 0, 2 or 4");
+        std::vector<TbFloat3> pos(G.VertexCount);
+        for (uint32_t v = 0; v < G.VertexCount; v++) {
+            const float* p = (const float*)((const uint8_t*)G.Positions + (size_t)v * G.PositionStrideBytes);
+            float x = p[0], y = p[1], z = p[2];
+            if (G.Transform3x4) { // TransformVertex, BottomLevelLoadTriangles.hlsli:83-86: mul(float3x4, float4(v,1))
+                const float* m = G.Transform3x4;
+                float tx = ((m[0] * x + m[1] * y) + m[2] * z) + m[3];
+                float ty = ((m[4] * x + m[5] * y) + m[6] * z) + m[7];
+                float tz = ((m[8] * x + m[9] * y) + m[10] * z) + m[11];
+                x = tx; y = ty; z = tz;
+            }
+            pos[v] = {x, y, z};
+        }
+        uint32_t count = G.IndexFormat == 0 ? G.VertexCount : G.IndexCount;
+        count -= count % 3;
+        std::vector<uint32_t> idx(count);
+        for (uint32_t i = 0; i < count; i++) {
+            uint32_t v = G.IndexFormat == 0 ? i : (G.IndexFormat == 2 ? ((const uint16_t*)G.Indices)[i] : ((const uint32_t*)G.Indices)[i]);
+            if (v >= G.VertexCount) return fail(h, TB_ERR_INVALID_ARG, "index out of range");
+            idx[i] = v;
+        }
+        uint32_t gi = tb::append_geometry(s, pos.data(), nullptr, nullptr, nullptr, G.VertexCount, idx.data(), count, 0);
+        s.geoms[gi].GeometryFlags = G.GeometryFlags;
+    }
+    h->scene = std::move(s);
+    return upload_and_build(h, flags);
+}
+
+TB_API int tb_trace_rays(TbHandle* h, const TbRay* rays, uint64_t n, TbHit* hits) {
+    if (!h || (n && (!rays || !hits))) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (!h->sceneLoaded) return fail(h, TB_ERR_STATE, "no acceleration structure");
+    if (n == 0) return TB_OK;
+    CUDA_OK(h, cudaSetDevice(h->device));
+    TbRay* dr = nullptr; TbHit* dh = nullptr;
+    CUDA_OK(h, cudaMalloc((void**)&dr, sizeof(TbRay) * n));
+    cudaError_t e = cudaMalloc((void**)&dh, sizeof(TbHit) * n);
+    if (e != cudaSuccess) { cudaFree(dr); return fail(h, TB_ERR_OOM, cudaGetErrorString(e)); }
+    e = cudaMemcpyAsync(dr, rays, sizeof(TbRay) * n, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = trace_rays(h->bvh, dr, n, dh, h->stream, h->lc);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hits, dh, sizeof(TbHit) * n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dr); cudaFree(dh);
+    if (e != cudaSuccess) return fail(h, TB_ERR_CUDA, cudaGetErrorString(e));
+    return TB_OK;
+}
+
+} // extern "C"

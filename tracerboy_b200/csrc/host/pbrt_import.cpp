@@ -1,0 +1,312 @@
+// pbrt_import.cpp — optional scene importer: pbrt::Scene (the reference's vendored
+// ingowald/pbrt-parser, a third-party dependency that is compiled in place from the
+// reference mount, never copied) -> tb::Scene. Restates the behaviour of
+// CreateMaterial (TracerBoy.cpp:273-505), TextureAllocator::CreateTexture (:177-251)
+// and LoadScene steps 2-4 (:1243-1272, 1356-1835, 1896-1944).
+//
+// Built into libtb_pbrtimport.so only when the parser sources are available; the main
+// library dlopen()s it for *.pbrt / *.pbf paths and reports TB_ERR_NOT_IMPL otherwise.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <unordered_map>
+#include "pbrtParser/Scene.h"
+#include "scene.h"
+
+using namespace tb;
+
+namespace {
+
+TbFloat3 cv3(const pbrt::vec3f& v) { return {v.x, v.y, v.z}; }
+float channel_average(const pbrt::vec3f& v) { return (float)((v.x + v.y + v.z) / 3.0); } // :117-120
+float specular_to_ior(float s) { return (float)((sqrt(s) + 1.0) / (1.0 - sqrt(s))); }   // :122-125
+
+struct Importer {
+    Scene& out;
+    std::string dir;
+    std::unordered_map<pbrt::Material*, uint32_t> matIndex; // MaterialTracker, TracerBoy.h:130-156
+    Importer(Scene& s, const std::string& d) : out(s), dir(d) {}
+
+    uint32_t add_material(pbrt::Material* key, const TbMaterial& m) {
+        uint32_t i = (uint32_t)out.materials.size();
+        matIndex[key] = i;
+        out.materials.push_back(m);
+        out.materialNames.push_back(key ? key->name : std::string());
+        return i;
+    }
+
+    uint32_t load_image(const std::string& fileName, bool* hasAlpha) {
+        // InitializeTexture, TracerBoy.cpp:2186-2246. Only Radiance .hdr (and the .pfm ->
+        // .hdr rename) is implemented; other formats went through DirectXTex/WIC.
+        std::string full = dir + fileName;
+        std::string ext = full.size() >= 4 ? full.substr(full.size() - 4) : "";
+        if (ext == ".pfm") { full = full.substr(0, full.size() - 4) + ".hdr"; ext = ".hdr"; }
+        if (ext != ".hdr") throw std::runtime_error("unsupported texture format (only .hdr): " + fileName);
+        Image img;
+        std::string err;
+        if (!load_hdr(full, img, err)) throw std::runtime_error(err);
+        if (hasAlpha) *hasAlpha = false;
+        out.images.push_back(std::move(img));
+        return (uint32_t)out.images.size() - 1;
+    }
+
+    // TextureAllocator::CreateTexture, TracerBoy.cpp:177-251
+    uint32_t create_texture(pbrt::Texture::SP tex, bool gammaCorrect = false, bool* hasAlpha = nullptr) {
+        if (!tex) return TB_INVALID_TEXTURE;
+        TbTextureData t;
+        memset(&t, 0, sizeof(t));
+        auto img = std::dynamic_pointer_cast<pbrt::ImageTexture>(tex);
+        auto chk = std::dynamic_pointer_cast<pbrt::CheckerTexture>(tex);
+        auto scl = std::dynamic_pointer_cast<pbrt::ScaleTexture>(tex);
+        if (img) {
+            t.TextureType = TB_IMAGE_TEXTURE_TYPE;
+            t.DescriptorHeapIndex = load_image(img->fileName, hasAlpha);
+            t.TextureFlags = 0; // float formats are not "normalized" => no gamma flag (:205-209)
+        } else if (chk) {
+            t.TextureType = TB_CHECKER_TEXTURE_TYPE;
+            t.UScale = chk->uScale;
+            t.VScale = chk->vScale;
+            t.CheckerColor1 = cv3(chk->tex1);
+            t.CheckerColor2 = cv3(chk->tex2);
+        } else if (scl) {
+            bool a1 = false, a2 = false;
+            if (std::dynamic_pointer_cast<pbrt::ScaleTexture>(scl->tex1) ||
+                std::dynamic_pointer_cast<pbrt::ScaleTexture>(scl->tex2))
+                throw std::runtime_error("nested scale textures are not supported (TracerBoy.cpp:233)");
+            t.TextureType = TB_SCALE_TEXTURE_TYPE;
+            t.TextureIndex1 = create_texture(scl->tex1, gammaCorrect, &a1);
+            t.TextureIndex2 = create_texture(scl->tex2, gammaCorrect, &a2);
+            t.ScaleColor1 = cv3(scl->scale1);
+            t.ScaleColor2 = cv3(scl->scale2);
+            if (hasAlpha) *hasAlpha = a1 || a2;
+        } else {
+            throw std::runtime_error("unsupported pbrt texture type: " + tex->toString());
+        }
+        out.textures.push_back(t);
+        return (uint32_t)out.textures.size() - 1;
+    }
+
+    // CreateMaterial, TracerBoy.cpp:273-505
+    TbMaterial create_material(pbrt::Material::SP mat, pbrt::Texture::SP* alphaTex, pbrt::vec3f emissive) {
+        TbMaterial m = default_material(cv3(emissive));
+        bool hasAlpha = false;
+        if (alphaTex) { m.alphaIndex = create_texture(*alphaTex); hasAlpha = true; }
+        auto substrate = std::dynamic_pointer_cast<pbrt::SubstrateMaterial>(mat);
+        auto uber = std::dynamic_pointer_cast<pbrt::UberMaterial>(mat);
+        auto mix = std::dynamic_pointer_cast<pbrt::MixMaterial>(mat);
+        auto mirror = std::dynamic_pointer_cast<pbrt::MirrorMaterial>(mat);
+        auto metal = std::dynamic_pointer_cast<pbrt::MetalMaterial>(mat);
+        auto fourier = std::dynamic_pointer_cast<pbrt::FourierMaterial>(mat);
+        auto glass = std::dynamic_pointer_cast<pbrt::GlassMaterial>(mat);
+        auto matte = std::dynamic_pointer_cast<pbrt::MatteMaterial>(mat);
+        auto disney = std::dynamic_pointer_cast<pbrt::DisneyMaterial>(mat);
+        auto plastic = std::dynamic_pointer_cast<pbrt::PlasticMaterial>(mat);
+        auto sss = std::dynamic_pointer_cast<pbrt::SubSurfaceMaterial>(mat);
+        auto translucent = std::dynamic_pointer_cast<pbrt::TranslucentMaterial>(mat);
+        if (!mat) {
+        } else if (disney) {
+            m.albedo = cv3(disney->color);
+            if (m.albedo.x > 0.7) m.albedo = {0.2f, 0.2f, 0.2f};
+            m.roughness = disney->roughness;
+            m.IOR = disney->eta;
+            if (disney->metallic > 0.5) m.Flags |= TB_METALLIC_MATERIAL_FLAG;
+            if (disney->specTrans > 0.001) {
+                m.Flags |= TB_SUBSURFACE_SCATTER_MATERIAL_FLAG;
+                m.absorption = {0, 0, 0};
+                m.roughness = 0;
+            }
+        } else if (uber) {
+            if (uber->map_kd) { bool a = false; m.albedoIndex = create_texture(uber->map_kd, true, &a); hasAlpha |= a; }
+            if (uber->map_normal) m.normalMapIndex = create_texture(uber->map_normal);
+            if (uber->map_emissive) m.emissiveIndex = create_texture(uber->map_emissive);
+            if (uber->map_specular) m.specularMapIndex = create_texture(uber->map_specular);
+            m.albedo = cv3(uber->kd);
+            m.roughness = uber->uRoughness > 0.0 ? uber->uRoughness : uber->roughness;
+            if (channel_average(uber->opacity) < 1.0) {
+                m.Flags |= TB_SUBSURFACE_SCATTER_MATERIAL_FLAG | TB_SINGLE_SIDED_MATERIAL_FLAG;
+                m.IOR = uber->index;
+                m.absorption = cv3(uber->kt);
+            }
+        } else if (mix) {
+            uint32_t i0 = add_material(mix->material0.get(), create_material(mix->material0, nullptr, emissive));
+            uint32_t i1 = add_material(mix->material1.get(), create_material(mix->material1, nullptr, emissive));
+            m.Flags = TB_MIX_MATERIAL_FLAG;
+            m.albedo = {(float)i0, (float)i1, channel_average(mix->amount)};
+        } else if (mirror) {
+            m.albedo = cv3(mirror->kr);
+            m.SpecularCoef = 1.0f;
+            m.roughness = 0.0f;
+            m.Flags |= TB_METALLIC_MATERIAL_FLAG;
+        } else if (metal) {
+            m.albedo = {1.0f, 1.0f, 1.0f};
+            m.IOR = channel_average(metal->eta);
+            m.roughness = metal->uRoughness;
+            m.Flags |= TB_METALLIC_MATERIAL_FLAG;
+        } else if (substrate) {
+            if (substrate->map_kd) { bool a = false; m.albedoIndex = create_texture(substrate->map_kd, false, &a); hasAlpha |= a; }
+            m.albedo = cv3(substrate->kd);
+            m.IOR = specular_to_ior(channel_average(substrate->ks));
+            m.SpecularCoef = channel_average(substrate->ks);
+            m.roughness = substrate->uRoughness;
+        } else if (glass) {
+            m.albedo = {0, 0, 0};
+            m.absorption = {0, 0, 0};
+            m.IOR = glass->index;
+            m.Flags |= TB_SUBSURFACE_SCATTER_MATERIAL_FLAG;
+        } else if (fourier) {
+            m.albedo = {0.6f, 0.6f, 0.6f};
+            m.roughness = 0.2f;
+        } else if (matte) {
+            m.roughness = matte->sigma;
+            if (matte->map_kd) { bool a = false; m.albedoIndex = create_texture(matte->map_kd, false, &a); hasAlpha |= a; }
+            m.albedo = cv3(matte->kd);
+            m.Flags |= TB_NO_SPECULAR_MATERIAL_FLAG;
+        } else if (plastic) {
+            m.roughness = plastic->roughness;
+            if (plastic->map_kd) { bool a = false; m.albedoIndex = create_texture(plastic->map_kd, false, &a); hasAlpha |= a; }
+            m.albedo = cv3(plastic->kd);
+            m.IOR = specular_to_ior(channel_average(plastic->ks));
+            m.SpecularCoef = channel_average(plastic->ks);
+        } else if (sss) {
+            throw std::runtime_error("pbrt 'subsurface' material is a HANDLE_FAILURE() in the reference (TracerBoy.cpp:451)");
+        } else if (translucent) {
+            if (translucent->map_kd) { bool a = false; m.albedoIndex = create_texture(translucent->map_kd, false, &a); hasAlpha |= a; }
+            else {
+                m.albedo = {0, 0, 0};
+                m.absorption = {0.001f, 0.001f, 0.001f};
+                m.Flags |= TB_SUBSURFACE_SCATTER_MATERIAL_FLAG;
+            }
+        } else {
+            m.albedo = {(float)(153.0 / 255.0f), (float)(102.0f / 255.0), 58.0f / 255.0f};
+            m.roughness = 0.2f;
+        }
+        if (!hasAlpha) m.Flags |= TB_NO_ALPHA_MATERIAL_FLAG;
+        return m;
+    }
+
+    void run(pbrt::Scene::SP scene) {
+        if (scene->cameras.empty()) throw std::runtime_error("scene has no camera");
+        // camera, TracerBoy.cpp:1243-1272
+        auto& cam = scene->cameras[0];
+        pbrt::vec3f pos = cam->frame * pbrt::vec3f(0.f);
+        pbrt::vec3f view = pbrt::math::normalize(pbrt::math::xfmVector(cam->frame, pbrt::vec3f(0.f, 0.f, 1.f)));
+        pbrt::vec3f right = pbrt::math::normalize(pbrt::math::xfmVector(cam->frame, pbrt::vec3f(1.f, 0.f, 0.f)));
+        pbrt::vec3f up = pbrt::math::xfmVector(cam->frame, pbrt::vec3f(0.f, 1.f, 0.f));
+        out.camera.LensHeight = (float)(2.0 * sqrtf(pbrt::math::dot(up, up)));
+        up = pbrt::math::normalize(up);
+        float fovAngle = (float)(cam->fov * M_PI / 180.0);
+        out.camera.FocalDistance = (float)((out.camera.LensHeight / 2.0) / tan(fovAngle / 2.0));
+        pos = pos + (out.camera.FocalDistance + 0.01f) * view;
+        out.camera.Position = cv3(pos);
+        out.camera.LookAt = cv3(pos + view);
+        out.camera.Right = cv3(right);
+        out.camera.Up = cv3(up);
+
+        // shapes: every top-level shape goes into the one global BLAS (:1361-1366). The SW
+        // path renders only that BLAS (TracerBoy.cpp:2862), so instances are not emitted.
+        auto& world = scene->world;
+        for (auto& shape : world->shapes) {
+            auto mesh = std::dynamic_pointer_cast<pbrt::TriangleMesh>(shape);
+            if (!mesh) continue; // curves: tessellation (:1426-1524) not implemented; others skipped as in the reference
+            pbrt::vec3f emissive(0.f);
+            std::vector<uint32_t> idx(mesh->index.size() * 3);
+            for (size_t i = 0; i < mesh->index.size(); i++) {
+                idx[3 * i] = mesh->index[i].x; idx[3 * i + 1] = mesh->index[i].y; idx[3 * i + 2] = mesh->index[i].z;
+            }
+            const TbFloat3* P = (const TbFloat3*)mesh->vertex.data();
+            const TbFloat3* N = mesh->normal.size() ? (const TbFloat3*)mesh->normal.data() : nullptr;
+            if (mesh->areaLight) {
+                auto dl = std::dynamic_pointer_cast<pbrt::DiffuseAreaLightRGB>(mesh->areaLight);
+                if (!dl) throw std::runtime_error("unsupported area light type (TracerBoy.cpp:253-266)");
+                emissive = dl->L;
+                append_area_lights(out, P, N, idx.data(), (uint32_t)idx.size(), cv3(emissive));
+            }
+            uint32_t matId;
+            auto it = matIndex.find(mesh->material.get());
+            if (it != matIndex.end()) matId = it->second;
+            else {
+                auto at = mesh->textures.find("alpha");
+                TbMaterial m = create_material(mesh->material, at != mesh->textures.end() ? &at->second : nullptr, emissive);
+                matId = add_material(mesh->material.get(), m);
+            }
+            // normals: normalize(xfmNormal(identity, n)) (:1647-1650)
+            std::vector<TbFloat3> nrm, tan;
+            std::vector<TbFloat2> uv;
+            size_t nv = mesh->vertex.size();
+            if (N) {
+                nrm.resize(nv);
+                for (size_t v = 0; v < nv; v++) nrm[v] = cv3(pbrt::math::normalize(mesh->normal[v]));
+            }
+            tan.resize(nv);
+            uv.resize(nv);
+            for (size_t v = 0; v < nv; v++) {
+                tan[v] = v < mesh->tangents.size() ? cv3(pbrt::math::normalize(mesh->tangents[v])) : TbFloat3{0, 0, 1};
+                uv[v] = v < mesh->texcoord.size() ? TbFloat2{mesh->texcoord[v].x, mesh->texcoord[v].y} : TbFloat2{0, 0};
+            }
+            append_geometry(out, P, N ? nrm.data() : nullptr, uv.data(), tan.data(), (uint32_t)nv, idx.data(),
+                            (uint32_t)idx.size(), matId);
+        }
+        // lights / environment, TracerBoy.cpp:1896-1934
+        for (auto& ls : world->lightSources) {
+            auto inf = std::dynamic_pointer_cast<pbrt::InfiniteLightSource>(ls);
+            auto dist = std::dynamic_pointer_cast<pbrt::DistantLightSource>(ls);
+            if (inf) {
+                out.envImage = (int32_t)load_image(inf->mapName, nullptr);
+                auto& l = inf->transform.l;
+                out.envTransform[0] = {l.vx.x, l.vx.y, l.vx.z, 0};
+                out.envTransform[1] = {l.vy.x, l.vy.y, l.vy.z, 0};
+                out.envTransform[2] = {l.vz.x, l.vz.y, l.vz.z, 0};
+                out.envColorScale = cv3(inf->scale);
+            } else if (dist) {
+                TbLight l;
+                memset(&l, 0, sizeof(l));
+                l.LightColor = cv3(dist->L);
+                l.LightType = TB_LIGHT_TYPE_DIRECTIONAL;
+                l.Direction = cv3(pbrt::math::normalize(dist->to - dist->from));
+                out.lights.push_back(l);
+            }
+        }
+        out.flipTextureUVs = 1; // PBRT uses GL-style texture sampling (:1208)
+    }
+};
+
+} // namespace
+
+extern "C" __attribute__((visibility("default")))
+int tb_pbrt_import(const char* path, void* sceneOut, char* err, size_t errCap) {
+    Scene& s = *(Scene*)sceneOut;
+    try {
+        std::string p(path);
+        std::string ext = p.size() >= 4 ? p.substr(p.size() - 4) : "";
+        pbrt::Scene::SP scene;
+        if (ext == "pbrt") scene = pbrt::importPBRT(p);
+        else if (ext == ".pbf") scene = pbrt::Scene::loadFrom(p);
+        else throw std::runtime_error("unsupported scene extension");
+        size_t slash = p.find_last_of('/');
+        std::string dir = slash == std::string::npos ? "" : p.substr(0, slash + 1);
+        s.clear();
+        Importer imp(s, dir);
+        imp.run(scene);
+        return 0;
+    } catch (const std::exception& e) {
+        if (err && errCap) { strncpy(err, e.what(), errCap - 1); err[errCap - 1] = 0; }
+        return -3;
+    }
+}
+
+// Import + write the .tbscene cache in one call (used by the build step that converts the
+// bundled scenes, and by tb_load_scene when it wants to cache).
+extern "C" __attribute__((visibility("default")))
+int tb_pbrt_convert(const char* path, const char* outTbscene, char* err, size_t errCap) {
+    Scene s;
+    int rc = tb_pbrt_import(path, &s, err, errCap);
+    if (rc != 0) return rc;
+    std::string e;
+    if (!save_tbscene(s, outTbscene, e)) {
+        if (err && errCap) { strncpy(err, e.c_str(), errCap - 1); err[errCap - 1] = 0; }
+        return -3;
+    }
+    return 0;
+}
