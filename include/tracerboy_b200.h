@@ -282,6 +282,12 @@ typedef struct TbRenderStats {
     uint64_t PathsStarted;
     uint64_t KernelLaunches;   /* CUDA kernels launched by the library since the last reset */
     double DeviceMilliseconds; /* CUDA-event time of tb_render calls since the last reset */
+    /* extend-stage (k_extend) share of the three counters above */
+    uint64_t ExtendRays, ExtendBoxesTested, ExtendTrianglesTested;
+    /* profiling mode only (tb_set_profiling): summed per-launch CUDA-event durations */
+    uint64_t ExtendLaunches;
+    double ExtendMilliseconds;
+    double ShadeMilliseconds;
 } TbRenderStats;
 
 typedef struct TbHandle TbHandle; /* opaque; owns all device memory */
@@ -337,6 +343,9 @@ TB_API int tb_readback(TbHandle* h, uint32_t kind, void* dst, uint64_t bytes);
 TB_API int tb_device_buffer(TbHandle* h, uint32_t kind, void** devPtr, uint64_t* bytes);
 TB_API int tb_get_render_stats(TbHandle* h, TbRenderStats* out);
 TB_API int tb_reset_render_stats(TbHandle* h);
+/* Profiling mode: record CUDA events around every traversal / shading launch (small
+ * overhead; off by default). Results appear in TbRenderStats.Extend/ShadeMilliseconds. */
+TB_API int tb_set_profiling(TbHandle* h, int enable);
 TB_API int tb_synchronize(TbHandle* h);
 
 /* --------------------------------------------------------------- materials */

@@ -699,8 +699,8 @@ __global__ void __launch_bounds__(128) k_shade(DeviceBvh bvh, DeviceScene sc, Fr
     for (int o = 16; o > 0; o >>= 1) {
         rays += __shfl_xor_sync(0xffffffffu, rays, o); tris += __shfl_xor_sync(0xffffffffu, tris, o); boxes += __shfl_xor_sync(0xffffffffu, boxes, o);
     }
-    if ((threadIdx.x & 31) == 0 && rays) {
-        atomicAdd(&st.stats[0], (unsigned long long)rays); atomicAdd(&st.stats[1], (unsigned long long)boxes); atomicAdd(&st.stats[2], (unsigned long long)tris);
+    if ((threadIdx.x & 31) == 0 && rays) { // slots 3..5: rays traced inside the shading stage (shadow feelers, SSS walk)
+        atomicAdd(&st.stats[3], (unsigned long long)rays); atomicAdd(&st.stats[4], (unsigned long long)boxes); atomicAdd(&st.stats[5], (unsigned long long)tris);
     }
 }
 
@@ -733,7 +733,7 @@ static int num_sms() {
 }
 
 cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const FrameConstants& fc, PathState& st,
-                         cudaStream_t stream, LaunchCounter& lc) {
+                         cudaStream_t stream, LaunchCounter& lc, KernelTimers* timers) {
     const uint32_t n = fc.width * fc.height;
     k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(sc, fc, st); lc.count++;
     // persistent grids: a multiple of the SM count, capped by the work available
@@ -745,8 +745,11 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
     const uint32_t heat = fc.settings.OutputType == TB_OUTPUT_HEATMAP;
     for (int b = 0; b < maxBounces; b++) {
         int qi = b & 1;
+        if (timers) cudaEventRecord(timers->next(KernelTimers::EXTEND), stream);
         k_extend<<<blocks, 128, 0, stream>>>(bvh, st, qi, b == 0, heat); lc.count++;
+        if (timers) cudaEventRecord(timers->next(KernelTimers::SHADE), stream);
         k_shade<<<blocks, 128, 0, stream>>>(bvh, sc, fc, st, qi); lc.count++;
+        if (timers) cudaEventRecord(timers->next(KernelTimers::END), stream);
     }
     return cudaGetLastError();
 }

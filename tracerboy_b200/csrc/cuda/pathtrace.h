@@ -1,5 +1,6 @@
 // pathtrace.h — host-visible interface of the CUDA translation units.
 #pragma once
+#include <vector>
 #include <cuda_runtime.h>
 #include "device_types.h"
 #include "launch.h"
@@ -27,8 +28,33 @@ struct PathState {
     float* aovDepth = nullptr;
     uint2* primaryHit = nullptr;
     uint2* counters = nullptr;     // per pixel (TrianglesTested, BoxesTested) of the current frame
-    unsigned long long* stats = nullptr; // rays, boxes, tris (cumulative)
+    unsigned long long* stats = nullptr; // [0..2] extend-stage rays, boxes, tris; [3..5] same for rays traced inside k_shade
     TbReadbackStats* readbackStats = nullptr;
+};
+
+// Optional per-kernel timing (profiling mode): CUDA events recorded on the launching stream
+// around every k_extend / k_shade launch; resolved by the caller after a stream sync.
+struct KernelTimers {
+    enum Tag { EXTEND = 0, SHADE = 1, END = 2 };
+    std::vector<cudaEvent_t> events;
+    std::vector<int> tags;
+    size_t used = 0;
+    cudaEvent_t next(Tag t) {
+        if (used == events.size()) { cudaEvent_t e; cudaEventCreate(&e); events.push_back(e); tags.push_back(0); }
+        tags[used] = (int)t;
+        return events[used++];
+    }
+    // adds elapsed ms per tag, returns number of (extend, shade) launch pairs
+    void resolve(double& extendMs, double& shadeMs, uint64_t& extendLaunches) {
+        for (size_t i = 0; i + 1 < used; i++) {
+            if (tags[i] == END) continue;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, events[i], events[i + 1]);
+            if (tags[i] == EXTEND) { extendMs += ms; extendLaunches++; } else shadeMs += ms;
+        }
+        used = 0;
+    }
+    ~KernelTimers() { for (auto e : events) cudaEventDestroy(e); }
 };
 
 uint64_t bvh_ref_bytes(uint32_t numPrims);
@@ -36,7 +62,7 @@ cudaError_t build_bvh(const TbGeometryRecord* d_geoms, const uint32_t* d_triPref
                       const float* d_positions, const uint32_t* d_indices, uint32_t numPrims, int treeletPasses,
                       DeviceBvh& out, cudaStream_t stream, LaunchCounter& lc);
 cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const FrameConstants& fc, PathState& st,
-                         cudaStream_t stream, LaunchCounter& lc);
+                         cudaStream_t stream, LaunchCounter& lc, KernelTimers* timers);
 cudaError_t resolve_rgb(const float4* accum, float* rgb, uint32_t n, cudaStream_t stream, LaunchCounter& lc);
 cudaError_t trace_rays(const DeviceBvh& bvh, const TbRay* d_rays, uint64_t n, TbHit* d_hits, cudaStream_t stream, LaunchCounter& lc);
 

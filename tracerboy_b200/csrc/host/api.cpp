@@ -47,6 +47,10 @@ struct TbHandle {
     std::mutex statusLock;
     TbSceneLoadStatus status{TB_LOAD_IDLE, 0, 0};
     std::vector<uint8_t> blueNoiseHost;
+    bool profiling = false;
+    KernelTimers timers;
+    double extendMs = 0.0, shadeMs = 0.0;
+    uint64_t extendLaunches = 0;
 };
 
 static std::string g_createError;
@@ -359,7 +363,7 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
     CUDA_OK(h, alloc((void**)&st.aovWorldPos[0], 16 * n)); CUDA_OK(h, alloc((void**)&st.aovWorldPos[1], 16 * n));
     CUDA_OK(h, alloc((void**)&st.aovDepth, 4 * n));
     CUDA_OK(h, alloc((void**)&st.primaryHit, 8 * n)); CUDA_OK(h, alloc((void**)&st.counters, 8 * n));
-    CUDA_OK(h, alloc((void**)&st.stats, 32)); CUDA_OK(h, alloc((void**)&st.readbackStats, sizeof(TbReadbackStats)));
+    CUDA_OK(h, alloc((void**)&st.stats, 64)); CUDA_OK(h, alloc((void**)&st.readbackStats, sizeof(TbReadbackStats)));
     CUDA_OK(h, alloc((void**)&h->resolved, 12 * n));
     h->width = w; h->height = hh;
     h->samplesRendered = 0;
@@ -407,15 +411,20 @@ TB_API int tb_render(TbHandle* h, const TbOutputSettings* s, uint32_t nSamples, 
         fc.halton2 = halton(2, (int)fc.frame);
         fc.halton3 = halton(3, (int)fc.frame);
         fc.clearAccum = h->samplesRendered == 0;
-        CUDA_OK(h, render_frame(h->bvh, h->dscene, fc, h->st, h->stream, h->lc));
+        CUDA_OK(h, render_frame(h->bvh, h->dscene, fc, h->st, h->stream, h->lc, h->profiling ? &h->timers : nullptr));
         h->samplesRendered++;
         h->pathsStarted += (uint64_t)h->width * h->height;
+        if (h->profiling && h->timers.used > 4096) { // bound the number of live events
+            CUDA_OK(h, cudaStreamSynchronize(h->stream));
+            h->timers.resolve(h->extendMs, h->shadeMs, h->extendLaunches);
+        }
     }
     CUDA_OK(h, cudaEventRecord(h->ev1, h->stream));
     CUDA_OK(h, cudaEventSynchronize(h->ev1));
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->deviceMs += ms;
+    if (h->profiling) h->timers.resolve(h->extendMs, h->shadeMs, h->extendLaunches);
     CUDA_OK(h, cudaGetLastError());
     return TB_OK;
 }
@@ -496,12 +505,14 @@ TB_API int tb_get_render_stats(TbHandle* h, TbRenderStats* out) {
     if (!h || !out) return fail(h, TB_ERR_INVALID_ARG, "null argument");
     memset(out, 0, sizeof(*out));
     if (h->st.stats) {
-        unsigned long long s[3];
+        unsigned long long s[6];
         CUDA_OK(h, cudaSetDevice(h->device));
         CUDA_OK(h, cudaMemcpyAsync(s, h->st.stats, sizeof(s), cudaMemcpyDeviceToHost, h->stream));
         CUDA_OK(h, cudaStreamSynchronize(h->stream));
-        out->RaysTraced = s[0]; out->BoxesTested = s[1]; out->TrianglesTested = s[2];
+        out->RaysTraced = s[0] + s[3]; out->BoxesTested = s[1] + s[4]; out->TrianglesTested = s[2] + s[5];
+        out->ExtendRays = s[0]; out->ExtendBoxesTested = s[1]; out->ExtendTrianglesTested = s[2];
     }
+    out->ExtendLaunches = h->extendLaunches; out->ExtendMilliseconds = h->extendMs; out->ShadeMilliseconds = h->shadeMs;
     out->PathsStarted = h->pathsStarted;
     out->KernelLaunches = h->lc.count;
     out->DeviceMilliseconds = h->deviceMs;
@@ -509,8 +520,14 @@ TB_API int tb_get_render_stats(TbHandle* h, TbRenderStats* out) {
 }
 TB_API int tb_reset_render_stats(TbHandle* h) {
     if (!h) return TB_ERR_INVALID_ARG;
-    if (h->st.stats) { CUDA_OK(h, cudaSetDevice(h->device)); CUDA_OK(h, cudaMemsetAsync(h->st.stats, 0, 32, h->stream)); }
+    if (h->st.stats) { CUDA_OK(h, cudaSetDevice(h->device)); CUDA_OK(h, cudaMemsetAsync(h->st.stats, 0, 64, h->stream)); }
     h->pathsStarted = 0; h->lc.count = 0; h->deviceMs = 0.0;
+    h->extendMs = h->shadeMs = 0.0; h->extendLaunches = 0;
+    return TB_OK;
+}
+TB_API int tb_set_profiling(TbHandle* h, int enable) {
+    if (!h) return TB_ERR_INVALID_ARG;
+    h->profiling = enable != 0;
     return TB_OK;
 }
 TB_API int tb_synchronize(TbHandle* h) {
