@@ -346,6 +346,9 @@ TB_API int tb_reset_render_stats(TbHandle* h);
 /* Profiling mode: record CUDA events around every traversal / shading launch (small
  * overhead; off by default). Results appear in TbRenderStats.Extend/ShadeMilliseconds. */
 TB_API int tb_set_profiling(TbHandle* h, int enable);
+/* Number of frames (samples) kept in flight on independent CUDA streams (default 8). The
+ * result does not depend on it: samples are added to the accumulation buffer in frame order. */
+TB_API int tb_set_frames_in_flight(TbHandle* h, uint32_t n);
 TB_API int tb_synchronize(TbHandle* h);
 
 /* --------------------------------------------------------------- materials */

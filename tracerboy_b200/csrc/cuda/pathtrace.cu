@@ -37,6 +37,8 @@ namespace {
 #define MIN_ROUGHNESS_SQUARED (0.04f * 0.04f)
 #define MIN_T 0.001f
 #define FAR_T 999999.0f
+#define AOV_FULL 1u     // this frame is the last one of the render call: it owns the overwritten-every-frame AOVs
+#define AOV_WORLDPOS 2u // last or last-1 frame: owns its ping-pong world-position buffer
 
 __device__ __forceinline__ f3 F3(const TbFloat3& v) { return mk3(v.x, v.y, v.z); }
 
@@ -379,7 +381,7 @@ __device__ __forceinline__ uint32_t pack_state(int bounce, bool prevSpec) { retu
 __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, FrameConstants fc, PathState st) {
     uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n = fc.width * fc.height;
-    if (pi == 0) { st.queueCount[0] = n; st.queueCount[1] = 0; }
+    if (pi == 0) { st.queueCount[0] = n; st.queueCount[1] = 0; st.queueCount[2] = 0; st.queueCount[3] = 0; }
     if (pi >= n) return;
     uint32_t px = pi % fc.width, py = pi / fc.width;
     Rng rng;
@@ -428,64 +430,110 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, FrameConstants f
     st.neighborDir[pi] = make_float4(ndir.x, ndir.y, ndir.z, 0.0f);
     st.queue[0][pi] = pi;
     // ClearAOVs (RayGenCommon.h:650-654) + zeroed world-position accumulators (:693-694)
-    st.aovAlbedo[pi] = make_float4(0, 0, 0, 1.0f);
-    st.aovNormal[pi] = make_float4(0, 0, 0, 1.0f);
-    st.aovWorldPos[fc.frame & 1][pi] = make_float4(0, 0, 0, 0);
-    st.primaryHit[pi] = make_uint2(0xffffffffu, 0xffffffffu);
-    st.counters[pi] = make_uint2(0, 0);
+    if (fc.aovMask & AOV_FULL) {
+        st.aovAlbedo[pi] = make_float4(0, 0, 0, 1.0f);
+        st.aovNormal[pi] = make_float4(0, 0, 0, 1.0f);
+        st.primaryHit[pi] = make_uint2(0xffffffffu, 0xffffffffu);
+        st.counters[pi] = make_uint2(0, 0);
+    }
+    if (fc.aovMask & AOV_WORLDPOS) st.aovWorldPos[fc.frame & 1][pi] = make_float4(0, 0, 0, 0);
+    // per-frame staging of the two AOVs that persist when a frame does not write them
+    st.stEmissive[pi] = make_float4(0, 0, 0, 0);
+    st.stDepth[pi] = -1.0f;
+    if (fc.settings.MaxBounces <= 0) { // the bounce loop never runs: Trace returns black
+        st.sample[pi] = make_float4(0.0f * filterWeight, 0.0f * filterWeight, 0.0f * filterWeight, filterWeight);
+        st.sampleSeed[pi] = rng.seed;
+    }
 }
 
 // ---------------------------------------------------------------------- extend
-__global__ void __launch_bounds__(128) k_extend(DeviceBvh bvh, PathState st, int qi, int bounceIsZero, uint32_t outputHeatmap) {
+// Persistent warps with per-lane dynamic ray fetch. A lane whose ray has finished does not
+// wait for the slowest ray of its warp: once fewer than REFILL_THRESHOLD lanes are still
+// traversing, the warp regroups, idle lanes grab the next rays of the queue with one
+// warp-aggregated atomic, and traversal resumes. (A static assignment ran at 3.5 active
+// lanes per instruction on the incoherent bounces of the Teapot scene — profiles/.)
+#define REFILL_THRESHOLD 20
+__global__ void __launch_bounds__(128) k_extend(DeviceBvh bvh, PathState st, int qi, int bounceIsZero, uint32_t outputHeatmap, uint32_t aovMask) {
     const uint32_t count = st.queueCount[qi];
     if (blockIdx.x == 0 && threadIdx.x == 0) st.queueCount[qi ^ 1] = 0; // next queue starts empty (consumed by k_shade)
-    uint32_t rays = 0, tris = 0, boxes = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        uint32_t pi = st.queue[qi][i];
-        float4 o = st.rayO[pi], d = st.rayD[pi];
-        HitRec h;
-        trace_ray(bvh, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), MIN_T, FAR_T, h);
-        st.hit[pi] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
-        st.hitGeom[pi] = h.geom;
-        uint2 c = st.counters[pi];
-        c.x += h.tris; c.y += h.boxes;
-        st.counters[pi] = c;
-        if (bounceIsZero) st.primaryHit[pi] = make_uint2(h.geom, h.prim);
-        if (outputHeatmap) st.aovAlbedo[pi] = make_float4((float)h.tris, (float)h.boxes, 0.0f, 0.0f);
-        rays++; tris += h.tris; boxes += h.boxes;
+    uint32_t* __restrict__ next = &st.queueCount[2 + qi];               // work counter, zeroed by the previous kernel
+    const uint32_t* __restrict__ queue = st.queue[qi];
+    const float4* __restrict__ pairs = (const float4*)bvh.pairs;
+    const float4* __restrict__ tris = (const float4*)bvh.tris;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t rays = 0, ntris = 0, nboxes = 0;
+    Traversal tr;
+    uint32_t stack[TB_STACK_DEPTH];
+    tr.sp = 0;
+    bool active = false, exhausted = false;
+    uint32_t pi = 0;
+    while (true) {
+        uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (idle && !exhausted) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(next, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!active) {
+                uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+                if (i < count) {
+                    pi = __ldg(queue + i);
+                    float4 o = st.rayO[pi], d = st.rayD[pi];
+                    tr.begin(bvh, stack, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), MIN_T, FAR_T);
+                    active = true;
+                }
+            }
+            if (base + (uint32_t)__popc(idle) >= count) exhausted = true;
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+        if (active) {
+            while (true) {
+                if (tr.done()) {
+                    HitRec h;
+                    tr.result(h);
+                    st.hit[pi] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
+                    st.hitGeom[pi] = h.geom;
+                    if (aovMask & AOV_FULL) {
+                        uint2 c = st.counters[pi];
+                        c.x += h.tris; c.y += h.boxes;
+                        st.counters[pi] = c;
+                        if (bounceIsZero) st.primaryHit[pi] = make_uint2(h.geom, h.prim);
+                        if (outputHeatmap) st.aovAlbedo[pi] = make_float4((float)h.tris, (float)h.boxes, 0.0f, 0.0f);
+                    }
+                    rays++; ntris += h.tris; nboxes += h.boxes;
+                    active = false;
+                    break;
+                }
+                tr.step(stack, pairs, tris);
+                // regroup for a refill when the warp has thinned out (heuristic only: results do not depend on it)
+                if (!exhausted && __popc(__activemask()) < REFILL_THRESHOLD) break;
+            }
+        }
     }
     // warp-reduced global statistics
     for (int o = 16; o > 0; o >>= 1) {
-        rays += __shfl_xor_sync(0xffffffffu, rays, o); tris += __shfl_xor_sync(0xffffffffu, tris, o); boxes += __shfl_xor_sync(0xffffffffu, boxes, o);
+        rays += __shfl_xor_sync(0xffffffffu, rays, o); ntris += __shfl_xor_sync(0xffffffffu, ntris, o); nboxes += __shfl_xor_sync(0xffffffffu, nboxes, o);
     }
-    if ((threadIdx.x & 31) == 0 && rays) {
-        atomicAdd(&st.stats[0], (unsigned long long)rays); atomicAdd(&st.stats[1], (unsigned long long)boxes); atomicAdd(&st.stats[2], (unsigned long long)tris);
+    if (lane == 0 && rays) {
+        atomicAdd(&st.stats[0], (unsigned long long)rays); atomicAdd(&st.stats[1], (unsigned long long)nboxes); atomicAdd(&st.stats[2], (unsigned long long)ntris);
     }
 }
 
 // ----------------------------------------------------------------------- shade
-// RayTraceCommon tail (RayGenCommon.h:696-727): firefly clamp + filter weight (kernel.glsl:1907-1920),
-// NaN rejection, OutputTexture +=, jittered buffer coin.
+// End of a path: firefly clamp + filter weight (kernel.glsl:1907-1920) and NaN rejection
+// (RayGenCommon.h:704-707). The sample and the path's rand() seed are staged per frame;
+// k_accumulate applies them to OutputTexture in frame order.
 __device__ __forceinline__ void finish_path(const FrameConstants& fc, PathState& st, uint32_t pi, f3 color, float filterWeight, Rng& rng) {
     if (fc.settings.FireflyClampValue >= EPSILON) color = min3(color, fc.settings.FireflyClampValue);
     f4 c = mk4(color * filterWeight, filterWeight);
     f4 outc = mk4(0, 0, 0, 0);
     if (!isnan_(c.x) && !isnan_(c.y) && !isnan_(c.z) && !isnan_(c.w)) outc = outc + c;
-    bool realtime = fc.settings.RenderMode == TB_RENDER_REALTIME;
-    bool clear = realtime || fc.clearAccum;
-    float4 prev = clear ? make_float4(0, 0, 0, 0) : st.accum[pi];
-    st.accum[pi] = make_float4(outc.x + prev.x, outc.y + prev.y, outc.z + prev.z, outc.w + prev.w);
-    if (!realtime) {
-        bool take = fc.frame == 0 || rng.next() < 0.5f; // the coin is not drawn on frame 0 (short circuit, :723)
-        if (take) {
-            float4 pj = fc.clearAccum ? make_float4(0, 0, 0, 0) : st.jittered[pi];
-            st.jittered[pi] = make_float4(outc.x + pj.x, outc.y + pj.y, outc.z + pj.z, outc.w + pj.w);
-        } else if (fc.clearAccum) st.jittered[pi] = make_float4(0, 0, 0, 0);
-    }
+    st.sample[pi] = make_float4(outc.x, outc.y, outc.z, outc.w);
+    st.sampleSeed[pi] = rng.seed;
 }
 
 __global__ void __launch_bounds__(128) k_shade(DeviceBvh bvh, DeviceScene sc, FrameConstants fc, PathState st, int qi) {
     const uint32_t count = st.queueCount[qi];
+    if (blockIdx.x == 0 && threadIdx.x == 0) st.queueCount[2 + (qi ^ 1)] = 0; // work counter of the next k_extend
     const TbOutputSettings& S = fc.settings;
     const int MaxBounces = S.MaxBounces;
     RayCount rc = {0, 0, 0};
@@ -513,7 +561,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceBvh bvh, DeviceScene sc, Fr
                 if (thr.x < EPSILON && thr.y < EPSILON && thr.z < EPSILON) { terminated = true; break; }
                 if (h4.x < 0.0f) { // miss
                     acc += thr * sample_environment_map(sc, dir);
-                    if (bFirstRay) st.aovEmissive[pi] = make_float4(acc.x, acc.y, acc.z, 1.0f);
+                    if (bFirstRay) st.stEmissive[pi] = make_float4(acc.x, acc.y, acc.z, 1.0f);
                     terminated = true; break;
                 }
                 Surface sf = surface_from_hit(sc, h4.y, h4.z, st.hitGeom[pi], __float_as_uint(h4.w));
@@ -529,10 +577,10 @@ __global__ void __launch_bounds__(128) k_shade(DeviceBvh bvh, DeviceScene sc, Fr
                     f3 nrp = mk3(nb.x, nb.y, nb.z) + mk3(nd.x, nd.y, nd.z) * h4.x;
                     f3 wp = mk3(0.0f) + RayPoint;
                     float dn = 0.0f + length(nrp - RayPoint);
-                    st.aovWorldPos[fc.frame & 1][pi] = make_float4(wp.x, wp.y, wp.z, dn);
-                    st.aovNormal[pi] = make_float4(detailNormal.x, detailNormal.y, detailNormal.z, 1.0f);
-                    st.aovDepth[pi] = saturate(h4.x / S.MaxZ);
-                    if ((int)(pi % fc.width) == fc.selectedX && (int)(pi / fc.width) == fc.selectedY) {
+                    if (fc.aovMask & AOV_WORLDPOS) st.aovWorldPos[fc.frame & 1][pi] = make_float4(wp.x, wp.y, wp.z, dn);
+                    if (fc.aovMask & AOV_FULL) st.aovNormal[pi] = make_float4(detailNormal.x, detailNormal.y, detailNormal.z, 1.0f);
+                    st.stDepth[pi] = saturate(h4.x / S.MaxZ);
+                    if ((fc.aovMask & AOV_FULL) && (int)(pi % fc.width) == fc.selectedX && (int)(pi / fc.width) == fc.selectedY) {
                         st.readbackStats->SelectedPixelDistance = h4.x;
                         st.readbackStats->SelectedMaterialID = sf.material;
                     }
@@ -634,7 +682,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceBvh bvh, DeviceScene sc, Fr
                         float PDFValue = IsMetallic(material) ? SpecularPDF : lerp(SpecularPDF, DiffusePDF, 0.5f);
                         thr /= PDFValue;
                     } else thr /= DiffusePDF;
-                    if (bFirstRay) st.aovEmissive[pi] = make_float4(material.emissive.x, material.emissive.y, material.emissive.z, 1.0f);
+                    if (bFirstRay) st.stEmissive[pi] = make_float4(material.emissive.x, material.emissive.y, material.emissive.z, 1.0f);
                     bool bRemoveAlbedo = (S.RenderMode == TB_RENDER_REALTIME) && bFirstRay;
                     f3 albedo = bRemoveAlbedo ? mk3(1.0f) : material.albedo;
                     if (IsMetallic(material)) {
@@ -657,7 +705,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceBvh bvh, DeviceScene sc, Fr
                     } else {
                         thr *= albedo * diffuse_brdf(dir, detailNormal);
                     }
-                    if (bFirstRay && S.OutputType != TB_OUTPUT_HEATMAP) st.aovAlbedo[pi] = make_float4(material.albedo.x, material.albedo.y, material.albedo.z, 1.0f);
+                    if (bFirstRay && (fc.aovMask & AOV_FULL) && S.OutputType != TB_OUTPUT_HEATMAP) st.aovAlbedo[pi] = make_float4(material.albedo.x, material.albedo.y, material.albedo.z, 1.0f);
                 }
                 // top of the next loop iteration: bounce limit, then russian roulette (kernel.glsl:1286-1302)
                 int next = bounce + 1;
@@ -672,7 +720,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceBvh bvh, DeviceScene sc, Fr
             } while (false);
 
             // per-pixel counters for the inline rays of this stage
-            if (rc.tris != cnt0.x || rc.boxes != cnt0.y) {
+            if ((fc.aovMask & AOV_FULL) && (rc.tris != cnt0.x || rc.boxes != cnt0.y)) {
                 uint2 c = st.counters[pi];
                 c.x += rc.tris - cnt0.x; c.y += rc.boxes - cnt0.y;
                 st.counters[pi] = c;
@@ -702,6 +750,31 @@ __global__ void __launch_bounds__(128) k_shade(DeviceBvh bvh, DeviceScene sc, Fr
     if ((threadIdx.x & 31) == 0 && rays) { // slots 3..5: rays traced inside the shading stage (shadow feelers, SSS walk)
         atomicAdd(&st.stats[3], (unsigned long long)rays); atomicAdd(&st.stats[4], (unsigned long long)boxes); atomicAdd(&st.stats[5], (unsigned long long)tris);
     }
+}
+
+// RayTraceCommon tail (RayGenCommon.h:709-727), one launch per frame, in frame order:
+// OutputTexture += sample, the jittered-buffer coin (one more rand() of the path's stream),
+// and the ordered merge of the two persistent AOVs.
+__global__ void __launch_bounds__(256) k_accumulate(FrameConstants fc, PathState st) {
+    uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= fc.width * fc.height) return;
+    float4 outc = st.sample[pi];
+    Rng rng; rng.seed = st.sampleSeed[pi]; rng.time = fc.time;
+    bool realtime = fc.settings.RenderMode == TB_RENDER_REALTIME;
+    bool clear = realtime || fc.clearAccum;
+    float4 prev = clear ? make_float4(0, 0, 0, 0) : st.accum[pi];
+    st.accum[pi] = make_float4(outc.x + prev.x, outc.y + prev.y, outc.z + prev.z, outc.w + prev.w);
+    if (!realtime) {
+        bool take = fc.frame == 0 || rng.next() < 0.5f; // the coin is not drawn on frame 0 (short circuit, :723)
+        if (take) {
+            float4 pj = fc.clearAccum ? make_float4(0, 0, 0, 0) : st.jittered[pi];
+            st.jittered[pi] = make_float4(outc.x + pj.x, outc.y + pj.y, outc.z + pj.z, outc.w + pj.w);
+        } else if (fc.clearAccum) st.jittered[pi] = make_float4(0, 0, 0, 0);
+    }
+    float4 e = st.stEmissive[pi];
+    if (e.w != 0.0f) st.aovEmissive[pi] = e;
+    float d = st.stDepth[pi];
+    if (d >= 0.0f) st.aovDepth[pi] = d;
 }
 
 __global__ void k_resolve(const float4* __restrict__ accum, float* __restrict__ rgb, uint32_t n) {
@@ -746,11 +819,17 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
     for (int b = 0; b < maxBounces; b++) {
         int qi = b & 1;
         if (timers) cudaEventRecord(timers->next(KernelTimers::EXTEND), stream);
-        k_extend<<<blocks, 128, 0, stream>>>(bvh, st, qi, b == 0, heat); lc.count++;
+        k_extend<<<blocks, 128, 0, stream>>>(bvh, st, qi, b == 0, heat, fc.aovMask); lc.count++;
         if (timers) cudaEventRecord(timers->next(KernelTimers::SHADE), stream);
         k_shade<<<blocks, 128, 0, stream>>>(bvh, sc, fc, st, qi); lc.count++;
         if (timers) cudaEventRecord(timers->next(KernelTimers::END), stream);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t accumulate_frame(const FrameConstants& fc, PathState& st, cudaStream_t stream, LaunchCounter& lc) {
+    const uint32_t n = fc.width * fc.height;
+    k_accumulate<<<(n + 255) / 256, 256, 0, stream>>>(fc, st); lc.count++;
     return cudaGetLastError();
 }
 

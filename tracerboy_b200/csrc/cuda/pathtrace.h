@@ -18,7 +18,13 @@ struct PathState {
     float4* neighbor = nullptr;    // neighbour camera ray origin (bounce 0 only)
     float4* neighborDir = nullptr; // neighbour camera ray direction
     uint32_t* queue[2] = {nullptr, nullptr};
-    uint32_t* queueCount = nullptr; // 2 counters
+    uint32_t* queueCount = nullptr; // [0..1] queue sizes, [2..3] k_extend work counters
+    // per-frame staging consumed by k_accumulate (frames in flight finish out of order)
+    float4* sample = nullptr;      // (rgb * w, w) after firefly clamp and NaN rejection
+    float* sampleSeed = nullptr;   // the path's rand() seed at termination (jittered-buffer coin)
+    float4* stEmissive = nullptr;  // w != 0 when written this frame
+    float* stDepth = nullptr;      // < 0 when not written this frame
+    // ---- everything below is shared by all frame slots ----
     float4* accum = nullptr;       // OutputTexture
     float4* jittered = nullptr;    // JitteredOutputTexture
     float4* aovAlbedo = nullptr;   // AOVCustomOutput
@@ -63,6 +69,7 @@ cudaError_t build_bvh(const TbGeometryRecord* d_geoms, const uint32_t* d_triPref
                       DeviceBvh& out, cudaStream_t stream, LaunchCounter& lc);
 cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const FrameConstants& fc, PathState& st,
                          cudaStream_t stream, LaunchCounter& lc, KernelTimers* timers);
+cudaError_t accumulate_frame(const FrameConstants& fc, PathState& st, cudaStream_t stream, LaunchCounter& lc);
 cudaError_t resolve_rgb(const float4* accum, float* rgb, uint32_t n, cudaStream_t stream, LaunchCounter& lc);
 cudaError_t trace_rays(const DeviceBvh& bvh, const TbRay* d_rays, uint64_t n, TbHit* d_hits, cudaStream_t stream, LaunchCounter& lc);
 

@@ -36,39 +36,49 @@ __device__ __forceinline__ bool slab(float& resultT, float closestT, tbm::f3 oin
     return fmaxf(minT, 0.0f) < fminf(maxT, closestT);
 }
 
-__device__ __forceinline__ void trace_ray(const DeviceBvh& bvh, tbm::f3 org, tbm::f3 dir, float tmin, float tmax, HitRec& out) {
-    using namespace tbm;
-    f3 inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
-    f3 oinv = org * inv;
-    f3 ainv = abs3(inv);
-    f3 ad = abs3(dir);
-    int kz = (ad.x > ad.y && ad.x > ad.z) ? 0 : (ad.y > ad.z ? 1 : 2);
-    int kx = kz == 2 ? 0 : kz + 1, ky = kx == 2 ? 0 : kx + 1;
-    if (comp(dir, kz) < 0.0f) { int t = kx; kx = ky; ky = t; }
-    float dz = comp(dir, kz);
-    f3 shear = mk3(comp(dir, kx) / dz, comp(dir, ky) / dz, 1.0f / dz);
-    // ray origin permuted once (the triangle test permutes v - org; permuting both is the same values)
-    float committedT = tmax;
-    bool haveHit = false;
-    uint32_t hitGeom = 0xffffffffu, hitPrim = 0xffffffffu;
-    float hb1 = 0.0f, hb2 = 0.0f;
-    uint32_t trisTested = 0, boxesTested = 0;
+// Resumable traversal: begin() once per ray, step() once per popped node until done().
+// Keeping the state in a struct lets the persistent kernel (k_extend) interleave rays of
+// different lengths in one warp (per-lane refill) while the inline queries of the shading
+// stage simply run it to completion. Per-ray visit order and counters are identical either way.
+struct Traversal {
+    tbm::f3 org, inv, oinv, shear;
+    int kx, ky, kz;
+    float tmin, tmax, committedT, hb1, hb2;
+    uint32_t hitGeom, hitPrim, trisTested, boxesTested;
+    bool haveHit;
+    int sp;
+    // The node stack is a separate per-thread array (passed in) so that the scalar state
+    // above stays in registers; only the dynamically indexed stack lives in local memory.
 
-    uint32_t stack[TB_STACK_DEPTH];
-    int sp = 0;
-    {
+    __device__ __forceinline__ void begin(const DeviceBvh& bvh, uint32_t* stack, tbm::f3 o, tbm::f3 dir, float tmin_, float tmax_) {
+        using namespace tbm;
+        org = o;
+        inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z); // GetRayData, TraverseFunction.hlsli:473-495
+        oinv = org * inv;
+        f3 ad = abs3(dir);
+        kz = (ad.x > ad.y && ad.x > ad.z) ? 0 : (ad.y > ad.z ? 1 : 2);
+        kx = kz == 2 ? 0 : kz + 1; ky = kx == 2 ? 0 : kx + 1;
+        if (comp(dir, kz) < 0.0f) { int t = kx; kx = ky; ky = t; }
+        float dz = comp(dir, kz);
+        shear = mk3(comp(dir, kx) / dz, comp(dir, ky) / dz, 1.0f / dz);
+        tmin = tmin_; tmax = tmax_; committedT = tmax_;
+        haveHit = false; hitGeom = hitPrim = 0xffffffffu; hb1 = hb2 = 0.0f;
+        trisTested = boxesTested = 0;
+        sp = 0;
         float unusedT;
-        if (slab(unusedT, committedT, oinv, inv, ainv, bvh.root.c[0], bvh.root.c[1], bvh.root.c[2], bvh.root.h[0], bvh.root.h[1], bvh.root.h[2]))
+        if (slab(unusedT, committedT, oinv, inv, abs3(inv), bvh.root.c[0], bvh.root.c[1], bvh.root.c[2], bvh.root.h[0], bvh.root.h[1], bvh.root.h[2]))
             stack[sp++] = (bvh.root.flags & 0x80000000u) ? (0x80000000u | (bvh.root.flags & 0x3fffffffu)) : 0u;
     }
-    const float4* __restrict__ pairs = (const float4*)bvh.pairs;
-    const float4* __restrict__ tris = (const float4*)bvh.tris;
-    while (sp > 0) {
+    __device__ __forceinline__ bool done() const { return sp == 0; }
+
+    __device__ __forceinline__ void step(uint32_t* stack, const float4* __restrict__ pairs, const float4* __restrict__ tris) {
+        using namespace tbm;
         uint32_t ref = stack[--sp];
         if (ref & 0x80000000u) {
             uint32_t slot = ref & 0x3fffffffu;
             float4 q0 = __ldg(tris + 3 * (size_t)slot), q1 = __ldg(tris + 3 * (size_t)slot + 1), q2 = __ldg(tris + 3 * (size_t)slot + 2);
             trisTested++;
+            // RayTriangleIntersect, TraverseFunction.hlsli:231-313 (two-sided, `precise` => unfused)
             f3 v0 = mk3(q0.x, q0.y, q0.z) - org, v1 = mk3(q1.x, q1.y, q1.z) - org, v2 = mk3(q2.x, q2.y, q2.z) - org;
             float Ax = comp(v0, kx), Ay = comp(v0, ky), Az = comp(v0, kz);
             float Bx = comp(v1, kx), By = comp(v1, ky), Bz = comp(v1, kz);
@@ -90,7 +100,7 @@ __device__ __forceinline__ void trace_ray(const DeviceBvh& bvh, tbm::f3 org, tbm
                     float rcpDet = 1.0f / det;
                     float t0 = T * rcpDet;
                     uint32_t g = __float_as_uint(q0.w), p = __float_as_uint(q1.w);
-                    bool closer = t0 < committedT;
+                    bool closer = t0 < committedT; // TestLeafNodeIntersections :420 + equal-t tie-break
                     bool tie = haveHit && t0 == committedT && (g < hitGeom || (g == hitGeom && p < hitPrim));
                     if ((closer || tie) && t0 > tmin) {
                         committedT = t0; hb1 = V * rcpDet; hb2 = W * rcpDet; hitGeom = g; hitPrim = p; haveHit = true;
@@ -100,12 +110,13 @@ __device__ __forceinline__ void trace_ray(const DeviceBvh& bvh, tbm::f3 org, tbm
         } else {
             float4 a = __ldg(pairs + 4 * (size_t)ref), b = __ldg(pairs + 4 * (size_t)ref + 1);
             float4 c = __ldg(pairs + 4 * (size_t)ref + 2), d = __ldg(pairs + 4 * (size_t)ref + 3);
+            f3 ainv = abs3(inv);
             float lt, rt;
             bool lh = slab(lt, committedT, oinv, inv, ainv, a.x, a.y, a.z, b.x, b.y, b.z);
             bool rh = slab(rt, committedT, oinv, inv, ainv, c.x, c.y, c.z, d.x, d.y, d.z);
             boxesTested += 2;
             uint32_t lref = __float_as_uint(a.w), rref = __float_as_uint(b.w);
-            if (lh && rh) {
+            if (lh && rh) { // far child first, near child on top; left is near on equal t (:754-765)
                 bool rightFirst = rt < lt;
                 if (sp + 2 <= TB_STACK_DEPTH) {
                     stack[sp++] = rightFirst ? lref : rref;
@@ -116,10 +127,22 @@ __device__ __forceinline__ void trace_ray(const DeviceBvh& bvh, tbm::f3 org, tbm
             }
         }
     }
-    out.tris = trisTested;
-    out.boxes = boxesTested;
-    if (haveHit && committedT < tmax) { out.t = committedT; out.b1 = hb1; out.b2 = hb2; out.prim = hitPrim; out.geom = hitGeom; }
-    else { out.t = -1.0f; out.b1 = out.b2 = 0.0f; out.prim = out.geom = 0xffffffffu; }
+    __device__ __forceinline__ void result(HitRec& out) const {
+        out.tris = trisTested;
+        out.boxes = boxesTested;
+        if (haveHit && committedT < tmax) { out.t = committedT; out.b1 = hb1; out.b2 = hb2; out.prim = hitPrim; out.geom = hitGeom; }
+        else { out.t = -1.0f; out.b1 = out.b2 = 0.0f; out.prim = out.geom = 0xffffffffu; }
+    }
+};
+
+__device__ __forceinline__ void trace_ray(const DeviceBvh& bvh, tbm::f3 org, tbm::f3 dir, float tmin, float tmax, HitRec& out) {
+    Traversal tr;
+    uint32_t stack[TB_STACK_DEPTH];
+    tr.begin(bvh, stack, org, dir, tmin, tmax);
+    const float4* __restrict__ pairs = (const float4*)bvh.pairs;
+    const float4* __restrict__ tris = (const float4*)bvh.tris;
+    while (!tr.done()) tr.step(stack, pairs, tris);
+    tr.result(out);
 }
 
 } // namespace tbd

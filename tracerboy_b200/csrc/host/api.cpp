@@ -30,7 +30,14 @@ struct TbHandle {
     DeviceBvh bvh;
     double bvhBuildMs = 0.0;
     // render state
-    PathState st;
+    PathState st;                   // shared buffers (+ slot 0's private ones)
+    // Frames in flight: each slot owns private path state + staging and its own stream, so the
+    // long tail of one frame's traversal kernels overlaps the next frames' work. h->stream is
+    // the accumulate stream: k_accumulate runs there in frame order.
+    struct Slot { PathState st; cudaStream_t stream = nullptr; cudaEvent_t frameDone = nullptr, accDone = nullptr; };
+    std::vector<Slot> slots;
+    uint32_t framesInFlight = 8;
+    uint64_t framesIssued = 0;
     std::vector<void*> frameAllocs;
     float* resolved = nullptr;
     uint32_t width = 0, height = 0;
@@ -98,6 +105,12 @@ static void free_scene(TbHandle* h) {
 }
 
 static void free_frame(TbHandle* h) {
+    for (auto& sl : h->slots) {
+        if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+        if (sl.frameDone) cudaEventDestroy(sl.frameDone);
+        if (sl.accDone) cudaEventDestroy(sl.accDone);
+    }
+    h->slots.clear();
     free_list(h->frameAllocs);
     h->st = PathState();
     h->resolved = nullptr;
@@ -351,12 +364,6 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
         return e;
     };
     PathState& st = h->st;
-    CUDA_OK(h, alloc((void**)&st.rayO, 16 * n)); CUDA_OK(h, alloc((void**)&st.rayD, 16 * n));
-    CUDA_OK(h, alloc((void**)&st.thr, 16 * n)); CUDA_OK(h, alloc((void**)&st.col, 16 * n));
-    CUDA_OK(h, alloc((void**)&st.hit, 16 * n)); CUDA_OK(h, alloc((void**)&st.hitGeom, 4 * n));
-    CUDA_OK(h, alloc((void**)&st.neighbor, 16 * n)); CUDA_OK(h, alloc((void**)&st.neighborDir, 16 * n));
-    CUDA_OK(h, alloc((void**)&st.queue[0], 4 * n)); CUDA_OK(h, alloc((void**)&st.queue[1], 4 * n));
-    CUDA_OK(h, alloc((void**)&st.queueCount, 16));
     CUDA_OK(h, alloc((void**)&st.accum, 16 * n)); CUDA_OK(h, alloc((void**)&st.jittered, 16 * n));
     CUDA_OK(h, alloc((void**)&st.aovAlbedo, 16 * n)); CUDA_OK(h, alloc((void**)&st.aovNormal, 16 * n));
     CUDA_OK(h, alloc((void**)&st.aovEmissive, 16 * n));
@@ -364,7 +371,24 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
     CUDA_OK(h, alloc((void**)&st.aovDepth, 4 * n));
     CUDA_OK(h, alloc((void**)&st.primaryHit, 8 * n)); CUDA_OK(h, alloc((void**)&st.counters, 8 * n));
     CUDA_OK(h, alloc((void**)&st.stats, 64)); CUDA_OK(h, alloc((void**)&st.readbackStats, sizeof(TbReadbackStats)));
+    h->slots.resize(h->framesInFlight);
+    for (auto& sl : h->slots) {
+        sl.st = st; // shared pointers
+        PathState& p = sl.st;
+        CUDA_OK(h, alloc((void**)&p.rayO, 16 * n)); CUDA_OK(h, alloc((void**)&p.rayD, 16 * n));
+        CUDA_OK(h, alloc((void**)&p.thr, 16 * n)); CUDA_OK(h, alloc((void**)&p.col, 16 * n));
+        CUDA_OK(h, alloc((void**)&p.hit, 16 * n)); CUDA_OK(h, alloc((void**)&p.hitGeom, 4 * n));
+        CUDA_OK(h, alloc((void**)&p.neighbor, 16 * n)); CUDA_OK(h, alloc((void**)&p.neighborDir, 16 * n));
+        CUDA_OK(h, alloc((void**)&p.queue[0], 4 * n)); CUDA_OK(h, alloc((void**)&p.queue[1], 4 * n));
+        CUDA_OK(h, alloc((void**)&p.queueCount, 16));
+        CUDA_OK(h, alloc((void**)&p.sample, 16 * n)); CUDA_OK(h, alloc((void**)&p.sampleSeed, 4 * n));
+        CUDA_OK(h, alloc((void**)&p.stEmissive, 16 * n)); CUDA_OK(h, alloc((void**)&p.stDepth, 4 * n));
+        CUDA_OK(h, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        CUDA_OK(h, cudaEventCreateWithFlags(&sl.frameDone, cudaEventDisableTiming));
+        CUDA_OK(h, cudaEventCreateWithFlags(&sl.accDone, cudaEventDisableTiming));
+    }
     CUDA_OK(h, alloc((void**)&h->resolved, 12 * n));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream)); // memsets done before the slot streams touch the buffers
     h->width = w; h->height = hh;
     h->samplesRendered = 0;
     return TB_OK;
@@ -394,11 +418,19 @@ TB_API int tb_render(TbHandle* h, const TbOutputSettings* s, uint32_t nSamples, 
     if (s->MaxBounces < 0 || s->MaxBounces > 255) return fail(h, TB_ERR_INVALID_ARG, "MaxBounces must be in [0,255]");
     CUDA_OK(h, cudaSetDevice(h->device));
     if (h->samplesRendered == 0) { h->renderStart = std::chrono::steady_clock::now(); }
+    // sample / time limits, TracerBoy.cpp:2679-2682. With a time limit the frames are issued one at
+    // a time (the last frame is not known in advance and it must own the AOVs).
+    uint32_t todo = nSamples;
+    if (s->SampleLimit > 0) {
+        uint32_t left = (int)h->samplesRendered >= s->SampleLimit ? 0u : (uint32_t)s->SampleLimit - h->samplesRendered;
+        if (todo > left) todo = left;
+    }
+    const bool timeLimited = s->TimeLimitInSeconds > 0.0f;
+    const bool serial = timeLimited || h->profiling;
     CUDA_OK(h, cudaEventRecord(h->ev0, h->stream));
-    for (uint32_t i = 0; i < nSamples; i++) {
-        // sample / time limits, TracerBoy.cpp:2679-2682
-        if (s->SampleLimit > 0 && (int)h->samplesRendered >= s->SampleLimit) break;
-        if (s->TimeLimitInSeconds > 0.0f &&
+    for (auto& sl : h->slots) CUDA_OK(h, cudaStreamWaitEvent(sl.stream, h->ev0, 0)); // slot streams start after ev0
+    for (uint32_t i = 0; i < todo; i++) {
+        if (timeLimited &&
             std::chrono::duration<float>(std::chrono::steady_clock::now() - h->renderStart).count() >= s->TimeLimitInSeconds) break;
         FrameConstants fc;
         memset(&fc, 0, sizeof(fc));
@@ -411,7 +443,17 @@ TB_API int tb_render(TbHandle* h, const TbOutputSettings* s, uint32_t nSamples, 
         fc.halton2 = halton(2, (int)fc.frame);
         fc.halton3 = halton(3, (int)fc.frame);
         fc.clearAccum = h->samplesRendered == 0;
-        CUDA_OK(h, render_frame(h->bvh, h->dscene, fc, h->st, h->stream, h->lc, h->profiling ? &h->timers : nullptr));
+        const bool last = serial || i + 1 == todo;
+        fc.aovMask = last ? 3u : (i + 2 == todo ? 2u : 0u);
+        TbHandle::Slot& sl = h->slots[serial ? 0 : h->framesIssued % h->slots.size()];
+        // the slot's previous frame must have been consumed by its k_accumulate
+        CUDA_OK(h, cudaStreamWaitEvent(sl.stream, sl.accDone, 0));
+        CUDA_OK(h, render_frame(h->bvh, h->dscene, fc, sl.st, sl.stream, h->lc, h->profiling ? &h->timers : nullptr));
+        CUDA_OK(h, cudaEventRecord(sl.frameDone, sl.stream));
+        CUDA_OK(h, cudaStreamWaitEvent(h->stream, sl.frameDone, 0));
+        CUDA_OK(h, accumulate_frame(fc, sl.st, h->stream, h->lc)); // frame order == issue order on h->stream
+        CUDA_OK(h, cudaEventRecord(sl.accDone, h->stream));
+        h->framesIssued++;
         h->samplesRendered++;
         h->pathsStarted += (uint64_t)h->width * h->height;
         if (h->profiling && h->timers.used > 4096) { // bound the number of live events
@@ -523,6 +565,19 @@ TB_API int tb_reset_render_stats(TbHandle* h) {
     if (h->st.stats) { CUDA_OK(h, cudaSetDevice(h->device)); CUDA_OK(h, cudaMemsetAsync(h->st.stats, 0, 64, h->stream)); }
     h->pathsStarted = 0; h->lc.count = 0; h->deviceMs = 0.0;
     h->extendMs = h->shadeMs = 0.0; h->extendLaunches = 0;
+    return TB_OK;
+}
+TB_API int tb_set_frames_in_flight(TbHandle* h, uint32_t n) {
+    if (!h || n == 0 || n > 64) return fail(h, TB_ERR_INVALID_ARG, "frames in flight must be in [1,64]");
+    if (n == h->framesInFlight) return TB_OK;
+    h->framesInFlight = n;
+    if (h->width) { // re-create the frame buffers with the new slot count
+        uint32_t w = h->width, hh = h->height;
+        CUDA_OK(h, cudaSetDevice(h->device));
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+        free_frame(h);
+        return tb_resize(h, w, hh);
+    }
     return TB_OK;
 }
 TB_API int tb_set_profiling(TbHandle* h, int enable) {
