@@ -27,6 +27,7 @@ import subprocess
 import sys
 import time
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # frames in flight: one HW queue per stream, before CUDA starts
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -304,6 +305,7 @@ def main():
     g.Render(s, min(spp, 16), 0.0)
     pst = g.GetRenderStats()
     g.SetProfiling(False)
+    # rays that finish inside k_extend (the rest are suspended and finish in k_extend_resume, timed separately)
     alg_bytes = 32.0 * pst.ExtendBoxesTested + 40.0 * pst.ExtendTrianglesTested + 64.0 * pst.ExtendRays
     peak, peak_src = measured_peak_gbs()
     ext_s = pst.ExtendMilliseconds / 1e3
@@ -314,7 +316,11 @@ def main():
         "frac": achieved / peak, "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
         "algorithmic_bytes_per_launch": alg_bytes / max(1, pst.ExtendLaunches),
         "avg_launch_ms": pst.ExtendMilliseconds / max(1, pst.ExtendLaunches), "launches": pst.ExtendLaunches,
-        "kernel_share_of_step": pst.ExtendMilliseconds / max(1e-9, pst.ExtendMilliseconds + pst.ShadeMilliseconds),
+        "kernel_share_of_step": pst.ExtendMilliseconds / max(1e-9, pst.ExtendMilliseconds + pst.ShadeMilliseconds + pst.ResumeMilliseconds),
+        "resume_rounds": {"rays": pst.ResumeRays, "ms": pst.ResumeMilliseconds,
+                          "algorithmic_bytes": 32.0 * pst.ResumeBoxesTested + 40.0 * pst.ResumeTrianglesTested + 64.0 * pst.ResumeRays},
+        # all rays of the timed region (every kernel, frames in flight overlapped) over the whole step time
+        "whole_step_algorithmic_GBps": world * (32.0 * st.BoxesTested + 40.0 * st.TrianglesTested + 64.0 * st.RaysTraced) / t_step / 1e9,
         "peak_source": peak_src,
         "note": "algorithmic bytes = 32 B x BoxesTested + 40 B x TrianglesTested + 64 B ray/hit (reference BVH2 layout); "
                 "a BVH that fits the 126 MB L2 is served from L2, so frac can exceed DRAM-only expectations",

@@ -288,6 +288,9 @@ typedef struct TbRenderStats {
     uint64_t ExtendLaunches;
     double ExtendMilliseconds;
     double ShadeMilliseconds;
+    /* rays that were suspended and finished in a k_extend_resume round */
+    uint64_t ResumeRays, ResumeBoxesTested, ResumeTrianglesTested;
+    double ResumeMilliseconds;
 } TbRenderStats;
 
 typedef struct TbHandle TbHandle; /* opaque; owns all device memory */
@@ -346,8 +349,8 @@ TB_API int tb_reset_render_stats(TbHandle* h);
 /* Profiling mode: record CUDA events around every traversal / shading launch (small
  * overhead; off by default). Results appear in TbRenderStats.Extend/ShadeMilliseconds. */
 TB_API int tb_set_profiling(TbHandle* h, int enable);
-/* Number of frames (samples) kept in flight on independent CUDA streams (default 8). The
- * result does not depend on it: samples are added to the accumulation buffer in frame order. */
+/* Number of frames (samples) kept in flight on independent CUDA streams (0 = automatic:
+ * as many as fit a 12 GB budget, between 4 and 32). The result does not depend on it: samples are added to the accumulation buffer in frame order. */
 TB_API int tb_set_frames_in_flight(TbHandle* h, uint32_t n);
 TB_API int tb_synchronize(TbHandle* h);
 

@@ -5,6 +5,11 @@ is a thin ctypes mirror of the reference's `class TracerBoy` (TracerBoy/TracerBo
 There is no CPU fallback: importing works anywhere, but every compute call raises
 TracerBoyError when the CUDA library or a CUDA device is missing.
 """
+import os as _os
+
+# frames in flight use independent CUDA streams: ask for more hardware queues before CUDA starts
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from .api import (TracerBoy, TracerBoyError, OutputSettings, Camera, Material, Ray, Hit, RenderStats,
                   SceneInfo, BufferKind, lib_path, load_library, convert_scene, get_default_output_settings)
 

@@ -66,7 +66,9 @@ class RenderStats(C.Structure):
     _fields_ = [("RaysTraced", C.c_uint64), ("BoxesTested", C.c_uint64), ("TrianglesTested", C.c_uint64),
                 ("PathsStarted", C.c_uint64), ("KernelLaunches", C.c_uint64), ("DeviceMilliseconds", C.c_double),
                 ("ExtendRays", C.c_uint64), ("ExtendBoxesTested", C.c_uint64), ("ExtendTrianglesTested", C.c_uint64),
-                ("ExtendLaunches", C.c_uint64), ("ExtendMilliseconds", C.c_double), ("ShadeMilliseconds", C.c_double)]
+                ("ExtendLaunches", C.c_uint64), ("ExtendMilliseconds", C.c_double), ("ShadeMilliseconds", C.c_double),
+                ("ResumeRays", C.c_uint64), ("ResumeBoxesTested", C.c_uint64), ("ResumeTrianglesTested", C.c_uint64),
+                ("ResumeMilliseconds", C.c_double)]
 
 
 class SceneInfo(C.Structure):

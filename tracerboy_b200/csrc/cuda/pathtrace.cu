@@ -17,6 +17,7 @@
 // reference's sequential per-pixel rand() stream in the reference's order (SURVEY
 // Appendix A) so that results are bit-identical to the CPU oracle.
 #include <cstdio>
+#include <cstdlib>
 #include "../common/tb_vec.h"
 #include "device_types.h"
 #include "launch.h"
@@ -381,7 +382,10 @@ __device__ __forceinline__ uint32_t pack_state(int bounce, bool prevSpec) { retu
 __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, FrameConstants fc, PathState st) {
     uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n = fc.width * fc.height;
-    if (pi == 0) { st.queueCount[0] = n; st.queueCount[1] = 0; st.queueCount[2] = 0; st.queueCount[3] = 0; }
+    if (pi == 0) {
+        st.queueCount[0] = n; st.queueCount[1] = 0; st.queueCount[2] = 0; st.queueCount[3] = 0;
+        for (int r = 0; r < 4; r++) st.susCount[r] = 0;
+    }
     if (pi >= n) return;
     uint32_t px = pi % fc.width, py = pi / fc.width;
     Rng rng;
@@ -453,7 +457,48 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, FrameConstants f
 // warp-aggregated atomic, and traversal resumes. (A static assignment ran at 3.5 active
 // lanes per instruction on the incoherent bounces of the Teapot scene — profiles/.)
 #define REFILL_THRESHOLD 20
-__global__ void __launch_bounds__(128) k_extend(DeviceBvh bvh, PathState st, int qi, int bounceIsZero, uint32_t outputHeatmap, uint32_t aovMask) {
+// Step budgets: a ray that is still traversing after `budget` node visits in one kernel is
+// suspended (Traversal::suspend) and resumed by the next k_extend_resume round, where it shares
+// a warp with other long rays instead of pinning a 1-active-lane warp of the main kernel.
+// On the Teapot scene the median ray needs 8 visits, the 99th percentile 155 and the maximum
+// about 6600 (triangle fans at the teapot's poles).
+#define EXTEND_BUDGET_MAIN 160u
+#define EXTEND_RESUME_ROUNDS 3
+
+__device__ __forceinline__ void write_hit(PathState& st, const Traversal& tr, uint32_t pi, int bounceIsZero, uint32_t outputHeatmap,
+                                          uint32_t aovMask, uint32_t& rays, uint32_t& ntris, uint32_t& nboxes) {
+    HitRec h;
+    tr.result(h);
+    st.hit[pi] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
+    st.hitGeom[pi] = h.geom;
+    if (aovMask & AOV_FULL) {
+        uint2 c = st.counters[pi];
+        c.x += h.tris; c.y += h.boxes;
+        st.counters[pi] = c;
+        if (bounceIsZero) st.primaryHit[pi] = make_uint2(h.geom, h.prim);
+        if (outputHeatmap) st.aovAlbedo[pi] = make_float4((float)h.tris, (float)h.boxes, 0.0f, 0.0f);
+    }
+    rays++; ntris += h.tris; nboxes += h.boxes;
+}
+
+__device__ __forceinline__ void flush_stats(PathState& st, int slot, uint32_t rays, uint32_t ntris, uint32_t nboxes) {
+    for (int o = 16; o > 0; o >>= 1) {
+        rays += __shfl_xor_sync(0xffffffffu, rays, o); ntris += __shfl_xor_sync(0xffffffffu, ntris, o); nboxes += __shfl_xor_sync(0xffffffffu, nboxes, o);
+    }
+    if ((threadIdx.x & 31) == 0 && rays) {
+        atomicAdd(&st.stats[slot], (unsigned long long)rays); atomicAdd(&st.stats[slot + 1], (unsigned long long)nboxes); atomicAdd(&st.stats[slot + 2], (unsigned long long)ntris);
+    }
+}
+
+// park the ray; returns false when the suspension buffer is full (caller keeps traversing)
+__device__ __forceinline__ bool try_suspend(PathState& st, int round, const Traversal& tr, const uint32_t* stack, uint32_t pi) {
+    uint32_t slot = atomicAdd(&st.susCount[round], 1u);
+    if (slot >= st.susCapacity) { atomicSub(&st.susCount[round], 1u); return false; }
+    tr.suspend(st.susBuf[round & 1] + (size_t)slot * Traversal::kRecordWords, stack, pi);
+    return true;
+}
+
+__global__ void __launch_bounds__(128) k_extend(DeviceBvh bvh, PathState st, int qi, int bounceIsZero, uint32_t outputHeatmap, uint32_t aovMask, uint32_t budgetMain) {
     const uint32_t count = st.queueCount[qi];
     if (blockIdx.x == 0 && threadIdx.x == 0) st.queueCount[qi ^ 1] = 0; // next queue starts empty (consumed by k_shade)
     uint32_t* __restrict__ next = &st.queueCount[2 + qi];               // work counter, zeroed by the previous kernel
@@ -466,7 +511,7 @@ __global__ void __launch_bounds__(128) k_extend(DeviceBvh bvh, PathState st, int
     uint32_t stack[TB_STACK_DEPTH];
     tr.sp = 0;
     bool active = false, exhausted = false;
-    uint32_t pi = 0;
+    uint32_t pi = 0, steps = 0;
     while (true) {
         uint32_t idle = __ballot_sync(0xffffffffu, !active);
         if (idle && !exhausted) {
@@ -480,6 +525,7 @@ __global__ void __launch_bounds__(128) k_extend(DeviceBvh bvh, PathState st, int
                     float4 o = st.rayO[pi], d = st.rayD[pi];
                     tr.begin(bvh, stack, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), MIN_T, FAR_T);
                     active = true;
+                    steps = 0;
                 }
             }
             if (base + (uint32_t)__popc(idle) >= count) exhausted = true;
@@ -488,34 +534,48 @@ __global__ void __launch_bounds__(128) k_extend(DeviceBvh bvh, PathState st, int
         if (active) {
             while (true) {
                 if (tr.done()) {
-                    HitRec h;
-                    tr.result(h);
-                    st.hit[pi] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
-                    st.hitGeom[pi] = h.geom;
-                    if (aovMask & AOV_FULL) {
-                        uint2 c = st.counters[pi];
-                        c.x += h.tris; c.y += h.boxes;
-                        st.counters[pi] = c;
-                        if (bounceIsZero) st.primaryHit[pi] = make_uint2(h.geom, h.prim);
-                        if (outputHeatmap) st.aovAlbedo[pi] = make_float4((float)h.tris, (float)h.boxes, 0.0f, 0.0f);
-                    }
-                    rays++; ntris += h.tris; nboxes += h.boxes;
+                    write_hit(st, tr, pi, bounceIsZero, outputHeatmap, aovMask, rays, ntris, nboxes);
                     active = false;
                     break;
                 }
+                if (steps >= budgetMain) {
+                    if (try_suspend(st, 0, tr, stack, pi)) { active = false; break; }
+                    steps = 0; // buffer full: keep going here
+                }
                 tr.step(stack, pairs, tris);
+                steps++;
                 // regroup for a refill when the warp has thinned out (heuristic only: results do not depend on it)
                 if (!exhausted && __popc(__activemask()) < REFILL_THRESHOLD) break;
             }
         }
     }
-    // warp-reduced global statistics
-    for (int o = 16; o > 0; o >>= 1) {
-        rays += __shfl_xor_sync(0xffffffffu, rays, o); ntris += __shfl_xor_sync(0xffffffffu, ntris, o); nboxes += __shfl_xor_sync(0xffffffffu, nboxes, o);
+    flush_stats(st, 0, rays, ntris, nboxes);
+}
+
+// Resume round `round` (1-based): continues the rays parked by round-1; the last round has no budget.
+__global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState st, int round, uint32_t budget, int bounceIsZero,
+                                                       uint32_t outputHeatmap, uint32_t aovMask) {
+    const uint32_t count = min(st.susCount[round - 1], st.susCapacity);
+    const float4* __restrict__ pairs = (const float4*)bvh.pairs;
+    const float4* __restrict__ tris = (const float4*)bvh.tris;
+    const uint32_t* __restrict__ in = st.susBuf[(round - 1) & 1];
+    uint32_t rays = 0, ntris = 0, nboxes = 0;
+    Traversal tr;
+    uint32_t stack[TB_STACK_DEPTH];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        uint32_t pi = tr.resume(bvh, in + (size_t)i * Traversal::kRecordWords, stack, st.rayO, st.rayD, MIN_T, FAR_T);
+        uint32_t steps = 0;
+        while (true) {
+            if (tr.done()) { write_hit(st, tr, pi, bounceIsZero, outputHeatmap, aovMask, rays, ntris, nboxes); break; }
+            if (budget && steps >= budget) {
+                if (try_suspend(st, round, tr, stack, pi)) break;
+                steps = 0;
+            }
+            tr.step(stack, pairs, tris);
+            steps++;
+        }
     }
-    if (lane == 0 && rays) {
-        atomicAdd(&st.stats[0], (unsigned long long)rays); atomicAdd(&st.stats[1], (unsigned long long)nboxes); atomicAdd(&st.stats[2], (unsigned long long)ntris);
-    }
+    flush_stats(st, 6, rays, ntris, nboxes);
 }
 
 // ----------------------------------------------------------------------- shade
@@ -533,7 +593,10 @@ __device__ __forceinline__ void finish_path(const FrameConstants& fc, PathState&
 
 __global__ void __launch_bounds__(128) k_shade(DeviceBvh bvh, DeviceScene sc, FrameConstants fc, PathState st, int qi) {
     const uint32_t count = st.queueCount[qi];
-    if (blockIdx.x == 0 && threadIdx.x == 0) st.queueCount[2 + (qi ^ 1)] = 0; // work counter of the next k_extend
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st.queueCount[2 + (qi ^ 1)] = 0; // work counter of the next k_extend
+        for (int r = 0; r < 4; r++) st.susCount[r] = 0; // suspension counters of the next bounce
+    }
     const TbOutputSettings& S = fc.settings;
     const int MaxBounces = S.MaxBounces;
     RayCount rc = {0, 0, 0};
@@ -819,7 +882,22 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
     for (int b = 0; b < maxBounces; b++) {
         int qi = b & 1;
         if (timers) cudaEventRecord(timers->next(KernelTimers::EXTEND), stream);
-        k_extend<<<blocks, 128, 0, stream>>>(bvh, st, qi, b == 0, heat, fc.aovMask); lc.count++;
+        static int suspendMode = -1;
+        static uint32_t budgetMain = EXTEND_BUDGET_MAIN, budgets[EXTEND_RESUME_ROUNDS] = {384u, 1536u, 0u};
+        if (suspendMode < 0) { // tuning knobs (results never depend on them)
+            const char* e = getenv("TB_SUSPEND"); suspendMode = e ? atoi(e) : 1;
+            if (const char* bs = getenv("TB_BUDGETS")) sscanf(bs, "%u,%u,%u", &budgetMain, &budgets[0], &budgets[1]);
+        }
+        k_extend<<<blocks, 128, 0, stream>>>(bvh, st, qi, b == 0, heat, fc.aovMask, suspendMode ? budgetMain : 0xffffffffu); lc.count++;
+        if (suspendMode) {
+            uint32_t rblocks = (st.susCapacity + 127) / 128;
+            if (rblocks > sms * 4) rblocks = sms * 4;
+            if (timers) cudaEventRecord(timers->next(KernelTimers::RESUME), stream);
+            for (int r = 1; r <= EXTEND_RESUME_ROUNDS; r++) {
+                k_extend_resume<<<rblocks, 128, 0, stream>>>(bvh, st, r, budgets[r - 1], b == 0, heat, fc.aovMask); lc.count++;
+                rblocks = (rblocks + 3) / 4 > sms ? (rblocks + 3) / 4 : sms;
+            }
+        }
         if (timers) cudaEventRecord(timers->next(KernelTimers::SHADE), stream);
         k_shade<<<blocks, 128, 0, stream>>>(bvh, sc, fc, st, qi); lc.count++;
         if (timers) cudaEventRecord(timers->next(KernelTimers::END), stream);

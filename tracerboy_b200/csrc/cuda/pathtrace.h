@@ -19,6 +19,10 @@ struct PathState {
     float4* neighborDir = nullptr; // neighbour camera ray direction
     uint32_t* queue[2] = {nullptr, nullptr};
     uint32_t* queueCount = nullptr; // [0..1] queue sizes, [2..3] k_extend work counters
+    // suspended long rays: two ping-pong record buffers, one counter per round
+    uint32_t* susBuf[2] = {nullptr, nullptr};
+    uint32_t* susCount = nullptr;   // 4 counters
+    uint32_t susCapacity = 0;       // records per buffer
     // per-frame staging consumed by k_accumulate (frames in flight finish out of order)
     float4* sample = nullptr;      // (rgb * w, w) after firefly clamp and NaN rejection
     float* sampleSeed = nullptr;   // the path's rand() seed at termination (jittered-buffer coin)
@@ -34,14 +38,14 @@ struct PathState {
     float* aovDepth = nullptr;
     uint2* primaryHit = nullptr;
     uint2* counters = nullptr;     // per pixel (TrianglesTested, BoxesTested) of the current frame
-    unsigned long long* stats = nullptr; // [0..2] extend-stage rays, boxes, tris; [3..5] same for rays traced inside k_shade
+    unsigned long long* stats = nullptr; // rays, boxes, tris finished in: [0..2] k_extend, [3..5] inside k_shade, [6..8] k_extend_resume
     TbReadbackStats* readbackStats = nullptr;
 };
 
 // Optional per-kernel timing (profiling mode): CUDA events recorded on the launching stream
 // around every k_extend / k_shade launch; resolved by the caller after a stream sync.
 struct KernelTimers {
-    enum Tag { EXTEND = 0, SHADE = 1, END = 2 };
+    enum Tag { EXTEND = 0, SHADE = 1, END = 2, RESUME = 3 };
     std::vector<cudaEvent_t> events;
     std::vector<int> tags;
     size_t used = 0;
@@ -51,12 +55,14 @@ struct KernelTimers {
         return events[used++];
     }
     // adds elapsed ms per tag, returns number of (extend, shade) launch pairs
-    void resolve(double& extendMs, double& shadeMs, uint64_t& extendLaunches) {
+    void resolve(double& extendMs, double& shadeMs, double& resumeMs, uint64_t& extendLaunches) {
         for (size_t i = 0; i + 1 < used; i++) {
             if (tags[i] == END) continue;
             float ms = 0;
             cudaEventElapsedTime(&ms, events[i], events[i + 1]);
-            if (tags[i] == EXTEND) { extendMs += ms; extendLaunches++; } else shadeMs += ms;
+            if (tags[i] == EXTEND) { extendMs += ms; extendLaunches++; }
+            else if (tags[i] == RESUME) resumeMs += ms;
+            else shadeMs += ms;
         }
         used = 0;
     }

@@ -127,6 +127,32 @@ struct Traversal {
             }
         }
     }
+    // ---- suspension: a long ray can be parked in global memory and resumed by a later kernel
+    // in a warp of similarly long rays. The state is exactly the registers below plus the live
+    // part of the stack, so pausing never changes the visit order or the counters.
+    static constexpr int kRecordWords = 112; // 12-word header + TB_STACK_DEPTH entries, 16 B aligned
+    __device__ __forceinline__ void suspend(uint32_t* __restrict__ rec, const uint32_t* stack, uint32_t pi) const {
+        uint4* r4 = (uint4*)rec;
+        r4[0] = make_uint4(pi, (uint32_t)sp, __float_as_uint(committedT), __float_as_uint(hb1));
+        r4[1] = make_uint4(__float_as_uint(hb2), hitGeom, hitPrim, haveHit ? 1u : 0u);
+        r4[2] = make_uint4(trisTested, boxesTested, 0u, 0u);
+        for (int i = 0; i < sp; i++) rec[12 + i] = stack[i];
+    }
+    // ray setup is recomputed from the ray (same arithmetic => same values), the rest is restored
+    __device__ __forceinline__ uint32_t resume(const DeviceBvh& bvh, const uint32_t* __restrict__ rec, uint32_t* stack,
+                                               const float4* __restrict__ rayO, const float4* __restrict__ rayD, float tmin_, float tmax_) {
+        const uint4* r4 = (const uint4*)rec;
+        uint4 a = r4[0], b = r4[1], c = r4[2];
+        uint32_t pi = a.x;
+        float4 o = rayO[pi], d = rayD[pi];
+        begin(bvh, stack, tbm::mk3(o.x, o.y, o.z), tbm::mk3(d.x, d.y, d.z), tmin_, tmax_);
+        sp = (int)a.y; committedT = __uint_as_float(a.z); hb1 = __uint_as_float(a.w);
+        hb2 = __uint_as_float(b.x); hitGeom = b.y; hitPrim = b.z; haveHit = b.w != 0;
+        trisTested = c.x; boxesTested = c.y;
+        for (int i = 0; i < sp; i++) stack[i] = rec[12 + i];
+        return pi;
+    }
+
     __device__ __forceinline__ void result(HitRec& out) const {
         out.tris = trisTested;
         out.boxes = boxesTested;

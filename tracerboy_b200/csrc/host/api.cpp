@@ -36,7 +36,7 @@ struct TbHandle {
     // the accumulate stream: k_accumulate runs there in frame order.
     struct Slot { PathState st; cudaStream_t stream = nullptr; cudaEvent_t frameDone = nullptr, accDone = nullptr; };
     std::vector<Slot> slots;
-    uint32_t framesInFlight = 8;
+    uint32_t framesInFlight = 0;    // 0 = automatic (memory budget), see tb_resize
     uint64_t framesIssued = 0;
     std::vector<void*> frameAllocs;
     float* resolved = nullptr;
@@ -56,7 +56,7 @@ struct TbHandle {
     std::vector<uint8_t> blueNoiseHost;
     bool profiling = false;
     KernelTimers timers;
-    double extendMs = 0.0, shadeMs = 0.0;
+    double extendMs = 0.0, shadeMs = 0.0, resumeMs = 0.0;
     uint64_t extendLaunches = 0;
 };
 
@@ -198,6 +198,9 @@ TB_API const char* tb_last_error(TbHandle* h) { return h ? h->err.c_str() : g_cr
 TB_API int tb_create(int device, TbHandle** out) {
     if (!out) return fail(nullptr, TB_ERR_INVALID_ARG, "out is null");
     *out = nullptr;
+    // Frames in flight run on independent streams; the default of 8 hardware queues would
+    // serialise them. Only effective if the CUDA context of this process does not exist yet.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -370,8 +373,18 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
     CUDA_OK(h, alloc((void**)&st.aovWorldPos[0], 16 * n)); CUDA_OK(h, alloc((void**)&st.aovWorldPos[1], 16 * n));
     CUDA_OK(h, alloc((void**)&st.aovDepth, 4 * n));
     CUDA_OK(h, alloc((void**)&st.primaryHit, 8 * n)); CUDA_OK(h, alloc((void**)&st.counters, 8 * n));
-    CUDA_OK(h, alloc((void**)&st.stats, 64)); CUDA_OK(h, alloc((void**)&st.readbackStats, sizeof(TbReadbackStats)));
-    h->slots.resize(h->framesInFlight);
+    CUDA_OK(h, alloc((void**)&st.stats, 128)); CUDA_OK(h, alloc((void**)&st.readbackStats, sizeof(TbReadbackStats)));
+    {
+        // private state per slot: 5 float4 + hitGeom + 2 float4 + 2 queues + staging (float4+float+float4+float)
+        // + 2 suspension buffers. Automatic policy: as many slots as fit ~12 GB, between 4 and 32.
+        size_t perSlot = n * (80 + 4 + 32 + 8 + 40) + 2 * (n / 16 + 1024) * 448;
+        uint32_t fif = h->framesInFlight;
+        if (fif == 0) {
+            size_t fit = ((size_t)12 << 30) / perSlot;
+            fif = (uint32_t)(fit < 4 ? 4 : (fit > 32 ? 32 : fit));
+        }
+        h->slots.resize(fif);
+    }
     for (auto& sl : h->slots) {
         sl.st = st; // shared pointers
         PathState& p = sl.st;
@@ -381,6 +394,9 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
         CUDA_OK(h, alloc((void**)&p.neighbor, 16 * n)); CUDA_OK(h, alloc((void**)&p.neighborDir, 16 * n));
         CUDA_OK(h, alloc((void**)&p.queue[0], 4 * n)); CUDA_OK(h, alloc((void**)&p.queue[1], 4 * n));
         CUDA_OK(h, alloc((void**)&p.queueCount, 16));
+        p.susCapacity = (uint32_t)(n / 16 + 1024);
+        CUDA_OK(h, alloc((void**)&p.susBuf[0], (size_t)p.susCapacity * 448)); CUDA_OK(h, alloc((void**)&p.susBuf[1], (size_t)p.susCapacity * 448));
+        CUDA_OK(h, alloc((void**)&p.susCount, 16));
         CUDA_OK(h, alloc((void**)&p.sample, 16 * n)); CUDA_OK(h, alloc((void**)&p.sampleSeed, 4 * n));
         CUDA_OK(h, alloc((void**)&p.stEmissive, 16 * n)); CUDA_OK(h, alloc((void**)&p.stDepth, 4 * n));
         CUDA_OK(h, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
@@ -458,7 +474,7 @@ TB_API int tb_render(TbHandle* h, const TbOutputSettings* s, uint32_t nSamples, 
         h->pathsStarted += (uint64_t)h->width * h->height;
         if (h->profiling && h->timers.used > 4096) { // bound the number of live events
             CUDA_OK(h, cudaStreamSynchronize(h->stream));
-            h->timers.resolve(h->extendMs, h->shadeMs, h->extendLaunches);
+            h->timers.resolve(h->extendMs, h->shadeMs, h->resumeMs, h->extendLaunches);
         }
     }
     CUDA_OK(h, cudaEventRecord(h->ev1, h->stream));
@@ -466,7 +482,7 @@ TB_API int tb_render(TbHandle* h, const TbOutputSettings* s, uint32_t nSamples, 
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->deviceMs += ms;
-    if (h->profiling) h->timers.resolve(h->extendMs, h->shadeMs, h->extendLaunches);
+    if (h->profiling) h->timers.resolve(h->extendMs, h->shadeMs, h->resumeMs, h->extendLaunches);
     CUDA_OK(h, cudaGetLastError());
     return TB_OK;
 }
@@ -547,14 +563,15 @@ TB_API int tb_get_render_stats(TbHandle* h, TbRenderStats* out) {
     if (!h || !out) return fail(h, TB_ERR_INVALID_ARG, "null argument");
     memset(out, 0, sizeof(*out));
     if (h->st.stats) {
-        unsigned long long s[6];
+        unsigned long long s[9];
         CUDA_OK(h, cudaSetDevice(h->device));
         CUDA_OK(h, cudaMemcpyAsync(s, h->st.stats, sizeof(s), cudaMemcpyDeviceToHost, h->stream));
         CUDA_OK(h, cudaStreamSynchronize(h->stream));
-        out->RaysTraced = s[0] + s[3]; out->BoxesTested = s[1] + s[4]; out->TrianglesTested = s[2] + s[5];
+        out->RaysTraced = s[0] + s[3] + s[6]; out->BoxesTested = s[1] + s[4] + s[7]; out->TrianglesTested = s[2] + s[5] + s[8];
         out->ExtendRays = s[0]; out->ExtendBoxesTested = s[1]; out->ExtendTrianglesTested = s[2];
+        out->ResumeRays = s[6]; out->ResumeBoxesTested = s[7]; out->ResumeTrianglesTested = s[8];
     }
-    out->ExtendLaunches = h->extendLaunches; out->ExtendMilliseconds = h->extendMs; out->ShadeMilliseconds = h->shadeMs;
+    out->ExtendLaunches = h->extendLaunches; out->ExtendMilliseconds = h->extendMs; out->ShadeMilliseconds = h->shadeMs; out->ResumeMilliseconds = h->resumeMs;
     out->PathsStarted = h->pathsStarted;
     out->KernelLaunches = h->lc.count;
     out->DeviceMilliseconds = h->deviceMs;
@@ -562,14 +579,14 @@ TB_API int tb_get_render_stats(TbHandle* h, TbRenderStats* out) {
 }
 TB_API int tb_reset_render_stats(TbHandle* h) {
     if (!h) return TB_ERR_INVALID_ARG;
-    if (h->st.stats) { CUDA_OK(h, cudaSetDevice(h->device)); CUDA_OK(h, cudaMemsetAsync(h->st.stats, 0, 64, h->stream)); }
+    if (h->st.stats) { CUDA_OK(h, cudaSetDevice(h->device)); CUDA_OK(h, cudaMemsetAsync(h->st.stats, 0, 128, h->stream)); }
     h->pathsStarted = 0; h->lc.count = 0; h->deviceMs = 0.0;
-    h->extendMs = h->shadeMs = 0.0; h->extendLaunches = 0;
+    h->extendMs = h->shadeMs = h->resumeMs = 0.0; h->extendLaunches = 0;
     return TB_OK;
 }
 TB_API int tb_set_frames_in_flight(TbHandle* h, uint32_t n) {
-    if (!h || n == 0 || n > 64) return fail(h, TB_ERR_INVALID_ARG, "frames in flight must be in [1,64]");
-    if (n == h->framesInFlight) return TB_OK;
+    if (!h || n > 64) return fail(h, TB_ERR_INVALID_ARG, "frames in flight must be in [0,64] (0 = automatic)");
+    if (n == h->framesInFlight && n == h->slots.size()) return TB_OK;
     h->framesInFlight = n;
     if (h->width) { // re-create the frame buffers with the new slot count
         uint32_t w = h->width, hh = h->height;
