@@ -37,12 +37,36 @@ def load():
         lib.oracle_resize.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         lib.oracle_select_pixel.argtypes = [C.c_void_p, C.c_int, C.c_int]
         lib.oracle_set_samples.argtypes = [C.c_void_p, C.c_uint32]
+        lib.oracle_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        lib.oracle_math_eval.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.oracle_math_eval.restype = None
+        lib.oracle_morton.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_morton.restype = C.c_uint32
         lib.oracle_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_int, C.POINTER(C.c_double)]
         lib.oracle_get_counts.argtypes = [C.c_void_p, C.c_void_p]
         lib.oracle_get_stats.argtypes = [C.c_void_p, C.c_void_p]
         lib.oracle_readback.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]
         _lib = lib
     return _lib
+
+
+MATH_FN = {"sin": 0, "cos": 1, "acos": 2, "atan2": 3, "exp": 4, "log": 5, "pow": 6, "hash13": 7, "halton": 8}
+
+
+def math_eval(fn, x, y=None):
+    """Evaluate one of the pinned intrinsics (tb_math.h) / noise functions over float32 arrays."""
+    lib = load()
+    x = np.ascontiguousarray(x, np.float32)
+    n = x.size // 3 if fn == "hash13" else x.size
+    y = np.zeros(n, np.float32) if y is None else np.ascontiguousarray(np.broadcast_to(np.asarray(y, np.float32), (n,)), np.float32)
+    out = np.empty(n, np.float32)
+    lib.oracle_math_eval(MATH_FN[fn], x.ctypes.data, y.ctypes.data, out.ctypes.data, n)
+    return out
+
+
+def morton(centroid, smin, smax):
+    a = [np.ascontiguousarray(v, np.float32) for v in (centroid, smin, smax)]
+    return load().oracle_morton(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data)
 
 
 class Oracle:
@@ -102,6 +126,9 @@ class Oracle:
 
     def SelectPixel(self, x, y):
         self.lib.oracle_select_pixel(self.h, x, y)
+
+    def SetFrameShard(self, offset, stride):
+        self._ck(self.lib.oracle_set_shard(self.h, offset, stride))
 
     def SetSamples(self, n):
         self.lib.oracle_set_samples(self.h, n)

@@ -216,6 +216,10 @@ void treelet_pass(std::vector<HNode>& H, const std::vector<Prim>& prims, uint32_
 
 } // namespace
 
+uint32_t morton_public(const float* c, const float* mn, const float* mx) {
+    return morton_code(mk3(c[0], c[1], c[2]), mk3(mn[0], mn[1], mn[2]), mk3(mx[0], mx[1], mx[2]));
+}
+
 bool build_bvh(Scene& s, int treeletPasses, std::string& err) {
     // LoadPrimitives (LoadPrimitivesPass.cpp:56-169, BottomLevelLoadTriangles.hlsli:88-126)
     std::vector<Prim> prims;

@@ -5,6 +5,7 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include "../tracerboy_b200/csrc/common/tb_vec.h"
 #include "oracle.h"
 
 using namespace oracle;
@@ -15,6 +16,7 @@ struct OracleHandle {
     TbCamera camera;
     std::string err;
     uint32_t samples = 0;
+    uint32_t shardOffset = 0, shardStride = 1; // frame f = offset + local * stride (multi-process sharding tests)
     int selX = -1, selY = -1;
 };
 
@@ -75,7 +77,8 @@ ORACLE_API int oracle_render(OracleHandle* h, const TbOutputSettings* s, uint32_
     auto t0 = std::chrono::high_resolution_clock::now();
     for (uint32_t i = 0; i < nSamples; i++) {
         RenderParams p;
-        p.settings = *s; p.camera = h->camera; p.time = time; p.frame = h->samples;
+        p.settings = *s; p.camera = h->camera; p.time = time; p.frame = h->shardOffset + h->samples * h->shardStride;
+        p.clearAccum = h->samples == 0;
         p.selectedX = h->selX; p.selectedY = h->selY;
         render_frame(h->scene, p, h->fb, threads);
         h->samples++;
@@ -83,6 +86,32 @@ ORACLE_API int oracle_render(OracleHandle* h, const TbOutputSettings* s, uint32_
     auto t1 = std::chrono::high_resolution_clock::now();
     if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
     return 0;
+}
+ORACLE_API int oracle_set_shard(OracleHandle* h, uint32_t offset, uint32_t stride) {
+    if (stride == 0 || offset >= stride) return -1;
+    h->shardOffset = offset; h->shardStride = stride; h->samples = 0;
+    return 0;
+}
+// pinned intrinsics and noise functions, exposed so tests can pin them against independent numpy restatements
+ORACLE_API void oracle_math_eval(int fn, const float* x, const float* y, float* out, uint64_t n) {
+    using namespace tbm;
+    for (uint64_t i = 0; i < n; i++) {
+        switch (fn) {
+        case 0: out[i] = sin_(x[i]); break;
+        case 1: out[i] = cos_(x[i]); break;
+        case 2: out[i] = acos_(x[i]); break;
+        case 3: out[i] = atan2_(y[i], x[i]); break;
+        case 4: out[i] = exp_(x[i]); break;
+        case 5: out[i] = log_(x[i]); break;
+        case 6: out[i] = pow_(x[i], y[i]); break;
+        case 7: out[i] = oracle::hash13_public(x[3 * i], x[3 * i + 1], x[3 * i + 2]); break;
+        case 8: out[i] = oracle::halton_public((int)y[i], (int)x[i]); break;
+        default: out[i] = 0.0f;
+        }
+    }
+}
+ORACLE_API uint32_t oracle_morton(const float* centroid, const float* smin, const float* smax) {
+    return oracle::morton_public(centroid, smin, smax);
 }
 ORACLE_API int oracle_get_counts(OracleHandle* h, uint64_t* out3) {
     out3[0] = h->fb.raysTraced; out3[1] = h->fb.boxesTested; out3[2] = h->fb.trianglesTested;
@@ -105,7 +134,10 @@ ORACLE_API int oracle_readback(OracleHandle* h, uint32_t kind, void* dst, uint64
         }
         src = tmp.data(); sz = n * 12; break;
     case TB_BUF_AOV_NORMAL: src = fb.aovNormal.data(); sz = n * 16; break;
-    case TB_BUF_AOV_WORLDPOS: src = fb.aovWorldPos[(h->samples + 1) % 2].data(); sz = n * 16; break;
+    case TB_BUF_AOV_WORLDPOS: {
+        uint32_t last = h->shardOffset + (h->samples ? h->samples - 1 : 0) * h->shardStride;
+        src = fb.aovWorldPos[last % 2].data(); sz = n * 16; break;
+    }
     case TB_BUF_AOV_DEPTH: src = fb.aovDepth.data(); sz = n * 4; break;
     case TB_BUF_AOV_ALBEDO: src = fb.aovAlbedo.data(); sz = n * 16; break;
     case TB_BUF_AOV_EMISSIVE: src = fb.aovEmissive.data(); sz = n * 16; break;

@@ -703,11 +703,17 @@ void render_frame(const Scene& s, const RenderParams& p, FrameBuffers& fb, int n
             TbFloat4 wp = {c.worldPosition.x, c.worldPosition.y, c.worldPosition.z, c.distanceToNeighbor};
             fb.aovWorldPos[p.frame % 2][pi] = wp;
             bool realtime = p.settings.RenderMode == TB_RENDER_REALTIME;
-            TbFloat4 prev = (realtime || p.frame == 0) ? TbFloat4{0, 0, 0, 0} : fb.accum[pi];
+            // On one process clearAccum == (frame == 0) and this is RayGenCommon.h:721-727 verbatim; a
+            // sample-sharded process starts at frame > 0 and must still start from an empty buffer.
+            bool clear = realtime || p.clearAccum;
+            TbFloat4 prev = clear ? TbFloat4{0, 0, 0, 0} : fb.accum[pi];
             fb.accum[pi] = {outc.x + prev.x, outc.y + prev.y, outc.z + prev.z, outc.w + prev.w};
-            if (!realtime && (p.frame == 0 || c.rand() < 0.5f)) {
-                TbFloat4 pj = p.frame > 0 ? fb.jittered[pi] : TbFloat4{0, 0, 0, 0};
-                fb.jittered[pi] = {outc.x + pj.x, outc.y + pj.y, outc.z + pj.z, outc.w + pj.w};
+            if (!realtime) {
+                bool take = p.frame == 0 || c.rand() < 0.5f;
+                if (take) {
+                    TbFloat4 pj = p.clearAccum ? TbFloat4{0, 0, 0, 0} : fb.jittered[pi];
+                    fb.jittered[pi] = {outc.x + pj.x, outc.y + pj.y, outc.z + pj.z, outc.w + pj.w};
+                } else if (p.clearAccum) fb.jittered[pi] = {0, 0, 0, 0};
             }
             fb.aovAlbedo[pi] = {c.aovAlbedo.x, c.aovAlbedo.y, c.aovAlbedo.z, c.aovAlbedo.w};
             fb.aovNormal[pi] = {c.aovNormal.x, c.aovNormal.y, c.aovNormal.z, c.aovNormal.w};
@@ -721,5 +727,8 @@ void render_frame(const Scene& s, const RenderParams& p, FrameBuffers& fb, int n
     }
     fb.raysTraced += rays; fb.trianglesTested += tris; fb.boxesTested += boxes;
 }
+
+float hash13_public(float x, float y, float z) { return hash13(mk3(x, y, z)); }
+float halton_public(int b, int i) { return halton(b, i); }
 
 } // namespace oracle

@@ -69,10 +69,15 @@ struct RenderParams {
     TbCamera camera;
     float time = 0.0f;
     uint32_t frame = 0; // GlobalFrameCount
+    bool clearAccum = true; // first frame after an invalidate (== frame 0 unless sample-sharded)
     int selectedX = -1, selectedY = -1;
 };
 
 // One SoftwareRayTraceCS dispatch (SoftwareRayTraceCS.hlsl:9-51): one sample per pixel.
 void render_frame(const Scene& s, const RenderParams& p, FrameBuffers& fb, int numThreads);
+
+float hash13_public(float x, float y, float z);
+float halton_public(int b, int i);
+uint32_t morton_public(const float* centroid, const float* smin, const float* smax);
 
 } // namespace oracle

@@ -151,3 +151,134 @@ def test_materials_scene_bit_exact(tmp_path, built):
     s = tb.get_default_output_settings()
     s.MaxBounces = 8
     _compare_render(g, o, s, 3)
+
+
+# ----------------------------------------------------------------- golden fixtures on the GPU
+import sys as _sys
+_sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import make_golden  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(make_golden.CASES))
+def test_gpu_matches_golden(name, built):
+    """The CUDA path against the committed fixtures (minted by the oracle, tests/golden/make_golden.py)."""
+    import hashlib
+    import tracerboy_b200 as tb
+    spec, w, h, spp, bounces, over = make_golden.CASES[name]
+    want = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    g = tb.TracerBoy(0)
+    g.LoadScene(make_golden.scene_file(spec))
+    g.Resize(w, h)
+    s = tb.get_default_output_settings()
+    s.MaxBounces = bounces
+    for k, v in over.items():
+        setattr(s, k, v)
+    g.Render(s, spp, 0.0)
+    bvh = g.GetBVH()
+    assert bvh.size == int(want["bvh_bytes"][0])
+    assert np.array_equal(np.frombuffer(hashlib.sha256(bvh.tobytes()).digest(), np.uint8), want["bvh_sha256"])
+    for key, kind in (("accum", 0), ("jittered", 1), ("normal", 3), ("depth", 5), ("albedo", 6), ("primary_hit", 8), ("counters", 9)):
+        a = g.Readback(kind)
+        assert np.array_equal(a.view(np.uint32), want[key].view(np.uint32)), key
+    st = g.GetRenderStats()
+    assert [st.RaysTraced, st.BoxesTested, st.TrianglesTested] == want["counts"].tolist()
+
+
+# ------------------------------------------------------- SW-RT boundary: build + trace on raw geometry
+def test_bvh_build_and_trace_custom_geometry(built):
+    """BuildRaytracingAccelerationStructure on caller geometry (uint16 / uint32 / non-indexed) and
+    SoftwareRayQuery known answers: one triangle at z = 2 gives t = 2 and barycentrics (x, y)."""
+    import tracerboy_b200 as tb
+    from tracerboy_b200.api import RAY_DTYPE
+    g = tb.TracerBoy(0)
+    tri = np.array([[0, 0, 2], [1, 0, 2], [0, 1, 2]], np.float32)
+    far = tri + np.array([0, 0, 3], np.float32)
+    g.BuildRaytracingAccelerationStructure([(tri, np.array([0, 1, 2], np.uint16)), (far, None), (far + 1, np.array([0, 1, 2], np.uint32))])
+    assert g.GetSceneInfo().NumTriangles == 3 and g.GetBVH().size == 116 * 3 - 16
+    rays = np.zeros(4, RAY_DTYPE)
+    rays["Origin"] = [[0.25, 0.5, 0], [0.25, 0.5, 3], [5, 5, 0], [0.25, 0.5, 0]]
+    rays["Direction"] = [[0, 0, 1], [0, 0, 1], [0, 0, 1], [0, 0, -1]]
+    rays["TMin"] = 0.001; rays["TMax"] = 999999.0
+    h = g.TraceRays(rays)
+    assert h["t"][0] == 2.0 and h["b1"][0] == 0.25 and h["b2"][0] == 0.5 and h["GeometryIndex"][0] == 0 and h["PrimitiveIndex"][0] == 0
+    assert h["t"][1] == 2.0 and h["GeometryIndex"][1] == 1   # starts behind the first triangle, hits the second
+    assert h["t"][2] == -1.0 and h["t"][3] == -1.0
+    # TMax is exclusive, TMin is exclusive (TraverseFunction.hlsli:420)
+    rays["TMax"][0] = 2.0
+    assert g.TraceRays(rays[:1])["t"][0] == -1.0
+    # errors: E_INVALIDARG paths of LoadPrimitivesPass.cpp:73-84
+    with pytest.raises(tb.TracerBoyError):
+        g.BuildRaytracingAccelerationStructure([(tri, np.array([0, 1, 7], np.uint32))])
+    with pytest.raises(tb.TracerBoyError):
+        g.BuildRaytracingAccelerationStructure([])
+
+
+def test_api_state_errors_and_materials(cornell):
+    import tracerboy_b200 as tb
+    g = tb.TracerBoy(0)
+    s = tb.get_default_output_settings()
+    with pytest.raises(tb.TracerBoyError) as e:
+        g.Render(s, 1, 0.0)
+    assert e.value.code == -7
+    g.LoadScene(cornell)
+    with pytest.raises(tb.TracerBoyError):
+        g.Render(s, 1, 0.0)          # no Resize yet
+    g.Resize(32, 32)
+    g.Render(s, 2, 0.0)
+    assert g.GetNumberOfSamplesSinceLastInvalidate() == 2
+    a = g.Readback(tb.BufferKind.ACCUM_RGBW).copy()
+    m, name = g.GetMaterial(0)
+    assert name == "Floor" and g.IsMaterialIDValid(7) and not g.IsMaterialIDValid(8)
+    m.albedo.x = 0.0
+    g.SetMaterial(0, m)              # invalidates history like the reference
+    assert g.GetNumberOfSamplesSinceLastInvalidate() == 0
+    g.Render(s, 2, 0.0)
+    assert not np.array_equal(a, g.Readback(tb.BufferKind.ACCUM_RGBW))
+    s.SampleLimit = 3
+    g.Render(s, 10, 0.0)
+    assert g.GetNumberOfSamplesSinceLastInvalidate() == 3
+    g.SelectPixel(16, 20)
+    g.InvalidateHistory(); s.SampleLimit = 0
+    g.Render(s, 1, 0.0)
+    st = g.GetReadbackStats()
+    assert st.SelectedPixelDistance > 0 and 0 <= st.SelectedMaterialID < 8
+
+
+# --------------------------------------------- size-independent properties at the BASELINE.json sizes
+def test_full_size_properties_teapot_1080p(teapot):
+    """Teapot 1920x1080 (configs[1]): determinism across runs and across frames-in-flight settings,
+    progressive accumulation (24 + 40 == 64 samples), weight channel == spp, finite radiance."""
+    import tracerboy_b200 as tb
+    s = tb.get_default_output_settings()
+    g = tb.TracerBoy(0)
+    g.LoadScene(teapot)
+    g.Resize(1920, 1080)
+    g.Render(s, 64, 0.0)
+    a = g.Readback(tb.BufferKind.ACCUM_RGBW).copy()
+    assert (a[..., 3] == 64.0).all() and np.isfinite(a).all() and (a[..., :3] >= 0).all()
+    g.InvalidateHistory()
+    g.Render(s, 24, 0.0)
+    g.Render(s, 40, 0.0)
+    assert np.array_equal(a.view(np.uint32), g.Readback(tb.BufferKind.ACCUM_RGBW).view(np.uint32))
+    g.SetFramesInFlight(1)
+    g.Render(s, 64, 0.0)
+    assert np.array_equal(a.view(np.uint32), g.Readback(tb.BufferKind.ACCUM_RGBW).view(np.uint32))
+    rgb = g.Readback(tb.BufferKind.RESOLVED_RGB)
+    assert np.allclose(rgb, a[..., :3] / a[..., 3:4], rtol=1e-6)
+
+
+def test_sample_sharding_sums_to_single_gpu(cornell):
+    """tb_set_frame_shard: two handles rendering frames {0,2,4} and {1,3,5} sum to the 6-frame render
+    (same samples, different float summation order)."""
+    import tracerboy_b200 as tb
+    s = tb.get_default_output_settings(); s.MaxBounces = 4
+    parts = []
+    for r in range(2):
+        g = tb.TracerBoy(0); g.LoadScene(cornell); g.Resize(64, 64); g.SetFrameShard(r, 2)
+        g.Render(s, 3, 0.0)
+        parts.append(g.Readback(tb.BufferKind.ACCUM_RGBW).astype(np.float64))
+    g = tb.TracerBoy(0); g.LoadScene(cornell); g.Resize(64, 64)
+    g.Render(s, 6, 0.0)
+    want = g.Readback(tb.BufferKind.ACCUM_RGBW)
+    assert np.allclose(parts[0] + parts[1], want, rtol=1e-5, atol=1e-6)
+    assert np.array_equal((parts[0] + parts[1])[..., 3], want[..., 3])

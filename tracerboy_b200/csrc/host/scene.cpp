@@ -309,7 +309,7 @@ static void add_quad(Scene& s, TbFloat3 a, TbFloat3 b, TbFloat3 c, TbFloat3 d, u
 // A displaced lat-long sphere with exactly 2*rings*segs - 2*segs... triangles; we build
 // (rings x segs) quads (poles are degenerate-free: ring 0 / ring R are single vertices).
 static void add_blob(Scene& s, TbFloat3 center, float radius, uint32_t rings, uint32_t segs,
-                     uint32_t seed, uint32_t mat) {
+                     uint32_t seed, uint32_t mat, float displacement = 1.0f) {
     std::vector<TbFloat3> pos, nrm;
     std::vector<TbFloat2> uv;
     std::vector<uint32_t> idx;
@@ -317,7 +317,7 @@ static void add_blob(Scene& s, TbFloat3 center, float radius, uint32_t rings, ui
     // low-frequency displacement: 3 random lobes
     uint32_t rs = seed * 2654435761u + 12345u;
     float ax[3], ph[3], am[3];
-    for (int k = 0; k < 3; k++) { ax[k] = 2.0f + floorf(unit(rs) * 5.0f); ph[k] = unit(rs) * 6.28f; am[k] = 0.04f + 0.06f * unit(rs); }
+    for (int k = 0; k < 3; k++) { ax[k] = 2.0f + floorf(unit(rs) * 5.0f); ph[k] = unit(rs) * 6.28f; am[k] = displacement * (0.04f + 0.06f * unit(rs)); }
     for (uint32_t r = 0; r <= rings; r++) {
         float th = PI_F * (float)r / (float)rings;
         float st = tbm::sin_(th), ct = tbm::cos_(th);
@@ -430,16 +430,15 @@ bool make_synthetic(Scene& s, const std::string& spec, std::string& err) {
         return true;
     }
     if (name == "furnace") {
-        // A closed diffuse box lit only by a constant white sky seen through nothing: the
-        // camera sits inside a unit sphere-ish blob of albedo a; every path bounces until
-        // RR/maxBounces. Used for energy-conservation known answers.
+        // One convex matte sphere of albedo a under a constant white sky, no lights. Known answer
+        // with MaxBounces = 2: every pixel that hits the sphere resolves to a (throughput =
+        // albedo * cos/pi / (cos/pi), second ray escapes to the sky), every other pixel to 1.
         TbMaterial m = default_material({0, 0, 0});
         float a = q.count("albedo") ? (float)atof(q["albedo"].c_str()) : 0.5f;
         m.albedo = {a, a, a};
         m.Flags |= TB_NO_SPECULAR_MATERIAL_FLAG;
         uint32_t mat = add_mat(s, "furnace", m);
-        add_blob(s, {0, 0, 0}, 5.0f, 16, 20, 0, mat);
-        // remove displacement influence is irrelevant for the furnace identity
+        add_blob(s, {0, 0, 0}, 5.0f, 48, 64, 0, mat, 0.0f); // plain convex sphere
         Image sky;
         sky.width = sky.height = 1; sky.format = 0;
         float px[4] = {1, 1, 1, 1};
