@@ -131,22 +131,30 @@ def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path (restated core; oracle/_ref when built) on host cores."""
     if rank != 0:
         return
+    from oracle import binding
     from oracle.binding import Oracle
     import tracerboy_b200 as tb
     spec, w, h, spp, bounces = WORKLOADS[args.workload]
+    # oracle/_ref = the reference's own kernel.glsl compiled as host C++ (built from the mount, travels as a
+    # binary); without it the hand-restated core runs ("port"). BVH build, traversal and glue are restated either way.
+    kind = "port"
+    if binding.reference_core_available():
+        binding.use_reference_core(True)
+        kind = "reference"
     o = Oracle()
     o.LoadScene(tbscene_for_oracle(spec), 3)
     o.Resize(w, h)
     s = tb.get_default_output_settings()
     s.MaxBounces = bounces
-    cores = Oracle.max_threads()
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     sample_spp = max(1, args.ref_spp)
     for _ in range(args.warmup):
-        o.Render(s, 1, 0.0)
+        o.Render(s, 1, 0.0, threads=cores)
     c0 = o.Counts()
     t = 0.0
     for _ in range(args.steps):
-        t += o.Render(s, sample_spp, 0.0)
+        t += o.Render(s, sample_spp, 0.0, threads=cores)
     c1 = o.Counts()
     rays = c1["rays"] - c0["rays"]
     value = rays / t / 1e6
@@ -156,7 +164,7 @@ def run_reference(args, rank, world):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic camera/seeds on the bundled scene",
         "config": {"workload": "%s %dx%d, %d bounces, CPU sample of %d spp per step" % (args.workload, w, h, bounces, sample_spp)},
         "samples_per_s": w * h * sample_spp * args.steps / t,
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind,
                          "sample": "%d spp of the %dx%d %s workload per step, OpenMP over pixels" % (sample_spp, w, h, args.workload)},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -328,16 +336,22 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import binding
         from oracle.binding import Oracle
+        kind = "port"
+        if binding.reference_core_available():
+            binding.use_reference_core(True)
+            kind = "reference"
         o = Oracle()
         o.LoadScene(tbscene_for_oracle(spec), 3)
         o.Resize(w, h)
-        o.Render(s, 1, 0.0)
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        o.Render(s, 1, 0.0, threads=cores)
         c0 = o.Counts()
-        sec = o.Render(s, args.cpu_baseline_spp, 0.0)
+        sec = o.Render(s, args.cpu_baseline_spp, 0.0, threads=cores)
         c1 = o.Counts()
-        cpu_baseline = {"value": (c1["rays"] - c0["rays"]) / sec / 1e6, "unit": "Mrays/s", "cores": Oracle.max_threads(),
-                        "kind": "port", "sample": "%d spp of the %dx%d %s workload (%.1f s), OpenMP over pixels" % (
+        cpu_baseline = {"value": (c1["rays"] - c0["rays"]) / sec / 1e6, "unit": "Mrays/s", "cores": cores,
+                        "kind": kind, "sample": "%d spp of the %dx%d %s workload (%.1f s), OpenMP over pixels" % (
                             args.cpu_baseline_spp, w, h, args.workload, sec)}
 
     if rank == 0:

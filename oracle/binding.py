@@ -15,10 +15,33 @@ def lib_path():
     return os.path.join(_HERE, "liboracle.so")
 
 
+_ref = None
+
+
+def ref_lib_path():
+    return os.path.join(_HERE, "_ref", "libref_core.so")
+
+
+def reference_core_available():
+    return os.path.exists(ref_lib_path())
+
+
+def use_reference_core(on):
+    """Route the oracle's per-pixel PathTrace through oracle/_ref (the reference's kernel.glsl compiled
+    as host C++) instead of the hand-restated core. Returns the number of pixels it has traced so far."""
+    global _ref
+    load()
+    if _ref is None:
+        _ref = C.CDLL(ref_lib_path())
+        _ref.ref_core_calls.restype = C.c_ulonglong
+    _ref.ref_core_enable(1 if on else 0)
+    return _ref.ref_core_calls()
+
+
 def load():
     global _lib
     if _lib is None:
-        lib = C.CDLL(lib_path())
+        lib = C.CDLL(lib_path(), mode=C.RTLD_GLOBAL)
         lib.oracle_create.restype = C.c_void_p
         lib.oracle_last_error.restype = C.c_char_p
         lib.oracle_bvh_size.restype = C.c_uint64

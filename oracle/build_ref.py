@@ -1,0 +1,43 @@
+"""Builds oracle/_ref/libref_core.so: the reference's TracerBoy/kernel.glsl compiled as host C++
+(TEST INFRASTRUCTURE). Needs the reference mount; outputs only into oracle/_ref/ (git-ignored,
+travels to the GPU box as a binary). See oracle/ref/prepass.py and oracle/ref/ref_glue.cpp."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+KERNEL = "/root/reference/TracerBoy/kernel.glsl"
+OUT = os.path.join(HERE, "_ref")
+GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def lib_path():
+    return os.path.join(OUT, "libref_core.so")
+
+
+def build(force=False):
+    if not os.path.exists(KERNEL):
+        return lib_path() if os.path.exists(lib_path()) else None
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_glue.cpp")] + \
+           [os.path.join(HERE, "glue.h"), os.path.join(HERE, "oracle.h"), KERNEL]
+    target = lib_path()
+    if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs) and \
+            os.path.getmtime(target) >= os.path.getmtime(os.path.join(HERE, "liboracle.so")):
+        return target
+    sys.path.insert(0, os.path.join(HERE, "ref"))
+    import prepass
+    prepass.run(KERNEL, os.path.join(OUT, "kernel_gen.inc"))
+    cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-mfma", "-ffp-contract=off",
+           "-fsingle-precision-constant",  # HLSL literals are float
+           "-fno-fast-math", "-fvisibility=hidden", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + HERE,
+           os.path.join(HERE, "ref", "ref_glue.cpp"), "-o", target, "-L" + HERE, "-loracle", "-Wl,-rpath,$ORIGIN/.."]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref build failed:\n" + r.stdout)
+    return target
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

@@ -17,6 +17,7 @@
 #include <omp.h>
 #endif
 #include "../tracerboy_b200/csrc/common/tb_vec.h"
+#include "glue.h"
 #include "oracle.h"
 
 using namespace tbm;
@@ -36,50 +37,10 @@ void FrameBuffers::resize(uint32_t w, uint32_t h) {
     memset(&stats, 0, sizeof(stats));
 }
 
-namespace {
 
-const float EPSILON = 0.000001f;        // kernel.glsl:1 (redefinition wins, SURVEY §8c trap 1)
-const float PI = 3.1415926535f;         // kernel.glsl:2
-const float LARGE_NUMBER = 1e20f;
-const float AIR_IOR = 1.0f;
-const float MIN_ROUGHNESS = 0.04f;
-const float MIN_ROUGHNESS_SQUARED = MIN_ROUGHNESS * MIN_ROUGHNESS;
-const float MIN_T = 0.001f;             // RayGenCommon.h:364
 
-inline f3 F3(const TbFloat3& v) { return mk3(v.x, v.y, v.z); }
 
-struct Material { // SharedShaderStructs.h:141-161 in registers
-    f3 albedo; uint32_t albedoIndex, alphaIndex, normalMapIndex, emissiveIndex, specularMapIndex;
-    float IOR; f3 absorption; float roughness; f3 scattering; f3 emissive; int Flags; float SpecularCoef;
-};
-inline Material load_material(const TbMaterial& m) {
-    Material r;
-    r.albedo = F3(m.albedo); r.albedoIndex = m.albedoIndex; r.alphaIndex = m.alphaIndex;
-    r.normalMapIndex = m.normalMapIndex; r.emissiveIndex = m.emissiveIndex; r.specularMapIndex = m.specularMapIndex;
-    r.IOR = m.IOR; r.absorption = F3(m.absorption); r.roughness = m.roughness; r.scattering = F3(m.scattering);
-    r.emissive = F3(m.emissive); r.Flags = m.Flags; r.SpecularCoef = m.SpecularCoef;
-    return r;
-}
 
-struct Ray { f3 origin, direction; };
-
-struct Ctx {
-    const Scene& sc;
-    const RenderParams& rp;
-    uint32_t W, H, px, py;
-    float seed;
-    // per-pixel side outputs
-    f3 worldPosition; float distanceToNeighbor;
-    f4 aovAlbedo, aovNormal, aovEmissive; bool wroteEmissive;
-    float aovDepth; bool wroteDepth;
-    uint32_t primGeom, primPrim; bool firstIntersect;
-    uint32_t tris, boxes, rays;
-    float statDistance; int statMaterial; bool wroteStats;
-    Ctx(const Scene& s, const RenderParams& r) : sc(s), rp(r) {}
-
-    float rand() { float s = seed; seed = seed + 1.0f; return frac(sin_(s + rp.time) * 43758.5453123f); } // kernel.glsl:39-40
-    bool selected() const { return (int)px == rp.selectedX && (int)py == rp.selectedY; }
-};
 
 // ---------------------------------------------------------------- textures
 f4 fetch_texel(const Image& im, int x, int y) {
@@ -170,7 +131,6 @@ float halton(int b, int i) { // RayGenCommon.h:49-60
     }
     return r;
 }
-struct BlueNoiseData { f2 PrimaryJitter, SecondaryRayDirection, AreaLightJitter, DOFJitter; };
 BlueNoiseData get_blue_noise(Ctx& c) { // RayGenCommon.h:104-122
     BlueNoiseData d;
     if (!c.rp.settings.EnableBlueNoise) {
@@ -193,10 +153,9 @@ BlueNoiseData get_blue_noise(Ctx& c) { // RayGenCommon.h:104-122
 }
 
 // ------------------------------------------------------------- intersect
-struct HitResult { float t; int material; f3 normal, tangent; f2 uv; };
 
 // IntersectWithMaxDistance (SW branch), RayGenCommon.h:365-414 + SharedHitGroup.h:48-151
-HitResult intersect(Ctx& c, const Ray& ray, float maxT = 999999.0f) {
+HitResult intersect(Ctx& c, const Ray& ray, float maxT) {
     TbRay r;
     r.Origin[0] = ray.origin.x; r.Origin[1] = ray.origin.y; r.Origin[2] = ray.origin.z; r.TMin = MIN_T;
     r.Direction[0] = ray.direction.x; r.Direction[1] = ray.direction.y; r.Direction[2] = ray.direction.z; r.TMax = maxT;
@@ -673,7 +632,8 @@ f4 path_trace(Ctx& c, f2 pixelCoord) {
     return mk4(col * filterWeight, filterWeight);
 }
 
-} // namespace
+static PathTraceFn g_pathTraceOverride = nullptr;
+void set_path_trace_override(PathTraceFn fn) { g_pathTraceOverride = fn; }
 
 // SoftwareRayTraceCS.hlsl:36-50 + RayTraceCommon (RayGenCommon.h:690-728)
 void render_frame(const Scene& s, const RenderParams& p, FrameBuffers& fb, int numThreads) {
@@ -697,7 +657,7 @@ void render_frame(const Scene& s, const RenderParams& p, FrameBuffers& fb, int n
             size_t pi = (size_t)y * W + x;
             f2 dispatchUV = mk2((float)x + 0.5f, (float)y + 0.5f) / mk2((float)W, (float)H);
             f2 uv = mk2(0.0f, 1.0f) + dispatchUV * mk2(1.0f, -1.0f);
-            f4 color = path_trace(c, uv * mk2((float)W, (float)H));
+            f4 color = g_pathTraceOverride ? g_pathTraceOverride(c, uv * mk2((float)W, (float)H)) : path_trace(c, uv * mk2((float)W, (float)H));
             f4 outc = mk4(0, 0, 0, 0);
             if (!isnan_(color.x) && !isnan_(color.y) && !isnan_(color.z) && !isnan_(color.w)) outc = outc + color;
             TbFloat4 wp = {c.worldPosition.x, c.worldPosition.y, c.worldPosition.z, c.distanceToNeighbor};

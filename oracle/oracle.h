@@ -6,11 +6,14 @@
 // --impl reference leg may load this library; the product (tracerboy_b200/) never does.
 //
 // PARITY PIN STATUS: the reference ships no tests, golden vectors or fixtures for this
-// path and its own implementation (HLSL + D3D12) cannot run here, so
-// this restatement is pinned by (i) oracle/ref_core, which compiles the reference's
-// kernel.glsl from the mount as host C++ and must agree with core.cpp bit for bit when
-// /root/reference is available, and (ii) analytic known answers in tests/. Where neither
-// applies the status is "parity unpinned" (see DESIGN.md §Oracle).
+// path and its host (HLSL + D3D12) cannot run here. Pins:
+//  (i)  tracer core (PathTrace/Trace/BRDF helpers): oracle/_ref compiles the reference's own
+//       kernel.glsl from the mount as host C++ (oracle/ref/) and tests/test_cpu_oracle.py
+//       requires core.cpp to match it bit for bit -> PINNED against the reference's code;
+//  (ii) BVH builder, traversal and the RayGenCommon/SharedHitGroup/SharedRaytracing glue are
+//       HLSL that cannot be compiled here: restated, checked by the fallback layer's own
+//       validator invariants, analytic known answers and independent numpy restatements
+//       -> "parity unpinned" by reference outputs for these parts.
 #pragma once
 #include <cstdint>
 #include <string>

@@ -1,0 +1,39 @@
+"""Pre-pass that turns the reference's TracerBoy/kernel.glsl (read from the mount, never copied
+into the repository) into text a C++ compiler accepts against hlsl_compat.h:
+
+  1. C preprocessor with IS_SHADER_TOY=0 (the configuration RayGenCommon.h:6 selects);
+  2. GLSL/HLSL parameter qualifiers:  out T x / inout T x -> T& x,  in T x -> T x;
+  3. multi-component swizzles become method calls (.xy -> .xy());
+  4. the two call sites that draw two rand() values inside one argument list are sequenced
+     left to right, as DXC evaluates them (g++ evaluates right to left; SURVEY §8c trap 17).
+
+The output goes to oracle/_ref/ (git-ignored) and is compiled there; nothing is written anywhere else.
+"""
+import re
+import subprocess
+import sys
+
+
+def run(src, dst):
+    text = subprocess.run(["gcc", "-E", "-P", "-x", "c", "-DIS_SHADER_TOY=0", src], check=True,
+                          stdout=subprocess.PIPE, text=True).stdout
+    text = re.sub(r"\b(?:inout|out)\s+([A-Za-z_]\w*)\s+([A-Za-z_]\w*)", r"\1& \2", text)
+    text = re.sub(r"\bin\s+([A-Za-z_]\w*)\s+([A-Za-z_]\w*)", r"\1 \2", text)
+    text = re.sub(r"\.(xyz|rgb|xy)\b(?!\s*\()", r".\1()", text)
+    hoists = {
+        "GenerateCosineWeightedDirection(normal, rand(), rand(), pdfValue)":
+            "[&]{ float r0_ = rand(); float r1_ = rand(); return GenerateCosineWeightedDirection(normal, r0_, r1_, pdfValue); }()",
+        "GenerateImportanceSampledDirection(normal, roughness, rand(), rand(), PDFValue)":
+            "[&]{ float r0_ = rand(); float r1_ = rand(); return GenerateImportanceSampledDirection(normal, roughness, r0_, r1_, PDFValue); }()",
+    }
+    for a, b in hoists.items():
+        if a not in text:
+            raise SystemExit("prepass: expected call site not found: " + a)
+        text = text.replace(a, b)
+    if re.search(r"\([^()]*rand\(\)[^()]*rand\(\)[^()]*\)", text):
+        raise SystemExit("prepass: an unsequenced pair of rand() calls is left in one argument list")
+    open(dst, "w").write(text)
+
+
+if __name__ == "__main__":
+    run(sys.argv[1], sys.argv[2])

@@ -241,3 +241,53 @@ def test_accumulation_is_progressive(cornell):
     # time is a seed input
     c = Oracle(); c.LoadScene(cornell, 3); c.Resize(32, 32); c.Render(s, 5, 0.25)
     assert not np.array_equal(c.Readback(0), b.Readback(0))
+
+
+# ------------------------------------------------------------ oracle/_ref: the reference's own core
+REF_CASES = [
+    ("cornell", 96, 96, 4, {"MaxBounces": 5}),
+    ("cornell", 64, 64, 3, {"EnableBlueNoise": 0}),
+    ("cornell", 64, 64, 3, {"DOFFocalDistance": 5.0, "FilterType": 1, "FilterWidth": 2.0}),
+    ("cornell", 64, 64, 3, {"FilterType": 2, "FireflyClampValue": 2.0, "EnableSamplingImportanceResampling": 1}),
+    ("cornell", 64, 64, 2, {"EnableNextEventEstimation": 0, "MaxBounces": 8}),
+    ("cornell", 48, 48, 2, {"OutputType": 9}),
+    ("synthetic:blobs?copies=27&tris=300&seed=3", 160, 90, 3, {"MaxBounces": 8}),
+    ("teapot", 240, 135, 3, {}),
+]
+
+
+@pytest.mark.parametrize("spec,w,h,spp,over", REF_CASES)
+def test_restated_core_equals_reference_core(spec, w, h, spp, over, tmp_path, built):
+    """The hand-restated PathTrace/Trace (oracle/core.cpp) against the reference's own kernel.glsl
+    compiled as host C++ (oracle/_ref, built from the mount): every buffer bit-identical, same ray
+    and traversal counts. This is what pins the restatement of the tracer core."""
+    import tracerboy_b200 as tb
+    from oracle import binding
+    if not binding.reference_core_available():
+        pytest.skip("oracle/_ref/libref_core.so not built (needs the reference mount at build time)")
+    if spec in ("cornell", "teapot"):
+        path = scene_path("cornell-box" if spec == "cornell" else "teapot")
+        if path is None:
+            pytest.skip("scene cache missing")
+    else:
+        path = str(tmp_path / "s.tbscene")
+        tb.convert_scene(spec, path)
+
+    def render(use_ref):
+        calls0 = binding.use_reference_core(use_ref)
+        o = binding.Oracle(); o.LoadScene(path, 3); o.Resize(w, h)
+        s = tb.get_default_output_settings()
+        for k, v in over.items():
+            setattr(s, k, v)
+        o.Render(s, spp, 0.0)
+        out = {k: o.Readback(k) for k in (0, 1, 3, 4, 5, 6, 7, 8, 9)}
+        calls1 = binding.use_reference_core(False)
+        return out, o.Counts(), calls1 - calls0
+    a, ca, na = render(False)
+    b, cb, nb = render(True)
+    assert na == 0 and nb == w * h * spp, "the reference core did not run"
+    assert ca == cb
+    for k in a:
+        x, y = a[k], b[k]
+        same = ((x.view(np.uint32) == y.view(np.uint32)) | ((x != x) & (y != y))) if x.dtype == np.float32 else (x == y)
+        assert same.all(), "buffer %d differs at %d elements" % (k, (~same).sum())

@@ -158,11 +158,10 @@ def build_all(force=False, verbose=False):
     build_pbrt_import(force)
     build_oracle(force)
     build_scene_cache(force)
-    try:
-        from oracle import build_ref  # optional: reference core compiled from the mount
-        build_ref.build(force)
-    except ImportError:
-        pass
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    from oracle import build_ref  # checker only: the reference's kernel.glsl compiled from the mount, when present
+    build_ref.build(force)
 
 
 if __name__ == "__main__":

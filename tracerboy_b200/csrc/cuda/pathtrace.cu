@@ -509,10 +509,11 @@ __global__ void __launch_bounds__(128) k_extend(DeviceBvh bvh, PathState st, int
     uint32_t rays = 0, ntris = 0, nboxes = 0;
     Traversal tr;
     uint32_t stack[TB_STACK_DEPTH];
-    tr.sp = 0;
+    tr.sp = 0; tr.cur = TB_NO_NODE;
     bool active = false, exhausted = false;
     uint32_t pi = 0, steps = 0;
     while (true) {
+        // ---- refill: idle lanes fetch the next rays of the queue (one atomic per warp)
         uint32_t idle = __ballot_sync(0xffffffffu, !active);
         if (idle && !exhausted) {
             uint32_t base = 0;
@@ -523,30 +524,39 @@ __global__ void __launch_bounds__(128) k_extend(DeviceBvh bvh, PathState st, int
                 if (i < count) {
                     pi = __ldg(queue + i);
                     float4 o = st.rayO[pi], d = st.rayD[pi];
-                    tr.begin(bvh, stack, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), MIN_T, FAR_T);
+                    tr.begin(bvh, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), MIN_T, FAR_T);
                     active = true;
                     steps = 0;
                 }
             }
             if (base + (uint32_t)__popc(idle) >= count) exhausted = true;
         }
-        if (!__any_sync(0xffffffffu, active)) break;
-        if (active) {
-            while (true) {
-                if (tr.done()) {
-                    write_hit(st, tr, pi, bounceIsZero, outputHeatmap, aovMask, rays, ntris, nboxes);
-                    active = false;
-                    break;
-                }
-                if (steps >= budgetMain) {
-                    if (try_suspend(st, 0, tr, stack, pi)) { active = false; break; }
-                    steps = 0; // buffer full: keep going here
-                }
-                tr.step(stack, pairs, tris);
-                steps++;
-                // regroup for a refill when the warp has thinned out (heuristic only: results do not depend on it)
-                if (!exhausted && __popc(__activemask()) < REFILL_THRESHOLD) break;
+        uint32_t activeMask = __ballot_sync(0xffffffffu, active);
+        if (!activeMask) break;
+        // ---- warp-synchronous traversal: every iteration the whole warp executes ONE of the two
+        // code paths, the one more lanes are waiting for (box pair test vs. triangle test), so the
+        // two paths never serialise inside an iteration. Lanes on the minority path wait; since
+        // waiting lanes accumulate, they become the majority within a few iterations.
+        while (true) {
+            bool wantLeaf = active && !tr.done() && tr.at_leaf();
+            bool wantInternal = active && !tr.done() && !tr.at_leaf();
+            uint32_t mL = __ballot_sync(0xffffffffu, wantLeaf), mI = __ballot_sync(0xffffffffu, wantInternal);
+            if (__popc(mI) >= __popc(mL)) {
+                if (wantInternal) { tr.step_internal(stack, pairs); steps++; }
+            } else {
+                if (wantLeaf) { tr.step_leaf(stack, tris); steps++; }
             }
+            // retire finished rays, park the ones over budget
+            if (active && tr.done()) {
+                write_hit(st, tr, pi, bounceIsZero, outputHeatmap, aovMask, rays, ntris, nboxes);
+                active = false;
+            } else if (active && steps >= budgetMain) {
+                if (try_suspend(st, 0, tr, stack, pi)) active = false;
+                else steps = 0; // buffer full: keep going here
+            }
+            uint32_t am = __ballot_sync(0xffffffffu, active);
+            if (!am) break;
+            if (!exhausted && __popc(am) < REFILL_THRESHOLD) break; // regroup and refill
         }
     }
     flush_stats(st, 0, rays, ntris, nboxes);

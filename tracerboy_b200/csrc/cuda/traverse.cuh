@@ -36,21 +36,24 @@ __device__ __forceinline__ bool slab(float& resultT, float closestT, tbm::f3 oin
     return fmaxf(minT, 0.0f) < fminf(maxT, closestT);
 }
 
-// Resumable traversal: begin() once per ray, step() once per popped node until done().
-// Keeping the state in a struct lets the persistent kernel (k_extend) interleave rays of
-// different lengths in one warp (per-lane refill) while the inline queries of the shading
-// stage simply run it to completion. Per-ray visit order and counters are identical either way.
+// Resumable traversal: begin() once per ray, then step_internal()/step_leaf() on the current
+// node until done(). The node to visit next is held in a register (`cur`), the rest of the
+// stack in a per-thread local array passed in by the caller, so only the far children of
+// two-hit nodes ever touch local memory. Splitting the step lets the persistent kernel
+// schedule a whole warp onto ONE of the two code paths per iteration (k_extend) while the
+// inline queries of the shading stage simply run to completion. Per-ray visit order and
+// counters are identical either way and identical to the reference's stack discipline.
+#define TB_NO_NODE 0x7fffffffu
 struct Traversal {
     tbm::f3 org, inv, oinv, shear;
     int kx, ky, kz;
     float tmin, tmax, committedT, hb1, hb2;
     uint32_t hitGeom, hitPrim, trisTested, boxesTested;
     bool haveHit;
-    int sp;
-    // The node stack is a separate per-thread array (passed in) so that the scalar state
-    // above stays in registers; only the dynamically indexed stack lives in local memory.
+    uint32_t cur; // node reference to process next (TB_NO_NODE = traversal finished)
+    int sp;       // entries in the memory stack below `cur`
 
-    __device__ __forceinline__ void begin(const DeviceBvh& bvh, uint32_t* stack, tbm::f3 o, tbm::f3 dir, float tmin_, float tmax_) {
+    __device__ __forceinline__ void begin(const DeviceBvh& bvh, tbm::f3 o, tbm::f3 dir, float tmin_, float tmax_) {
         using namespace tbm;
         org = o;
         inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z); // GetRayData, TraverseFunction.hlsli:473-495
@@ -65,68 +68,78 @@ struct Traversal {
         haveHit = false; hitGeom = hitPrim = 0xffffffffu; hb1 = hb2 = 0.0f;
         trisTested = boxesTested = 0;
         sp = 0;
+        cur = TB_NO_NODE;
         float unusedT;
         if (slab(unusedT, committedT, oinv, inv, abs3(inv), bvh.root.c[0], bvh.root.c[1], bvh.root.c[2], bvh.root.h[0], bvh.root.h[1], bvh.root.h[2]))
-            stack[sp++] = (bvh.root.flags & 0x80000000u) ? (0x80000000u | (bvh.root.flags & 0x3fffffffu)) : 0u;
+            cur = (bvh.root.flags & 0x80000000u) ? (0x80000000u | (bvh.root.flags & 0x3fffffffu)) : 0u;
     }
-    __device__ __forceinline__ bool done() const { return sp == 0; }
+    __device__ __forceinline__ bool done() const { return cur == TB_NO_NODE; }
+    __device__ __forceinline__ bool at_leaf() const { return (cur & 0x80000000u) != 0; }
+    __device__ __forceinline__ void pop(const uint32_t* stack) { cur = sp > 0 ? stack[--sp] : TB_NO_NODE; }
 
-    __device__ __forceinline__ void step(uint32_t* stack, const float4* __restrict__ pairs, const float4* __restrict__ tris) {
+    // cur is a leaf: RayTriangleIntersect, TraverseFunction.hlsli:231-313 (two-sided, `precise` => unfused)
+    __device__ __forceinline__ void step_leaf(uint32_t* stack, const float4* __restrict__ tris) {
         using namespace tbm;
-        uint32_t ref = stack[--sp];
-        if (ref & 0x80000000u) {
-            uint32_t slot = ref & 0x3fffffffu;
-            float4 q0 = __ldg(tris + 3 * (size_t)slot), q1 = __ldg(tris + 3 * (size_t)slot + 1), q2 = __ldg(tris + 3 * (size_t)slot + 2);
-            trisTested++;
-            // RayTriangleIntersect, TraverseFunction.hlsli:231-313 (two-sided, `precise` => unfused)
-            f3 v0 = mk3(q0.x, q0.y, q0.z) - org, v1 = mk3(q1.x, q1.y, q1.z) - org, v2 = mk3(q2.x, q2.y, q2.z) - org;
-            float Ax = comp(v0, kx), Ay = comp(v0, ky), Az = comp(v0, kz);
-            float Bx = comp(v1, kx), By = comp(v1, ky), Bz = comp(v1, kz);
-            float Cx = comp(v2, kx), Cy = comp(v2, ky), Cz = comp(v2, kz);
-            Ax = Ax - shear.x * Az; Ay = Ay - shear.y * Az;
-            Bx = Bx - shear.x * Bz; By = By - shear.y * Bz;
-            Cx = Cx - shear.x * Cz; Cy = Cy - shear.y * Cz;
-            float U = Cx * By - Cy * Bx;
-            float V = Ax * Cy - Ay * Cx;
-            float W = Bx * Ay - By * Ax;
-            float det = (U + V) + W;
-            bool ok = !((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) && det != 0.0f;
-            if (ok) {
-                Az = shear.z * Az; Bz = shear.z * Bz; Cz = shear.z * Cz;
-                float T = (U * Az + V * Bz) + W * Cz;
-                float sct = fabsf(T);
-                if ((T > 0.0f) != (det > 0.0f)) sct = -sct;
-                if (!(sct < 0.0f || sct > committedT * fabsf(det))) {
-                    float rcpDet = 1.0f / det;
-                    float t0 = T * rcpDet;
-                    uint32_t g = __float_as_uint(q0.w), p = __float_as_uint(q1.w);
-                    bool closer = t0 < committedT; // TestLeafNodeIntersections :420 + equal-t tie-break
-                    bool tie = haveHit && t0 == committedT && (g < hitGeom || (g == hitGeom && p < hitPrim));
-                    if ((closer || tie) && t0 > tmin) {
-                        committedT = t0; hb1 = V * rcpDet; hb2 = W * rcpDet; hitGeom = g; hitPrim = p; haveHit = true;
-                    }
+        uint32_t slot = cur & 0x3fffffffu;
+        float4 q0 = __ldg(tris + 3 * (size_t)slot), q1 = __ldg(tris + 3 * (size_t)slot + 1), q2 = __ldg(tris + 3 * (size_t)slot + 2);
+        trisTested++;
+        f3 v0 = mk3(q0.x, q0.y, q0.z) - org, v1 = mk3(q1.x, q1.y, q1.z) - org, v2 = mk3(q2.x, q2.y, q2.z) - org;
+        float Ax = comp(v0, kx), Ay = comp(v0, ky), Az = comp(v0, kz);
+        float Bx = comp(v1, kx), By = comp(v1, ky), Bz = comp(v1, kz);
+        float Cx = comp(v2, kx), Cy = comp(v2, ky), Cz = comp(v2, kz);
+        Ax = Ax - shear.x * Az; Ay = Ay - shear.y * Az;
+        Bx = Bx - shear.x * Bz; By = By - shear.y * Bz;
+        Cx = Cx - shear.x * Cz; Cy = Cy - shear.y * Cz;
+        float U = Cx * By - Cy * Bx;
+        float V = Ax * Cy - Ay * Cx;
+        float W = Bx * Ay - By * Ax;
+        float det = (U + V) + W;
+        bool ok = !((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) && det != 0.0f;
+        if (ok) {
+            Az = shear.z * Az; Bz = shear.z * Bz; Cz = shear.z * Cz;
+            float T = (U * Az + V * Bz) + W * Cz;
+            float sct = fabsf(T);
+            if ((T > 0.0f) != (det > 0.0f)) sct = -sct;
+            if (!(sct < 0.0f || sct > committedT * fabsf(det))) {
+                float rcpDet = 1.0f / det;
+                float t0 = T * rcpDet;
+                uint32_t g = __float_as_uint(q0.w), p = __float_as_uint(q1.w);
+                bool closer = t0 < committedT; // TestLeafNodeIntersections :420 + equal-t tie-break
+                bool tie = haveHit && t0 == committedT && (g < hitGeom || (g == hitGeom && p < hitPrim));
+                if ((closer || tie) && t0 > tmin) {
+                    committedT = t0; hb1 = V * rcpDet; hb2 = W * rcpDet; hitGeom = g; hitPrim = p; haveHit = true;
                 }
-            }
-        } else {
-            float4 a = __ldg(pairs + 4 * (size_t)ref), b = __ldg(pairs + 4 * (size_t)ref + 1);
-            float4 c = __ldg(pairs + 4 * (size_t)ref + 2), d = __ldg(pairs + 4 * (size_t)ref + 3);
-            f3 ainv = abs3(inv);
-            float lt, rt;
-            bool lh = slab(lt, committedT, oinv, inv, ainv, a.x, a.y, a.z, b.x, b.y, b.z);
-            bool rh = slab(rt, committedT, oinv, inv, ainv, c.x, c.y, c.z, d.x, d.y, d.z);
-            boxesTested += 2;
-            uint32_t lref = __float_as_uint(a.w), rref = __float_as_uint(b.w);
-            if (lh && rh) { // far child first, near child on top; left is near on equal t (:754-765)
-                bool rightFirst = rt < lt;
-                if (sp + 2 <= TB_STACK_DEPTH) {
-                    stack[sp++] = rightFirst ? lref : rref;
-                    stack[sp++] = rightFirst ? rref : lref;
-                }
-            } else if (lh || rh) {
-                if (sp + 1 <= TB_STACK_DEPTH) stack[sp++] = rh ? rref : lref;
             }
         }
+        pop(stack);
     }
+
+    // cur is an internal node: both child boxes, push far then near; left is near on equal t (:754-765)
+    __device__ __forceinline__ void step_internal(uint32_t* stack, const float4* __restrict__ pairs) {
+        using namespace tbm;
+        uint32_t ref = cur;
+        float4 a = __ldg(pairs + 4 * (size_t)ref), b = __ldg(pairs + 4 * (size_t)ref + 1);
+        float4 c = __ldg(pairs + 4 * (size_t)ref + 2), d = __ldg(pairs + 4 * (size_t)ref + 3);
+        f3 ainv = abs3(inv);
+        float lt, rt;
+        bool lh = slab(lt, committedT, oinv, inv, ainv, a.x, a.y, a.z, b.x, b.y, b.z);
+        bool rh = slab(rt, committedT, oinv, inv, ainv, c.x, c.y, c.z, d.x, d.y, d.z);
+        boxesTested += 2;
+        uint32_t lref = __float_as_uint(a.w), rref = __float_as_uint(b.w);
+        if (lh && rh) {
+            bool rightFirst = rt < lt;
+            if (sp < TB_STACK_DEPTH) stack[sp++] = rightFirst ? lref : rref; // far child waits in memory
+            cur = rightFirst ? rref : lref;                                  // near child is visited next
+        } else if (lh || rh) {
+            cur = rh ? rref : lref;
+        } else {
+            pop(stack);
+        }
+    }
+    __device__ __forceinline__ void step(uint32_t* stack, const float4* __restrict__ pairs, const float4* __restrict__ tris) {
+        if (at_leaf()) step_leaf(stack, tris); else step_internal(stack, pairs);
+    }
+
     // ---- suspension: a long ray can be parked in global memory and resumed by a later kernel
     // in a warp of similarly long rays. The state is exactly the registers below plus the live
     // part of the stack, so pausing never changes the visit order or the counters.
@@ -135,7 +148,7 @@ struct Traversal {
         uint4* r4 = (uint4*)rec;
         r4[0] = make_uint4(pi, (uint32_t)sp, __float_as_uint(committedT), __float_as_uint(hb1));
         r4[1] = make_uint4(__float_as_uint(hb2), hitGeom, hitPrim, haveHit ? 1u : 0u);
-        r4[2] = make_uint4(trisTested, boxesTested, 0u, 0u);
+        r4[2] = make_uint4(trisTested, boxesTested, cur, 0u);
         for (int i = 0; i < sp; i++) rec[12 + i] = stack[i];
     }
     // ray setup is recomputed from the ray (same arithmetic => same values), the rest is restored
@@ -145,10 +158,10 @@ struct Traversal {
         uint4 a = r4[0], b = r4[1], c = r4[2];
         uint32_t pi = a.x;
         float4 o = rayO[pi], d = rayD[pi];
-        begin(bvh, stack, tbm::mk3(o.x, o.y, o.z), tbm::mk3(d.x, d.y, d.z), tmin_, tmax_);
+        begin(bvh, tbm::mk3(o.x, o.y, o.z), tbm::mk3(d.x, d.y, d.z), tmin_, tmax_);
         sp = (int)a.y; committedT = __uint_as_float(a.z); hb1 = __uint_as_float(a.w);
         hb2 = __uint_as_float(b.x); hitGeom = b.y; hitPrim = b.z; haveHit = b.w != 0;
-        trisTested = c.x; boxesTested = c.y;
+        trisTested = c.x; boxesTested = c.y; cur = c.z;
         for (int i = 0; i < sp; i++) stack[i] = rec[12 + i];
         return pi;
     }
@@ -164,7 +177,7 @@ struct Traversal {
 __device__ __forceinline__ void trace_ray(const DeviceBvh& bvh, tbm::f3 org, tbm::f3 dir, float tmin, float tmax, HitRec& out) {
     Traversal tr;
     uint32_t stack[TB_STACK_DEPTH];
-    tr.begin(bvh, stack, org, dir, tmin, tmax);
+    tr.begin(bvh, org, dir, tmin, tmax);
     const float4* __restrict__ pairs = (const float4*)bvh.pairs;
     const float4* __restrict__ tris = (const float4*)bvh.tris;
     while (!tr.done()) tr.step(stack, pairs, tris);
