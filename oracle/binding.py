@@ -38,6 +38,11 @@ def use_reference_core(on):
     return _ref.ref_core_calls()
 
 
+def set_literal_rcp(on):
+    """Test hook: literal rcp(0) = inf in GetRayData (deviation D6 off)."""
+    load().oracle_set_literal_rcp(1 if on else 0)
+
+
 def load():
     global _lib
     if _lib is None:

@@ -55,6 +55,8 @@ bool build_bvh(Scene& s, int treeletPasses, std::string& err);
 
 // SoftwareRayQuery::TraceRayInline + Proceed (TraverseFunction.hlsli:537-785), FAST_PATH.
 void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit);
+// test hook: evaluate GetRayData's rcp literally (inf for zero components) instead of the clamped form
+void set_literal_rcp(bool on);
 
 struct FrameBuffers {
     uint32_t width = 0, height = 0;

@@ -59,6 +59,9 @@ inline bool ray_tri(float& hitT, float& b1, float& b2, f3 org, int kx, int ky, i
 }
 } // namespace
 
+static bool g_literalRcp = false;
+void set_literal_rcp(bool on) { g_literalRcp = on; }
+
 void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit) {
     const uint8_t* bvh = s.bvh.data();
     uint32_t header[4];
@@ -71,6 +74,12 @@ void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit) {
     f3 dir = mk3(ray.Direction[0], ray.Direction[1], ray.Direction[2]);
     // GetRayData, TraverseFunction.hlsli:473-495
     f3 inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+    // Deviation D6: the reciprocal is clamped to +-1e18. With rcp(0) = inf the slab
+    // arithmetic below yields NaN, which min/max drop, so a ray with an exactly-zero direction
+    // component ignores that axis and walks every node overlapping the other two slabs. The
+    // reference's rand() returns exactly 0 about once in 300 draws, so such rays are common.
+    // Hits are identical either way (tests/test_cpu_oracle.py::test_clamped_reciprocal...).
+    if (!g_literalRcp) inv = mk3(clamp_(inv.x, -1.0e18f, 1.0e18f), clamp_(inv.y, -1.0e18f, 1.0e18f), clamp_(inv.z, -1.0e18f, 1.0e18f));
     f3 oinv = org * inv;
     f3 ad = abs3(dir);
     int kz = (ad.x > ad.y && ad.x > ad.z) ? 0 : (ad.y > ad.z ? 1 : 2);

@@ -291,3 +291,35 @@ def test_restated_core_equals_reference_core(spec, w, h, spp, over, tmp_path, bu
         x, y = a[k], b[k]
         same = ((x.view(np.uint32) == y.view(np.uint32)) | ((x != x) & (y != y))) if x.dtype == np.float32 else (x == y)
         assert same.all(), "buffer %d differs at %d elements" % (k, (~same).sum())
+
+
+@pytest.mark.parametrize("spec,w,h,spp", [("cornell", 96, 96, 6), ("teapot", 240, 135, 3),
+                                          ("synthetic:blobs?copies=8&tris=2000&seed=2", 128, 72, 3)])
+def test_clamped_reciprocal_keeps_hits_and_radiance(spec, w, h, spp, tmp_path, built):
+    """Deviation D6: clamping rcp(direction) to +-1e18 (instead of inf for exactly-zero components,
+    which makes the slab test NaN and the ray walk whole slabs of the BVH) changes traversal
+    counters only: radiance, primary-hit ids and ray counts are bit-identical to the literal form."""
+    import tracerboy_b200 as tb
+    from oracle import binding
+    if spec in ("cornell", "teapot"):
+        path = scene_path("cornell-box" if spec == "cornell" else "teapot")
+        if path is None:
+            pytest.skip("scene cache missing")
+    else:
+        path = str(tmp_path / "s.tbscene")
+        tb.convert_scene(spec, path)
+    out = []
+    try:
+        for literal in (True, False):
+            binding.set_literal_rcp(literal)
+            o = binding.Oracle(); o.LoadScene(path, 3); o.Resize(w, h)
+            s = tb.get_default_output_settings()
+            o.Render(s, spp, 0.0)
+            out.append((o.Readback(0), o.Readback(1), o.Readback(8), o.Counts()))
+    finally:
+        binding.set_literal_rcp(False)
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
+    assert np.array_equal(out[0][1].view(np.uint32), out[1][1].view(np.uint32))
+    assert np.array_equal(out[0][2], out[1][2])
+    assert out[0][3]["rays"] == out[1][3]["rays"]
+    assert out[1][3]["boxes"] <= out[0][3]["boxes"] and out[1][3]["tris"] <= out[0][3]["tris"]
