@@ -19,11 +19,27 @@ namespace {
 struct AABBNode { float c[3]; uint32_t flags; float h[3]; uint32_t right; };
 
 // RayBoxTest, TraverseFunction.hlsli:203-221
-inline bool ray_box(float& resultT, float closestT, f3 oinv, f3 inv, const AABBNode& b) {
+inline bool zero_axis_inside(float c, float h, float o) { // D6: |c - o| <= h + 1e-5 (|c| + h)
+    float t = fabsf(c) + h;
+    float tol = h + 1.0e-5f * t;
+    return fabsf(c - o) <= tol;
+}
+inline bool ray_box(float& resultT, float closestT, f3 org, int zmask, f3 oinv, f3 inv, const AABBNode& b) {
     f3 ainv = abs3(inv);
     float rx = fmaf(b.c[0], inv.x, -oinv.x), ry = fmaf(b.c[1], inv.y, -oinv.y), rz = fmaf(b.c[2], inv.z, -oinv.z);
     float maxx = fmaf(b.h[0], ainv.x, rx), maxy = fmaf(b.h[1], ainv.y, ry), maxz = fmaf(b.h[2], ainv.z, rz);
     float minx = fmaf(-b.h[0], ainv.x, rx), miny = fmaf(-b.h[1], ainv.y, ry), minz = fmaf(-b.h[2], ainv.z, rz);
+    if (zmask) {
+        const float inf = as_float(0x7f800000u);
+        bool inside = true;
+        if (zmask & 1) { minx = -inf; maxx = inf; inside = inside && zero_axis_inside(b.c[0], b.h[0], org.x); }
+        if (zmask & 2) { miny = -inf; maxy = inf; inside = inside && zero_axis_inside(b.c[1], b.h[1], org.y); }
+        if (zmask & 4) { minz = -inf; maxz = inf; inside = inside && zero_axis_inside(b.c[2], b.h[2], org.z); }
+        float minTz = fmaxf(fmaxf(minx, miny), minz);
+        float maxTz = fminf(fminf(maxx, maxy), maxz);
+        resultT = fmaxf(minTz, 0.0f);
+        return inside && fmaxf(minTz, 0.0f) < fminf(maxTz, closestT);
+    }
     float minT = fmaxf(fmaxf(minx, miny), minz);
     float maxT = fminf(fminf(maxx, maxy), maxz);
     resultT = fmaxf(minT, 0.0f);
@@ -74,12 +90,15 @@ void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit) {
     f3 dir = mk3(ray.Direction[0], ray.Direction[1], ray.Direction[2]);
     // GetRayData, TraverseFunction.hlsli:473-495
     f3 inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
-    // Deviation D6: the reciprocal is clamped to +-1e18. With rcp(0) = inf the slab
-    // arithmetic below yields NaN, which min/max drop, so a ray with an exactly-zero direction
-    // component ignores that axis and walks every node overlapping the other two slabs. The
-    // reference's rand() returns exactly 0 about once in 300 draws, so such rays are common.
-    // Hits are identical either way (tests/test_cpu_oracle.py::test_clamped_reciprocal...).
-    if (!g_literalRcp) inv = mk3(clamp_(inv.x, -1.0e18f, 1.0e18f), clamp_(inv.y, -1.0e18f, 1.0e18f), clamp_(inv.z, -1.0e18f, 1.0e18f));
+    // Deviation D6: exactly-zero direction components. Literally, rcp(0) = inf turns
+    // that axis' slab arithmetic into NaN, which min/max drop: the axis is ignored and the ray
+    // walks every node overlapping the other two slabs. The reference's rand() returns exactly 0
+    // about once in 300 draws, so such rays are common. Here a zero axis is tested by containment
+    // of the ray's (constant) coordinate in the box, widened by 1e-5 relative so that every node
+    // the literal form needs for its hits is still visited; hits are identical
+    // (tests/test_cpu_oracle.py::test_zero_axis_rule_keeps_hits_and_radiance), visits drop sharply.
+    int zmask = 0;
+    if (!g_literalRcp) zmask = (dir.x == 0.0f ? 1 : 0) | (dir.y == 0.0f ? 2 : 0) | (dir.z == 0.0f ? 4 : 0);
     f3 oinv = org * inv;
     f3 ad = abs3(dir);
     int kz = (ad.x > ad.y && ad.x > ad.z) ? 0 : (ad.y > ad.z ? 1 : 2);
@@ -96,7 +115,7 @@ void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit) {
     static thread_local std::vector<uint32_t> stack; // unbounded (reference: 16, unchecked)
     stack.clear();
     float unusedT;
-    if (ray_box(unusedT, committedT, oinv, inv, nodes[0])) stack.push_back(0);
+    if (ray_box(unusedT, committedT, org, zmask, oinv, inv, nodes[0])) stack.push_back(0);
     while (!stack.empty()) {
         uint32_t ni = stack.back();
         stack.pop_back();
@@ -117,8 +136,8 @@ void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit) {
         } else {
             uint32_t l = nd.flags & 0x3fffffffu, r = nd.right;
             float lt, rt;
-            bool lh = ray_box(lt, committedT, oinv, inv, nodes[l]);
-            bool rh = ray_box(rt, committedT, oinv, inv, nodes[r]);
+            bool lh = ray_box(lt, committedT, org, zmask, oinv, inv, nodes[l]);
+            bool rh = ray_box(rt, committedT, org, zmask, oinv, inv, nodes[r]);
             boxesTested += 2;
             if (lh && rh) { // far first, near last; on equal t left is near (:754-765)
                 bool rightFirst = rt < lt;

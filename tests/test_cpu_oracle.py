@@ -295,10 +295,10 @@ def test_restated_core_equals_reference_core(spec, w, h, spp, over, tmp_path, bu
 
 @pytest.mark.parametrize("spec,w,h,spp", [("cornell", 96, 96, 6), ("teapot", 240, 135, 3),
                                           ("synthetic:blobs?copies=8&tris=2000&seed=2", 128, 72, 3)])
-def test_clamped_reciprocal_keeps_hits_and_radiance(spec, w, h, spp, tmp_path, built):
-    """Deviation D6: clamping rcp(direction) to +-1e18 (instead of inf for exactly-zero components,
-    which makes the slab test NaN and the ray walk whole slabs of the BVH) changes traversal
-    counters only: radiance, primary-hit ids and ray counts are bit-identical to the literal form."""
+def test_zero_axis_rule_keeps_hits_and_radiance(spec, w, h, spp, tmp_path, built):
+    """Deviation D6: testing exactly-zero direction axes by containment (instead of the literal
+    rcp(0) = inf, which makes the slab test NaN and the ray walk whole slabs of the BVH) changes
+    traversal counters only: radiance, primary-hit ids and ray counts are bit-identical."""
     import tracerboy_b200 as tb
     from oracle import binding
     if spec in ("cornell", "teapot"):

@@ -36,6 +36,29 @@ __device__ __forceinline__ bool slab(float& resultT, float closestT, tbm::f3 oin
     return fmaxf(minT, 0.0f) < fminf(maxT, closestT);
 }
 
+// D6: slab test for a ray with exactly-zero direction components: those axes constrain nothing in t
+// and are tested by containment |c - o| <= h + 1e-5 (|c| + h).
+__device__ __forceinline__ bool zero_axis_inside(float c, float h, float o) {
+    float t = fabsf(c) + h;
+    float tol = h + 1.0e-5f * t;
+    return fabsf(c - o) <= tol;
+}
+__device__ __noinline__ bool slab_zero(float& resultT, float closestT, tbm::f3 org, int zmask, tbm::f3 oinv, tbm::f3 inv, tbm::f3 ainv,
+                                       float cx, float cy, float cz, float hx, float hy, float hz) {
+    float rx = fmaf(cx, inv.x, -oinv.x), ry = fmaf(cy, inv.y, -oinv.y), rz = fmaf(cz, inv.z, -oinv.z);
+    float maxx = fmaf(hx, ainv.x, rx), maxy = fmaf(hy, ainv.y, ry), maxz = fmaf(hz, ainv.z, rz);
+    float minx = fmaf(-hx, ainv.x, rx), miny = fmaf(-hy, ainv.y, ry), minz = fmaf(-hz, ainv.z, rz);
+    const float inf = __uint_as_float(0x7f800000u);
+    bool inside = true;
+    if (zmask & 1) { minx = -inf; maxx = inf; inside = inside && zero_axis_inside(cx, hx, org.x); }
+    if (zmask & 2) { miny = -inf; maxy = inf; inside = inside && zero_axis_inside(cy, hy, org.y); }
+    if (zmask & 4) { minz = -inf; maxz = inf; inside = inside && zero_axis_inside(cz, hz, org.z); }
+    float minT = fmaxf(fmaxf(minx, miny), minz);
+    float maxT = fminf(fminf(maxx, maxy), maxz);
+    resultT = fmaxf(minT, 0.0f);
+    return inside && fmaxf(minT, 0.0f) < fminf(maxT, closestT);
+}
+
 // Resumable traversal: begin() once per ray, then step_internal()/step_leaf() on the current
 // node until done(). The node to visit next is held in a register (`cur`), the rest of the
 // stack in a per-thread local array passed in by the caller, so only the far children of
@@ -50,6 +73,7 @@ struct Traversal {
     float tmin, tmax, committedT, hb1, hb2;
     uint32_t hitGeom, hitPrim, trisTested, boxesTested;
     bool haveHit;
+    int zmask;    // bit a set: direction component a is exactly zero (deviation D6)
     uint32_t cur; // node reference to process next (TB_NO_NODE = traversal finished)
     int sp;       // entries in the memory stack below `cur`
 
@@ -57,11 +81,11 @@ struct Traversal {
         using namespace tbm;
         org = o;
         inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z); // GetRayData, TraverseFunction.hlsli:473-495
-        // Deviation D6: clamp the reciprocal. rcp(0) = inf turns the slab arithmetic into
-        // NaN, which min/max drop, so a ray with an exactly-zero direction component (the reference's
-        // rand() returns exactly 0 about once in 300 draws) would walk every node overlapping the other
-        // two slabs. Same hits, orders of magnitude fewer visits; the oracle pins the same form.
-        inv = mk3(clamp_(inv.x, -1.0e18f, 1.0e18f), clamp_(inv.y, -1.0e18f, 1.0e18f), clamp_(inv.z, -1.0e18f, 1.0e18f));
+        // Deviation D6: exactly-zero direction components (the reference's rand() returns
+        // exactly 0 about once in 300 draws). Literally rcp(0) = inf makes that axis' slab test NaN, which
+        // min/max drop, so the ray would walk every node overlapping the other two slabs. A zero axis is
+        // tested by containment instead (slab_zero); same hits, orders of magnitude fewer visits.
+        zmask = (dir.x == 0.0f ? 1 : 0) | (dir.y == 0.0f ? 2 : 0) | (dir.z == 0.0f ? 4 : 0);
         oinv = org * inv;
         f3 ad = abs3(dir);
         kz = (ad.x > ad.y && ad.x > ad.z) ? 0 : (ad.y > ad.z ? 1 : 2);
@@ -75,7 +99,9 @@ struct Traversal {
         sp = 0;
         cur = TB_NO_NODE;
         float unusedT;
-        if (slab(unusedT, committedT, oinv, inv, abs3(inv), bvh.root.c[0], bvh.root.c[1], bvh.root.c[2], bvh.root.h[0], bvh.root.h[1], bvh.root.h[2]))
+        bool rootHit = zmask ? slab_zero(unusedT, committedT, org, zmask, oinv, inv, abs3(inv), bvh.root.c[0], bvh.root.c[1], bvh.root.c[2], bvh.root.h[0], bvh.root.h[1], bvh.root.h[2])
+                             : slab(unusedT, committedT, oinv, inv, abs3(inv), bvh.root.c[0], bvh.root.c[1], bvh.root.c[2], bvh.root.h[0], bvh.root.h[1], bvh.root.h[2]);
+        if (rootHit)
             cur = (bvh.root.flags & 0x80000000u) ? (0x80000000u | (bvh.root.flags & 0x3fffffffu)) : 0u;
     }
     __device__ __forceinline__ bool done() const { return cur == TB_NO_NODE; }
@@ -127,8 +153,14 @@ struct Traversal {
         float4 c = __ldg(pairs + 4 * (size_t)ref + 2), d = __ldg(pairs + 4 * (size_t)ref + 3);
         f3 ainv = abs3(inv);
         float lt, rt;
-        bool lh = slab(lt, committedT, oinv, inv, ainv, a.x, a.y, a.z, b.x, b.y, b.z);
-        bool rh = slab(rt, committedT, oinv, inv, ainv, c.x, c.y, c.z, d.x, d.y, d.z);
+        bool lh, rh;
+        if (zmask) { // rare path, kept out of line
+            lh = slab_zero(lt, committedT, org, zmask, oinv, inv, ainv, a.x, a.y, a.z, b.x, b.y, b.z);
+            rh = slab_zero(rt, committedT, org, zmask, oinv, inv, ainv, c.x, c.y, c.z, d.x, d.y, d.z);
+        } else {
+            lh = slab(lt, committedT, oinv, inv, ainv, a.x, a.y, a.z, b.x, b.y, b.z);
+            rh = slab(rt, committedT, oinv, inv, ainv, c.x, c.y, c.z, d.x, d.y, d.z);
+        }
         boxesTested += 2;
         uint32_t lref = __float_as_uint(a.w), rref = __float_as_uint(b.w);
         if (lh && rh) {
