@@ -510,53 +510,50 @@ __global__ void __launch_bounds__(128) k_extend(DeviceBvh bvh, PathState st, int
     Traversal tr;
     uint32_t stack[TB_STACK_DEPTH];
     tr.sp = 0; tr.cur = TB_NO_NODE;
-    bool active = false, exhausted = false;
+    bool haveRay = false, exhausted = false; // haveRay: this lane owns a ray (traversing or finished, not yet retired)
     uint32_t pi = 0, steps = 0;
     while (true) {
-        // ---- refill: idle lanes fetch the next rays of the queue (one atomic per warp)
-        uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        // ---- service phase (whole warp): retire finished rays, park rays over budget, refill idle lanes
+        if (haveRay && tr.done()) {
+            write_hit(st, tr, pi, bounceIsZero, outputHeatmap, aovMask, rays, ntris, nboxes);
+            haveRay = false;
+        } else if (haveRay && steps >= budgetMain) {
+            if (try_suspend(st, 0, tr, stack, pi)) haveRay = false;
+            else steps = 0; // buffer full: keep going here
+        }
+        uint32_t idle = __ballot_sync(0xffffffffu, !haveRay);
         if (idle && !exhausted) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(next, (uint32_t)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (!active) {
+            if (!haveRay) {
                 uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
                 if (i < count) {
                     pi = __ldg(queue + i);
                     float4 o = st.rayO[pi], d = st.rayD[pi];
                     tr.begin(bvh, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), MIN_T, FAR_T);
-                    active = true;
+                    haveRay = true;
                     steps = 0;
                 }
             }
             if (base + (uint32_t)__popc(idle) >= count) exhausted = true;
         }
-        uint32_t activeMask = __ballot_sync(0xffffffffu, active);
-        if (!activeMask) break;
-        // ---- warp-synchronous traversal: every iteration the whole warp executes ONE of the two
-        // code paths, the one more lanes are waiting for (box pair test vs. triangle test), so the
-        // two paths never serialise inside an iteration. Lanes on the minority path wait; since
-        // waiting lanes accumulate, they become the majority within a few iterations.
+        if (!__any_sync(0xffffffffu, haveRay)) break;
+        // ---- traversal phase: every iteration the whole warp executes ONE of the two code paths, the
+        // one more lanes are waiting for (box-pair test vs. triangle test), so the two never serialise
+        // inside an iteration; lanes on the minority path wait and soon become the majority. The phase
+        // ends when enough lanes have finished to make a service phase worthwhile.
         while (true) {
-            bool wantLeaf = active && !tr.done() && tr.at_leaf();
-            bool wantInternal = active && !tr.done() && !tr.at_leaf();
-            uint32_t mL = __ballot_sync(0xffffffffu, wantLeaf), mI = __ballot_sync(0xffffffffu, wantInternal);
-            if (__popc(mI) >= __popc(mL)) {
-                if (wantInternal) { tr.step_internal(stack, pairs); steps++; }
-            } else {
+            bool busy = haveRay && !tr.done();
+            bool wantLeaf = busy && tr.at_leaf();
+            uint32_t mB = __ballot_sync(0xffffffffu, busy), mL = __ballot_sync(0xffffffffu, wantLeaf);
+            uint32_t nB = __popc(mB), nL = __popc(mL);
+            if (nB == 0 || (!exhausted && nB < REFILL_THRESHOLD)) break;
+            if (2 * nL > nB) {
                 if (wantLeaf) { tr.step_leaf(stack, tris); steps++; }
+            } else {
+                if (busy && !wantLeaf) { tr.step_internal(stack, pairs); steps++; }
             }
-            // retire finished rays, park the ones over budget
-            if (active && tr.done()) {
-                write_hit(st, tr, pi, bounceIsZero, outputHeatmap, aovMask, rays, ntris, nboxes);
-                active = false;
-            } else if (active && steps >= budgetMain) {
-                if (try_suspend(st, 0, tr, stack, pi)) active = false;
-                else steps = 0; // buffer full: keep going here
-            }
-            uint32_t am = __ballot_sync(0xffffffffu, active);
-            if (!am) break;
-            if (!exhausted && __popc(am) < REFILL_THRESHOLD) break; // regroup and refill
         }
     }
     flush_stats(st, 0, rays, ntris, nboxes);
