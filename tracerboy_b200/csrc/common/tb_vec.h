@@ -62,7 +62,17 @@ TB_HD f3 exp3(f3 a) { return mk3(exp_(a.x), exp_(a.y), exp_(a.z)); }
 TB_HD f3 pow3(f3 a, float e) { return mk3(pow_(a.x, e), pow_(a.y, e), pow_(a.z, e)); }
 TB_HD f3 frac3(f3 a) { return mk3(frac(a.x), frac(a.y), frac(a.z)); }
 TB_HD f2 frac2(f2 a) { return mk2(frac(a.x), frac(a.y)); }
-TB_HD float comp(f3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+TB_HD float comp(f3 v, int i) {
+#if defined(__CUDA_ARCH__)
+    // two predicated selects; the plain ternary is compiled to divergent branch regions by nvcc 12.9
+    float r;
+    asm("{\n\t.reg .pred p0, p1;\n\tsetp.eq.s32 p0, %4, 0;\n\tsetp.eq.s32 p1, %4, 1;\n\tselp.f32 %0, %2, %3, p1;\n\tselp.f32 %0, %1, %0, p0;\n\t}"
+        : "=f"(r) : "f"(v.x), "f"(v.y), "f"(v.z), "r"(i));
+    return r;
+#else
+    return i == 0 ? v.x : (i == 1 ? v.y : v.z);
+#endif
+}
 
 } // namespace tbm
 #endif

@@ -456,6 +456,12 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, FrameConstants f
 // traversing, the warp regroups, idle lanes grab the next rays of the queue with one
 // warp-aggregated atomic, and traversal resumes. (A static assignment ran at 3.5 active
 // lanes per instruction on the incoherent bounces of the Teapot scene — profiles/.)
+#ifndef EXTEND_MIN_BLOCKS
+#define EXTEND_MIN_BLOCKS 8
+#endif
+#ifndef SHADE_MIN_BLOCKS
+#define SHADE_MIN_BLOCKS 8
+#endif
 #define REFILL_THRESHOLD 20
 // Step budgets: a ray that is still traversing after `budget` node visits in one kernel is
 // suspended (Traversal::suspend) and resumed by the next k_extend_resume round, where it shares
@@ -498,7 +504,7 @@ __device__ __forceinline__ bool try_suspend(PathState& st, int round, const Trav
     return true;
 }
 
-__global__ void __launch_bounds__(128) k_extend(DeviceBvh bvh, PathState st, int qi, int bounceIsZero, uint32_t outputHeatmap, uint32_t aovMask, uint32_t budgetMain) {
+__global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh, PathState st, int qi, int bounceIsZero, uint32_t outputHeatmap, uint32_t aovMask, uint32_t budgetMain) {
     const uint32_t count = st.queueCount[qi];
     if (blockIdx.x == 0 && threadIdx.x == 0) st.queueCount[qi ^ 1] = 0; // next queue starts empty (consumed by k_shade)
     uint32_t* __restrict__ next = &st.queueCount[2 + qi];               // work counter, zeroed by the previous kernel
@@ -598,7 +604,7 @@ __device__ __forceinline__ void finish_path(const FrameConstants& fc, PathState&
     st.sampleSeed[pi] = rng.seed;
 }
 
-__global__ void __launch_bounds__(128) k_shade(DeviceBvh bvh, DeviceScene sc, FrameConstants fc, PathState st, int qi) {
+__global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, DeviceScene sc, FrameConstants fc, PathState st, int qi) {
     const uint32_t count = st.queueCount[qi];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st.queueCount[2 + (qi ^ 1)] = 0; // work counter of the next k_extend
@@ -643,11 +649,13 @@ __global__ void __launch_bounds__(128) k_shade(DeviceBvh bvh, DeviceScene sc, Fr
                 Mat material = get_material(sc, rng, sf.material, sf.uv, backside);
                 f3 detailNormal = get_detail_normal(sc, fc, material, normal, sf.tangent, sf.uv);
                 if (bFirstRay) {
-                    float4 nb = st.neighbor[pi], nd = st.neighborDir[pi];
-                    f3 nrp = mk3(nb.x, nb.y, nb.z) + mk3(nd.x, nd.y, nd.z) * h4.x;
-                    f3 wp = mk3(0.0f) + RayPoint;
-                    float dn = 0.0f + length(nrp - RayPoint);
-                    if (fc.aovMask & AOV_WORLDPOS) st.aovWorldPos[fc.frame & 1][pi] = make_float4(wp.x, wp.y, wp.z, dn);
+                    if (fc.aovMask & AOV_WORLDPOS) {
+                        float4 nb = st.neighbor[pi], nd = st.neighborDir[pi];
+                        f3 nrp = mk3(nb.x, nb.y, nb.z) + mk3(nd.x, nd.y, nd.z) * h4.x;
+                        f3 wp = mk3(0.0f) + RayPoint;
+                        float dn = 0.0f + length(nrp - RayPoint);
+                        st.aovWorldPos[fc.frame & 1][pi] = make_float4(wp.x, wp.y, wp.z, dn);
+                    }
                     if (fc.aovMask & AOV_FULL) st.aovNormal[pi] = make_float4(detailNormal.x, detailNormal.y, detailNormal.z, 1.0f);
                     st.stDepth[pi] = saturate(h4.x / S.MaxZ);
                     if ((fc.aovMask & AOV_FULL) && (int)(pi % fc.width) == fc.selectedX && (int)(pi / fc.width) == fc.selectedY) {
