@@ -111,9 +111,11 @@ def test_trace_rays_bit_exact(spec, tmp_path, built):
     assert (hg["t"] > 0).sum() > 1000
 
 
-def test_cornell_render_bit_exact(cornell):
+@pytest.mark.parametrize("shadow_mode", [0, 1])
+def test_cornell_render_bit_exact(shadow_mode, cornell):
     import tracerboy_b200 as tb
     g, o = _pair(cornell, 128, 128)
+    g.SetShadowMode(shadow_mode)
     s = tb.get_default_output_settings()
     s.MaxBounces = 4
     _compare_render(g, o, s, 4)
@@ -143,11 +145,14 @@ def test_settings_variants(variant, cornell):
     _compare_render(g, o, s, 3)
 
 
-def test_materials_scene_bit_exact(tmp_path, built):
-    """Glass (SSS walk), metal, substrate, matte, area light + constant sky."""
+@pytest.mark.parametrize("shadow_mode", [0, 1])
+def test_materials_scene_bit_exact(shadow_mode, tmp_path, built):
+    """Glass (SSS walk), metal, substrate, matte, area light + constant sky; next-event shadow rays
+    traced inline (0) and as their own wavefront stage (1)."""
     import tracerboy_b200 as tb
     path = _tbscene("synthetic:blobs?copies=27&tris=300&seed=3", tmp_path)
     g, o = _pair(path, 160, 90)
+    g.SetShadowMode(shadow_mode)
     s = tb.get_default_output_settings()
     s.MaxBounces = 8
     _compare_render(g, o, s, 3)

@@ -140,7 +140,7 @@ def load_library():
         "tb_render": [vp, C.POINTER(OutputSettings), u32, C.c_float], "tb_samples_rendered": [vp, C.POINTER(u32)],
         "tb_invalidate_history": [vp], "tb_set_frame_shard": [vp, u32, u32], "tb_buffer_size": [vp, u32, C.POINTER(u64)],
         "tb_readback": [vp, u32, vp, u64], "tb_device_buffer": [vp, u32, C.POINTER(vp), C.POINTER(u64)],
-        "tb_get_render_stats": [vp, C.POINTER(RenderStats)], "tb_reset_render_stats": [vp], "tb_synchronize": [vp], "tb_set_profiling": [vp, i32], "tb_set_frames_in_flight": [vp, u32],
+        "tb_get_render_stats": [vp, C.POINTER(RenderStats)], "tb_reset_render_stats": [vp], "tb_synchronize": [vp], "tb_set_profiling": [vp, i32], "tb_set_frames_in_flight": [vp, u32], "tb_set_shadow_mode": [vp, i32],
         "tb_is_material_id_valid": [vp, i32], "tb_get_material": [vp, i32, C.POINTER(Material), C.c_char_p, u32],
         "tb_set_material": [vp, i32, C.POINTER(Material)],
         "tb_bvh_prebuild_info": [C.POINTER(GeometryDesc), u32, C.POINTER(PrebuildInfo)],
@@ -159,7 +159,7 @@ EXPORTED_SYMBOLS = ["tb_create", "tb_destroy", "tb_last_error", "tb_version", "t
                     "tb_get_bvh", "tb_get_bvh_build_ms", "tb_get_default_settings", "tb_get_camera", "tb_set_camera",
                     "tb_resize", "tb_select_pixel", "tb_get_stats", "tb_render", "tb_samples_rendered",
                     "tb_invalidate_history", "tb_set_frame_shard", "tb_buffer_size", "tb_readback", "tb_device_buffer",
-                    "tb_get_render_stats", "tb_reset_render_stats", "tb_set_profiling", "tb_set_frames_in_flight", "tb_synchronize", "tb_is_material_id_valid",
+                    "tb_get_render_stats", "tb_reset_render_stats", "tb_set_profiling", "tb_set_frames_in_flight", "tb_set_shadow_mode", "tb_synchronize", "tb_is_material_id_valid",
                     "tb_get_material", "tb_set_material", "tb_bvh_prebuild_info", "tb_bvh_build", "tb_trace_rays"]
 
 
@@ -337,6 +337,9 @@ class TracerBoy:
 
     def SetFramesInFlight(self, n):
         self._ck(self._lib.tb_set_frames_in_flight(self._h, int(n)))
+
+    def SetShadowMode(self, mode):
+        self._ck(self._lib.tb_set_shadow_mode(self._h, int(mode)))
 
     def SetProfiling(self, enable):
         self._ck(self._lib.tb_set_profiling(self._h, int(bool(enable))))

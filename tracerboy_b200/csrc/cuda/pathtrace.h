@@ -18,7 +18,13 @@ struct PathState {
     float4* neighbor = nullptr;    // neighbour camera ray origin (bounce 0 only)
     float4* neighborDir = nullptr; // neighbour camera ray direction
     uint32_t* queue[2] = {nullptr, nullptr};
-    uint32_t* queueCount = nullptr; // [0..1] queue sizes, [2..3] k_extend work counters
+    uint32_t* queueCount = nullptr; // [0..1] queue sizes, [2..3] k_extend work counters, [4] shadow queue size, [5] its work counter
+    // next-event shadow rays: queued by k_shade<0>, traced by k_extend<true>, consumed by k_shade<1>
+    uint32_t* shadowQueue = nullptr;
+    float4* shRayO = nullptr;
+    float4* shRayD = nullptr;
+    float4* shHit = nullptr;       // t, b1, b2, bits(primitiveIndex) of the first hit along the shadow feeler
+    uint32_t* shHitGeom = nullptr;
     // suspended long rays: two ping-pong record buffers, one counter per round
     uint32_t* susBuf[2] = {nullptr, nullptr};
     uint32_t* susCount = nullptr;   // 4 counters
@@ -69,12 +75,17 @@ struct KernelTimers {
     ~KernelTimers() { for (auto e : events) cudaEventDestroy(e); }
 };
 
+// scheduling knobs; none of them changes a result
+struct RenderOptions {
+    int shadowMode = 2; // next-event shadow rays: 0 traced inline in k_shade, 1 own wavefront stage, 2 automatic
+};
+
 uint64_t bvh_ref_bytes(uint32_t numPrims);
 cudaError_t build_bvh(const TbGeometryRecord* d_geoms, const uint32_t* d_triPrefix, uint32_t numGeoms,
                       const float* d_positions, const uint32_t* d_indices, uint32_t numPrims, int treeletPasses,
                       DeviceBvh& out, cudaStream_t stream, LaunchCounter& lc);
 cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const FrameConstants& fc, PathState& st,
-                         cudaStream_t stream, LaunchCounter& lc, KernelTimers* timers);
+                         cudaStream_t stream, LaunchCounter& lc, KernelTimers* timers, const RenderOptions& opts);
 cudaError_t accumulate_frame(const FrameConstants& fc, PathState& st, cudaStream_t stream, LaunchCounter& lc);
 cudaError_t resolve_rgb(const float4* accum, float* rgb, uint32_t n, cudaStream_t stream, LaunchCounter& lc);
 cudaError_t trace_rays(const DeviceBvh& bvh, const TbRay* d_rays, uint64_t n, TbHit* d_hits, cudaStream_t stream, LaunchCounter& lc);

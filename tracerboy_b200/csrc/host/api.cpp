@@ -55,6 +55,7 @@ struct TbHandle {
     TbSceneLoadStatus status{TB_LOAD_IDLE, 0, 0};
     std::vector<uint8_t> blueNoiseHost;
     bool profiling = false;
+    RenderOptions options;
     KernelTimers timers;
     double extendMs = 0.0, shadeMs = 0.0, resumeMs = 0.0;
     uint64_t extendLaunches = 0;
@@ -376,12 +377,13 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
     CUDA_OK(h, alloc((void**)&st.stats, 128)); CUDA_OK(h, alloc((void**)&st.readbackStats, sizeof(TbReadbackStats)));
     {
         // private state per slot: 5 float4 + hitGeom + 2 float4 + 2 queues + staging (float4+float+float4+float)
-        // + 2 suspension buffers. Automatic policy: as many slots as fit ~12 GB, between 4 and 32.
-        size_t perSlot = n * (80 + 4 + 32 + 8 + 40) + 2 * (n / 16 + 1024) * 448;
+        // + 2 suspension buffers. Automatic policy: as many slots as fit ~12 GB, between 4 and 8 (more
+        // buys nothing once no kernel has a long tail, see profiles/README.md).
+        size_t perSlot = n * (80 + 4 + 32 + 8 + 40 + 56) + 2 * (n / 16 + 1024) * 448;
         uint32_t fif = h->framesInFlight;
         if (fif == 0) {
             size_t fit = ((size_t)12 << 30) / perSlot;
-            fif = (uint32_t)(fit < 4 ? 4 : (fit > 32 ? 32 : fit));
+            fif = (uint32_t)(fit < 4 ? 4 : (fit > 8 ? 8 : fit));
         }
         h->slots.resize(fif);
     }
@@ -393,7 +395,9 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
         CUDA_OK(h, alloc((void**)&p.hit, 16 * n)); CUDA_OK(h, alloc((void**)&p.hitGeom, 4 * n));
         CUDA_OK(h, alloc((void**)&p.neighbor, 16 * n)); CUDA_OK(h, alloc((void**)&p.neighborDir, 16 * n));
         CUDA_OK(h, alloc((void**)&p.queue[0], 4 * n)); CUDA_OK(h, alloc((void**)&p.queue[1], 4 * n));
-        CUDA_OK(h, alloc((void**)&p.queueCount, 16));
+        CUDA_OK(h, alloc((void**)&p.queueCount, 32));
+        CUDA_OK(h, alloc((void**)&p.shadowQueue, 4 * n)); CUDA_OK(h, alloc((void**)&p.shRayO, 16 * n)); CUDA_OK(h, alloc((void**)&p.shRayD, 16 * n));
+        CUDA_OK(h, alloc((void**)&p.shHit, 16 * n)); CUDA_OK(h, alloc((void**)&p.shHitGeom, 4 * n));
         p.susCapacity = (uint32_t)(n / 16 + 1024);
         CUDA_OK(h, alloc((void**)&p.susBuf[0], (size_t)p.susCapacity * 448)); CUDA_OK(h, alloc((void**)&p.susBuf[1], (size_t)p.susCapacity * 448));
         CUDA_OK(h, alloc((void**)&p.susCount, 16));
@@ -464,7 +468,7 @@ TB_API int tb_render(TbHandle* h, const TbOutputSettings* s, uint32_t nSamples, 
         TbHandle::Slot& sl = h->slots[serial ? 0 : h->framesIssued % h->slots.size()];
         // the slot's previous frame must have been consumed by its k_accumulate
         CUDA_OK(h, cudaStreamWaitEvent(sl.stream, sl.accDone, 0));
-        CUDA_OK(h, render_frame(h->bvh, h->dscene, fc, sl.st, sl.stream, h->lc, h->profiling ? &h->timers : nullptr));
+        CUDA_OK(h, render_frame(h->bvh, h->dscene, fc, sl.st, sl.stream, h->lc, h->profiling ? &h->timers : nullptr, h->options));
         CUDA_OK(h, cudaEventRecord(sl.frameDone, sl.stream));
         CUDA_OK(h, cudaStreamWaitEvent(h->stream, sl.frameDone, 0));
         CUDA_OK(h, accumulate_frame(fc, sl.st, h->stream, h->lc)); // frame order == issue order on h->stream
@@ -595,6 +599,11 @@ TB_API int tb_set_frames_in_flight(TbHandle* h, uint32_t n) {
         free_frame(h);
         return tb_resize(h, w, hh);
     }
+    return TB_OK;
+}
+TB_API int tb_set_shadow_mode(TbHandle* h, int mode) {
+    if (!h || mode < 0 || mode > 2) return fail(h, TB_ERR_INVALID_ARG, "shadow mode must be 0 (inline), 1 (queue) or 2 (auto)");
+    h->options.shadowMode = mode;
     return TB_OK;
 }
 TB_API int tb_set_profiling(TbHandle* h, int enable) {
