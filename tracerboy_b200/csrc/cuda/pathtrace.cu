@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, FrameConstants f
     uint32_t n = fc.width * fc.height;
     if (pi == 0) {
         st.queueCount[0] = n; st.queueCount[1] = 0; st.queueCount[2] = 0; st.queueCount[3] = 0; st.queueCount[4] = 0; st.queueCount[5] = 0;
+        for (int r = 6; r < 10; r++) st.queueCount[r] = 0;
         for (int r = 0; r < 4; r++) st.susCount[r] = 0;
     }
     if (pi >= n) return;
@@ -471,12 +472,15 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, FrameConstants f
 #define EXTEND_BUDGET_MAIN 160u
 #define EXTEND_RESUME_ROUNDS 3
 
-__device__ __forceinline__ void write_hit(PathState& st, const Traversal& tr, uint32_t pi, int bounceIsZero, uint32_t outputHeatmap,
+// returns true when the ray hit something (the path then goes to the hit queue, otherwise to the miss queue)
+__device__ __forceinline__ bool write_hit(PathState& st, const Traversal& tr, uint32_t pi, int bounceIsZero, uint32_t outputHeatmap,
                                           uint32_t aovMask, uint32_t& rays, uint32_t& ntris, uint32_t& nboxes) {
     HitRec h;
     tr.result(h);
-    st.hit[pi] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
-    st.hitGeom[pi] = h.geom;
+    if (h.t >= 0.0f) { // a miss needs no hit record: k_shade_miss only reads the ray
+        st.hit[pi] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
+        st.hitGeom[pi] = h.geom;
+    }
     if (aovMask & AOV_FULL) {
         uint2 c = st.counters[pi];
         c.x += h.tris; c.y += h.boxes;
@@ -485,6 +489,13 @@ __device__ __forceinline__ void write_hit(PathState& st, const Traversal& tr, ui
         if (outputHeatmap) st.aovAlbedo[pi] = make_float4((float)h.tris, (float)h.boxes, 0.0f, 0.0f);
     }
     rays++; ntris += h.tris; nboxes += h.boxes;
+    return h.t >= 0.0f;
+}
+
+// hit / miss queues of the bounce: counters [6 + 2*qi] (hits) and [7 + 2*qi] (misses)
+__device__ __forceinline__ void push_sorted(PathState& st, int qi, uint32_t pi, bool hit) {
+    uint32_t slot = atomicAdd(&st.queueCount[6 + 2 * qi + (hit ? 0 : 1)], 1u);
+    (hit ? st.hitQueue : st.missQueue)[slot] = pi;
 }
 
 __device__ __forceinline__ void flush_stats(PathState& st, int slot, uint32_t rays, uint32_t ntris, uint32_t nboxes) {
@@ -528,6 +539,7 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
     uint32_t pi = 0, steps = 0;
     while (true) {
         // ---- service phase (whole warp): retire finished rays, park rays over budget, refill idle lanes
+        bool retired = false, retiredHit = false;
         if (haveRay && tr.done()) {
             if (SHADOW) {
                 HitRec h;
@@ -536,11 +548,28 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
                 st.shHitGeom[pi] = h.geom;
                 if (aovMask & AOV_FULL) { uint2 c = st.counters[pi]; c.x += h.tris; c.y += h.boxes; st.counters[pi] = c; }
                 rays++; ntris += h.tris; nboxes += h.boxes;
-            } else write_hit(st, tr, pi, bounceIsZero, outputHeatmap, aovMask, rays, ntris, nboxes);
+            } else {
+                retiredHit = write_hit(st, tr, pi, bounceIsZero, outputHeatmap, aovMask, rays, ntris, nboxes);
+                retired = true;
+            }
             haveRay = false;
         } else if (!SHADOW && haveRay && steps >= budgetMain) {
             if (try_suspend(st, 0, tr, stack, pi)) haveRay = false;
             else steps = 0; // buffer full: keep going here
+        }
+        if (!SHADOW) { // sort retired paths into the hit / miss queues (material-class split of the shading stage)
+            uint32_t mh = __ballot_sync(0xffffffffu, retired && retiredHit), mm = __ballot_sync(0xffffffffu, retired && !retiredHit);
+            if (mh | mm) {
+                uint32_t bh = 0, bm = 0;
+                if (lane == 0) {
+                    if (mh) bh = atomicAdd(&st.queueCount[6 + 2 * qi], (uint32_t)__popc(mh));
+                    if (mm) bm = atomicAdd(&st.queueCount[7 + 2 * qi], (uint32_t)__popc(mm));
+                }
+                bh = __shfl_sync(0xffffffffu, bh, 0); bm = __shfl_sync(0xffffffffu, bm, 0);
+                const uint32_t below = (1u << lane) - 1u;
+                if (retired && retiredHit) st.hitQueue[bh + __popc(mh & below)] = pi;
+                if (retired && !retiredHit) st.missQueue[bm + __popc(mm & below)] = pi;
+            }
         }
         uint32_t idle = __ballot_sync(0xffffffffu, !haveRay);
         if (idle && !exhausted) {
@@ -581,7 +610,7 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
 }
 
 // Resume round `round` (1-based): continues the rays parked by round-1; the last round has no budget.
-__global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState st, int round, uint32_t budget, int bounceIsZero,
+__global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState st, int qi, int round, uint32_t budget, int bounceIsZero,
                                                        uint32_t outputHeatmap, uint32_t aovMask) {
     const uint32_t count = min(st.susCount[round - 1], st.susCapacity);
     const float4* __restrict__ pairs = (const float4*)bvh.pairs;
@@ -594,7 +623,7 @@ __global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState 
         uint32_t pi = tr.resume(bvh, in + (size_t)i * Traversal::kRecordWords, stack, st.rayO, st.rayD, MIN_T, FAR_T);
         uint32_t steps = 0;
         while (true) {
-            if (tr.done()) { write_hit(st, tr, pi, bounceIsZero, outputHeatmap, aovMask, rays, ntris, nboxes); break; }
+            if (tr.done()) { push_sorted(st, qi, pi, write_hit(st, tr, pi, bounceIsZero, outputHeatmap, aovMask, rays, ntris, nboxes)); break; }
             if (budget && steps >= budget) {
                 if (try_suspend(st, round, tr, stack, pi)) break;
                 steps = 0;
@@ -627,10 +656,11 @@ __device__ __forceinline__ void finish_path(const FrameConstants& fc, PathState&
 //          never reach that code; kept for tb_set_shadow_mode(0) A/B measurements).
 template <int STAGE>
 __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, DeviceScene sc, FrameConstants fc, PathState st, int qi) {
-    const uint32_t count = STAGE == 1 ? st.queueCount[4] : st.queueCount[qi];
-    const uint32_t* __restrict__ inQueue = STAGE == 1 ? st.shadowQueue : st.queue[qi];
+    const uint32_t count = STAGE == 1 ? st.queueCount[4] : st.queueCount[6 + 2 * qi];
+    const uint32_t* __restrict__ inQueue = STAGE == 1 ? st.shadowQueue : st.hitQueue;
     if (STAGE != 1 && blockIdx.x == 0 && threadIdx.x == 0) {
         st.queueCount[2 + (qi ^ 1)] = 0; // work counter of the next k_extend
+        st.queueCount[6 + 2 * (qi ^ 1)] = 0; st.queueCount[7 + 2 * (qi ^ 1)] = 0; // hit / miss queues of the next bounce
         for (int r = 0; r < 4; r++) st.susCount[r] = 0; // suspension counters of the next bounce
     }
     const TbOutputSettings& S = fc.settings;
@@ -878,6 +908,24 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, 
     }
 }
 
+// Paths whose extension ray left the scene (kernel.glsl:1328-1343): radiance += throughput * environment,
+// then the path ends. Split from k_shade so that the (large) miss population neither diverges against
+// surface shading nor pays for its register footprint; reads only the ray, throughput and colour.
+__global__ void __launch_bounds__(256) k_shade_miss(DeviceScene sc, FrameConstants fc, PathState st, int qi) {
+    const uint32_t count = st.queueCount[7 + 2 * qi];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        uint32_t pi = st.missQueue[i];
+        float4 o4 = st.rayO[pi], d4 = st.rayD[pi], t4 = st.thr[pi], c4 = st.col[pi];
+        Rng rng; rng.seed = o4.w; rng.time = fc.time;
+        f3 thr = mk3(t4.x, t4.y, t4.z), acc = mk3(c4.x, c4.y, c4.z);
+        if (!(thr.x < EPSILON && thr.y < EPSILON && thr.z < EPSILON)) { // kernel.glsl:1319-1326 comes first
+            acc += thr * sample_environment_map(sc, mk3(d4.x, d4.y, d4.z));
+            if ((__float_as_uint(d4.w) & 0xffu) == 0u) st.stEmissive[pi] = make_float4(acc.x, acc.y, acc.z, 1.0f);
+        }
+        finish_path(fc, st, pi, acc, t4.w, rng);
+    }
+}
+
 // RayTraceCommon tail (RayGenCommon.h:709-727), one launch per frame, in frame order:
 // OutputTexture += sample, the jittered-buffer coin (one more rand() of the path's stream),
 // and the ordered merge of the two persistent AOVs.
@@ -957,11 +1005,12 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
             if (rblocks > sms * 4) rblocks = sms * 4;
             if (timers) cudaEventRecord(timers->next(KernelTimers::RESUME), stream);
             for (int r = 1; r <= EXTEND_RESUME_ROUNDS; r++) {
-                k_extend_resume<<<rblocks, 128, 0, stream>>>(bvh, st, r, budgets[r - 1], b == 0, heat, fc.aovMask); lc.count++;
+                k_extend_resume<<<rblocks, 128, 0, stream>>>(bvh, st, qi, r, budgets[r - 1], b == 0, heat, fc.aovMask); lc.count++;
                 rblocks = (rblocks + 3) / 4 > sms ? (rblocks + 3) / 4 : sms;
             }
         }
         if (timers) cudaEventRecord(timers->next(KernelTimers::SHADE), stream);
+        k_shade_miss<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(sc, fc, st, qi); lc.count++;
         // next-event shadow rays exist only with lights and NEE on; then shading runs as two stages
         // around a traversal kernel for the shadow queue
         const bool nee = sc.numLights > 0 && fc.settings.EnableNextEventEstimation;

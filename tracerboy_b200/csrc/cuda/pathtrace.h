@@ -18,7 +18,10 @@ struct PathState {
     float4* neighbor = nullptr;    // neighbour camera ray origin (bounce 0 only)
     float4* neighborDir = nullptr; // neighbour camera ray direction
     uint32_t* queue[2] = {nullptr, nullptr};
-    uint32_t* queueCount = nullptr; // [0..1] queue sizes, [2..3] k_extend work counters, [4] shadow queue size, [5] its work counter
+    uint32_t* queueCount = nullptr; // [0..1] queue sizes, [2..3] k_extend work counters, [4] shadow queue size, [5] its work counter, [6..9] hit/miss queue sizes
+    // the bounce's paths sorted by k_extend into "hit something" / "left the scene"; counters [6..9] by queue parity
+    uint32_t* hitQueue = nullptr;
+    uint32_t* missQueue = nullptr;
     // next-event shadow rays: queued by k_shade<0>, traced by k_extend<true>, consumed by k_shade<1>
     uint32_t* shadowQueue = nullptr;
     float4* shRayO = nullptr;
