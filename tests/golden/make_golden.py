@@ -21,6 +21,7 @@ CASES = {
     "cornell_64_default": ("cornell-box.tbscene", 64, 64, 4, 4, {}),
     "cornell_48_nobluenoise": ("cornell-box.tbscene", 48, 48, 3, 5, {"EnableBlueNoise": 0}),
     "blobs_64x36": ("synthetic:blobs?copies=8&tris=200&seed=2", 64, 36, 3, 8, {}),
+    "showcase_96x54": ("synthetic:showcase?tris=300&seed=1", 96, 54, 4, 8, {"EnableNormalMaps": 1}),
 }
 
 

@@ -253,6 +253,11 @@ REF_CASES = [
     ("cornell", 48, 48, 2, {"OutputType": 9}),
     ("synthetic:blobs?copies=27&tris=300&seed=3", 160, 90, 3, {"MaxBounces": 8}),
     ("teapot", 240, 135, 3, {}),
+    # every material / texture / light path: mix, specular map, scale + image textures (float and RGBA8 with
+    # gamma), normal map, emissive texture, glass / rough glass / single-sided / artist-albedo SSS, mirror,
+    # hair flag, area + directional light, transformed sky
+    ("synthetic:showcase?tris=400&seed=1", 200, 112, 4, {"MaxBounces": 8, "EnableNormalMaps": 1}),
+    ("synthetic:showcase?tris=200&seed=2", 128, 72, 3, {"MaxBounces": 6, "EnableBlueNoise": 0, "EnableSamplingImportanceResampling": 1}),
 ]
 
 

@@ -158,6 +158,31 @@ def test_materials_scene_bit_exact(shadow_mode, tmp_path, built):
     _compare_render(g, o, s, 3)
 
 
+@pytest.mark.parametrize("shadow_mode", [0, 1])
+def test_showcase_scene_bit_exact(shadow_mode, tmp_path, built):
+    """Every material / texture / light path (mix, specular map, scale + image textures incl. gamma,
+    normal map, emissive texture, glass variants, artist-albedo SSS, mirror, hair flag, directional
+    light, transformed sky), normal maps enabled."""
+    import tracerboy_b200 as tb
+    path = _tbscene("synthetic:showcase?tris=400&seed=1", tmp_path)
+    g, o = _pair(path, 200, 112)
+    g.SetShadowMode(shadow_mode)
+    s = tb.get_default_output_settings()
+    s.MaxBounces = 8
+    s.EnableNormalMaps = 1
+    _compare_render(g, o, s, 4)
+
+
+def test_showcase_scene_no_blue_noise_sir(tmp_path, built):
+    import tracerboy_b200 as tb
+    path = _tbscene("synthetic:showcase?tris=200&seed=2", tmp_path)
+    g, o = _pair(path, 128, 72)
+    s = tb.get_default_output_settings()
+    s.EnableBlueNoise = 0
+    s.EnableSamplingImportanceResampling = 1
+    _compare_render(g, o, s, 3)
+
+
 # ----------------------------------------------------------------- golden fixtures on the GPU
 import sys as _sys
 _sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))

@@ -429,6 +429,108 @@ bool make_synthetic(Scene& s, const std::string& spec, std::string& err) {
         s.camera.Up = up;
         return true;
     }
+    if (name == "showcase") {
+        // Every material / texture / light code path of the tracer in one small scene (parity coverage):
+        // matte + checker, substrate + scale(checker, image) texture, plastic-like dielectric + RGBA8 image with
+        // gamma flag, metal with specular map, mirror, glass, single-sided uber glass, SSS with artist albedo,
+        // mix(metal, matte), emissive texture, hair flag; one area light, one directional light, HDR-ish sky.
+        long tris = geti("tris", 400), seed = geti("seed", 1);
+        uint32_t rings = 2, segs = 3;
+        while (2ul * rings * segs - 2ul * segs < (unsigned long)tris) { rings++; segs = rings + rings / 4; if (segs < 3) segs = 3; }
+        // images: 0 = sky (float4 4x2), 1 = RGBA8 8x8 pattern, 2 = float4 4x4 pattern
+        {
+            Image sky; sky.width = 4; sky.height = 2; sky.format = 0;
+            float px[8][4] = {{0.3f, 0.4f, 0.7f, 1}, {0.5f, 0.5f, 0.6f, 1}, {2.5f, 2.2f, 1.8f, 1}, {0.4f, 0.45f, 0.6f, 1},
+                              {0.2f, 0.2f, 0.25f, 1}, {0.25f, 0.22f, 0.2f, 1}, {0.3f, 0.25f, 0.2f, 1}, {0.2f, 0.2f, 0.22f, 1}};
+            sky.data.assign((uint8_t*)px, (uint8_t*)px + sizeof(px));
+            s.images.push_back(sky);
+            Image a; a.width = a.height = 8; a.format = 1; a.data.resize(8 * 8 * 4);
+            uint32_t rs = (uint32_t)seed * 977u + 5u;
+            for (size_t i = 0; i < a.data.size(); i++) a.data[i] = (uint8_t)(64 + (lcg(rs) >> 25));
+            s.images.push_back(a);
+            Image b; b.width = b.height = 4; b.format = 0; b.data.resize(4 * 4 * 16);
+            float* bp = (float*)b.data.data();
+            for (int i = 0; i < 64; i++) bp[i] = 0.1f + 0.8f * unit(rs);
+            s.images.push_back(b);
+        }
+        s.envImage = 0;
+        s.envTransform[0] = {0.8f, 0.0f, 0.6f, 0}; s.envTransform[1] = {0.0f, 1.0f, 0.0f, 0}; s.envTransform[2] = {-0.6f, 0.0f, 0.8f, 0};
+        s.envColorScale = {1.0f, 0.9f, 0.8f};
+        s.flipTextureUVs = 1;
+        auto checker = [&](float us, float vs, TbFloat3 c1, TbFloat3 c2) {
+            TbTextureData t; memset(&t, 0, sizeof(t));
+            t.TextureType = TB_CHECKER_TEXTURE_TYPE; t.UScale = us; t.VScale = vs; t.CheckerColor1 = c1; t.CheckerColor2 = c2;
+            s.textures.push_back(t); return (uint32_t)s.textures.size() - 1;
+        };
+        auto image = [&](uint32_t img, uint32_t flags) {
+            TbTextureData t; memset(&t, 0, sizeof(t));
+            t.TextureType = TB_IMAGE_TEXTURE_TYPE; t.DescriptorHeapIndex = img; t.TextureFlags = flags;
+            s.textures.push_back(t); return (uint32_t)s.textures.size() - 1;
+        };
+        uint32_t texChecker = checker(6.0f, 3.0f, {0.8f, 0.2f, 0.2f}, {0.2f, 0.2f, 0.8f});
+        uint32_t texImg8 = image(1, TB_NEEDS_GAMMA_CORRECTION_TEXTURE_FLAG);
+        uint32_t texImgF = image(2, 0);
+        uint32_t texScale;
+        {
+            TbTextureData t; memset(&t, 0, sizeof(t));
+            t.TextureType = TB_SCALE_TEXTURE_TYPE; t.TextureIndex1 = texChecker; t.TextureIndex2 = texImgF;
+            t.ScaleColor1 = {0.5f, 0.6f, 0.7f}; t.ScaleColor2 = {0.4f, 0.3f, 0.2f};
+            s.textures.push_back(t); texScale = (uint32_t)s.textures.size() - 1;
+        }
+        uint32_t texSpec = checker(4.0f, 4.0f, {0.0f, 0.35f, 1.0f}, {0.0f, 0.1f, 0.0f}); // g = roughness, b > 0.5 => metallic
+        std::vector<uint32_t> mats;
+        TbMaterial m;
+        m = default_material({0, 0, 0}); m.albedo = {0.5f, 0.5f, 0.5f}; m.albedoIndex = texChecker; m.Flags |= TB_NO_SPECULAR_MATERIAL_FLAG; mats.push_back(add_mat(s, "matte_checker", m));
+        m = default_material({0, 0, 0}); m.albedo = {0.9f, 0.9f, 0.9f}; m.albedoIndex = texScale; m.IOR = 1.5f; m.SpecularCoef = 0.04f; m.roughness = 0.2f; mats.push_back(add_mat(s, "substrate_scale", m));
+        m = default_material({0, 0, 0}); m.albedo = {0.5f, 0.5f, 0.5f}; m.albedoIndex = texImg8; m.IOR = 1.46f; m.SpecularCoef = 0.04f; m.roughness = 0.03f; mats.push_back(add_mat(s, "plastic_image", m));
+        m = default_material({0, 0, 0}); m.albedo = {0.9f, 0.8f, 0.6f}; m.specularMapIndex = texSpec; m.roughness = 0.3f; m.IOR = 0.8f; mats.push_back(add_mat(s, "specmap", m));
+        m = default_material({0, 0, 0}); m.albedo = {0.9f, 0.9f, 0.9f}; m.SpecularCoef = 1.0f; m.roughness = 0.0f; m.Flags |= TB_METALLIC_MATERIAL_FLAG; mats.push_back(add_mat(s, "mirror", m));
+        m = default_material({0, 0, 0}); m.albedo = {0, 0, 0}; m.IOR = 1.5f; m.roughness = 0.0f; m.Flags |= TB_SUBSURFACE_SCATTER_MATERIAL_FLAG; mats.push_back(add_mat(s, "glass", m));
+        m = default_material({0, 0, 0}); m.albedo = {0, 0, 0}; m.IOR = 1.3f; m.roughness = 0.3f; m.Flags |= TB_SUBSURFACE_SCATTER_MATERIAL_FLAG; mats.push_back(add_mat(s, "rough_glass", m));
+        m = default_material({0, 0, 0}); m.albedo = {0.0f, 0.0f, 0.0f}; m.IOR = 1.5f; m.absorption = {0.2f, 0.05f, 0.4f}; m.roughness = 0.1f; m.Flags |= TB_SUBSURFACE_SCATTER_MATERIAL_FLAG | TB_SINGLE_SIDED_MATERIAL_FLAG; mats.push_back(add_mat(s, "uber_thin", m));
+        m = default_material({0, 0, 0}); m.albedo = {0.8f, 0.5f, 0.3f}; m.scattering = {2.0f, 1.0f, 0.5f}; m.IOR = 1.4f; m.roughness = 0.4f; m.Flags |= TB_SUBSURFACE_SCATTER_MATERIAL_FLAG | TB_NO_SPECULAR_MATERIAL_FLAG; mats.push_back(add_mat(s, "sss_albedo", m));
+        {   // mix(metal, matte): sub-materials first, as MaterialTracker adds them (TracerBoy.cpp:365-373)
+            TbMaterial a = default_material({0, 0, 0}); a.albedo = {1, 1, 1}; a.IOR = 0.9f; a.roughness = 0.15f; a.Flags |= TB_METALLIC_MATERIAL_FLAG;
+            uint32_t i0 = add_mat(s, "mix_metal", a);
+            TbMaterial b = default_material({0, 0, 0}); b.albedo = {0.1f, 0.3f, 0.6f}; b.Flags |= TB_NO_SPECULAR_MATERIAL_FLAG;
+            uint32_t i1 = add_mat(s, "mix_matte", b);
+            m = default_material({0, 0, 0}); m.Flags = TB_MIX_MATERIAL_FLAG; m.albedo = {(float)i0, (float)i1, 0.35f};
+            mats.push_back(add_mat(s, "mix", m));
+        }
+        m = default_material({0, 0, 0}); m.albedo = {0.3f, 0.3f, 0.3f}; m.emissiveIndex = texImgF; m.Flags |= TB_NO_SPECULAR_MATERIAL_FLAG; mats.push_back(add_mat(s, "emissive_tex", m));
+        m = default_material({0, 0, 0}); m.albedo = {0.4f, 0.25f, 0.1f}; m.roughness = 0.25f; m.Flags |= TB_HAIR_MATERIAL_FLAG; mats.push_back(add_mat(s, "hair", m));
+        m = default_material({0, 0, 0}); m.albedo = {0.6f, 0.6f, 0.6f}; m.normalMapIndex = texImgF; m.IOR = 1.5f; m.SpecularCoef = 0.05f; m.roughness = 0.3f; mats.push_back(add_mat(s, "normalmapped", m));
+        uint32_t side = 4;
+        for (size_t k = 0; k < mats.size(); k++) {
+            TbFloat3 c = {-45.0f + 30.0f * (float)(k % side), -20.0f + 28.0f * (float)(k / side), 10.0f * (float)((k * 7) % 3)};
+            add_blob(s, c, 11.0f, rings, segs, (uint32_t)(seed * 131 + k), mats[k]);
+        }
+        m = default_material({0, 0, 0}); m.albedo = {0.5f, 0.5f, 0.5f}; m.albedoIndex = texChecker; m.IOR = 1.5f; m.SpecularCoef = 0.04f; m.roughness = 0.15f;
+        uint32_t floorMat = add_mat(s, "floor", m);
+        TbFloat3 Le = {30.0f, 28.0f, 24.0f};
+        m = default_material(Le); m.Flags |= TB_NO_SPECULAR_MATERIAL_FLAG;
+        uint32_t lightMat = add_mat(s, "light", m);
+        add_quad(s, {-120, -34, -120}, {-120, -34, 120}, {120, -34, 120}, {120, -34, -120}, floorMat, false, {0, 0, 0});
+        add_quad(s, {-30, 110, -30}, {30, 110, -30}, {30, 110, 30}, {-30, 110, 30}, lightMat, true, Le);
+        {   // directional light (TracerBoy.cpp:1908-1916)
+            TbLight l; memset(&l, 0, sizeof(l));
+            l.LightType = TB_LIGHT_TYPE_DIRECTIONAL; l.LightColor = {1.5f, 1.4f, 1.2f};
+            TbFloat3 d = normalize3({-0.3f, -0.8f, 0.5f}); l.Direction = d;
+            s.lights.push_back(l);
+        }
+        TbFloat3 eye = {20.0f, 40.0f, -230.0f}, target = {0, 20.0f, 0};
+        TbFloat3 view = normalize3(sub3(target, eye));
+        TbFloat3 right = normalize3(cross3({0, 1, 0}, view));
+        TbFloat3 up = cross3(view, right);
+        s.camera.LensHeight = 2.0f;
+        s.camera.FocalDistance = 1.0f / 0.36397f;
+        float fd = s.camera.FocalDistance + 0.01f;
+        s.camera.Position = {eye.x + fd * view.x, eye.y + fd * view.y, eye.z + fd * view.z};
+        s.camera.LookAt = {s.camera.Position.x + view.x, s.camera.Position.y + view.y, s.camera.Position.z + view.z};
+        s.camera.Right = right;
+        s.camera.Up = up;
+        return true;
+    }
     if (name == "furnace") {
         // One convex matte sphere of albedo a under a constant white sky, no lights. Known answer
         // with MaxBounces = 2: every pixel that hits the sphere resolves to a (throughput =
