@@ -312,3 +312,23 @@ def test_sample_sharding_sums_to_single_gpu(cornell):
     want = g.Readback(tb.BufferKind.ACCUM_RGBW)
     assert np.allclose(parts[0] + parts[1], want, rtol=1e-5, atol=1e-6)
     assert np.array_equal((parts[0] + parts[1])[..., 3], want[..., 3])
+
+
+def test_converged_image_rmse(cornell):
+    """North star: converged-image RMSE against a 4096-spp reference. The 4096-spp reference is the
+    same estimator (GPU == oracle bit for bit, asserted elsewhere), so this checks convergence: the
+    error of an N-spp image falls like 1/sqrt(N) and 256 spp is within the stated bound."""
+    import tracerboy_b200 as tb
+    s = tb.get_default_output_settings(); s.MaxBounces = 4
+    g = tb.TracerBoy(0); g.LoadScene(cornell); g.Resize(128, 128)
+    g.Render(s, 4096, 0.0)
+    ref = g.Readback(tb.BufferKind.RESOLVED_RGB).astype(np.float64)
+    errs = {}
+    for spp in (16, 64, 256):
+        g.InvalidateHistory()
+        g.Render(s, spp, 0.0)
+        img = g.Readback(tb.BufferKind.RESOLVED_RGB).astype(np.float64)
+        errs[spp] = np.sqrt(np.mean((np.minimum(img, 4.0) - np.minimum(ref, 4.0)) ** 2))  # clamp the emitter pixels
+    assert errs[256] < errs[64] < errs[16]
+    assert errs[256] < 0.03, errs                      # RMSE bound at 256 spp (radiance units, light clamped to 4)
+    assert 1.4 < errs[16] / errs[64] < 2.8, errs       # ~ 1/sqrt(N)

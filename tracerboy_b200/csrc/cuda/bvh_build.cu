@@ -9,8 +9,8 @@
 // Pipeline (one stream, no host sync inside):
 //   load_prims      BottomLevelLoadTriangles.hlsli:88-126 + scene AABB (CalculateSceneAABB*.hlsl)
 //   morton          CalculateMortonCodesBindings.h:117-162 (30 bit, y,x,z interleave)
-//   radix sort      replaces the O(N log^2 N) bitonic sort (BitonicSort.cpp:67-143); a stable
-//                   LSD radix sort of (code, index) gives the same order as the reference's
+//   radix sort      hand-written stable LSD radix sort (4 x 8 bit) in place of the O(N log^2 N) bitonic
+//                   sort (BitonicSort.cpp:67-143); stability reproduces the reference's
 //                   tie-break-by-index compare (BitonicSortCommon.hlsli:37-47)
 //   rearrange       RearrangeTriangles.hlsl:29-36
 //   karras          BuildBVHSplits.hlsli:34-141
@@ -24,7 +24,6 @@
 // (swap iff leftCount > rightCount), and treelet climbing is not capped at 33 levels.
 #include <cfloat>
 #include <cstdio>
-#include <cub/device/device_radix_sort.cuh>
 #include "../common/tb_vec.h"
 #include "device_types.h"
 #include "launch.h"
@@ -122,6 +121,101 @@ __global__ void k_rearrange(const Prim* __restrict__ prims, const Meta* __restri
 #pragma unroll
     for (int k = 0; k < 10; k++) dst[k] = src[k];
     outMeta[i] = meta[s];
+}
+
+// --------------------------------------------------------------- radix sort
+// Stable LSD radix sort of (morton code, primitive index) pairs, 8 bits per pass, 4 passes over the
+// 30-bit codes. Replaces the reference's bitonic sort (BitonicSort.cpp:67-143, O(N log^2 N) passes over
+// global memory); stability gives the same order as its tie-break-by-index compare
+// (BitonicSortCommon.hlsli:37-47). Three kernels per pass: per-block digit histograms, one exclusive
+// scan over (digit, block), and an order-preserving scatter that ranks items with warp match/ballot.
+#define RS_THREADS 256
+#define RS_ITEMS 16
+#define RS_TILE (RS_THREADS * RS_ITEMS)
+
+__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t numBlocks,
+                                                           uint32_t* __restrict__ hist /* [256][numBlocks] */) {
+    __shared__ uint32_t sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t base = blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int c = 0; c < RS_ITEMS; c++) {
+        uint32_t i = base + c * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&sh[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[threadIdx.x * numBlocks + blockIdx.x] = sh[threadIdx.x];
+}
+
+// Exclusive scan of hist[256][numBlocks] in (digit, block) order, two small kernels: each block scans one
+// digit row (coalesced, running carry) and records the row total; then 256 row totals are scanned.
+__global__ void __launch_bounds__(256) k_radix_scan_rows(uint32_t* __restrict__ hist, uint32_t numBlocks, uint32_t* __restrict__ rowTotal) {
+    __shared__ uint32_t warpSum[8];
+    __shared__ uint32_t carry;
+    uint32_t* row = hist + (size_t)blockIdx.x * numBlocks;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < numBlocks; base += 256) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < numBlocks ? row[i] : 0u;
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += t; }
+        if (lane == 31) warpSum[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+        for (uint32_t w = 0; w < warp; w++) before += warpSum[w];
+        uint32_t c = carry;
+        if (i < numBlocks) row[i] = c + before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = c + before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) rowTotal[blockIdx.x] = carry;
+}
+__global__ void __launch_bounds__(256) k_radix_scan_digits(uint32_t* __restrict__ rowTotal) {
+    __shared__ uint32_t sh[256];
+    sh[threadIdx.x] = rowTotal[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t run = 0; for (int d = 0; d < 256; d++) { uint32_t t = sh[d]; sh[d] = run; run += t; } }
+    __syncthreads();
+    rowTotal[threadIdx.x] = sh[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn, uint32_t n,
+                                                              int shift, uint32_t numBlocks, const uint32_t* __restrict__ offsets /* row-scanned hist */,
+                                                              const uint32_t* __restrict__ digitStart, uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut) {
+    __shared__ uint32_t digitBase[256];                 // global position of the next item of each digit from this block
+    __shared__ uint32_t warpCount[RS_THREADS / 32][256]; // per chunk: items of each digit in each warp, then exclusive prefix over warps
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    digitBase[threadIdx.x] = digitStart[threadIdx.x] + offsets[(size_t)threadIdx.x * numBlocks + blockIdx.x];
+    const uint32_t base = blockIdx.x * RS_TILE;
+    for (int c = 0; c < RS_ITEMS; c++) {
+        for (int w = 0; w < RS_THREADS / 32; w++) warpCount[w][threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t i = base + c * RS_THREADS + threadIdx.x;
+        bool valid = i < n;
+        uint32_t key = valid ? keysIn[i] : 0u, val = valid ? valsIn[i] : 0u;
+        uint32_t digit = valid ? ((key >> shift) & 255u) : 256u; // invalid items form their own group
+        uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank == 0) warpCount[warp][digit] = __popc(peers);
+        __syncthreads();
+        { // thread d: exclusive prefix over the warps for digit d, then advance the block's base
+            uint32_t run = 0;
+            for (int w = 0; w < RS_THREADS / 32; w++) { uint32_t t = warpCount[w][threadIdx.x]; warpCount[w][threadIdx.x] = run; run += t; }
+            __syncthreads();
+            if (valid) {
+                uint32_t pos = digitBase[digit] + warpCount[warp][digit] + rank;
+                keysOut[pos] = key;
+                valsOut[pos] = val;
+            }
+            __syncthreads();
+            digitBase[threadIdx.x] += run;
+        }
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------- Karras
@@ -236,7 +330,7 @@ __constant__ uint8_t c_masksBySize[128];
 __constant__ uint8_t c_sizeStart[9];
 
 // TreeletReorder.hlsl:38-312 — one warp per base treelet root, climbing to the BVH root.
-__global__ void __launch_bounds__(128) k_treelet_reorder(uint32_t n, HNode* H, float* aabb, uint32_t* numTris,
+__global__ void __launch_bounds__(128, 5) k_treelet_reorder(uint32_t n, HNode* H, float* aabb, uint32_t* numTris,
                                                          const uint32_t* baseCount, const uint32_t* baseRoots) {
     const uint32_t warpsPerBlock = blockDim.x / 32;
     const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x & 31;
@@ -478,7 +572,7 @@ cudaError_t build_bvh(const TbGeometryRecord* d_geoms, const uint32_t* d_triPref
     cudaError_t err;
 #define CK(x) do { err = (x); if (err != cudaSuccess) return err; } while (0)
     Prim* prims; Meta* meta; uint32_t *codes, *order, *codesAlt, *orderAlt, *sceneBox, *numTris, *baseCount, *baseRoots;
-    HNode* H; float* aabb; void* cubTemp = nullptr; size_t cubBytes = 0;
+    HNode* H; float* aabb; 
     CK(cudaMallocAsync(&prims, sizeof(Prim) * (size_t)n, stream));
     CK(cudaMallocAsync(&meta, sizeof(Meta) * (size_t)n, stream));
     CK(cudaMallocAsync(&codes, 4 * (size_t)n, stream));
@@ -491,21 +585,30 @@ cudaError_t build_bvh(const TbGeometryRecord* d_geoms, const uint32_t* d_triPref
     CK(cudaMallocAsync(&baseRoots, 4 * (size_t)(n / 7 + 1), stream));
     CK(cudaMallocAsync(&H, sizeof(HNode) * (size_t)total, stream));
     CK(cudaMallocAsync(&aabb, 24 * (size_t)total, stream));
-    cub::DoubleBuffer<uint32_t> dk(codes, codesAlt), dv(order, orderAlt);
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, cubBytes, dk, dv, (int)n, 0, 30, stream));
-    CK(cudaMallocAsync(&cubTemp, cubBytes, stream));
+    const uint32_t sortBlocks = (n + RS_TILE - 1) / RS_TILE;
+    uint32_t* radixHist;
+    CK(cudaMallocAsync(&radixHist, 4 * 256 * ((size_t)sortBlocks + 1), stream));
+    uint32_t* radixDigitStart = radixHist + 256 * (size_t)sortBlocks;
 
     uint32_t boxInit[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     CK(cudaMemcpyAsync(sceneBox, boxInit, sizeof(boxInit), cudaMemcpyHostToDevice, stream));
     k_load_prims<<<grid(n), T, 0, stream>>>(d_geoms, d_triPrefix, numGeoms, d_positions, d_indices, n, prims, meta, sceneBox); lc.count++;
     k_morton<<<grid(n), T, 0, stream>>>(prims, n, sceneBox, codes, order); lc.count++;
-    CK(cub::DeviceRadixSort::SortPairs(cubTemp, cubBytes, dk, dv, (int)n, 0, 30, stream));
+    uint32_t *kIn = codes, *vIn = order, *kOut = codesAlt, *vOut = orderAlt;
+    for (int shift = 0; shift < 30; shift += 8) {
+        k_radix_hist<<<sortBlocks, RS_THREADS, 0, stream>>>(kIn, n, shift, sortBlocks, radixHist); lc.count++;
+        k_radix_scan_rows<<<256, 256, 0, stream>>>(radixHist, sortBlocks, radixDigitStart); lc.count++;
+        k_radix_scan_digits<<<1, 256, 0, stream>>>(radixDigitStart); lc.count++;
+        k_radix_scatter<<<sortBlocks, RS_THREADS, 0, stream>>>(kIn, vIn, n, shift, sortBlocks, radixHist, radixDigitStart, kOut, vOut); lc.count++;
+        uint32_t* t = kIn; kIn = kOut; kOut = t; t = vIn; vIn = vOut; vOut = t;
+    }
+    const uint32_t* sortedCodes = kIn; const uint32_t* sortedOrder = vIn;
     uint8_t* bvh = out.ref;
     Prim* sortedPrims = (Prim*)(bvh + 16 + 32 * (size_t)total);
     Meta* sortedMeta = (Meta*)(bvh + 16 + 32 * (size_t)total + 40 * (size_t)n);
-    k_rearrange<<<grid(n), T, 0, stream>>>(prims, meta, dv.Current(), n, sortedPrims, sortedMeta); lc.count++;
+    k_rearrange<<<grid(n), T, 0, stream>>>(prims, meta, sortedOrder, n, sortedPrims, sortedMeta); lc.count++;
     if (n > 1) {
-        k_karras<<<grid(nInternal), T, 0, stream>>>(dk.Current(), n, H); lc.count++;
+        k_karras<<<grid(nInternal), T, 0, stream>>>(sortedCodes, n, H); lc.count++;
         uint32_t minTris = 7;
         for (int pass = 0; pass < treeletPasses; pass++) {
             if (minTris > n) break;
@@ -513,7 +616,7 @@ cudaError_t build_bvh(const TbGeometryRecord* d_geoms, const uint32_t* d_triPref
             k_find_treelets<<<grid(n), T, 0, stream>>>(sortedPrims, n, minTris, H, aabb, numTris, baseCount, baseRoots); lc.count++;
             uint32_t maxRoots = n / minTris + 1;
             uint32_t blocks = (maxRoots + 3) / 4;
-            if (blocks > 148 * 16) blocks = 148 * 16;
+            if (blocks > 148 * 32) blocks = 148 * 32;
             k_treelet_reorder<<<blocks, 128, 0, stream>>>(n, H, aabb, numTris, baseCount, baseRoots); lc.count++;
             minTris *= 2;
         }
@@ -526,7 +629,7 @@ cudaError_t build_bvh(const TbGeometryRecord* d_geoms, const uint32_t* d_triPref
     cudaFreeAsync(prims, stream); cudaFreeAsync(meta, stream); cudaFreeAsync(codes, stream); cudaFreeAsync(order, stream);
     cudaFreeAsync(codesAlt, stream); cudaFreeAsync(orderAlt, stream); cudaFreeAsync(sceneBox, stream); cudaFreeAsync(numTris, stream);
     cudaFreeAsync(baseCount, stream); cudaFreeAsync(baseRoots, stream); cudaFreeAsync(H, stream); cudaFreeAsync(aabb, stream);
-    cudaFreeAsync(cubTemp, stream);
+    cudaFreeAsync(radixHist, stream);
     CK(cudaStreamSynchronize(stream));
     out.numPrims = n;
 #undef CK
