@@ -652,9 +652,12 @@ __device__ __forceinline__ void finish_path(const FrameConstants& fc, PathState&
 //          joins the shadow queue and is NOT advanced (no state is written for it).
 // STAGE 1: the paths of the shadow queue, after k_extend<SHADOW> has traced their rays: the same
 //          code from the top (same inputs, same rand() draws), now with the occluder known.
-// STAGE 2: single stage with the shadow ray traced inline (frames without next-event estimation
-//          never reach that code; kept for tb_set_shadow_mode(0) A/B measurements).
-template <int STAGE>
+// STAGE 2: single stage with the shadow ray traced inline (small scenes, tb_set_shadow_mode(0)).
+// STAGE 3: single stage for frames that cannot cast shadow rays (no lights, or NEE off).
+// SSS:     the scene has subsurface / glass materials, whose random walk traces rays inline. Scenes
+//          without them (checked on the host) get a kernel with no traversal code at all in stages
+//          0, 1 and 3: fewer registers, no local-memory stack.
+template <int STAGE, bool SSS>
 __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, DeviceScene sc, FrameConstants fc, PathState st, int qi) {
     const uint32_t count = STAGE == 1 ? st.queueCount[4] : st.queueCount[6 + 2 * qi];
     const uint32_t* __restrict__ inQueue = STAGE == 1 ? st.shadowQueue : st.hitQueue;
@@ -731,10 +734,10 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, 
                 if (bPrevSpec || bFirstRay || !IsLight(material) || !S.EnableNextEventEstimation) acc += thr * material.emissive;
                 if (IsLight(material)) { terminated = true; break; }
 
-                float lightPDF, lightAttenuation;
-                f3 lightDirection, lightColor, lightNormal;
-                get_one_light_sample(sc, fc, rng, RayPoint, lightDirection, lightColor, lightPDF, lightNormal, lightAttenuation);
-                if (!bPerfectSpec && lightPDF > EPSILON && dot(lightDirection, lightNormal) < 0.0f) {
+                float lightPDF = 0.0f, lightAttenuation = 0.0f;
+                f3 lightDirection = mk3(0.0f), lightColor = mk3(0.0f), lightNormal = mk3(0.0f);
+                if (STAGE != 3) get_one_light_sample(sc, fc, rng, RayPoint, lightDirection, lightColor, lightPDF, lightNormal, lightAttenuation);
+                if (STAGE != 3 && !bPerfectSpec && lightPDF > EPSILON && dot(lightDirection, lightNormal) < 0.0f) {
                     f3 ShadowMultiplier = mk3(1.0f);
                     Surface ss; float stt;
                     bool occluded;
@@ -748,9 +751,9 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, 
                         float4 sh = st.shHit[pi];
                         occluded = sh.x >= 0.0f;
                         if (occluded) ss = surface_from_hit(sc, sh.y, sh.z, st.shHitGeom[pi], __float_as_uint(sh.w));
-                    } else {
+                    } else if (STAGE == 2) {
                         occluded = intersect_inline(bvh, sc, RayPoint + normal * EPSILON, lightDirection, rc, ss, stt);
-                    }
+                    } else occluded = false;
                     if (occluded) {
                         bool shBack = dot(ss.normal, lightDirection) > 0.0f;
                         Mat sm = get_material(sc, rng, ss.material, ss.uv, shBack);
@@ -774,7 +777,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, 
                     f3 dd = mk3(sin_(phi) * cos_(theta), cos_(phi), sin_(phi) * sin_(theta));
                     f3 hh = reorient_around_normal(dd, normal);
                     dir = reflect(dir, hh);
-                } else if (IsSSS(material)) {
+                } else if (SSS && IsSSS(material)) {
                     float nr = CurrentIOR / NewIOR;
                     if (refract_or_reflect(rng, dir, normal, nr, RdotN, bPerfectSpec, material.roughness, bPrevSpec) == GIVE_UP) { terminated = true; break; }
                     bool noScatter = material.scattering.x < EPSILON;
@@ -1018,13 +1021,19 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
         // part of the bounce before the shadow ray, which only pays off when traversal is expensive
         // (measured: 874 k triangles +9 %, 36 triangles -26 %)
         const int shadowMode = opts.shadowMode == 2 ? (bvh.numPrims >= 32768u ? 1 : 0) : opts.shadowMode;
+        const bool sss = opts.sceneHasSSS;
+#define TB_LAUNCH_SHADE(STG) do { if (sss) k_shade<STG, true><<<blocks, 128, 0, stream>>>(bvh, sc, fc, st, qi); \
+                                  else k_shade<STG, false><<<blocks, 128, 0, stream>>>(bvh, sc, fc, st, qi); lc.count++; } while (0)
         if (nee && shadowMode) {
-            k_shade<0><<<blocks, 128, 0, stream>>>(bvh, sc, fc, st, qi); lc.count++;
+            TB_LAUNCH_SHADE(0);
             k_extend<true><<<blocks, 128, 0, stream>>>(bvh, st, qi, 0, 0, fc.aovMask, 0xffffffffu); lc.count++;
-            k_shade<1><<<blocks, 128, 0, stream>>>(bvh, sc, fc, st, qi); lc.count++;
+            TB_LAUNCH_SHADE(1);
+        } else if (nee) {
+            TB_LAUNCH_SHADE(2);
         } else {
-            k_shade<2><<<blocks, 128, 0, stream>>>(bvh, sc, fc, st, qi); lc.count++;
+            TB_LAUNCH_SHADE(3);
         }
+#undef TB_LAUNCH_SHADE
         if (timers) cudaEventRecord(timers->next(KernelTimers::END), stream);
     }
     return cudaGetLastError();

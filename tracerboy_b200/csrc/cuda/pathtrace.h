@@ -81,6 +81,7 @@ struct KernelTimers {
 // scheduling knobs; none of them changes a result
 struct RenderOptions {
     int shadowMode = 2; // next-event shadow rays: 0 traced inline in k_shade, 1 own wavefront stage, 2 automatic
+    bool sceneHasSSS = true; // any material with the subsurface flag (selects the k_shade variant with the inline random walk)
 };
 
 uint64_t bvh_ref_bytes(uint32_t numPrims);

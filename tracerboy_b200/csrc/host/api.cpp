@@ -184,6 +184,8 @@ static int upload_and_build(TbHandle* h, uint32_t flags) {
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->bvhBuildMs = ms;
     h->camera = s.camera;
+    h->options.sceneHasSSS = false;
+    for (const TbMaterial& m : s.materials) if (m.Flags & TB_SUBSURFACE_SCATTER_MATERIAL_FLAG) h->options.sceneHasSSS = true;
     h->sceneLoaded = true;
     h->samplesRendered = 0;
     set_status(h, TB_LOAD_FINISHED, (uint32_t)s.geoms.size(), (uint32_t)s.geoms.size());
@@ -631,6 +633,7 @@ TB_API int tb_set_material(TbHandle* h, int id, const TbMaterial* m) {
     if (!h || !m) return fail(h, TB_ERR_INVALID_ARG, "null argument");
     if (!tb_is_material_id_valid(h, id)) return fail(h, TB_ERR_INVALID_ARG, "invalid material id");
     h->scene.materials[id] = *m;
+    if (m->Flags & TB_SUBSURFACE_SCATTER_MATERIAL_FLAG) h->options.sceneHasSSS = true;
     CUDA_OK(h, cudaSetDevice(h->device));
     CUDA_OK(h, cudaMemcpyAsync((void*)(h->dscene.materials + id), m, sizeof(*m), cudaMemcpyHostToDevice, h->stream));
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
