@@ -36,6 +36,12 @@ __device__ __forceinline__ bool slab(float& resultT, float closestT, tbm::f3 oin
     return fmaxf(minT, 0.0f) < fminf(maxT, closestT);
 }
 
+// 256-bit read-only global load (32-byte aligned)
+__device__ __forceinline__ void ldg256(const float4* __restrict__ p, float4& lo, float4& hi) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "l"(p));
+}
+
 // D6: slab test for a ray with exactly-zero direction components: those axes constrain nothing in t
 // and are tested by containment |c - o| <= h + 1e-5 (|c| + h).
 __device__ __forceinline__ bool zero_axis_inside(float c, float h, float o) {
@@ -149,8 +155,11 @@ struct Traversal {
     __device__ __forceinline__ void step_internal(uint32_t* stack, const float4* __restrict__ pairs) {
         using namespace tbm;
         uint32_t ref = cur;
-        float4 a = __ldg(pairs + 4 * (size_t)ref), b = __ldg(pairs + 4 * (size_t)ref + 1);
-        float4 c = __ldg(pairs + 4 * (size_t)ref + 2), d = __ldg(pairs + 4 * (size_t)ref + 3);
+        // one 64-byte node = two 256-bit loads (LDG.E.256, sm_100): the kernel is bound by L1 wavefronts
+        // (one per lane per load instruction for scattered nodes), so halving the load count matters
+        float4 a, b, c, d;
+        ldg256(pairs + 4 * (size_t)ref, a, b);
+        ldg256(pairs + 4 * (size_t)ref + 2, c, d);
         f3 ainv = abs3(inv);
         float lt, rt;
         bool lh, rh;

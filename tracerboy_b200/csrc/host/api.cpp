@@ -184,8 +184,15 @@ static int upload_and_build(TbHandle* h, uint32_t flags) {
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->bvhBuildMs = ms;
     h->camera = s.camera;
+    // subsurface / glass materials reachable from the geometry (directly or through a mix material)
     h->options.sceneHasSSS = false;
-    for (const TbMaterial& m : s.materials) if (m.Flags & TB_SUBSURFACE_SCATTER_MATERIAL_FLAG) h->options.sceneHasSSS = true;
+    for (const TbGeometryRecord& g : s.geoms) {
+        const TbMaterial& m = s.materials[g.MaterialIndex];
+        uint32_t ids[3] = {g.MaterialIndex, g.MaterialIndex, g.MaterialIndex};
+        if (m.Flags & TB_MIX_MATERIAL_FLAG) { ids[1] = (uint32_t)m.albedo.x; ids[2] = (uint32_t)m.albedo.y; }
+        for (uint32_t id : ids)
+            if (id < s.materials.size() && (s.materials[id].Flags & TB_SUBSURFACE_SCATTER_MATERIAL_FLAG)) h->options.sceneHasSSS = true;
+    }
     h->sceneLoaded = true;
     h->samplesRendered = 0;
     set_status(h, TB_LOAD_FINISHED, (uint32_t)s.geoms.size(), (uint32_t)s.geoms.size());
