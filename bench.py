@@ -182,6 +182,9 @@ def main():
     ap.add_argument("--ref-spp", type=int, default=2, help="CPU sample size per step for --impl reference")
     ap.add_argument("--cpu-baseline-spp", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="samples", choices=["samples", "rows"],
+                    help="N>1: 'samples' = frame f on rank f mod N (weak scaling, default); 'rows' = interleaved bands of 8 rows, "
+                         "every rank renders all frames of its bands (strong scaling, bit-identical to one GPU)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -211,7 +214,10 @@ def main():
     g = tb.TracerBoy(local_rank)
     g.LoadScene(scene_arg(spec))
     g.Resize(w, h)
-    g.SetFrameShard(rank, world)  # frame f rendered on rank f mod N
+    if args.shard == "rows":
+        g.SetRowShard(rank, world)    # bands of 8 rows, band b on rank b mod N
+    else:
+        g.SetFrameShard(rank, world)  # frame f rendered on rank f mod N
     load_s = time.time() - t_load
     s = tb.get_default_output_settings()
     s.MaxBounces = bounces
@@ -358,13 +364,15 @@ def main():
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": 1e3 * t_step / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic camera/seeds on the bundled scene",
+            "scaling": "strong" if (args.shard == "rows" and world > 1) else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic camera/seeds on the bundled scene",
             "config": {"workload": "%s %dx%d, %d spp per step per GPU, %d bounces, NEE on, blue noise on, Time=0" % (
                            args.workload, w, h, spp, bounces),
-                       "triangles": info.NumTriangles, "sharding": "frame f on rank f mod N; all-reduce of the accumulation buffer per step",
+                       "triangles": info.NumTriangles, "sharding": ("bands of 8 rows, band b on rank b mod N" if args.shard == "rows" else "frame f on rank f mod N") +
+                                   "; all-reduce of the accumulation buffer per step",
                        "l2": "inputs exceed L2: %d MB of path state + accumulation buffers are rewritten every sample" % (
                            (w * h * 16 * 14) >> 20)},
-            "samples_per_s": world * w * h * spp * args.steps / t_step,
+            "samples_per_s": (1 if args.shard == "rows" else world) * w * h * spp * args.steps / t_step,
             "rays_per_step": rays_total / args.steps,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(host_in.numel()),
                     "d2h_bytes_per_step": int(host_img.numel() * 4), "ms_per_step": 1e3 * wall_e / args.steps},

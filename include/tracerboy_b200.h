@@ -339,6 +339,10 @@ TB_API int tb_invalidate_history(TbHandle* h);
 /* Sample-index sharding for multi-GPU: this handle renders only
  * frames f with f % stride == offset. Default (0, 1). */
 TB_API int tb_set_frame_shard(TbHandle* h, uint32_t offset, uint32_t stride);
+/* Row-band sharding for multi-GPU (partitioning 1): the image is cut into bands of 8 rows
+ * and this handle renders band b iff b % stride == offset; all other pixels stay zero in every buffer,
+ * so the sum (or gather) of the shards' buffers is bit-identical to the single-GPU result. Default (0, 1). */
+TB_API int tb_set_row_shard(TbHandle* h, uint32_t offset, uint32_t stride);
 TB_API int tb_buffer_size(TbHandle* h, uint32_t kind, uint64_t* bytes);
 TB_API int tb_readback(TbHandle* h, uint32_t kind, void* dst, uint64_t bytes);
 /* Device pointer of the float4 accumulation buffer (for the NCCL reduce; the

@@ -138,7 +138,7 @@ def load_library():
         "tb_set_camera": [vp, C.POINTER(Camera)], "tb_resize": [vp, u32, u32], "tb_select_pixel": [vp, i32, i32],
         "tb_get_stats": [vp, C.POINTER(ReadbackStats)],
         "tb_render": [vp, C.POINTER(OutputSettings), u32, C.c_float], "tb_samples_rendered": [vp, C.POINTER(u32)],
-        "tb_invalidate_history": [vp], "tb_set_frame_shard": [vp, u32, u32], "tb_buffer_size": [vp, u32, C.POINTER(u64)],
+        "tb_invalidate_history": [vp], "tb_set_frame_shard": [vp, u32, u32], "tb_set_row_shard": [vp, u32, u32], "tb_buffer_size": [vp, u32, C.POINTER(u64)],
         "tb_readback": [vp, u32, vp, u64], "tb_device_buffer": [vp, u32, C.POINTER(vp), C.POINTER(u64)],
         "tb_get_render_stats": [vp, C.POINTER(RenderStats)], "tb_reset_render_stats": [vp], "tb_synchronize": [vp], "tb_set_profiling": [vp, i32], "tb_set_frames_in_flight": [vp, u32], "tb_set_shadow_mode": [vp, i32],
         "tb_is_material_id_valid": [vp, i32], "tb_get_material": [vp, i32, C.POINTER(Material), C.c_char_p, u32],
@@ -158,7 +158,7 @@ EXPORTED_SYMBOLS = ["tb_create", "tb_destroy", "tb_last_error", "tb_version", "t
                     "tb_get_load_status", "tb_save_scene", "tb_convert_scene", "tb_get_scene_info", "tb_get_bvh_size",
                     "tb_get_bvh", "tb_get_bvh_build_ms", "tb_get_default_settings", "tb_get_camera", "tb_set_camera",
                     "tb_resize", "tb_select_pixel", "tb_get_stats", "tb_render", "tb_samples_rendered",
-                    "tb_invalidate_history", "tb_set_frame_shard", "tb_buffer_size", "tb_readback", "tb_device_buffer",
+                    "tb_invalidate_history", "tb_set_frame_shard", "tb_set_row_shard", "tb_buffer_size", "tb_readback", "tb_device_buffer",
                     "tb_get_render_stats", "tb_reset_render_stats", "tb_set_profiling", "tb_set_frames_in_flight", "tb_set_shadow_mode", "tb_synchronize", "tb_is_material_id_valid",
                     "tb_get_material", "tb_set_material", "tb_bvh_prebuild_info", "tb_bvh_build", "tb_trace_rays"]
 
@@ -313,6 +313,9 @@ class TracerBoy:
 
     def SetFrameShard(self, offset, stride):
         self._ck(self._lib.tb_set_frame_shard(self._h, offset, stride))
+
+    def SetRowShard(self, offset, stride):
+        self._ck(self._lib.tb_set_row_shard(self._h, offset, stride))
 
     def Readback(self, kind, out=None):
         dt, ch = BufferKind._shape[kind]

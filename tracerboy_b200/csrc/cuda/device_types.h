@@ -62,6 +62,7 @@ struct FrameConstants {
     uint32_t width, height;
     int32_t selectedX, selectedY;
     float halton2, halton3; // Halton23(frame), RayGenCommon.h:79-82 (per-frame constant)
+    uint32_t rowOffset, rowStride; // row-band shard: bands of 8 rows, band b is rendered iff b % rowStride == rowOffset
     uint32_t aovMask;       // AOV_FULL / AOV_WORLDPOS ownership of this frame (frames run concurrently)
     uint32_t clearAccum;    // 1 on the first frame this handle renders after an invalidate. Equals
                             // (GlobalFrameCount == 0) on one GPU; differs only under sample sharding.

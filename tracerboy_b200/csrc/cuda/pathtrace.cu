@@ -382,12 +382,22 @@ __device__ __forceinline__ uint32_t pack_state(int bounce, bool prevSpec) { retu
 __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, FrameConstants fc, PathState st) {
     uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n = fc.width * fc.height;
-    if (pi == 0) {
-        st.queueCount[0] = n; st.queueCount[1] = 0; st.queueCount[2] = 0; st.queueCount[3] = 0; st.queueCount[4] = 0; st.queueCount[5] = 0;
-        for (int r = 6; r < 10; r++) st.queueCount[r] = 0;
-        for (int r = 0; r < 4; r++) st.susCount[r] = 0;
+    // (all queue / suspension counters were zeroed by the memset node in front of this kernel)
+    // row-band sharding (partitioning 1): bands of 8 rows, band b belongs to the shard b % stride
+    const bool owned = pi < n && ((pi / fc.width) / 8u) % fc.rowStride == fc.rowOffset;
+    if (fc.rowStride == 1) { // every pixel: the first queue is the identity
+        if (pi == 0) st.queueCount[0] = n;
+        if (pi < n) st.queue[0][pi] = pi;
+    } else {
+        uint32_t m = __ballot_sync(0xffffffffu, owned);
+        if (m) {
+            uint32_t lane = threadIdx.x & 31, base = 0;
+            if (lane == 0) base = atomicAdd(&st.queueCount[0], (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (owned) st.queue[0][base + __popc(m & ((1u << lane) - 1u))] = pi;
+        }
     }
-    if (pi >= n) return;
+    if (!owned) return;
     uint32_t px = pi % fc.width, py = pi / fc.width;
     Rng rng;
     rng.time = fc.time;
@@ -433,7 +443,6 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, FrameConstants f
     st.col[pi] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     st.neighbor[pi] = make_float4(focalPoint.x, focalPoint.y, focalPoint.z, 0.0f);
     st.neighborDir[pi] = make_float4(ndir.x, ndir.y, ndir.z, 0.0f);
-    st.queue[0][pi] = pi;
     // ClearAOVs (RayGenCommon.h:650-654) + zeroed world-position accumulators (:693-694)
     if (fc.aovMask & AOV_FULL) {
         st.aovAlbedo[pi] = make_float4(0, 0, 0, 1.0f);
@@ -935,6 +944,7 @@ __global__ void __launch_bounds__(256) k_shade_miss(DeviceScene sc, FrameConstan
 __global__ void __launch_bounds__(256) k_accumulate(FrameConstants fc, PathState st) {
     uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
     if (pi >= fc.width * fc.height) return;
+    if (((pi / fc.width) / 8u) % fc.rowStride != fc.rowOffset) return; // not this shard's row band
     float4 outc = st.sample[pi];
     Rng rng; rng.seed = st.sampleSeed[pi]; rng.time = fc.time;
     bool realtime = fc.settings.RenderMode == TB_RENDER_REALTIME;
@@ -985,6 +995,8 @@ static int num_sms() {
 cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const FrameConstants& fc, PathState& st,
                          cudaStream_t stream, LaunchCounter& lc, KernelTimers* timers, const RenderOptions& opts) {
     const uint32_t n = fc.width * fc.height;
+    cudaMemsetAsync(st.queueCount, 0, 64, stream);
+    cudaMemsetAsync(st.susCount, 0, 16, stream);
     k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(sc, fc, st); lc.count++;
     // persistent grids: a multiple of the SM count, capped by the work available
     const uint32_t sms = (uint32_t)num_sms();

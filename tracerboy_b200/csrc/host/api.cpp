@@ -44,6 +44,7 @@ struct TbHandle {
     TbCamera camera{};
     uint32_t samplesRendered = 0; // local samples since the last invalidate
     uint32_t shardOffset = 0, shardStride = 1;
+    uint32_t rowOffset = 0, rowStride = 1;
     int selX = -1, selY = -1;
     LaunchCounter lc;
     double deviceMs = 0.0;
@@ -473,6 +474,7 @@ TB_API int tb_render(TbHandle* h, const TbOutputSettings* s, uint32_t nSamples, 
         fc.halton2 = halton(2, (int)fc.frame);
         fc.halton3 = halton(3, (int)fc.frame);
         fc.clearAccum = h->samplesRendered == 0;
+        fc.rowOffset = h->rowOffset; fc.rowStride = h->rowStride;
         const bool last = serial || i + 1 == todo;
         fc.aovMask = last ? 3u : (i + 2 == todo ? 2u : 0u);
         TbHandle::Slot& sl = h->slots[serial ? 0 : h->framesIssued % h->slots.size()];
@@ -515,6 +517,20 @@ TB_API int tb_set_frame_shard(TbHandle* h, uint32_t offset, uint32_t stride) {
     if (!h || stride == 0 || offset >= stride) return fail(h, TB_ERR_INVALID_ARG, "need offset < stride");
     h->shardOffset = offset; h->shardStride = stride;
     h->samplesRendered = 0;
+    return TB_OK;
+}
+
+TB_API int tb_set_row_shard(TbHandle* h, uint32_t offset, uint32_t stride) {
+    if (!h || stride == 0 || offset >= stride) return fail(h, TB_ERR_INVALID_ARG, "need offset < stride");
+    h->rowOffset = offset; h->rowStride = stride;
+    h->samplesRendered = 0;
+    if (h->width) { // pixels of other shards must read as zero
+        CUDA_OK(h, cudaSetDevice(h->device));
+        size_t n = (size_t)h->width * h->height;
+        CUDA_OK(h, cudaMemsetAsync(h->st.accum, 0, 16 * n, h->stream));
+        CUDA_OK(h, cudaMemsetAsync(h->st.jittered, 0, 16 * n, h->stream));
+        CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    }
     return TB_OK;
 }
 
