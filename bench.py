@@ -36,6 +36,7 @@ WORKLOADS = {
     "teapot": ("teapot", 1920, 1080, 64, 6),
     "cornell": ("cornell-box", 512, 512, 16, 4),
     "dragon": ("synthetic:blobs?copies=1&tris=871000&seed=1", 1920, 1080, 256, 8),
+    "vwvan": ("vw-van", 3840, 2160, 128, 6),  # configs[3], variant scene (tracerboy_b200/build.py)
     "blobs20m": ("synthetic:blobs?copies=20000&tris=1000&seed=1", 1920, 1080, 1024, 6),
 }
 

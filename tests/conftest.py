@@ -51,6 +51,14 @@ def teapot(built):
     return p
 
 
+@pytest.fixture(scope="session")
+def vwvan(built):
+    p = scene_path("vw-van")
+    if not p:
+        pytest.skip("vw-van.tbscene not in scenes/_cache (needs the reference mount at build time)")
+    return p
+
+
 def has_cuda():
     try:
         import torch

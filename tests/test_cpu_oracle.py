@@ -13,6 +13,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import make_golden  # noqa: E402
 
 
+NAMED = {"cornell": "cornell-box", "teapot": "teapot", "vwvan": "vw-van"}  # bundled scenes (.tbscene caches)
+
+
 def _ulp_err(got, ref64):
     ref32 = ref64.astype(np.float32)
     ulp = np.abs(np.nextafter(np.abs(ref32), np.float32(np.inf)) - np.abs(ref32)).astype(np.float64)
@@ -145,13 +148,13 @@ def validate_bvh(b, positions=None, tri_index=None):
     return n
 
 
-@pytest.mark.parametrize("spec", ["cornell", "teapot", "synthetic:blobs?copies=8&tris=200&seed=2",
+@pytest.mark.parametrize("spec", ["cornell", "teapot", "vwvan", "synthetic:blobs?copies=8&tris=200&seed=2",
                                   "synthetic:blobs?copies=1&tris=5000&seed=9", "synthetic:furnace"])
 def test_oracle_bvh_invariants(spec, tmp_path, built):
     import tracerboy_b200 as tb
     from oracle.binding import Oracle
-    if spec in ("cornell", "teapot"):
-        path = scene_path("cornell-box" if spec == "cornell" else "teapot")
+    if spec in NAMED:
+        path = scene_path(NAMED[spec])
         if path is None:
             pytest.skip("scene cache missing")
     else:
@@ -164,7 +167,7 @@ def test_oracle_bvh_invariants(spec, tmp_path, built):
         assert n == o.NumTriangles()
         # the reference caps treelet climbing at 33 levels per thread group; below that our
         # uncapped rule is identical (deviation D2)
-        assert o.MaxTreeletClimb() <= 33 or spec == "teapot"
+        assert o.MaxTreeletClimb() <= 33 or spec in ("teapot", "vwvan")
         o.close()
 
 
@@ -253,6 +256,8 @@ REF_CASES = [
     ("cornell", 48, 48, 2, {"OutputType": 9}),
     ("synthetic:blobs?copies=27&tris=300&seed=3", 160, 90, 3, {"MaxBounces": 8}),
     ("teapot", 240, 135, 3, {}),
+    # BASELINE.json configs[3] (variant): glass x4, metal x2, mirror/substrate mix, uber, env lighting
+    ("vwvan", 160, 90, 2, {}),
     # every material / texture / light path: mix, specular map, scale + image textures (float and RGBA8 with
     # gamma), normal map, emissive texture, glass / rough glass / single-sided / artist-albedo SSS, mirror,
     # hair flag, area + directional light, transformed sky
@@ -270,8 +275,8 @@ def test_restated_core_equals_reference_core(spec, w, h, spp, over, tmp_path, bu
     from oracle import binding
     if not binding.reference_core_available():
         pytest.skip("oracle/_ref/libref_core.so not built (needs the reference mount at build time)")
-    if spec in ("cornell", "teapot"):
-        path = scene_path("cornell-box" if spec == "cornell" else "teapot")
+    if spec in NAMED:
+        path = scene_path(NAMED[spec])
         if path is None:
             pytest.skip("scene cache missing")
     else:
@@ -306,8 +311,8 @@ def test_zero_axis_rule_keeps_hits_and_radiance(spec, w, h, spp, tmp_path, built
     traversal counters only: radiance, primary-hit ids and ray counts are bit-identical."""
     import tracerboy_b200 as tb
     from oracle import binding
-    if spec in ("cornell", "teapot"):
-        path = scene_path("cornell-box" if spec == "cornell" else "teapot")
+    if spec in NAMED:
+        path = scene_path(NAMED[spec])
         if path is None:
             pytest.skip("scene cache missing")
     else:

@@ -128,6 +128,40 @@ def test_teapot_render_bit_exact(teapot):
     _compare_render(g, o, s, 2)
 
 
+def test_vwvan_render_bit_exact(vwvan):
+    """BASELINE.json configs[3] (variant, see build.py): 683 k triangles, glass x4 (refraction walk), metal,
+    mirror/substrate mix, uber; BVH bytes, every buffer and the traversal counters equal the oracle's."""
+    import tracerboy_b200 as tb
+    g, o = _pair(vwvan, 256, 144)
+    assert np.array_equal(g.GetBVH(), o.GetBVH())
+    s = tb.get_default_output_settings()
+    _compare_render(g, o, s, 2)
+    rays = _random_rays(100000, g.GetCamera(), 5)
+    hg, ho = g.TraceRays(rays), o.TraceRays(rays)
+    for f in hg.dtype.names:
+        assert (hg[f].view(np.uint32) == ho[f].view(np.uint32)).all(), f
+
+
+def test_full_size_properties_vwvan_4k(vwvan):
+    """configs[3] at its full 3840x2160: progressive accumulation is exact (3 + 5 == 8 samples), the weight
+    channel counts the samples, radiance is finite, and frames in flight do not change a bit."""
+    import tracerboy_b200 as tb
+    s = tb.get_default_output_settings()
+    g = tb.TracerBoy(0)
+    g.LoadScene(vwvan)
+    g.Resize(3840, 2160)
+    g.Render(s, 8, 0.0)
+    a = g.Readback(tb.BufferKind.ACCUM_RGBW).copy()
+    assert (a[..., 3] == 8.0).all() and np.isfinite(a).all() and (a[..., :3] >= 0).all()
+    g.InvalidateHistory()
+    g.Render(s, 3, 0.0)
+    g.Render(s, 5, 0.0)
+    assert np.array_equal(a.view(np.uint32), g.Readback(tb.BufferKind.ACCUM_RGBW).view(np.uint32))
+    g.SetFramesInFlight(1)
+    g.Render(s, 8, 0.0)
+    assert np.array_equal(a.view(np.uint32), g.Readback(tb.BufferKind.ACCUM_RGBW).view(np.uint32))
+
+
 @pytest.mark.parametrize("variant", ["no_blue_noise", "no_nee", "sir", "dof", "triangle", "gaussian", "firefly", "heatmap"])
 def test_settings_variants(variant, cornell):
     import tracerboy_b200 as tb

@@ -13,6 +13,7 @@ import os
 import shutil
 import subprocess
 import sys
+import tempfile
 from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -130,7 +131,29 @@ def build_oracle(force=False):
 BUNDLED_SCENES = {
     "cornell-box": "Scenes/cornell-box/scene.pbrt",
     "teapot": "Scenes/Teapot/scene.pbrt",
+    "vw-van": "variant:vw-van",
 }
+
+
+def _vw_van_variant(tmp):
+    """BASELINE.json configs[3]: the mount lacks geometry/mesh_00125.ply and the scene's only
+    light, textures/pisa_latlong.hdr. The variant is the reference's own vw-van.pbrt, read from the mount at
+    build time, minus the one Shape line that names the missing mesh, with Teapot's envmap.hdr standing in
+    for the missing lat-long map. Both back-ends render the same variant. Nothing is written into the repo
+    except the flattened scenes/_cache/vw-van.tbscene (git-ignored)."""
+    src = os.path.join(REF, "Scenes/vw-van")
+    env = os.path.join(REF, "Scenes/Teapot/textures/envmap.hdr")
+    if not os.path.exists(os.path.join(src, "vw-van.pbrt")) or not os.path.exists(env):
+        return None
+    os.makedirs(os.path.join(tmp, "textures"))
+    os.symlink(os.path.join(src, "geometry"), os.path.join(tmp, "geometry"))
+    os.symlink(env, os.path.join(tmp, "textures", "pisa_latlong.hdr"))
+    with open(os.path.join(src, "vw-van.pbrt")) as f:
+        lines = [ln for ln in f if "geometry/mesh_00125.ply" not in ln]
+    out = os.path.join(tmp, "vw-van.pbrt")
+    with open(out, "w") as f:
+        f.writelines(lines)
+    return out
 
 
 def build_scene_cache(force=False):
@@ -144,10 +167,20 @@ def build_scene_cache(force=False):
     err = ctypes.create_string_buffer(1024)
     for name, rel in BUNDLED_SCENES.items():
         out = os.path.join(cache, name + ".tbscene")
-        src = os.path.join(REF, rel)
         if os.path.exists(out) and not force:
             continue
+        tmp = None
+        if rel.startswith("variant:"):
+            tmp = tempfile.mkdtemp(prefix="tb_variant_")
+            src = _vw_van_variant(tmp)
+            if not src:
+                shutil.rmtree(tmp, ignore_errors=True)
+                continue
+        else:
+            src = os.path.join(REF, rel)
         rc = lib.tb_pbrt_convert(src.encode(), out.encode(), err, 1024)
+        if tmp:
+            shutil.rmtree(tmp, ignore_errors=True)
         if rc != 0:
             raise RuntimeError("scene conversion failed for %s: %s" % (src, err.value.decode()))
     return cache
