@@ -188,6 +188,23 @@ typedef struct TbOutputSettings {
     int32_t MaxBounces;            /* 6 */
 } TbOutputSettings;
 
+/* Tonemap.h:3-10 */
+typedef enum TbTonemapType {
+    TB_TONEMAP_REINHARD = 0, TB_TONEMAP_ACES = 1, TB_TONEMAP_CLAMP = 2, TB_TONEMAP_UNCHARTED = 3,
+    TB_TONEMAP_KHRONOS_PBR_NEUTRAL = 4, TB_TONEMAP_AGX = 5, TB_TONEMAP_AGX_PUNCHY = 6, TB_TONEMAP_GT = 7
+} TbTonemapType;
+
+/* PostProcessSettings (TracerBoy.h:222-229) + DebugSettings::m_VarianceMultiplier as they reach
+ * PostProcessConstants (SharedPostProcessStructs.h:3-14, TracerBoy.cpp:3172-3180). Defaults from
+ * GetDefaultOutputSettings (TracerBoy.h:298, 308-313). */
+typedef struct TbPostProcessSettings {
+    float ExposureMultiplier;     /* 1.0 */
+    uint32_t TonemapType;         /* TbTonemapType, default AgX punchy */
+    uint32_t UseGammaCorrection;  /* 1 */
+    uint32_t UseAutoExposure;     /* 1: luminance histogram -> averaged luminance -> exposure (TracerBoy.cpp:2948-3039) */
+    float VarianceMultiplier;     /* 1.0 */
+} TbPostProcessSettings;
+
 /* TracerBoy.h:114-128 */
 typedef enum TbSceneLoadState {
     TB_LOAD_IDLE = 0, TB_LOADING_PBRT, TB_LOADING_HOST, TB_RECORDING_DEVICE_WORK,
@@ -224,7 +241,11 @@ typedef enum TbBufferKind {
     TB_BUF_AOV_ALBEDO = 6,     /* float4: AOVCustomOutput (:524-530) */
     TB_BUF_AOV_EMISSIVE = 7,   /* float4: AOVEmissive (:532-535) */
     TB_BUF_PRIMARY_HIT_IDS = 8,/* uint2:  (geometryIndex, primitiveIndex) of the last frame's primary hit, 0xffffffff on miss */
-    TB_BUF_RAY_COUNTERS = 9    /* uint2:  per-pixel (TrianglesTested, BoxesTested) summed over the last frame's rays */
+    TB_BUF_RAY_COUNTERS = 9,   /* uint2:  per-pixel (TrianglesTested, BoxesTested) summed over the last frame's rays */
+    /* written by tb_postprocess */
+    TB_BUF_POSTPROCESS_RGBA = 10,   /* float4: PostProcessCS output before the back-buffer format conversion (PostProcessCS.hlsl:195) */
+    TB_BUF_BACKBUFFER_RGBA8 = 11,   /* uchar4: the same after the UNORM8 store, i.e. what lands in m_pPostProcessOutput */
+    TB_BUF_LUMINANCE_HISTOGRAM = 12 /* uint32[256] LuminanceHistogram + 1 float AveragedLuminance (1028 bytes) */
 } TbBufferKind;
 
 /* ----------------------------------------------------------- SW-RT boundary */
@@ -361,6 +382,23 @@ TB_API int tb_set_frames_in_flight(TbHandle* h, uint32_t n);
  * only: results are identical. */
 TB_API int tb_set_shadow_mode(TbHandle* h, int mode);
 TB_API int tb_synchronize(TbHandle* h);
+
+/* ------------------------------------------------------------ post-process */
+/* The step right after the path: auto exposure (GenerateHistogramCS.hlsl,
+ * CalculateAveragedLuminanceCS.hlsl; host side TracerBoy.cpp:2948-3039) and PostProcessCS.hlsl
+ * (:3163-3199) on the buffer GetOutputSRV(OutputType) selects (TracerBoy.cpp:2354-2383): Lit / Luminance /
+ * LiveWaves read the accumulation buffer, Albedo / LivePixels / Heatmap AOVCustomOutput, Normals AOVNormals,
+ * Depth AOVDepth. MotionVectors and LuminanceVariance have no producer on this path -> TB_ERR_NOT_IMPL
+ * (tb_postprocess_image accepts them). Results: TB_BUF_POSTPROCESS_RGBA, TB_BUF_BACKBUFFER_RGBA8,
+ * TB_BUF_LUMINANCE_HISTOGRAM. */
+TB_API int tb_get_default_postprocess_settings(TbPostProcessSettings* out);
+TB_API int tb_postprocess(TbHandle* h, uint32_t outputType, const TbPostProcessSettings* s);
+/* The same operator on caller-provided HOST images (float4 per pixel; aux may be NULL = zeros and is only read
+ * by LiveWaves). outRGBA: float4 per pixel; outRGBA8 (may be NULL): 4 bytes per pixel; hist (may be NULL):
+ * 256 words; avgLum (may be NULL): 1 float. */
+TB_API int tb_postprocess_image(TbHandle* h, const float* inRGBA, const float* auxRGBA, uint32_t width, uint32_t height,
+                                uint32_t outputType, const TbPostProcessSettings* s, float* outRGBA, uint8_t* outRGBA8,
+                                uint32_t* hist, float* avgLum);
 
 /* --------------------------------------------------------------- materials */
 TB_API int tb_is_material_id_valid(TbHandle* h, int id);                 /* IsMaterialIDValid */

@@ -38,6 +38,59 @@ def use_reference_core(on):
     return _ref.ref_core_calls()
 
 
+def ref_post_lib_path():
+    return os.path.join(_HERE, "_ref", "libref_post.so")
+
+
+def reference_post_available():
+    return os.path.exists(ref_post_lib_path())
+
+
+_ref_post = None
+
+
+def postprocess_image(img, output_type, settings, aux=None):
+    """oracle_postprocess_image (oracle/postprocess.cpp): returns (float4 image, rgba8 image, histogram[256],
+    averaged luminance). `settings` is a tracerboy_b200.api.PostProcessSettings."""
+    lib = load()
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape[:2]
+    auxp = None
+    if aux is not None:
+        aux = np.ascontiguousarray(aux, np.float32)
+        auxp = aux.ctypes.data_as(C.c_void_p)
+    out = np.empty((h, w, 4), np.float32)
+    rgba8 = np.empty((h, w, 4), np.uint8)
+    hist = np.zeros(256, np.uint32)
+    avg = C.c_float(0.0)
+    rc = lib.oracle_postprocess_image(img.ctypes.data_as(C.c_void_p), auxp, w, h, int(output_type), C.byref(settings),
+                                      out.ctypes.data_as(C.c_void_p), rgba8.ctypes.data_as(C.c_void_p),
+                                      hist.ctypes.data_as(C.c_void_p), C.byref(avg))
+    assert rc == 0
+    return out, rgba8, hist, avg.value
+
+
+def reference_postprocess_image(img, output_type, settings, averaged_luminance, aux=None):
+    """The reference's own Tonemap.h + PostProcessCS.hlsl Process* functions compiled from the mount as host C++
+    (oracle/_ref/libref_post.so). The averaged luminance is an input here."""
+    global _ref_post
+    if _ref_post is None:
+        _ref_post = C.CDLL(ref_post_lib_path())
+        _ref_post.ref_postprocess_image.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                                    C.c_float, C.c_void_p]
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape[:2]
+    auxp = None
+    if aux is not None:
+        aux = np.ascontiguousarray(aux, np.float32)
+        auxp = aux.ctypes.data_as(C.c_void_p)
+    out = np.empty((h, w, 4), np.float32)
+    rc = _ref_post.ref_postprocess_image(img.ctypes.data_as(C.c_void_p), auxp, w, h, int(output_type), C.byref(settings),
+                                         C.c_float(averaged_luminance), out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return out
+
+
 def set_literal_rcp(on):
     """Test hook: literal rcp(0) = inf in GetRayData (deviation D6 off)."""
     load().oracle_set_literal_rcp(1 if on else 0)
@@ -74,6 +127,8 @@ def load():
         lib.oracle_get_counts.argtypes = [C.c_void_p, C.c_void_p]
         lib.oracle_get_stats.argtypes = [C.c_void_p, C.c_void_p]
         lib.oracle_readback.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]
+        lib.oracle_postprocess_image.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
 

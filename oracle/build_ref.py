@@ -39,5 +39,35 @@ def build(force=False):
     return target
 
 
+TONEMAP = "/root/reference/TracerBoy/Tonemap.h"
+POSTPROCESS = "/root/reference/TracerBoy/PostProcessCS.hlsl"
+
+
+def post_lib_path():
+    return os.path.join(OUT, "libref_post.so")
+
+
+def build_post(force=False):
+    """oracle/_ref/libref_post.so: the reference's Tonemap.h + PostProcessCS.hlsl Process* functions as host C++."""
+    target = post_lib_path()
+    if not (os.path.exists(TONEMAP) and os.path.exists(POSTPROCESS)):
+        return target if os.path.exists(target) else None
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_post.cpp")] + [TONEMAP, POSTPROCESS]
+    if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs):
+        return target
+    sys.path.insert(0, os.path.join(HERE, "ref"))
+    import prepass
+    prepass.run_post(TONEMAP, POSTPROCESS, os.path.join(OUT, "post_gen.inc"))
+    cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-mfma", "-ffp-contract=off", "-fsingle-precision-constant",
+           "-fno-fast-math", "-fvisibility=hidden", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + HERE,
+           os.path.join(HERE, "ref", "ref_post.cpp"), "-o", target]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref post-process build failed:\n" + r.stdout)
+    return target
+
+
 if __name__ == "__main__":
+    print(build_post(force="--force" in sys.argv))
     print(build(force="--force" in sys.argv))

@@ -20,9 +20,13 @@ struct float2 {
     tbm::f2 t() const { return tbm::mk2(x, y); }
     float2 xy() const { return *this; }
 };
+struct float4;
 struct float3 {
     union { struct { float x, y, z; }; struct { float r, g, b; }; };
     float3() : x(0), y(0), z(0) {}
+#ifdef RC_POST
+    float3(const float4& v); // HLSL implicit truncation float4 -> float3 (PostProcessCS.hlsl:26, 69, 118)
+#endif
     float3(float s) : x(s), y(s), z(s) {}
     float3(float x_, float y_, float z_) : x(x_), y(y_), z(z_) {}
     float3(float2 a, float z_) : x(a.x), y(a.y), z(z_) {}
@@ -42,6 +46,9 @@ struct float4 {
     float3 xyz() const { return float3(x, y, z); }
     float3 rgb() const { return float3(x, y, z); }
 };
+#ifdef RC_POST
+inline float3::float3(const float4& v) : x(v.x), y(v.y), z(v.z) {}
+#endif
 typedef float2 vec2;
 typedef float3 vec3;
 typedef float4 vec4;

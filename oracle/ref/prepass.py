@@ -35,5 +35,17 @@ def run(src, dst):
     open(dst, "w").write(text)
 
 
+def run_post(tonemap_h, postprocess_hlsl, dst):
+    """Tonemap.h whole + the Process* functions of PostProcessCS.hlsl (everything between the root-signature
+    macro and the entry point; the resource declarations and main()'s switch cannot be compiled and are
+    restated in ref_post.cpp)."""
+    t = open(tonemap_h).read().replace("#pragma once", "")
+    p = open(postprocess_hlsl).read()
+    a, b = p.index("float3 ProcessLit(float4 color)"), p.index("[numthreads(8, 8, 1)]")
+    text = t + "\n" + p[a:b]
+    text = re.sub(r"\.(xyz|rgb|xy)\b(?!\s*\()", r".\1()", text)
+    open(dst, "w").write(text)
+
+
 if __name__ == "__main__":
     run(sys.argv[1], sys.argv[2])

@@ -46,6 +46,19 @@ class OutputSettings(C.Structure):  # TracerBoy.h:212-288 (members that reach Pe
                 ("MaxBounces", C.c_int32)]
 
 
+class PostProcessSettings(C.Structure):  # TracerBoy.h:222-229 as they reach PostProcessConstants (SharedPostProcessStructs.h:3-14)
+    _fields_ = [("ExposureMultiplier", C.c_float), ("TonemapType", C.c_uint32), ("UseGammaCorrection", C.c_uint32),
+                ("UseAutoExposure", C.c_uint32), ("VarianceMultiplier", C.c_float)]
+
+
+class OutputType:  # TracerBoy.h:171-183
+    LIT, ALBEDO, NORMALS, DEPTH, MOTION_VECTORS, LUMINANCE, LUMINANCE_VARIANCE, LIVE_PIXELS, LIVE_WAVES, HEATMAP = range(10)
+
+
+class TonemapType:  # Tonemap.h:3-10
+    REINHARD, ACES, CLAMP, UNCHARTED, KHRONOS_PBR_NEUTRAL, AGX, AGX_PUNCHY, GT = range(8)
+
+
 class Ray(C.Structure):
     _fields_ = [("Origin", C.c_float * 3), ("TMin", C.c_float), ("Direction", C.c_float * 3), ("TMax", C.c_float)]
 
@@ -98,9 +111,10 @@ class PrebuildInfo(C.Structure):
 
 class BufferKind:
     ACCUM_RGBW, JITTERED_RGBW, RESOLVED_RGB, AOV_NORMAL, AOV_WORLDPOS, AOV_DEPTH, AOV_ALBEDO, AOV_EMISSIVE, \
-        PRIMARY_HIT_IDS, RAY_COUNTERS = range(10)
+        PRIMARY_HIT_IDS, RAY_COUNTERS, POSTPROCESS_RGBA, BACKBUFFER_RGBA8, LUMINANCE_HISTOGRAM = range(13)
     _shape = {0: (np.float32, 4), 1: (np.float32, 4), 2: (np.float32, 3), 3: (np.float32, 4), 4: (np.float32, 4),
-              5: (np.float32, 1), 6: (np.float32, 4), 7: (np.float32, 4), 8: (np.uint32, 2), 9: (np.uint32, 2)}
+              5: (np.float32, 1), 6: (np.float32, 4), 7: (np.float32, 4), 8: (np.uint32, 2), 9: (np.uint32, 2),
+              10: (np.float32, 4), 11: (np.uint8, 4)}
 
 
 BVH_BUILD_PREFER_FAST_TRACE = 0x4
@@ -145,6 +159,9 @@ def load_library():
         "tb_set_material": [vp, i32, C.POINTER(Material)],
         "tb_bvh_prebuild_info": [C.POINTER(GeometryDesc), u32, C.POINTER(PrebuildInfo)],
         "tb_bvh_build": [vp, C.POINTER(GeometryDesc), u32, u32], "tb_trace_rays": [vp, vp, u64, vp],
+        "tb_get_default_postprocess_settings": [C.POINTER(PostProcessSettings)],
+        "tb_postprocess": [vp, u32, C.POINTER(PostProcessSettings)],
+        "tb_postprocess_image": [vp, vp, vp, u32, u32, u32, C.POINTER(PostProcessSettings), vp, vp, vp, C.POINTER(C.c_float)],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -160,13 +177,21 @@ EXPORTED_SYMBOLS = ["tb_create", "tb_destroy", "tb_last_error", "tb_version", "t
                     "tb_resize", "tb_select_pixel", "tb_get_stats", "tb_render", "tb_samples_rendered",
                     "tb_invalidate_history", "tb_set_frame_shard", "tb_set_row_shard", "tb_buffer_size", "tb_readback", "tb_device_buffer",
                     "tb_get_render_stats", "tb_reset_render_stats", "tb_set_profiling", "tb_set_frames_in_flight", "tb_set_shadow_mode", "tb_synchronize", "tb_is_material_id_valid",
-                    "tb_get_material", "tb_set_material", "tb_bvh_prebuild_info", "tb_bvh_build", "tb_trace_rays"]
+                    "tb_get_material", "tb_set_material", "tb_bvh_prebuild_info", "tb_bvh_build", "tb_trace_rays",
+                    "tb_get_default_postprocess_settings", "tb_postprocess", "tb_postprocess_image"]
 
 
 def get_default_output_settings():
     """TracerBoy::GetDefaultOutputSettings (TracerBoy.h:290-360)."""
     s = OutputSettings()
     load_library().tb_get_default_settings(C.byref(s))
+    return s
+
+
+def get_default_postprocess_settings():
+    """PostProcessSettings of TracerBoy::GetDefaultOutputSettings (TracerBoy.h:308-313)."""
+    s = PostProcessSettings()
+    load_library().tb_get_default_postprocess_settings(C.byref(s))
     return s
 
 
@@ -324,6 +349,33 @@ class TracerBoy:
             out = np.empty(shape, dt)
         self._ck(self._lib.tb_readback(self._h, kind, out.ctypes.data, out.nbytes))
         return out
+
+    def PostProcess(self, output_type, settings):
+        """Auto exposure + PostProcessCS on the buffer the output type selects (TracerBoy.cpp:2948-3039, 3163-3199).
+        Results: Readback(POSTPROCESS_RGBA / BACKBUFFER_RGBA8), GetLuminanceHistogram()."""
+        self._ck(self._lib.tb_postprocess(self._h, int(output_type), C.byref(settings)))
+
+    def GetLuminanceHistogram(self):
+        """(LuminanceHistogram[256], AveragedLuminance) of the last PostProcess call."""
+        raw = np.empty(257, np.uint32)
+        self._ck(self._lib.tb_readback(self._h, BufferKind.LUMINANCE_HISTOGRAM, raw.ctypes.data, raw.nbytes))
+        return raw[:256].copy(), float(raw[256:].view(np.float32)[0])
+
+    def PostProcessImage(self, img, output_type, settings, aux=None):
+        """The same operator on a host float4 image: returns (float4 image, rgba8 image, histogram, averaged luminance)."""
+        img = np.ascontiguousarray(img, np.float32)
+        h, w = img.shape[:2]
+        auxp = None
+        if aux is not None:
+            aux = np.ascontiguousarray(aux, np.float32)
+            auxp = aux.ctypes.data
+        out = np.empty((h, w, 4), np.float32)
+        out8 = np.empty((h, w, 4), np.uint8)
+        hist = np.zeros(256, np.uint32)
+        avg = C.c_float(0.0)
+        self._ck(self._lib.tb_postprocess_image(self._h, img.ctypes.data, auxp, w, h, int(output_type), C.byref(settings),
+                                                out.ctypes.data, out8.ctypes.data, hist.ctypes.data, C.byref(avg)))
+        return out, out8, hist, avg.value
 
     def DeviceBuffer(self, kind):
         p, n = C.c_void_p(), C.c_uint64()

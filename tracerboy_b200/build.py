@@ -28,9 +28,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",
               "-I" + os.path.join(ROOT, "include"), "-ccbin", GXX]
 
-CUDA_SRCS = ["csrc/cuda/bvh_build.cu", "csrc/cuda/pathtrace.cu"]
+CUDA_SRCS = ["csrc/cuda/bvh_build.cu", "csrc/cuda/pathtrace.cu", "csrc/cuda/postprocess.cu"]
 HOST_SRCS = ["csrc/host/api.cpp", "csrc/host/scene.cpp"]
-HEADERS = ["csrc/cuda/device_types.h", "csrc/cuda/pathtrace.h", "csrc/cuda/traverse.cuh", "csrc/cuda/launch.h",
+HEADERS = ["csrc/cuda/device_types.h", "csrc/cuda/pathtrace.h", "csrc/cuda/traverse.cuh", "csrc/cuda/launch.h", "csrc/cuda/postprocess.h",
            "csrc/common/tb_math.h", "csrc/common/tb_vec.h", "csrc/host/scene.h", "../include/tracerboy_b200.h"]
 
 
@@ -195,6 +195,7 @@ def build_all(force=False, verbose=False):
         sys.path.insert(0, ROOT)
     from oracle import build_ref  # checker only: the reference's kernel.glsl compiled from the mount, when present
     build_ref.build(force)
+    build_ref.build_post(force)
 
 
 if __name__ == "__main__":

@@ -200,5 +200,14 @@ TB_HD float pow_(float x, float y) {
     return exp_(y * log_(x));
 }
 
+// log2 / exp2 / smoothstep (post-processing: Tonemap.h agx + GTTonemap, GenerateHistogramCS.hlsl:27,
+// CalculateAveragedLuminanceCS.hlsl:36), pinned on top of log_/exp_
+TB_HD float log2_(float x) { return log_(x) * 1.44269504088896341f; }
+TB_HD float exp2_(float x) { return exp_(x * 0.693147180559945309f); }
+TB_HD float smoothstep_(float a, float b, float x) {
+    float t = saturate((x - a) / (b - a));
+    return (t * t) * (3.0f - 2.0f * t);
+}
+
 } // namespace tbm
 #endif

@@ -27,6 +27,7 @@ TB_HD f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
 TB_HD f3 operator*(float s, f3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
 TB_HD f3 operator/(f3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
 TB_HD f3 operator+(f3 a, float s) { return mk3(a.x + s, a.y + s, a.z + s); }
+TB_HD f3 operator+(float s, f3 a) { return mk3(s + a.x, s + a.y, s + a.z); }
 TB_HD f3 operator-(f3 a, float s) { return mk3(a.x - s, a.y - s, a.z - s); }
 TB_HD f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
 TB_HD f3& operator+=(f3& a, f3 b) { a = a + b; return a; }

@@ -380,14 +380,23 @@ __device__ __forceinline__ uint32_t pack_state(int bounce, bool prevSpec) { retu
 
 // ---------------------------------------------------------------------- raygen
 __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, FrameConstants fc, PathState st) {
-    uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t pi = slot;
     uint32_t n = fc.width * fc.height;
+    // Thread -> pixel mapping (the role of ThreadGroupTilingX, ComputeShaderUtil.h:12-67; results do not
+    // depend on it): a warp owns an 8x4 pixel tile, so the 32 primary rays that enter k_extend together
+    // walk nearly the same nodes and their loads coalesce into few L1 wavefronts.
+    if ((fc.width & 7u) == 0 && (fc.height & 3u) == 0) {
+        const uint32_t tile = slot >> 5, l = slot & 31u, tilesX = fc.width >> 3;
+        pi = ((tile / tilesX) * 4u + (l >> 3)) * fc.width + (tile % tilesX) * 8u + (l & 7u);
+        if (slot >= n) pi = n;
+    }
     // (all queue / suspension counters were zeroed by the memset node in front of this kernel)
     // row-band sharding (partitioning 1): bands of 8 rows, band b belongs to the shard b % stride
     const bool owned = pi < n && ((pi / fc.width) / 8u) % fc.rowStride == fc.rowOffset;
     if (fc.rowStride == 1) { // every pixel: the first queue is the identity
-        if (pi == 0) st.queueCount[0] = n;
-        if (pi < n) st.queue[0][pi] = pi;
+        if (slot == 0) st.queueCount[0] = n;
+        if (slot < n) st.queue[0][slot] = pi;
     } else {
         uint32_t m = __ballot_sync(0xffffffffu, owned);
         if (m) {

@@ -13,6 +13,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "../cuda/pathtrace.h"
+#include "../cuda/postprocess.h"
 #include "scene.h"
 #include "tracerboy_b200.h"
 
@@ -40,6 +41,10 @@ struct TbHandle {
     uint64_t framesIssued = 0;
     std::vector<void*> frameAllocs;
     float* resolved = nullptr;
+    float4* post = nullptr;         // PostProcessCS output (float4) ...
+    uchar4* post8 = nullptr;        // ... and after the UNORM8 back-buffer store
+    uint32_t* lumHist = nullptr;    // LuminanceHistogram[256] + AveragedLuminance
+    int numSMs = 148;
     uint32_t width = 0, height = 0;
     TbCamera camera{};
     uint32_t samplesRendered = 0; // local samples since the last invalidate
@@ -116,6 +121,7 @@ static void free_frame(TbHandle* h) {
     free_list(h->frameAllocs);
     h->st = PathState();
     h->resolved = nullptr;
+    h->post = nullptr; h->post8 = nullptr; h->lumHist = nullptr;
     h->width = h->height = 0;
 }
 
@@ -419,6 +425,10 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
         CUDA_OK(h, cudaEventCreateWithFlags(&sl.accDone, cudaEventDisableTiming));
     }
     CUDA_OK(h, alloc((void**)&h->resolved, 12 * n));
+    CUDA_OK(h, alloc((void**)&h->post, 16 * n)); CUDA_OK(h, alloc((void**)&h->post8, 4 * n));
+    CUDA_OK(h, alloc((void**)&h->lumHist, 257 * sizeof(uint32_t)));
+    cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, h->device);
+    if (h->numSMs <= 0) h->numSMs = 148;
     CUDA_OK(h, cudaStreamSynchronize(h->stream)); // memsets done before the slot streams touch the buffers
     h->width = w; h->height = hh;
     h->samplesRendered = 0;
@@ -551,6 +561,9 @@ static int buffer_info(TbHandle* h, uint32_t kind, void** p, uint64_t* bytes) {
     case TB_BUF_AOV_EMISSIVE: *p = st.aovEmissive; *bytes = 16 * n; break;
     case TB_BUF_PRIMARY_HIT_IDS: *p = st.primaryHit; *bytes = 8 * n; break;
     case TB_BUF_RAY_COUNTERS: *p = st.counters; *bytes = 8 * n; break;
+    case TB_BUF_POSTPROCESS_RGBA: *p = h->post; *bytes = 16 * n; break;
+    case TB_BUF_BACKBUFFER_RGBA8: *p = h->post8; *bytes = 4 * n; break;
+    case TB_BUF_LUMINANCE_HISTOGRAM: *p = h->lumHist; *bytes = 257 * sizeof(uint32_t); break;
     default: return fail(h, TB_ERR_INVALID_ARG, "unknown buffer kind");
     }
     return TB_OK;
@@ -586,6 +599,64 @@ TB_API int tb_readback(TbHandle* h, uint32_t kind, void* dst, uint64_t bytes) {
     if (kind == TB_BUF_RESOLVED_RGB) CUDA_OK(h, resolve_rgb(h->st.accum, h->resolved, h->width * h->height, h->stream, h->lc));
     CUDA_OK(h, cudaMemcpyAsync(dst, p, need, cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return TB_OK;
+}
+
+// ------------------------------------------------------------ post-process
+TB_API int tb_get_default_postprocess_settings(TbPostProcessSettings* s) {
+    if (!s) return TB_ERR_INVALID_ARG;
+    s->ExposureMultiplier = 1.0f; s->TonemapType = TB_TONEMAP_AGX_PUNCHY; s->UseGammaCorrection = 1; // TracerBoy.h:308-313
+    s->UseAutoExposure = 1; s->VarianceMultiplier = 1.0f;                                             // :298
+    return TB_OK;
+}
+
+TB_API int tb_postprocess(TbHandle* h, uint32_t outputType, const TbPostProcessSettings* s) {
+    if (!h || !s) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (!h->width) return fail(h, TB_ERR_STATE, "no frame buffers (tb_resize)");
+    const void* in = nullptr;
+    bool scalar = false;
+    switch (outputType) { // GetOutputSRV, TracerBoy.cpp:2354-2383
+    case TB_OUTPUT_LIT: case TB_OUTPUT_LUMINANCE: case TB_OUTPUT_LIVE_WAVES: in = h->st.accum; break;
+    case TB_OUTPUT_ALBEDO: case TB_OUTPUT_LIVE_PIXELS: case TB_OUTPUT_HEATMAP: in = h->st.aovAlbedo; break;
+    case TB_OUTPUT_NORMALS: in = h->st.aovNormal; break;
+    case TB_OUTPUT_DEPTH: in = h->st.aovDepth; scalar = true; break;
+    case TB_OUTPUT_MOTION_VECTORS: case TB_OUTPUT_LUMINANCE_VARIANCE:
+        return fail(h, TB_ERR_NOT_IMPL, "motion vectors / luminance variance are not produced by this path");
+    default: return fail(h, TB_ERR_INVALID_ARG, "unknown output type");
+    }
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, postprocess(in, scalar, h->st.aovAlbedo, h->width, h->height, outputType, *s, h->lumHist, h->post, h->post8,
+                           h->numSMs, h->stream, h->lc));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return TB_OK;
+}
+
+TB_API int tb_postprocess_image(TbHandle* h, const float* inRGBA, const float* auxRGBA, uint32_t width, uint32_t height,
+                                uint32_t outputType, const TbPostProcessSettings* s, float* outRGBA, uint8_t* outRGBA8,
+                                uint32_t* hist, float* avgLum) {
+    if (!h || !inRGBA || !s || !outRGBA) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (width == 0 || height == 0 || (uint64_t)width * height > (1ull << 28)) return fail(h, TB_ERR_INVALID_ARG, "bad resolution");
+    if (outputType > TB_OUTPUT_HEATMAP) return fail(h, TB_ERR_INVALID_ARG, "unknown output type");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const size_t n = (size_t)width * height;
+    std::vector<void*> tmp;
+    struct Guard { std::vector<void*>& v; ~Guard() { free_list(v); } } guard{tmp};
+    auto alloc = [&](void** p, size_t bytes) -> cudaError_t { cudaError_t e = cudaMalloc(p, bytes); if (e == cudaSuccess) tmp.push_back(*p); return e; };
+    float4 *dIn = nullptr, *dAux = nullptr, *dOut = nullptr; uchar4* dOut8 = nullptr; uint32_t* dHist = nullptr;
+    CUDA_OK(h, alloc((void**)&dIn, 16 * n)); CUDA_OK(h, alloc((void**)&dOut, 16 * n)); CUDA_OK(h, alloc((void**)&dOut8, 4 * n));
+    CUDA_OK(h, alloc((void**)&dHist, 257 * sizeof(uint32_t)));
+    CUDA_OK(h, cudaMemcpyAsync(dIn, inRGBA, 16 * n, cudaMemcpyHostToDevice, h->stream));
+    if (auxRGBA) { CUDA_OK(h, alloc((void**)&dAux, 16 * n)); CUDA_OK(h, cudaMemcpyAsync(dAux, auxRGBA, 16 * n, cudaMemcpyHostToDevice, h->stream)); }
+    CUDA_OK(h, postprocess(dIn, false, dAux, width, height, outputType, *s, dHist, dOut, dOut8, sms, h->stream, h->lc));
+    CUDA_OK(h, cudaMemcpyAsync(outRGBA, dOut, 16 * n, cudaMemcpyDeviceToHost, h->stream));
+    if (outRGBA8) CUDA_OK(h, cudaMemcpyAsync(outRGBA8, dOut8, 4 * n, cudaMemcpyDeviceToHost, h->stream));
+    uint32_t hh[257];
+    CUDA_OK(h, cudaMemcpyAsync(hh, dHist, sizeof(hh), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    if (hist) memcpy(hist, hh, 256 * sizeof(uint32_t));
+    if (avgLum) memcpy(avgLum, &hh[256], 4);
     return TB_OK;
 }
 
