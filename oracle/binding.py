@@ -91,6 +91,11 @@ def reference_postprocess_image(img, output_type, settings, averaged_luminance, 
     return out
 
 
+def set_literal_mode(mask):
+    """Test hook: bit 0 = deviation D6 off (literal rcp(0) = inf), bit 1 = deviation D7 off (NaN rays walk the tree)."""
+    load().oracle_set_literal_mode(int(mask))
+
+
 def set_literal_rcp(on):
     """Test hook: literal rcp(0) = inf in GetRayData (deviation D6 off)."""
     load().oracle_set_literal_rcp(1 if on else 0)

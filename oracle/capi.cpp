@@ -88,6 +88,7 @@ ORACLE_API int oracle_render(OracleHandle* h, const TbOutputSettings* s, uint32_
     return 0;
 }
 ORACLE_API void oracle_set_literal_rcp(int on) { oracle::set_literal_rcp(on != 0); }
+ORACLE_API void oracle_set_literal_mode(int mask) { oracle::set_literal_mode(mask); }
 ORACLE_API int oracle_set_shard(OracleHandle* h, uint32_t offset, uint32_t stride) {
     if (stride == 0 || offset >= stride) return -1;
     h->shardOffset = offset; h->shardStride = stride; h->samples = 0;

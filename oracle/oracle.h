@@ -57,6 +57,7 @@ bool build_bvh(Scene& s, int treeletPasses, std::string& err);
 void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit);
 // test hook: evaluate GetRayData's rcp literally (inf for zero components) instead of the clamped form
 void set_literal_rcp(bool on);
+void set_literal_mode(int mask); // bit 0: D6 off (literal zero axes), bit 1: D7 off (NaN rays walk the tree)
 
 struct FrameBuffers {
     uint32_t width = 0, height = 0;

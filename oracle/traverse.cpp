@@ -75,8 +75,10 @@ inline bool ray_tri(float& hitT, float& b1, float& b2, f3 org, int kx, int ky, i
 }
 } // namespace
 
-static bool g_literalRcp = false;
-void set_literal_rcp(bool on) { g_literalRcp = on; }
+static bool g_literalRcp = false; // D6 off: literal rcp(0) = inf
+static bool g_literalNaN = false; // D7 off: NaN rays walk the tree
+void set_literal_rcp(bool on) { g_literalRcp = on; g_literalNaN = on; }
+void set_literal_mode(int mask) { g_literalRcp = (mask & 1) != 0; g_literalNaN = (mask & 2) != 0; }
 
 void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit) {
     const uint8_t* bvh = s.bvh.data();
@@ -88,6 +90,16 @@ void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit) {
 
     f3 org = mk3(ray.Origin[0], ray.Origin[1], ray.Origin[2]);
     f3 dir = mk3(ray.Direction[0], ray.Direction[1], ray.Direction[2]);
+    // Deviation D7: a ray with a NaN origin or direction component can never commit a hit (every
+    // U/V/W of the watertight test is NaN, so t0 is NaN and `t0 < resultT` is false), but literally its NaN
+    // slabs are dropped by min/max, so it walks every node overlapping the remaining axes — the whole tree
+    // (2.7 M box tests on the vw-van scene) when the direction is all NaN, which the glass walk produces a
+    // few times per million paths. Such a ray is reported as the miss it is, with zero tests.
+    if (!g_literalNaN && (org.x != org.x || org.y != org.y || org.z != org.z || dir.x != dir.x || dir.y != dir.y || dir.z != dir.z)) {
+        hit.TrianglesTested = hit.BoxesTested = 0; hit.InstanceIndex = 0;
+        hit.t = -1.0f; hit.b1 = hit.b2 = 0; hit.PrimitiveIndex = hit.GeometryIndex = 0xffffffffu;
+        return;
+    }
     // GetRayData, TraverseFunction.hlsli:473-495
     f3 inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
     // Deviation D6: exactly-zero direction components. Literally, rcp(0) = inf turns

@@ -611,12 +611,14 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
         // one more lanes are waiting for (box-pair test vs. triangle test), so the two never serialise
         // inside an iteration; lanes on the minority path wait and soon become the majority. The phase
         // ends when enough lanes have finished to make a service phase worthwhile.
-        while (true) {
+        // Once the queue is exhausted there is nothing to refill with, so the phase would only end when the last
+        // ray does; it is cut every 64 iterations instead so that the service phase can park rays over budget.
+        for (uint32_t iter = 0;; iter++) {
             bool busy = haveRay && !tr.done();
             bool wantLeaf = busy && tr.at_leaf();
             uint32_t mB = __ballot_sync(0xffffffffu, busy), mL = __ballot_sync(0xffffffffu, wantLeaf);
             uint32_t nB = __popc(mB), nL = __popc(mL);
-            if (nB == 0 || (!exhausted && nB < REFILL_THRESHOLD)) break;
+            if (nB == 0 || (!exhausted && nB < REFILL_THRESHOLD) || (!SHADOW && exhausted && iter >= 64u)) break;
             if (2 * nL > nB) {
                 if (wantLeaf) { tr.step_leaf(stack, tris); steps++; }
             } else {

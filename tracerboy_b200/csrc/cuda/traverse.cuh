@@ -107,7 +107,11 @@ struct Traversal {
         float unusedT;
         bool rootHit = zmask ? slab_zero(unusedT, committedT, org, zmask, oinv, inv, abs3(inv), bvh.root.c[0], bvh.root.c[1], bvh.root.c[2], bvh.root.h[0], bvh.root.h[1], bvh.root.h[2])
                              : slab(unusedT, committedT, oinv, inv, abs3(inv), bvh.root.c[0], bvh.root.c[1], bvh.root.c[2], bvh.root.h[0], bvh.root.h[1], bvh.root.h[2]);
-        if (rootHit)
+        // Deviation D7: a ray with a NaN origin or direction component can never commit a hit (t0 is
+        // NaN), but its NaN slabs are dropped by min/max, so literally it walks every node overlapping the other
+        // axes (the whole tree for an all-NaN direction). It is reported as the miss it is, with zero tests.
+        const bool nanRay = o.x != o.x || o.y != o.y || o.z != o.z || dir.x != dir.x || dir.y != dir.y || dir.z != dir.z;
+        if (rootHit && !nanRay)
             cur = (bvh.root.flags & 0x80000000u) ? (0x80000000u | (bvh.root.flags & 0x3fffffffu)) : 0u;
     }
     __device__ __forceinline__ bool done() const { return cur == TB_NO_NODE; }
