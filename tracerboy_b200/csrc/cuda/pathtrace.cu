@@ -377,6 +377,7 @@ __device__ __forceinline__ float gaussian(float x, float mu, float sigma) {
 
 // state word packing in rayD.w: bits 0..7 bounce index, bit 8 prevPerfectlySpecular
 __device__ __forceinline__ uint32_t pack_state(int bounce, bool prevSpec) { return (uint32_t)bounce | (prevSpec ? 0x100u : 0u); }
+// walkers (k_shade -> k_walk) also carry bit 9: the bounce's perfect-specular flag
 
 // ---------------------------------------------------------------------- raygen
 __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, FrameConstants fc, PathState st) {
@@ -541,6 +542,7 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
     if (!SHADOW && blockIdx.x == 0 && threadIdx.x == 0) {
         st.queueCount[qi ^ 1] = 0;                       // next queue starts empty (consumed by k_shade)
         st.queueCount[4] = 0; st.queueCount[5] = 0;      // shadow queue of this bounce + its work counter
+        st.queueCount[10] = 0; st.queueCount[11] = 0;    // walk queue of this bounce + its work counter
     }
     uint32_t* __restrict__ next = SHADOW ? &st.queueCount[5] : &st.queueCount[2 + qi]; // work counter, zeroed by the previous kernel
     const uint32_t* __restrict__ queue = SHADOW ? st.shadowQueue : st.queue[qi];
@@ -695,6 +697,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < countUp; i += stride) {
         bool alive = false;    // does this path continue to the next bounce?
         bool deferred = false; // STAGE 0: waits for its shadow ray
+        bool walker = false, walkerPerfectSpec = false; // entered a subsurface / glass medium: continues in k_walk
         uint32_t pi = 0;
         if (i < count) {
             pi = inQueue[i];
@@ -804,32 +807,14 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, 
                     float DistancePerScatter = 1.0f / (((material.scattering.x + material.scattering.y) + material.scattering.z) / 3.0f);
                     float maxTravelDistance = noScatter ? LARGE_NUMBER : DistancePerScatter;
                     bool exitting = (material.Flags & TB_SINGLE_SIDED_MATERIAL_FLAG) != 0;
-                    for (int k = 0; k < 100 && !exitting; k++) {
-                        float travelDistance = fmaxf(-log_(rng.next()), 0.1f) * maxTravelDistance;
-                        Surface ws; float wt;
-                        bool found = intersect_inline(bvh, sc, org, dir, rc, ws, wt);
-                        normal = ws.normal;
-                        if (!found) { thr = mk3(0.0f); break; }
-                        float tt = fminf(travelDistance, wt);
-                        exitting = tt < travelDistance || noScatter;
-                        if (k == 99 && !exitting) thr = mk3(0.0f);
-                        RayPoint = org + dir * tt;
-                        org = RayPoint + normal * EPSILON;
-                        thr *= exp3((-tt) * material.absorption);
-                        if (exitting) {
-                            RdotN = dot(normal, dir);
-                            if (RdotN >= 0.0f) { normal = -normal; RdotN = -RdotN; }
-                            RefractResult rr = refract_or_reflect(rng, dir, normal, NewIOR / CurrentIOR, RdotN, bPerfectSpec, material.roughness, bPrevSpec);
-                            if (rr == GIVE_UP) break;
-                            if (rr == REFLECTED) exitting = false;
-                        } else {
-                            // GenerateRandomDirection(), kernel.glsl:991-999
-                            float u1 = rng.next(), u2 = rng.next();
-                            float r = sqrtf(1.0f - u1 * u1);
-                            float phi = 2.0f * 3.14f * u2;
-                            dir = mk3(cos_(phi) * r, sin_(phi) * r, u1);
-                            thr /= 1.0f;
-                        }
+                    if (!exitting) {
+                        // The random walk inside the medium (kernel.glsl:1571-1688) traces up to 100 rays. It runs in
+                        // k_walk, in warps made of walkers only: inline here it ran at 3.2 active lanes per instruction
+                        // on the vw-van scene (profiles/). Hand over what the walk reads besides the path state.
+                        st.walkA[pi] = make_float4(material.absorption.x, material.absorption.y, material.absorption.z, maxTravelDistance);
+                        st.walkB[pi] = make_float4(CurrentIOR, NewIOR, material.roughness, 0.0f);
+                        walker = true; walkerPerfectSpec = bPerfectSpec;
+                        break;
                     }
                     skipBrdf = true; // `continue`, kernel.glsl:1690
                 } else {
@@ -895,6 +880,12 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, 
                 st.counters[pi] = c;
             }
             if (deferred) { /* nothing is written: STAGE 1 redoes this path from the same inputs */ }
+            else if (walker) {
+                st.rayO[pi] = make_float4(org.x, org.y, org.z, rng.seed);
+                st.rayD[pi] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(pack_state(bounce, bPrevSpec) | (walkerPerfectSpec ? 0x200u : 0u)));
+                st.thr[pi] = make_float4(thr.x, thr.y, thr.z, filterWeight);
+                st.col[pi] = make_float4(acc.x, acc.y, acc.z, 0.0f);
+            }
             else if (terminated) finish_path(fc, st, pi, acc, filterWeight, rng);
             else {
                 st.rayO[pi] = make_float4(org.x, org.y, org.z, rng.seed);
@@ -911,6 +902,15 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, 
             if (lane == 0) base = atomicAdd(&st.queueCount[qi ^ 1], (uint32_t)__popc(ballot));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (alive) st.queue[qi ^ 1][base + __popc(ballot & ((1u << lane) - 1u))] = pi;
+        }
+        if (SSS) { // walk queue, same warp-aggregated append
+            uint32_t wballot = __ballot_sync(0xffffffffu, walker);
+            if (wballot) {
+                uint32_t lane = threadIdx.x & 31, base = 0;
+                if (lane == 0) base = atomicAdd(&st.queueCount[10], (uint32_t)__popc(wballot));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (walker) st.walkQueue[base + __popc(wballot & ((1u << lane) - 1u))] = pi;
+            }
         }
         if (STAGE == 0) { // shadow queue, same warp-aggregated append
             uint32_t dballot = __ballot_sync(0xffffffffu, deferred);
@@ -929,6 +929,145 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, 
     if ((threadIdx.x & 31) == 0 && rays) { // slots 3..5: rays traced inside the shading stage (shadow feelers, SSS walk)
         atomicAdd(&st.stats[3], (unsigned long long)rays); atomicAdd(&st.stats[4], (unsigned long long)boxes); atomicAdd(&st.stats[5], (unsigned long long)tris);
     }
+}
+
+// The random walk of a path inside a subsurface / glass medium (kernel.glsl:1571-1688), for the walkers queued by
+// k_shade. Same persistent-warp scheme as k_extend: every lane owns a walker, the traversal phase steps all lanes'
+// rays together (one code path per iteration), and the service phase runs one walk step for the lanes whose ray has
+// finished: Beer-Lambert, exit refraction / internal reflection or an isotropic scatter, then either the next ray of
+// the walk or the end of the bounce (russian roulette, next queue / finish_path) and a new walker from the queue.
+__global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, FrameConstants fc, PathState st, int qi) {
+    const uint32_t count = st.queueCount[10];
+    uint32_t* __restrict__ next = &st.queueCount[11];
+    const float4* __restrict__ pairs = (const float4*)bvh.pairs;
+    const float4* __restrict__ tris = (const float4*)bvh.tris;
+    const uint32_t lane = threadIdx.x & 31;
+    const int MaxBounces = fc.settings.MaxBounces;
+    uint32_t rays = 0, ntris = 0, nboxes = 0;
+    Traversal tr;
+    uint32_t stack[TB_STACK_DEPTH];
+    tr.sp = 0; tr.cur = TB_NO_NODE;
+    bool have = false, exhausted = false;
+    // walker state
+    uint32_t pi = 0;
+    Rng rng; rng.seed = 0.0f; rng.time = fc.time;
+    f3 org = mk3(0.0f), dir = mk3(0.0f), thr = mk3(0.0f), absorption = mk3(0.0f);
+    float maxTravelDistance = 0.0f, CurrentIOR = 1.0f, NewIOR = 1.0f, roughness = 0.0f, travelDistance = 0.0f;
+    uint32_t sw = 0; // bounce | prevSpec << 8 | perfectSpec << 9
+    int k = 0;
+    while (true) {
+        // ---- service phase
+        bool alive = false;
+        if (have && tr.done()) {
+            HitRec h;
+            tr.result(h);
+            rays++; ntris += h.tris; nboxes += h.boxes;
+            if (fc.aovMask & AOV_FULL) { uint2 c = st.counters[pi]; c.x += h.tris; c.y += h.boxes; st.counters[pi] = c; }
+            const bool noScatter = maxTravelDistance == LARGE_NUMBER; // DistancePerScatter < 1/EPSILON otherwise
+            const bool bPerfectSpec = (sw & 0x200u) != 0;
+            bool bPrevSpec = (sw & 0x100u) != 0;
+            bool walkOn = false;
+            if (h.t < 0.0f) thr = mk3(0.0f); // left the medium without a surface: `break`, kernel.glsl:1584
+            else {
+                Surface ws = surface_from_hit(sc, h.b1, h.b2, h.geom, h.prim);
+                f3 normal = ws.normal;
+                float tt = fminf(travelDistance, h.t);
+                bool exitting = tt < travelDistance || noScatter;
+                if (k == 99 && !exitting) thr = mk3(0.0f);
+                f3 RayPoint = org + dir * tt;
+                org = RayPoint + normal * EPSILON;
+                thr *= exp3((-tt) * absorption);
+                bool giveUp = false;
+                if (exitting) {
+                    float RdotN = dot(normal, dir);
+                    if (RdotN >= 0.0f) { normal = -normal; RdotN = -RdotN; }
+                    RefractResult rr = refract_or_reflect(rng, dir, normal, NewIOR / CurrentIOR, RdotN, bPerfectSpec, roughness, bPrevSpec);
+                    if (rr == GIVE_UP) giveUp = true;
+                    if (rr == REFLECTED) exitting = false;
+                } else {
+                    // GenerateRandomDirection(), kernel.glsl:991-999
+                    float u1 = rng.next(), u2 = rng.next();
+                    float r = sqrtf(1.0f - u1 * u1);
+                    float phi = 2.0f * 3.14f * u2;
+                    dir = mk3(cos_(phi) * r, sin_(phi) * r, u1);
+                    thr /= 1.0f;
+                }
+                k++;
+                walkOn = !giveUp && k < 100 && !exitting;
+            }
+            sw = (sw & ~0x100u) | (bPrevSpec ? 0x100u : 0u);
+            if (walkOn) {
+                travelDistance = fmaxf(-log_(rng.next()), 0.1f) * maxTravelDistance;
+                tr.begin(bvh, org, dir, MIN_T, FAR_T);
+            } else {
+                // the walk is over; `continue` (kernel.glsl:1690) to the top of the next loop iteration:
+                // bounce limit, then russian roulette (kernel.glsl:1286-1302)
+                have = false;
+                float4 t4 = st.thr[pi], c4 = st.col[pi];
+                int bounce = (int)(sw & 0xffu) + 1;
+                bool terminated = bounce >= MaxBounces;
+                if (!terminated && bounce >= 2) {
+                    float p = fmaxf(fmaxf(thr.x, thr.y), thr.z);
+                    p = fmaxf(p, EPSILON);
+                    if (p < rng.next()) terminated = true;
+                    else thr *= 1.0f / p;
+                }
+                if (terminated) finish_path(fc, st, pi, mk3(c4.x, c4.y, c4.z), t4.w, rng);
+                else {
+                    st.rayO[pi] = make_float4(org.x, org.y, org.z, rng.seed);
+                    st.rayD[pi] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(pack_state(bounce, bPrevSpec)));
+                    st.thr[pi] = make_float4(thr.x, thr.y, thr.z, t4.w);
+                    alive = true;
+                }
+            }
+        }
+        uint32_t ballot = __ballot_sync(0xffffffffu, alive);
+        if (ballot) { // survivors join the next bounce's queue
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&st.queueCount[qi ^ 1], (uint32_t)__popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (alive) st.queue[qi ^ 1][base + __popc(ballot & ((1u << lane) - 1u))] = pi;
+        }
+        uint32_t idle = __ballot_sync(0xffffffffu, !have);
+        if (idle && !exhausted) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(next, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!have) {
+                uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+                if (i < count) {
+                    pi = st.walkQueue[i];
+                    float4 o = st.rayO[pi], d = st.rayD[pi], t4 = st.thr[pi], a = st.walkA[pi], b = st.walkB[pi];
+                    org = mk3(o.x, o.y, o.z); rng.seed = o.w;
+                    dir = mk3(d.x, d.y, d.z); sw = __float_as_uint(d.w);
+                    thr = mk3(t4.x, t4.y, t4.z);
+                    absorption = mk3(a.x, a.y, a.z); maxTravelDistance = a.w;
+                    CurrentIOR = b.x; NewIOR = b.y; roughness = b.z;
+                    k = 0;
+                    travelDistance = fmaxf(-log_(rng.next()), 0.1f) * maxTravelDistance;
+                    tr.begin(bvh, org, dir, MIN_T, FAR_T);
+                    have = true;
+                }
+            }
+            if (base + (uint32_t)__popc(idle) >= count) exhausted = true;
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        // ---- traversal phase (see k_extend)
+        while (true) {
+            bool busy = have && !tr.done();
+            bool wantLeaf = busy && tr.at_leaf();
+            uint32_t mB = __ballot_sync(0xffffffffu, busy), mL = __ballot_sync(0xffffffffu, wantLeaf);
+            uint32_t nB = __popc(mB), nL = __popc(mL);
+            uint32_t nHave = __popc(__ballot_sync(0xffffffffu, have));
+            if (nB == 0 || nHave - nB >= 8u) break; // enough finished rays to make a walk step (and a refill) worthwhile
+            if (2 * nL > nB) {
+                if (wantLeaf) tr.step_leaf(stack, tris);
+            } else {
+                if (busy && !wantLeaf) tr.step_internal(stack, pairs);
+            }
+        }
+    }
+    flush_stats(st, 3, rays, ntris, nboxes);
 }
 
 // Paths whose extension ray left the scene (kernel.glsl:1328-1343): radiance += throughput * environment,
@@ -1057,6 +1196,10 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
             TB_LAUNCH_SHADE(3);
         }
 #undef TB_LAUNCH_SHADE
+        if (sss) { // the bounce's glass / subsurface walkers (queued by the k_shade launches above)
+            uint32_t wblocks = blocks > sms * 4 ? sms * 4 : blocks;
+            k_walk<<<wblocks, 128, 0, stream>>>(bvh, sc, fc, st, qi); lc.count++;
+        }
         if (timers) cudaEventRecord(timers->next(KernelTimers::END), stream);
     }
     return cudaGetLastError();

@@ -18,7 +18,7 @@ struct PathState {
     float4* neighbor = nullptr;    // neighbour camera ray origin (bounce 0 only)
     float4* neighborDir = nullptr; // neighbour camera ray direction
     uint32_t* queue[2] = {nullptr, nullptr};
-    uint32_t* queueCount = nullptr; // [0..1] queue sizes, [2..3] k_extend work counters, [4] shadow queue size, [5] its work counter, [6..9] hit/miss queue sizes
+    uint32_t* queueCount = nullptr; // [0..1] queue sizes, [2..3] k_extend work counters, [4] shadow queue size, [5] its work counter, [6..9] hit/miss queue sizes, [10] walk queue size, [11] its work counter
     // the bounce's paths sorted by k_extend into "hit something" / "left the scene"; counters [6..9] by queue parity
     uint32_t* hitQueue = nullptr;
     uint32_t* missQueue = nullptr;
@@ -28,6 +28,10 @@ struct PathState {
     float4* shRayD = nullptr;
     float4* shHit = nullptr;       // t, b1, b2, bits(primitiveIndex) of the first hit along the shadow feeler
     uint32_t* shHitGeom = nullptr;
+    // glass / subsurface walkers: queued by k_shade, walked by k_walk (queueCount[10] size, [11] work counter)
+    uint32_t* walkQueue = nullptr;
+    float4* walkA = nullptr;       // absorption.xyz, maxTravelDistance
+    float4* walkB = nullptr;       // CurrentIOR, NewIOR, roughness, -
     // suspended long rays: two ping-pong record buffers, one counter per round
     uint32_t* susBuf[2] = {nullptr, nullptr};
     uint32_t* susCount = nullptr;   // 4 counters
