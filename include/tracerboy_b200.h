@@ -205,6 +205,16 @@ typedef struct TbPostProcessSettings {
     float VarianceMultiplier;     /* 1.0 */
 } TbPostProcessSettings;
 
+/* TemporalAccumulationConstants (TemporalAccumulationSharedShaderStructs.h:6-34) as TemporalAccumulationPass::Run
+ * fills them (TemporalAccumulationPass.cpp:87-103). */
+typedef struct TbTemporalAccumulationParams {
+    TbCamera Camera;                  /* current frame: LensHeight and FocalDistance are read from here */
+    TbCamera PrevCamera;              /* previous frame: Position, LookAt, Right, Up */
+    float HistoryWeight;              /* 0.95 at both call sites (TracerBoy.cpp:3081, 3155) */
+    uint32_t IgnoreHistory;
+    uint32_t OutputMomentInformation; /* 1: also update (mean luminance, mean luminance^2, sample count); alpha = variance */
+} TbTemporalAccumulationParams;
+
 /* TracerBoy.h:114-128 */
 typedef enum TbSceneLoadState {
     TB_LOAD_IDLE = 0, TB_LOADING_PBRT, TB_LOADING_HOST, TB_RECORDING_DEVICE_WORK,
@@ -396,6 +406,14 @@ TB_API int tb_postprocess(TbHandle* h, uint32_t outputType, const TbPostProcessS
 /* The same operator on caller-provided HOST images (float4 per pixel; aux may be NULL = zeros and is only read
  * by LiveWaves). outRGBA: float4 per pixel; outRGBA8 (may be NULL): 4 bytes per pixel; hist (may be NULL):
  * 256 words; avgLum (may be NULL): 1 float. */
+/* Realtime temporal accumulation: TemporalAccumulationCS.hlsl:100-235 on caller-provided HOST
+ * images, all float4 per pixel (history, current frame, world position of this and of the previous frame, normals,
+ * moment history — the last may be NULL when OutputMomentInformation is 0). outColor: float4 (rgb, alpha = variance or 1);
+ * outMoment (may be NULL): float4 (mean luminance, mean luminance^2, sample count, 0). */
+TB_API int tb_temporal_accumulate_image(TbHandle* h, const TbTemporalAccumulationParams* p, uint32_t width, uint32_t height,
+                                        const float* history, const float* current, const float* worldPos,
+                                        const float* prevWorldPos, const float* normals, const float* momentHistory,
+                                        float* outColor, float* outMoment);
 TB_API int tb_postprocess_image(TbHandle* h, const float* inRGBA, const float* auxRGBA, uint32_t width, uint32_t height,
                                 uint32_t outputType, const TbPostProcessSettings* s, float* outRGBA, uint8_t* outRGBA8,
                                 uint32_t* hist, float* avgLum);

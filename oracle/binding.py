@@ -91,6 +91,22 @@ def reference_postprocess_image(img, output_type, settings, averaged_luminance, 
     return out
 
 
+def temporal_accumulate_image(params, history, current, world_pos, prev_world_pos, normals, moment_history=None):
+    """oracle_temporal_accumulate_image (oracle/temporal.cpp): returns (color float4, moment float4 or None)."""
+    lib = load()
+    imgs = [np.ascontiguousarray(a, np.float32) for a in (history, current, world_pos, prev_world_pos, normals)]
+    h, w = imgs[0].shape[:2]
+    mh = np.ascontiguousarray(moment_history, np.float32) if moment_history is not None else None
+    out = np.empty((h, w, 4), np.float32)
+    mom = np.empty((h, w, 4), np.float32) if params.OutputMomentInformation else None
+    rc = lib.oracle_temporal_accumulate_image(C.byref(params), w, h, *[a.ctypes.data_as(C.c_void_p) for a in imgs],
+                                              mh.ctypes.data_as(C.c_void_p) if mh is not None else None,
+                                              out.ctypes.data_as(C.c_void_p),
+                                              mom.ctypes.data_as(C.c_void_p) if mom is not None else None)
+    assert rc == 0
+    return out, mom
+
+
 def set_literal_mode(mask):
     """Test hook: bit 0 = deviation D6 off (literal rcp(0) = inf), bit 1 = deviation D7 off (NaN rays walk the tree)."""
     load().oracle_set_literal_mode(int(mask))
@@ -132,6 +148,7 @@ def load():
         lib.oracle_get_counts.argtypes = [C.c_void_p, C.c_void_p]
         lib.oracle_get_stats.argtypes = [C.c_void_p, C.c_void_p]
         lib.oracle_readback.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]
+        lib.oracle_temporal_accumulate_image.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32] + [C.c_void_p] * 8
         lib.oracle_postprocess_image.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = lib

@@ -51,6 +51,11 @@ class PostProcessSettings(C.Structure):  # TracerBoy.h:222-229 as they reach Pos
                 ("UseAutoExposure", C.c_uint32), ("VarianceMultiplier", C.c_float)]
 
 
+class TemporalAccumulationParams(C.Structure):  # TemporalAccumulationSharedShaderStructs.h:6-34
+    _fields_ = [("Camera", Camera), ("PrevCamera", Camera), ("HistoryWeight", C.c_float), ("IgnoreHistory", C.c_uint32),
+                ("OutputMomentInformation", C.c_uint32)]
+
+
 class OutputType:  # TracerBoy.h:171-183
     LIT, ALBEDO, NORMALS, DEPTH, MOTION_VECTORS, LUMINANCE, LUMINANCE_VARIANCE, LIVE_PIXELS, LIVE_WAVES, HEATMAP = range(10)
 
@@ -161,6 +166,7 @@ def load_library():
         "tb_bvh_build": [vp, C.POINTER(GeometryDesc), u32, u32], "tb_trace_rays": [vp, vp, u64, vp],
         "tb_get_default_postprocess_settings": [C.POINTER(PostProcessSettings)],
         "tb_postprocess": [vp, u32, C.POINTER(PostProcessSettings)],
+        "tb_temporal_accumulate_image": [vp, C.POINTER(TemporalAccumulationParams), u32, u32, vp, vp, vp, vp, vp, vp, vp, vp],
         "tb_postprocess_image": [vp, vp, vp, u32, u32, u32, C.POINTER(PostProcessSettings), vp, vp, vp, C.POINTER(C.c_float)],
     }
     for name, args in sig.items():
@@ -178,7 +184,8 @@ EXPORTED_SYMBOLS = ["tb_create", "tb_destroy", "tb_last_error", "tb_version", "t
                     "tb_invalidate_history", "tb_set_frame_shard", "tb_set_row_shard", "tb_buffer_size", "tb_readback", "tb_device_buffer",
                     "tb_get_render_stats", "tb_reset_render_stats", "tb_set_profiling", "tb_set_frames_in_flight", "tb_set_shadow_mode", "tb_synchronize", "tb_is_material_id_valid",
                     "tb_get_material", "tb_set_material", "tb_bvh_prebuild_info", "tb_bvh_build", "tb_trace_rays",
-                    "tb_get_default_postprocess_settings", "tb_postprocess", "tb_postprocess_image"]
+                    "tb_get_default_postprocess_settings", "tb_postprocess", "tb_postprocess_image",
+                    "tb_temporal_accumulate_image"]
 
 
 def get_default_output_settings():
@@ -376,6 +383,18 @@ class TracerBoy:
         self._ck(self._lib.tb_postprocess_image(self._h, img.ctypes.data, auxp, w, h, int(output_type), C.byref(settings),
                                                 out.ctypes.data, out8.ctypes.data, hist.ctypes.data, C.byref(avg)))
         return out, out8, hist, avg.value
+
+    def TemporalAccumulateImage(self, params, history, current, world_pos, prev_world_pos, normals, moment_history=None):
+        """TemporalAccumulationPass::Run on host float4 images: returns (color float4, moment float4 or None)."""
+        imgs = [np.ascontiguousarray(a, np.float32) for a in (history, current, world_pos, prev_world_pos, normals)]
+        h, w = imgs[0].shape[:2]
+        mh = np.ascontiguousarray(moment_history, np.float32) if moment_history is not None else None
+        out = np.empty((h, w, 4), np.float32)
+        mom = np.empty((h, w, 4), np.float32) if params.OutputMomentInformation else None
+        self._ck(self._lib.tb_temporal_accumulate_image(self._h, C.byref(params), w, h, *[a.ctypes.data for a in imgs],
+                                                        mh.ctypes.data if mh is not None else None, out.ctypes.data,
+                                                        mom.ctypes.data if mom is not None else None))
+        return out, mom
 
     def DeviceBuffer(self, kind):
         p, n = C.c_void_p(), C.c_uint64()

@@ -222,7 +222,123 @@ __global__ void __launch_bounds__(256) k_postprocess(const void* __restrict__ in
     }
 }
 
+// ------------------------------------------------------------------ realtime temporal accumulation
+// TemporalAccumulationCS.hlsl:100-235 (NEIGHBORHOOD_CLAMPING 0, WORLD_POSITION_HISTORY_REJECTION 1). One thread per
+// pixel, 32x8 tiles so that a warp reads one row segment (coalesced float4 loads; the 3x3 world-position neighbourhood
+// and the 2x2 reprojected history taps come from L1/L2). HBM-bound: 5 float4 images read once + 2 written = 112 B per
+// pixel of compulsory traffic.
+struct Img4 {
+    const float4* p; int w, h;
+    __device__ __forceinline__ float4 load(int x, int y) const { // Texture2D::operator[]: out of bounds reads zero
+        if (!p || x < 0 || y < 0 || x >= w || y >= h) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        return __ldg(p + (size_t)y * w + x);
+    }
+    __device__ __forceinline__ f3 load3(int x, int y) const { float4 v = load(x, y); return mk3(v.x, v.y, v.z); }
+    __device__ f3 bilinear_clamp(float u, float v) const { // SampleLevel(BilinearSampler, uv, 0), clamp addressing
+        if (!p) return mk3(0.0f);
+        float fx = u * (float)w - 0.5f, fy = v * (float)h - 0.5f;
+        float x0f = floorf(fx), y0f = floorf(fy);
+        float tx = fx - x0f, ty = fy - y0f;
+        int x0 = min(max((int)x0f, 0), w - 1), x1 = min(max((int)(x0f + 1.0f), 0), w - 1);
+        int y0 = min(max((int)y0f, 0), h - 1), y1 = min(max((int)(y0f + 1.0f), 0), h - 1);
+        f3 a = lerp(load3(x0, y0), load3(x1, y0), tx);
+        f3 b = lerp(load3(x0, y1), load3(x1, y1), tx);
+        return lerp(a, b, ty);
+    }
+};
+__device__ __forceinline__ f3 F3(const TbFloat3& v) { return mk3(v.x, v.y, v.z); }
+
+__global__ void __launch_bounds__(256) k_temporal_accumulate(TbTemporalAccumulationParams P, int W, int H, const float4* __restrict__ history,
+                                                             const float4* __restrict__ current, const float4* __restrict__ worldPos,
+                                                             const float4* __restrict__ prevWorldPos, const float4* __restrict__ normals,
+                                                             const float4* __restrict__ momentHistory, float4* __restrict__ outColor,
+                                                             float4* __restrict__ outMoment) {
+    const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (px >= W || py >= H) return;
+    Img4 hist{history, W, H}, cur{current, W, H}, wp{worldPos, W, H}, pwp{prevWorldPos, W, H}, nrm{normals, W, H}, mom{momentHistory, W, H};
+    const f3 prevPos = F3(P.PrevCamera.Position);
+    f3 WorldPosition = wp.load3(px, py);
+    f3 WorldNormal = nrm.load3(px, py);
+    bool bHitValid = WorldNormal.x != 0.0f || WorldNormal.y != 0.0f || WorldNormal.z != 0.0f;
+    float aspectRatio = (float)W / (float)H;
+    float lensHeight = P.Camera.LensHeight;
+    float lensWidth = lensHeight * aspectRatio;
+    f3 PrevFrameCameraDir = normalize(F3(P.PrevCamera.LookAt) - prevPos);
+    f3 PrevFrameFocalPoint = prevPos - P.Camera.FocalDistance * PrevFrameCameraDir;
+    f3 PrevFrameRayDirection = normalize(WorldPosition - PrevFrameFocalPoint);
+    f3 RawOutputColor = cur.load3(px, py);
+    f3 NMin = WorldPosition, NMax = WorldPosition;
+#pragma unroll
+    for (int x = -1; x <= 1; x++)
+#pragma unroll
+        for (int y = -1; y <= 1; y++) {
+            int cx = px + x, cy = py + y;
+            bool valid = cx > 0 && cy > 0 && cx < W && cy < H; // all(coord > 0), :139
+            if (valid && !(x == 0 && y == 0)) {
+                f3 w = wp.load3(cx, cy);
+                NMin = min3(NMin, w);
+                NMax = max3(NMax, w);
+            }
+        }
+    f3 PrevFrameColor = mk3(0.0f), PrevMomentData = mk3(0.0f);
+    float denom = dot(PrevFrameCameraDir, PrevFrameRayDirection); // PlaneIntersection, :73-82
+    float t = fabsf(denom) > 0.0f ? dot(prevPos - PrevFrameFocalPoint, PrevFrameCameraDir) / denom : -1.0f;
+    bool bValidHistory = false;
+    if (!P.IgnoreHistory && t >= 0.0f && bHitValid) {
+        f3 LensPosition = PrevFrameFocalPoint + PrevFrameRayDirection * t;
+        f3 OffsetFromCenter = LensPosition - prevPos;
+        float u = dot(OffsetFromCenter, F3(P.PrevCamera.Right)) / (lensWidth / 2.0f);
+        float v = dot(OffsetFromCenter, F3(P.PrevCamera.Up)) / (lensHeight / 2.0f);
+        u = (u + 1.0f) / 2.0f; v = (v + 1.0f) / 2.0f;
+        v = 1.0f - v;
+        if (u >= 0.0f && u <= 1.0f && v >= 0.0f && v <= 1.0f) {
+            float distanceToNeighbor = length(NMax - NMin);
+            float fx = u * (float)W - 0.5f, fy = v * (float)H - 0.5f;
+            float SummedWeight = 0.0f;
+#pragma unroll
+            for (int x = 0; x < 2; x++)
+#pragma unroll
+                for (int y = 0; y < 2; y++) {
+                    int ix = (int)fx + x, iy = (int)fy + y;
+                    f3 PrevWP = pwp.load3(ix, iy);
+                    if (length(PrevWP - WorldPosition) < distanceToNeighbor) {
+                        float xWeight = x == 0 ? 1.0f - frac(fx) : frac(fx);
+                        float yWeight = y == 0 ? 1.0f - frac(fy) : frac(fy);
+                        float weight = xWeight * yWeight;
+                        PrevFrameColor += hist.load3(ix, iy) * weight;
+                        SummedWeight += weight;
+                        if (P.OutputMomentInformation) PrevMomentData += mom.load3(ix, iy) * weight;
+                    }
+                }
+            bValidHistory = SummedWeight > 0.0f;
+            if (bValidHistory) { PrevFrameColor /= SummedWeight; PrevMomentData /= SummedWeight; }
+            PrevMomentData = mom.bilinear_clamp(u, v); // :199, overrides the weighted sum
+        }
+    }
+    float outputAlpha = 1.0f;
+    if (P.OutputMomentInformation) {
+        float luminance = color_to_luma(RawOutputColor);
+        float luminanceSquared = luminance * luminance;
+        float sampleCount = PrevMomentData.z + 1.0f;
+        float lerpFactor = 1.0f / fminf(sampleCount, 32.0f);
+        float m1 = lerp(PrevMomentData.x, luminance, lerpFactor), m2 = lerp(PrevMomentData.y, luminanceSquared, lerpFactor);
+        if (outMoment) outMoment[(size_t)py * W + px] = make_float4(m1, m2, sampleCount, 0.0f);
+        outputAlpha = fmaxf(m2 - m1 * m1, 0.0f);
+    }
+    f3 OutputColor = lerp(RawOutputColor, PrevFrameColor, bValidHistory ? P.HistoryWeight : 0.0f);
+    outColor[(size_t)py * W + px] = make_float4(OutputColor.x, OutputColor.y, OutputColor.z, outputAlpha);
+}
+
 } // namespace
+
+cudaError_t temporal_accumulate(const TbTemporalAccumulationParams& p, uint32_t width, uint32_t height, const float4* history,
+                                const float4* current, const float4* worldPos, const float4* prevWorldPos, const float4* normals,
+                                const float4* momentHistory, float4* outColor, float4* outMoment, cudaStream_t stream, LaunchCounter& lc) {
+    dim3 grid((width + 31) / 32, (height + 7) / 8);
+    k_temporal_accumulate<<<grid, 256, 0, stream>>>(p, (int)width, (int)height, history, current, worldPos, prevWorldPos, normals,
+                                                    momentHistory, outColor, outMoment); lc.count++;
+    return cudaGetLastError();
+}
 
 cudaError_t postprocess(const void* in, bool scalarInput, const float4* aux, uint32_t width, uint32_t height, uint32_t outputType,
                         const TbPostProcessSettings& s, uint32_t* hist257, float4* out, uchar4* out8, int numSMs,

@@ -13,4 +13,9 @@ cudaError_t postprocess(const void* in, bool scalarInput, const float4* aux, uin
                         const TbPostProcessSettings& s, uint32_t* hist257, float4* out, uchar4* out8, int numSMs,
                         cudaStream_t stream, LaunchCounter& lc);
 
+// Realtime temporal accumulation (TemporalAccumulationCS.hlsl) on device images, all float4 per pixel.
+cudaError_t temporal_accumulate(const TbTemporalAccumulationParams& p, uint32_t width, uint32_t height, const float4* history,
+                                const float4* current, const float4* worldPos, const float4* prevWorldPos, const float4* normals,
+                                const float4* momentHistory, float4* outColor, float4* outMoment, cudaStream_t stream, LaunchCounter& lc);
+
 } // namespace tbd

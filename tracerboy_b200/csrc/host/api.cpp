@@ -661,6 +661,34 @@ TB_API int tb_postprocess_image(TbHandle* h, const float* inRGBA, const float* a
     return TB_OK;
 }
 
+TB_API int tb_temporal_accumulate_image(TbHandle* h, const TbTemporalAccumulationParams* p, uint32_t width, uint32_t height,
+                                        const float* history, const float* current, const float* worldPos,
+                                        const float* prevWorldPos, const float* normals, const float* momentHistory,
+                                        float* outColor, float* outMoment) {
+    if (!h || !p || !history || !current || !worldPos || !prevWorldPos || !normals || !outColor) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (p->OutputMomentInformation && !momentHistory) return fail(h, TB_ERR_INVALID_ARG, "moment history required");
+    if (width == 0 || height == 0 || (uint64_t)width * height > (1ull << 28)) return fail(h, TB_ERR_INVALID_ARG, "bad resolution");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    const size_t n = (size_t)width * height;
+    std::vector<void*> tmp;
+    struct Guard { std::vector<void*>& v; ~Guard() { free_list(v); } } guard{tmp};
+    const float* src[6] = {history, current, worldPos, prevWorldPos, normals, momentHistory};
+    float4* dev[8] = {};
+    for (int i = 0; i < 8; i++) {
+        if (i < 6 && !src[i]) continue;
+        void* q = nullptr;
+        CUDA_OK(h, cudaMalloc(&q, 16 * n));
+        tmp.push_back(q);
+        dev[i] = (float4*)q;
+        if (i < 6) CUDA_OK(h, cudaMemcpyAsync(q, src[i], 16 * n, cudaMemcpyHostToDevice, h->stream));
+    }
+    CUDA_OK(h, temporal_accumulate(*p, width, height, dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7], h->stream, h->lc));
+    CUDA_OK(h, cudaMemcpyAsync(outColor, dev[6], 16 * n, cudaMemcpyDeviceToHost, h->stream));
+    if (outMoment && p->OutputMomentInformation) CUDA_OK(h, cudaMemcpyAsync(outMoment, dev[7], 16 * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return TB_OK;
+}
+
 TB_API int tb_get_render_stats(TbHandle* h, TbRenderStats* out) {
     if (!h || !out) return fail(h, TB_ERR_INVALID_ARG, "null argument");
     memset(out, 0, sizeof(*out));
