@@ -534,20 +534,28 @@ __device__ __forceinline__ bool try_suspend(PathState& st, int round, const Trav
     return true;
 }
 
-// SHADOW = false: the bounce's extension rays (queue qi -> st.hit). SHADOW = true: the next-event shadow
-// feelers queued by k_shade<0> (st.shadowQueue, st.shRayO/D -> st.shHit); no suspension, no AOVs.
-template <bool SHADOW>
+// KIND 0 (EXT_MAIN): the bounce's extension rays (queue qi -> st.hit, hit / miss queues, suspension).
+// KIND 1 (EXT_SHADOW): the next-event shadow feelers queued by k_shade<0> (st.shadowQueue, st.shRayO/D -> st.shHit).
+// KIND 2 (EXT_WALK): the current rays of the glass / subsurface walkers of walk queue `qi` (0/1) -> st.hit, read by
+//         k_walk_step. Kinds 1 and 2 have no suspension, no AOVs and no output queues.
+#define EXT_MAIN 0
+#define EXT_SHADOW 1
+#define EXT_WALK 2
+template <int KIND>
 __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh, PathState st, int qi, int bounceIsZero, uint32_t outputHeatmap, uint32_t aovMask, uint32_t budgetMain) {
-    const uint32_t count = SHADOW ? st.queueCount[4] : st.queueCount[qi];
-    if (!SHADOW && blockIdx.x == 0 && threadIdx.x == 0) {
+    const uint32_t count = KIND == EXT_SHADOW ? st.queueCount[4] : KIND == EXT_WALK ? st.queueCount[10 + qi] : st.queueCount[qi];
+    if (KIND == EXT_MAIN && blockIdx.x == 0 && threadIdx.x == 0) {
         st.queueCount[qi ^ 1] = 0;                       // next queue starts empty (consumed by k_shade)
         st.queueCount[4] = 0; st.queueCount[5] = 0;      // shadow queue of this bounce + its work counter
-        st.queueCount[10] = 0; st.queueCount[11] = 0;    // walk queue of this bounce + its work counter
+        st.queueCount[10] = 0; st.queueCount[12] = 0;    // walk queue 0 of this bounce (filled by k_shade) + its work counter
     }
-    uint32_t* __restrict__ next = SHADOW ? &st.queueCount[5] : &st.queueCount[2 + qi]; // work counter, zeroed by the previous kernel
-    const uint32_t* __restrict__ queue = SHADOW ? st.shadowQueue : st.queue[qi];
-    const float4* __restrict__ rayO = SHADOW ? st.shRayO : st.rayO;
-    const float4* __restrict__ rayD = SHADOW ? st.shRayD : st.rayD;
+    if (KIND == EXT_WALK && blockIdx.x == 0 && threadIdx.x == 0) {
+        st.queueCount[10 + (qi ^ 1)] = 0; st.queueCount[12 + (qi ^ 1)] = 0; // the other walk queue: filled by the k_walk_step after this kernel
+    }
+    uint32_t* __restrict__ next = KIND == EXT_SHADOW ? &st.queueCount[5] : KIND == EXT_WALK ? &st.queueCount[12 + qi] : &st.queueCount[2 + qi]; // work counter, zeroed by an earlier kernel
+    const uint32_t* __restrict__ queue = KIND == EXT_SHADOW ? st.shadowQueue : KIND == EXT_WALK ? st.walkQueue[qi] : st.queue[qi];
+    const float4* __restrict__ rayO = KIND == EXT_SHADOW ? st.shRayO : st.rayO;
+    const float4* __restrict__ rayD = KIND == EXT_SHADOW ? st.shRayD : st.rayD;
     const float4* __restrict__ pairs = (const float4*)bvh.pairs;
     const float4* __restrict__ tris = (const float4*)bvh.tris;
     const uint32_t lane = threadIdx.x & 31;
@@ -561,11 +569,12 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
         // ---- service phase (whole warp): retire finished rays, park rays over budget, refill idle lanes
         bool retired = false, retiredHit = false;
         if (haveRay && tr.done()) {
-            if (SHADOW) {
+            if (KIND != EXT_MAIN) {
                 HitRec h;
                 tr.result(h);
-                st.shHit[pi] = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
-                st.shHitGeom[pi] = h.geom;
+                float4 rec = make_float4(h.t, h.b1, h.b2, __uint_as_float(h.prim));
+                if (KIND == EXT_SHADOW) { st.shHit[pi] = rec; st.shHitGeom[pi] = h.geom; }
+                else { st.hit[pi] = rec; st.hitGeom[pi] = h.geom; }
                 if (aovMask & AOV_FULL) { uint2 c = st.counters[pi]; c.x += h.tris; c.y += h.boxes; st.counters[pi] = c; }
                 rays++; ntris += h.tris; nboxes += h.boxes;
             } else {
@@ -573,11 +582,11 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
                 retired = true;
             }
             haveRay = false;
-        } else if (!SHADOW && haveRay && steps >= budgetMain) {
+        } else if (KIND == EXT_MAIN && haveRay && steps >= budgetMain) {
             if (try_suspend(st, 0, tr, stack, pi)) haveRay = false;
             else steps = 0; // buffer full: keep going here
         }
-        if (!SHADOW) { // sort retired paths into the hit / miss queues (material-class split of the shading stage)
+        if (KIND == EXT_MAIN) { // sort retired paths into the hit / miss queues (material-class split of the shading stage)
             uint32_t mh = __ballot_sync(0xffffffffu, retired && retiredHit), mm = __ballot_sync(0xffffffffu, retired && !retiredHit);
             if (mh | mm) {
                 uint32_t bh = 0, bm = 0;
@@ -620,7 +629,7 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
             bool wantLeaf = busy && tr.at_leaf();
             uint32_t mB = __ballot_sync(0xffffffffu, busy), mL = __ballot_sync(0xffffffffu, wantLeaf);
             uint32_t nB = __popc(mB), nL = __popc(mL);
-            if (nB == 0 || (!exhausted && nB < REFILL_THRESHOLD) || (!SHADOW && exhausted && iter >= 64u)) break;
+            if (nB == 0 || (!exhausted && nB < REFILL_THRESHOLD) || (KIND == EXT_MAIN && exhausted && iter >= 64u)) break;
             if (2 * nL > nB) {
                 if (wantLeaf) { tr.step_leaf(stack, tris); steps++; }
             } else {
@@ -628,7 +637,7 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
             }
         }
     }
-    flush_stats(st, SHADOW ? 3 : 0, rays, ntris, nboxes);
+    flush_stats(st, KIND == EXT_MAIN ? 0 : 3, rays, ntris, nboxes);
 }
 
 // Resume round `round` (1-based): continues the rays parked by round-1; the last round has no budget.
@@ -809,10 +818,12 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, 
                     bool exitting = (material.Flags & TB_SINGLE_SIDED_MATERIAL_FLAG) != 0;
                     if (!exitting) {
                         // The random walk inside the medium (kernel.glsl:1571-1688) traces up to 100 rays. It runs in
-                        // k_walk, in warps made of walkers only: inline here it ran at 3.2 active lanes per instruction
-                        // on the vw-van scene (profiles/). Hand over what the walk reads besides the path state.
+                        // its own stages (k_extend<EXT_WALK> + k_walk_step, then k_walk), in warps made of walkers only:
+                        // inline here it ran at 3.2 active lanes per instruction on the vw-van scene (profiles/).
+                        // Hand over what the walk reads besides the path state.
+                        float travelDistance = fmaxf(-log_(rng.next()), 0.1f) * maxTravelDistance; // first iteration, kernel.glsl:1573
                         st.walkA[pi] = make_float4(material.absorption.x, material.absorption.y, material.absorption.z, maxTravelDistance);
-                        st.walkB[pi] = make_float4(CurrentIOR, NewIOR, material.roughness, 0.0f);
+                        st.walkB[pi] = make_float4(CurrentIOR, NewIOR, material.roughness, travelDistance);
                         walker = true; walkerPerfectSpec = bPerfectSpec;
                         break;
                     }
@@ -909,7 +920,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, 
                 uint32_t lane = threadIdx.x & 31, base = 0;
                 if (lane == 0) base = atomicAdd(&st.queueCount[10], (uint32_t)__popc(wballot));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (walker) st.walkQueue[base + __popc(wballot & ((1u << lane) - 1u))] = pi;
+                if (walker) st.walkQueue[0][base + __popc(wballot & ((1u << lane) - 1u))] = pi;
             }
         }
         if (STAGE == 0) { // shadow queue, same warp-aggregated append
@@ -931,30 +942,144 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, 
     }
 }
 
-// The random walk of a path inside a subsurface / glass medium (kernel.glsl:1571-1688), for the walkers queued by
-// k_shade. Same persistent-warp scheme as k_extend: every lane owns a walker, the traversal phase steps all lanes'
-// rays together (one code path per iteration), and the service phase runs one walk step for the lanes whose ray has
-// finished: Beer-Lambert, exit refraction / internal reflection or an isotropic scatter, then either the next ray of
-// the walk or the end of the bounce (russian roulette, next queue / finish_path) and a new walker from the queue.
-__global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, FrameConstants fc, PathState st, int qi) {
-    const uint32_t count = st.queueCount[10];
-    uint32_t* __restrict__ next = &st.queueCount[11];
+// ------------------------------------------------------------------------ walk
+// The random walk of a path inside a subsurface / glass medium (kernel.glsl:1571-1688), one ray per step.
+// State word `sw` (rayD.w): bits 0..7 bounce, 8 prevPerfectlySpecular, 9 the bounce's perfect-specular flag, 16..23 k.
+struct Walker {
+    uint32_t pi, sw;
+    Rng rng;
+    f3 org, dir, thr, absorption;
+    float maxTravelDistance, CurrentIOR, NewIOR, roughness, travelDistance;
+};
+__device__ __forceinline__ void walker_load(const PathState& st, const FrameConstants& fc, uint32_t pi, Walker& w) {
+    float4 o = st.rayO[pi], d = st.rayD[pi], t4 = st.thr[pi], a = st.walkA[pi], b = st.walkB[pi];
+    w.pi = pi;
+    w.org = mk3(o.x, o.y, o.z); w.rng.seed = o.w; w.rng.time = fc.time;
+    w.dir = mk3(d.x, d.y, d.z); w.sw = __float_as_uint(d.w);
+    w.thr = mk3(t4.x, t4.y, t4.z);
+    w.absorption = mk3(a.x, a.y, a.z); w.maxTravelDistance = a.w;
+    w.CurrentIOR = b.x; w.NewIOR = b.y; w.roughness = b.z; w.travelDistance = b.w;
+}
+// the walker waits for its next ray: what changed since walker_load goes back to memory
+__device__ __forceinline__ void walker_store(PathState& st, const Walker& w) {
+    st.rayO[w.pi] = make_float4(w.org.x, w.org.y, w.org.z, w.rng.seed);
+    st.rayD[w.pi] = make_float4(w.dir.x, w.dir.y, w.dir.z, __uint_as_float(w.sw));
+    float4 t4 = st.thr[w.pi];
+    st.thr[w.pi] = make_float4(w.thr.x, w.thr.y, w.thr.z, t4.w);
+    st.walkB[w.pi] = make_float4(w.CurrentIOR, w.NewIOR, w.roughness, w.travelDistance);
+}
+// One iteration of the walk loop after its ray came back (t < 0: nothing hit). Returns true when the walk goes on:
+// org / dir / travelDistance then describe the next ray.
+__device__ bool walk_step(const DeviceScene& sc, Walker& w, float t, float b1, float b2, uint32_t geom, uint32_t prim) {
+    const bool noScatter = w.maxTravelDistance == LARGE_NUMBER; // DistancePerScatter < 1/EPSILON otherwise
+    const bool bPerfectSpec = (w.sw & 0x200u) != 0;
+    bool bPrevSpec = (w.sw & 0x100u) != 0;
+    uint32_t k = (w.sw >> 16) & 0xffu;
+    bool walkOn = false;
+    if (t < 0.0f) w.thr = mk3(0.0f); // left the medium without meeting a surface: `break`, kernel.glsl:1584
+    else {
+        Surface ws = surface_from_hit(sc, b1, b2, geom, prim);
+        f3 normal = ws.normal;
+        float tt = fminf(w.travelDistance, t);
+        bool exitting = tt < w.travelDistance || noScatter;
+        if (k == 99u && !exitting) w.thr = mk3(0.0f);
+        f3 RayPoint = w.org + w.dir * tt;
+        w.org = RayPoint + normal * EPSILON;
+        w.thr *= exp3((-tt) * w.absorption);
+        bool giveUp = false;
+        if (exitting) {
+            float RdotN = dot(normal, w.dir);
+            if (RdotN >= 0.0f) { normal = -normal; RdotN = -RdotN; }
+            RefractResult rr = refract_or_reflect(w.rng, w.dir, normal, w.NewIOR / w.CurrentIOR, RdotN, bPerfectSpec, w.roughness, bPrevSpec);
+            if (rr == GIVE_UP) giveUp = true;
+            if (rr == REFLECTED) exitting = false;
+        } else {
+            // GenerateRandomDirection(), kernel.glsl:991-999
+            float u1 = w.rng.next(), u2 = w.rng.next();
+            float r = sqrtf(1.0f - u1 * u1);
+            float phi = 2.0f * 3.14f * u2;
+            w.dir = mk3(cos_(phi) * r, sin_(phi) * r, u1);
+            w.thr /= 1.0f;
+        }
+        k++;
+        walkOn = !giveUp && k < 100u && !exitting;
+    }
+    w.sw = (w.sw & 0x0000feffu) | (bPrevSpec ? 0x100u : 0u) | (k << 16);
+    if (walkOn) w.travelDistance = fmaxf(-log_(w.rng.next()), 0.1f) * w.maxTravelDistance;
+    return walkOn;
+}
+// The walk is over: `continue` (kernel.glsl:1690) to the top of the next loop iteration — bounce limit, then russian
+// roulette (kernel.glsl:1286-1302). Returns true when the path joins the next bounce's queue.
+__device__ bool walk_finish(const FrameConstants& fc, PathState& st, Walker& w) {
+    float4 t4 = st.thr[w.pi], c4 = st.col[w.pi];
+    const bool bPrevSpec = (w.sw & 0x100u) != 0;
+    int bounce = (int)(w.sw & 0xffu) + 1;
+    bool terminated = bounce >= fc.settings.MaxBounces;
+    if (!terminated && bounce >= 2) {
+        float p = fmaxf(fmaxf(w.thr.x, w.thr.y), w.thr.z);
+        p = fmaxf(p, EPSILON);
+        if (p < w.rng.next()) terminated = true;
+        else w.thr *= 1.0f / p;
+    }
+    if (terminated) { finish_path(fc, st, w.pi, mk3(c4.x, c4.y, c4.z), t4.w, w.rng); return false; }
+    st.rayO[w.pi] = make_float4(w.org.x, w.org.y, w.org.z, w.rng.seed);
+    st.rayD[w.pi] = make_float4(w.dir.x, w.dir.y, w.dir.z, __uint_as_float(pack_state(bounce, bPrevSpec)));
+    st.thr[w.pi] = make_float4(w.thr.x, w.thr.y, w.thr.z, t4.w);
+    return true;
+}
+__device__ __forceinline__ void append_warp(uint32_t* counter, uint32_t* queue, bool pred, uint32_t value) {
+    uint32_t ballot = __ballot_sync(0xffffffffu, pred);
+    if (ballot) {
+        uint32_t lane = threadIdx.x & 31, base = 0;
+        if (lane == 0) base = atomicAdd(counter, (uint32_t)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pred) queue[base + __popc(ballot & ((1u << lane) - 1u))] = value;
+    }
+}
+
+// Walk round `wr`: one step for every walker of walk queue wr, whose rays k_extend<EXT_WALK> has just traced. Walkers
+// that go on wait in queue wr ^ 1 for the next round; the others end their bounce. No traversal code in here, so the
+// (frequent) one- and two-ray walks of clear glass run at the occupancy and coherence of the regular stages.
+__global__ void __launch_bounds__(256) k_walk_step(DeviceScene sc, FrameConstants fc, PathState st, int qi, int wr) {
+    const uint32_t count = st.queueCount[10 + wr];
+    const uint32_t countUp = (count + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < countUp; i += gridDim.x * blockDim.x) {
+        bool walkOn = false, alive = false;
+        uint32_t pi = 0;
+        if (i < count) {
+            pi = st.walkQueue[wr][i];
+            Walker w;
+            walker_load(st, fc, pi, w);
+            float4 h = st.hit[pi];
+            walkOn = walk_step(sc, w, h.x, h.y, h.z, st.hitGeom[pi], __float_as_uint(h.w));
+            if (walkOn) walker_store(st, w);
+            else alive = walk_finish(fc, st, w);
+        }
+        append_warp(&st.queueCount[10 + (wr ^ 1)], st.walkQueue[wr ^ 1], walkOn, pi);
+        append_warp(&st.queueCount[qi ^ 1], st.queue[qi ^ 1], alive, pi);
+    }
+}
+
+// The long tail: walkers still inside their medium after the wavefront rounds (total internal reflection in closed
+// glass bodies, real subsurface scattering: up to 100 rays). Same persistent-warp scheme as k_extend: every lane owns
+// a walker, the traversal phase steps all lanes' rays together (one code path per iteration), and the service phase
+// runs walk_step for the lanes whose ray has finished, then either starts the walker's next ray or ends its bounce
+// and takes a new walker from queue `wr`.
+__global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, FrameConstants fc, PathState st, int qi, int wr) {
+    const uint32_t count = st.queueCount[10 + wr];
+    uint32_t* __restrict__ next = &st.queueCount[12 + wr];
     const float4* __restrict__ pairs = (const float4*)bvh.pairs;
     const float4* __restrict__ tris = (const float4*)bvh.tris;
     const uint32_t lane = threadIdx.x & 31;
-    const int MaxBounces = fc.settings.MaxBounces;
     uint32_t rays = 0, ntris = 0, nboxes = 0;
     Traversal tr;
     uint32_t stack[TB_STACK_DEPTH];
     tr.sp = 0; tr.cur = TB_NO_NODE;
     bool have = false, exhausted = false;
-    // walker state
-    uint32_t pi = 0;
-    Rng rng; rng.seed = 0.0f; rng.time = fc.time;
-    f3 org = mk3(0.0f), dir = mk3(0.0f), thr = mk3(0.0f), absorption = mk3(0.0f);
-    float maxTravelDistance = 0.0f, CurrentIOR = 1.0f, NewIOR = 1.0f, roughness = 0.0f, travelDistance = 0.0f;
-    uint32_t sw = 0; // bounce | prevSpec << 8 | perfectSpec << 9
-    int k = 0;
+    Walker w;
+    w.pi = 0; w.sw = 0; w.rng.seed = 0.0f; w.rng.time = fc.time;
+    w.org = w.dir = w.thr = w.absorption = mk3(0.0f);
+    w.maxTravelDistance = w.roughness = w.travelDistance = 0.0f; w.CurrentIOR = w.NewIOR = 1.0f;
     while (true) {
         // ---- service phase
         bool alive = false;
@@ -962,72 +1087,11 @@ __global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, 
             HitRec h;
             tr.result(h);
             rays++; ntris += h.tris; nboxes += h.boxes;
-            if (fc.aovMask & AOV_FULL) { uint2 c = st.counters[pi]; c.x += h.tris; c.y += h.boxes; st.counters[pi] = c; }
-            const bool noScatter = maxTravelDistance == LARGE_NUMBER; // DistancePerScatter < 1/EPSILON otherwise
-            const bool bPerfectSpec = (sw & 0x200u) != 0;
-            bool bPrevSpec = (sw & 0x100u) != 0;
-            bool walkOn = false;
-            if (h.t < 0.0f) thr = mk3(0.0f); // left the medium without a surface: `break`, kernel.glsl:1584
-            else {
-                Surface ws = surface_from_hit(sc, h.b1, h.b2, h.geom, h.prim);
-                f3 normal = ws.normal;
-                float tt = fminf(travelDistance, h.t);
-                bool exitting = tt < travelDistance || noScatter;
-                if (k == 99 && !exitting) thr = mk3(0.0f);
-                f3 RayPoint = org + dir * tt;
-                org = RayPoint + normal * EPSILON;
-                thr *= exp3((-tt) * absorption);
-                bool giveUp = false;
-                if (exitting) {
-                    float RdotN = dot(normal, dir);
-                    if (RdotN >= 0.0f) { normal = -normal; RdotN = -RdotN; }
-                    RefractResult rr = refract_or_reflect(rng, dir, normal, NewIOR / CurrentIOR, RdotN, bPerfectSpec, roughness, bPrevSpec);
-                    if (rr == GIVE_UP) giveUp = true;
-                    if (rr == REFLECTED) exitting = false;
-                } else {
-                    // GenerateRandomDirection(), kernel.glsl:991-999
-                    float u1 = rng.next(), u2 = rng.next();
-                    float r = sqrtf(1.0f - u1 * u1);
-                    float phi = 2.0f * 3.14f * u2;
-                    dir = mk3(cos_(phi) * r, sin_(phi) * r, u1);
-                    thr /= 1.0f;
-                }
-                k++;
-                walkOn = !giveUp && k < 100 && !exitting;
-            }
-            sw = (sw & ~0x100u) | (bPrevSpec ? 0x100u : 0u);
-            if (walkOn) {
-                travelDistance = fmaxf(-log_(rng.next()), 0.1f) * maxTravelDistance;
-                tr.begin(bvh, org, dir, MIN_T, FAR_T);
-            } else {
-                // the walk is over; `continue` (kernel.glsl:1690) to the top of the next loop iteration:
-                // bounce limit, then russian roulette (kernel.glsl:1286-1302)
-                have = false;
-                float4 t4 = st.thr[pi], c4 = st.col[pi];
-                int bounce = (int)(sw & 0xffu) + 1;
-                bool terminated = bounce >= MaxBounces;
-                if (!terminated && bounce >= 2) {
-                    float p = fmaxf(fmaxf(thr.x, thr.y), thr.z);
-                    p = fmaxf(p, EPSILON);
-                    if (p < rng.next()) terminated = true;
-                    else thr *= 1.0f / p;
-                }
-                if (terminated) finish_path(fc, st, pi, mk3(c4.x, c4.y, c4.z), t4.w, rng);
-                else {
-                    st.rayO[pi] = make_float4(org.x, org.y, org.z, rng.seed);
-                    st.rayD[pi] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(pack_state(bounce, bPrevSpec)));
-                    st.thr[pi] = make_float4(thr.x, thr.y, thr.z, t4.w);
-                    alive = true;
-                }
-            }
+            if (fc.aovMask & AOV_FULL) { uint2 c = st.counters[w.pi]; c.x += h.tris; c.y += h.boxes; st.counters[w.pi] = c; }
+            if (walk_step(sc, w, h.t, h.b1, h.b2, h.geom, h.prim)) tr.begin(bvh, w.org, w.dir, MIN_T, FAR_T);
+            else { alive = walk_finish(fc, st, w); have = false; }
         }
-        uint32_t ballot = __ballot_sync(0xffffffffu, alive);
-        if (ballot) { // survivors join the next bounce's queue
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&st.queueCount[qi ^ 1], (uint32_t)__popc(ballot));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (alive) st.queue[qi ^ 1][base + __popc(ballot & ((1u << lane) - 1u))] = pi;
-        }
+        append_warp(&st.queueCount[qi ^ 1], st.queue[qi ^ 1], alive, w.pi); // survivors join the next bounce's queue
         uint32_t idle = __ballot_sync(0xffffffffu, !have);
         if (idle && !exhausted) {
             uint32_t base = 0;
@@ -1036,16 +1100,8 @@ __global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, 
             if (!have) {
                 uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
                 if (i < count) {
-                    pi = st.walkQueue[i];
-                    float4 o = st.rayO[pi], d = st.rayD[pi], t4 = st.thr[pi], a = st.walkA[pi], b = st.walkB[pi];
-                    org = mk3(o.x, o.y, o.z); rng.seed = o.w;
-                    dir = mk3(d.x, d.y, d.z); sw = __float_as_uint(d.w);
-                    thr = mk3(t4.x, t4.y, t4.z);
-                    absorption = mk3(a.x, a.y, a.z); maxTravelDistance = a.w;
-                    CurrentIOR = b.x; NewIOR = b.y; roughness = b.z;
-                    k = 0;
-                    travelDistance = fmaxf(-log_(rng.next()), 0.1f) * maxTravelDistance;
-                    tr.begin(bvh, org, dir, MIN_T, FAR_T);
+                    walker_load(st, fc, st.walkQueue[wr][i], w);
+                    tr.begin(bvh, w.org, w.dir, MIN_T, FAR_T);
                     have = true;
                 }
             }
@@ -1164,7 +1220,7 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
             const char* e = getenv("TB_SUSPEND"); suspendMode = e ? atoi(e) : 1;
             if (const char* bs = getenv("TB_BUDGETS")) sscanf(bs, "%u,%u,%u", &budgetMain, &budgets[0], &budgets[1]);
         }
-        k_extend<false><<<blocks, 128, 0, stream>>>(bvh, st, qi, b == 0, heat, fc.aovMask, suspendMode ? budgetMain : 0xffffffffu); lc.count++;
+        k_extend<EXT_MAIN><<<blocks, 128, 0, stream>>>(bvh, st, qi, b == 0, heat, fc.aovMask, suspendMode ? budgetMain : 0xffffffffu); lc.count++;
         if (suspendMode) {
             uint32_t rblocks = (st.susCapacity + 127) / 128;
             if (rblocks > sms * 4) rblocks = sms * 4;
@@ -1188,7 +1244,7 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
                                   else k_shade<STG, false><<<blocks, 128, 0, stream>>>(bvh, sc, fc, st, qi); lc.count++; } while (0)
         if (nee && shadowMode) {
             TB_LAUNCH_SHADE(0);
-            k_extend<true><<<blocks, 128, 0, stream>>>(bvh, st, qi, 0, 0, fc.aovMask, 0xffffffffu); lc.count++;
+            k_extend<EXT_SHADOW><<<blocks, 128, 0, stream>>>(bvh, st, qi, 0, 0, fc.aovMask, 0xffffffffu); lc.count++;
             TB_LAUNCH_SHADE(1);
         } else if (nee) {
             TB_LAUNCH_SHADE(2);
@@ -1196,9 +1252,16 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
             TB_LAUNCH_SHADE(3);
         }
 #undef TB_LAUNCH_SHADE
-        if (sss) { // the bounce's glass / subsurface walkers (queued by the k_shade launches above)
+        if (sss) { // the bounce's glass / subsurface walkers (queued by the k_shade launches above into walk queue 0)
+            static int roundsEnv = -2; // tuning knob (results never depend on it)
+            if (roundsEnv == -2) { const char* e = getenv("TB_WALK_ROUNDS"); roundsEnv = e ? atoi(e) : -1; }
+            const int rounds = roundsEnv >= 0 ? roundsEnv : opts.walkRounds; // wavefront rounds before the persistent tail (which reads queue rounds & 1)
+            for (int r = 0; r < rounds; r++) {
+                k_extend<EXT_WALK><<<blocks, 128, 0, stream>>>(bvh, st, r & 1, 0, 0, fc.aovMask, 0xffffffffu); lc.count++;
+                k_walk_step<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(sc, fc, st, qi, r & 1); lc.count++;
+            }
             uint32_t wblocks = blocks > sms * 4 ? sms * 4 : blocks;
-            k_walk<<<wblocks, 128, 0, stream>>>(bvh, sc, fc, st, qi); lc.count++;
+            k_walk<<<wblocks, 128, 0, stream>>>(bvh, sc, fc, st, qi, rounds & 1); lc.count++;
         }
         if (timers) cudaEventRecord(timers->next(KernelTimers::END), stream);
     }

@@ -18,7 +18,7 @@ struct PathState {
     float4* neighbor = nullptr;    // neighbour camera ray origin (bounce 0 only)
     float4* neighborDir = nullptr; // neighbour camera ray direction
     uint32_t* queue[2] = {nullptr, nullptr};
-    uint32_t* queueCount = nullptr; // [0..1] queue sizes, [2..3] k_extend work counters, [4] shadow queue size, [5] its work counter, [6..9] hit/miss queue sizes, [10] walk queue size, [11] its work counter
+    uint32_t* queueCount = nullptr; // [0..1] queue sizes, [2..3] k_extend work counters, [4] shadow queue size, [5] its work counter, [6..9] hit/miss queue sizes, [10..11] walk queue sizes, [12..13] their work counters
     // the bounce's paths sorted by k_extend into "hit something" / "left the scene"; counters [6..9] by queue parity
     uint32_t* hitQueue = nullptr;
     uint32_t* missQueue = nullptr;
@@ -28,10 +28,12 @@ struct PathState {
     float4* shRayD = nullptr;
     float4* shHit = nullptr;       // t, b1, b2, bits(primitiveIndex) of the first hit along the shadow feeler
     uint32_t* shHitGeom = nullptr;
-    // glass / subsurface walkers: queued by k_shade, walked by k_walk (queueCount[10] size, [11] work counter)
-    uint32_t* walkQueue = nullptr;
+    // glass / subsurface walkers: queued by k_shade, advanced one ray at a time by k_extend<WALK> + k_walk_step for
+    // the first rounds, the long tail finished by the persistent k_walk. Ping-pong queues: sizes queueCount[10..11],
+    // work counters [12..13].
+    uint32_t* walkQueue[2] = {nullptr, nullptr};
     float4* walkA = nullptr;       // absorption.xyz, maxTravelDistance
-    float4* walkB = nullptr;       // CurrentIOR, NewIOR, roughness, -
+    float4* walkB = nullptr;       // CurrentIOR, NewIOR, roughness, travelDistance of the ray in flight
     // suspended long rays: two ping-pong record buffers, one counter per round
     uint32_t* susBuf[2] = {nullptr, nullptr};
     uint32_t* susCount = nullptr;   // 4 counters
@@ -85,6 +87,7 @@ struct KernelTimers {
 // scheduling knobs; none of them changes a result
 struct RenderOptions {
     int shadowMode = 2; // next-event shadow rays: 0 traced inline in k_shade, 1 own wavefront stage, 2 automatic
+    int walkRounds = 2; // glass / subsurface walk: wavefront rounds (k_extend<EXT_WALK> + k_walk_step) before the persistent tail kernel
     bool sceneHasSSS = true; // any material with the subsurface flag (selects the k_shade variant with the inline random walk)
 };
 

@@ -395,7 +395,7 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
         // private state per slot: 5 float4 + hitGeom + 2 float4 + 2 queues + staging (float4+float+float4+float)
         // + 2 suspension buffers. Automatic policy: as many slots as fit ~12 GB, between 4 and 8 (more
         // buys nothing once no kernel has a long tail, see profiles/README.md).
-        size_t perSlot = n * (80 + 4 + 32 + 8 + 40 + 56 + 8 + 36) + 2 * (n / 16 + 1024) * 448;
+        size_t perSlot = n * (80 + 4 + 32 + 8 + 40 + 56 + 8 + 40) + 2 * (n / 16 + 1024) * 448;
         uint32_t fif = h->framesInFlight;
         if (fif == 0) {
             size_t fit = ((size_t)12 << 30) / perSlot;
@@ -415,7 +415,7 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
         CUDA_OK(h, alloc((void**)&p.hitQueue, 4 * n)); CUDA_OK(h, alloc((void**)&p.missQueue, 4 * n));
         CUDA_OK(h, alloc((void**)&p.shadowQueue, 4 * n)); CUDA_OK(h, alloc((void**)&p.shRayO, 16 * n)); CUDA_OK(h, alloc((void**)&p.shRayD, 16 * n));
         CUDA_OK(h, alloc((void**)&p.shHit, 16 * n)); CUDA_OK(h, alloc((void**)&p.shHitGeom, 4 * n));
-        CUDA_OK(h, alloc((void**)&p.walkQueue, 4 * n)); CUDA_OK(h, alloc((void**)&p.walkA, 16 * n)); CUDA_OK(h, alloc((void**)&p.walkB, 16 * n));
+        CUDA_OK(h, alloc((void**)&p.walkQueue[0], 4 * n)); CUDA_OK(h, alloc((void**)&p.walkQueue[1], 4 * n)); CUDA_OK(h, alloc((void**)&p.walkA, 16 * n)); CUDA_OK(h, alloc((void**)&p.walkB, 16 * n));
         p.susCapacity = (uint32_t)(n / 16 + 1024);
         CUDA_OK(h, alloc((void**)&p.susBuf[0], (size_t)p.susCapacity * 448)); CUDA_OK(h, alloc((void**)&p.susBuf[1], (size_t)p.susCapacity * 448));
         CUDA_OK(h, alloc((void**)&p.susCount, 16));
