@@ -385,7 +385,7 @@ TB_API int tb_reset_render_stats(TbHandle* h);
  * overhead; off by default). Results appear in TbRenderStats.Extend/ShadeMilliseconds. */
 TB_API int tb_set_profiling(TbHandle* h, int enable);
 /* Number of frames (samples) kept in flight on independent CUDA streams (0 = automatic:
- * as many as fit a 12 GB budget, between 4 and 8). The result does not depend on it: samples are added to the accumulation buffer in frame order. */
+ * as many as fit a third of the free device memory, between 4 and 16). The result does not depend on it: samples are added to the accumulation buffer in frame order. */
 TB_API int tb_set_frames_in_flight(TbHandle* h, uint32_t n);
 /* Next-event shadow rays: 0 = traced inline in the shading kernel, 1 = own wavefront stage
  * (shade A -> shadow traversal -> shade B), 2 = automatic (default; by triangle count). Scheduling

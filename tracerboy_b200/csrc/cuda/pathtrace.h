@@ -87,7 +87,7 @@ struct KernelTimers {
 // scheduling knobs; none of them changes a result
 struct RenderOptions {
     int shadowMode = 2; // next-event shadow rays: 0 traced inline in k_shade, 1 own wavefront stage, 2 automatic
-    int walkRounds = 2; // glass / subsurface walk: wavefront rounds (k_extend<EXT_WALK> + k_walk_step) before the persistent tail kernel
+    int walkRounds = 1; // glass / subsurface walk: wavefront rounds (k_extend<EXT_WALK> + k_walk_step) before the persistent tail kernel
     bool sceneHasSSS = true; // any material with the subsurface flag (selects the k_shade variant with the inline random walk)
 };
 
