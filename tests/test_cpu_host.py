@@ -157,3 +157,83 @@ def test_sample_sharding_world_size_2_gloo(cornell, tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "SHARD_OK" in outs[0]
+
+
+CURVES_PBRT = """LookAt 0 0 8  1.5 0.5 0  0 1 0
+Camera "perspective" "float fov" [40]
+WorldBegin
+LightSource "distant" "point from" [0 5 5] "point to" [0 0 0] "rgb L" [3 3 3]
+Material "matte" "rgb Kd" [0.5 0.4 0.3]
+Shape "curve" "string type" "cylinder" "point P" [0 0 0  1 1 0  2 -1 0  3 0 0] "float width0" 0.1 "float width1" 0.05
+Shape "curve" "string type" "cylinder" "point P" [0 1 0  1 2 0  2 0 0  3 1 0  4 2 1] "float width0" 0.2 "float width1" 0.2
+Material "matte" "rgb Kd" [0.1 0.9 0.3]
+Shape "curve" "string type" "cylinder" "point P" [0 -1 0  1 -1 1  2 -1 -1  3 -1 0] "float width0" 0.3 "float width1" 0.1
+Shape "trianglemesh" "point P" [-5 -2 -5  5 -2 -5  5 -2 5  -5 -2 5] "integer indices" [0 1 2 0 2 3]
+WorldEnd
+"""
+
+
+def _read_tbscene_geometry(path):
+    import struct
+    raw = open(path, "rb").read()
+    magic, version, flip, ng, nv, ni, nm, nl, nt, nimg, env = struct.unpack_from("<8sII7Ii", raw, 0)
+    off = 8 + 4 + 4 + 7 * 4 + 4 + 14 * 4 + 3 * 16 + 12 + 8 * 4
+    geoms = np.frombuffer(raw, np.uint32, ng * 8, off).reshape(ng, 8); off += ng * 32
+    pos = np.frombuffer(raw, np.float32, nv * 3, off).reshape(nv, 3); off += nv * 12
+    vtx = np.frombuffer(raw, np.float32, nv * 8, off).reshape(nv, 8); off += nv * 32
+    idx = np.frombuffer(raw, np.uint32, ni, off)
+    return geoms, pos, vtx, idx
+
+
+def test_curve_tessellation_matches_the_reference_rules(tmp_path, built):
+    """LoadScene's hair path (TracerBoy.cpp:1426-1524, Curves.cpp): three 3-vertex rings per cubic segment, ring faces
+    that always index the first segment's rings, the (1.0 - 1) tangent term, and the ten-pass merge loop that
+    re-tessellates a curve without a mergeable successor. Positions against an independent float64 restatement."""
+    import tracerboy_b200 as tb
+    from tracerboy_b200 import build
+    if not os.path.exists(os.path.join(build.LIB, "libtb_pbrtimport.so")):
+        pytest.skip("PBRT importer not built (needs the reference mount at build time)")
+    src, dst = str(tmp_path / "c.pbrt"), str(tmp_path / "c.tbscene")
+    open(src, "w").write(CURVES_PBRT)
+    tb.convert_scene(src, dst)
+    geoms, pos, vtx, idx = _read_tbscene_geometry(dst)
+    # geometry 0: curve A once + curve B on each of the nine remaining passes; geometry 1: the lone curve C ten times
+    assert geoms.shape[0] == 3
+    assert (geoms[0][4] // 3, geoms[1][4] // 3, geoms[2][4] // 3) == (12 + 9 * 24, 10 * 12, 2)
+    assert (geoms[0][2], geoms[1][2]) == (9 + 9 * 18, 10 * 9)
+    assert geoms[0][0] != geoms[1][0]  # two materials
+
+    def rings(P, w0, w1):
+        P = np.asarray(P, np.float64).reshape(-1, 3)
+        nseg = len(P) - 3
+        out = []
+        for seg in range(nseg):
+            p0, p1, p2, p3 = P[seg:seg + 4]
+            for ring in range(3):
+                t = seg / nseg + ring / nseg / 3
+                radius = t * w1 + (1 - t) * w0
+                q = lambda a, b, c: (a * (1 - t) + b * t) * (1 - t) + (b * (1 - t) + c * t) * t
+                centre = q(p0, p1, p2) * (1 - t) + q(p1, p2, p3) * t
+                tangent = (p2 - p1) * 6 * t * (1 - t) + (p3 - p2) * 3 * t * t   # first term: * (1.0 - 1)
+                with np.errstate(invalid="ignore"):
+                    fwd = tangent / np.linalg.norm(tangent)
+                up = np.array([0, 1, 0.0]) if fwd[1] < 0.99 else np.array([0, 0, 1.0])
+                n0 = np.cross(fwd, up); n0 /= np.linalg.norm(n0)
+                n1 = np.cross(n0, fwd); n1 /= np.linalg.norm(n1)
+                for v in range(3):
+                    th = v * (3.14 * 2.0 / 3)
+                    out.append(centre + (np.cos(th) * n0 + np.sin(th) * n1) * radius)
+        return np.array(out)
+    first = int(geoms[1][1])
+    want = rings([0, -1, 0, 1, -1, 1, 2, -1, -1, 3, -1, 0], 0.3, 0.1)
+    got = pos[first:first + 9]
+    # ring 0 sits at t = 0 where the reference's tangent is exactly zero: normalize(0) = NaN, reproduced as is
+    assert np.isnan(got[:3]).all() and np.isnan(want[:3]).all()
+    assert np.allclose(got[3:], want[3:], atol=1e-5)
+    assert np.array_equal(pos[first + 9:first + 18][3:], got[3:])  # second pass: the same curve again
+    # faces of the first tessellation: ring r joins ring r-1, vertex offsets relative to this pass
+    f = idx[int(geoms[1][3]):int(geoms[1][3]) + 36].reshape(12, 3)
+    assert f[0].tolist() == [3, 4, 0] and f[1].tolist() == [4, 0, 1] and f[5].tolist() == [3, 2, 0] and f[6].tolist() == [6, 7, 3]
+    # segment 1 of curve B reuses segment 0's ring indices (loopStartIndex ignores curveIndex)
+    gb = idx[int(geoms[0][3]) + 36:int(geoms[0][3]) + 36 + 72].reshape(24, 3)
+    assert np.array_equal(gb[:12], gb[12:])

@@ -142,6 +142,25 @@ def test_vwvan_render_bit_exact(vwvan):
         assert (hg[f].view(np.uint32) == ho[f].view(np.uint32)).all(), f
 
 
+def test_curves_scene_bit_exact(tmp_path, built):
+    """Hair / curve shapes through the importer's tessellation (TracerBoy.cpp:1426-1524): the tubes' first ring is NaN
+    (the reference's tangent is zero at t = 0), so the builder and the traversal see NaN triangles; BVH bytes, every
+    buffer and the counters still equal the oracle's."""
+    import tracerboy_b200 as tb
+    from tracerboy_b200 import build
+    from test_cpu_host import CURVES_PBRT
+    if not os.path.exists(os.path.join(build.LIB, "libtb_pbrtimport.so")):
+        pytest.skip("PBRT importer not built (needs the reference mount at build time)")
+    src, dst = str(tmp_path / "c.pbrt"), str(tmp_path / "c.tbscene")
+    open(src, "w").write(CURVES_PBRT)
+    tb.convert_scene(src, dst)
+    g, o = _pair(dst, 200, 150)
+    assert np.array_equal(g.GetBVH(), o.GetBVH())
+    s = tb.get_default_output_settings()
+    _compare_render(g, o, s, 3)
+    assert (g.Readback(tb.BufferKind.PRIMARY_HIT_IDS)[..., 0] < 2).sum() > 100  # the tubes are visible
+
+
 def test_full_size_properties_vwvan_4k(vwvan):
     """configs[3] at its full 3840x2160: progressive accumulation is exact (3 + 5 == 8 samples), the weight
     channel counts the samples, radiance is finite, and frames in flight do not change a bit."""

@@ -186,6 +186,63 @@ struct Importer {
         return m;
     }
 
+    // Hair / curve shapes -> triangle tubes, TracerBoy.cpp:1426-1524 with Curves.cpp:3-52. Every quirk is kept because it
+    // decides the geometry the tracer sees: three rings of three vertices per cubic segment and none at the segment's
+    // end; ring faces index the *first* segment's rings whatever the segment (loopStartIndex ignores curveIndex);
+    // the tangent's first term is multiplied by (1.0 - 1); the radius lerp runs from width0 to width1 *widths*, not
+    // half widths; and the merge loop runs ten times whether or not the next shape is a matching curve, so a curve
+    // with no mergeable successor is tessellated again on every remaining pass.
+    static pbrt::vec3f quad_bezier(const pbrt::vec3f& a, const pbrt::vec3f& b, const pbrt::vec3f& c, float t) {
+        return (a * (1.0f - t) + b * t) * (1.0f - t) + (b * (1.0f - t) + c * t) * t;
+    }
+    pbrt::TriangleMesh::SP tessellate_curves(std::vector<pbrt::Shape::SP>& shapes, size_t& si, pbrt::Curve::SP curve) {
+        using pbrt::vec3f;
+        auto mesh = std::make_shared<pbrt::TriangleMesh>();
+        const uint32_t ringVerts = 3, ringsPerSegment = 3;
+        const float radiansPerVert = 3.14 * 2.0 / (float)(ringVerts);
+        for (int pass = 0; pass < 10; pass++) {
+            if (pass > 0 && si + 1 < shapes.size()) {
+                auto nextCurve = std::dynamic_pointer_cast<pbrt::Curve>(shapes[si + 1]);
+                if (nextCurve && nextCurve->material == curve->material && nextCurve->areaLight == curve->areaLight) { curve = nextCurve; si++; }
+            }
+            const uint32_t vertexOffset = (uint32_t)mesh->vertex.size();
+            mesh->material = curve->material;
+            mesh->areaLight = curve->areaLight;
+            if (curve->P.size() < 4) throw std::runtime_error("curve needs at least 4 control points (TracerBoy.cpp:1467)");
+            const uint32_t segments = (uint32_t)curve->P.size() - 3;
+            const float stepPerSegment = 1.0 / (float)segments;
+            const float stepPerRing = stepPerSegment / (float)ringsPerSegment;
+            for (uint32_t seg = 0; seg < segments; seg++) {
+                const vec3f p0 = curve->P[seg], p1 = curve->P[seg + 1], p2 = curve->P[seg + 2], p3 = curve->P[seg + 3];
+                for (uint32_t ring = 0; ring < ringsPerSegment; ring++) {
+                    const float t = seg * stepPerSegment + ring * stepPerRing;
+                    const float radius = t * curve->width1 + (1.0 - t) * curve->width0;
+                    const vec3f centre = quad_bezier(p0, p1, p2, t) * (1.0f - t) + quad_bezier(p1, p2, p3, t) * t;
+                    const vec3f tangent = (p1 - p0) * 3.0 * (1.0 - t) * (1.0 - 1) + (p2 - p1) * 6.0 * t * (1.0 - t) + (p3 - p2) * 3.0 * t * t;
+                    const vec3f forward = pbrt::math::normalize(tangent);
+                    const vec3f up = forward.y < 0.99f ? vec3f(0, 1, 0) : vec3f(0, 0, 1);
+                    const vec3f n0 = pbrt::math::normalize(pbrt::math::cross(forward, up));
+                    const vec3f n1 = pbrt::math::normalize(pbrt::math::cross(n0, forward));
+                    for (uint32_t v = 0; v < ringVerts; v++) {
+                        const float theta = v * radiansPerVert;
+                        const vec3f normal = std::cos(theta) * n0 + std::sin(theta) * n1;
+                        mesh->vertex.push_back(centre + normal * radius);
+                        mesh->normal.push_back(normal);
+                        mesh->tangents.push_back(forward);
+                    }
+                    if (ring == 0) continue; // the first ring has no previous ring to form faces with
+                    const uint32_t ringStart = ringVerts * ring + vertexOffset, prevStart = ringVerts * (ring - 1) + vertexOffset;
+                    for (uint32_t f = 0; f < ringVerts; f++) {
+                        const uint32_t l = f, r = f == ringVerts - 1 ? 0 : f + 1;
+                        mesh->index.push_back(pbrt::vec3i(ringStart + l, ringStart + r, prevStart + l));
+                        mesh->index.push_back(pbrt::vec3i(ringStart + r, prevStart + l, prevStart + r));
+                    }
+                }
+            }
+        }
+        return mesh;
+    }
+
     void run(pbrt::Scene::SP scene) {
         if (scene->cameras.empty()) throw std::runtime_error("scene has no camera");
         // camera, TracerBoy.cpp:1243-1272
@@ -207,9 +264,10 @@ struct Importer {
         // shapes: every top-level shape goes into the one global BLAS (:1361-1366). The SW
         // path renders only that BLAS (TracerBoy.cpp:2862), so instances are not emitted.
         auto& world = scene->world;
-        for (auto& shape : world->shapes) {
-            auto mesh = std::dynamic_pointer_cast<pbrt::TriangleMesh>(shape);
-            if (!mesh) continue; // curves: tessellation (:1426-1524) not implemented; others skipped as in the reference
+        for (size_t si = 0; si < world->shapes.size(); si++) {
+            auto mesh = std::dynamic_pointer_cast<pbrt::TriangleMesh>(world->shapes[si]);
+            if (auto curve = std::dynamic_pointer_cast<pbrt::Curve>(world->shapes[si])) mesh = tessellate_curves(world->shapes, si, curve);
+            if (!mesh) continue; // spheres, disks, ...: skipped as in the reference
             pbrt::vec3f emissive(0.f);
             std::vector<uint32_t> idx(mesh->index.size() * 3);
             for (size_t i = 0; i < mesh->index.size(); i++) {
