@@ -406,6 +406,15 @@ TB_API int tb_postprocess(TbHandle* h, uint32_t outputType, const TbPostProcessS
 /* The same operator on caller-provided HOST images (float4 per pixel; aux may be NULL = zeros and is only read
  * by LiveWaves). outRGBA: float4 per pixel; outRGBA8 (may be NULL): 4 bytes per pixel; hist (may be NULL):
  * 256 words; avgLum (may be NULL): 1 float. */
+/* Image files (the reference captures its back buffer as PNG, D3D12App.cpp:341-363). The extension
+ * selects the format: ".png" writes an 8-bit buffer (TB_BUF_BACKBUFFER_RGBA8, i.e. after tb_postprocess);
+ * ".exr" (OpenEXR scanline, uncompressed, 32-bit float) and ".pfm" write a float buffer: TB_BUF_RESOLVED_RGB,
+ * TB_BUF_POSTPROCESS_RGBA, TB_BUF_ACCUM_RGBW or an AOV (float4 kinds keep their 4th channel as A in .exr). */
+TB_API int tb_save_image(TbHandle* h, uint32_t kind, const char* path);
+/* Host-only: the same writers on a caller-provided image (top row first; 4 x 8 bit for .png, 3 or 4 x float for .exr / .pfm). */
+TB_API int tb_write_image(const char* path, const void* pixels, uint32_t width, uint32_t height, uint32_t channels,
+                          uint32_t bytesPerChannel, char* err, size_t errCap);
+
 /* Realtime temporal accumulation: TemporalAccumulationCS.hlsl:100-235 on caller-provided HOST
  * images, all float4 per pixel (history, current frame, world position of this and of the previous frame, normals,
  * moment history — the last may be NULL when OutputMomentInformation is 0). outColor: float4 (rgb, alpha = variance or 1);

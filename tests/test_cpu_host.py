@@ -237,3 +237,68 @@ def test_curve_tessellation_matches_the_reference_rules(tmp_path, built):
     # segment 1 of curve B reuses segment 0's ring indices (loopStartIndex ignores curveIndex)
     gb = idx[int(geoms[0][3]) + 36:int(geoms[0][3]) + 36 + 72].reshape(24, 3)
     assert np.array_equal(gb[:12], gb[12:])
+
+
+def test_image_writers_roundtrip(tmp_path, built):
+    """tb_write_image: .png decodes (PIL) to the same bytes; .exr (scanline, uncompressed, float) and .pfm parse back
+    to the same floats with an independent reader."""
+    import struct
+    import tracerboy_b200 as tb
+    rng = np.random.default_rng(0)
+    h, w = 37, 53
+    u8 = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    tb.write_image(tmp_path / "a.png", u8)
+    try:
+        from PIL import Image
+        assert np.array_equal(np.asarray(Image.open(tmp_path / "a.png").convert("RGBA")), u8)
+    except ImportError:
+        pass
+    raw = open(tmp_path / "a.png", "rb").read()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n" and raw[12:16] == b"IHDR" and struct.unpack(">II", raw[16:24]) == (w, h)
+    import zlib
+    pos, idat = 8, b""
+    while pos < len(raw):
+        n, typ = struct.unpack(">I4s", raw[pos:pos + 8])
+        body = raw[pos + 8:pos + 8 + n]
+        assert zlib.crc32(typ + body) == struct.unpack(">I", raw[pos + 8 + n:pos + 12 + n])[0]
+        if typ == b"IDAT":
+            idat += body
+        pos += 12 + n
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 4 * w)
+    assert (rows[:, 0] == 0).all() and np.array_equal(rows[:, 1:].reshape(h, w, 4), u8)
+
+    for ch in (3, 4):
+        f = rng.normal(0, 10, (h, w, ch)).astype(np.float32)
+        f[0, 0, 0] = np.inf
+        tb.write_image(tmp_path / "b.exr", f)
+        raw = open(tmp_path / "b.exr", "rb").read()
+        assert struct.unpack("<II", raw[:8]) == (20000630, 2)
+        pos, attrs = 8, {}
+        while raw[pos] != 0:
+            e = raw.index(b"\0", pos); name = raw[pos:e].decode(); pos = e + 1
+            e = raw.index(b"\0", pos); typ = raw[pos:e].decode(); pos = e + 1
+            size = struct.unpack("<I", raw[pos:pos + 4])[0]; pos += 4
+            attrs[name] = (typ, raw[pos:pos + size]); pos += size
+        pos += 1
+        assert attrs["compression"][1] == b"\0" and struct.unpack("<4i", attrs["dataWindow"][1]) == (0, 0, w - 1, h - 1)
+        names = [c.split(b"\0")[0].decode() for c in [attrs["channels"][1][i * 18:(i + 1) * 18] for i in range(ch)]]
+        assert names == (["A", "B", "G", "R"] if ch == 4 else ["B", "G", "R"])
+        offsets = struct.unpack("<%dQ" % h, raw[pos:pos + 8 * h])
+        got = np.empty((h, w, ch), np.float32)
+        for y in range(h):
+            yy, nbytes = struct.unpack("<iI", raw[offsets[y]:offsets[y] + 8])
+            assert yy == y and nbytes == 4 * w * ch
+            line = np.frombuffer(raw, np.float32, w * ch, offsets[y] + 8).reshape(ch, w)
+            for i, nm in enumerate(names):
+                got[y, :, "RGBA".index(nm)] = line[i]
+        assert np.array_equal(got.view(np.uint32), f.view(np.uint32))
+        tb.write_image(tmp_path / "c.pfm", f)
+        raw = open(tmp_path / "c.pfm", "rb").read()
+        hdr = b"PF\n%d %d\n-1.0\n" % (w, h)
+        assert raw.startswith(hdr)
+        back = np.frombuffer(raw, np.float32, w * h * 3, len(hdr)).reshape(h, w, 3)[::-1]
+        assert np.array_equal(back.view(np.uint32), f[..., :3].view(np.uint32))
+    with pytest.raises(tb.TracerBoyError):
+        tb.write_image(tmp_path / "x.jpg", u8)
+    with pytest.raises(tb.TracerBoyError):
+        tb.write_image(tmp_path / "x.png", u8[..., :3])

@@ -2,6 +2,7 @@
 CPU oracle (oracle/postprocess.cpp, itself pinned against the reference's shader text): float4 output bit-exact,
 histogram and UNORM8 back buffer exact."""
 import itertools
+import os
 
 import numpy as np
 import pytest
@@ -86,3 +87,36 @@ def test_postprocess_full_size_properties(gpu):
     bins = np.where(lum < 1e-5, 0, (np.clip((np.log2(lum.astype(np.float64)) + 10) / 16, 0, 1) * 254 + 1).astype(np.int64))
     ref_hist = np.bincount(bins.ravel(), minlength=256)
     assert np.abs(ref_hist.astype(np.int64) - hist.astype(np.int64)).sum() <= 200  # float32 vs float64 log2 at bin edges
+
+
+def test_save_image_from_the_handle(gpu, cornell, tmp_path):
+    """tb_save_image: the tonemapped back buffer as .png and the resolved radiance as .exr / .pfm."""
+    import struct
+    import zlib
+    import tracerboy_b200 as tb
+    gpu.LoadScene(cornell)
+    gpu.Resize(96, 64)
+    gpu.Render(tb.get_default_output_settings(), 4, 0.0)
+    gpu.PostProcess(tb.OutputType.LIT, tb.get_default_postprocess_settings())
+    K = tb.BufferKind
+    gpu.SaveImage(K.BACKBUFFER_RGBA8, tmp_path / "frame0.png")
+    raw = open(tmp_path / "frame0.png", "rb").read()
+    pos, idat = 8, b""
+    while pos < len(raw):
+        n, typ = struct.unpack(">I4s", raw[pos:pos + 8])
+        if typ == b"IDAT":
+            idat += raw[pos + 8:pos + 8 + n]
+        pos += 12 + n
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(64, 1 + 4 * 96)
+    assert np.array_equal(rows[:, 1:].reshape(64, 96, 4), gpu.Readback(K.BACKBUFFER_RGBA8))
+    gpu.SaveImage(K.RESOLVED_RGB, tmp_path / "radiance.pfm")
+    raw = open(tmp_path / "radiance.pfm", "rb").read()
+    hdr = b"PF\n96 64\n-1.0\n"
+    back = np.frombuffer(raw, np.float32, 96 * 64 * 3, len(hdr)).reshape(64, 96, 3)[::-1]
+    assert np.array_equal(back, gpu.Readback(K.RESOLVED_RGB))
+    gpu.SaveImage(K.ACCUM_RGBW, tmp_path / "accum.exr")
+    assert os.path.getsize(tmp_path / "accum.exr") > 96 * 64 * 16
+    with pytest.raises(tb.TracerBoyError):
+        gpu.SaveImage(K.PRIMARY_HIT_IDS, tmp_path / "ids.exr")
+    with pytest.raises(tb.TracerBoyError):
+        gpu.SaveImage(K.ACCUM_RGBW, tmp_path / "accum.png")

@@ -167,6 +167,8 @@ def load_library():
         "tb_get_default_postprocess_settings": [C.POINTER(PostProcessSettings)],
         "tb_postprocess": [vp, u32, C.POINTER(PostProcessSettings)],
         "tb_temporal_accumulate_image": [vp, C.POINTER(TemporalAccumulationParams), u32, u32, vp, vp, vp, vp, vp, vp, vp, vp],
+        "tb_save_image": [vp, u32, C.c_char_p],
+        "tb_write_image": [C.c_char_p, vp, u32, u32, u32, u32, C.c_char_p, C.c_size_t],
         "tb_postprocess_image": [vp, vp, vp, u32, u32, u32, C.POINTER(PostProcessSettings), vp, vp, vp, C.POINTER(C.c_float)],
     }
     for name, args in sig.items():
@@ -185,7 +187,7 @@ EXPORTED_SYMBOLS = ["tb_create", "tb_destroy", "tb_last_error", "tb_version", "t
                     "tb_get_render_stats", "tb_reset_render_stats", "tb_set_profiling", "tb_set_frames_in_flight", "tb_set_shadow_mode", "tb_synchronize", "tb_is_material_id_valid",
                     "tb_get_material", "tb_set_material", "tb_bvh_prebuild_info", "tb_bvh_build", "tb_trace_rays",
                     "tb_get_default_postprocess_settings", "tb_postprocess", "tb_postprocess_image",
-                    "tb_temporal_accumulate_image"]
+                    "tb_temporal_accumulate_image", "tb_save_image", "tb_write_image"]
 
 
 def get_default_output_settings():
@@ -200,6 +202,15 @@ def get_default_postprocess_settings():
     s = PostProcessSettings()
     load_library().tb_get_default_postprocess_settings(C.byref(s))
     return s
+
+
+def write_image(path, pixels):
+    """Host-only: write an (h, w, 4) uint8 array as .png, or an (h, w, 3|4) float32 array as .exr / .pfm."""
+    a = np.ascontiguousarray(pixels)
+    err = C.create_string_buffer(512)
+    rc = load_library().tb_write_image(str(path).encode(), a.ctypes.data, a.shape[1], a.shape[0], a.shape[2], a.dtype.itemsize, err, 512)
+    if rc != 0:
+        raise TracerBoyError(rc, err.value.decode())
 
 
 def convert_scene(src, dst):
@@ -395,6 +406,10 @@ class TracerBoy:
                                                         mh.ctypes.data if mh is not None else None, out.ctypes.data,
                                                         mom.ctypes.data if mom is not None else None))
         return out, mom
+
+    def SaveImage(self, kind, path):
+        """Write a buffer as .png (BACKBUFFER_RGBA8), .exr or .pfm (float buffers)."""
+        self._ck(self._lib.tb_save_image(self._h, int(kind), str(path).encode()))
 
     def DeviceBuffer(self, kind):
         p, n = C.c_void_p(), C.c_uint64()

@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, FrameConstants f
 #ifndef SHADE_MIN_BLOCKS
 #define SHADE_MIN_BLOCKS 8
 #endif
-#define REFILL_THRESHOLD 20
+#define REFILL_THRESHOLD 14
 // Step budgets: a ray that is still traversing after `budget` node visits in one kernel is
 // suspended (Traversal::suspend) and resumed by the next k_extend_resume round, where it shares
 // a warp with other long rays instead of pinning a 1-active-lane warp of the main kernel.
@@ -542,7 +542,7 @@ __device__ __forceinline__ bool try_suspend(PathState& st, int round, const Trav
 #define EXT_SHADOW 1
 #define EXT_WALK 2
 template <int KIND>
-__global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh, PathState st, int qi, int bounceIsZero, uint32_t outputHeatmap, uint32_t aovMask, uint32_t budgetMain) {
+__global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh, PathState st, int qi, int bounceIsZero, uint32_t outputHeatmap, uint32_t aovMask, uint32_t budgetMain, uint32_t refillBelow) {
     const uint32_t count = KIND == EXT_SHADOW ? st.queueCount[4] : KIND == EXT_WALK ? st.queueCount[10 + qi] : st.queueCount[qi];
     if (KIND == EXT_MAIN && blockIdx.x == 0 && threadIdx.x == 0) {
         st.queueCount[qi ^ 1] = 0;                       // next queue starts empty (consumed by k_shade)
@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
             bool wantLeaf = busy && tr.at_leaf();
             uint32_t mB = __ballot_sync(0xffffffffu, busy), mL = __ballot_sync(0xffffffffu, wantLeaf);
             uint32_t nB = __popc(mB), nL = __popc(mL);
-            if (nB == 0 || (!exhausted && nB < REFILL_THRESHOLD) || (KIND == EXT_MAIN && exhausted && iter >= 64u)) break;
+            if (nB == 0 || (!exhausted && nB < refillBelow) || (KIND == EXT_MAIN && exhausted && iter >= 64u)) break;
             if (2 * nL > nB) {
                 if (wantLeaf) { tr.step_leaf(stack, tris); steps++; }
             } else {
@@ -1215,12 +1215,13 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
         int qi = b & 1;
         if (timers) cudaEventRecord(timers->next(KernelTimers::EXTEND), stream);
         static int suspendMode = -1;
-        static uint32_t budgetMain = EXTEND_BUDGET_MAIN, budgets[EXTEND_RESUME_ROUNDS] = {384u, 1536u, 0u};
+        static uint32_t budgetMain = EXTEND_BUDGET_MAIN, budgets[EXTEND_RESUME_ROUNDS] = {384u, 1536u, 0u}, refillBelow = REFILL_THRESHOLD;
         if (suspendMode < 0) { // tuning knobs (results never depend on them)
             const char* e = getenv("TB_SUSPEND"); suspendMode = e ? atoi(e) : 1;
             if (const char* bs = getenv("TB_BUDGETS")) sscanf(bs, "%u,%u,%u", &budgetMain, &budgets[0], &budgets[1]);
+            if (const char* rs = getenv("TB_REFILL")) refillBelow = (uint32_t)atoi(rs);
         }
-        k_extend<EXT_MAIN><<<blocks, 128, 0, stream>>>(bvh, st, qi, b == 0, heat, fc.aovMask, suspendMode ? budgetMain : 0xffffffffu); lc.count++;
+        k_extend<EXT_MAIN><<<blocks, 128, 0, stream>>>(bvh, st, qi, b == 0, heat, fc.aovMask, suspendMode ? budgetMain : 0xffffffffu, refillBelow); lc.count++;
         if (suspendMode) {
             uint32_t rblocks = (st.susCapacity + 127) / 128;
             if (rblocks > sms * 4) rblocks = sms * 4;
@@ -1244,7 +1245,7 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
                                   else k_shade<STG, false><<<blocks, 128, 0, stream>>>(bvh, sc, fc, st, qi); lc.count++; } while (0)
         if (nee && shadowMode) {
             TB_LAUNCH_SHADE(0);
-            k_extend<EXT_SHADOW><<<blocks, 128, 0, stream>>>(bvh, st, qi, 0, 0, fc.aovMask, 0xffffffffu); lc.count++;
+            k_extend<EXT_SHADOW><<<blocks, 128, 0, stream>>>(bvh, st, qi, 0, 0, fc.aovMask, 0xffffffffu, refillBelow); lc.count++;
             TB_LAUNCH_SHADE(1);
         } else if (nee) {
             TB_LAUNCH_SHADE(2);
@@ -1257,7 +1258,7 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
             if (roundsEnv == -2) { const char* e = getenv("TB_WALK_ROUNDS"); roundsEnv = e ? atoi(e) : -1; }
             const int rounds = roundsEnv >= 0 ? roundsEnv : opts.walkRounds; // wavefront rounds before the persistent tail (which reads queue rounds & 1)
             for (int r = 0; r < rounds; r++) {
-                k_extend<EXT_WALK><<<blocks, 128, 0, stream>>>(bvh, st, r & 1, 0, 0, fc.aovMask, 0xffffffffu); lc.count++;
+                k_extend<EXT_WALK><<<blocks, 128, 0, stream>>>(bvh, st, r & 1, 0, 0, fc.aovMask, 0xffffffffu, REFILL_THRESHOLD); lc.count++;
                 k_walk_step<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(sc, fc, st, qi, r & 1); lc.count++;
             }
             uint32_t wblocks = blocks > sms * 4 ? sms * 4 : blocks;

@@ -666,6 +666,45 @@ TB_API int tb_postprocess_image(TbHandle* h, const float* inRGBA, const float* a
     return TB_OK;
 }
 
+// host-only: no device needed
+TB_API int tb_write_image(const char* path, const void* pixels, uint32_t width, uint32_t height, uint32_t channels,
+                          uint32_t bytesPerChannel, char* err, size_t errCap) {
+    auto bad = [&](int code, const std::string& m) { if (err && errCap) { strncpy(err, m.c_str(), errCap - 1); err[errCap - 1] = 0; } return code; };
+    if (!path || !pixels || !width || !height) return bad(TB_ERR_INVALID_ARG, "null argument");
+    std::string p(path), ext = p.size() >= 4 ? p.substr(p.size() - 4) : "", e;
+    bool ok;
+    if (ext == ".png") {
+        if (channels != 4 || bytesPerChannel != 1) return bad(TB_ERR_INVALID_ARG, ".png needs 4 x 8-bit channels");
+        ok = tb::save_png_rgba8(p, (const uint8_t*)pixels, width, height, e);
+    } else if (ext == ".exr" || ext == ".pfm") {
+        if ((channels != 3 && channels != 4) || bytesPerChannel != 4) return bad(TB_ERR_INVALID_ARG, "float image formats need 3 or 4 x 32-bit float channels");
+        ok = ext == ".exr" ? tb::save_exr_f32(p, (const float*)pixels, width, height, (int)channels, e)
+                           : tb::save_pfm_rgb(p, (const float*)pixels, width, height, (int)channels, e);
+    } else return bad(TB_ERR_NOT_IMPL, "unsupported image extension (use .png, .exr or .pfm)");
+    return ok ? TB_OK : bad(TB_ERR_IO, e);
+}
+
+TB_API int tb_save_image(TbHandle* h, uint32_t kind, const char* path) {
+    if (!h || !path) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (!h->width) return fail(h, TB_ERR_STATE, "no frame buffers (tb_resize)");
+    uint64_t bytes = 0;
+    int rc = tb_buffer_size(h, kind, &bytes);
+    if (rc != TB_OK) return rc;
+    const uint64_t n = (uint64_t)h->width * h->height;
+    std::vector<uint8_t> host(bytes);
+    rc = tb_readback(h, kind, host.data(), bytes);
+    if (rc != TB_OK) return rc;
+    uint32_t channels, bpc;
+    if (kind == TB_BUF_BACKBUFFER_RGBA8) { channels = 4; bpc = 1; }
+    else if (kind == TB_BUF_PRIMARY_HIT_IDS || kind == TB_BUF_RAY_COUNTERS || kind == TB_BUF_LUMINANCE_HISTOGRAM || (bytes != 16 * n && bytes != 12 * n))
+        return fail(h, TB_ERR_INVALID_ARG, "not an image buffer kind");
+    else { channels = bytes == 16 * n ? 4 : 3; bpc = 4; }
+    char err[512] = {0};
+    rc = tb_write_image(path, host.data(), h->width, h->height, channels, bpc, err, sizeof(err));
+    if (rc != TB_OK) return fail(h, rc, err);
+    return TB_OK;
+}
+
 TB_API int tb_temporal_accumulate_image(TbHandle* h, const TbTemporalAccumulationParams* p, uint32_t width, uint32_t height,
                                         const float* history, const float* current, const float* worldPos,
                                         const float* prevWorldPos, const float* normals, const float* momentHistory,

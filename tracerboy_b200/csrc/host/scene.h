@@ -60,4 +60,9 @@ void append_area_lights(Scene& s, const TbFloat3* pos, const TbFloat3* nrm, cons
 
 TbMaterial default_material(TbFloat3 emissive); // CreateMaterial prologue, TracerBoy.cpp:275-283
 
+// image_io.cpp
+bool save_png_rgba8(const std::string& path, const uint8_t* rgba, uint32_t w, uint32_t h, std::string& err);
+bool save_exr_f32(const std::string& path, const float* px, uint32_t w, uint32_t h, int channels, std::string& err);
+bool save_pfm_rgb(const std::string& path, const float* px, uint32_t w, uint32_t h, int channels, std::string& err);
+
 } // namespace tb
