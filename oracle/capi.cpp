@@ -64,6 +64,24 @@ ORACLE_API int oracle_trace_rays(OracleHandle* h, const TbRay* rays, uint64_t n,
     for (int64_t i = 0; i < (int64_t)n; i++) trace_ray(h->scene, rays[i], hits[i]);
     return 0;
 }
+// analysis hook (tools/simd_model.py): the visit-type sequence of each ray, concatenated; offsets[n + 1]
+ORACLE_API int oracle_trace_rays_visits(OracleHandle* h, const TbRay* rays, uint64_t n, TbHit* hits, uint8_t* seq, uint64_t seqCap, uint64_t* offsets) {
+    if (h->scene.bvh.empty()) { h->err = "no bvh"; return -7; }
+    std::vector<uint8_t> log;
+    oracle::set_visit_log(&log);
+    uint64_t at = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        log.clear();
+        trace_ray(h->scene, rays[i], hits[i]);
+        offsets[i] = at;
+        if (at + log.size() > seqCap) { oracle::set_visit_log(nullptr); h->err = "sequence buffer too small"; return -1; }
+        memcpy(seq + at, log.data(), log.size());
+        at += log.size();
+    }
+    offsets[n] = at;
+    oracle::set_visit_log(nullptr);
+    return 0;
+}
 ORACLE_API int oracle_get_camera(OracleHandle* h, TbCamera* c) { *c = h->camera; return 0; }
 ORACLE_API int oracle_set_camera(OracleHandle* h, const TbCamera* c) { h->camera = *c; h->samples = 0; return 0; }
 ORACLE_API int oracle_resize(OracleHandle* h, uint32_t w, uint32_t hh) { h->fb.resize(w, hh); h->samples = 0; return 0; }

@@ -56,6 +56,7 @@ bool build_bvh(Scene& s, int treeletPasses, std::string& err);
 // SoftwareRayQuery::TraceRayInline + Proceed (TraverseFunction.hlsli:537-785), FAST_PATH.
 void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit);
 // test hook: evaluate GetRayData's rcp literally (inf for zero components) instead of the clamped form
+void set_visit_log(std::vector<uint8_t>* log); // analysis hook: per-thread log of node visits (0 internal, 1 leaf)
 void set_literal_rcp(bool on);
 void set_literal_mode(int mask); // bit 0: D6 off (literal zero axes), bit 1: D7 off (NaN rays walk the tree)
 

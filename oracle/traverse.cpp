@@ -8,6 +8,7 @@
 // (geometryIndex, primitiveIndex) wins (reference: first found).
 #include <cfloat>
 #include <cstring>
+#include <vector>
 #include "../tracerboy_b200/csrc/common/tb_vec.h"
 #include "oracle.h"
 
@@ -75,6 +76,9 @@ inline bool ray_tri(float& hitT, float& b1, float& b2, f3 org, int kx, int ky, i
 }
 } // namespace
 
+// test / analysis hook: when set, trace_ray appends one byte per node visit (0 internal, 1 leaf) for the calling thread
+static thread_local std::vector<uint8_t>* g_visitLog = nullptr;
+void set_visit_log(std::vector<uint8_t>* log) { g_visitLog = log; }
 static bool g_literalRcp = false; // D6 off: literal rcp(0) = inf
 static bool g_literalNaN = false; // D7 off: NaN rays walk the tree
 void set_literal_rcp(bool on) { g_literalRcp = on; g_literalNaN = on; }
@@ -132,6 +136,7 @@ void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit) {
         uint32_t ni = stack.back();
         stack.pop_back();
         const AABBNode& nd = nodes[ni];
+        if (g_visitLog) g_visitLog->push_back((nd.flags & 0x80000000u) ? 1 : 0);
         if (nd.flags & 0x80000000u) {
             uint32_t leaf = nd.flags & 0x3fffffffu;
             const uint32_t* m = meta + 3 * (size_t)leaf;
