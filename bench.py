@@ -27,6 +27,7 @@ import subprocess
 import sys
 import time
 
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line (NCCL prints its version banner there otherwise)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # frames in flight: one HW queue per stream, before CUDA starts
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
