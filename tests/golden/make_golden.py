@@ -22,6 +22,10 @@ CASES = {
     "cornell_48_nobluenoise": ("cornell-box.tbscene", 48, 48, 3, 5, {"EnableBlueNoise": 0}),
     "blobs_64x36": ("synthetic:blobs?copies=8&tris=200&seed=2", 64, 36, 3, 8, {}),
     "showcase_96x54": ("synthetic:showcase?tris=300&seed=1", 96, 54, 4, 8, {"EnableNormalMaps": 1}),
+    # bundled scenes of BASELINE.json configs[1] and [3]: flattened at build time from the reference mount into
+    # scenes/_cache (tracerboy_b200/build.py); the cases are skipped where the cache is absent
+    "teapot_96x54": ("cache:teapot", 96, 54, 3, 6, {}),
+    "vwvan_96x54": ("cache:vw-van", 96, 54, 3, 6, {}),
 }
 
 
@@ -31,11 +35,16 @@ def scene_file(spec):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         tb.convert_scene(spec, out)
         return out
+    if spec.startswith("cache:"):
+        p = os.path.join(ROOT, "scenes", "_cache", spec[6:] + ".tbscene")
+        return p if os.path.exists(p) else None
     return os.path.join(HERE, spec)
 
 
 def render_case(name):
     spec, w, h, spp, bounces, over = CASES[name]
+    if scene_file(spec) is None:
+        return None
     o = Oracle()
     o.LoadScene(scene_file(spec), 3)
     o.Resize(w, h)
@@ -59,5 +68,8 @@ def render_case(name):
 if __name__ == "__main__":
     for name in CASES:
         data = render_case(name)
+        if data is None:
+            print(name, "skipped: scene cache missing")
+            continue
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
         print(name, {k: (v.shape, str(v.dtype)) for k, v in data.items()})

@@ -197,6 +197,8 @@ def test_oracle_matches_golden(name, built):
     """Regression pin: the oracle reproduces the committed fixtures bit for bit."""
     want = np.load(os.path.join(GOLDEN, name + ".npz"))
     got = make_golden.render_case(name)
+    if got is None:
+        pytest.skip("scene cache missing (needs the reference mount at build time)")
     for k in want.files:
         a, b = got[k], want[k]
         assert a.shape == b.shape, k

@@ -251,6 +251,8 @@ def test_gpu_matches_golden(name, built):
     import tracerboy_b200 as tb
     spec, w, h, spp, bounces, over = make_golden.CASES[name]
     want = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    if make_golden.scene_file(spec) is None:
+        pytest.skip("scene cache missing (needs the reference mount at build time)")
     g = tb.TracerBoy(0)
     g.LoadScene(make_golden.scene_file(spec))
     g.Resize(w, h)
