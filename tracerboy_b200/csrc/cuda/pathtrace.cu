@@ -18,6 +18,7 @@
 // Appendix A) so that results are bit-identical to the CPU oracle.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include "../common/tb_vec.h"
 #include "device_types.h"
 #include "launch.h"
@@ -380,7 +381,8 @@ __device__ __forceinline__ uint32_t pack_state(int bounce, bool prevSpec) { retu
 // walkers (k_shade -> k_walk) also carry bit 9: the bounce's perfect-specular flag
 
 // ---------------------------------------------------------------------- raygen
-__global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, FrameConstants fc, PathState st) {
+__global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, const FrameConstants* __restrict__ fcp, PathState st) {
+    const FrameConstants& fc = *fcp;
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t pi = slot;
     uint32_t n = fc.width * fc.height;
@@ -542,7 +544,8 @@ __device__ __forceinline__ bool try_suspend(PathState& st, int round, const Trav
 #define EXT_SHADOW 1
 #define EXT_WALK 2
 template <int KIND>
-__global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh, PathState st, int qi, int bounceIsZero, uint32_t outputHeatmap, uint32_t aovMask, uint32_t budgetMain, uint32_t refillBelow) {
+__global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh, PathState st, int qi, int bounceIsZero, uint32_t outputHeatmap, const FrameConstants* __restrict__ fcp, uint32_t budgetMain, uint32_t refillBelow) {
+    const uint32_t aovMask = fcp->aovMask;
     const uint32_t count = KIND == EXT_SHADOW ? st.queueCount[4] : KIND == EXT_WALK ? st.queueCount[10 + qi] : st.queueCount[qi];
     if (KIND == EXT_MAIN && blockIdx.x == 0 && threadIdx.x == 0) {
         st.queueCount[qi ^ 1] = 0;                       // next queue starts empty (consumed by k_shade)
@@ -642,7 +645,8 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
 
 // Resume round `round` (1-based): continues the rays parked by round-1; the last round has no budget.
 __global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState st, int qi, int round, uint32_t budget, int bounceIsZero,
-                                                       uint32_t outputHeatmap, uint32_t aovMask) {
+                                                       uint32_t outputHeatmap, const FrameConstants* __restrict__ fcp) {
+    const uint32_t aovMask = fcp->aovMask;
     const uint32_t count = min(st.susCount[round - 1], st.susCapacity);
     const float4* __restrict__ pairs = (const float4*)bvh.pairs;
     const float4* __restrict__ tris = (const float4*)bvh.tris;
@@ -689,7 +693,8 @@ __device__ __forceinline__ void finish_path(const FrameConstants& fc, PathState&
 //          without them (checked on the host) get a kernel with no traversal code at all in stages
 //          0, 1 and 3: fewer registers, no local-memory stack.
 template <int STAGE, bool SSS>
-__global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, DeviceScene sc, FrameConstants fc, PathState st, int qi) {
+__global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, DeviceScene sc, const FrameConstants* __restrict__ fcp, PathState st, int qi) {
+    const FrameConstants& fc = *fcp;
     const uint32_t count = STAGE == 1 ? st.queueCount[4] : st.queueCount[6 + 2 * qi];
     const uint32_t* __restrict__ inQueue = STAGE == 1 ? st.shadowQueue : st.hitQueue;
     if (STAGE != 1 && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1040,7 +1045,8 @@ __device__ __forceinline__ void append_warp(uint32_t* counter, uint32_t* queue, 
 // Walk round `wr`: one step for every walker of walk queue wr, whose rays k_extend<EXT_WALK> has just traced. Walkers
 // that go on wait in queue wr ^ 1 for the next round; the others end their bounce. No traversal code in here, so the
 // (frequent) one- and two-ray walks of clear glass run at the occupancy and coherence of the regular stages.
-__global__ void __launch_bounds__(256) k_walk_step(DeviceScene sc, FrameConstants fc, PathState st, int qi, int wr) {
+__global__ void __launch_bounds__(256) k_walk_step(DeviceScene sc, const FrameConstants* __restrict__ fcp, PathState st, int qi, int wr) {
+    const FrameConstants& fc = *fcp;
     const uint32_t count = st.queueCount[10 + wr];
     const uint32_t countUp = (count + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < countUp; i += gridDim.x * blockDim.x) {
@@ -1065,7 +1071,8 @@ __global__ void __launch_bounds__(256) k_walk_step(DeviceScene sc, FrameConstant
 // a walker, the traversal phase steps all lanes' rays together (one code path per iteration), and the service phase
 // runs walk_step for the lanes whose ray has finished, then either starts the walker's next ray or ends its bounce
 // and takes a new walker from queue `wr`.
-__global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, FrameConstants fc, PathState st, int qi, int wr) {
+__global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, const FrameConstants* __restrict__ fcp, PathState st, int qi, int wr) {
+    const FrameConstants& fc = *fcp;
     const uint32_t count = st.queueCount[10 + wr];
     uint32_t* __restrict__ next = &st.queueCount[12 + wr];
     const float4* __restrict__ pairs = (const float4*)bvh.pairs;
@@ -1129,7 +1136,8 @@ __global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, 
 // Paths whose extension ray left the scene (kernel.glsl:1328-1343): radiance += throughput * environment,
 // then the path ends. Split from k_shade so that the (large) miss population neither diverges against
 // surface shading nor pays for its register footprint; reads only the ray, throughput and colour.
-__global__ void __launch_bounds__(256) k_shade_miss(DeviceScene sc, FrameConstants fc, PathState st, int qi) {
+__global__ void __launch_bounds__(256) k_shade_miss(DeviceScene sc, const FrameConstants* __restrict__ fcp, PathState st, int qi) {
+    const FrameConstants& fc = *fcp;
     const uint32_t count = st.queueCount[7 + 2 * qi];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         uint32_t pi = st.missQueue[i];
@@ -1198,12 +1206,16 @@ static int num_sms() {
     return g_numSMs;
 }
 
-cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const FrameConstants& fc, PathState& st,
-                         cudaStream_t stream, LaunchCounter& lc, KernelTimers* timers, const RenderOptions& opts) {
+// Per-frame constants live in device memory (one copy per frame slot) so that the frame's kernel sequence can be
+// captured once into a CUDA graph and replayed: nothing baked into the graph changes from frame to frame.
+__global__ void k_set_frame(FrameConstants fc, FrameConstants* dst) { *dst = fc; }
+
+static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, const FrameConstants& fc, const FrameConstants* fcDev,
+                                PathState& st, cudaStream_t stream, uint64_t& launches, KernelTimers* timers, const RenderOptions& opts) {
     const uint32_t n = fc.width * fc.height;
     cudaMemsetAsync(st.queueCount, 0, 64, stream);
     cudaMemsetAsync(st.susCount, 0, 16, stream);
-    k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(sc, fc, st); lc.count++;
+    k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(sc, fcDev, st); launches++;
     // persistent grids: a multiple of the SM count, capped by the work available
     const uint32_t sms = (uint32_t)num_sms();
     const uint32_t maxBlocks = sms * 16;
@@ -1221,18 +1233,18 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
             if (const char* bs = getenv("TB_BUDGETS")) sscanf(bs, "%u,%u,%u", &budgetMain, &budgets[0], &budgets[1]);
             if (const char* rs = getenv("TB_REFILL")) refillBelow = (uint32_t)atoi(rs);
         }
-        k_extend<EXT_MAIN><<<blocks, 128, 0, stream>>>(bvh, st, qi, b == 0, heat, fc.aovMask, suspendMode ? budgetMain : 0xffffffffu, refillBelow); lc.count++;
+        k_extend<EXT_MAIN><<<blocks, 128, 0, stream>>>(bvh, st, qi, b == 0, heat, fcDev, suspendMode ? budgetMain : 0xffffffffu, refillBelow); launches++;
         if (suspendMode) {
             uint32_t rblocks = (st.susCapacity + 127) / 128;
             if (rblocks > sms * 4) rblocks = sms * 4;
             if (timers) cudaEventRecord(timers->next(KernelTimers::RESUME), stream);
             for (int r = 1; r <= EXTEND_RESUME_ROUNDS; r++) {
-                k_extend_resume<<<rblocks, 128, 0, stream>>>(bvh, st, qi, r, budgets[r - 1], b == 0, heat, fc.aovMask); lc.count++;
+                k_extend_resume<<<rblocks, 128, 0, stream>>>(bvh, st, qi, r, budgets[r - 1], b == 0, heat, fcDev); launches++;
                 rblocks = (rblocks + 3) / 4 > sms ? (rblocks + 3) / 4 : sms;
             }
         }
         if (timers) cudaEventRecord(timers->next(KernelTimers::SHADE), stream);
-        k_shade_miss<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(sc, fc, st, qi); lc.count++;
+        k_shade_miss<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(sc, fcDev, st, qi); launches++;
         // next-event shadow rays exist only with lights and NEE on; then shading runs as two stages
         // around a traversal kernel for the shadow queue
         const bool nee = sc.numLights > 0 && fc.settings.EnableNextEventEstimation;
@@ -1241,11 +1253,11 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
         // (measured: 874 k triangles +9 %, 36 triangles -26 %)
         const int shadowMode = opts.shadowMode == 2 ? (bvh.numPrims >= 32768u ? 1 : 0) : opts.shadowMode;
         const bool sss = opts.sceneHasSSS;
-#define TB_LAUNCH_SHADE(STG) do { if (sss) k_shade<STG, true><<<blocks, 128, 0, stream>>>(bvh, sc, fc, st, qi); \
-                                  else k_shade<STG, false><<<blocks, 128, 0, stream>>>(bvh, sc, fc, st, qi); lc.count++; } while (0)
+#define TB_LAUNCH_SHADE(STG) do { if (sss) k_shade<STG, true><<<blocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi); \
+                                  else k_shade<STG, false><<<blocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi); launches++; } while (0)
         if (nee && shadowMode) {
             TB_LAUNCH_SHADE(0);
-            k_extend<EXT_SHADOW><<<blocks, 128, 0, stream>>>(bvh, st, qi, 0, 0, fc.aovMask, 0xffffffffu, refillBelow); lc.count++;
+            k_extend<EXT_SHADOW><<<blocks, 128, 0, stream>>>(bvh, st, qi, 0, 0, fcDev, 0xffffffffu, refillBelow); launches++;
             TB_LAUNCH_SHADE(1);
         } else if (nee) {
             TB_LAUNCH_SHADE(2);
@@ -1258,15 +1270,54 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
             if (roundsEnv == -2) { const char* e = getenv("TB_WALK_ROUNDS"); roundsEnv = e ? atoi(e) : -1; }
             const int rounds = roundsEnv >= 0 ? roundsEnv : opts.walkRounds; // wavefront rounds before the persistent tail (which reads queue rounds & 1)
             for (int r = 0; r < rounds; r++) {
-                k_extend<EXT_WALK><<<blocks, 128, 0, stream>>>(bvh, st, r & 1, 0, 0, fc.aovMask, 0xffffffffu, REFILL_THRESHOLD); lc.count++;
-                k_walk_step<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(sc, fc, st, qi, r & 1); lc.count++;
+                k_extend<EXT_WALK><<<blocks, 128, 0, stream>>>(bvh, st, r & 1, 0, 0, fcDev, 0xffffffffu, REFILL_THRESHOLD); launches++;
+                k_walk_step<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(sc, fcDev, st, qi, r & 1); launches++;
             }
             uint32_t wblocks = blocks > sms * 4 ? sms * 4 : blocks;
-            k_walk<<<wblocks, 128, 0, stream>>>(bvh, sc, fc, st, qi, rounds & 1); lc.count++;
+            k_walk<<<wblocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi, rounds & 1); launches++;
         }
         if (timers) cudaEventRecord(timers->next(KernelTimers::END), stream);
     }
     return cudaGetLastError();
+}
+
+void FrameGraph::reset() {
+    if (exec) cudaGraphExecDestroy(exec);
+    exec = nullptr;
+    launches = 0;
+}
+
+// One frame (one sample per pixel) on `stream`. With a FrameGraph the kernel sequence is captured the first time and
+// replayed afterwards: one k_set_frame launch + one graph launch per frame instead of ~35 launches, which is what a
+// small frame (cornell 512^2: 8 us of GPU work per kernel) is bound by. The key lists everything that is baked into
+// the captured launches; `epoch` is bumped by the host whenever a device pointer baked into them may have changed.
+cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const FrameConstants& fc, FrameConstants* fcDev, PathState& st,
+                         cudaStream_t stream, LaunchCounter& lc, KernelTimers* timers, const RenderOptions& opts, FrameGraph* graph) {
+    k_set_frame<<<1, 1, 0, stream>>>(fc, fcDev); lc.count++;
+    static int useGraphs = -1;
+    if (useGraphs < 0) { const char* e = getenv("TB_GRAPHS"); useGraphs = e ? atoi(e) : 1; }
+    if (!graph || timers || !useGraphs) return launch_frame(bvh, sc, fc, fcDev, st, stream, lc.count, timers, opts);
+    FrameGraph::Key key = {opts.epoch, fc.width, fc.height, fc.settings.MaxBounces, fc.settings.OutputType == TB_OUTPUT_HEATMAP,
+                           fc.settings.EnableNextEventEstimation != 0, opts.shadowMode, opts.walkRounds, opts.sceneHasSSS};
+    if (!graph->exec || memcmp(&key, &graph->key, sizeof(key)) != 0) {
+        graph->reset();
+        (void)num_sms(); // device query outside the capture
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) return e;
+        uint64_t launches = 0;
+        cudaError_t le = launch_frame(bvh, sc, fc, fcDev, st, stream, launches, nullptr, opts);
+        e = cudaStreamEndCapture(stream, &g);
+        if (le != cudaSuccess) { if (g) cudaGraphDestroy(g); return le; }
+        if (e != cudaSuccess) return e;
+        e = cudaGraphInstantiate(&graph->exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { graph->exec = nullptr; return e; }
+        graph->key = key;
+        graph->launches = launches;
+    }
+    lc.count += graph->launches;
+    return cudaGraphLaunch(graph->exec, stream);
 }
 
 cudaError_t accumulate_frame(const FrameConstants& fc, PathState& st, cudaStream_t stream, LaunchCounter& lc) {

@@ -87,6 +87,7 @@ struct KernelTimers {
 // scheduling knobs; none of them changes a result
 struct RenderOptions {
     int shadowMode = 2; // next-event shadow rays: 0 traced inline in k_shade, 1 own wavefront stage, 2 automatic
+    uint32_t epoch = 0; // bumped by the host when the scene / BVH / frame buffers are re-created (invalidates captured frame graphs)
     int walkRounds = 1; // glass / subsurface walk: wavefront rounds (k_extend<EXT_WALK> + k_walk_step) before the persistent tail kernel
     bool sceneHasSSS = true; // any material with the subsurface flag (selects the k_shade variant with the inline random walk)
 };
@@ -95,8 +96,16 @@ uint64_t bvh_ref_bytes(uint32_t numPrims);
 cudaError_t build_bvh(const TbGeometryRecord* d_geoms, const uint32_t* d_triPrefix, uint32_t numGeoms,
                       const float* d_positions, const uint32_t* d_indices, uint32_t numPrims, int treeletPasses,
                       DeviceBvh& out, cudaStream_t stream, LaunchCounter& lc);
-cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const FrameConstants& fc, PathState& st,
-                         cudaStream_t stream, LaunchCounter& lc, KernelTimers* timers, const RenderOptions& opts);
+// The captured kernel sequence of one frame on one frame slot (see render_frame).
+struct FrameGraph {
+    struct Key { uint32_t epoch, width, height; int maxBounces; bool heat, nee; int shadowMode, walkRounds; bool sss; };
+    Key key{};
+    cudaGraphExec_t exec = nullptr;
+    uint64_t launches = 0; // kernels inside the graph
+    void reset();
+};
+cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const FrameConstants& fc, FrameConstants* fcDev, PathState& st,
+                         cudaStream_t stream, LaunchCounter& lc, KernelTimers* timers, const RenderOptions& opts, FrameGraph* graph);
 cudaError_t accumulate_frame(const FrameConstants& fc, PathState& st, cudaStream_t stream, LaunchCounter& lc);
 cudaError_t resolve_rgb(const float4* accum, float* rgb, uint32_t n, cudaStream_t stream, LaunchCounter& lc);
 cudaError_t trace_rays(const DeviceBvh& bvh, const TbRay* d_rays, uint64_t n, TbHit* d_hits, cudaStream_t stream, LaunchCounter& lc);

@@ -35,7 +35,8 @@ struct TbHandle {
     // Frames in flight: each slot owns private path state + staging and its own stream, so the
     // long tail of one frame's traversal kernels overlaps the next frames' work. h->stream is
     // the accumulate stream: k_accumulate runs there in frame order.
-    struct Slot { PathState st; cudaStream_t stream = nullptr; cudaEvent_t frameDone = nullptr, accDone = nullptr; };
+    struct Slot { PathState st; cudaStream_t stream = nullptr; cudaEvent_t frameDone = nullptr, accDone = nullptr;
+                  FrameConstants* fcDev = nullptr; FrameGraph graph; };
     std::vector<Slot> slots;
     uint32_t framesInFlight = 0;    // 0 = automatic (memory budget), see tb_resize
     uint64_t framesIssued = 0;
@@ -102,6 +103,7 @@ static cudaError_t upload(TbHandle* h, std::vector<void*>& owner, const T* src, 
 static void free_list(std::vector<void*>& v) { for (void* p : v) cudaFree(p); v.clear(); }
 
 static void free_scene(TbHandle* h) {
+    h->options.epoch++; // device pointers baked into captured frame graphs are about to change
     free_list(h->sceneAllocs);
     if (h->bvh.ref) cudaFree(h->bvh.ref);
     if (h->bvh.pairs) cudaFree(h->bvh.pairs);
@@ -114,6 +116,7 @@ static void free_scene(TbHandle* h) {
 static void free_frame(TbHandle* h) {
     for (auto& sl : h->slots) {
         if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+        sl.graph.reset();
         if (sl.frameDone) cudaEventDestroy(sl.frameDone);
         if (sl.accDone) cudaEventDestroy(sl.accDone);
     }
@@ -426,6 +429,7 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
         CUDA_OK(h, alloc((void**)&p.susCount, 16));
         CUDA_OK(h, alloc((void**)&p.sample, 16 * n)); CUDA_OK(h, alloc((void**)&p.sampleSeed, 4 * n));
         CUDA_OK(h, alloc((void**)&p.stEmissive, 16 * n)); CUDA_OK(h, alloc((void**)&p.stDepth, 4 * n));
+        CUDA_OK(h, alloc((void**)&sl.fcDev, sizeof(FrameConstants)));
         CUDA_OK(h, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         CUDA_OK(h, cudaEventCreateWithFlags(&sl.frameDone, cudaEventDisableTiming));
         CUDA_OK(h, cudaEventCreateWithFlags(&sl.accDone, cudaEventDisableTiming));
@@ -496,7 +500,8 @@ TB_API int tb_render(TbHandle* h, const TbOutputSettings* s, uint32_t nSamples, 
         TbHandle::Slot& sl = h->slots[serial ? 0 : h->framesIssued % h->slots.size()];
         // the slot's previous frame must have been consumed by its k_accumulate
         CUDA_OK(h, cudaStreamWaitEvent(sl.stream, sl.accDone, 0));
-        CUDA_OK(h, render_frame(h->bvh, h->dscene, fc, sl.st, sl.stream, h->lc, h->profiling ? &h->timers : nullptr, h->options));
+        CUDA_OK(h, render_frame(h->bvh, h->dscene, fc, sl.fcDev, sl.st, sl.stream, h->lc, h->profiling ? &h->timers : nullptr, h->options,
+                                serial ? nullptr : &sl.graph));
         CUDA_OK(h, cudaEventRecord(sl.frameDone, sl.stream));
         CUDA_OK(h, cudaStreamWaitEvent(h->stream, sl.frameDone, 0));
         CUDA_OK(h, accumulate_frame(fc, sl.st, h->stream, h->lc)); // frame order == issue order on h->stream
