@@ -1226,13 +1226,16 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
     for (int b = 0; b < maxBounces; b++) {
         int qi = b & 1;
         if (timers) cudaEventRecord(timers->next(KernelTimers::EXTEND), stream);
-        static int suspendMode = -1;
+        static int suspendEnv = -2;
         static uint32_t budgetMain = EXTEND_BUDGET_MAIN, budgets[EXTEND_RESUME_ROUNDS] = {384u, 1536u, 0u}, refillBelow = REFILL_THRESHOLD;
-        if (suspendMode < 0) { // tuning knobs (results never depend on them)
-            const char* e = getenv("TB_SUSPEND"); suspendMode = e ? atoi(e) : 1;
+        if (suspendEnv == -2) { // tuning knobs (results never depend on them)
+            const char* e = getenv("TB_SUSPEND"); suspendEnv = e ? atoi(e) : -1;
             if (const char* bs = getenv("TB_BUDGETS")) sscanf(bs, "%u,%u,%u", &budgetMain, &budgets[0], &budgets[1]);
             if (const char* rs = getenv("TB_REFILL")) refillBelow = (uint32_t)atoi(rs);
         }
+        // ray suspension pays when few frames are in flight (their tails have nothing to overlap with): measured with 16
+        // slots it costs 1-2 % (three mostly empty launches per bounce), with one slot it is worth 2.2x on Teapot
+        const int suspendMode = suspendEnv >= 0 ? suspendEnv : (opts.suspendRays ? 1 : 0);
         k_extend<EXT_MAIN><<<blocks, 128, 0, stream>>>(bvh, st, qi, b == 0, heat, fcDev, suspendMode ? budgetMain : 0xffffffffu, refillBelow); launches++;
         if (suspendMode) {
             uint32_t rblocks = (st.susCapacity + 127) / 128;
@@ -1297,8 +1300,9 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
     static int useGraphs = -1;
     if (useGraphs < 0) { const char* e = getenv("TB_GRAPHS"); useGraphs = e ? atoi(e) : 1; }
     if (!graph || timers || !useGraphs) return launch_frame(bvh, sc, fc, fcDev, st, stream, lc.count, timers, opts);
-    FrameGraph::Key key = {opts.epoch, fc.width, fc.height, fc.settings.MaxBounces, fc.settings.OutputType == TB_OUTPUT_HEATMAP,
-                           fc.settings.EnableNextEventEstimation != 0, opts.shadowMode, opts.walkRounds, opts.sceneHasSSS};
+    FrameGraph::Key key = {opts.epoch, fc.width, fc.height, (uint32_t)fc.settings.MaxBounces, fc.settings.OutputType == TB_OUTPUT_HEATMAP ? 1u : 0u,
+                           fc.settings.EnableNextEventEstimation ? 1u : 0u, (uint32_t)opts.shadowMode, (uint32_t)opts.walkRounds,
+                           opts.sceneHasSSS ? 1u : 0u, opts.suspendRays ? 1u : 0u};
     if (!graph->exec || memcmp(&key, &graph->key, sizeof(key)) != 0) {
         graph->reset();
         (void)num_sms(); // device query outside the capture

@@ -89,6 +89,7 @@ struct RenderOptions {
     int shadowMode = 2; // next-event shadow rays: 0 traced inline in k_shade, 1 own wavefront stage, 2 automatic
     uint32_t epoch = 0; // bumped by the host when the scene / BVH / frame buffers are re-created (invalidates captured frame graphs)
     int walkRounds = 1; // glass / subsurface walk: wavefront rounds (k_extend<EXT_WALK> + k_walk_step) before the persistent tail kernel
+    bool suspendRays = true; // park rays over budget and resume them in k_extend_resume rounds (set by the host: on with fewer than 8 frames in flight)
     bool sceneHasSSS = true; // any material with the subsurface flag (selects the k_shade variant with the inline random walk)
 };
 
@@ -98,7 +99,7 @@ cudaError_t build_bvh(const TbGeometryRecord* d_geoms, const uint32_t* d_triPref
                       DeviceBvh& out, cudaStream_t stream, LaunchCounter& lc);
 // The captured kernel sequence of one frame on one frame slot (see render_frame).
 struct FrameGraph {
-    struct Key { uint32_t epoch, width, height; int maxBounces; bool heat, nee; int shadowMode, walkRounds; bool sss; };
+    struct Key { uint32_t epoch, width, height, maxBounces, heat, nee, shadowMode, walkRounds, sss, suspend; }; // no padding: compared with memcmp
     Key key{};
     cudaGraphExec_t exec = nullptr;
     uint64_t launches = 0; // kernels inside the graph

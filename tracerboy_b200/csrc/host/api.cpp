@@ -480,6 +480,7 @@ TB_API int tb_render(TbHandle* h, const TbOutputSettings* s, uint32_t nSamples, 
     const bool serial = timeLimited || h->profiling;
     CUDA_OK(h, cudaEventRecord(h->ev0, h->stream));
     for (auto& sl : h->slots) CUDA_OK(h, cudaStreamWaitEvent(sl.stream, h->ev0, 0)); // slot streams start after ev0
+    h->options.suspendRays = serial || h->slots.size() < 8;
     for (uint32_t i = 0; i < todo; i++) {
         if (timeLimited &&
             std::chrono::duration<float>(std::chrono::steady_clock::now() - h->renderStart).count() >= s->TimeLimitInSeconds) break;
