@@ -38,6 +38,47 @@ def use_reference_core(on):
     return _ref.ref_core_calls()
 
 
+def ref_traverse_lib_path():
+    return os.path.join(_HERE, "_ref", "libref_traverse.so")
+
+
+def reference_traverse_available():
+    return os.path.exists(ref_traverse_lib_path())
+
+
+def ray_query_functions(which):
+    """The three pure functions of the ray query — ray_data(org, dir), ray_box(...), ray_tri(...) — of the oracle
+    (`which` = "oracle") or of the reference's own text compiled from the mount ("reference"). All take / return numpy
+    float32 arrays; see tests/test_cpu_oracle.py::test_ray_query_functions_equal_reference_text."""
+    lib = load() if which == "oracle" else C.CDLL(ref_traverse_lib_path())
+    pre = "oracle_" if which == "oracle" else "ref_"
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    data, box, tri = getattr(lib, pre + "ray_data"), getattr(lib, pre + "ray_box"), getattr(lib, pre + "ray_tri")
+    data.argtypes = [fp, fp, fp, fp, fp, ip]; data.restype = None
+    box.argtypes = [C.c_float, fp, fp, fp, fp, fp]; box.restype = C.c_int
+    tri.argtypes = [fp, fp, ip, fp, fp, fp]; tri.restype = C.c_int
+
+    def f(a):
+        return a.ctypes.data_as(fp)
+
+    def ray_data(org, dir_):
+        inv, oinv, shear, swz = np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros(3, np.int32)
+        data(f(org), f(dir_), f(inv), f(oinv), f(shear), swz.ctypes.data_as(ip))
+        return inv, oinv, shear, swz
+
+    def ray_box(closest, oinv, inv, c, h):
+        t = np.zeros(1, np.float32)
+        hit = box(C.c_float(closest), f(oinv), f(inv), f(c), f(h), f(t))
+        return hit, t[0]
+
+    def ray_tri(hit_t, org, swz, shear, v9):
+        t = np.array([hit_t], np.float32)
+        bary = np.zeros(2, np.float32)
+        hit = tri(f(t), f(org), swz.ctypes.data_as(ip), f(shear), f(v9), f(bary))
+        return hit, t[0], bary
+    return ray_data, ray_box, ray_tri
+
+
 def ref_post_lib_path():
     return os.path.join(_HERE, "_ref", "libref_post.so")
 

@@ -68,6 +68,43 @@ def build_post(force=False):
     return target
 
 
+TRAVERSE = "/root/reference/D3D12RaytracingFallback/src/TraverseFunction.hlsli"
+
+
+def traverse_lib_path():
+    return os.path.join(OUT, "libref_traverse.so")
+
+
+def build_traverse(force=False):
+    """oracle/_ref/libref_traverse.so: the reference's RayBoxTest (contraction on), GetRayData and RayTriangleIntersect
+    (contraction off) as host C++."""
+    target = traverse_lib_path()
+    if not os.path.exists(TRAVERSE):
+        return target if os.path.exists(target) else None
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_traverse_box.cpp", "ref_traverse_rest.cpp")] + [TRAVERSE]
+    if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs):
+        return target
+    sys.path.insert(0, os.path.join(HERE, "ref"))
+    import prepass
+    prepass.run_traverse(TRAVERSE, os.path.join(OUT, "traverse_box_gen.inc"), os.path.join(OUT, "traverse_rest_gen.inc"))
+    common = [GXX, "-O2", "-std=c++17", "-fPIC", "-mfma", "-fsingle-precision-constant", "-fno-fast-math", "-fvisibility=hidden", "-w",
+              "-I" + os.path.join(ROOT, "include"), "-I" + HERE, "-c"]
+    objs = []
+    for name, contract in (("ref_traverse_box", "fast"), ("ref_traverse_rest", "off")):
+        obj = os.path.join(OUT, name + ".o")
+        r = subprocess.run(common + ["-ffp-contract=" + contract, os.path.join(HERE, "ref", name + ".cpp"), "-o", obj],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("oracle/_ref traversal build failed:\n" + r.stdout)
+        objs.append(obj)
+    r = subprocess.run([GXX, "-shared", "-o", target] + objs, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref traversal link failed:\n" + r.stdout)
+    return target
+
+
 if __name__ == "__main__":
+    print(build_traverse(force="--force" in sys.argv))
     print(build_post(force="--force" in sys.argv))
     print(build(force="--force" in sys.argv))

@@ -10,7 +10,10 @@
 //  (i)  tracer core (PathTrace/Trace/BRDF helpers): oracle/_ref compiles the reference's own
 //       kernel.glsl from the mount as host C++ (oracle/ref/) and tests/test_cpu_oracle.py
 //       requires core.cpp to match it bit for bit -> PINNED against the reference's code;
-//  (ii) BVH builder, traversal and the RayGenCommon/SharedHitGroup/SharedRaytracing glue are
+//  (i') post-process (Tonemap.h, PostProcessCS.hlsl Process*) and the ray query's pure functions (GetRayData, RayBoxTest,
+//       RayTriangleIntersect) are compiled from the mount the same way (oracle/ref/ref_post.cpp, ref_traverse_*.cpp) and
+//       the restatements must match them bit for bit -> PINNED against the reference's code;
+//  (ii) BVH builder, traversal loop and the RayGenCommon/SharedHitGroup/SharedRaytracing glue are
 //       HLSL that cannot be compiled here: restated, checked by the fallback layer's own
 //       validator invariants, analytic known answers and independent numpy restatements
 //       -> "parity unpinned" by reference outputs for these parts.

@@ -35,6 +35,10 @@ struct float3 {
     float2 xy() const { return float2(x, y); }
     float3 xyz() const { return *this; }
     float3 rgb() const { return *this; }
+#ifdef RC_TRAVERSE
+    void set_xy(float2 v) { x = v.x; y = v.y; }                      // `A.xy = ...` (TraverseFunction.hlsli:257-259)
+    float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); } // `v[swizzleOrder.x]` (:225)
+#endif
 };
 struct float4 {
     union { struct { float x, y, z, w; }; struct { float r, g, b, a; }; };

@@ -47,5 +47,25 @@ def run_post(tonemap_h, postprocess_hlsl, dst):
     open(dst, "w").write(text)
 
 
+def run_traverse(src, dst_box, dst_rest):
+    """The three pure functions of the fallback layer's ray query (TraverseFunction.hlsli): RayBoxTest into one
+    file (compiled with contraction on: the pinned slab test is one fma per product), GetRayData and the watertight
+    RayTriangleIntersect into another (compiled unfused: `precise`)."""
+    t = open(src).read()
+    a, b = t.index("inline\nbool RayBoxTest("), t.index("float3 Swizzle(float3 v, int3 swizzleOrder)")
+    c = t.index("#define MULTIPLE_LEAVES_PER_NODE")
+    d, e = t.index("int GetIndexOfBiggestChannel(float3 vec)"), t.index("#define TOP_LEVEL_INDEX")
+    f, g = t.index("struct RayData"), t.index("bool Cull(bool opaque, uint rayFlags)")
+
+    def fix(text):
+        text = re.sub(r"\b(?:inout|out)\s+([A-Za-z_]\w*)\s+([A-Za-z_]\w*)", r"\1& \2", text)
+        text = re.sub(r"\bin\s+([A-Za-z_]\w*)\s+([A-Za-z_]\w*)", r"\1 \2", text)
+        text = re.sub(r"\b(\w+)\.xy\s*=\s*([^;]+);", r"\1.set_xy(\2);", text)   # swizzle on the left-hand side
+        text = re.sub(r"\.(xyz|rgb|xy)\b(?!\s*\()", r".\1()", text)
+        return text
+    open(dst_box, "w").write(fix(t[a:b]))
+    open(dst_rest, "w").write(fix(t[d:e] + t[f:g] + t[b:c]))
+
+
 if __name__ == "__main__":
     run(sys.argv[1], sys.argv[2])

@@ -174,3 +174,32 @@ void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit) {
 }
 
 } // namespace oracle
+
+// ---- test hooks: the three pure functions of the ray query, so that tests can compare them with the reference's
+// own text compiled from the mount (oracle/ref/ref_traverse_*.cpp)
+extern "C" __attribute__((visibility("default")))
+void oracle_ray_data(const float* org, const float* dir, float* inv, float* oinv, float* shear, int* swz) {
+    using namespace oracle;
+    f3 o = mk3(org[0], org[1], org[2]), d = mk3(dir[0], dir[1], dir[2]);
+    f3 i = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    f3 oi = o * i;
+    f3 ad = abs3(d);
+    int kz = (ad.x > ad.y && ad.x > ad.z) ? 0 : (ad.y > ad.z ? 1 : 2);
+    int kx = (kz + 1) % 3, ky = (kz + 2) % 3;
+    if (comp(d, kz) < 0.0f) { int t = kx; kx = ky; ky = t; }
+    f3 sh = mk3(comp(d, kx) / comp(d, kz), comp(d, ky) / comp(d, kz), 1.0f / comp(d, kz));
+    inv[0] = i.x; inv[1] = i.y; inv[2] = i.z; oinv[0] = oi.x; oinv[1] = oi.y; oinv[2] = oi.z;
+    shear[0] = sh.x; shear[1] = sh.y; shear[2] = sh.z; swz[0] = kx; swz[1] = ky; swz[2] = kz;
+}
+extern "C" __attribute__((visibility("default")))
+int oracle_ray_box(float closestT, const float* oinv, const float* inv, const float* c, const float* h, float* resultT) {
+    using namespace oracle;
+    AABBNode b;
+    b.c[0] = c[0]; b.c[1] = c[1]; b.c[2] = c[2]; b.h[0] = h[0]; b.h[1] = h[1]; b.h[2] = h[2]; b.flags = 0; b.right = 0;
+    return ray_box(*resultT, closestT, mk3(0.0f), 0, mk3(oinv[0], oinv[1], oinv[2]), mk3(inv[0], inv[1], inv[2]), b) ? 1 : 0;
+}
+extern "C" __attribute__((visibility("default")))
+int oracle_ray_tri(float* hitT, const float* org, const int* swz, const float* shear, const float* v9, float* bary) {
+    using namespace oracle;
+    return ray_tri(*hitT, bary[0], bary[1], mk3(org[0], org[1], org[2]), swz[0], swz[1], swz[2], mk3(shear[0], shear[1], shear[2]), v9) ? 1 : 0;
+}

@@ -421,3 +421,64 @@ def test_zero_axis_rule_drops_only_spurious_hits(vwvan):
         ox, oz = rays["Origin"][i, 0], rays["Origin"][i, 2]
         dist = max(max(tri[:, 0].min() - ox, ox - tri[:, 0].max()), max(tri[:, 2].min() - oz, oz - tri[:, 2].max()))
         assert dist > 1.0, "the literal hit is on a triangle whose box is %.3g units away from the ray" % dist
+
+
+def test_ray_query_functions_equal_reference_text(built):
+    """GetRayData, RayBoxTest and the watertight RayTriangleIntersect of the oracle (oracle/traverse.cpp) against the
+    reference's own TraverseFunction.hlsli text compiled from the mount (oracle/_ref/libref_traverse.so): every output
+    bit-identical on random rays, boxes and triangles and on the edge cases the tracer meets — exactly-zero direction
+    components (rcp = inf, NaN slabs), rays through vertices and along edges, degenerate and far-away sliver
+    triangles, boxes of zero extent, NaN rays."""
+    from oracle import binding
+    if not binding.reference_traverse_available():
+        pytest.skip("oracle/_ref/libref_traverse.so not built (needs the reference mount at build time)")
+    o_data, o_box, o_tri = binding.ray_query_functions("oracle")
+    r_data, r_box, r_tri = binding.ray_query_functions("reference")
+    rng = np.random.default_rng(7)
+    f32 = np.float32
+
+    def bits(x):
+        return np.atleast_1d(np.asarray(x, f32)).view(np.uint32).tolist()
+
+    def same(a, b):
+        a, b = np.atleast_1d(np.asarray(a, f32)), np.atleast_1d(np.asarray(b, f32))
+        return bool((((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b)))).all())
+
+    hits = box_hits = 0
+    for i in range(6000):
+        org = rng.normal(0, 10, 3).astype(f32)
+        d = rng.normal(0, 1, 3).astype(f32)
+        d /= np.linalg.norm(d)
+        kind = i % 12
+        if kind == 1: d[rng.integers(3)] = 0.0                       # one exactly-zero component (D6 territory)
+        if kind == 2: d[:] = 0; d[rng.integers(3)] = rng.choice([-1.0, 1.0])  # axis-aligned
+        if kind == 3: d[rng.integers(3)] = -0.0
+        if kind == 4: d[rng.integers(3)] = np.nan                    # NaN ray (D7 territory)
+        if kind == 5: org[rng.integers(3)] = np.nan
+        od, rd = o_data(org, d), r_data(org, d)
+        for a, b in zip(od, rd):
+            assert same(a, b) if a.dtype == np.float32 else np.array_equal(a, b), (org, d)
+        inv, oinv, shear, swz = od
+        # boxes: around the ray's path, far away, zero extent
+        t = f32(rng.uniform(0, 30))
+        c = (org + d * t + rng.normal(0, 2, 3)).astype(f32) if kind < 4 else rng.normal(0, 10, 3).astype(f32)
+        h = np.abs(rng.normal(0, 2, 3)).astype(f32)
+        if i % 7 == 0: h[rng.integers(3)] = 0.0
+        closest = f32(rng.choice([999999.0, float(t), 0.5]))
+        ob, rb = o_box(closest, oinv, inv, c, h), r_box(closest, oinv, inv, c, h)
+        assert ob[0] == rb[0] and same(ob[1], rb[1]), (org, d, c, h)
+        box_hits += ob[0]
+        # triangles: around a point on the ray, through a vertex, along an edge, degenerate, far sliver
+        p = np.nan_to_num(org + d * t).astype(f32)
+        tri = (p + rng.normal(0, 1.5, (3, 3))).astype(f32)
+        if i % 5 == 1: tri[0] = p                                     # ray through a vertex
+        if i % 5 == 2: tri[1] = (2 * p - tri[0]).astype(f32)          # p on the edge v0-v1
+        if i % 5 == 3: tri[2] = tri[1]                                # degenerate
+        if i % 5 == 4: tri = (tri * f32(1e-3) + rng.normal(0, 400, 3)).astype(f32)  # far-away sliver
+        v9 = tri.reshape(9).copy()
+        ot, rt = o_tri(closest, org, swz, shear, v9), r_tri(closest, org, swz, shear, v9)
+        assert ot[0] == rt[0], (org, d, tri)
+        if ot[0]:
+            assert same(ot[1], rt[1]) and same(ot[2], rt[2]), (org, d, tri)
+            hits += 1
+    assert hits > 500 and box_hits > 500

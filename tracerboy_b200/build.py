@@ -196,6 +196,7 @@ def build_all(force=False, verbose=False):
     from oracle import build_ref  # checker only: the reference's kernel.glsl compiled from the mount, when present
     build_ref.build(force)
     build_ref.build_post(force)
+    build_ref.build_traverse(force)
 
 
 if __name__ == "__main__":
