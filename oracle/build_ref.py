@@ -104,7 +104,121 @@ def build_traverse(force=False):
     return target
 
 
+MORTON = "/root/reference/D3D12RaytracingFallback/src/CalculateMortonCodesBindings.h"
+
+
+def morton_lib_path():
+    return os.path.join(OUT, "libref_morton.so")
+
+
+def build_morton(force=False):
+    """oracle/_ref/libref_morton.so: the reference's CalculateMortonCode as host C++."""
+    target = morton_lib_path()
+    if not os.path.exists(MORTON):
+        return target if os.path.exists(target) else None
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_morton.cpp")] + [MORTON]
+    if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs):
+        return target
+    sys.path.insert(0, os.path.join(HERE, "ref"))
+    import prepass
+    prepass.run_morton(MORTON, os.path.join(OUT, "morton_gen.inc"))
+    cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma", "-ffp-contract=off", "-fsingle-precision-constant", "-fno-fast-math",
+           "-fvisibility=hidden", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + HERE, os.path.join(HERE, "ref", "ref_morton.cpp"), "-o", target]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref morton build failed:\n" + r.stdout)
+    return target
+
+
+KARRAS = "/root/reference/D3D12RaytracingFallback/src/BuildBVHSplits.hlsli"
+
+
+def karras_lib_path():
+    return os.path.join(OUT, "libref_karras.so")
+
+
+def build_karras(force=False):
+    """oracle/_ref/libref_karras.so: the reference's GenerateHierarchy (Karras 2012) as host C++."""
+    target = karras_lib_path()
+    if not os.path.exists(KARRAS):
+        return target if os.path.exists(target) else None
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_karras.cpp")] + [KARRAS]
+    if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs):
+        return target
+    sys.path.insert(0, os.path.join(HERE, "ref"))
+    import prepass
+    prepass.run_karras(KARRAS, os.path.join(OUT, "karras_gen.inc"))
+    cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-fno-fast-math", "-fvisibility=hidden", "-w",
+           "-I" + os.path.join(ROOT, "include"), "-I" + HERE, os.path.join(HERE, "ref", "ref_karras.cpp"), "-o", target]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref karras build failed:\n" + r.stdout)
+    return target
+
+
+TREELET_H = "/root/reference/D3D12RaytracingFallback/src/TreeletReorderBindings.h"
+TREELET = "/root/reference/D3D12RaytracingFallback/src/TreeletReorder.hlsl"
+
+
+def treelet_lib_path():
+    return os.path.join(OUT, "libref_treelet.so")
+
+
+def build_treelet(force=False):
+    """oracle/_ref/libref_treelet.so: the reference's treelet optimisation (group shader) as host C++, 32 threads + barrier."""
+    target = treelet_lib_path()
+    if not (os.path.exists(TREELET_H) and os.path.exists(TREELET)):
+        return target if os.path.exists(target) else None
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_treelet.cpp")] + [TREELET_H, TREELET]
+    if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs):
+        return target
+    sys.path.insert(0, os.path.join(HERE, "ref"))
+    import prepass
+    prepass.run_treelet(TREELET_H, TREELET, os.path.join(OUT, "treelet_gen.inc"))
+    cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-mfma", "-ffp-contract=off", "-fsingle-precision-constant",
+           "-fno-fast-math", "-fvisibility=hidden", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + HERE,
+           os.path.join(HERE, "ref", "ref_treelet.cpp"), "-o", target]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref treelet build failed:\n" + r.stdout)
+    return target
+
+
+HELPER = "/root/reference/D3D12RaytracingFallback/src/RayTracingHelper.hlsli"
+
+
+def boxes_lib_path():
+    return os.path.join(OUT, "libref_boxes.so")
+
+
+def build_boxes(force=False):
+    """oracle/_ref/libref_boxes.so: the reference's leaf / parent box constructors as host C++."""
+    target = boxes_lib_path()
+    if not os.path.exists(HELPER):
+        return target if os.path.exists(target) else None
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_boxes.cpp")] + [HELPER]
+    if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs):
+        return target
+    sys.path.insert(0, os.path.join(HERE, "ref"))
+    import prepass
+    prepass.run_boxes(HELPER, os.path.join(OUT, "boxes_gen.inc"))
+    cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma", "-ffp-contract=off", "-fsingle-precision-constant", "-fno-fast-math",
+           "-fvisibility=hidden", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + HERE, os.path.join(HERE, "ref", "ref_boxes.cpp"), "-o", target]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref boxes build failed:\n" + r.stdout)
+    return target
+
+
 if __name__ == "__main__":
+    print(build_boxes(force="--force" in sys.argv))
+    print(build_treelet(force="--force" in sys.argv))
+    print(build_karras(force="--force" in sys.argv))
+    print(build_morton(force="--force" in sys.argv))
     print(build_traverse(force="--force" in sys.argv))
     print(build_post(force="--force" in sys.argv))
     print(build(force="--force" in sys.argv))

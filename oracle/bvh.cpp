@@ -104,6 +104,92 @@ inline void leaf_box(const Prim& p, f3& center, f3& half) {
     half = mx - center;
 }
 
+// GetBoxFromChildBoxes + AABBtoBoundingBox, RayTracingHelper.hlsli:229-235, 275-285: the parent box is fitted around the
+// children's centre +- half-extent corners (not around their original min / max), then stored as centre / half-extent
+inline void parent_box(f3 ac, f3 ah, f3 bc, f3 bh, f3& c, f3& h) {
+    f3 mn = min3(ac - ah, bc - bh);
+    f3 mx = max3(ac + ah, bc + bh);
+    c = (mn + mx) * 0.5f;
+    h = mx - c;
+}
+
+// One treelet: FormTreelet, FindOptimalPartitions, ReformTree (TreeletReorder.hlsl:38-236) for the treelet rooted at `root`.
+void optimize_treelet(std::vector<HNode>& H, std::vector<Box>& aabb, uint32_t nInternal, uint32_t root) {
+    auto isLeaf = [&](uint32_t i) { return i >= nInternal; };
+    // FormTreelet (TreeletReorder.hlsl:38-80)
+    uint32_t leaves[7], internals[6];
+    internals[0] = root;
+    leaves[0] = H[root].left;
+    leaves[1] = H[root].right;
+    for (uint32_t size = 2; size < 7; size++) {
+        float largest = 0.0f;
+        uint32_t pick = 0, pickIdx = 0;
+        for (uint32_t i = 0; i < size; i++) {
+            uint32_t t = leaves[i];
+            if (!isLeaf(t)) {
+                float sa = surface_area(aabb[t]);
+                if (sa > largest) { largest = sa; pick = t; pickIdx = i; }
+            }
+        }
+        HNode nt = H[pick];
+        internals[size - 1] = pick;
+        leaves[pickIdx] = nt.left;
+        leaves[size] = nt.right;
+    }
+    // FindOptimalPartitions (:82-171)
+    float cost[128];
+    uint32_t part[128];
+    memset(part, 0, sizeof(part));
+    cost[0] = 0.0f;
+    for (uint32_t mask = 1; mask < 128; mask++) {
+        Box b = {mk3(FLT_MAX), mk3(-FLT_MAX)};
+        for (uint32_t i = 0; i < 7; i++)
+            if ((1u << i) & mask) b = combine(b, aabb[leaves[i]]);
+        cost[mask] = surface_area(b);
+    }
+    float rootSA = surface_area(aabb[root]);
+    for (uint32_t i = 0; i < 7; i++) cost[1u << i] = 1.0f * surface_area(aabb[leaves[i]]) / rootSA;
+    for (uint32_t subset = 2; subset <= 7; subset++) {
+        for (uint32_t mask = 1; mask < 128; mask++) {
+            if ((uint32_t)__builtin_popcount(mask) != subset) continue;
+            float lowest = FLT_MAX;
+            uint32_t best = 0;
+            uint32_t delta = (mask - 1) & mask;
+            uint32_t p = (0u - delta) & mask;
+            do {
+                float c = cost[p] + cost[mask ^ p];
+                if (c < lowest) { lowest = c; best = p; }
+                p = (p - delta) & mask;
+            } while (p != 0);
+            cost[mask] = 1.0f * cost[mask] + lowest;
+            part[mask] = best;
+        }
+    }
+    // ReformTree (:173-236)
+    struct Entry { uint32_t mask, node; };
+    Entry stack[7];
+    uint32_t allocated = 1, sp = 1;
+    stack[0] = {127u, internals[0]};
+    while (sp > 0) {
+        Entry e = stack[--sp];
+        Entry l, r;
+        l.mask = part[e.mask];
+        if (__builtin_popcount(l.mask) > 1) { l.node = internals[allocated++]; stack[sp++] = l; }
+        else l.node = leaves[__builtin_ctz(l.mask)];
+        r.mask = e.mask ^ l.mask;
+        if (__builtin_popcount(r.mask) > 1) { r.node = internals[allocated++]; stack[sp++] = r; }
+        else r.node = leaves[__builtin_ctz(r.mask)];
+        H[e.node].left = l.node;
+        H[e.node].right = r.node;
+        H[l.node].parent = e.node;
+        H[r.node].parent = e.node;
+    }
+    for (int j = 5; j >= 0; j--) {
+        uint32_t in = internals[j];
+        aabb[in] = combine(aabb[H[in].left], aabb[H[in].right]);
+    }
+}
+
 // One treelet-reorder pass (ClearBuffers.hlsl, FindTreelets.hlsl, TreeletReorder.hlsl).
 void treelet_pass(std::vector<HNode>& H, const std::vector<Prim>& prims, uint32_t n, uint32_t minTris,
                   uint32_t& maxClimb) {
@@ -134,87 +220,61 @@ void treelet_pass(std::vector<HNode>& H, const std::vector<Prim>& prims, uint32_
         count[node] = count[H[node].left] + count[H[node].right];
         aabb[node] = combine(aabb[H[node].left], aabb[H[node].right]);
     }
-    auto isLeaf = [&](uint32_t i) { return i >= nInternal; };
     for (uint32_t root : order) {
         if (count[root] < minTris) continue;
         bool base = count[H[root].left] < minTris && count[H[root].right] < minTris;
         if (base) maxClimb = std::max(maxClimb, depth[root] + 1);
-        // FormTreelet (TreeletReorder.hlsl:38-80)
-        uint32_t leaves[7], internals[6];
-        internals[0] = root;
-        leaves[0] = H[root].left;
-        leaves[1] = H[root].right;
-        for (uint32_t size = 2; size < 7; size++) {
-            float largest = 0.0f;
-            uint32_t pick = 0, pickIdx = 0;
-            for (uint32_t i = 0; i < size; i++) {
-                uint32_t t = leaves[i];
-                if (!isLeaf(t)) {
-                    float sa = surface_area(aabb[t]);
-                    if (sa > largest) { largest = sa; pick = t; pickIdx = i; }
-                }
-            }
-            HNode nt = H[pick];
-            internals[size - 1] = pick;
-            leaves[pickIdx] = nt.left;
-            leaves[size] = nt.right;
-        }
-        // FindOptimalPartitions (:82-171)
-        float cost[128];
-        uint32_t part[128];
-        memset(part, 0, sizeof(part));
-        cost[0] = 0.0f;
-        for (uint32_t mask = 1; mask < 128; mask++) {
-            Box b = {mk3(FLT_MAX), mk3(-FLT_MAX)};
-            for (uint32_t i = 0; i < 7; i++)
-                if ((1u << i) & mask) b = combine(b, aabb[leaves[i]]);
-            cost[mask] = surface_area(b);
-        }
-        float rootSA = surface_area(aabb[root]);
-        for (uint32_t i = 0; i < 7; i++) cost[1u << i] = 1.0f * surface_area(aabb[leaves[i]]) / rootSA;
-        for (uint32_t subset = 2; subset <= 7; subset++) {
-            for (uint32_t mask = 1; mask < 128; mask++) {
-                if ((uint32_t)__builtin_popcount(mask) != subset) continue;
-                float lowest = FLT_MAX;
-                uint32_t best = 0;
-                uint32_t delta = (mask - 1) & mask;
-                uint32_t p = (0u - delta) & mask;
-                do {
-                    float c = cost[p] + cost[mask ^ p];
-                    if (c < lowest) { lowest = c; best = p; }
-                    p = (p - delta) & mask;
-                } while (p != 0);
-                cost[mask] = 1.0f * cost[mask] + lowest;
-                part[mask] = best;
-            }
-        }
-        // ReformTree (:173-236)
-        struct Entry { uint32_t mask, node; };
-        Entry stack[7];
-        uint32_t allocated = 1, sp = 1;
-        stack[0] = {127u, internals[0]};
-        while (sp > 0) {
-            Entry e = stack[--sp];
-            Entry l, r;
-            l.mask = part[e.mask];
-            if (__builtin_popcount(l.mask) > 1) { l.node = internals[allocated++]; stack[sp++] = l; }
-            else l.node = leaves[__builtin_ctz(l.mask)];
-            r.mask = e.mask ^ l.mask;
-            if (__builtin_popcount(r.mask) > 1) { r.node = internals[allocated++]; stack[sp++] = r; }
-            else r.node = leaves[__builtin_ctz(r.mask)];
-            H[e.node].left = l.node;
-            H[e.node].right = r.node;
-            H[l.node].parent = e.node;
-            H[r.node].parent = e.node;
-        }
-        for (int j = 5; j >= 0; j--) {
-            uint32_t in = internals[j];
-            aabb[in] = combine(aabb[H[in].left], aabb[H[in].right]);
-        }
+        optimize_treelet(H, aabb, nInternal, root);
     }
 }
 
 } // namespace
+
+// test hook: the Karras hierarchy over sorted codes (parent, left, right per node; 2n-1 nodes), for the comparison with
+// the reference's own BuildBVHSplits.hlsli text (oracle/ref/ref_karras.cpp)
+void karras_public(const uint32_t* codes, uint32_t n, uint32_t* out3) {
+    const uint32_t nInternal = n - 1, total = 2 * n - 1;
+    std::vector<HNode> H(total, HNode{0xffffffffu, 0, 0});
+    Karras K{codes, n};
+    for (uint32_t idx = 0; idx < nInternal; idx++) {
+        uint32_t first, last;
+        K.range(idx, first, last);
+        uint32_t split = K.split(first, last);
+        uint32_t a = (split == first) ? nInternal + split : split;
+        uint32_t b = (split + 1 == last) ? nInternal + split + 1 : split + 1;
+        H[idx].left = a; H[idx].right = b; H[a].parent = idx; H[b].parent = idx;
+    }
+    memcpy(out3, H.data(), sizeof(HNode) * total);
+}
+
+// test hook: one treelet optimisation on a caller-provided hierarchy (3 words per node) and boxes (min, max: 6 floats per
+// node), for the comparison with the reference's own TreeletReorder.hlsl text (oracle/ref/ref_treelet.cpp)
+void treelet_public(uint32_t* H3, float* aabb6, uint32_t n, uint32_t root) {
+    const uint32_t total = 2 * n - 1;
+    std::vector<HNode> H(total);
+    std::vector<Box> boxes(total);
+    memcpy(H.data(), H3, sizeof(HNode) * total);
+    for (uint32_t i = 0; i < total; i++) boxes[i] = {mk3(aabb6[6 * i], aabb6[6 * i + 1], aabb6[6 * i + 2]), mk3(aabb6[6 * i + 3], aabb6[6 * i + 4], aabb6[6 * i + 5])};
+    optimize_treelet(H, boxes, n - 1, root);
+    memcpy(H3, H.data(), sizeof(HNode) * total);
+    for (uint32_t i = 0; i < total; i++) {
+        aabb6[6 * i] = boxes[i].mn.x; aabb6[6 * i + 1] = boxes[i].mn.y; aabb6[6 * i + 2] = boxes[i].mn.z;
+        aabb6[6 * i + 3] = boxes[i].mx.x; aabb6[6 * i + 4] = boxes[i].mx.y; aabb6[6 * i + 5] = boxes[i].mx.z;
+    }
+}
+
+// test hooks: the two box constructors of the node writer (leaf from a triangle, parent from two children)
+void leaf_box_public(const float* v9, float* c3, float* h3) {
+    Prim p; p.type = 1; memcpy(p.v, v9, 36);
+    f3 c, h;
+    leaf_box(p, c, h);
+    c3[0] = c.x; c3[1] = c.y; c3[2] = c.z; h3[0] = h.x; h3[1] = h.y; h3[2] = h.z;
+}
+void parent_box_public(const float* ac, const float* ah, const float* bc, const float* bh, float* c3, float* h3) {
+    f3 c, h;
+    parent_box(mk3(ac[0], ac[1], ac[2]), mk3(ah[0], ah[1], ah[2]), mk3(bc[0], bc[1], bc[2]), mk3(bh[0], bh[1], bh[2]), c, h);
+    c3[0] = c.x; c3[1] = c.y; c3[2] = c.z; h3[0] = h.x; h3[1] = h.y; h3[2] = h.z;
+}
 
 uint32_t morton_public(const float* c, const float* mn, const float* mx) {
     return morton_code(mk3(c[0], c[1], c[2]), mk3(mn[0], mn[1], mn[2]), mk3(mx[0], mx[1], mx[2]));
@@ -328,10 +388,8 @@ bool build_bvh(Scene& s, int treeletPasses, std::string& err) {
                 const AABBNode& B = nodes[r];
                 f3 ac = mk3(A.c[0], A.c[1], A.c[2]), ah = mk3(A.h[0], A.h[1], A.h[2]);
                 f3 bc = mk3(B.c[0], B.c[1], B.c[2]), bh = mk3(B.h[0], B.h[1], B.h[2]);
-                f3 mn = min3(ac - ah, bc - bh); // GetBoxFromChildBoxes, RayTracingHelper.hlsli:275-285
-                f3 mx = max3(ac + ah, bc + bh);
-                f3 c = (mn + mx) * 0.5f;
-                f3 h = mx - c;
+                f3 c, h;
+                parent_box(ac, ah, bc, bh, c, h);
                 AABBNode& nd = nodes[node];
                 nd.c[0] = c.x; nd.c[1] = c.y; nd.c[2] = c.z;
                 nd.h[0] = h.x; nd.h[1] = h.y; nd.h[2] = h.z;

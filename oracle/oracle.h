@@ -13,7 +13,9 @@
 //  (i') post-process (Tonemap.h, PostProcessCS.hlsl Process*) and the ray query's pure functions (GetRayData, RayBoxTest,
 //       RayTriangleIntersect) are compiled from the mount the same way (oracle/ref/ref_post.cpp, ref_traverse_*.cpp) and
 //       the restatements must match them bit for bit -> PINNED against the reference's code;
-//  (ii) BVH builder, traversal loop and the RayGenCommon/SharedHitGroup/SharedRaytracing glue are
+//       likewise the builder's arithmetic: CalculateMortonCode, GenerateHierarchy (Karras), one treelet optimisation round
+//       (the group shader run by 32 host threads + barrier) and the leaf / parent box constructors -> PINNED;
+//  (ii) the builder's resource-bound glue, the traversal loop and the RayGenCommon/SharedHitGroup/SharedRaytracing glue are
 //       HLSL that cannot be compiled here: restated, checked by the fallback layer's own
 //       validator invariants, analytic known answers and independent numpy restatements
 //       -> "parity unpinned" by reference outputs for these parts.
@@ -89,5 +91,9 @@ void render_frame(const Scene& s, const RenderParams& p, FrameBuffers& fb, int n
 float hash13_public(float x, float y, float z);
 float halton_public(int b, int i);
 uint32_t morton_public(const float* centroid, const float* smin, const float* smax);
+void karras_public(const uint32_t* sortedCodes, uint32_t n, uint32_t* parentLeftRight);
+void leaf_box_public(const float* v9, float* c3, float* h3);
+void parent_box_public(const float* ac, const float* ah, const float* bc, const float* bh, float* c3, float* h3);
+void treelet_public(uint32_t* parentLeftRight, float* aabbMinMax, uint32_t n, uint32_t root);
 
 } // namespace oracle

@@ -67,5 +67,59 @@ def run_traverse(src, dst_box, dst_rest):
     open(dst_rest, "w").write(fix(t[d:e] + t[f:g] + t[b:c]))
 
 
+def run_morton(src, dst):
+    """GetMortonCodesFromUnitCoord(float3) + CalculateMortonCode(float3): from `#define BIT(x)` to the entry point."""
+    t = open(src).read()
+    a = t.index("#define BIT(x) (1 << (x))")
+    b = t.index("[numthreads(THREAD_GROUP_1D_WIDTH, 1, 1)]", a)
+    text = t[a:b]
+    # `uint coords[numAxis] = { adjustedCoord.y, ... }`: HLSL converts float -> uint implicitly (truncation); C++ list
+    # initialisation forbids the narrowing, so the conversion is spelled out
+    text = re.sub(r"\{ adjustedCoord\.y, adjustedCoord\.x, adjustedCoord\.z \}",
+                  "{ (uint)adjustedCoord.y, (uint)adjustedCoord.x, (uint)adjustedCoord.z }", text)
+    open(dst, "w").write(text)
+
+
+def run_karras(src, dst):
+    """BuildBVHSplits.hlsli from CountLeadingZeroes to GenerateHierarchy (everything between the include and main())."""
+    t = open(src).read()
+    a, b = t.index("int CountLeadingZeroes(uint num)"), t.index("[numthreads(THREAD_GROUP_1D_WIDTH, 1, 1)]")
+    open(dst, "w").write(t[a:b])
+
+
+def run_treelet(bindings_h, treelet_hlsl, dst):
+    """TreeletReorderBindings.h: `FullTreeletSize` and everything from `#define BIT` to the end of CombineAABB (tables,
+    GetBitPermutation, IsLeaf, ComputeBoxSurfaceArea, CombineAABB); TreeletReorder.hlsl: CalculateCost, the groupshared
+    declarations, FormTreelet, FindOptimalPartitions, ReformTree (up to TraverseToParent)."""
+    b = open(bindings_h).read()
+    t = open(treelet_hlsl).read()
+    b0 = "static const uint FullTreeletSize = 7;\n"
+    assert b0 in b
+    a1 = b.index("#define BIT(x) (1 << (x))")
+    e1 = b.index("#endif", a1)
+    a2, e2 = t.index("static const float CostOfRayBoxIntersection"), t.index("void TraverseToParent(")
+    text = b0 + b[a1:e1] + "\n" + t[a2:e2]
+    text = re.sub(r"\bin\s+([A-Za-z_]\w*)\s+([A-Za-z_]\w*)", r"\1 \2", text)
+    text = text.replace("[unroll]", "")
+    # The group is 32 threads = one wave, which executes in lockstep: every thread has written its share of the union
+    # surface areas before any thread overwrites the single-leaf entries (TreeletReorder.hlsl:96-127 has no barrier
+    # between the two). Host threads are not in lockstep, so the implicit ordering is made explicit.
+    marker = "    AABB nodeAABB = AABBBuffer[nodeIndex];"
+    assert text.count(marker) == 1
+    text = text.replace(marker, "    GroupMemoryBarrierWithGroupSync(); /* wave lockstep made explicit */\n" + marker)
+    open(dst, "w").write(text)
+
+
+def run_boxes(src, dst):
+    """RayTracingHelper.hlsli: CreateFlag, AABBtoBoundingBox, BoundingBoxToAABB, GetBoxDataFromTriangle ... GetBoxFromChildBoxes."""
+    t = open(src).read()
+    a0, e0 = t.index("uint2 CreateFlag(uint leftNodeIndex, uint rightNodeIndex)"), t.index("uint GetLeftNodeIndex(uint2 flag)")
+    a1, e1 = t.index("BoundingBox AABBtoBoundingBox(AABB aabb)"), t.index("AABB RawDataToAABB(int4 a, int4 b)")
+    a2, e2 = t.index("BoundingBox GetBoxDataFromTriangle("), t.index("float Determinant(")
+    text = t[a0:e0] + t[a1:e1] + t[a2:e2]
+    text = re.sub(r"\b(?:inout|out)\s+([A-Za-z_]\w*)\s+([A-Za-z_]\w*)", r"\1& \2", text)
+    open(dst, "w").write(text)
+
+
 if __name__ == "__main__":
     run(sys.argv[1], sys.argv[2])

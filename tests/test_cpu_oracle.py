@@ -482,3 +482,150 @@ def test_ray_query_functions_equal_reference_text(built):
             assert same(ot[1], rt[1]) and same(ot[2], rt[2]), (org, d, tri)
             hits += 1
     assert hits > 500 and box_hits > 500
+
+
+def test_morton_code_equals_reference_text(built):
+    """CalculateMortonCode of the oracle against the reference's own CalculateMortonCodesBindings.h text compiled from the
+    mount (oracle/_ref/libref_morton.so): random centroids inside, on the faces of and outside the scene box, flat
+    scene boxes (extent below the 1e-5 epsilon), huge and tiny scenes."""
+    import ctypes as C
+    from oracle import binding
+    path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_morton.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_morton.so not built (needs the reference mount at build time)")
+    ref = C.CDLL(path)
+    fp = C.POINTER(C.c_float)
+    ref.ref_morton.argtypes = [fp, fp, fp]; ref.ref_morton.restype = C.c_uint32
+    lib = binding.load()
+    rng = np.random.default_rng(3)
+    seen = set()
+    for i in range(20000):
+        scale = np.float32(10.0 ** rng.uniform(-4, 4))
+        smin = (rng.normal(0, 1, 3) * scale).astype(np.float32)
+        ext = (np.abs(rng.normal(0, 1, 3)) * scale).astype(np.float32)
+        if i % 9 == 0: ext[rng.integers(3)] = 0.0            # flat scene: the epsilon clamp decides
+        if i % 9 == 1: ext[rng.integers(3)] = np.float32(5e-6)
+        smax = (smin + ext).astype(np.float32)
+        u = rng.uniform(-0.1, 1.1, 3)
+        if i % 5 == 0: u[rng.integers(3)] = rng.choice([0.0, 1.0])   # on a face of the scene box
+        c = (smin + u * ext).astype(np.float32)
+        a = lib.oracle_morton(c.ctypes.data_as(C.c_void_p), smin.ctypes.data_as(C.c_void_p), smax.ctypes.data_as(C.c_void_p))
+        b = ref.ref_morton(c.ctypes.data_as(fp), smin.ctypes.data_as(fp), smax.ctypes.data_as(fp))
+        assert a == b, (c, smin, smax, a, b)
+        seen.add(a)
+    assert len(seen) > 10000 and max(seen) < (1 << 30)
+
+
+def test_karras_hierarchy_equals_reference_text(built):
+    """The oracle's Karras-2012 hierarchy (parent / left / right of all 2N-1 nodes) against the reference's own
+    BuildBVHSplits.hlsli text compiled from the mount (oracle/_ref/libref_karras.so): random sorted 30-bit codes,
+    heavy duplication (the index tie-break), all-equal codes, N from 2 to 20000."""
+    import ctypes as C
+    from oracle import binding
+    path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_karras.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_karras.so not built (needs the reference mount at build time)")
+    ref = C.CDLL(path)
+    lib = binding.load()
+    for f in (ref.ref_karras, lib.oracle_karras):
+        f.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]; f.restype = None
+    rng = np.random.default_rng(5)
+    for n, distinct in ((2, 2), (3, 1), (7, 3), (64, 64), (1000, 1 << 30), (1000, 17), (5000, 1), (20000, 1 << 30), (20000, 300)):
+        codes = np.sort(rng.integers(0, distinct, n, dtype=np.uint64).astype(np.uint32) if distinct < (1 << 30)
+                        else rng.integers(0, 1 << 30, n, dtype=np.uint64).astype(np.uint32))
+        a = np.zeros((2 * n - 1, 3), np.uint32)
+        b = np.zeros((2 * n - 1, 3), np.uint32)
+        lib.oracle_karras(codes.ctypes.data, n, a.ctypes.data)
+        ref.ref_karras(codes.ctypes.data, n, b.ctypes.data)
+        assert np.array_equal(a, b), (n, distinct)
+        # and it is a tree: every node but the root has a parent, every internal node two distinct children
+        assert a[0, 0] == 0xffffffff and (a[1:, 0] < n - 1).all()
+        kids = np.sort(a[:n - 1, 1:].ravel())
+        assert np.array_equal(kids, np.arange(1, 2 * n - 1))
+
+
+def test_treelet_optimisation_equals_reference_text(built):
+    """One treelet-optimisation round (FormTreelet, FindOptimalPartitions — the SAH dynamic programme over the 128
+    subsets of 7 leaves — and ReformTree) of the oracle against the reference's own TreeletReorder.hlsl group shader
+    compiled from the mount and run by a 32-thread group with real barriers (oracle/_ref/libref_treelet.so): hierarchy
+    and boxes bit-identical, on Karras trees over random boxes, for treelet roots of every size class."""
+    import ctypes as C
+    from oracle import binding
+    path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_treelet.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_treelet.so not built (needs the reference mount at build time)")
+    ref = C.CDLL(path)
+    lib = binding.load()
+    for f in (ref.ref_treelet, lib.oracle_treelet):
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]; f.restype = None
+    lib.oracle_karras.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]; lib.oracle_karras.restype = None
+    rng = np.random.default_rng(9)
+    changed = 0
+    for trial in range(60):
+        n = int(rng.integers(8, 400))
+        codes = np.sort(rng.integers(0, 1 << 30, n, dtype=np.uint64).astype(np.uint32))
+        H = np.zeros((2 * n - 1, 3), np.uint32)
+        lib.oracle_karras(codes.ctypes.data, n, H.ctypes.data)
+        # leaf boxes: small boxes scattered in space (some flat, some huge); internal boxes fitted bottom-up
+        box = np.zeros((2 * n - 1, 6), np.float32)
+        c = rng.normal(0, 10, (n, 3)); e = np.abs(rng.normal(0, 1, (n, 3))) * rng.choice([0.0, 0.1, 1.0, 30.0], (n, 1))
+        box[n - 1:, :3] = c - e; box[n - 1:, 3:] = c + e
+
+        def fit(i):
+            if i >= n - 1:
+                return
+            l, r = int(H[i, 1]), int(H[i, 2])
+            fit(l); fit(r)
+            box[i, :3] = np.minimum(box[l, :3], box[r, :3]); box[i, 3:] = np.maximum(box[l, 3:], box[r, 3:])
+        import sys
+        sys.setrecursionlimit(10000)
+        fit(0)
+
+        def count(i):
+            return 1 if i >= n - 1 else count(int(H[i, 1])) + count(int(H[i, 2]))
+        roots = [i for i in range(n - 1) if count(i) >= 7]
+        for root in rng.choice(roots, min(6, len(roots)), replace=False):
+            Ha, Hb, ba, bb = H.copy(), H.copy(), box.copy(), box.copy()
+            lib.oracle_treelet(Ha.ctypes.data, ba.ctypes.data, n, int(root))
+            ref.ref_treelet(Hb.ctypes.data, bb.ctypes.data, n, int(root))
+            assert np.array_equal(Ha, Hb), (trial, n, root)
+            assert np.array_equal(ba.view(np.uint32), bb.view(np.uint32)), (trial, n, root)
+            changed += int(not np.array_equal(Ha, H))
+    assert changed > 50  # the optimisation really rewires most treelets
+
+
+def test_node_boxes_equal_reference_text(built):
+    """The two box constructors of the BVH node writer — leaf box from a triangle (min padded by 0.001, stored as
+    centre / half-extent) and parent box from two children's centre / half-extent boxes — against the reference's own
+    RayTracingHelper.hlsli text compiled from the mount (oracle/_ref/libref_boxes.so), bit for bit."""
+    import ctypes as C
+    from oracle import binding
+    path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_boxes.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_boxes.so not built (needs the reference mount at build time)")
+    ref = C.CDLL(path)
+    lib = binding.load()
+    fp = C.POINTER(C.c_float)
+    ref.ref_leaf_box.argtypes = [fp, C.c_int, fp, fp]; ref.ref_leaf_box.restype = C.c_uint32
+    lib.oracle_leaf_box.argtypes = [fp, fp, fp]; lib.oracle_leaf_box.restype = None
+    for f in (ref.ref_parent_box, lib.oracle_parent_box):
+        f.argtypes = [fp] * 6; f.restype = None
+    rng = np.random.default_rng(2)
+
+    def p(a):
+        return a.ctypes.data_as(fp)
+    for i in range(20000):
+        scale = np.float32(10.0 ** rng.uniform(-3, 4))
+        v = (rng.normal(0, 1, 9) * scale).astype(np.float32)
+        if i % 4 == 0: v[3:6] = v[0:3]                                      # degenerate
+        if i % 4 == 1: v[[1, 4, 7]] = v[1]                                  # axis-aligned flat: the 0.001 padding decides
+        c1, h1, c2, h2 = (np.zeros(3, np.float32) for _ in range(4))
+        lib.oracle_leaf_box(p(v), p(c1), p(h1))
+        flag = ref.ref_leaf_box(p(v), i, p(c2), p(h2))
+        assert np.array_equal(c1.view(np.uint32), c2.view(np.uint32)) and np.array_equal(h1.view(np.uint32), h2.view(np.uint32)), v
+        assert flag == (i | 0x80000000)
+        ac, bc = (rng.normal(0, 1, 3) * scale).astype(np.float32), (rng.normal(0, 1, 3) * scale).astype(np.float32)
+        ah, bh = (np.abs(rng.normal(0, 1, 3)) * scale).astype(np.float32), (np.abs(rng.normal(0, 1, 3)) * scale * 0.01).astype(np.float32)
+        lib.oracle_parent_box(p(ac), p(ah), p(bc), p(bh), p(c1), p(h1))
+        ref.ref_parent_box(p(ac), p(ah), p(bc), p(bh), p(c2), p(h2))
+        assert np.array_equal(c1.view(np.uint32), c2.view(np.uint32)) and np.array_equal(h1.view(np.uint32), h2.view(np.uint32)), (ac, ah, bc, bh)

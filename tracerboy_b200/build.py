@@ -197,6 +197,10 @@ def build_all(force=False, verbose=False):
     build_ref.build(force)
     build_ref.build_post(force)
     build_ref.build_traverse(force)
+    build_ref.build_morton(force)
+    build_ref.build_karras(force)
+    build_ref.build_treelet(force)
+    build_ref.build_boxes(force)
 
 
 if __name__ == "__main__":
