@@ -214,7 +214,38 @@ def build_boxes(force=False):
     return target
 
 
+STRUCTS = "/root/reference/TracerBoy/SharedShaderStructs.h"
+RAYGEN = "/root/reference/TracerBoy/RayGenCommon.h"
+
+
+def raygen_lib_path():
+    return os.path.join(OUT, "libref_raygen.so")
+
+
+def build_raygen(force=False):
+    """oracle/_ref/libref_raygen.so: light sampling, environment lookup, Halton and hash13 of RayGenCommon.h as host C++."""
+    target = raygen_lib_path()
+    if not (os.path.exists(STRUCTS) and os.path.exists(RAYGEN)):
+        return target if os.path.exists(target) else None
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_raygen.cpp")] + \
+           [STRUCTS, RAYGEN, os.path.join(HERE, "glue.h"), os.path.join(HERE, "liboracle.so")]
+    if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs):
+        return target
+    sys.path.insert(0, os.path.join(HERE, "ref"))
+    import prepass
+    prepass.run_raygen(STRUCTS, RAYGEN, os.path.join(OUT, "raygen_light_gen.inc"), os.path.join(OUT, "raygen_gen.inc"))
+    cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma", "-ffp-contract=off", "-fsingle-precision-constant", "-fno-fast-math",
+           "-fvisibility=hidden", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + HERE, os.path.join(HERE, "ref", "ref_raygen.cpp"),
+           "-o", target, "-L" + HERE, "-loracle", "-Wl,-rpath,$ORIGIN/.."]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref raygen build failed:\n" + r.stdout)
+    return target
+
+
 if __name__ == "__main__":
+    print(build_raygen(force="--force" in sys.argv))
     print(build_boxes(force="--force" in sys.argv))
     print(build_treelet(force="--force" in sys.argv))
     print(build_karras(force="--force" in sys.argv))

@@ -7,6 +7,7 @@
 #endif
 #include "../tracerboy_b200/csrc/common/tb_vec.h"
 #include "oracle.h"
+#include "glue.h"
 
 using namespace oracle;
 
@@ -134,6 +135,35 @@ ORACLE_API void oracle_karras(const uint32_t* codes, uint32_t n, uint32_t* out3)
 ORACLE_API void oracle_treelet(uint32_t* H3, float* aabb6, uint32_t n, uint32_t root) { oracle::treelet_public(H3, aabb6, n, root); }
 ORACLE_API void oracle_leaf_box(const float* v9, float* c3, float* h3) { oracle::leaf_box_public(v9, c3, h3); }
 ORACLE_API void oracle_parent_box(const float* ac, const float* ah, const float* bc, const float* bh, float* c3, float* h3) { oracle::parent_box_public(ac, ah, bc, bh, c3, h3); }
+// test hooks for oracle/ref/ref_raygen.cpp: the restated light sampling and environment lookup on caller-provided data
+ORACLE_API void oracle_light_sample(const TbLight* lights, uint32_t n, uint32_t nee, uint32_t sir, float debug1, float debug2, float time,
+                                    const float* pos, float* seed, float* out12) {
+    Scene sc;
+    sc.lights.assign(lights, lights + n);
+    RenderParams rp;
+    memset(&rp.settings, 0, sizeof(rp.settings));
+    rp.settings.EnableNextEventEstimation = nee; rp.settings.EnableSamplingImportanceResampling = sir;
+    rp.settings.DebugValue = debug1; rp.settings.DebugValue2 = debug2;
+    rp.time = time;
+    Ctx c(sc, rp);
+    c.seed = *seed;
+    tbm::f3 dir, col, nrm; float pdf, att;
+    get_one_light_sample(c, tbm::mk3(pos[0], pos[1], pos[2]), dir, col, pdf, nrm, att);
+    *seed = c.seed;
+    float o[12] = {dir.x, dir.y, dir.z, col.x, col.y, col.z, nrm.x, nrm.y, nrm.z, pdf, att, 0.0f};
+    memcpy(out12, o, sizeof(o));
+}
+ORACLE_API void oracle_env(const float* rgba, uint32_t w, uint32_t h, const float* transform12, const float* scale3, const float* v, float* out3) {
+    Scene sc;
+    sc.images.resize(1);
+    sc.images[0].width = w; sc.images[0].height = h; sc.images[0].format = 0;
+    sc.images[0].data.assign((const uint8_t*)rgba, (const uint8_t*)rgba + 16ull * w * h);
+    sc.envImage = 0;
+    for (int r = 0; r < 3; r++) sc.envTransform[r] = TbFloat4{transform12[4 * r], transform12[4 * r + 1], transform12[4 * r + 2], transform12[4 * r + 3]};
+    sc.envColorScale = TbFloat3{scale3[0], scale3[1], scale3[2]};
+    tbm::f3 c = sample_environment_map(sc, tbm::mk3(v[0], v[1], v[2]));
+    out3[0] = c.x; out3[1] = c.y; out3[2] = c.z;
+}
 ORACLE_API uint32_t oracle_morton(const float* centroid, const float* smin, const float* smax) {
     return oracle::morton_public(centroid, smin, smax);
 }

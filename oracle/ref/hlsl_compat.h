@@ -35,6 +35,7 @@ struct float3 {
     float2 xy() const { return float2(x, y); }
     float3 xyz() const { return *this; }
     float3 rgb() const { return *this; }
+    float3 yzx() const { return float3(y, z, x); }
 #ifdef RC_TRAVERSE
     void set_xy(float2 v) { x = v.x; y = v.y; }                      // `A.xy = ...` (TraverseFunction.hlsli:257-259)
     float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); } // `v[swizzleOrder.x]` (:225)

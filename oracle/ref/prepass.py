@@ -121,5 +121,25 @@ def run_boxes(src, dst):
     open(dst, "w").write(text)
 
 
+def run_raygen(structs_h, raygen_h, dst_light, dst):
+    """`struct Light` (with its HLSL-only GetPosition) and the pure functions of RayGenCommon.h: SampleEnvironmentMap,
+    Halton*, GetRandomBarycentric ... GetOneLightSample, hash13."""
+    sh = open(structs_h).read()
+    a, b = sh.index("struct Light\n{"), sh.index("struct AreaLightData") if "struct AreaLightData" in sh else None
+    e = sh.index("#define LIGHT_TYPE_DIRECTIONAL 1") + len("#define LIGHT_TYPE_DIRECTIONAL 1")
+    open(dst_light, "w").write(sh[a:e] + "\n")
+    t = open(raygen_h).read()
+    s1, e1 = t.index("float3 SampleEnvironmentMap(float3 v)"), t.index("float rand();")
+    s2, e2 = t.index("float Halton(int b, int i)"), t.index("struct BlueNoiseData")
+    s3 = t.index("float3 GetRandomBarycentric()")
+    e3 = t.index("float4 GetLastFrameData()") - 1                  # the function after GetOneLightSample
+    s4, e4 = t.index("float hash13(vec3 p3)"), t.index("bool ShouldSkipRay()")
+    text = t[s1:e1] + t[s2:e2] + t[s3:e3] + "\n" + t[s4:e4]
+    text = re.sub(r"\b(?:inout|out)\s+([A-Za-z_]\w*)\s+([A-Za-z_]\w*)", r"\1& \2", text)
+    text = re.sub(r"\bin\s+([A-Za-z_]\w*)\s+([A-Za-z_]\w*)", r"\1 \2", text)
+    text = re.sub(r"\.(xyz|rgb|xy|yzx)\b(?!\s*\()", r".\1()", text)
+    open(dst, "w").write(text)
+
+
 if __name__ == "__main__":
     run(sys.argv[1], sys.argv[2])

@@ -629,3 +629,78 @@ def test_node_boxes_equal_reference_text(built):
         lib.oracle_parent_box(p(ac), p(ah), p(bc), p(bh), p(c1), p(h1))
         ref.ref_parent_box(p(ac), p(ah), p(bc), p(bh), p(c2), p(h2))
         assert np.array_equal(c1.view(np.uint32), c2.view(np.uint32)) and np.array_equal(h1.view(np.uint32), h2.view(np.uint32)), (ac, ah, bc, bh)
+
+
+def test_raygen_glue_equals_reference_text(built):
+    """The restated RayGenCommon.h glue against the reference's own text compiled from the mount
+    (oracle/_ref/libref_raygen.so): GetOneLightSample (uniform and 16-candidate SIR, area and directional lights, NEE
+    off, the DebugValue override) incl. the rand() stream position afterwards; SampleEnvironmentMap (transform, the
+    3.14 constants, bilinear fetch) on a random HDR lat-long image; hash13 and Halton."""
+    import ctypes as C
+    from oracle import binding
+    path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_raygen.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_raygen.so not built (needs the reference mount at build time)")
+    lib = binding.load()
+    ref = C.CDLL(path)
+    fp = C.POINTER(C.c_float)
+    sig = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, fp, fp, fp]
+    for f in (lib.oracle_light_sample, ref.ref_light_sample):
+        f.argtypes = sig; f.restype = None
+    for f in (lib.oracle_env, ref.ref_env):
+        f.argtypes = [fp, C.c_uint32, C.c_uint32, fp, fp, fp, fp]; f.restype = None
+    ref.ref_hash13.argtypes = [C.c_float] * 3; ref.ref_hash13.restype = C.c_float
+    ref.ref_halton.argtypes = [C.c_int, C.c_int]; ref.ref_halton.restype = C.c_float
+    rng = np.random.default_rng(4)
+
+    def p(a):
+        return a.ctypes.data_as(fp)
+    # lights: TbLight = 26 words (type, colour3, area, P0 P1 P2, N0 N1 N2, direction)
+    nl = 9
+    lights = np.zeros((nl, 26), np.float32)
+    lights[:, 1:4] = rng.uniform(0.1, 20, (nl, 3))
+    lights[:, 4] = rng.uniform(0.01, 5, nl)
+    lights[:, 5:14] = rng.normal(0, 3, (nl, 9))
+    nrm = rng.normal(0, 1, (nl, 3, 3)); nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    lights[:, 14:23] = nrm.reshape(nl, 9)
+    d = rng.normal(0, 1, (nl, 3)); lights[:, 23:26] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    types = np.zeros(nl, np.uint32); types[[2, 5]] = 1            # two directional lights
+    lights.view(np.uint32)[:, 0] = types
+    for i in range(3000):
+        pos = rng.normal(0, 4, 3).astype(np.float32)
+        nee, sir = int(i % 7 != 0), int(i % 3 == 0)
+        dbg = np.float32(1.0 if i % 2 else 0.0)                     # DebugValue defaults to 1: the override is live
+        n = nl if i % 11 else 0
+        s1 = np.array([rng.uniform(0, 1)], np.float32); s2 = s1.copy()
+        o1, o2 = np.zeros(12, np.float32), np.zeros(12, np.float32)
+        lib.oracle_light_sample(lights.ctypes.data, n, nee, sir, dbg, np.float32(0.7), np.float32(0.25 * (i % 3)), p(pos), p(s1), p(o1))
+        ref.ref_light_sample(lights.ctypes.data, n, nee, sir, dbg, np.float32(0.7), np.float32(0.25 * (i % 3)), p(pos), p(s2), p(o2))
+        assert s1[0] == s2[0], "rand() stream position differs (%d)" % i
+        assert ((o1.view(np.uint32) == o2.view(np.uint32)) | (np.isnan(o1) & np.isnan(o2))).all(), (i, o1, o2)
+    # environment lookup
+    w, h = 64, 32
+    env = np.exp(rng.normal(0, 1, (h, w, 4))).astype(np.float32)
+    ang = 0.7
+    tr = np.array([[np.cos(ang), 0, np.sin(ang), 0], [0.1, 0.9, -0.2, 0], [-np.sin(ang), 0.3, np.cos(ang), 0]], np.float32)
+    scale = np.array([1.5, 0.5, 2.0], np.float32)
+    for i in range(3000):
+        v = rng.normal(0, 1, 3).astype(np.float32)
+        if i % 50 == 0: v[:] = [0, 0, 1]                              # pole
+        if i % 50 == 1: v[:] = [-1, 0, 0]                             # the atan2 seam
+        a, b = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        lib.oracle_env(p(env), w, h, p(tr), p(scale), p(v), p(a))
+        ref.ref_env(p(env), w, h, p(tr), p(scale), p(v), p(b))
+        assert ((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all(), (v, a, b)
+    # hash13 / Halton
+    xs = rng.integers(0, 4096, (2000, 3)).astype(np.float32)
+    got = np.zeros(2000, np.float32)
+    lib.oracle_math_eval(7, xs.ctypes.data, None, got.ctypes.data, 2000)
+    want = np.array([ref.ref_hash13(*map(float, x)) for x in xs], np.float32)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    idx = np.arange(0, 3000, dtype=np.float32)
+    for base in (2, 3):
+        got = np.zeros(3000, np.float32)
+        bases = np.full(3000, base, np.float32)
+        lib.oracle_math_eval(8, idx.ctypes.data, bases.ctypes.data, got.ctypes.data, 3000)
+        want = np.array([ref.ref_halton(base, int(i)) for i in idx], np.float32)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

@@ -201,6 +201,7 @@ def build_all(force=False, verbose=False):
     build_ref.build_karras(force)
     build_ref.build_treelet(force)
     build_ref.build_boxes(force)
+    build_ref.build_raygen(force)
 
 
 if __name__ == "__main__":
