@@ -564,10 +564,10 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
     const uint32_t lane = threadIdx.x & 31;
     uint32_t rays = 0, ntris = 0, nboxes = 0;
     Traversal tr;
-    uint32_t stack[TB_STACK_DEPTH];
-    tr.sp = 0; tr.cur = TB_NO_NODE;
+    uint32_t stack[TB_STACK_WORDS];
+    tr.idle(stack);
     bool haveRay = false, exhausted = false; // haveRay: this lane owns a ray (traversing or finished, not yet retired)
-    uint32_t pi = 0, steps = 0;
+    uint32_t pi = 0, suspendAt = budgetMain; // suspendAt: node visits (tr.steps()) after which the ray is parked
     while (true) {
         // ---- service phase (whole warp): retire finished rays, park rays over budget, refill idle lanes
         bool retired = false, retiredHit = false;
@@ -585,9 +585,9 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
                 retired = true;
             }
             haveRay = false;
-        } else if (KIND == EXT_MAIN && haveRay && steps >= budgetMain) {
-            if (try_suspend(st, 0, tr, stack, pi)) haveRay = false;
-            else steps = 0; // buffer full: keep going here
+        } else if (KIND == EXT_MAIN && haveRay && tr.steps() >= suspendAt) {
+            if (try_suspend(st, 0, tr, stack, pi)) { haveRay = false; tr.cur = TB_NO_NODE; }
+            else suspendAt += budgetMain; // buffer full: keep going here
         }
         if (KIND == EXT_MAIN) { // sort retired paths into the hit / miss queues (material-class split of the shading stage)
             uint32_t mh = __ballot_sync(0xffffffffu, retired && retiredHit), mm = __ballot_sync(0xffffffffu, retired && !retiredHit);
@@ -613,9 +613,9 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
                 if (i < count) {
                     pi = __ldg(queue + i);
                     float4 o = rayO[pi], d = rayD[pi];
-                    tr.begin(bvh, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), MIN_T, FAR_T);
+                    tr.begin(bvh, stack, mk3(o.x, o.y, o.z), mk3(d.x, d.y, d.z), MIN_T, FAR_T);
                     haveRay = true;
-                    steps = 0;
+                    suspendAt = budgetMain;
                 }
             }
             if (base + (uint32_t)__popc(idle) >= count) exhausted = true;
@@ -634,9 +634,9 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
             uint32_t nB = __popc(mB), nL = __popc(mL);
             if (nB == 0 || (!exhausted && nB < refillBelow) || (KIND == EXT_MAIN && exhausted && iter >= 64u)) break;
             if (2 * nL > nB) {
-                if (wantLeaf) { tr.step_leaf(stack, tris); steps++; }
+                if (wantLeaf) tr.step_leaf(stack, tris);
             } else {
-                if (busy && !wantLeaf) { tr.step_internal(stack, pairs); steps++; }
+                if (busy && !wantLeaf) tr.step_internal(stack, pairs);
             }
         }
     }
@@ -653,18 +653,17 @@ __global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState 
     const uint32_t* __restrict__ in = st.susBuf[(round - 1) & 1];
     uint32_t rays = 0, ntris = 0, nboxes = 0;
     Traversal tr;
-    uint32_t stack[TB_STACK_DEPTH];
+    uint32_t stack[TB_STACK_WORDS];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         uint32_t pi = tr.resume(bvh, in + (size_t)i * Traversal::kRecordWords, stack, st.rayO, st.rayD, MIN_T, FAR_T);
-        uint32_t steps = 0;
+        uint32_t suspendAt = tr.steps() + budget;
         while (true) {
             if (tr.done()) { push_sorted(st, qi, pi, write_hit(st, tr, pi, bounceIsZero, outputHeatmap, aovMask, rays, ntris, nboxes)); break; }
-            if (budget && steps >= budget) {
+            if (budget && tr.steps() >= suspendAt) {
                 if (try_suspend(st, round, tr, stack, pi)) break;
-                steps = 0;
+                suspendAt += budget;
             }
             tr.step(stack, pairs, tris);
-            steps++;
         }
     }
     flush_stats(st, 6, rays, ntris, nboxes);
@@ -1080,8 +1079,8 @@ __global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, 
     const uint32_t lane = threadIdx.x & 31;
     uint32_t rays = 0, ntris = 0, nboxes = 0;
     Traversal tr;
-    uint32_t stack[TB_STACK_DEPTH];
-    tr.sp = 0; tr.cur = TB_NO_NODE;
+    uint32_t stack[TB_STACK_WORDS];
+    tr.idle(stack);
     bool have = false, exhausted = false;
     Walker w;
     w.pi = 0; w.sw = 0; w.rng.seed = 0.0f; w.rng.time = fc.time;
@@ -1095,7 +1094,7 @@ __global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, 
             tr.result(h);
             rays++; ntris += h.tris; nboxes += h.boxes;
             if (fc.aovMask & AOV_FULL) { uint2 c = st.counters[w.pi]; c.x += h.tris; c.y += h.boxes; st.counters[w.pi] = c; }
-            if (walk_step(sc, w, h.t, h.b1, h.b2, h.geom, h.prim)) tr.begin(bvh, w.org, w.dir, MIN_T, FAR_T);
+            if (walk_step(sc, w, h.t, h.b1, h.b2, h.geom, h.prim)) tr.begin(bvh, stack, w.org, w.dir, MIN_T, FAR_T);
             else { alive = walk_finish(fc, st, w); have = false; }
         }
         append_warp(&st.queueCount[qi ^ 1], st.queue[qi ^ 1], alive, w.pi); // survivors join the next bounce's queue
@@ -1108,7 +1107,7 @@ __global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, 
                 uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
                 if (i < count) {
                     walker_load(st, fc, st.walkQueue[wr][i], w);
-                    tr.begin(bvh, w.org, w.dir, MIN_T, FAR_T);
+                    tr.begin(bvh, stack, w.org, w.dir, MIN_T, FAR_T);
                     have = true;
                 }
             }

@@ -24,16 +24,26 @@ struct HitRec {
 };
 
 #define TB_STACK_DEPTH 96
+// The memory stack is `uint32_t stack[TB_STACK_WORDS]`: word 0 is a sentinel (TB_NO_NODE, written by
+// begin()/resume()), words 1..depth are the waiting far children. Popping the sentinel ends the traversal,
+// so pop is one unconditional load with no emptiness test.
+#define TB_STACK_WORDS (TB_STACK_DEPTH + 1)
 
-__device__ __forceinline__ bool slab(float& resultT, float closestT, tbm::f3 oinv, tbm::f3 inv, tbm::f3 ainv,
-                                     float cx, float cy, float cz, float hx, float hy, float hz) {
+// RayBoxTest (TraverseFunction.hlsli:203-221) as an interval: the box is hit iff enter < exit, and `enter` is the
+// reference's resultT. Returned by value so that neither end ever has its address taken (a by-reference result
+// shared with the out-of-line zero-axis variant used to pin both entry distances in local memory).
+struct SlabRange { float enter, exit; };
+__device__ __forceinline__ SlabRange slab(float closestT, tbm::f3 oinv, tbm::f3 inv, tbm::f3 ainv,
+                                          float cx, float cy, float cz, float hx, float hy, float hz) {
     float rx = fmaf(cx, inv.x, -oinv.x), ry = fmaf(cy, inv.y, -oinv.y), rz = fmaf(cz, inv.z, -oinv.z);
     float maxx = fmaf(hx, ainv.x, rx), maxy = fmaf(hy, ainv.y, ry), maxz = fmaf(hz, ainv.z, rz);
     float minx = fmaf(-hx, ainv.x, rx), miny = fmaf(-hy, ainv.y, ry), minz = fmaf(-hz, ainv.z, rz);
     float minT = fmaxf(fmaxf(minx, miny), minz);
     float maxT = fminf(fminf(maxx, maxy), maxz);
-    resultT = fmaxf(minT, 0.0f);
-    return fmaxf(minT, 0.0f) < fminf(maxT, closestT);
+    SlabRange r;
+    r.enter = fmaxf(minT, 0.0f);
+    r.exit = fminf(maxT, closestT);
+    return r;
 }
 
 // 256-bit read-only global load (32-byte aligned)
@@ -49,8 +59,8 @@ __device__ __forceinline__ bool zero_axis_inside(float c, float h, float o) {
     float tol = h + 1.0e-5f * t;
     return fabsf(c - o) <= tol;
 }
-__device__ __noinline__ bool slab_zero(float& resultT, float closestT, tbm::f3 org, int zmask, tbm::f3 oinv, tbm::f3 inv, tbm::f3 ainv,
-                                       float cx, float cy, float cz, float hx, float hy, float hz) {
+__device__ __noinline__ SlabRange slab_zero(float closestT, tbm::f3 org, int zmask, tbm::f3 oinv, tbm::f3 inv, tbm::f3 ainv,
+                                            float cx, float cy, float cz, float hx, float hy, float hz) {
     float rx = fmaf(cx, inv.x, -oinv.x), ry = fmaf(cy, inv.y, -oinv.y), rz = fmaf(cz, inv.z, -oinv.z);
     float maxx = fmaf(hx, ainv.x, rx), maxy = fmaf(hy, ainv.y, ry), maxz = fmaf(hz, ainv.z, rz);
     float minx = fmaf(-hx, ainv.x, rx), miny = fmaf(-hy, ainv.y, ry), minz = fmaf(-hz, ainv.z, rz);
@@ -61,8 +71,10 @@ __device__ __noinline__ bool slab_zero(float& resultT, float closestT, tbm::f3 o
     if (zmask & 4) { minz = -inf; maxz = inf; inside = inside && zero_axis_inside(cz, hz, org.z); }
     float minT = fmaxf(fmaxf(minx, miny), minz);
     float maxT = fminf(fminf(maxx, maxy), maxz);
-    resultT = fmaxf(minT, 0.0f);
-    return inside && fmaxf(minT, 0.0f) < fminf(maxT, closestT);
+    SlabRange r;
+    r.enter = fmaxf(minT, 0.0f);
+    r.exit = inside ? fminf(maxT, closestT) : -inf; // outside on a zero axis: empty interval
+    return r;
 }
 
 // Resumable traversal: begin() once per ray, then step_internal()/step_leaf() on the current
@@ -77,13 +89,17 @@ struct Traversal {
     tbm::f3 org, inv, oinv, shear;
     int kx, ky, kz;
     float tmin, tmax, committedT, hb1, hb2;
-    uint32_t hitGeom, hitPrim, trisTested, boxesTested;
+    uint32_t hitGeom, hitPrim, trisTested, pairsTested; // BoxesTested = 2 x pairsTested (:751 counts both children)
     bool haveHit;
-    int zmask;    // bit a set: direction component a is exactly zero (deviation D6)
-    uint32_t cur; // node reference to process next (TB_NO_NODE = traversal finished)
-    int sp;       // entries in the memory stack below `cur`
+    int zmask;     // bit a set: direction component a is exactly zero (deviation D6)
+    uint32_t cur;  // node reference to process next (TB_NO_NODE = traversal finished)
+    int sp;        // index of the top entry of the memory stack (0: only the sentinel is left)
 
-    __device__ __forceinline__ void begin(const DeviceBvh& bvh, tbm::f3 o, tbm::f3 dir, float tmin_, float tmax_) {
+    __device__ __forceinline__ uint32_t boxes_tested() const { return 2u * pairsTested; }
+    __device__ __forceinline__ uint32_t steps() const { return trisTested + pairsTested; } // node visits so far
+    __device__ __forceinline__ void idle(uint32_t* stack) { stack[0] = TB_NO_NODE; sp = 0; cur = TB_NO_NODE; }
+
+    __device__ __forceinline__ void begin(const DeviceBvh& bvh, uint32_t* stack, tbm::f3 o, tbm::f3 dir, float tmin_, float tmax_) {
         using namespace tbm;
         org = o;
         inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z); // GetRayData, TraverseFunction.hlsli:473-495
@@ -101,12 +117,13 @@ struct Traversal {
         shear = mk3(comp(dir, kx) / dz, comp(dir, ky) / dz, 1.0f / dz);
         tmin = tmin_; tmax = tmax_; committedT = tmax_;
         haveHit = false; hitGeom = hitPrim = 0xffffffffu; hb1 = hb2 = 0.0f;
-        trisTested = boxesTested = 0;
+        trisTested = pairsTested = 0;
+        stack[0] = TB_NO_NODE;
         sp = 0;
         cur = TB_NO_NODE;
-        float unusedT;
-        bool rootHit = zmask ? slab_zero(unusedT, committedT, org, zmask, oinv, inv, abs3(inv), bvh.root.c[0], bvh.root.c[1], bvh.root.c[2], bvh.root.h[0], bvh.root.h[1], bvh.root.h[2])
-                             : slab(unusedT, committedT, oinv, inv, abs3(inv), bvh.root.c[0], bvh.root.c[1], bvh.root.c[2], bvh.root.h[0], bvh.root.h[1], bvh.root.h[2]);
+        const SlabRange rr = zmask ? slab_zero(committedT, org, zmask, oinv, inv, abs3(inv), bvh.root.c[0], bvh.root.c[1], bvh.root.c[2], bvh.root.h[0], bvh.root.h[1], bvh.root.h[2])
+                                   : slab(committedT, oinv, inv, abs3(inv), bvh.root.c[0], bvh.root.c[1], bvh.root.c[2], bvh.root.h[0], bvh.root.h[1], bvh.root.h[2]);
+        const bool rootHit = rr.enter < rr.exit;
         // Deviation D7: a ray with a NaN origin or direction component can never commit a hit (t0 is
         // NaN), but its NaN slabs are dropped by min/max, so literally it walks every node overlapping the other
         // axes (the whole tree for an all-NaN direction). It is reported as the miss it is, with zero tests.
@@ -116,10 +133,10 @@ struct Traversal {
     }
     __device__ __forceinline__ bool done() const { return cur == TB_NO_NODE; }
     __device__ __forceinline__ bool at_leaf() const { return (cur & 0x80000000u) != 0; }
-    __device__ __forceinline__ void pop(const uint32_t* stack) { cur = sp > 0 ? stack[--sp] : TB_NO_NODE; }
+    __device__ __forceinline__ void pop(const uint32_t* stack) { cur = stack[sp]; --sp; } // the sentinel ends the traversal
 
     // cur is a leaf: RayTriangleIntersect, TraverseFunction.hlsli:231-313 (two-sided, `precise` => unfused)
-    __device__ __forceinline__ void step_leaf(uint32_t* stack, const float4* __restrict__ tris) {
+    __device__ __forceinline__ void step_leaf(const uint32_t* stack, const float4* __restrict__ tris) {
         using namespace tbm;
         uint32_t slot = cur & 0x3fffffffu;
         float4 q0 = __ldg(tris + 3 * (size_t)slot), q1 = __ldg(tris + 3 * (size_t)slot + 1), q2 = __ldg(tris + 3 * (size_t)slot + 2);
@@ -165,26 +182,28 @@ struct Traversal {
         ldg256(pairs + 4 * (size_t)ref, a, b);
         ldg256(pairs + 4 * (size_t)ref + 2, c, d);
         f3 ainv = abs3(inv);
-        float lt, rt;
-        bool lh, rh;
+        SlabRange L, R;
         if (zmask) { // rare path, kept out of line
-            lh = slab_zero(lt, committedT, org, zmask, oinv, inv, ainv, a.x, a.y, a.z, b.x, b.y, b.z);
-            rh = slab_zero(rt, committedT, org, zmask, oinv, inv, ainv, c.x, c.y, c.z, d.x, d.y, d.z);
+            L = slab_zero(committedT, org, zmask, oinv, inv, ainv, a.x, a.y, a.z, b.x, b.y, b.z);
+            R = slab_zero(committedT, org, zmask, oinv, inv, ainv, c.x, c.y, c.z, d.x, d.y, d.z);
         } else {
-            lh = slab(lt, committedT, oinv, inv, ainv, a.x, a.y, a.z, b.x, b.y, b.z);
-            rh = slab(rt, committedT, oinv, inv, ainv, c.x, c.y, c.z, d.x, d.y, d.z);
+            L = slab(committedT, oinv, inv, ainv, a.x, a.y, a.z, b.x, b.y, b.z);
+            R = slab(committedT, oinv, inv, ainv, c.x, c.y, c.z, d.x, d.y, d.z);
         }
-        boxesTested += 2;
-        uint32_t lref = __float_as_uint(a.w), rref = __float_as_uint(b.w);
-        if (lh && rh) {
-            bool rightFirst = rt < lt;
-            if (sp < TB_STACK_DEPTH) stack[sp++] = rightFirst ? lref : rref; // far child waits in memory
-            cur = rightFirst ? rref : lref;                                  // near child is visited next
-        } else if (lh || rh) {
-            cur = rh ? rref : lref;
-        } else {
-            pop(stack);
-        }
+        const bool lh = L.enter < L.exit, rh = R.enter < R.exit;
+        const float lt = L.enter, rt = R.enter;
+        pairsTested++;
+        const uint32_t lref = __float_as_uint(a.w), rref = __float_as_uint(b.w);
+        // Branch-free child selection (the three outcomes used to serialise as divergent branches):
+        // the near child (or the only one hit) is visited next, the far child of a two-hit node waits in
+        // memory (predicated store), a node with no hit pops (predicated load).
+        const bool both = lh && rh;
+        const bool takeRight = rh && (!lh || rt < lt); // both hit: right only when strictly nearer (:754-765)
+        const uint32_t nearRef = takeRight ? rref : lref;
+        const uint32_t farRef = takeRight ? lref : rref;
+        if (both && sp < TB_STACK_DEPTH) { ++sp; stack[sp] = farRef; }
+        cur = nearRef;
+        if (!(lh || rh)) pop(stack);
     }
     __device__ __forceinline__ void step(uint32_t* stack, const float4* __restrict__ pairs, const float4* __restrict__ tris) {
         if (at_leaf()) step_leaf(stack, tris); else step_internal(stack, pairs);
@@ -198,8 +217,8 @@ struct Traversal {
         uint4* r4 = (uint4*)rec;
         r4[0] = make_uint4(pi, (uint32_t)sp, __float_as_uint(committedT), __float_as_uint(hb1));
         r4[1] = make_uint4(__float_as_uint(hb2), hitGeom, hitPrim, haveHit ? 1u : 0u);
-        r4[2] = make_uint4(trisTested, boxesTested, cur, 0u);
-        for (int i = 0; i < sp; i++) rec[12 + i] = stack[i];
+        r4[2] = make_uint4(trisTested, pairsTested, cur, 0u);
+        for (int i = 0; i < sp; i++) rec[12 + i] = stack[1 + i];
     }
     // ray setup is recomputed from the ray (same arithmetic => same values), the rest is restored
     __device__ __forceinline__ uint32_t resume(const DeviceBvh& bvh, const uint32_t* __restrict__ rec, uint32_t* stack,
@@ -208,17 +227,17 @@ struct Traversal {
         uint4 a = r4[0], b = r4[1], c = r4[2];
         uint32_t pi = a.x;
         float4 o = rayO[pi], d = rayD[pi];
-        begin(bvh, tbm::mk3(o.x, o.y, o.z), tbm::mk3(d.x, d.y, d.z), tmin_, tmax_);
+        begin(bvh, stack, tbm::mk3(o.x, o.y, o.z), tbm::mk3(d.x, d.y, d.z), tmin_, tmax_);
         sp = (int)a.y; committedT = __uint_as_float(a.z); hb1 = __uint_as_float(a.w);
         hb2 = __uint_as_float(b.x); hitGeom = b.y; hitPrim = b.z; haveHit = b.w != 0;
-        trisTested = c.x; boxesTested = c.y; cur = c.z;
-        for (int i = 0; i < sp; i++) stack[i] = rec[12 + i];
+        trisTested = c.x; pairsTested = c.y; cur = c.z;
+        for (int i = 0; i < sp; i++) stack[1 + i] = rec[12 + i];
         return pi;
     }
 
     __device__ __forceinline__ void result(HitRec& out) const {
         out.tris = trisTested;
-        out.boxes = boxesTested;
+        out.boxes = boxes_tested();
         if (haveHit && committedT < tmax) { out.t = committedT; out.b1 = hb1; out.b2 = hb2; out.prim = hitPrim; out.geom = hitGeom; }
         else { out.t = -1.0f; out.b1 = out.b2 = 0.0f; out.prim = out.geom = 0xffffffffu; }
     }
@@ -226,8 +245,8 @@ struct Traversal {
 
 __device__ __forceinline__ void trace_ray(const DeviceBvh& bvh, tbm::f3 org, tbm::f3 dir, float tmin, float tmax, HitRec& out) {
     Traversal tr;
-    uint32_t stack[TB_STACK_DEPTH];
-    tr.begin(bvh, org, dir, tmin, tmax);
+    uint32_t stack[TB_STACK_WORDS];
+    tr.begin(bvh, stack, org, dir, tmin, tmax);
     const float4* __restrict__ pairs = (const float4*)bvh.pairs;
     const float4* __restrict__ tris = (const float4*)bvh.tris;
     while (!tr.done()) tr.step(stack, pairs, tris);
