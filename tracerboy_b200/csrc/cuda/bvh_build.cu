@@ -330,135 +330,182 @@ __constant__ uint8_t c_masksBySize[128];
 __constant__ uint8_t c_sizeStart[9];
 
 // TreeletReorder.hlsl:38-312 — one warp per base treelet root, climbing to the BVH root.
-__global__ void __launch_bounds__(128, 5) k_treelet_reorder(uint32_t n, HNode* H, float* aabb, uint32_t* numTris,
+//
+// The pass is a chain of dependent L2 round trips per treelet (every word handed between warps goes through
+// ld.cg / st.cg), so the kernel is organised around having as few of them as possible on the critical path
+// (profiles/: the first version spent ~30 per treelet and 83 % of the 20 M-triangle build):
+//  * every lane that holds a treelet leaf keeps that node's box AND its two children in registers, loaded in
+//    one round trip when the lane receives the node; expanding the largest leaf is then shuffles only;
+//  * the record of the root's parent (needed for the climb) is requested before FormTreelet starts;
+//  * ReformTree: lane 0 derives the topology from the partition table (registers + shared memory only, same
+//    allocation order as the reference's stack walk), lanes 0..5 then write one internal node each; a new
+//    node's box is the union of the treelet leaves in its subset, which is bit-identical to the reference's
+//    bottom-up recombination because min/max are exact and order-independent;
+//  * the climb carries the parent's record, box and triangle count into the next iteration in registers.
+__global__ void __launch_bounds__(128, 8) k_treelet_reorder(uint32_t n, HNode* H, float* aabb, uint32_t* numTris,
                                                          const uint32_t* baseCount, const uint32_t* baseRoots) {
     const uint32_t warpsPerBlock = blockDim.x / 32;
     const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x & 31;
-    const uint32_t nInternal = n - 1;
+    const uint32_t nInternal = n - 1, total = 2 * n - 1;
+    const uint32_t FULL = 0xffffffffu;
     __shared__ float s_cost[4][128];
     __shared__ uint8_t s_part[4][128];
     __shared__ float s_box[4][7][6];
+    __shared__ uint32_t s_new[4][6][3]; // per new internal node: leaf subset, left child code, right child code
     float* cost = s_cost[warp];
     uint8_t* part = s_part[warp];
     const uint32_t numRoots = *baseCount;
     for (uint32_t w = blockIdx.x * warpsPerBlock + warp; w < numRoots; w += gridDim.x * warpsPerBlock) {
         uint32_t root = baseRoots[w];
+        // the root's record; every lane reads the same words (one broadcast transaction each)
+        uint32_t rl = ld_u(&H[root].left), rr = ld_u(&H[root].right), rparent = ld_u(&H[root].parent);
+        uint32_t mine = ld_u(&numTris[root]);
+        Box rb = ld_box(aabb, root);
         while (true) {
-            // ---- FormTreelet: lanes 0..6 hold the treelet leaves, lanes 0..5 the internal nodes
-            uint32_t leaf = 0xffffffffu, internal = 0xffffffffu;
-            if (lane == 0) { leaf = ld_u(&H[root].left); internal = root; }
-            if (lane == 1) leaf = ld_u(&H[root].right);
+            // the parent's record is only needed by the climb: requested now, consumed after the treelet is done.
+            // Nobody rewrites it before this warp (or its sibling's) has climbed there.
+            uint32_t pl = 0, pr = 0, pparent = 0;
+            if (root != 0) { pl = ld_u(&H[rparent].left); pr = ld_u(&H[rparent].right); pparent = ld_u(&H[rparent].parent); }
+            // ---- FormTreelet: lanes 0..6 hold the treelet leaves (id, box, children), lanes 0..5 the internal nodes
+            uint32_t leaf = 0xffffffffu, internal = 0xffffffffu, cl = 0xffffffffu, cr = 0xffffffffu;
+            Box lb; lb.mn = mk3(FLT_MAX); lb.mx = mk3(-FLT_MAX);
+            if (lane == 0) { leaf = rl; internal = root; }
+            if (lane == 1) leaf = rr;
+            if (lane < 2) {
+                lb = ld_box(aabb, leaf);
+                if (leaf < nInternal) { cl = ld_u(&H[leaf].left); cr = ld_u(&H[leaf].right); }
+            }
+            bool degenerate = false;
             for (uint32_t size = 2; size < 7; size++) {
                 float sa = 0.0f;
-                if (lane < size && leaf < nInternal) sa = surface_area(ld_box(aabb, leaf));
+                if (lane < size && leaf < nInternal) sa = surface_area(lb);
                 // argmax, first index wins on ties, must be strictly > 0
                 float best = sa; uint32_t bestLane = lane;
 #pragma unroll
                 for (int o = 4; o > 0; o >>= 1) { // lanes 0..7 are enough
-                    float os = __shfl_xor_sync(0xffffffffu, best, o);
-                    uint32_t ol = __shfl_xor_sync(0xffffffffu, bestLane, o);
+                    float os = __shfl_xor_sync(FULL, best, o);
+                    uint32_t ol = __shfl_xor_sync(FULL, bestLane, o);
                     if (os > best || (os == best && ol < bestLane)) { best = os; bestLane = ol; }
                 }
-                bestLane = __shfl_sync(0xffffffffu, bestLane, 0);
-                uint32_t pick = __shfl_sync(0xffffffffu, leaf, bestLane);
-                uint32_t pl = ld_u(&H[pick].left), pr = ld_u(&H[pick].right);
-                if (lane == bestLane) leaf = pl;
-                if (lane == size) leaf = pr;
+                bestLane = __shfl_sync(FULL, bestLane, 0);
+                const uint32_t pick = __shfl_sync(FULL, leaf, bestLane);
+                const uint32_t pcl = __shfl_sync(FULL, cl, bestLane), pcr = __shfl_sync(FULL, cr, bestLane);
+                // No expandable leaf (every candidate has a zero-area or NaN box): the reference then follows
+                // whatever the node array holds for a leaf; here the treelet is left as it is.
+                if (pick >= nInternal) { degenerate = true; break; }
+                bool fresh = false;
+                if (lane == bestLane) { leaf = pcl; fresh = true; }
+                if (lane == size) { leaf = pcr; fresh = true; }
                 if (lane == size - 1) internal = pick;
+                if (fresh) {
+                    cl = cr = 0xffffffffu;
+                    if (leaf < total) lb = ld_box(aabb, leaf);
+                    if (size < 6 && leaf < nInternal) { cl = ld_u(&H[leaf].left); cr = ld_u(&H[leaf].right); }
+                }
             }
-            // lane (size-1) collected internals for size=2..6 -> lanes 1..5; lane 0 has root
-            Box lb;
-            if (lane < 7) {
-                lb = ld_box(aabb, leaf);
-                float* sb = s_box[warp][lane];
-                sb[0] = lb.mn.x; sb[1] = lb.mn.y; sb[2] = lb.mn.z; sb[3] = lb.mx.x; sb[4] = lb.mx.y; sb[5] = lb.mx.z;
-            }
-            __syncwarp();
-            // ---- FindOptimalPartitions
-            Box rb = ld_box(aabb, root);
-            float rootSA = surface_area(rb);
-            for (uint32_t mask = lane * 4; mask < lane * 4 + 4; mask++) {
-                if (mask == 0) { cost[0] = 0.0f; continue; }
-                Box b; b.mn = mk3(FLT_MAX); b.mx = mk3(-FLT_MAX);
+            if (!degenerate) {
+                if (lane < 7) {
+                    float* sb = s_box[warp][lane];
+                    sb[0] = lb.mn.x; sb[1] = lb.mn.y; sb[2] = lb.mn.z; sb[3] = lb.mx.x; sb[4] = lb.mx.y; sb[5] = lb.mx.z;
+                }
+                __syncwarp();
+                // ---- FindOptimalPartitions
+                float rootSA = surface_area(rb);
+                for (uint32_t mask = lane * 4; mask < lane * 4 + 4; mask++) {
+                    if (mask == 0) { cost[0] = 0.0f; continue; }
+                    Box b; b.mn = mk3(FLT_MAX); b.mx = mk3(-FLT_MAX);
 #pragma unroll
-                for (uint32_t i = 0; i < 7; i++)
-                    if ((1u << i) & mask) {
-                        const float* sb = s_box[warp][i];
-                        Box t; t.mn = mk3(sb[0], sb[1], sb[2]); t.mx = mk3(sb[3], sb[4], sb[5]);
-                        b = combine(b, t);
+                    for (uint32_t i = 0; i < 7; i++)
+                        if ((1u << i) & mask) {
+                            const float* sb = s_box[warp][i];
+                            Box t; t.mn = mk3(sb[0], sb[1], sb[2]); t.mx = mk3(sb[3], sb[4], sb[5]);
+                            b = combine(b, t);
+                        }
+                    cost[mask] = surface_area(b);
+                }
+                __syncwarp();
+                if (lane < 7) cost[1u << lane] = 1.0f * surface_area(lb) / rootSA;
+                __syncwarp();
+                for (uint32_t sz = 2; sz <= 7; sz++) {
+                    for (uint32_t k = c_sizeStart[sz] + lane; k < c_sizeStart[sz + 1]; k += 32) {
+                        uint32_t mask = c_masksBySize[k];
+                        float lowest = FLT_MAX;
+                        uint32_t bestP = 0;
+                        uint32_t delta = (mask - 1) & mask;
+                        uint32_t p = (0u - delta) & mask;
+                        do {
+                            float c = cost[p] + cost[mask ^ p];
+                            if (c < lowest) { lowest = c; bestP = p; }
+                            p = (p - delta) & mask;
+                        } while (p != 0);
+                        cost[mask] = 1.0f * cost[mask] + lowest;
+                        part[mask] = (uint8_t)bestP;
                     }
-                cost[mask] = surface_area(b);
-            }
-            __syncwarp();
-            if (lane < 7) cost[1u << lane] = 1.0f * surface_area(lb) / rootSA;
-            __syncwarp();
-            for (uint32_t s = 2; s <= 7; s++) {
-                for (uint32_t k = c_sizeStart[s] + lane; k < c_sizeStart[s + 1]; k += 32) {
-                    uint32_t mask = c_masksBySize[k];
-                    float lowest = FLT_MAX;
-                    uint32_t bestP = 0;
-                    uint32_t delta = (mask - 1) & mask;
-                    uint32_t p = (0u - delta) & mask;
-                    do {
-                        float c = cost[p] + cost[mask ^ p];
-                        if (c < lowest) { lowest = c; bestP = p; }
-                        p = (p - delta) & mask;
-                    } while (p != 0);
-                    cost[mask] = 1.0f * cost[mask] + lowest;
-                    part[mask] = (uint8_t)bestP;
+                    __syncwarp();
+                }
+                // ---- ReformTree. Lane 0 walks the partition table exactly like the reference's stack loop (pop an
+                // entry, allocate the left then the right composite child, push in that order). A stack entry is
+                // (internal slot << 7 | subset), 10 bits, kept in one 64-bit register. A child code is an internal
+                // slot (0..5) or 8 + treelet leaf index.
+                if (lane == 0) {
+                    unsigned long long stk = 127ull; // slot 0, all seven leaves
+                    uint32_t sp = 1, allocated = 1;
+                    while (sp > 0) {
+                        --sp;
+                        const uint32_t e = (uint32_t)(stk >> (10 * sp)) & 1023u;
+                        stk &= ~(1023ull << (10 * sp));
+                        const uint32_t em = e & 127u, es = e >> 7;
+                        const uint32_t lm = part[em], rm = em ^ lm;
+                        uint32_t lcode, rcode;
+                        if (__popc(lm) > 1) { lcode = allocated++; stk |= (unsigned long long)((lcode << 7) | lm) << (10 * sp); sp++; }
+                        else lcode = 8u + (uint32_t)(__ffs(lm) - 1);
+                        if (__popc(rm) > 1) { rcode = allocated++; stk |= (unsigned long long)((rcode << 7) | rm) << (10 * sp); sp++; }
+                        else rcode = 8u + (uint32_t)(__ffs(rm) - 1);
+                        s_new[warp][es][0] = em; s_new[warp][es][1] = lcode; s_new[warp][es][2] = rcode;
+                    }
+                }
+                __syncwarp();
+                {
+                    uint32_t em = 0, lcode = 0, rcode = 0;
+                    if (lane < 6) { em = s_new[warp][lane][0]; lcode = s_new[warp][lane][1]; rcode = s_new[warp][lane][2]; }
+                    // node ids of the children: internal slot k lives in lane k's `internal`, treelet leaf i in lane i's `leaf`
+                    const uint32_t lInt = __shfl_sync(FULL, internal, lcode & 7u), lLeaf = __shfl_sync(FULL, leaf, lcode & 7u);
+                    const uint32_t rInt = __shfl_sync(FULL, internal, rcode & 7u), rLeaf = __shfl_sync(FULL, leaf, rcode & 7u);
+                    if (lane < 6) {
+                        const uint32_t ln = lcode >= 8u ? lLeaf : lInt, rn = rcode >= 8u ? rLeaf : rInt;
+                        __stcg(&H[internal].left, ln);
+                        __stcg(&H[internal].right, rn);
+                        __stcg(&H[ln].parent, internal);
+                        __stcg(&H[rn].parent, internal);
+                        Box b; b.mn = mk3(FLT_MAX); b.mx = mk3(-FLT_MAX);
+#pragma unroll
+                        for (uint32_t i = 0; i < 7; i++)
+                            if ((1u << i) & em) {
+                                const float* sb = s_box[warp][i];
+                                Box t; t.mn = mk3(sb[0], sb[1], sb[2]); t.mx = mk3(sb[3], sb[4], sb[5]);
+                                b = combine(b, t);
+                            }
+                        st_box(aabb, internal, b);
+                        __threadfence();
+                    }
                 }
                 __syncwarp();
             }
-            // ---- ReformTree (lane 0), with leaves / internals gathered by shuffles
-            uint32_t leaves[7], internals[6];
-#pragma unroll
-            for (int i = 0; i < 7; i++) leaves[i] = __shfl_sync(0xffffffffu, leaf, i);
-#pragma unroll
-            for (int i = 0; i < 6; i++) internals[i] = __shfl_sync(0xffffffffu, internal, i);
-            bool finished = false;
+            // ---- TraverseToParent: the second warp to arrive at the parent goes on with it
+            if (root == 0) break;
+            uint32_t other = 0;
             if (lane == 0) {
-                uint32_t stackMask[7], stackNode[7];
-                uint32_t allocated = 1, sp = 1;
-                stackMask[0] = 127u; stackNode[0] = internals[0];
-                while (sp > 0) {
-                    --sp;
-                    uint32_t em = stackMask[sp], en = stackNode[sp];
-                    uint32_t lm = part[em], ln, rm, rn;
-                    if (__popc(lm) > 1) { ln = internals[allocated++]; stackMask[sp] = lm; stackNode[sp] = ln; sp++; }
-                    else ln = leaves[__ffs(lm) - 1];
-                    rm = em ^ lm;
-                    if (__popc(rm) > 1) { rn = internals[allocated++]; stackMask[sp] = rm; stackNode[sp] = rn; sp++; }
-                    else rn = leaves[__ffs(rm) - 1];
-                    __stcg(&H[en].left, ln);
-                    __stcg(&H[en].right, rn);
-                    __stcg(&H[ln].parent, en);
-                    __stcg(&H[rn].parent, en);
-                }
-                for (int j = 5; j >= 0; j--) {
-                    uint32_t in = internals[j];
-                    Box b = combine(ld_box(aabb, ld_u(&H[in].left)), ld_box(aabb, ld_u(&H[in].right)));
-                    st_box(aabb, in, b);
-                }
-                // ---- TraverseToParent
-                if (root == 0) finished = true;
-                else {
-                    uint32_t parent = ld_u(&H[root].parent);
-                    uint32_t mine = ld_u(&numTris[root]);
-                    __threadfence();
-                    uint32_t other = atomicAdd(&numTris[parent], mine);
-                    if (other == 0) finished = true;
-                    else {
-                        __threadfence();
-                        Box b = combine(ld_box(aabb, ld_u(&H[parent].left)), ld_box(aabb, ld_u(&H[parent].right)));
-                        st_box(aabb, parent, b);
-                        root = parent;
-                    }
-                }
+                __threadfence();
+                other = atomicAdd(&numTris[rparent], mine);
             }
-            finished = __shfl_sync(0xffffffffu, (int)finished, 0);
-            root = __shfl_sync(0xffffffffu, root, 0);
+            other = __shfl_sync(FULL, other, 0);
+            if (other == 0) break;
+            __threadfence();
+            const uint32_t sibling = (pl == root) ? pr : pl;
+            Box b = combine(rb, ld_box(aabb, sibling)); // every lane computes it, lane 0 publishes it
+            if (lane == 0) st_box(aabb, rparent, b);
+            root = rparent; rl = pl; rr = pr; rparent = pparent; mine += other; rb = b;
             __syncwarp();
-            if (finished) break;
         }
     }
 }

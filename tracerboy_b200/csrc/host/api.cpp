@@ -233,6 +233,16 @@ TB_API int tb_create(int device, TbHandle** out) {
         delete h;
         return fail(nullptr, TB_ERR_CUDA, "cannot initialise CUDA stream/events");
     }
+    // The builder's temporaries come from the device's default stream-ordered pool; keep up to 16 GiB of it
+    // mapped between builds instead of handing it back to the driver at every synchronise.
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = 16ull << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     // blue noise (TracerBoy.cpp:2126-2134): LDR_RGBA_0/1 decoded to raw RGBA8
     h->blueNoiseHost.assign(2 * 256 * 256 * 4, 0);
     std::string bn = lib_dir() + "/../data/bluenoise_rgba8_256.bin";
