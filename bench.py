@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--ref-spp", type=int, default=2, help="CPU sample size per step for --impl reference")
     ap.add_argument("--cpu-baseline-spp", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fif", type=int, default=0, help="frames in flight (0: the library's automatic policy)")
     ap.add_argument("--shard", default="samples", choices=["samples", "rows"],
                     help="N>1: 'samples' = frame f on rank f mod N (weak scaling, default); 'rows' = interleaved bands of 8 rows, "
                          "every rank renders all frames of its bands (strong scaling, bit-identical to one GPU)")
@@ -219,6 +220,8 @@ def main():
     build_first_ms = g.GetBVHBuildMilliseconds()  # includes the first-use costs: module load, growth of the memory pool
     g.LoadScene(scene_arg(spec))                  # the same build again: the steady-state builder time
     g.Resize(w, h)
+    if args.fif:
+        g.SetFramesInFlight(args.fif)
     if args.shard == "rows":
         g.SetRowShard(rank, world)    # bands of 8 rows, band b on rank b mod N
     else:
@@ -386,7 +389,8 @@ def main():
                        "triangles": info.NumTriangles, "sharding": ("bands of 8 rows, band b on rank b mod N" if args.shard == "rows" else "frame f on rank f mod N") +
                                    "; all-reduce of the accumulation buffer per step",
                        "l2": "inputs exceed L2: %d MB of path state + accumulation buffers are rewritten every sample" % (
-                           (w * h * 16 * 14) >> 20)},
+                           (w * h * 16 * 14) >> 20),
+                       "frames_in_flight": args.fif if args.fif else "auto (memory budget, <= 32)"},
             "samples_per_s": (1 if args.shard == "rows" else world) * w * h * spp * args.steps / t_step,
             "rays_per_step": rays_total / args.steps,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(host_in.numel()),

@@ -76,15 +76,31 @@ __global__ void k_load_prims(const TbGeometryRecord* __restrict__ geoms, const u
         Meta m = {lo, t, G.GeometryFlags};
         meta[i] = m;
     }
-    // warp reduce then 6 atomics per warp (min/max are order independent => deterministic)
+    // warp reduce, block reduce, then 6 atomics per block (min/max are order independent => deterministic). One set of
+    // atomics per warp serialised 3.9 M same-address operations at 20 M triangles (2.8 ms for a 0.3 ms copy).
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         mn.x = fminf(mn.x, __shfl_xor_sync(0xffffffffu, mn.x, o)); mn.y = fminf(mn.y, __shfl_xor_sync(0xffffffffu, mn.y, o)); mn.z = fminf(mn.z, __shfl_xor_sync(0xffffffffu, mn.z, o));
         mx.x = fmaxf(mx.x, __shfl_xor_sync(0xffffffffu, mx.x, o)); mx.y = fmaxf(mx.y, __shfl_xor_sync(0xffffffffu, mx.y, o)); mx.z = fmaxf(mx.z, __shfl_xor_sync(0xffffffffu, mx.z, o));
     }
-    if ((threadIdx.x & 31) == 0 && mn.x <= mx.x) {
-        atomicMin(&sceneBox[0], float_to_ordered(mn.x)); atomicMin(&sceneBox[1], float_to_ordered(mn.y)); atomicMin(&sceneBox[2], float_to_ordered(mn.z));
-        atomicMax(&sceneBox[3], float_to_ordered(mx.x)); atomicMax(&sceneBox[4], float_to_ordered(mx.y)); atomicMax(&sceneBox[5], float_to_ordered(mx.z));
+    __shared__ float s_red[32][6];
+    const uint32_t warp = threadIdx.x >> 5, warps = (blockDim.x + 31) >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        const bool valid = mn.x <= mx.x; // a warp without triangles (or with NaN only) contributes nothing
+        s_red[warp][0] = valid ? mn.x : FLT_MAX; s_red[warp][1] = valid ? mn.y : FLT_MAX; s_red[warp][2] = valid ? mn.z : FLT_MAX;
+        s_red[warp][3] = valid ? mx.x : -FLT_MAX; s_red[warp][4] = valid ? mx.y : -FLT_MAX; s_red[warp][5] = valid ? mx.z : -FLT_MAX;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const bool isMin = threadIdx.x < 3;
+        float r = s_red[0][threadIdx.x];
+        for (uint32_t k = 1; k < warps; k++) r = isMin ? fminf(r, s_red[k][threadIdx.x]) : fmaxf(r, s_red[k][threadIdx.x]);
+        float bmn = s_red[0][0], bmx = s_red[0][3];
+        for (uint32_t k = 1; k < warps; k++) { bmn = fminf(bmn, s_red[k][0]); bmx = fmaxf(bmx, s_red[k][3]); }
+        if (bmn <= bmx) {
+            if (isMin) atomicMin(&sceneBox[threadIdx.x], float_to_ordered(r));
+            else atomicMax(&sceneBox[threadIdx.x], float_to_ordered(r));
+        }
     }
 }
 
@@ -269,18 +285,20 @@ __device__ __forceinline__ void leaf_box(const Prim* prims, uint32_t i, f3& c, f
     c = (mn + mx) * 0.5f;
     h = mx - c;
 }
-// L2-coherent accessors for data handed between thread blocks (L1 is not coherent)
+// L2-coherent accessors for data handed between thread blocks (L1 is not coherent). A scratch box is
+// 8 floats (min.xyz, pad, max.xyz, pad) so that it moves as two 128-bit transactions instead of six scalar ones.
 __device__ __forceinline__ Box ld_box(const float* aabb, uint32_t i) {
-    const float* p = aabb + 6 * (size_t)i;
+    const float4* p = (const float4*)(aabb + 8 * (size_t)i);
+    const float4 lo = __ldcg(p), hi = __ldcg(p + 1);
     Box b;
-    b.mn = mk3(__ldcg(p), __ldcg(p + 1), __ldcg(p + 2));
-    b.mx = mk3(__ldcg(p + 3), __ldcg(p + 4), __ldcg(p + 5));
+    b.mn = mk3(lo.x, lo.y, lo.z);
+    b.mx = mk3(hi.x, hi.y, hi.z);
     return b;
 }
 __device__ __forceinline__ void st_box(float* aabb, uint32_t i, const Box& b) {
-    float* p = aabb + 6 * (size_t)i;
-    __stcg(p, b.mn.x); __stcg(p + 1, b.mn.y); __stcg(p + 2, b.mn.z);
-    __stcg(p + 3, b.mx.x); __stcg(p + 4, b.mx.y); __stcg(p + 5, b.mx.z);
+    float4* p = (float4*)(aabb + 8 * (size_t)i);
+    __stcg(p, make_float4(b.mn.x, b.mn.y, b.mn.z, 0.0f));
+    __stcg(p + 1, make_float4(b.mx.x, b.mx.y, b.mx.z, 0.0f));
 }
 __device__ __forceinline__ uint32_t ld_u(const uint32_t* p) { return __ldcg(p); }
 
@@ -329,184 +347,227 @@ __global__ void k_find_treelets(const Prim* __restrict__ prims, uint32_t n, uint
 __constant__ uint8_t c_masksBySize[128];
 __constant__ uint8_t c_sizeStart[9];
 
-// TreeletReorder.hlsl:38-312 — one warp per base treelet root, climbing to the BVH root.
+// TreeletReorder.hlsl:38-312 — one OCTET (8 lanes) per base treelet root, climbing to the BVH root; the four
+// octets of a warp run in lock step, each on its own treelet.
 //
-// The pass is a chain of dependent L2 round trips per treelet (every word handed between warps goes through
-// ld.cg / st.cg), so the kernel is organised around having as few of them as possible on the critical path
-// (profiles/: the first version spent ~30 per treelet and 83 % of the 20 M-triangle build):
+// A treelet has 7 leaves and 6 internal nodes, so 8 lanes hold it; a whole warp per treelet (the first version)
+// left three quarters of every instruction idle and, more importantly, only one treelet per warp in flight on a
+// pass that is a chain of dependent L2 / DRAM round trips (every word handed between warps goes through ld.cg /
+// st.cg). The kernel is organised around few round trips per treelet and many treelets in flight per SM
+// (profiles/: the first version spent ~30 round trips per treelet and 83 % of the 20 M-triangle build):
 //  * every lane that holds a treelet leaf keeps that node's box AND its two children in registers, loaded in
 //    one round trip when the lane receives the node; expanding the largest leaf is then shuffles only;
 //  * the record of the root's parent (needed for the climb) is requested before FormTreelet starts;
+//  * FindOptimalPartitions: subsets are spread over the 8 lanes; the one 7-leaf subset, whose 63 partitions
+//    would be a serial tail, is searched by all 8 lanes with a lexicographic (cost, sequence index) argmin,
+//    which is the reference's first-lowest-wins rule;
 //  * ReformTree: lane 0 derives the topology from the partition table (registers + shared memory only, same
 //    allocation order as the reference's stack walk), lanes 0..5 then write one internal node each; a new
 //    node's box is the union of the treelet leaves in its subset, which is bit-identical to the reference's
 //    bottom-up recombination because min/max are exact and order-independent;
 //  * the climb carries the parent's record, box and triangle count into the next iteration in registers.
+// Treelets are independent unless one is an ancestor of the other, and an ancestor only starts after both of
+// its children have arrived (atomic counter), so any schedule produces the reference's result.
+#define TL_OCTETS 16 // per 128-thread block
 __global__ void __launch_bounds__(128, 8) k_treelet_reorder(uint32_t n, HNode* H, float* aabb, uint32_t* numTris,
                                                          const uint32_t* baseCount, const uint32_t* baseRoots) {
-    const uint32_t warpsPerBlock = blockDim.x / 32;
-    const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31, ol = lane & 7u;
+    const uint32_t oct = threadIdx.x >> 3; // octet within the block
     const uint32_t nInternal = n - 1, total = 2 * n - 1;
     const uint32_t FULL = 0xffffffffu;
-    __shared__ float s_cost[4][128];
-    __shared__ uint8_t s_part[4][128];
-    __shared__ float s_box[4][7][6];
-    __shared__ uint32_t s_new[4][6][3]; // per new internal node: leaf subset, left child code, right child code
-    float* cost = s_cost[warp];
-    uint8_t* part = s_part[warp];
+    __shared__ float s_cost[TL_OCTETS][128];
+    __shared__ uint8_t s_part[TL_OCTETS][128];
+    __shared__ float s_box[TL_OCTETS][7][6];
+    __shared__ uint32_t s_new[TL_OCTETS][6][3]; // per new internal node: leaf subset, left child code, right child code
+    float* cost = s_cost[oct];
+    uint8_t* part = s_part[oct];
     const uint32_t numRoots = *baseCount;
-    for (uint32_t w = blockIdx.x * warpsPerBlock + warp; w < numRoots; w += gridDim.x * warpsPerBlock) {
-        uint32_t root = baseRoots[w];
-        // the root's record; every lane reads the same words (one broadcast transaction each)
-        uint32_t rl = ld_u(&H[root].left), rr = ld_u(&H[root].right), rparent = ld_u(&H[root].parent);
-        uint32_t mine = ld_u(&numTris[root]);
-        Box rb = ld_box(aabb, root);
-        while (true) {
-            // the parent's record is only needed by the climb: requested now, consumed after the treelet is done.
-            // Nobody rewrites it before this warp (or its sibling's) has climbed there.
-            uint32_t pl = 0, pr = 0, pparent = 0;
-            if (root != 0) { pl = ld_u(&H[rparent].left); pr = ld_u(&H[rparent].right); pparent = ld_u(&H[rparent].parent); }
-            // ---- FormTreelet: lanes 0..6 hold the treelet leaves (id, box, children), lanes 0..5 the internal nodes
-            uint32_t leaf = 0xffffffffu, internal = 0xffffffffu, cl = 0xffffffffu, cr = 0xffffffffu;
-            Box lb; lb.mn = mk3(FLT_MAX); lb.mx = mk3(-FLT_MAX);
-            if (lane == 0) { leaf = rl; internal = root; }
-            if (lane == 1) leaf = rr;
-            if (lane < 2) {
-                lb = ld_box(aabb, leaf);
-                if (leaf < nInternal) { cl = ld_u(&H[leaf].left); cr = ld_u(&H[leaf].right); }
-            }
-            bool degenerate = false;
-            for (uint32_t size = 2; size < 7; size++) {
-                float sa = 0.0f;
-                if (lane < size && leaf < nInternal) sa = surface_area(lb);
-                // argmax, first index wins on ties, must be strictly > 0
-                float best = sa; uint32_t bestLane = lane;
+    const uint32_t stride = gridDim.x * TL_OCTETS;
+    uint32_t w = blockIdx.x * TL_OCTETS + oct; // next base root of this octet
+    bool have = false;                          // this octet is working on a treelet
+    uint32_t root = 0, rl = 0, rr = 0, rparent = 0, mine = 0;
+    Box rb; rb.mn = mk3(0.0f); rb.mx = mk3(0.0f);
+    while (true) {
+        if (!have && w < numRoots) {
+            // the root's record; the lanes of the octet read the same words (one broadcast transaction each)
+            root = baseRoots[w];
+            w += stride;
+            rl = ld_u(&H[root].left); rr = ld_u(&H[root].right); rparent = ld_u(&H[root].parent);
+            mine = ld_u(&numTris[root]);
+            rb = ld_box(aabb, root);
+            have = true;
+        }
+        if (!__any_sync(FULL, have)) break;
+        // The parent's record is only needed by the climb: requested now, consumed after the treelet is done.
+        // Nobody rewrites it before this octet (or its sibling's) has climbed there.
+        uint32_t pl = 0, pr = 0, pparent = 0;
+        if (have && root != 0) { pl = ld_u(&H[rparent].left); pr = ld_u(&H[rparent].right); pparent = ld_u(&H[rparent].parent); }
+        // ---- FormTreelet: lanes 0..6 hold the treelet leaves (id, box, children), lanes 0..5 the internal nodes
+        uint32_t leaf = 0xffffffffu, internal = 0xffffffffu, cl = 0xffffffffu, cr = 0xffffffffu;
+        Box lb; lb.mn = mk3(FLT_MAX); lb.mx = mk3(-FLT_MAX);
+        if (ol == 0) { leaf = rl; internal = root; }
+        if (ol == 1) leaf = rr;
+        if (have && ol < 2) {
+            lb = ld_box(aabb, leaf);
+            if (leaf < nInternal) { cl = ld_u(&H[leaf].left); cr = ld_u(&H[leaf].right); }
+        }
+        // No expandable leaf (every candidate has a zero-area or NaN box): the reference then follows whatever the
+        // node array holds for a leaf; here the treelet is left as it is.
+        bool degenerate = false;
+        for (uint32_t size = 2; size < 7; size++) {
+            float sa = 0.0f;
+            if (ol < size && leaf < nInternal) sa = surface_area(lb);
+            // argmax, first index wins on ties, must be strictly > 0
+            float best = sa; uint32_t bestLane = ol;
 #pragma unroll
-                for (int o = 4; o > 0; o >>= 1) { // lanes 0..7 are enough
-                    float os = __shfl_xor_sync(FULL, best, o);
-                    uint32_t ol = __shfl_xor_sync(FULL, bestLane, o);
-                    if (os > best || (os == best && ol < bestLane)) { best = os; bestLane = ol; }
-                }
-                bestLane = __shfl_sync(FULL, bestLane, 0);
-                const uint32_t pick = __shfl_sync(FULL, leaf, bestLane);
-                const uint32_t pcl = __shfl_sync(FULL, cl, bestLane), pcr = __shfl_sync(FULL, cr, bestLane);
-                // No expandable leaf (every candidate has a zero-area or NaN box): the reference then follows
-                // whatever the node array holds for a leaf; here the treelet is left as it is.
-                if (pick >= nInternal) { degenerate = true; break; }
+            for (int o = 4; o > 0; o >>= 1) {
+                float os = __shfl_xor_sync(FULL, best, o, 8);
+                uint32_t bl = __shfl_xor_sync(FULL, bestLane, o, 8);
+                if (os > best || (os == best && bl < bestLane)) { best = os; bestLane = bl; }
+            }
+            bestLane = __shfl_sync(FULL, bestLane, 0, 8);
+            const uint32_t pick = __shfl_sync(FULL, leaf, bestLane, 8);
+            const uint32_t pcl = __shfl_sync(FULL, cl, bestLane, 8), pcr = __shfl_sync(FULL, cr, bestLane, 8);
+            if (pick >= nInternal) degenerate = true;
+            if (have && !degenerate) {
                 bool fresh = false;
-                if (lane == bestLane) { leaf = pcl; fresh = true; }
-                if (lane == size) { leaf = pcr; fresh = true; }
-                if (lane == size - 1) internal = pick;
+                if (ol == bestLane) { leaf = pcl; fresh = true; }
+                if (ol == size) { leaf = pcr; fresh = true; }
+                if (ol == size - 1) internal = pick;
                 if (fresh) {
                     cl = cr = 0xffffffffu;
                     if (leaf < total) lb = ld_box(aabb, leaf);
                     if (size < 6 && leaf < nInternal) { cl = ld_u(&H[leaf].left); cr = ld_u(&H[leaf].right); }
                 }
             }
-            if (!degenerate) {
-                if (lane < 7) {
-                    float* sb = s_box[warp][lane];
-                    sb[0] = lb.mn.x; sb[1] = lb.mn.y; sb[2] = lb.mn.z; sb[3] = lb.mx.x; sb[4] = lb.mx.y; sb[5] = lb.mx.z;
-                }
-                __syncwarp();
-                // ---- FindOptimalPartitions
-                float rootSA = surface_area(rb);
-                for (uint32_t mask = lane * 4; mask < lane * 4 + 4; mask++) {
-                    if (mask == 0) { cost[0] = 0.0f; continue; }
-                    Box b; b.mn = mk3(FLT_MAX); b.mx = mk3(-FLT_MAX);
+        }
+        const bool work = have && !degenerate;
+        if (ol < 7) {
+            float* sb = s_box[oct][ol];
+            sb[0] = lb.mn.x; sb[1] = lb.mn.y; sb[2] = lb.mn.z; sb[3] = lb.mx.x; sb[4] = lb.mx.y; sb[5] = lb.mx.z;
+        }
+        __syncwarp();
+        // ---- FindOptimalPartitions
+        const float rootSA = surface_area(rb);
+        for (uint32_t mask = ol * 16; mask < ol * 16 + 16; mask++) {
+            if (mask == 0) { cost[0] = 0.0f; continue; }
+            Box b; b.mn = mk3(FLT_MAX); b.mx = mk3(-FLT_MAX);
 #pragma unroll
-                    for (uint32_t i = 0; i < 7; i++)
-                        if ((1u << i) & mask) {
-                            const float* sb = s_box[warp][i];
-                            Box t; t.mn = mk3(sb[0], sb[1], sb[2]); t.mx = mk3(sb[3], sb[4], sb[5]);
-                            b = combine(b, t);
-                        }
-                    cost[mask] = surface_area(b);
+            for (uint32_t i = 0; i < 7; i++)
+                if ((1u << i) & mask) {
+                    const float* sb = s_box[oct][i];
+                    Box t; t.mn = mk3(sb[0], sb[1], sb[2]); t.mx = mk3(sb[3], sb[4], sb[5]);
+                    b = combine(b, t);
                 }
-                __syncwarp();
-                if (lane < 7) cost[1u << lane] = 1.0f * surface_area(lb) / rootSA;
-                __syncwarp();
-                for (uint32_t sz = 2; sz <= 7; sz++) {
-                    for (uint32_t k = c_sizeStart[sz] + lane; k < c_sizeStart[sz + 1]; k += 32) {
-                        uint32_t mask = c_masksBySize[k];
-                        float lowest = FLT_MAX;
-                        uint32_t bestP = 0;
-                        uint32_t delta = (mask - 1) & mask;
-                        uint32_t p = (0u - delta) & mask;
-                        do {
-                            float c = cost[p] + cost[mask ^ p];
-                            if (c < lowest) { lowest = c; bestP = p; }
-                            p = (p - delta) & mask;
-                        } while (p != 0);
-                        cost[mask] = 1.0f * cost[mask] + lowest;
-                        part[mask] = (uint8_t)bestP;
-                    }
-                    __syncwarp();
-                }
-                // ---- ReformTree. Lane 0 walks the partition table exactly like the reference's stack loop (pop an
-                // entry, allocate the left then the right composite child, push in that order). A stack entry is
-                // (internal slot << 7 | subset), 10 bits, kept in one 64-bit register. A child code is an internal
-                // slot (0..5) or 8 + treelet leaf index.
-                if (lane == 0) {
-                    unsigned long long stk = 127ull; // slot 0, all seven leaves
-                    uint32_t sp = 1, allocated = 1;
-                    while (sp > 0) {
-                        --sp;
-                        const uint32_t e = (uint32_t)(stk >> (10 * sp)) & 1023u;
-                        stk &= ~(1023ull << (10 * sp));
-                        const uint32_t em = e & 127u, es = e >> 7;
-                        const uint32_t lm = part[em], rm = em ^ lm;
-                        uint32_t lcode, rcode;
-                        if (__popc(lm) > 1) { lcode = allocated++; stk |= (unsigned long long)((lcode << 7) | lm) << (10 * sp); sp++; }
-                        else lcode = 8u + (uint32_t)(__ffs(lm) - 1);
-                        if (__popc(rm) > 1) { rcode = allocated++; stk |= (unsigned long long)((rcode << 7) | rm) << (10 * sp); sp++; }
-                        else rcode = 8u + (uint32_t)(__ffs(rm) - 1);
-                        s_new[warp][es][0] = em; s_new[warp][es][1] = lcode; s_new[warp][es][2] = rcode;
-                    }
-                }
-                __syncwarp();
-                {
-                    uint32_t em = 0, lcode = 0, rcode = 0;
-                    if (lane < 6) { em = s_new[warp][lane][0]; lcode = s_new[warp][lane][1]; rcode = s_new[warp][lane][2]; }
-                    // node ids of the children: internal slot k lives in lane k's `internal`, treelet leaf i in lane i's `leaf`
-                    const uint32_t lInt = __shfl_sync(FULL, internal, lcode & 7u), lLeaf = __shfl_sync(FULL, leaf, lcode & 7u);
-                    const uint32_t rInt = __shfl_sync(FULL, internal, rcode & 7u), rLeaf = __shfl_sync(FULL, leaf, rcode & 7u);
-                    if (lane < 6) {
-                        const uint32_t ln = lcode >= 8u ? lLeaf : lInt, rn = rcode >= 8u ? rLeaf : rInt;
-                        __stcg(&H[internal].left, ln);
-                        __stcg(&H[internal].right, rn);
-                        __stcg(&H[ln].parent, internal);
-                        __stcg(&H[rn].parent, internal);
-                        Box b; b.mn = mk3(FLT_MAX); b.mx = mk3(-FLT_MAX);
-#pragma unroll
-                        for (uint32_t i = 0; i < 7; i++)
-                            if ((1u << i) & em) {
-                                const float* sb = s_box[warp][i];
-                                Box t; t.mn = mk3(sb[0], sb[1], sb[2]); t.mx = mk3(sb[3], sb[4], sb[5]);
-                                b = combine(b, t);
-                            }
-                        st_box(aabb, internal, b);
-                        __threadfence();
-                    }
-                }
-                __syncwarp();
+            cost[mask] = surface_area(b);
+        }
+        __syncwarp();
+        if (ol < 7) cost[1u << ol] = 1.0f * surface_area(lb) / rootSA;
+        __syncwarp();
+        for (uint32_t sz = 2; sz <= 6; sz++) {
+            for (uint32_t k = c_sizeStart[sz] + ol; k < c_sizeStart[sz + 1]; k += 8) {
+                uint32_t mask = c_masksBySize[k];
+                float lowest = FLT_MAX;
+                uint32_t bestP = 0;
+                uint32_t delta = (mask - 1) & mask;
+                uint32_t p = (0u - delta) & mask;
+                do {
+                    float c = cost[p] + cost[mask ^ p];
+                    if (c < lowest) { lowest = c; bestP = p; }
+                    p = (p - delta) & mask;
+                } while (p != 0);
+                cost[mask] = 1.0f * cost[mask] + lowest;
+                part[mask] = (uint8_t)bestP;
             }
-            // ---- TraverseToParent: the second warp to arrive at the parent goes on with it
-            if (root == 0) break;
-            uint32_t other = 0;
-            if (lane == 0) {
+            __syncwarp();
+        }
+        {
+            // all seven leaves: the reference's sequence p = 2, 4, ..., 126 (delta = 126), the first lowest wins.
+            // Lane ol takes the sequence positions j = ol, ol + 8, ...; p_j = 2 (j + 1).
+            float lowest = FLT_MAX;
+            uint32_t bestJ = 0xffffffffu;
+            for (uint32_t j = ol; j < 63; j += 8) {
+                const uint32_t p = 2u * (j + 1u);
+                float c = cost[p] + cost[127u ^ p];
+                if (c < lowest) { lowest = c; bestJ = j; }
+            }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                float oc = __shfl_xor_sync(FULL, lowest, o, 8);
+                uint32_t oj = __shfl_xor_sync(FULL, bestJ, o, 8);
+                if (oc < lowest || (oc == lowest && oj < bestJ)) { lowest = oc; bestJ = oj; }
+            }
+            // bestJ == 0xffffffff: no partition was below FLT_MAX (NaN costs); the serial loop then leaves bestP = 0
+            if (ol == 0) part[127] = bestJ == 0xffffffffu ? (uint8_t)0 : (uint8_t)(2u * (bestJ + 1u));
+        }
+        __syncwarp();
+        // ---- ReformTree. Lane 0 walks the partition table exactly like the reference's stack loop (pop an entry,
+        // allocate the left then the right composite child, push in that order). A stack entry is
+        // (internal slot << 7 | subset), 10 bits, kept in one 64-bit register. A child code is an internal slot
+        // (0..5) or 8 + treelet leaf index.
+        if (ol == 0) {
+            unsigned long long stk = 127ull; // slot 0, all seven leaves
+            uint32_t sp = 1, allocated = 1;
+            while (sp > 0) {
+                --sp;
+                const uint32_t e = (uint32_t)(stk >> (10 * sp)) & 1023u;
+                stk &= ~(1023ull << (10 * sp));
+                const uint32_t em = e & 127u, es = e >> 7;
+                uint32_t lm = part[em];
+                if (lm == 0 || (lm & ~em) != 0 || lm == em) lm = em & (0u - em); // table not meaningful (NaN costs, idle octet): stay in bounds
+                const uint32_t rm = em ^ lm;
+                uint32_t lcode, rcode;
+                if (__popc(lm) > 1) { lcode = allocated++; stk |= (unsigned long long)((lcode << 7) | lm) << (10 * sp); sp++; }
+                else lcode = 8u + (uint32_t)(__ffs(lm) - 1);
+                if (__popc(rm) > 1) { rcode = allocated++; stk |= (unsigned long long)((rcode << 7) | rm) << (10 * sp); sp++; }
+                else rcode = 8u + (uint32_t)(__ffs(rm) - 1);
+                s_new[oct][es][0] = em; s_new[oct][es][1] = lcode; s_new[oct][es][2] = rcode;
+            }
+        }
+        __syncwarp();
+        {
+            uint32_t em = 0, lcode = 0, rcode = 0;
+            if (ol < 6) { em = s_new[oct][ol][0]; lcode = s_new[oct][ol][1]; rcode = s_new[oct][ol][2]; }
+            // node ids of the children: internal slot k lives in lane k's `internal`, treelet leaf i in lane i's `leaf`
+            const uint32_t lInt = __shfl_sync(FULL, internal, lcode & 7u, 8), lLeaf = __shfl_sync(FULL, leaf, lcode & 7u, 8);
+            const uint32_t rInt = __shfl_sync(FULL, internal, rcode & 7u, 8), rLeaf = __shfl_sync(FULL, leaf, rcode & 7u, 8);
+            if (work && ol < 6) {
+                const uint32_t ln = lcode >= 8u ? lLeaf : lInt, rn = rcode >= 8u ? rLeaf : rInt;
+                __stcg(&H[internal].left, ln);
+                __stcg(&H[internal].right, rn);
+                __stcg(&H[ln].parent, internal);
+                __stcg(&H[rn].parent, internal);
+                Box b; b.mn = mk3(FLT_MAX); b.mx = mk3(-FLT_MAX);
+#pragma unroll
+                for (uint32_t i = 0; i < 7; i++)
+                    if ((1u << i) & em) {
+                        const float* sb = s_box[oct][i];
+                        Box t; t.mn = mk3(sb[0], sb[1], sb[2]); t.mx = mk3(sb[3], sb[4], sb[5]);
+                        b = combine(b, t);
+                    }
+                st_box(aabb, internal, b);
                 __threadfence();
-                other = atomicAdd(&numTris[rparent], mine);
             }
-            other = __shfl_sync(FULL, other, 0);
-            if (other == 0) break;
+        }
+        __syncwarp();
+        // ---- TraverseToParent: the second octet to arrive at the parent goes on with it
+        uint32_t other = 0;
+        const bool climbing = have && root != 0;
+        if (climbing && ol == 0) {
+            __threadfence();
+            other = atomicAdd(&numTris[rparent], mine);
+        }
+        other = __shfl_sync(FULL, other, 0, 8);
+        if (climbing && other != 0) {
             __threadfence();
             const uint32_t sibling = (pl == root) ? pr : pl;
             Box b = combine(rb, ld_box(aabb, sibling)); // every lane computes it, lane 0 publishes it
-            if (lane == 0) st_box(aabb, rparent, b);
+            if (ol == 0) st_box(aabb, rparent, b);
             root = rparent; rl = pl; rr = pr; rparent = pparent; mine += other; rb = b;
-            __syncwarp();
+        } else {
+            have = false;
         }
+        __syncwarp();
     }
 }
 
@@ -528,9 +589,9 @@ __global__ void k_refit(uint32_t n, const HNode* H, uint8_t* bvh, uint32_t* coun
     {
         f3 c, h;
         leaf_box(prims, node - nInternal, c, h);
-        float* nd = nodes + 8 * (size_t)node;
-        __stcg(nd, c.x); __stcg(nd + 1, c.y); __stcg(nd + 2, c.z); __stcg((uint32_t*)nd + 3, (node - nInternal) | 0x80000000u);
-        __stcg(nd + 4, h.x); __stcg(nd + 5, h.y); __stcg(nd + 6, h.z); __stcg((uint32_t*)nd + 7, 1u);
+        float4* nd = (float4*)(nodes + 8 * (size_t)node); // 16-byte aligned: the node array starts 16 bytes into the buffer
+        __stcg(nd, make_float4(c.x, c.y, c.z, __uint_as_float((node - nInternal) | 0x80000000u)));
+        __stcg(nd + 1, make_float4(h.x, h.y, h.z, __uint_as_float(1u)));
     }
     while (node != 0) {
         uint32_t parent = ld_u(&H[node].parent);
@@ -541,16 +602,17 @@ __global__ void k_refit(uint32_t n, const HNode* H, uint8_t* bvh, uint32_t* coun
         uint32_t l = ld_u(&H[parent].left), r = ld_u(&H[parent].right);
         uint32_t lc = (l == node) ? count : other, rc = (l == node) ? other : count;
         if (lc > rc) { uint32_t t = l; l = r; r = t; } // smaller subtree left; ties keep Karras order
-        const float* A = nodes + 8 * (size_t)l;
-        const float* B = nodes + 8 * (size_t)r;
-        f3 ac = mk3(__ldcg(A), __ldcg(A + 1), __ldcg(A + 2)), ah = mk3(__ldcg(A + 4), __ldcg(A + 5), __ldcg(A + 6));
-        f3 bc = mk3(__ldcg(B), __ldcg(B + 1), __ldcg(B + 2)), bh = mk3(__ldcg(B + 4), __ldcg(B + 5), __ldcg(B + 6));
+        const float4* A = (const float4*)(nodes + 8 * (size_t)l);
+        const float4* B = (const float4*)(nodes + 8 * (size_t)r);
+        const float4 a0 = __ldcg(A), a1 = __ldcg(A + 1), b0 = __ldcg(B), b1 = __ldcg(B + 1);
+        f3 ac = mk3(a0.x, a0.y, a0.z), ah = mk3(a1.x, a1.y, a1.z);
+        f3 bc = mk3(b0.x, b0.y, b0.z), bh = mk3(b1.x, b1.y, b1.z);
         f3 mn = min3(ac - ah, bc - bh), mx = max3(ac + ah, bc + bh);
         f3 c = (mn + mx) * 0.5f;
         f3 h = mx - c;
-        float* nd = nodes + 8 * (size_t)parent;
-        __stcg(nd, c.x); __stcg(nd + 1, c.y); __stcg(nd + 2, c.z); __stcg((uint32_t*)nd + 3, l & 0x3fffffffu);
-        __stcg(nd + 4, h.x); __stcg(nd + 5, h.y); __stcg(nd + 6, h.z); __stcg((uint32_t*)nd + 7, r);
+        float4* nd = (float4*)(nodes + 8 * (size_t)parent);
+        __stcg(nd, make_float4(c.x, c.y, c.z, __uint_as_float(l & 0x3fffffffu)));
+        __stcg(nd + 1, make_float4(h.x, h.y, h.z, __uint_as_float(r)));
         node = parent;
         count += other;
     }
@@ -631,7 +693,7 @@ cudaError_t build_bvh(const TbGeometryRecord* d_geoms, const uint32_t* d_triPref
     CK(cudaMallocAsync(&baseCount, 4, stream));
     CK(cudaMallocAsync(&baseRoots, 4 * (size_t)(n / 7 + 1), stream));
     CK(cudaMallocAsync(&H, sizeof(HNode) * (size_t)total, stream));
-    CK(cudaMallocAsync(&aabb, 24 * (size_t)total, stream));
+    CK(cudaMallocAsync(&aabb, 32 * (size_t)total, stream));
     const uint32_t sortBlocks = (n + RS_TILE - 1) / RS_TILE;
     uint32_t* radixHist;
     CK(cudaMallocAsync(&radixHist, 4 * 256 * ((size_t)sortBlocks + 1), stream));
@@ -662,7 +724,7 @@ cudaError_t build_bvh(const TbGeometryRecord* d_geoms, const uint32_t* d_triPref
             k_treelet_clear<<<grid(n), T, 0, stream>>>(numTris, nInternal, baseCount); lc.count++;
             k_find_treelets<<<grid(n), T, 0, stream>>>(sortedPrims, n, minTris, H, aabb, numTris, baseCount, baseRoots); lc.count++;
             uint32_t maxRoots = n / minTris + 1;
-            uint32_t blocks = (maxRoots + 3) / 4;
+            uint32_t blocks = (maxRoots + TL_OCTETS - 1) / TL_OCTETS; // one octet (8 lanes) per base root
             if (blocks > 148 * 32) blocks = 148 * 32;
             k_treelet_reorder<<<blocks, 128, 0, stream>>>(n, H, aabb, numTris, baseCount, baseRoots); lc.count++;
             minTris *= 2;

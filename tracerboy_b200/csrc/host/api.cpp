@@ -407,17 +407,18 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
     {
         // private state per slot: 5 float4 + hitGeom + 2 float4 + 2 queues + staging (float4+float+float4+float)
         // + walk state + 2 suspension buffers. Automatic policy: as many slots as fit a third of the free device
-        // memory (at most 48 GB), between 4 and 16. Measured (profiles/README.md): 16 instead of 8 slots is +1 %
+        // memory (at most 64 GB), between 4 and 32. Measured (profiles/README.md): 16 instead of 8 slots is +1 %
         // on Teapot, +12 % on the dragon stand-in and +22 % on vw-van at 4K, whose glass walks end in a
-        // millisecond-long tail of a few sequential 100-ray walkers that only other frames' work can hide.
+        // millisecond-long tail of a few sequential 100-ray walkers that only other frames' work can hide;
+        // 32 instead of 16 is another +6 % on vw-van and on the 20 M-triangle scene, +1.5 % on the dragon stand-in.
         size_t perSlot = n * (80 + 4 + 32 + 8 + 40 + 56 + 8 + 40) + 2 * (n / 16 + 1024) * 448;
         uint32_t fif = h->framesInFlight;
         if (fif == 0) {
             size_t freeB = 0, totalB = 0;
-            size_t budget = (size_t)48 << 30;
+            size_t budget = (size_t)64 << 30;
             if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess && freeB / 3 < budget) budget = freeB / 3;
             size_t fit = budget / perSlot;
-            fif = (uint32_t)(fit < 4 ? 4 : (fit > 16 ? 16 : fit));
+            fif = (uint32_t)(fit < 4 ? 4 : (fit > 32 ? 32 : fit));
         }
         h->slots.resize(fif);
     }
