@@ -449,33 +449,55 @@ __global__ void __launch_bounds__(128, 8) k_treelet_reorder(uint32_t n, HNode* H
         __syncwarp();
         // ---- FindOptimalPartitions
         const float rootSA = surface_area(rb);
-        for (uint32_t mask = ol * 16; mask < ol * 16 + 16; mask++) {
-            if (mask == 0) { cost[0] = 0.0f; continue; }
-            Box b; b.mn = mk3(FLT_MAX); b.mx = mk3(-FLT_MAX);
+        {
+            // Surface area of every leaf subset: lane ol takes the 16 subsets whose leaves 4..6 are the bits of ol.
+            // Leaves 0, 1 and the union of the lane's high leaves are held in registers, so a subset costs a few
+            // register min/max pairs instead of 6 shared-memory loads per member (this loop was the larger
+            // half of the kernel's shared-memory traffic, which bounds it: profiles/).
+            auto box_at = [&](uint32_t i) {
+                const float* sb = s_box[oct][i];
+                Box t; t.mn = mk3(sb[0], sb[1], sb[2]); t.mx = mk3(sb[3], sb[4], sb[5]);
+                return t;
+            };
+            Box base; base.mn = mk3(FLT_MAX); base.mx = mk3(-FLT_MAX);
 #pragma unroll
-            for (uint32_t i = 0; i < 7; i++)
-                if ((1u << i) & mask) {
-                    const float* sb = s_box[oct][i];
-                    Box t; t.mn = mk3(sb[0], sb[1], sb[2]); t.mx = mk3(sb[3], sb[4], sb[5]);
-                    b = combine(b, t);
+            for (uint32_t i = 4; i < 7; i++)
+                if ((ol >> (i - 4)) & 1u) base = combine(base, box_at(i));
+            const Box L0 = box_at(0), L1 = box_at(1);
+#pragma unroll
+            for (uint32_t hi = 0; hi < 4; hi++) { // leaves 2 and 3 (re-read per group: registers are the scarce resource)
+                Box g = base;
+                if (hi & 1u) g = combine(g, box_at(2));
+                if (hi & 2u) g = combine(g, box_at(3));
+#pragma unroll
+                for (uint32_t lo = 0; lo < 4; lo++) {
+                    Box b = g;
+                    if (lo & 1u) b = combine(b, L0);
+                    if (lo & 2u) b = combine(b, L1);
+                    const uint32_t mask = ol * 16 + hi * 4 + lo;
+                    cost[mask] = mask == 0 ? 0.0f : surface_area(b);
                 }
-            cost[mask] = surface_area(b);
+            }
         }
         __syncwarp();
         if (ol < 7) cost[1u << ol] = 1.0f * surface_area(lb) / rootSA;
         __syncwarp();
         for (uint32_t sz = 2; sz <= 6; sz++) {
+            const uint32_t count = (1u << (sz - 1)) - 1u; // partitions of a subset of sz leaves (its lowest leaf stays right)
             for (uint32_t k = c_sizeStart[sz] + ol; k < c_sizeStart[sz + 1]; k += 8) {
-                uint32_t mask = c_masksBySize[k];
+                const uint32_t mask = c_masksBySize[k];
                 float lowest = FLT_MAX;
                 uint32_t bestP = 0;
-                uint32_t delta = (mask - 1) & mask;
+                const uint32_t delta = (mask - 1) & mask;
                 uint32_t p = (0u - delta) & mask;
-                do {
-                    float c = cost[p] + cost[mask ^ p];
+                // the reference's do/while over p, with a known trip count so that the loads of several
+                // iterations are in flight together (the loop is shared-memory latency bound)
+#pragma unroll 4
+                for (uint32_t j = 0; j < count; j++) {
+                    const float c = cost[p] + cost[mask ^ p];
                     if (c < lowest) { lowest = c; bestP = p; }
                     p = (p - delta) & mask;
-                } while (p != 0);
+                }
                 cost[mask] = 1.0f * cost[mask] + lowest;
                 part[mask] = (uint8_t)bestP;
             }
