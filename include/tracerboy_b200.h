@@ -150,6 +150,18 @@ typedef struct TbCamera {
     float FocalDistance;
 } TbCamera;
 
+/* TracerBoy.h:69-77 */
+typedef struct TbControllerState {
+    float RightStickX, RightStickY, RightTrigger;
+    float LeftStickX, LeftStickY, LeftTrigger;
+} TbControllerState;
+
+/* TracerBoy::CameraSettings, TracerBoy.h:386-390 */
+typedef struct TbCameraSettings {
+    float MovementSpeed;
+    uint32_t IgnoreMouse;
+} TbCameraSettings;
+
 /* ---------------------------------------------------------------- settings */
 /* TracerBoy.h:171-197 */
 typedef enum TbOutputType {
@@ -356,6 +368,18 @@ TB_API int tb_get_bvh_build_ms(TbHandle* h, double* ms);
 TB_API int tb_get_default_settings(TbOutputSettings* out); /* TracerBoy::GetDefaultOutputSettings */
 TB_API int tb_get_camera(TbHandle* h, TbCamera* out);
 TB_API int tb_set_camera(TbHandle* h, const TbCamera* cam); /* invalidates history like TracerBoy::Update */
+/* TracerBoy::Update (TracerBoy.cpp:3386-3500): mouse look (yaw about +Y, pitch about the XZ-aligned right axis),
+ * WASD/QE and controller motion. keyboardInput has CHAR_MAX (127) entries indexed by character, as in the
+ * reference; controller and cameraSettings may be NULL (no controller; speed 1, mouse honoured). A call that
+ * moves the camera invalidates the history. Mouse look needs the output size, i.e. tb_resize first
+ * (the reference tests m_pPostProcessOutput). */
+TB_API int tb_update(TbHandle* h, int mouseX, int mouseY, const uint8_t* keyboardInput, float dt,
+                     const TbControllerState* controller, const TbCameraSettings* cameraSettings);
+/* The same step on caller-owned state (host only, needs no device): lastMouse[2] is m_mouseX/m_mouseY and is
+ * updated; width/height 0 disables mouse look; *moved (optional) receives bCameraMoved. */
+TB_API int tb_camera_update(TbCamera* camera, uint32_t lastMouse[2], uint32_t width, uint32_t height,
+                            int mouseX, int mouseY, const uint8_t* keyboardInput, float dt,
+                            const TbControllerState* controller, const TbCameraSettings* cameraSettings, int* moved);
 TB_API int tb_resize(TbHandle* h, uint32_t width, uint32_t height); /* ResizeBuffersIfNeeded, TracerBoy.cpp:3624-3929 */
 TB_API int tb_select_pixel(TbHandle* h, int x, int y);      /* TracerBoy::SelectPixel */
 TB_API int tb_get_stats(TbHandle* h, TbReadbackStats* out);

@@ -302,3 +302,90 @@ def test_image_writers_roundtrip(tmp_path, built):
         tb.write_image(tmp_path / "x.jpg", u8)
     with pytest.raises(tb.TracerBoyError):
         tb.write_image(tmp_path / "x.png", u8[..., :3])
+
+
+def _camera(pos=(0, 1, 5), look=(0, 1, 4), right=(1, 0, 0), up=(0, 1, 0)):
+    import tracerboy_b200 as tb
+    c = tb.Camera()
+    for name, v in (("Position", pos), ("LookAt", look), ("Right", right), ("Up", up)):
+        f = getattr(c, name)
+        f.x, f.y, f.z = v
+    c.LensHeight, c.FocalDistance = 2.0, 7.0
+    return c
+
+
+def _v(f):
+    return np.array([f.x, f.y, f.z], np.float64)
+
+
+def test_camera_update_follows_tracerboy_update(built):
+    """tb_camera_update against TracerBoy::Update (TracerBoy.cpp:3386-3500), evaluated here in float64:
+    mouse look = yaw about +Y by 0.5 * 2 * 6.28 * dx / width then pitch about the XZ-aligned right axis by
+    0.5 * 3.14 * dy / height; WASD/QE move Position and LookAt by dt * speed along view / right / up; sticks beyond the
+    0.2 dead zone scale the motion; the frame is re-orthonormalised; nothing is stored unless the camera moved.
+    Tolerance 1e-5 (float32 trigonometry; DirectXMath's own polynomial sin/cos differs at that level too)."""
+    import tracerboy_b200 as tb
+    W, H = 1920, 1080
+
+    def rot(v, axis, a):
+        n = axis / np.linalg.norm(axis)
+        return v * np.cos(a) + np.cross(n, v) * np.sin(a) + n * np.dot(n, v) * (1 - np.cos(a))
+
+    # 1) no input at the stored mouse position: not moved, camera untouched (even a non-orthonormal one)
+    cam = _camera(right=(2, 0, 0))
+    last = (C.c_uint32 * 2)(10, 20)
+    assert tb.camera_update(cam, last, W, H, 10, 20) is False
+    assert _v(cam.Right).tolist() == [2, 0, 0] and _v(cam.Position).tolist() == [0, 1, 5]
+
+    # 2) mouse look
+    cam = _camera()
+    last = (C.c_uint32 * 2)(100, 100)
+    assert tb.camera_update(cam, last, W, H, 340, 40) is True
+    assert (last[0], last[1]) == (340, 40)
+    yaw, pitch = 0.5 * 2.0 * 6.28 * 240 / W, 0.5 * 3.14 * -60 / H
+    view = rot(rot(np.array([0.0, 0, -1]), np.array([0.0, 1, 0]), yaw), np.array([1.0, 0, 0]), pitch)
+    view /= np.linalg.norm(view)
+    right = np.cross([0, 1, 0], view); right /= np.linalg.norm(right)
+    up = np.cross(view, right); up /= np.linalg.norm(up)
+    assert np.allclose(_v(cam.LookAt) - _v(cam.Position), view, atol=1e-5)
+    assert np.allclose(_v(cam.Right), right, atol=1e-5) and np.allclose(_v(cam.Up), up, atol=1e-5)
+    assert np.allclose(_v(cam.Position), [0, 1, 5])
+    assert cam.LensHeight == 2.0 and cam.FocalDistance == 7.0
+
+    # 3) m_ignoreMouse: the mouse position is remembered but neither rotates nor counts as movement
+    cam = _camera()
+    last = (C.c_uint32 * 2)(0, 0)
+    ignore = tb.CameraSettings(3.0, 1)
+    assert tb.camera_update(cam, last, W, H, 500, 500, cameraSettings=ignore) is False
+    assert (last[0], last[1]) == (500, 500) and _v(cam.LookAt).tolist() == [0, 1, 4]
+
+    # 4) keys: W forward, D right, Q up, and their opposites cancel
+    for keys, want in (("w", (0, 0, -1)), ("S", (0, 0, 1)), ("d", (-1, 0, 0)), ("A", (1, 0, 0)), ("q", (0, 1, 0)), ("E", (0, -1, 0)),
+                       ("ws", (0, 0, 0)), ("wd", (-1, 0, -1))):
+        cam = _camera()
+        last = (C.c_uint32 * 2)(7, 7)
+        assert tb.camera_update(cam, last, W, H, 7, 7, keys, 0.25, cameraSettings=tb.CameraSettings(2.0, 0)) is True
+        step = 0.25 * 2.0 * np.array(want, np.float64)
+        assert np.allclose(_v(cam.Position), np.array([0, 1, 5]) + step, atol=1e-6), keys
+        assert np.allclose(_v(cam.LookAt), np.array([0, 1, 4]) + step, atol=1e-6), keys
+        # right = normalize(cross(+Y, view)): for view = -Z that is -X (the reference's convention)
+        assert np.allclose(_v(cam.Right), [-1, 0, 0], atol=1e-6) and np.allclose(_v(cam.Up), [0, 1, 0], atol=1e-6)
+
+    # 5) controller: dead zone, stick-scaled motion, right stick rotation with its 0.001 * dt scale
+    cam = _camera()
+    last = (C.c_uint32 * 2)(0, 0)
+    assert tb.camera_update(cam, last, 0, 0, 0, 0, None, 1.0, tb.ControllerState(0.1, -0.2, 0.2, 0.15, 0.2, 0.0)) is False
+    cam = _camera()
+    cs = tb.ControllerState(0.0, 0.0, 0.5, 0.0, -0.5, 0.0)   # right trigger: up, left stick Y: backwards at half speed
+    assert tb.camera_update(cam, last, 0, 0, 0, 0, None, 2.0, cs) is True     # default settings: speed 1
+    assert np.allclose(_v(cam.Position), [0, 1 + 2.0 * 0.5, 5 + 2.0 * 0.5], atol=1e-6)
+    cam = _camera()
+    cs = tb.ControllerState(0.8, 0.0, 0, 0, 0, 0)
+    assert tb.camera_update(cam, last, 0, 0, 0, 0, None, 100.0, cs) is True
+    view = rot(np.array([0.0, 0, -1]), np.array([0.0, 1, 0]), 0.8 * 0.001 * 100.0)
+    assert np.allclose(_v(cam.LookAt) - _v(cam.Position), view, atol=1e-5)
+
+    # 6) argument checking
+    lib = tb.load_library()
+    assert lib.tb_camera_update(None, last, 0, 0, 0, 0, None, 0.0, None, None, None) != 0
+    assert lib.tb_update(None, 0, 0, None, 0.0, None, None) != 0

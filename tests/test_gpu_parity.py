@@ -331,6 +331,36 @@ def test_api_state_errors_and_materials(cornell):
     assert st.SelectedPixelDistance > 0 and 0 <= st.SelectedMaterialID < 8
 
 
+def test_update_moves_the_camera_and_invalidates_history(cornell):
+    """TracerBoy::Update on a handle: an idle call changes nothing and keeps the history; W moves Position and LookAt
+    along the view direction, invalidates the history, and the next render is the one tb_set_camera gives for that
+    camera (TracerBoy.cpp:3386-3500)."""
+    import tracerboy_b200 as tb
+    g = tb.TracerBoy(0)
+    g.LoadScene(cornell)
+    g.Resize(48, 48)
+    s = tb.get_default_output_settings()
+    g.Render(s, 2, 0.0)
+    c0 = g.GetCamera()
+    g.Update(0, 0, None, 0.016)
+    assert g.GetNumberOfSamplesSinceLastInvalidate() == 2
+    g.Update(0, 0, "w", 0.5, cameraSettings=tb.CameraSettings(0.2, 1))
+    assert g.GetNumberOfSamplesSinceLastInvalidate() == 0
+    c1 = g.GetCamera()
+    view = np.array([c0.LookAt.x - c0.Position.x, c0.LookAt.y - c0.Position.y, c0.LookAt.z - c0.Position.z])
+    view /= np.linalg.norm(view)
+    moved = np.array([c1.Position.x - c0.Position.x, c1.Position.y - c0.Position.y, c1.Position.z - c0.Position.z])
+    assert np.allclose(moved, 0.5 * 0.2 * view, atol=1e-5)
+    g.Render(s, 2, 0.0)
+    a = g.Readback(tb.BufferKind.ACCUM_RGBW).copy()
+    h = tb.TracerBoy(0)
+    h.LoadScene(cornell)
+    h.Resize(48, 48)
+    h.SetCamera(c1)
+    h.Render(s, 2, 0.0)
+    assert np.array_equal(a.view(np.uint32), h.Readback(tb.BufferKind.ACCUM_RGBW).view(np.uint32))
+
+
 # --------------------------------------------- size-independent properties at the BASELINE.json sizes
 def test_full_size_properties_teapot_1080p(teapot):
     """Teapot 1920x1080 (configs[1]): determinism across runs and across frames-in-flight settings,

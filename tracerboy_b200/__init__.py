@@ -13,9 +13,9 @@ _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 from .api import (TracerBoy, TracerBoyError, OutputSettings, Camera, Material, Ray, Hit, RenderStats,
                   SceneInfo, BufferKind, lib_path, load_library, convert_scene, get_default_output_settings,
                   PostProcessSettings, OutputType, TonemapType, get_default_postprocess_settings,
-                  TemporalAccumulationParams, write_image)
+                  TemporalAccumulationParams, write_image, ControllerState, CameraSettings, camera_update)
 
 __all__ = ["TracerBoy", "TracerBoyError", "OutputSettings", "Camera", "Material", "Ray", "Hit", "RenderStats",
            "SceneInfo", "BufferKind", "lib_path", "load_library", "convert_scene", "get_default_output_settings",
            "PostProcessSettings", "OutputType", "TonemapType", "get_default_postprocess_settings",
-           "TemporalAccumulationParams", "write_image"]
+           "TemporalAccumulationParams", "write_image", "ControllerState", "CameraSettings", "camera_update"]

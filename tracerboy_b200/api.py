@@ -36,6 +36,15 @@ class Camera(C.Structure):  # TracerBoy.h:59-67
                 ("LensHeight", C.c_float), ("FocalDistance", C.c_float)]
 
 
+class ControllerState(C.Structure):  # TracerBoy.h:69-77
+    _fields_ = [("RightStickX", C.c_float), ("RightStickY", C.c_float), ("RightTrigger", C.c_float),
+                ("LeftStickX", C.c_float), ("LeftStickY", C.c_float), ("LeftTrigger", C.c_float)]
+
+
+class CameraSettings(C.Structure):  # TracerBoy::CameraSettings, TracerBoy.h:386-390
+    _fields_ = [("MovementSpeed", C.c_float), ("IgnoreMouse", C.c_uint32)]
+
+
 class OutputSettings(C.Structure):  # TracerBoy.h:212-288 (members that reach PerFrameConstants)
     _fields_ = [("OutputType", C.c_uint32), ("EnableNormalMaps", C.c_uint32), ("RenderMode", C.c_uint32),
                 ("SampleLimit", C.c_int32), ("TimeLimitInSeconds", C.c_float), ("DebugValue", C.c_float),
@@ -155,6 +164,9 @@ def load_library():
         "tb_get_bvh": [vp, vp, u64], "tb_get_bvh_build_ms": [vp, C.POINTER(C.c_double)],
         "tb_get_default_settings": [C.POINTER(OutputSettings)], "tb_get_camera": [vp, C.POINTER(Camera)],
         "tb_set_camera": [vp, C.POINTER(Camera)], "tb_resize": [vp, u32, u32], "tb_select_pixel": [vp, i32, i32],
+        "tb_update": [vp, i32, i32, C.c_void_p, C.c_float, C.POINTER(ControllerState), C.POINTER(CameraSettings)],
+        "tb_camera_update": [C.POINTER(Camera), C.POINTER(C.c_uint32), u32, u32, i32, i32, C.c_void_p, C.c_float,
+                             C.POINTER(ControllerState), C.POINTER(CameraSettings), C.POINTER(C.c_int)],
         "tb_get_stats": [vp, C.POINTER(ReadbackStats)],
         "tb_render": [vp, C.POINTER(OutputSettings), u32, C.c_float], "tb_samples_rendered": [vp, C.POINTER(u32)],
         "tb_invalidate_history": [vp], "tb_set_frame_shard": [vp, u32, u32], "tb_set_row_shard": [vp, u32, u32], "tb_buffer_size": [vp, u32, C.POINTER(u64)],
@@ -187,7 +199,35 @@ EXPORTED_SYMBOLS = ["tb_create", "tb_destroy", "tb_last_error", "tb_version", "t
                     "tb_get_render_stats", "tb_reset_render_stats", "tb_set_profiling", "tb_set_frames_in_flight", "tb_set_shadow_mode", "tb_synchronize", "tb_is_material_id_valid",
                     "tb_get_material", "tb_set_material", "tb_bvh_prebuild_info", "tb_bvh_build", "tb_trace_rays",
                     "tb_get_default_postprocess_settings", "tb_postprocess", "tb_postprocess_image",
-                    "tb_temporal_accumulate_image", "tb_save_image", "tb_write_image"]
+                    "tb_temporal_accumulate_image", "tb_save_image", "tb_write_image", "tb_update", "tb_camera_update"]
+
+
+def _key_table(keyboardInput):
+    """bool keyboardInput[CHAR_MAX] of TracerBoy::Update from an iterable of pressed characters (or a ready table)."""
+    if keyboardInput is None:
+        return None
+    table = (C.c_uint8 * 127)()
+    if isinstance(keyboardInput, (bytes, bytearray)) and len(keyboardInput) == 127:
+        for i, v in enumerate(keyboardInput):
+            table[i] = 1 if v else 0
+    else:
+        for ch in keyboardInput:
+            table[ord(ch) if isinstance(ch, str) else int(ch)] = 1
+    return C.cast(table, C.c_void_p)
+
+
+def camera_update(camera, last_mouse, width, height, mouseX, mouseY, keyboardInput=None, dt=0.0, controllerState=None,
+                  cameraSettings=None):
+    """tb_camera_update: TracerBoy::Update on caller-owned state (host only). Returns bCameraMoved; camera and
+    last_mouse (a 2-element ctypes c_uint32 array) are updated in place."""
+    moved = C.c_int(0)
+    rc = load_library().tb_camera_update(C.byref(camera), last_mouse, int(width), int(height), int(mouseX), int(mouseY),
+                                         _key_table(keyboardInput), float(dt),
+                                         C.byref(controllerState) if controllerState is not None else None,
+                                         C.byref(cameraSettings) if cameraSettings is not None else None, C.byref(moved))
+    if rc != 0:
+        raise TracerBoyError(rc, "tb_camera_update")
+    return bool(moved.value)
 
 
 def get_default_output_settings():
@@ -330,6 +370,12 @@ class TracerBoy:
     def Resize(self, width, height):
         self._ck(self._lib.tb_resize(self._h, width, height))
         self.width, self.height = width, height
+
+    def Update(self, mouseX, mouseY, keyboardInput=None, dt=0.0, controllerState=None, cameraSettings=None):
+        """TracerBoy::Update (TracerBoy.cpp:3386-3500). keyboardInput: iterable of pressed characters or a 127-entry table."""
+        self._ck(self._lib.tb_update(self._h, int(mouseX), int(mouseY), _key_table(keyboardInput), float(dt),
+                                     C.byref(controllerState) if controllerState is not None else None,
+                                     C.byref(cameraSettings) if cameraSettings is not None else None))
 
     def SelectPixel(self, x, y):
         self._ck(self._lib.tb_select_pixel(self._h, x, y))

@@ -627,12 +627,17 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
         // ends when enough lanes have finished to make a service phase worthwhile.
         // Once the queue is exhausted there is nothing to refill with, so the phase would only end when the last
         // ray does; it is cut every 64 iterations instead so that the service phase can park rays over budget.
-        for (uint32_t iter = 0;; iter++) {
-            bool busy = haveRay && !tr.done();
-            bool wantLeaf = busy && tr.at_leaf();
-            uint32_t mB = __ballot_sync(0xffffffffu, busy), mL = __ballot_sync(0xffffffffu, wantLeaf);
-            uint32_t nB = __popc(mB), nL = __popc(mL);
-            if (nB == 0 || (!exhausted && nB < refillBelow) || (KIND == EXT_MAIN && exhausted && iter >= 64u)) break;
+        // (A lane without a ray always has tr.cur == TB_NO_NODE, so `cur` alone says what the lane wants.)
+        uint32_t minBusy = exhausted ? 1u : max(refillBelow, 1u);
+        uint32_t left = (KIND == EXT_MAIN && exhausted) ? 64u : 0xffffffffu;
+        asm volatile("" : "+r"(minBusy), "+r"(left)); // loop constants live in registers (ptxas re-derived them every iteration)
+        while (true) {
+            const bool busy = !tr.done();
+            const bool wantLeaf = (int32_t)tr.cur < 0;
+            const uint32_t nB = __popc(__ballot_sync(0xffffffffu, busy)), nL = __popc(__ballot_sync(0xffffffffu, wantLeaf));
+            const bool stop = (nB < minBusy) | (left == 0u);
+            left--;
+            if (stop) break;
             if (2 * nL > nB) {
                 if (wantLeaf) tr.step_leaf(stack, tris);
             } else {

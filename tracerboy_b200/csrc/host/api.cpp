@@ -52,6 +52,7 @@ struct TbHandle {
     uint32_t shardOffset = 0, shardStride = 1;
     uint32_t rowOffset = 0, rowStride = 1;
     int selX = -1, selY = -1;
+    uint32_t lastMouse[2] = {0, 0}; // m_mouseX, m_mouseY (TracerBoy.cpp:511-512)
     LaunchCounter lc;
     double deviceMs = 0.0;
     uint64_t pathsStarted = 0;
@@ -381,6 +382,98 @@ TB_API int tb_set_camera(TbHandle* h, const TbCamera* c) {
     if (!h || !c) return fail(h, TB_ERR_INVALID_ARG, "null argument");
     h->camera = *c;
     h->samplesRendered = 0; // m_bInvalidateHistory
+    return TB_OK;
+}
+
+// ---- TracerBoy::Update (TracerBoy.cpp:3386-3500), restated on plain float3 math.
+namespace {
+struct V3 { float x, y, z; };
+inline V3 vadd(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 vsub(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 vmul(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline float vdot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+inline V3 vcross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline V3 vnorm(V3 a) { float l = std::sqrt(vdot(a, a)); return l > 0.0f ? vmul(a, 1.0f / l) : a; } // XMVector3Normalize
+// v * XMMatrixRotationAxis(axis, angle): row-vector product with the axis-angle matrix, i.e. Rodrigues' formula
+inline V3 rotate_about(V3 v, V3 axis, float angle) {
+    V3 n = vnorm(axis);
+    float s = std::sin(angle), c = std::cos(angle);
+    return vadd(vadd(vmul(v, c), vmul(vcross(n, v), s)), vmul(n, vdot(n, v) * (1.0f - c)));
+}
+} // namespace
+
+extern "C" TB_API int tb_camera_update(TbCamera* cam, uint32_t lastMouse[2], uint32_t width, uint32_t height, int mouseX, int mouseY,
+                                       const uint8_t* keys, float dt, const TbControllerState* controller,
+                                       const TbCameraSettings* settings, int* movedOut) {
+    if (!cam || !lastMouse) return TB_ERR_INVALID_ARG;
+    const TbControllerState noController = {0, 0, 0, 0, 0, 0};
+    const TbCameraSettings defaults = {1.0f, 0u};
+    const TbControllerState& cs = controller ? *controller : noController;
+    const TbCameraSettings& set = settings ? *settings : defaults;
+    auto key = [&](int lower, int upper) { return keys && (keys[lower] || keys[upper]); };
+    bool moved = false;
+    float yaw = 0.0f, pitch = 0.0f;
+    if (width && height && !set.IgnoreMouse) { // :3393-3399 (the products are evaluated in double there: 2.0 is a double literal)
+        const float rotationScaler = 0.5f;
+        yaw = (float)(rotationScaler * 2.0 * 6.28f * ((float)mouseX - (float)lastMouse[0]) / (float)width);
+        pitch = rotationScaler * 3.14f * ((float)mouseY - (float)lastMouse[1]) / (float)height;
+    }
+    const float deadzone = 0.2f; // :3401
+    if (std::fabs(cs.RightStickX) > deadzone || std::fabs(cs.RightStickY) > deadzone) {
+        const float rotationScaler = 0.001f;
+        yaw += cs.RightStickX * rotationScaler * dt;
+        pitch += -cs.RightStickY * rotationScaler * dt;
+        moved = true;
+    }
+    if (lastMouse[0] != (uint32_t)mouseX || lastMouse[1] != (uint32_t)mouseY) { // :3410-3418
+        if (!set.IgnoreMouse) moved = true;
+        lastMouse[0] = (uint32_t)mouseX;
+        lastMouse[1] = (uint32_t)mouseY;
+    }
+    V3 right = {cam->Right.x, cam->Right.y, cam->Right.z};
+    V3 position = {cam->Position.x, cam->Position.y, cam->Position.z};
+    V3 lookAt = {cam->LookAt.x, cam->LookAt.y, cam->LookAt.z};
+    V3 viewDir = vsub(lookAt, position);
+    const V3 globalUp = {0.0f, 1.0f, 0.0f};
+    const V3 xzRight = vnorm(V3{right.x, 0.0f, right.z});
+    // RotationAxis(GlobalUp, yaw) * RotationAxis(XZAlignedRight, pitch), row vectors: yaw first, then pitch (:3431-3432)
+    viewDir = vnorm(rotate_about(rotate_about(viewDir, globalUp, yaw), xzRight, pitch));
+    right = vnorm(vcross(globalUp, viewDir));
+    V3 up = vnorm(vcross(viewDir, right));
+    lookAt = vadd(position, viewDir);
+    const float speed = set.MovementSpeed;
+    // Position += dt * speed * Axis * multiplier: the scalar dt * speed first, then the vector, then the multiplier
+    auto move = [&](V3 dir, float multiplier, bool add) {
+        const V3 d = vmul(vmul(dir, dt * speed), multiplier);
+        position = add ? vadd(position, d) : vsub(position, d);
+        lookAt = add ? vadd(lookAt, d) : vsub(lookAt, d);
+        moved = true;
+    };
+    const bool lsy = std::fabs(cs.LeftStickY) > deadzone, lsx = std::fabs(cs.LeftStickX) > deadzone;
+    const bool rtr = cs.RightTrigger > deadzone, ltr = cs.LeftTrigger > deadzone;
+    if (key('w', 'W') || lsy) move(viewDir, lsy ? cs.LeftStickY : 1.0f, true);
+    if (key('s', 'S')) move(viewDir, 1.0f, false);
+    if (key('a', 'A')) move(right, 1.0f, false);
+    if (key('d', 'D') || lsx) move(right, lsx ? cs.LeftStickX : 1.0f, true);
+    if (key('q', 'Q') || rtr) move(up, rtr ? cs.RightTrigger : 1.0f, true);
+    if (key('e', 'E') || ltr) move(up, ltr ? cs.LeftTrigger : 1.0f, false);
+    if (moved) { // :3491-3498: the rotated frame is only stored when something moved
+        cam->Position = {position.x, position.y, position.z};
+        cam->LookAt = {lookAt.x, lookAt.y, lookAt.z};
+        cam->Right = {right.x, right.y, right.z};
+        cam->Up = {up.x, up.y, up.z};
+    }
+    if (movedOut) *movedOut = moved ? 1 : 0;
+    return TB_OK;
+}
+
+TB_API int tb_update(TbHandle* h, int mouseX, int mouseY, const uint8_t* keys, float dt, const TbControllerState* controller,
+                     const TbCameraSettings* settings) {
+    if (!h) return TB_ERR_INVALID_ARG;
+    int moved = 0;
+    int rc = tb_camera_update(&h->camera, h->lastMouse, h->width, h->height, mouseX, mouseY, keys, dt, controller, settings, &moved);
+    if (rc != TB_OK) return fail(h, rc, "tb_update: bad argument");
+    if (moved) h->samplesRendered = 0; // InvalidateHistory()
     return TB_OK;
 }
 
