@@ -415,6 +415,10 @@ TB_API int tb_set_frames_in_flight(TbHandle* h, uint32_t n);
  * (shade A -> shadow traversal -> shade B), 2 = automatic (default; by triangle count). Scheduling
  * only: results are identical. */
 TB_API int tb_set_shadow_mode(TbHandle* h, int mode);
+/* Spatial sort of the ray queues before traversal (counting sort by the Morton cell of the ray origin): 0 = off,
+ * 1 = the bounce queue, 3 = bounce and shadow queues, 4 = automatic (default: 3 for scenes whose traversal BVH is
+ * beyond 256 MB, i.e. far outside L2, else 0). Scheduling only: results are identical. */
+TB_API int tb_set_ray_sort(TbHandle* h, int mode);
 TB_API int tb_synchronize(TbHandle* h);
 
 /* ------------------------------------------------------------ post-process */

@@ -79,6 +79,40 @@ def test_bvh_bytes_identical(spec, passes, tmp_path, built):
     assert np.array_equal(g2.GetBVH(), a)
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 6, 7, 8, 13, 14, 29, 100])
+def test_bvh_bytes_identical_tiny_and_degenerate(n, tmp_path, built):
+    """Edge cases of the builder against the oracle, byte for byte: fewer triangles than one treelet (n < 7: no
+    treelet pass runs), exactly one treelet, treelet counts around the 7 / 14 / 28 thresholds of the three passes, and
+    degenerate input (coincident triangles = equal Morton codes, zero-area triangles, a flat axis-aligned patch whose
+    boxes have zero surface area in one axis)."""
+    import tracerboy_b200 as tb
+    from oracle.binding import Oracle
+    rng = np.random.default_rng(n)
+    verts = rng.uniform(-1, 1, (n, 3, 3)).astype(np.float32)
+    if n >= 6:
+        verts[1] = verts[0]                      # coincident triangles: equal Morton codes, tie broken by index
+        verts[2, 1] = verts[2, 0]                # zero-area triangle
+        verts[3:6, :, 2] = 0.25                  # flat patch in z
+    g = tb.TracerBoy(0)
+    g.BuildRaytracingAccelerationStructure([(verts.reshape(-1, 3), None)])
+    path = str(tmp_path / "tiny.tbscene")
+    g.SaveScene(path)
+    o = Oracle()
+    o.LoadScene(path, 3)
+    a, b = g.GetBVH(), o.GetBVH()
+    assert a.shape == b.shape == (116 * n - 16,)
+    diff = np.flatnonzero(a != b)
+    assert diff.size == 0, "BVH differs at %d bytes, first at %d" % (diff.size, diff[0])
+    # and the traversal agrees on it
+    from tracerboy_b200.api import RAY_DTYPE
+    rays = np.zeros(256, RAY_DTYPE)
+    rays["Origin"] = rng.uniform(-2, 2, (256, 3)); rays["Direction"] = rng.normal(0, 1, (256, 3))
+    rays["TMin"] = 0.001; rays["TMax"] = 999999.0
+    hg, ho = g.TraceRays(rays), o.TraceRays(rays)
+    for f in hg.dtype.names: # t, barycentrics, ids and both counters
+        assert np.array_equal(hg[f].view(np.uint32), ho[f].view(np.uint32)), f
+
+
 def _random_rays(n, cam, seed):
     from tracerboy_b200.api import RAY_DTYPE
     rng = np.random.default_rng(seed)
@@ -211,6 +245,22 @@ def test_materials_scene_bit_exact(shadow_mode, tmp_path, built):
     s = tb.get_default_output_settings()
     s.MaxBounces = 8
     _compare_render(g, o, s, 3)
+
+
+def test_ray_sort_changes_nothing(tmp_path, built):
+    """The spatial sort of the bounce and shadow queues (automatic only for scenes far beyond L2) is scheduling only:
+    forced on, a scene with every material / light path still equals the oracle bit for bit, counters included."""
+    import tracerboy_b200 as tb
+    path = _tbscene("synthetic:showcase?tris=400&seed=5", tmp_path)
+    g, o = _pair(path, 96, 64)
+    g.SetShadowMode(1)
+    s = tb.get_default_output_settings()
+    s.MaxBounces = 6
+    for mode in (3, 1, 0):
+        g.SetRaySort(mode)
+        _compare_render(g, o, s, 2) # both sides keep accumulating: frames 0-1, 2-3, 4-5
+    with pytest.raises(tb.TracerBoyError):
+        g.SetRaySort(2)
 
 
 @pytest.mark.parametrize("shadow_mode", [0, 1])

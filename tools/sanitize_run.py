@@ -23,6 +23,7 @@ for spec, w, h, shadow in (("tests/golden/cornell-box.tbscene", 96, 64, 2), ("sy
     g.LoadScene(path)
     g.Resize(w, h)
     g.SetShadowMode(shadow)
+    g.SetRaySort(3 if shadow == 1 else 4)  # the queue sort kernels on two of the scenes
     s.MaxBounces = 5
     s.EnableNormalMaps = 1
     g.Render(s, 3, 0.0)          # frame graphs captured here

@@ -171,7 +171,7 @@ def load_library():
         "tb_render": [vp, C.POINTER(OutputSettings), u32, C.c_float], "tb_samples_rendered": [vp, C.POINTER(u32)],
         "tb_invalidate_history": [vp], "tb_set_frame_shard": [vp, u32, u32], "tb_set_row_shard": [vp, u32, u32], "tb_buffer_size": [vp, u32, C.POINTER(u64)],
         "tb_readback": [vp, u32, vp, u64], "tb_device_buffer": [vp, u32, C.POINTER(vp), C.POINTER(u64)],
-        "tb_get_render_stats": [vp, C.POINTER(RenderStats)], "tb_reset_render_stats": [vp], "tb_synchronize": [vp], "tb_set_profiling": [vp, i32], "tb_set_frames_in_flight": [vp, u32], "tb_set_shadow_mode": [vp, i32],
+        "tb_get_render_stats": [vp, C.POINTER(RenderStats)], "tb_reset_render_stats": [vp], "tb_synchronize": [vp], "tb_set_profiling": [vp, i32], "tb_set_frames_in_flight": [vp, u32], "tb_set_shadow_mode": [vp, i32], "tb_set_ray_sort": [vp, i32],
         "tb_is_material_id_valid": [vp, i32], "tb_get_material": [vp, i32, C.POINTER(Material), C.c_char_p, u32],
         "tb_set_material": [vp, i32, C.POINTER(Material)],
         "tb_bvh_prebuild_info": [C.POINTER(GeometryDesc), u32, C.POINTER(PrebuildInfo)],
@@ -199,7 +199,7 @@ EXPORTED_SYMBOLS = ["tb_create", "tb_destroy", "tb_last_error", "tb_version", "t
                     "tb_get_render_stats", "tb_reset_render_stats", "tb_set_profiling", "tb_set_frames_in_flight", "tb_set_shadow_mode", "tb_synchronize", "tb_is_material_id_valid",
                     "tb_get_material", "tb_set_material", "tb_bvh_prebuild_info", "tb_bvh_build", "tb_trace_rays",
                     "tb_get_default_postprocess_settings", "tb_postprocess", "tb_postprocess_image",
-                    "tb_temporal_accumulate_image", "tb_save_image", "tb_write_image", "tb_update", "tb_camera_update"]
+                    "tb_temporal_accumulate_image", "tb_save_image", "tb_write_image", "tb_update", "tb_camera_update", "tb_set_ray_sort"]
 
 
 def _key_table(keyboardInput):
@@ -475,6 +475,10 @@ class TracerBoy:
 
     def SetShadowMode(self, mode):
         self._ck(self._lib.tb_set_shadow_mode(self._h, int(mode)))
+
+    def SetRaySort(self, mode):
+        """0 off, 1 bounce queue, 3 bounce + shadow queues, 4 automatic (scheduling only, results are identical)."""
+        self._ck(self._lib.tb_set_ray_sort(self._h, int(mode)))
 
     def SetProfiling(self, enable):
         self._ck(self._lib.tb_set_profiling(self._h, int(bool(enable))))

@@ -674,6 +674,81 @@ __global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState 
     flush_stats(st, 6, rays, ntris, nboxes);
 }
 
+// ------------------------------------------------------------------ ray sort
+// Spatial sort of a bounce's ray queue (counting sort by the Morton cell of the ray origin, 5 bits per axis inside
+// the scene box). The queue order k_shade leaves behind is the order in which rays retired from the previous
+// traversal, i.e. random within a window of ~150 k paths; on a scene whose BVH is far larger than L2 every lane of a
+// warp then walks its own part of the tree through DRAM. Sorted, the rays a warp (and its neighbours in time) pick up
+// start in the same cell and share the lower levels of the tree in L1 / L2. Path results do not depend on queue
+// order (every path is independent and accumulation is ordered per frame), so this changes timing only.
+__device__ __forceinline__ uint32_t spread5(uint32_t v) { // bit k of a 5-bit value -> bit 3k
+    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6) | ((v & 16u) << 8);
+}
+// Rays of one warp mostly fall into a few cells (that is the point of sorting them), so the cell counters are
+// updated once per distinct key per warp (__match_any_sync), not once per ray: plain per-ray atomics serialised
+// millions of same-address operations on scenes whose rays crowd a few cells.
+__global__ void __launch_bounds__(256) k_sort_keys(DeviceBvh bvh, PathState st, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ countPtr,
+                                                   const float4* __restrict__ rayO) {
+    const uint32_t count = *countPtr;
+    const uint32_t lane = threadIdx.x & 31;
+    const float sx = 16.0f / fmaxf(bvh.root.h[0], 1e-30f), sy = 16.0f / fmaxf(bvh.root.h[1], 1e-30f), sz = 16.0f / fmaxf(bvh.root.h[2], 1e-30f);
+    const float ox = bvh.root.c[0] - bvh.root.h[0], oy = bvh.root.c[1] - bvh.root.h[1], oz = bvh.root.c[2] - bvh.root.h[2];
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < count; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + lane;
+        uint32_t key = 0xffffffffu;
+        if (i < count) {
+            const uint32_t pi = queue[i];
+            const float4 o = rayO[pi];
+            // NaN / out-of-box origins land in cell 0 or 31 of the axis: any cell is fine, the key only orders work
+            const uint32_t cx = (uint32_t)fminf(fmaxf((o.x - ox) * sx, 0.0f), 31.0f);
+            const uint32_t cy = (uint32_t)fminf(fmaxf((o.y - oy) * sy, 0.0f), 31.0f);
+            const uint32_t cz = (uint32_t)fminf(fmaxf((o.z - oz) * sz, 0.0f), 31.0f);
+            key = spread5(cx) | (spread5(cy) << 1) | (spread5(cz) << 2);
+            st.sortKeys[i] = key;
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        if (i < count && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&st.sortHist[key], (uint32_t)__popc(peers));
+    }
+}
+// exclusive scan of the TB_SORT_CELLS counters in place (one block of 1024 threads, 32 cells per thread)
+__global__ void __launch_bounds__(1024) k_sort_scan(PathState st) {
+    __shared__ uint32_t s_warp[32];
+    const uint32_t t = threadIdx.x, per = TB_SORT_CELLS / 1024u;
+    uint32_t local[TB_SORT_CELLS / 1024u];
+    uint32_t sum = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < per; k++) { local[k] = st.sortHist[t * per + k]; sum += local[k]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((t & 31) >= (uint32_t)o) incl += v; }
+    if ((t & 31) == 31) s_warp[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32) {
+        uint32_t w = s_warp[t], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, wi, o); if (t >= (uint32_t)o) wi += v; }
+        s_warp[t] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = s_warp[t >> 5] + incl - sum;
+#pragma unroll
+    for (uint32_t k = 0; k < per; k++) { st.sortHist[t * per + k] = run; run += local[k]; }
+}
+__global__ void __launch_bounds__(256) k_sort_scatter(PathState st, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ countPtr) {
+    const uint32_t count = *countPtr;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < count; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + lane;
+        const uint32_t key = i < count ? st.sortKeys[i] : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+        uint32_t pos = 0;
+        if (i < count && lane == leader) pos = atomicAdd(&st.sortHist[key], (uint32_t)__popc(peers));
+        pos = __shfl_sync(0xffffffffu, pos, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        if (i < count) st.sortTmp[pos] = queue[i];
+    }
+}
+
 // ----------------------------------------------------------------------- shade
 // End of a path: firefly clamp + filter weight (kernel.glsl:1907-1920) and NaN rejection
 // (RayGenCommon.h:704-707). The sample and the path's rand() seed are staged per frame;
@@ -1214,6 +1289,11 @@ static int num_sms() {
 // captured once into a CUDA graph and replayed: nothing baked into the graph changes from frame to frame.
 __global__ void k_set_frame(FrameConstants fc, FrameConstants* dst) { *dst = fc; }
 
+// Sorting the bounce queues pays when node fetches go to DRAM: traversal layout (112 B per triangle) well beyond the
+// 126 MB L2. Measured (bounce + shadow queues): 20.8 M triangles (2.3 GB) +10.6 %; 875 k triangles (98 MB) -2 %,
+// Teapot (14 MB) -5 %: when the nodes already come from L1 / L2 the three extra launches per queue are pure cost.
+static bool sort_pays(const DeviceBvh& bvh) { return (uint64_t)bvh.numPrims * 112ull > (256ull << 20); }
+
 static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, const FrameConstants& fc, const FrameConstants* fcDev,
                                 PathState& st, cudaStream_t stream, uint64_t& launches, KernelTimers* timers, const RenderOptions& opts) {
     const uint32_t n = fc.width * fc.height;
@@ -1240,7 +1320,23 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
         // ray suspension pays when few frames are in flight (their tails have nothing to overlap with): measured with 16
         // slots it costs 1-2 % (three mostly empty launches per bounce), with one slot it is worth 2.2x on Teapot
         const int suspendMode = suspendEnv >= 0 ? suspendEnv : (opts.suspendRays ? 1 : 0);
-        k_extend<EXT_MAIN><<<blocks, 128, 0, stream>>>(bvh, st, qi, b == 0, heat, fcDev, suspendMode ? budgetMain : 0xffffffffu, refillBelow); launches++;
+        // bounce queues of large scenes are sorted by origin cell first (primary rays already come in 8x4 pixel tiles)
+        static int sortEnv = -2; // tuning knob (results never depend on it)
+        if (sortEnv == -2) { const char* e = getenv("TB_SORT"); sortEnv = e ? atoi(e) : -1; }
+        // bit 0: the bounce queue, bit 1: the shadow queue
+        const int sortMode = sortEnv >= 0 ? sortEnv : (opts.sortRays == 2 ? (sort_pays(bvh) ? 3 : 0) : opts.sortRays);
+        PathState stx = st; // what k_extend<EXT_MAIN> reads its queue from
+        auto sort_queue = [&](const uint32_t* queue, const uint32_t* countPtr, const float4* rayO) {
+            cudaMemsetAsync(st.sortHist, 0, 4 * (TB_SORT_CELLS + 1), stream);
+            k_sort_keys<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(bvh, st, queue, countPtr, rayO); launches++;
+            k_sort_scan<<<1, 1024, 0, stream>>>(st); launches++;
+            k_sort_scatter<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(st, queue, countPtr); launches++;
+        };
+        if (sortMode && b > 0) {
+            sort_queue(st.queue[qi], &st.queueCount[qi], st.rayO);
+            stx.queue[qi] = st.sortTmp;
+        }
+        k_extend<EXT_MAIN><<<blocks, 128, 0, stream>>>(bvh, stx, qi, b == 0, heat, fcDev, suspendMode ? budgetMain : 0xffffffffu, refillBelow); launches++;
         if (suspendMode) {
             uint32_t rblocks = (st.susCapacity + 127) / 128;
             if (rblocks > sms * 4) rblocks = sms * 4;
@@ -1264,7 +1360,12 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
                                   else k_shade<STG, false><<<blocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi); launches++; } while (0)
         if (nee && shadowMode) {
             TB_LAUNCH_SHADE(0);
-            k_extend<EXT_SHADOW><<<blocks, 128, 0, stream>>>(bvh, st, qi, 0, 0, fcDev, 0xffffffffu, refillBelow); launches++;
+            PathState sts = st; // what k_extend<EXT_SHADOW> reads its queue from
+            if (sortMode & 2) { // the bounce's shadow feelers, by origin cell (sortTmp is free again: k_extend<EXT_MAIN> is done)
+                sort_queue(st.shadowQueue, &st.queueCount[4], st.shRayO);
+                sts.shadowQueue = st.sortTmp;
+            }
+            k_extend<EXT_SHADOW><<<blocks, 128, 0, stream>>>(bvh, sts, qi, 0, 0, fcDev, 0xffffffffu, refillBelow); launches++;
             TB_LAUNCH_SHADE(1);
         } else if (nee) {
             TB_LAUNCH_SHADE(2);
@@ -1306,7 +1407,7 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
     if (!graph || timers || !useGraphs) return launch_frame(bvh, sc, fc, fcDev, st, stream, lc.count, timers, opts);
     FrameGraph::Key key = {opts.epoch, fc.width, fc.height, (uint32_t)fc.settings.MaxBounces, fc.settings.OutputType == TB_OUTPUT_HEATMAP ? 1u : 0u,
                            fc.settings.EnableNextEventEstimation ? 1u : 0u, (uint32_t)opts.shadowMode, (uint32_t)opts.walkRounds,
-                           opts.sceneHasSSS ? 1u : 0u, opts.suspendRays ? 1u : 0u};
+                           opts.sceneHasSSS ? 1u : 0u, opts.suspendRays ? 1u : 0u, (uint32_t)opts.sortRays};
     if (!graph->exec || memcmp(&key, &graph->key, sizeof(key)) != 0) {
         graph->reset();
         (void)num_sms(); // device query outside the capture

@@ -34,6 +34,10 @@ struct PathState {
     uint32_t* walkQueue[2] = {nullptr, nullptr};
     float4* walkA = nullptr;       // absorption.xyz, maxTravelDistance
     float4* walkB = nullptr;       // CurrentIOR, NewIOR, roughness, travelDistance of the ray in flight
+    // spatial sort of a bounce's ray queue (large scenes): cell key per entry, sorted copy, cell histogram / offsets
+    uint32_t* sortKeys = nullptr;
+    uint32_t* sortTmp = nullptr;
+    uint32_t* sortHist = nullptr;   // TB_SORT_CELLS + 1 words
     // suspended long rays: two ping-pong record buffers, one counter per round
     uint32_t* susBuf[2] = {nullptr, nullptr};
     uint32_t* susCount = nullptr;   // 4 counters
@@ -85,11 +89,14 @@ struct KernelTimers {
 };
 
 // scheduling knobs; none of them changes a result
+#define TB_SORT_CELLS 32768u // 5 bits per axis of the ray origin inside the scene box
+
 struct RenderOptions {
     int shadowMode = 2; // next-event shadow rays: 0 traced inline in k_shade, 1 own wavefront stage, 2 automatic
     uint32_t epoch = 0; // bumped by the host when the scene / BVH / frame buffers are re-created (invalidates captured frame graphs)
     int walkRounds = 1; // glass / subsurface walk: wavefront rounds (k_extend<EXT_WALK> + k_walk_step) before the persistent tail kernel
     bool suspendRays = true; // park rays over budget and resume them in k_extend_resume rounds (set by the host: on with fewer than 8 frames in flight)
+    int sortRays = 2;   // spatial sort of the ray queues before traversal: 0 off, bit 0 bounce queue, bit 1 shadow queue (1 or 3), 2 automatic (3 for scenes whose BVH is far beyond L2)
     bool sceneHasSSS = true; // any material with the subsurface flag (selects the k_shade variant with the inline random walk)
 };
 
@@ -99,7 +106,7 @@ cudaError_t build_bvh(const TbGeometryRecord* d_geoms, const uint32_t* d_triPref
                       DeviceBvh& out, cudaStream_t stream, LaunchCounter& lc);
 // The captured kernel sequence of one frame on one frame slot (see render_frame).
 struct FrameGraph {
-    struct Key { uint32_t epoch, width, height, maxBounces, heat, nee, shadowMode, walkRounds, sss, suspend; }; // no padding: compared with memcmp
+    struct Key { uint32_t epoch, width, height, maxBounces, heat, nee, shadowMode, walkRounds, sss, suspend, sort; }; // no padding: compared with memcmp
     Key key{};
     cudaGraphExec_t exec = nullptr;
     uint64_t launches = 0; // kernels inside the graph

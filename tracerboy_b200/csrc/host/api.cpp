@@ -504,7 +504,7 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
         // on Teapot, +12 % on the dragon stand-in and +22 % on vw-van at 4K, whose glass walks end in a
         // millisecond-long tail of a few sequential 100-ray walkers that only other frames' work can hide;
         // 32 instead of 16 is another +6 % on vw-van and on the 20 M-triangle scene, +1.5 % on the dragon stand-in.
-        size_t perSlot = n * (80 + 4 + 32 + 8 + 40 + 56 + 8 + 40) + 2 * (n / 16 + 1024) * 448;
+        size_t perSlot = n * (80 + 4 + 32 + 8 + 40 + 56 + 8 + 40 + 8) + 2 * (n / 16 + 1024) * 448;
         uint32_t fif = h->framesInFlight;
         if (fif == 0) {
             size_t freeB = 0, totalB = 0;
@@ -525,6 +525,7 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
         CUDA_OK(h, alloc((void**)&p.queue[0], 4 * n)); CUDA_OK(h, alloc((void**)&p.queue[1], 4 * n));
         CUDA_OK(h, alloc((void**)&p.queueCount, 64));
         CUDA_OK(h, alloc((void**)&p.hitQueue, 4 * n)); CUDA_OK(h, alloc((void**)&p.missQueue, 4 * n));
+        CUDA_OK(h, alloc((void**)&p.sortKeys, 4 * n)); CUDA_OK(h, alloc((void**)&p.sortTmp, 4 * n)); CUDA_OK(h, alloc((void**)&p.sortHist, 4 * (TB_SORT_CELLS + 1)));
         CUDA_OK(h, alloc((void**)&p.shadowQueue, 4 * n)); CUDA_OK(h, alloc((void**)&p.shRayO, 16 * n)); CUDA_OK(h, alloc((void**)&p.shRayD, 16 * n));
         CUDA_OK(h, alloc((void**)&p.shHit, 16 * n)); CUDA_OK(h, alloc((void**)&p.shHitGeom, 4 * n));
         CUDA_OK(h, alloc((void**)&p.walkQueue[0], 4 * n)); CUDA_OK(h, alloc((void**)&p.walkQueue[1], 4 * n)); CUDA_OK(h, alloc((void**)&p.walkA, 16 * n)); CUDA_OK(h, alloc((void**)&p.walkB, 16 * n));
@@ -884,6 +885,11 @@ TB_API int tb_set_frames_in_flight(TbHandle* h, uint32_t n) {
 TB_API int tb_set_shadow_mode(TbHandle* h, int mode) {
     if (!h || mode < 0 || mode > 2) return fail(h, TB_ERR_INVALID_ARG, "shadow mode must be 0 (inline), 1 (queue) or 2 (auto)");
     h->options.shadowMode = mode;
+    return TB_OK;
+}
+TB_API int tb_set_ray_sort(TbHandle* h, int mode) {
+    if (!h || mode < 0 || mode > 4 || mode == 2) return fail(h, TB_ERR_INVALID_ARG, "ray sort must be 0 (off), 1 (bounce queue), 3 (bounce + shadow queues) or 4 (auto)");
+    h->options.sortRays = mode == 4 ? 2 : mode;
     return TB_OK;
 }
 TB_API int tb_set_profiling(TbHandle* h, int enable) {
