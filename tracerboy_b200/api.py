@@ -138,7 +138,8 @@ _lib = None
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "libtracerboy_b200.so")
+    # TB_LIB: an alternative build of the same library (tuning experiments, e.g. other launch bounds)
+    return os.environ.get("TB_LIB") or os.path.join(_HERE, "lib", "libtracerboy_b200.so")
 
 
 def load_library():
