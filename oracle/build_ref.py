@@ -68,6 +68,34 @@ def build_post(force=False):
     return target
 
 
+TEMPORAL = "/root/reference/TracerBoy/TemporalAccumulationCS.hlsl"
+
+
+def temporal_lib_path():
+    return os.path.join(OUT, "libref_temporal.so")
+
+
+def build_temporal(force=False):
+    """oracle/_ref/libref_temporal.so: the reference's TemporalAccumulationCS.hlsl main() as host C++ (resources shimmed)."""
+    target = temporal_lib_path()
+    if not (os.path.exists(TONEMAP) and os.path.exists(TEMPORAL)):
+        return target if os.path.exists(target) else None
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_temporal.cpp")] + [TONEMAP, TEMPORAL]
+    if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs):
+        return target
+    sys.path.insert(0, os.path.join(HERE, "ref"))
+    import prepass
+    prepass.run_temporal(TONEMAP, TEMPORAL, os.path.join(OUT, "temporal_gen.inc"))
+    cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-mfma", "-ffp-contract=off", "-fsingle-precision-constant",
+           "-fno-fast-math", "-fvisibility=hidden", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + HERE,
+           os.path.join(HERE, "ref", "ref_temporal.cpp"), "-o", target]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref temporal accumulation build failed:\n" + r.stdout)
+    return target
+
+
 TRAVERSE = "/root/reference/D3D12RaytracingFallback/src/TraverseFunction.hlsli"
 
 
@@ -245,6 +273,7 @@ def build_raygen(force=False):
 
 
 if __name__ == "__main__":
+    print(build_temporal(force="--force" in sys.argv))
     print(build_raygen(force="--force" in sys.argv))
     print(build_boxes(force="--force" in sys.argv))
     print(build_treelet(force="--force" in sys.argv))

@@ -15,7 +15,9 @@
 //       the restatements must match them bit for bit -> PINNED against the reference's code;
 //       likewise the builder's arithmetic: CalculateMortonCode, GenerateHierarchy (Karras), one treelet optimisation round
 //       (the group shader run by 32 host threads + barrier) and the leaf / parent box constructors -> PINNED;
-//  (ii) the builder's resource-bound glue, the traversal loop and the RayGenCommon/SharedHitGroup/SharedRaytracing glue are
+//       the light sampling / environment lookup / hash13 / Halton of RayGenCommon.h (ref_raygen.cpp) and the whole main() of
+//       TemporalAccumulationCS.hlsl (ref_temporal.cpp, resources shimmed) -> PINNED;
+//  (ii) the builder's resource-bound glue, the traversal loop and the rest of the RayGenCommon/SharedHitGroup/SharedRaytracing glue are
 //       HLSL that cannot be compiled here: restated, checked by the fallback layer's own
 //       validator invariants, analytic known answers and independent numpy restatements
 //       -> "parity unpinned" by reference outputs for these parts.

@@ -24,8 +24,11 @@ struct float4;
 struct float3 {
     union { struct { float x, y, z; }; struct { float r, g, b; }; };
     float3() : x(0), y(0), z(0) {}
-#ifdef RC_POST
-    float3(const float4& v); // HLSL implicit truncation float4 -> float3 (PostProcessCS.hlsl:26, 69, 118)
+#if defined(RC_POST) || defined(RC_TEMPORAL)
+    float3(const float4& v); // HLSL implicit truncation float4 -> float3 (PostProcessCS.hlsl:26, 69, 118; TemporalAccumulationCS.hlsl:106, 184)
+#endif
+#ifdef RC_TEMPORAL
+    float2 rg() const { return float2(x, y); } // PrevMomentData.rg (TemporalAccumulationCS.hlsl:222)
 #endif
     float3(float s) : x(s), y(s), z(s) {}
     float3(float x_, float y_, float z_) : x(x_), y(y_), z(z_) {}
@@ -51,7 +54,7 @@ struct float4 {
     float3 xyz() const { return float3(x, y, z); }
     float3 rgb() const { return float3(x, y, z); }
 };
-#ifdef RC_POST
+#if defined(RC_POST) || defined(RC_TEMPORAL)
 inline float3::float3(const float4& v) : x(v.x), y(v.y), z(v.z) {}
 #endif
 typedef float2 vec2;

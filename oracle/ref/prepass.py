@@ -47,6 +47,32 @@ def run_post(tonemap_h, postprocess_hlsl, dst):
     open(dst, "w").write(text)
 
 
+def run_temporal(tonemap_h, temporal_hlsl, dst):
+    """ColorToLuma of Tonemap.h + PlaneIntersection and the whole body of main() of TemporalAccumulationCS.hlsl (with its
+    NEIGHBORHOOD_CLAMPING / WORLD_POSITION_HISTORY_REJECTION switches). The resource declarations, the root signature
+    and the entry-point attributes cannot be compiled; the resources are shims in ref_temporal.cpp. The unused
+    SampleTextureCatmullRom is skipped."""
+    t = open(tonemap_h).read()
+    a = t.index("float ColorToLuma(float3 color)")
+    luma = t[a:t.index("}", a) + 1]
+    h = open(temporal_hlsl).read()
+    a, b = h.index("float PlaneIntersection("), h.index("#define ComputeRS")
+    plane = h[a:b]
+    a = h.index("#define NEIGHBORHOOD_CLAMPING 0")
+    body = h[a:]
+    for attr in ("[RootSignature(ComputeRS)]", "[numthreads(TEMPORAL_ACCUMULATION_THREAD_GROUP_WIDTH, TEMPORAL_ACCUMULATION_THREAD_GROUP_HEIGHT, 1)]"):
+        if attr not in body:
+            raise SystemExit("prepass: expected attribute not found: " + attr)
+        body = body.replace(attr, "")
+    entry = "void main( uint3 DTid : SV_DispatchThreadID )"
+    if entry not in body:
+        raise SystemExit("prepass: entry point not found")
+    body = body.replace(entry, "static void shader_main(uint3 DTid)")
+    text = luma + "\n" + plane + "\n" + body
+    text = re.sub(r"\.(xyz|rgb|xy|rg)\b(?!\s*\()", r".\1()", text)
+    open(dst, "w").write(text)
+
+
 def run_traverse(src, dst_box, dst_rest):
     """The three pure functions of the fallback layer's ray query (TraverseFunction.hlsli): RayBoxTest into one
     file (compiled with contraction on: the pinned slab test is one fma per product), GetRayData and the watertight

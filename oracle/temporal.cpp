@@ -1,10 +1,11 @@
 // temporal.cpp — CPU ORACLE (test infrastructure): realtime temporal accumulation.
 //
 // Hand restatement of TemporalAccumulationCS.hlsl:100-235 (NEIGHBORHOOD_CLAMPING 0, WORLD_POSITION_HISTORY_REJECTION 1)
-// with the constants TemporalAccumulationPass.cpp:72-127 fills. PARITY UNPINNED by reference outputs: the shader is
-// resource-bound HLSL (Texture2D loads, SampleLevel) and cannot be compiled here. Pinned choices: out-of-bounds
-// texture loads return 0 (D3D); int2(float) truncates toward zero; the bilinear fetch of the moment history
-// (SampleLevel, clamp addressing) uses exact float weights.
+// with the constants TemporalAccumulationPass.cpp:72-127 fills. Pinned against the reference's own shader text:
+// oracle/_ref/libref_temporal.so compiles main() from the mount with only the resources shimmed (oracle/ref/
+// ref_temporal.cpp) and tests/test_cpu_temporal.py requires this file to match it bit for bit. What stays a pinned
+// CHOICE (texture-unit behaviour that has no source text): out-of-bounds texture loads return 0 (D3D); the bilinear
+// fetch of the moment history (SampleLevel, clamp addressing) uses exact float weights.
 #include <cmath>
 #include <cstring>
 #include "../tracerboy_b200/csrc/common/tb_vec.h"

@@ -1,6 +1,6 @@
 """Realtime temporal accumulation oracle (oracle/temporal.cpp, TemporalAccumulationCS.hlsl:100-235) on the CPU:
-analytic known answers. The shader is resource-bound HLSL that cannot be compiled here, so this restatement is
-"parity unpinned" by reference outputs."""
+analytic known answers, and bit equality with the reference's own shader text compiled from the mount
+(oracle/_ref/libref_temporal.so, resources shimmed)."""
 import numpy as np
 import pytest
 
@@ -97,3 +97,58 @@ def test_moved_camera_rejects_disoccluded_history(built):
     far = pwp.copy(); far[..., :3] += 1000.0
     out, _ = binding.temporal_accumulate_image(p, history, current, wp, far, nn)
     assert np.array_equal(out[..., :3], current[..., :3])
+
+
+def test_restatement_equals_reference_shader_text(built):
+    """oracle/temporal.cpp against the reference's own TemporalAccumulationCS.hlsl main() compiled from the mount
+    (oracle/_ref/libref_temporal.so; only the resources are shims there): colour, alpha (variance) and moments
+    bit for bit, for a static camera, shifted previous cameras (reprojection, history rejection, off-screen
+    history), rotated previous frames, IgnoreHistory, moments on and off, invalid hits (zero normals) and random
+    (non-planar) world positions that exercise the neighbourhood rejection test."""
+    import ctypes as C
+    import os
+    from oracle import binding
+    path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_temporal.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_temporal.so not built (needs the reference mount at build time)")
+    ref = C.CDLL(path)
+    ref.ref_temporal_accumulate_image.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32] + [C.c_void_p] * 8
+    ref.ref_temporal_accumulate_image.restype = C.c_int
+    rng = np.random.default_rng(12)
+
+    def run_ref(p, history, current, wp, pwp, nn, moments):
+        h, w = current.shape[:2]
+        color = np.zeros((h, w, 4), np.float32)
+        mom = np.zeros((h, w, 4), np.float32)
+        imgs = [np.ascontiguousarray(a, np.float32) for a in (history, current, wp, pwp, nn, moments)]
+        rc = ref.ref_temporal_accumulate_image(C.byref(p), w, h, *[a.ctypes.data_as(C.c_void_p) for a in imgs],
+                                               color.ctypes.data_as(C.c_void_p), mom.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        return color, mom
+
+    cases = 0
+    for seed, shift in ((0, (0.0, 0.0, 0.0)), (1, (0.31, 0.0, 0.0)), (2, (-0.2, 0.13, 0.05)), (3, (4.0, 0.0, 0.0)), (4, (0.0, -0.4, 0.6))):
+        for variant in ("plain", "no_moments", "ignore_history", "rotated", "random_positions", "holes"):
+            p, history, current, wp, pwp, nn, moments = make_inputs(seed, 80, 48, shift)
+            if variant == "no_moments": p.OutputMomentInformation = 0
+            if variant == "ignore_history": p.IgnoreHistory = 1
+            if variant == "rotated":
+                a = 0.07
+                p.PrevCamera.LookAt.x = p.PrevCamera.Position.x + np.sin(a)
+                p.PrevCamera.LookAt.z = p.PrevCamera.Position.z - np.cos(a)
+                p.PrevCamera.Right.x, p.PrevCamera.Right.z = np.cos(a), np.sin(a)
+            if variant == "random_positions":
+                wp[..., :3] += rng.normal(0, 0.4, wp[..., :3].shape).astype(np.float32)
+                pwp[..., :3] += rng.normal(0, 0.4, pwp[..., :3].shape).astype(np.float32)
+            if variant == "holes":
+                nn[rng.random(nn.shape[:2]) < 0.2] = 0.0
+                history[rng.random(nn.shape[:2]) < 0.05] = np.nan
+            c0, m0 = binding.temporal_accumulate_image(p, history, current, wp, pwp, nn, moments)
+            c1, m1 = run_ref(p, history, current, wp, pwp, nn, moments)
+            same = (c0.view(np.uint32) == c1.view(np.uint32)) | (np.isnan(c0) & np.isnan(c1))
+            assert same.all(), (seed, variant, int((~same).sum()))
+            if p.OutputMomentInformation:
+                same = (m0.view(np.uint32) == m1.view(np.uint32)) | (np.isnan(m0) & np.isnan(m1))
+                assert same.all(), (seed, variant, "moments", int((~same).sum()))
+            cases += 1
+    assert cases == 30

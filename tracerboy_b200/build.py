@@ -202,6 +202,7 @@ def build_all(force=False, verbose=False):
     build_ref.build_treelet(force)
     build_ref.build_boxes(force)
     build_ref.build_raygen(force)
+    build_ref.build_temporal(force)
 
 
 if __name__ == "__main__":
