@@ -68,6 +68,36 @@ def build_post(force=False):
     return target
 
 
+GENHIST = "/root/reference/TracerBoy/GenerateHistogramCS.hlsl"
+AVGLUM = "/root/reference/TracerBoy/CalculateAveragedLuminanceCS.hlsl"
+
+
+def hist_lib_path():
+    return os.path.join(OUT, "libref_hist.so")
+
+
+def build_hist(force=False):
+    """oracle/_ref/libref_hist.so: the reference's auto-exposure shaders (GenerateHistogramCS.hlsl, CalculateAveragedLuminanceCS.hlsl)
+    as host C++, a 16x16 group = 256 host threads."""
+    target = hist_lib_path()
+    if not (os.path.exists(TONEMAP) and os.path.exists(GENHIST) and os.path.exists(AVGLUM)):
+        return target if os.path.exists(target) else None
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_hist.cpp")] + [TONEMAP, GENHIST, AVGLUM]
+    if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs):
+        return target
+    sys.path.insert(0, os.path.join(HERE, "ref"))
+    import prepass
+    prepass.run_hist(TONEMAP, GENHIST, AVGLUM, os.path.join(OUT, "hist_gen.inc"), os.path.join(OUT, "hist_avg.inc"))
+    cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-mfma", "-ffp-contract=off", "-fsingle-precision-constant",
+           "-fno-fast-math", "-fvisibility=hidden", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + HERE,
+           os.path.join(HERE, "ref", "ref_hist.cpp"), "-o", target]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref histogram build failed:\n" + r.stdout)
+    return target
+
+
 TEMPORAL = "/root/reference/TracerBoy/TemporalAccumulationCS.hlsl"
 
 
@@ -274,6 +304,7 @@ def build_raygen(force=False):
 
 if __name__ == "__main__":
     print(build_temporal(force="--force" in sys.argv))
+    print(build_hist(force="--force" in sys.argv))
     print(build_raygen(force="--force" in sys.argv))
     print(build_boxes(force="--force" in sys.argv))
     print(build_treelet(force="--force" in sys.argv))

@@ -16,7 +16,8 @@
 //       likewise the builder's arithmetic: CalculateMortonCode, GenerateHierarchy (Karras), one treelet optimisation round
 //       (the group shader run by 32 host threads + barrier) and the leaf / parent box constructors -> PINNED;
 //       the light sampling / environment lookup / hash13 / Halton of RayGenCommon.h (ref_raygen.cpp) and the whole main() of
-//       TemporalAccumulationCS.hlsl (ref_temporal.cpp, resources shimmed) -> PINNED;
+//       TemporalAccumulationCS.hlsl (ref_temporal.cpp, resources shimmed) -> PINNED; the auto-exposure group shaders
+//       GenerateHistogramCS.hlsl / CalculateAveragedLuminanceCS.hlsl run by a 256-thread host group (ref_hist.cpp) -> PINNED;
 //  (ii) the builder's resource-bound glue, the traversal loop and the rest of the RayGenCommon/SharedHitGroup/SharedRaytracing glue are
 //       HLSL that cannot be compiled here: restated, checked by the fallback layer's own
 //       validator invariants, analytic known answers and independent numpy restatements

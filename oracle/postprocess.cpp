@@ -10,7 +10,8 @@
 // PIN: oracle/ref/ref_post.cpp compiles Tonemap.h and the Process* functions of PostProcessCS.hlsl from the
 // reference mount as host C++ (oracle/_ref/libref_post.so); tests/test_cpu_postprocess.py requires this
 // restatement to match that build bit for bit on random and rendered inputs -> PINNED against the
-// reference's own text. The two histogram shaders are resource-bound HLSL: restated only (integer work).
+// reference's own text. The two histogram shaders are group shaders with resources: restated here and pinned against
+// their own text run by a 256-thread host group (oracle/ref/ref_hist.cpp, tests/test_cpu_postprocess.py).
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -150,12 +151,20 @@ uint32_t luminance_to_histogram_index(float luminance) {                        
     return (uint32_t)(logLuminance * 254.0f + 1.0f);
 }
 
-void luminance_histogram(const TbFloat4* in, size_t n, uint32_t hist[256]) {                              // :32-55
+// Each 16x16 group builds a groupshared histogram and thread Gid adds bin Gid to the global one at the end -- but the
+// threads outside the image have returned by then (:39), so in a partial group at the right / bottom edge the bins
+// whose thread lies outside the image are never added: a pixel is counted iff thread `bin` of its group exists.
+// (1920x1080: the last row of groups has 8 rows of threads, its bins 128..255 -- luminance above 0.25 -- are dropped.)
+void luminance_histogram(const TbFloat4* in, uint32_t width, uint32_t height, uint32_t hist[256]) {     // :32-55
     memset(hist, 0, 256 * sizeof(uint32_t));
-    for (size_t i = 0; i < n; i++) {
-        f3 Color = xyz(in[i]) / in[i].w;
-        hist[luminance_to_histogram_index(ColorToLuma(Color))]++;
-    }
+    for (uint32_t y = 0; y < height; y++)
+        for (uint32_t x = 0; x < width; x++) {
+            const TbFloat4& p = in[(size_t)y * width + x];
+            f3 Color = xyz(p) / p.w;
+            uint32_t bin = luminance_to_histogram_index(ColorToLuma(Color));
+            bool flushed = (x & ~15u) + (bin & 15u) < width && (y & ~15u) + (bin >> 4) < height;
+            if (flushed) hist[bin]++;
+        }
 }
 
 float averaged_luminance(const uint32_t hist[256], uint32_t pixelCount) {                                 // CalculateAveragedLuminanceCS.hlsl:15-42
@@ -237,7 +246,7 @@ ORACLE_API int oracle_postprocess_image(const TbFloat4* in, const TbFloat4* aux,
     memset(h, 0, sizeof(h));
     float avg = 0.0f;
     if (C->UseAutoExposure) {
-        luminance_histogram(in, n, h);
+        luminance_histogram(in, width, height, h);
         avg = averaged_luminance(h, (uint32_t)n);
     }
     if (hist) memcpy(hist, h, sizeof(h));

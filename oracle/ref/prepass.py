@@ -73,6 +73,33 @@ def run_temporal(tonemap_h, temporal_hlsl, dst):
     open(dst, "w").write(text)
 
 
+def run_hist(tonemap_h, generate_hlsl, average_hlsl, dst_gen, dst_avg):
+    """GenerateHistogramCS.hlsl from the groupshared declaration to the end (LuminanceToHistogramIndex + main()) with
+    Tonemap.h's ColorToLuma in front, and CalculateAveragedLuminanceCS.hlsl from its groupshared declaration to the end.
+    Resource declarations are shims in ref_hist.cpp; the entry points become plain functions."""
+    t = open(tonemap_h).read()
+    a = t.index("float ColorToLuma(float3 color)")
+    luma = t[a:t.index("}", a) + 1]
+    g = open(generate_hlsl).read()
+    body = g[g.index("groupshared uint GroupHistogram[NUM_HISTOGRAM_BINS];"):]
+    for old, new in (("[numthreads(GENERATE_HISTOGRAM_THREAD_GROUP_WIDTH, GENERATE_HISTOGRAM_THREAD_GROUP_HEIGHT, 1)]", ""),
+                     ("void main( uint3 DTid : SV_DispatchThreadID, uint Gid : SV_GroupIndex )", "static void shader_main(uint3 DTid, uint Gid)")):
+        if old not in body:
+            raise SystemExit("prepass: expected text not found: " + old)
+        body = body.replace(old, new)
+    text = luma + "\n" + body
+    text = re.sub(r"\.(xyz|rgb|xy)\b(?!\s*\()", r".\1()", text)
+    open(dst_gen, "w").write(text)
+    c = open(average_hlsl).read()
+    body = c[c.index("groupshared uint AveragedHistogramCount;"):]
+    for old, new in (("[numthreads(CALCULATE_AVERAGED_LUMINANCE_THREAD_GROUP_WIDTH, CALCULATE_AVERAGED_LUMINANCE_THREAD_GROUP_HEIGHT, 1)]", ""),
+                     ("void main(uint Gid : SV_GroupIndex )", "static void shader_main(uint Gid)")):
+        if old not in body:
+            raise SystemExit("prepass: expected text not found: " + old)
+        body = body.replace(old, new)
+    open(dst_avg, "w").write(body)
+
+
 def run_traverse(src, dst_box, dst_rest):
     """The three pure functions of the fallback layer's ray query (TraverseFunction.hlsli): RayBoxTest into one
     file (compiled with contraction on: the pinned slab test is one fma per product), GetRayData and the watertight

@@ -36,6 +36,25 @@ def test_postprocess_image_bit_exact_all_modes(gpu):
         assert np.array_equal(o8, g8), what
 
 
+def test_histogram_edge_groups_match_oracle(gpu):
+    """GenerateHistogramCS.hlsl adds bin Gid from thread Gid after the threads outside the image have returned: partial
+    16x16 groups at the right and bottom edges drop the bins of their missing threads. Sizes with partial groups on
+    either or both edges, against the oracle (itself pinned against the shader text run by a 256-thread host group)."""
+    import tracerboy_b200 as tb
+    from oracle import binding
+    s = tb.PostProcessSettings(1.0, tb.TonemapType.ACES, 1, 1, 1.0)
+    for seed, (h, w) in enumerate([(50, 70), (16, 33), (31, 16), (1, 1), (7, 300), (1080 // 4, 1920 // 4)]):
+        img, _ = _inputs(seed=20 + seed, h=max(h, 5), w=max(w, 8))
+        img = np.ascontiguousarray(img[:h, :w])
+        o, o8, oh, oavg = binding.postprocess_image(img, tb.OutputType.LIT, s)
+        g, g8, gh, gavg = gpu.PostProcessImage(img, tb.OutputType.LIT, s)
+        assert np.array_equal(oh, gh), (h, w)
+        assert np.float32(oavg).view(np.uint32) == np.float32(gavg).view(np.uint32), (h, w)
+        assert _same(o, g) and np.array_equal(o8, g8), (h, w)
+        if h % 16 or w % 16:
+            assert gh.sum() < h * w
+
+
 def test_postprocess_of_a_render_matches_oracle(gpu, cornell):
     """The whole chain on the handle's own buffers: render -> auto exposure -> tonemap, for the output types that have
     a producer on this path (GetOutputSRV, TracerBoy.cpp:2354-2383)."""

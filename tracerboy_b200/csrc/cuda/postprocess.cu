@@ -133,14 +133,22 @@ __device__ __forceinline__ float4 load_px(const void* __restrict__ in, uint32_t 
     return __ldg((const float4*)in + i);
 }
 
-__global__ void __launch_bounds__(256) k_luminance_histogram(const void* __restrict__ in, uint32_t scalar, uint32_t n, uint32_t* __restrict__ hist) {
+// The reference's 16x16 groups add bin Gid of their groupshared histogram from thread Gid, after the threads outside
+// the image have returned (GenerateHistogramCS.hlsl:39, 54): in a partial group at the right / bottom edge the bins
+// whose thread does not exist are never added. A pixel therefore counts iff thread `bin` of its group is inside the
+// image; the blocks here are free to cover the pixels any way they like.
+__global__ void __launch_bounds__(256) k_luminance_histogram(const void* __restrict__ in, uint32_t scalar, uint32_t width, uint32_t height,
+                                                             uint32_t* __restrict__ hist) {
     __shared__ uint32_t sh[256];
     sh[threadIdx.x] = 0;
     __syncthreads();
+    const size_t n = (size_t)width * height;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float4 a = load_px(in, scalar, i);
         f3 c = mk3(a.x, a.y, a.z) / a.w;
-        atomicAdd(&sh[luminance_to_bin(color_to_luma(c))], 1u);
+        const uint32_t bin = luminance_to_bin(color_to_luma(c));
+        const uint32_t x = (uint32_t)(i % width), y = (uint32_t)(i / width);
+        if ((x & ~15u) + (bin & 15u) < width && (y & ~15u) + (bin >> 4) < height) atomicAdd(&sh[bin], 1u);
     }
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
@@ -349,7 +357,7 @@ cudaError_t postprocess(const void* in, bool scalarInput, const float4* aux, uin
     if (blocks > cap) blocks = cap;
     cudaMemsetAsync(hist257, 0, 257 * sizeof(uint32_t), stream);
     if (s.UseAutoExposure) { // the histogram passes run only with auto exposure (TracerBoy.cpp:2948)
-        k_luminance_histogram<<<blocks, 256, 0, stream>>>(in, scalarInput ? 1u : 0u, n, hist257); lc.count++;
+        k_luminance_histogram<<<blocks, 256, 0, stream>>>(in, scalarInput ? 1u : 0u, width, height, hist257); lc.count++;
     }
     k_postprocess<<<blocks, 256, 0, stream>>>(in, scalarInput ? 1u : 0u, aux, width, height, outputType, s, hist257, out, out8); lc.count++;
     return cudaGetLastError();
