@@ -127,6 +127,7 @@ def build_temporal(force=False):
 
 
 TRAVERSE = "/root/reference/D3D12RaytracingFallback/src/TraverseFunction.hlsli"
+HELPER = "/root/reference/D3D12RaytracingFallback/src/RayTracingHelper.hlsli"  # also used by build_boxes
 
 
 def traverse_lib_path():
@@ -140,23 +141,25 @@ def build_traverse(force=False):
     if not os.path.exists(TRAVERSE):
         return target if os.path.exists(target) else None
     os.makedirs(OUT, exist_ok=True)
-    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_traverse_box.cpp", "ref_traverse_rest.cpp")] + [TRAVERSE]
+    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_traverse_box.cpp", "ref_traverse_rest.cpp",
+                                                     "ref_traverse_loop.cpp")] + [TRAVERSE, HELPER]
     if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs):
         return target
     sys.path.insert(0, os.path.join(HERE, "ref"))
     import prepass
     prepass.run_traverse(TRAVERSE, os.path.join(OUT, "traverse_box_gen.inc"), os.path.join(OUT, "traverse_rest_gen.inc"))
+    prepass.run_traverse_loop(HELPER, TRAVERSE, os.path.join(OUT, "traverse_loop_gen.inc"))
     common = [GXX, "-O2", "-std=c++17", "-fPIC", "-mfma", "-fsingle-precision-constant", "-fno-fast-math", "-fvisibility=hidden", "-w",
               "-I" + os.path.join(ROOT, "include"), "-I" + HERE, "-c"]
     objs = []
-    for name, contract in (("ref_traverse_box", "fast"), ("ref_traverse_rest", "off")):
+    for name, contract in (("ref_traverse_box", "fast"), ("ref_traverse_rest", "off"), ("ref_traverse_loop", "off")):
         obj = os.path.join(OUT, name + ".o")
-        r = subprocess.run(common + ["-ffp-contract=" + contract, os.path.join(HERE, "ref", name + ".cpp"), "-o", obj],
+        r = subprocess.run(common + ["-fopenmp", "-ffp-contract=" + contract, os.path.join(HERE, "ref", name + ".cpp"), "-o", obj],
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError("oracle/_ref traversal build failed:\n" + r.stdout)
         objs.append(obj)
-    r = subprocess.run([GXX, "-shared", "-o", target] + objs, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    r = subprocess.run([GXX, "-shared", "-fopenmp", "-o", target] + objs, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("oracle/_ref traversal link failed:\n" + r.stdout)
     return target

@@ -18,7 +18,9 @@
 //       the light sampling / environment lookup / hash13 / Halton of RayGenCommon.h (ref_raygen.cpp) and the whole main() of
 //       TemporalAccumulationCS.hlsl (ref_temporal.cpp, resources shimmed) -> PINNED; the auto-exposure group shaders
 //       GenerateHistogramCS.hlsl / CalculateAveragedLuminanceCS.hlsl run by a 256-thread host group (ref_hist.cpp) -> PINNED;
-//  (ii) the builder's resource-bound glue, the traversal loop and the rest of the RayGenCommon/SharedHitGroup/SharedRaytracing glue are
+//       the ray query LOOP itself (Traverse, SoftwareRayQuery, TestLeafNodeIntersections, the node / primitive readers:
+//       ref_traverse_loop.cpp) on the oracle's own BVH bytes: every field of every hit record incl. both counters -> PINNED;
+//  (ii) the builder's resource-bound glue and the rest of the RayGenCommon/SharedHitGroup/SharedRaytracing glue are
 //       HLSL that cannot be compiled here: restated, checked by the fallback layer's own
 //       validator invariants, analytic known answers and independent numpy restatements
 //       -> "parity unpinned" by reference outputs for these parts.

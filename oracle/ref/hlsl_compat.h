@@ -40,6 +40,7 @@ struct float3 {
     float3 rgb() const { return *this; }
     float3 yzx() const { return float3(y, z, x); }
 #ifdef RC_TRAVERSE
+    float3(float x_, float2 yz) : x(x_), y(yz.x), z(yz.y) {}          // float3(a.w, b.xy) (RayTracingHelper.hlsli:223)
     void set_xy(float2 v) { x = v.x; y = v.y; }                      // `A.xy = ...` (TraverseFunction.hlsli:257-259)
     float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); } // `v[swizzleOrder.x]` (:225)
 #endif

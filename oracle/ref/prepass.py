@@ -120,6 +120,41 @@ def run_traverse(src, dst_box, dst_rest):
     open(dst_rest, "w").write(fix(t[d:e] + t[f:g] + t[b:c]))
 
 
+def run_traverse_loop(helper_hlsli, traverse_hlsli, dst):
+    """The fallback layer's ray query LOOP: from RayTracingHelper.hlsli the node / primitive readers (IsLeafFlag ...
+    BVHReadTriangle), from TraverseFunction.hlsli everything except the three pure functions that are compiled on their
+    own (RayBoxTest, RayTriangleIntersect with Swizzle / IsPositive, GetRayData with its helpers): SoftwareRayDesc /
+    SoftwareHitData / SoftwareRayQuery, the stack helpers, IsOpaque, TestLeafNodeIntersections, struct RayData, Cull,
+    the flag helpers, Traverse and SoftwareRayQuery::Proceed. The #if FAST_PATH / DISABLE_ANYHIT /
+    DISABLE_PROCEDURAL_GEOMETRY switches stay in the text and are set by ref_traverse_loop.cpp the way RayGenCommon.h:355-362
+    sets them."""
+    h = open(helper_hlsli).read()
+    helper = h[h.index("static const int IsLeafFlag = 0x80000000;"):h.index("BoundingBox AABBtoBoundingBox(AABB aabb)")]
+    t = open(traverse_hlsli).read()
+    box = t.index("inline\nbool RayBoxTest(")
+    leaves = t.index("#define MULTIPLE_LEAVES_PER_NODE")
+    biggest = t.index("int GetIndexOfBiggestChannel(float3 vec)")
+    levels = t.index("#define TOP_LEVEL_INDEX")
+    raydata = t.index("struct RayData")
+    getraydata = t.index("RayData GetRayData(float3 rayOrigin, float3 rayDirection)")
+    cull = t.index("bool Cull(bool opaque, uint rayFlags)")
+    head = t[t.index("#define INSTANCE_FLAG_NONE"):box]
+    # strip the comment banner that introduces RayBoxTest from the tail of `head` (plain text, harmless) -- kept as is
+    text = helper + "\n" + head + "\n" + t[leaves:biggest] + "\n" + t[levels:raydata] + "\n" + t[raydata:getraydata] + \
+        "\nRayData GetRayData(float3 rayOrigin, float3 rayDirection);\n" + t[cull:]
+    for old, new in (("const GpuVA nullptr = GpuVA(0, 0);", "const GpuVA nullptr_va = GpuVA(0, 0);"),
+                     ("Traverse(this);", "Traverse(*this);"),
+                     ("uint stackPointer = 0;", "int stackPointer = 0;"),
+                     ("Declare_Fallback_SetPendingAttr(BuiltInTriangleIntersectionAttributes);", "")):
+        if old not in text:
+            raise SystemExit("prepass: expected text not found: " + old)
+        text = text.replace(old, new)
+    text = re.sub(r"\b(?:inout|out)\s+([A-Za-z_]\w*)\s+([A-Za-z_]\w*)", r"\1& \2", text)
+    text = re.sub(r"\bin\s+([A-Za-z_]\w*)\s+([A-Za-z_]\w*)", r"\1 \2", text)
+    text = re.sub(r"\.(xyz|rgb|xy|zw)\b(?!\s*\()", r".\1()", text)
+    open(dst, "w").write(text)
+
+
 def run_morton(src, dst):
     """GetMortonCodesFromUnitCoord(float3) + CalculateMortonCode(float3): from `#define BIT(x)` to the entry point."""
     t = open(src).read()

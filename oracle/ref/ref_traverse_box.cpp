@@ -6,6 +6,10 @@
 
 namespace refcore {
 #include "../_ref/traverse_box_gen.inc"
+// out-of-line entry for ref_traverse_loop.cpp (the shader's function is `inline` and leaves no symbol of its own)
+bool RayBoxTest_fused(float& resultT, float closestT, float3 rayOriginTimesRayInverseDirection, float3 rayInverseDirection, float3 boxCenter, float3 boxHalfDim) {
+    return RayBoxTest(resultT, closestT, rayOriginTimesRayInverseDirection, rayInverseDirection, boxCenter, boxHalfDim);
+}
 } // namespace refcore
 
 extern "C" __attribute__((visibility("default")))

@@ -18,6 +18,12 @@ static const uint D3D12_RAYTRACING_INSTANCE_FLAG_TRIANGLE_FRONT_COUNTERCLOCKWISE
 
 #include "../_ref/traverse_rest_gen.inc"
 
+// out-of-line entry for ref_traverse_loop.cpp (the shader's function is `inline` and leaves no symbol of its own)
+void RayTriangleIntersect_precise(float& hitT, uint rayFlags, uint instanceFlags, float2& bary, float3 rayOrigin, float3 rayDirection,
+                                  int3 swizzledIndicies, float3 shear, float3 v0, float3 v1, float3 v2) {
+    RayTriangleIntersect(hitT, rayFlags, instanceFlags, bary, rayOrigin, rayDirection, swizzledIndicies, shear, v0, v1, v2);
+}
+
 } // namespace refcore
 
 extern "C" __attribute__((visibility("default")))

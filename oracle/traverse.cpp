@@ -6,6 +6,11 @@
 // the watertight triangle test is evaluated unfused (`precise`); the traversal stack is
 // unbounded (reference: 16 entries, unchecked); on exactly equal t the hit with the lower
 // (geometryIndex, primitiveIndex) wins (reference: first found).
+//
+// Pinned against the reference's own text: the three pure functions (RayBoxTest, GetRayData, RayTriangleIntersect) and
+// the whole loop (Traverse / SoftwareRayQuery / TestLeafNodeIntersections) are compiled from the mount
+// (oracle/ref/ref_traverse_*.cpp -> oracle/_ref/libref_traverse.so) and tests/test_cpu_oracle.py requires this file, in
+// its literal mode, to produce bit-identical hit records and counters on the oracle's own BVH bytes.
 #include <cfloat>
 #include <cstring>
 #include <vector>

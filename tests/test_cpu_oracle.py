@@ -704,3 +704,81 @@ def test_raygen_glue_equals_reference_text(built):
         lib.oracle_math_eval(8, idx.ctypes.data, bases.ctypes.data, got.ctypes.data, 3000)
         want = np.array([ref.ref_halton(base, int(i)) for i in idx], np.float32)
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("spec", ["cornell", "teapot", "synthetic:blobs?copies=27&tris=300&seed=3", "synthetic:showcase?tris=300&seed=2"])
+def test_traversal_loop_equals_reference_text(spec, tmp_path, built):
+    """The ray query LOOP — stack discipline, near child first with left on equal t, leaf acceptance, the
+    BoxesTested / TrianglesTested counters — against the reference's own Traverse / SoftwareRayQuery / TestLeafNode-
+    Intersections text (TraverseFunction.hlsli) compiled from the mount with FAST_PATH, DISABLE_ANYHIT and
+    DISABLE_PROCEDURAL_GEOMETRY (oracle/_ref/libref_traverse.so: ref_trace_rays) and run on the oracle's reference-layout
+    BVH bytes. Every field of every hit record must be bit-identical: t, barycentrics, primitive / geometry / instance
+    index and both counters. The oracle runs in its literal mode here (deviations D6 / D7 off: a zero direction
+    component is rcp(0) = inf, a NaN ray walks the tree), so that rays with exactly-zero components, NaN rays, rays
+    along box faces and rays starting inside the geometry are part of the comparison; the only tolerated difference is
+    deviation D3 (on exactly equal t the oracle prefers the lower id, the reference the first triangle met)."""
+    import ctypes as C
+    import tracerboy_b200 as tb
+    from tracerboy_b200.api import HIT_DTYPE, RAY_DTYPE
+    from oracle import binding
+    path = binding.ref_traverse_lib_path()
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_traverse.so not built (needs the reference mount at build time)")
+    ref = C.CDLL(path)
+    if not hasattr(ref, "ref_trace_rays"):
+        pytest.skip("oracle/_ref/libref_traverse.so predates the loop build")
+    ref.ref_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    ref.ref_trace_rays.restype = C.c_int
+    if spec in NAMED:
+        scene = scene_path(NAMED[spec])
+        if scene is None:
+            pytest.skip("scene cache missing")
+    else:
+        scene = str(tmp_path / "s.tbscene")
+        tb.convert_scene(spec, scene)
+    rng = np.random.default_rng(5)
+    try:
+        binding.set_literal_rcp(True)
+        o = binding.Oracle(); o.LoadScene(scene, 3)
+        bvh = np.ascontiguousarray(o.GetBVH())
+        cam = o.GetCamera()
+        eye = np.array([cam.Position.x, cam.Position.y, cam.Position.z], np.float32)
+        look = np.array([cam.LookAt.x, cam.LookAt.y, cam.LookAt.z], np.float32)
+        n = 60000
+        rays = np.zeros(n, RAY_DTYPE)
+        rays["Origin"] = eye + rng.normal(0, 0.05, (n, 3)).astype(np.float32)
+        d = look - eye + rng.normal(0, 0.3, (n, 3)).astype(np.float32)
+        rays["Direction"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+        rays["TMin"] = 0.001; rays["TMax"] = 999999.0
+        k = n // 3                                   # incoherent rays from points around the look-at target
+        rays["Origin"][:k] = look + rng.normal(0, 0.5, (k, 3)).astype(np.float32)
+        rays["Direction"][:k] = rng.normal(0, 1, (k, 3)).astype(np.float32)
+        z = slice(k, k + 3000)                       # exactly-zero direction components (one or two axes)
+        zero = rng.integers(1, 7, 3000)
+        dz = rays["Direction"][z]
+        for a in range(3):
+            dz[(zero >> a) & 1 == 1, a] = 0.0
+        dz[(dz == 0).all(1)] = [0, 1, 0]
+        rays["Direction"][z] = dz
+        rays["Direction"][k + 3000:k + 3050] = np.nan  # NaN rays
+        rays["Origin"][k + 3050:k + 3060, 0] = np.nan
+        rays["TMax"][k + 3100:k + 3600] = rng.uniform(0.5, 20, 500).astype(np.float32)   # short rays
+        rays["TMin"][k + 3600:k + 3800] = rng.uniform(0.5, 5, 200).astype(np.float32)    # late starts
+        ho = o.TraceRays(rays)
+    finally:
+        binding.set_literal_rcp(False)
+    hr = np.zeros(n, HIT_DTYPE)
+    assert ref.ref_trace_rays(bvh.ctypes.data_as(C.c_void_p), rays.ctypes.data_as(C.c_void_p), n, hr.ctypes.data_as(C.c_void_p)) == 0
+    assert (ho["t"] > 0).sum() > n // 10
+    bad = np.zeros(n, bool)
+    for f in HIT_DTYPE.names:
+        a, b = ho[f].view(np.uint32), hr[f].view(np.uint32)
+        bad |= a != b
+    # D3: identical t, barycentrics may differ with the triangle
+    tie = bad & (ho["t"].view(np.uint32) == hr["t"].view(np.uint32)) & (ho["t"] > 0) & \
+        ((ho["PrimitiveIndex"] != hr["PrimitiveIndex"]) | (ho["GeometryIndex"] != hr["GeometryIndex"]))
+    assert (bad & ~tie).sum() == 0, "%d rays differ, first %s: oracle %s reference %s" % (
+        (bad & ~tie).sum(), np.flatnonzero(bad & ~tie)[:5], ho[np.flatnonzero(bad & ~tie)[:3]], hr[np.flatnonzero(bad & ~tie)[:3]])
+    assert tie.sum() <= n // 1000
+    # the counters of the tie rays still agree
+    assert np.array_equal(ho["BoxesTested"][tie], hr["BoxesTested"][tie]) and np.array_equal(ho["TrianglesTested"][tie], hr["TrianglesTested"][tie])
