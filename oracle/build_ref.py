@@ -149,6 +149,8 @@ def build_traverse(force=False):
     import prepass
     prepass.run_traverse(TRAVERSE, os.path.join(OUT, "traverse_box_gen.inc"), os.path.join(OUT, "traverse_rest_gen.inc"))
     prepass.run_traverse_loop(HELPER, TRAVERSE, os.path.join(OUT, "traverse_loop_gen.inc"))
+    prepass.run_intersect("/root/reference/TracerBoy/SharedShaderStructs.h", "/root/reference/TracerBoy/SharedHitGroup.h",
+                          "/root/reference/TracerBoy/RayGenCommon.h", os.path.join(OUT, "intersect_gen.inc"))
     common = [GXX, "-O2", "-std=c++17", "-fPIC", "-mfma", "-fsingle-precision-constant", "-fno-fast-math", "-fvisibility=hidden", "-w",
               "-I" + os.path.join(ROOT, "include"), "-I" + HERE, "-c"]
     objs = []

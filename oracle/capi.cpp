@@ -164,6 +164,28 @@ ORACLE_API void oracle_env(const float* rgba, uint32_t w, uint32_t h, const floa
     tbm::f3 c = sample_environment_map(sc, tbm::mk3(v[0], v[1], v[2]));
     out3[0] = c.x; out3[1] = c.y; out3[2] = c.z;
 }
+// test hooks for the pin of IntersectWithMaxDistance + the SharedHitGroup.h geometry fetch (tests/test_cpu_oracle.py)
+ORACLE_API int oracle_scene_arrays(OracleHandle* h, const void** geoms, uint32_t* numGeoms, const void** indices, const void** vertices) {
+    *geoms = h->scene.geoms.data(); *numGeoms = (uint32_t)h->scene.geoms.size();
+    *indices = h->scene.indices.data(); *vertices = h->scene.vertices.data();
+    return 0;
+}
+// out: 12 floats per ray = t, material, normal.xyz, tangent.xyz, uv.xy, TrianglesTested, BoxesTested
+ORACLE_API int oracle_intersect(OracleHandle* h, const TbRay* rays, uint64_t n, float* out12) {
+    RenderParams rp;
+    memset(&rp.settings, 0, sizeof(rp.settings));
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        Ctx c(h->scene, rp);
+        c.firstIntersect = false; c.rays = c.tris = c.boxes = 0;
+        Ray ray{tbm::mk3(rays[i].Origin[0], rays[i].Origin[1], rays[i].Origin[2]), tbm::mk3(rays[i].Direction[0], rays[i].Direction[1], rays[i].Direction[2])};
+        HitResult r = intersect(c, ray, rays[i].TMax);
+        float* o = out12 + 12 * i;
+        o[0] = r.t; o[1] = (float)r.material; o[2] = r.normal.x; o[3] = r.normal.y; o[4] = r.normal.z;
+        o[5] = r.tangent.x; o[6] = r.tangent.y; o[7] = r.tangent.z; o[8] = r.uv.x; o[9] = r.uv.y; o[10] = (float)c.tris; o[11] = (float)c.boxes;
+    }
+    return 0;
+}
 ORACLE_API uint32_t oracle_morton(const float* centroid, const float* smin, const float* smax) {
     return oracle::morton_public(centroid, smin, smax);
 }

@@ -20,6 +20,7 @@
 //       GenerateHistogramCS.hlsl / CalculateAveragedLuminanceCS.hlsl run by a 256-thread host group (ref_hist.cpp) -> PINNED;
 //       the ray query LOOP itself (Traverse, SoftwareRayQuery, TestLeafNodeIntersections, the node / primitive readers:
 //       ref_traverse_loop.cpp) on the oracle's own BVH bytes: every field of every hit record incl. both counters -> PINNED;
+//       IntersectWithMaxDistance + the SharedHitGroup.h geometry fetch (same file): t, material, normal, tangent, uv -> PINNED;
 //  (ii) the builder's resource-bound glue and the rest of the RayGenCommon/SharedHitGroup/SharedRaytracing glue are
 //       HLSL that cannot be compiled here: restated, checked by the fallback layer's own
 //       validator invariants, analytic known answers and independent numpy restatements

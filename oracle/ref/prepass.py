@@ -155,6 +155,31 @@ def run_traverse_loop(helper_hlsli, traverse_hlsli, dst):
     open(dst, "w").write(text)
 
 
+def run_intersect(structs_h, hitgroup_h, raygen_h, dst):
+    """What sits between the ray query and the path tracer: struct RayPayload (SharedShaderStructs.h), the geometry
+    fetch of SharedHitGroup.h (HitGroupShaderRecord ... GetHitInfo: shader record -> indices -> three vertices ->
+    interpolated, normalised normal / tangent and uv) and IntersectWithMaxDistance of RayGenCommon.h (the text keeps its
+    #if USE_INLINE_RAYTRACING / USE_SW_RAYTRACING branches; ref_traverse_loop.cpp selects the software one). Only the
+    three resource declarations lose their register bindings."""
+    sh = open(structs_h).read()
+    a = sh.index("struct RayPayload")
+    payload = sh[a:sh.index("};", a) + 2]
+    hg = open(hitgroup_h).read()
+    geo = hg[hg.index("#define VertexStride 8"):hg.index("Material GetMaterial_NonRecursive(int MaterialID);")]
+    for old, new in (("StructuredBuffer<HitGroupShaderRecord> ShaderTable: register(t11);", "static thread_local StructuredBuffer<HitGroupShaderRecord> ShaderTable;"),
+                     ("Buffer<uint> IndexBuffers[] : register(t0, space2);", "static thread_local Buffer<uint> IndexBuffers[1];"),
+                     ("Buffer<float> VertexBuffers[] : register(t0, space3);", "static thread_local Buffer<float> VertexBuffers[1];")):
+        if old not in geo:
+            raise SystemExit("prepass: expected resource declaration not found: " + old)
+        geo = geo.replace(old, new)
+    rg = open(raygen_h).read()
+    isect = rg[rg.index("#define MIN_T 0.001f"):rg.index("float2 IntersectAnything(")]
+    text = payload + "\n" + geo + "\n" + isect
+    text = re.sub(r"\b(?:inout|out)\s+([A-Za-z_]\w*)\s+([A-Za-z_]\w*)", r"\1& \2", text)
+    text = re.sub(r"\.(xyz|rgb|xy)\b(?!\s*\()", r".\1()", text)
+    open(dst, "w").write(text)
+
+
 def run_morton(src, dst):
     """GetMortonCodesFromUnitCoord(float3) + CalculateMortonCode(float3): from `#define BIT(x)` to the entry point."""
     t = open(src).read()

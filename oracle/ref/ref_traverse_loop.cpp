@@ -16,13 +16,14 @@
 #include "hlsl_compat.h"
 #include <cfloat>
 #include <cstring>
+#include <vector>
 #include "tracerboy_b200.h"
 
 namespace refcore {
 
 struct int3 { int x, y, z; int3() : x(0), y(0), z(0) {} int3(int a, int b, int c) : x(a), y(b), z(c) {} };
 struct uint2 { uint x, y; uint2() : x(0), y(0) {} uint2(uint a, uint b) : x(a), y(b) {} };
-struct uint3 { uint x, y, z; };
+struct uint3 { uint x, y, z; uint3() : x(0), y(0), z(0) {} uint3(uint a, uint b, uint c) : x(a), y(b), z(c) {} };
 struct uint4 { uint x, y, z, w; };
 struct int4 { int x, y, z, w; int4() : x(0), y(0), z(0), w(0) {} int4(const uint4& u) : x((int)u.x), y((int)u.y), z((int)u.z), w((int)u.w) {} };
 struct float4e : float4 { // float4 with the two extra swizzles BVHReadTriangle uses
@@ -94,6 +95,22 @@ inline float3 float3_from(float a, float2 b) { return float3(a, b.x, b.y); }
 
 #include "../_ref/traverse_loop_gen.inc"
 
+// ---- between the query and the path tracer: SharedHitGroup.h geometry fetch + RayGenCommon.h IntersectWithMaxDistance
+// (prepass.run_intersect -> oracle/_ref/intersect_gen.inc). Shims: StructuredBuffer / Buffer element access, the
+// built-in RayDesc (same members as SoftwareRayDesc), kernel.glsl's Ray, OutputRayStats (RayGenCommon.h:537-543 writes
+// the heat map AOV; here it records the two counters).
+template <typename T> struct StructuredBuffer { const T* p = nullptr; const T& operator[](uint i) const { return p[i]; } };
+template <typename T> struct Buffer { const T* p = nullptr; T operator[](uint i) const { return p[i]; } };
+inline uint NonUniformResourceIndex(uint i) { return i; }
+typedef SoftwareRayDesc RayDesc;
+struct Ray { float3 origin; float3 direction; };
+static thread_local uint g_statTris, g_statBoxes;
+inline void OutputRayStats(uint TrianglesTested, uint BoxesTested) { g_statTris = TrianglesTested; g_statBoxes = BoxesTested; }
+#define USE_INLINE_RAYTRACING 1
+#define USE_SW_RAYTRACING 1
+#undef float4
+#include "../_ref/intersect_gen.inc"
+
 } // namespace refcore
 
 // Same result record as tb_trace_rays / oracle_trace_rays (TbHit), on a reference-layout BVH (tb_get_bvh bytes).
@@ -120,6 +137,40 @@ int ref_trace_rays(const uint8_t* bvh, const TbRay* rays, uint64_t n, TbHit* hit
             h.t = -1.0f; h.PrimitiveIndex = h.GeometryIndex = 0xffffffffu;
         }
         h.TrianglesTested = q.TrianglesTested; h.BoxesTested = q.BoxesTested;
+    }
+    return 0;
+}
+
+// IntersectWithMaxDistance on caller-provided scene arrays: geoms become the 72-byte hit-group shader records the way
+// TracerBoy.cpp:1896-1944 fills them (one pooled vertex buffer of 8-float vertices, one pooled index buffer; offsets in
+// bytes). out: 12 floats per ray = t, material, normal.xyz, tangent.xyz, uv.xy, TrianglesTested, BoxesTested.
+extern "C" __attribute__((visibility("default")))
+int ref_intersect(const uint8_t* bvh, const TbGeometryRecord* geoms, uint32_t numGeoms, const uint32_t* indices, const TbVertex* vertices,
+                  const TbRay* rays, uint64_t n, float* out12) {
+    using namespace refcore;
+    std::vector<HitGroupShaderRecord> table(numGeoms);
+    for (uint32_t g = 0; g < numGeoms; g++) {
+        memset(&table[g], 0, sizeof(HitGroupShaderRecord));
+        table[g].MaterialIndex = geoms[g].MaterialIndex;
+        table[g].VertexBufferIndex = 0; table[g].VertexBufferOffset = geoms[g].VertexFirst * 8u * 4u;
+        table[g].IndexBufferIndex = 0; table[g].IndexBufferOffset = geoms[g].IndexFirst * 4u;
+        table[g].GeometryIndex = geoms[g].GeometryIndex;
+    }
+    static_assert(sizeof(HitGroupShaderRecord) == 72, "HitGroupShaderRecord is 72 bytes (SharedHitGroup.h:13-23)");
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        g_bvh.bytes = const_cast<uint8_t*>(bvh);
+        GI = 0;
+        ShaderTable.p = table.data(); IndexBuffers[0].p = indices; VertexBuffers[0].p = (const float*)vertices;
+        Ray ray;
+        ray.origin = float3(rays[i].Origin[0], rays[i].Origin[1], rays[i].Origin[2]);
+        ray.direction = float3(rays[i].Direction[0], rays[i].Direction[1], rays[i].Direction[2]);
+        float3 normal, tangent; float2 uv; uint primitiveID = 123;
+        float2 r = IntersectWithMaxDistance(ray, rays[i].TMax, normal, tangent, uv, primitiveID);
+        float* o = out12 + 12 * i;
+        o[0] = r.x; o[1] = r.y; o[2] = normal.x; o[3] = normal.y; o[4] = normal.z; o[5] = tangent.x; o[6] = tangent.y; o[7] = tangent.z;
+        o[8] = uv.x; o[9] = uv.y; o[10] = (float)g_statTris; o[11] = (float)g_statBoxes;
+        if (primitiveID != 0) o[0] = -12345.0f; // PrimitiveID = 0 always (RayGenCommon.h:405)
     }
     return 0;
 }

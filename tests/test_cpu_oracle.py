@@ -782,3 +782,70 @@ def test_traversal_loop_equals_reference_text(spec, tmp_path, built):
     assert tie.sum() <= n // 1000
     # the counters of the tie rays still agree
     assert np.array_equal(ho["BoxesTested"][tie], hr["BoxesTested"][tie]) and np.array_equal(ho["TrianglesTested"][tie], hr["TrianglesTested"][tie])
+
+
+@pytest.mark.parametrize("spec", ["cornell", "teapot", "synthetic:showcase?tris=300&seed=2"])
+def test_intersect_and_geometry_fetch_equal_reference_text(spec, tmp_path, built):
+    """What sits between the ray query and the path tracer — IntersectWithMaxDistance (RayGenCommon.h:365-414, software
+    branch) and the geometry fetch of SharedHitGroup.h (GetGeometryInfo, GetIndices, GetUV, GetNormal, GetTangent,
+    GetBarycentrics3, GetHitInfo): hit-group record -> indices -> three 8-float vertices -> interpolated, normalised
+    normal and tangent, uv, material index — compiled from the mount on top of the compiled ray query
+    (oracle/_ref/libref_traverse.so: ref_intersect), against the oracle's intersect(). t, material, normal, tangent, uv
+    and the two counters passed to OutputRayStats must be bit-identical (NaN == NaN: a zero-length interpolated tangent
+    normalises to NaN on both sides). Literal mode as in the loop test; D3 ties are compared on t and counters only."""
+    import ctypes as C
+    import tracerboy_b200 as tb
+    from tracerboy_b200.api import RAY_DTYPE
+    from oracle import binding
+    path = binding.ref_traverse_lib_path()
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_traverse.so not built (needs the reference mount at build time)")
+    ref = C.CDLL(path)
+    if not hasattr(ref, "ref_intersect"):
+        pytest.skip("oracle/_ref/libref_traverse.so predates the intersect build")
+    ref.ref_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    ref.ref_intersect.restype = C.c_int
+    lib = binding.load()
+    lib.oracle_scene_arrays.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.oracle_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    if spec in NAMED:
+        scene = scene_path(NAMED[spec])
+        if scene is None:
+            pytest.skip("scene cache missing")
+    else:
+        scene = str(tmp_path / "s.tbscene")
+        tb.convert_scene(spec, scene)
+    rng = np.random.default_rng(9)
+    try:
+        binding.set_literal_rcp(True)
+        o = binding.Oracle(); o.LoadScene(scene, 3)
+        bvh = np.ascontiguousarray(o.GetBVH())
+        cam = o.GetCamera()
+        eye = np.array([cam.Position.x, cam.Position.y, cam.Position.z], np.float32)
+        look = np.array([cam.LookAt.x, cam.LookAt.y, cam.LookAt.z], np.float32)
+        n = 40000
+        rays = np.zeros(n, RAY_DTYPE)
+        rays["Origin"] = eye + rng.normal(0, 0.05, (n, 3)).astype(np.float32)
+        d = look - eye + rng.normal(0, 0.3, (n, 3)).astype(np.float32)
+        rays["Direction"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+        rays["TMax"] = 999999.0
+        k = n // 2
+        rays["Origin"][:k] = look + rng.normal(0, 0.5, (k, 3)).astype(np.float32)
+        rays["Direction"][:k] = rng.normal(0, 1, (k, 3)).astype(np.float32)
+        rays["TMax"][k:k + 500] = rng.uniform(0.5, 20, 500).astype(np.float32)   # the shadow-ray form: a finite maxT
+        a = np.zeros((n, 12), np.float32)
+        assert lib.oracle_intersect(o.h, rays.ctypes.data_as(C.c_void_p), n, a.ctypes.data_as(C.c_void_p)) == 0
+        geoms, ng, idx, vtx = C.c_void_p(), C.c_uint32(), C.c_void_p(), C.c_void_p()
+        lib.oracle_scene_arrays(o.h, C.byref(geoms), C.byref(ng), C.byref(idx), C.byref(vtx))
+        b = np.zeros((n, 12), np.float32)
+        assert ref.ref_intersect(bvh.ctypes.data_as(C.c_void_p), geoms, ng.value, idx, vtx, rays.ctypes.data_as(C.c_void_p), n,
+                                 b.ctypes.data_as(C.c_void_p)) == 0
+    finally:
+        binding.set_literal_rcp(False)
+    assert (a[:, 0] > 0).sum() > n // 10 and len(np.unique(a[a[:, 0] > 0, 1])) >= 2   # more than one material was hit
+    same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+    bad = ~same.all(1)
+    tie = bad & same[:, 0] & same[:, 10] & same[:, 11] & (a[:, 0] > 0)   # D3: same t and counters, another triangle
+    assert (bad & ~tie).sum() == 0, "%d rays differ, first: oracle %s reference %s" % (
+        (bad & ~tie).sum(), a[np.flatnonzero(bad & ~tie)[:2]], b[np.flatnonzero(bad & ~tie)[:2]])
+    assert tie.sum() <= n // 1000
