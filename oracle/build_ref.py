@@ -298,6 +298,7 @@ def build_raygen(force=False):
     sys.path.insert(0, os.path.join(HERE, "ref"))
     import prepass
     prepass.run_raygen(STRUCTS, RAYGEN, os.path.join(OUT, "raygen_light_gen.inc"), os.path.join(OUT, "raygen_gen.inc"))
+    prepass.run_material(STRUCTS, TONEMAP, "/root/reference/TracerBoy/SharedRaytracing.h", RAYGEN, os.path.join(OUT, "raygen_material_gen.inc"))
     cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma", "-ffp-contract=off", "-fsingle-precision-constant", "-fno-fast-math",
            "-fvisibility=hidden", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + HERE, os.path.join(HERE, "ref", "ref_raygen.cpp"),
            "-o", target, "-L" + HERE, "-loracle", "-Wl,-rpath,$ORIGIN/.."]

@@ -186,6 +186,44 @@ ORACLE_API int oracle_intersect(OracleHandle* h, const TbRay* rays, uint64_t n, 
     }
     return 0;
 }
+// test hooks for the pin of the material / texture fetch (GetMaterialInternal, GetDetailNormal, GetTextureData)
+ORACLE_API const void* oracle_scene_ptr(OracleHandle* h) { return &h->scene; }
+ORACLE_API uint32_t oracle_num_materials(OracleHandle* h) { return (uint32_t)h->scene.materials.size(); }
+ORACLE_API uint32_t oracle_num_textures(OracleHandle* h) { return (uint32_t)h->scene.textures.size(); }
+static void pack_material(const Material& m, void* out21) {
+    TbMaterial t;
+    memset(&t, 0, sizeof(t));
+    t.albedo = {m.albedo.x, m.albedo.y, m.albedo.z}; t.albedoIndex = m.albedoIndex; t.alphaIndex = m.alphaIndex;
+    t.normalMapIndex = m.normalMapIndex; t.emissiveIndex = m.emissiveIndex; t.specularMapIndex = m.specularMapIndex;
+    t.IOR = m.IOR; t.absorption = {m.absorption.x, m.absorption.y, m.absorption.z}; t.roughness = m.roughness;
+    t.scattering = {m.scattering.x, m.scattering.y, m.scattering.z}; t.emissive = {m.emissive.x, m.emissive.y, m.emissive.z};
+    t.Flags = m.Flags; t.SpecularCoef = m.SpecularCoef;
+    memcpy(out21, &t, sizeof(t));
+}
+ORACLE_API void oracle_material(OracleHandle* h, float time, int materialId, const float* uv, int backside, float* seed, void* out21) {
+    RenderParams rp;
+    memset(&rp.settings, 0, sizeof(rp.settings));
+    rp.time = time;
+    Ctx c(h->scene, rp);
+    c.seed = *seed;
+    Material m = get_material_internal(c, materialId, tbm::mk2(uv[0], uv[1]), backside != 0);
+    *seed = c.seed;
+    pack_material(m, out21);
+}
+ORACLE_API void oracle_detail_normal(OracleHandle* h, uint32_t enableNormalMaps, int materialId, const float* normal, const float* tangent,
+                                     const float* uv, float* out3) {
+    RenderParams rp;
+    memset(&rp.settings, 0, sizeof(rp.settings));
+    rp.settings.EnableNormalMaps = enableNormalMaps;
+    Ctx c(h->scene, rp);
+    tbm::f3 n = get_detail_normal(c, load_material(h->scene.materials[materialId]), tbm::mk3(normal[0], normal[1], normal[2]),
+                                  tbm::mk3(tangent[0], tangent[1], tangent[2]), tbm::mk2(uv[0], uv[1]));
+    out3[0] = n.x; out3[1] = n.y; out3[2] = n.z;
+}
+ORACLE_API void oracle_texture(OracleHandle* h, uint32_t textureIndex, const float* uv, float* out4) {
+    tbm::f4 t = get_texture_data(h->scene, textureIndex, tbm::mk2(uv[0], uv[1]));
+    out4[0] = t.x; out4[1] = t.y; out4[2] = t.z; out4[3] = t.w;
+}
 ORACLE_API uint32_t oracle_morton(const float* centroid, const float* smin, const float* smax) {
     return oracle::morton_public(centroid, smin, smax);
 }

@@ -64,6 +64,7 @@ Material get_material_internal(Ctx& c, int id, f2 uv, bool backside);   // :298-
 f3 get_detail_normal(Ctx& c, const Material& mat, f3 normal, f3 tangent, f2 uv); // :273-295
 void get_one_light_sample(Ctx& c, f3 pos, f3& LightDirection, f3& LightColor, float& PDFValue, f3& LightNormal, float& LightAttenuation); // :170-261
 f3 sample_environment_map(const Scene& sc, f3 v);                       // :21-44
+f4 get_texture_data(const Scene& sc, uint32_t index, f2 uv);            // SharedRaytracing.h:67-137
 f4 sample_bilinear_wrap(const Image& im, f2 uv);                        // SampleLevel(BilinearSampler, uv, 0), pinned weights
 float hash13(f3 p3);                                                    // :662-667
 f4 path_trace(Ctx& c, f2 pixelCoord);                                   // the hand-restated PathTrace (core.cpp)

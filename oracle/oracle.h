@@ -15,7 +15,8 @@
 //       the restatements must match them bit for bit -> PINNED against the reference's code;
 //       likewise the builder's arithmetic: CalculateMortonCode, GenerateHierarchy (Karras), one treelet optimisation round
 //       (the group shader run by 32 host threads + barrier) and the leaf / parent box constructors -> PINNED;
-//       the light sampling / environment lookup / hash13 / Halton of RayGenCommon.h (ref_raygen.cpp) and the whole main() of
+//       the light sampling / environment lookup / hash13 / Halton of RayGenCommon.h, GetMaterialInternal / GetDetailNormal /
+//       GetTextureData (ref_raygen.cpp) and the whole main() of
 //       TemporalAccumulationCS.hlsl (ref_temporal.cpp, resources shimmed) -> PINNED; the auto-exposure group shaders
 //       GenerateHistogramCS.hlsl / CalculateAveragedLuminanceCS.hlsl run by a 256-thread host group (ref_hist.cpp) -> PINNED;
 //       the ray query LOOP itself (Traverse, SoftwareRayQuery, TestLeafNodeIntersections, the node / primitive readers:

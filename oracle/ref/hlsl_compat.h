@@ -24,7 +24,7 @@ struct float4;
 struct float3 {
     union { struct { float x, y, z; }; struct { float r, g, b; }; };
     float3() : x(0), y(0), z(0) {}
-#if defined(RC_POST) || defined(RC_TEMPORAL)
+#if defined(RC_POST) || defined(RC_TEMPORAL) || defined(RC_MATERIAL)
     float3(const float4& v); // HLSL implicit truncation float4 -> float3 (PostProcessCS.hlsl:26, 69, 118; TemporalAccumulationCS.hlsl:106, 184)
 #endif
 #ifdef RC_TEMPORAL
@@ -54,8 +54,11 @@ struct float4 {
     float2 xy() const { return float2(x, y); }
     float3 xyz() const { return float3(x, y, z); }
     float3 rgb() const { return float3(x, y, z); }
+#ifdef RC_MATERIAL
+    void set_rgb(float3 v) { x = v.x; y = v.y; z = v.z; }           // `data.rgb = ...` (SharedRaytracing.h:110)
+#endif
 };
-#if defined(RC_POST) || defined(RC_TEMPORAL)
+#if defined(RC_POST) || defined(RC_TEMPORAL) || defined(RC_MATERIAL)
 inline float3::float3(const float4& v) : x(v.x), y(v.y), z(v.z) {}
 #endif
 typedef float2 vec2;

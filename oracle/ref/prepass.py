@@ -254,5 +254,29 @@ def run_raygen(structs_h, raygen_h, dst_light, dst):
     open(dst, "w").write(text)
 
 
+def run_material(structs_h, tonemap_h, sharedrt_h, raygen_h, dst):
+    """Material and texture fetch: the material / texture flag defines, struct Material and struct TextureData
+    (SharedShaderStructs.h), GammaToLinear (Tonemap.h), GetMaterial_NonRecursive ... GetTextureData_Recursive
+    (SharedRaytracing.h:55-137: image / checker / scale textures, the uv flip, the gamma flag) and GetDetailNormal +
+    GetMaterialInternal (RayGenCommon.h:273-341: mix materials, albedo / emissive / specular-map overrides)."""
+    sh = open(structs_h).read()
+    a = sh.index("#define DEFAULT_MATERIAL_FLAG 0x0")
+    b = sh.index("struct TextureData")
+    structs = sh[a:sh.index("};", b) + 2]
+    t = open(tonemap_h).read()
+    a = t.index("float3 GammaToLinear(float3 color)")
+    gamma = t[a:t.index("}", a) + 1]
+    rt = open(sharedrt_h).read()
+    tex = rt[rt.index("Material GetMaterial_NonRecursive(int MaterialID)"):]
+    rg = open(raygen_h).read()
+    mat = rg[rg.index("float3 GetDetailNormal(Material mat, float3 normal, float3 tangent, float2 uv)"):rg.index("struct Ray\n{")]
+    text = structs + "\n" + gamma + "\n" + tex + "\n" + mat
+    if "data.rgb = GammaToLinear(data.rgb);" not in text:
+        raise SystemExit("prepass: expected swizzle assignment not found")
+    text = re.sub(r"\b(\w+)\.rgb\s*=\s*([^;]+);", r"\1.set_rgb(\2);", text)   # swizzle on the left-hand side
+    text = re.sub(r"\.(xyz|rgb|xy)\b(?!\s*\()", r".\1()", text)
+    open(dst, "w").write(text)
+
+
 if __name__ == "__main__":
     run(sys.argv[1], sys.argv[2])

@@ -6,7 +6,9 @@
 // bilinear fetch itself is the oracle's pinned sampler), `float4x3` and `mul(v, M)` as SURVEY §8c trap 19 reads them,
 // and rand() (kernel.glsl:39-40) with its seed / Time exposed.
 #define HLSL 1
+#define RC_MATERIAL 1
 #include "hlsl_compat.h"
+#include <climits>
 #include <cstring>
 #include "../glue.h"
 
@@ -15,8 +17,8 @@ namespace refcore {
 struct float4x3 { float4 c0, c1, c2; }; // three float4 columns (ConfigConstants.EnvironmentMapTransform)
 inline float3 mul(float3 v, const float4x3& m) { return float3(dot(v, m.c0.xyz()), dot(v, m.c1.xyz()), dot(v, m.c2.xyz())); }
 inline float atan2(float y, float x) { return tbm::atan2_(y, x); }
-struct PerFrame { uint LightCount, EnableNextEventEstimation, EnableSamplingImportanceResampling, GlobalFrameCount, IsRealTime; float DebugValue, DebugValue2, Time; };
-struct Config { float4x3 EnvironmentMapTransform; float3 EnvironmentMapColorScale; };
+struct PerFrame { uint LightCount, EnableNextEventEstimation, EnableSamplingImportanceResampling, GlobalFrameCount, IsRealTime; float DebugValue, DebugValue2, Time; uint EnableNormalMaps; };
+struct Config { float4x3 EnvironmentMapTransform; float3 EnvironmentMapColorScale; uint FlipTextureUVs; };
 static thread_local PerFrame perFrameConstants;
 static thread_local Config configConstants;
 struct SamplerShim {} static BilinearSampler;
@@ -36,6 +38,23 @@ inline float ColorToLuma(float3 color) { return dot(color, float3(0.212671, 0.71
 static thread_local const Light* LightList;
 #include "../_ref/raygen_gen.inc"
 
+// ---- material and texture fetch (prepass.run_material -> oracle/_ref/raygen_material_gen.inc): struct Material / TextureData
+// and the texture / material flag values, GammaToLinear, GetMaterial_NonRecursive ... GetTextureData_Recursive
+// (SharedRaytracing.h:55-137), GetDetailNormal and GetMaterialInternal (RayGenCommon.h:273-341). Shims: the structured
+// buffers as pointers into the oracle's scene, the image table (the bilinear fetch itself is the oracle's pinned sampler,
+// as for the environment map).
+struct Material;
+struct TextureData;
+template <typename T> struct BufferShim { const T* p = nullptr; const T& operator[](uint i) const { return p[i]; } };
+struct ImageTableShim {
+    const oracle::Image* images = nullptr;
+    TextureShim operator[](uint i) const { TextureShim t; t.image = images + i; return t; }
+};
+inline uint NonUniformResourceIndex(uint i) { return i; }
+static thread_local ImageTableShim ImageTextures;
+static thread_local BufferShim<Material> MaterialBuffer;       // holds pointers only: the structs are defined by the text below
+static thread_local BufferShim<TextureData> TextureDataBuffer;
+#include "../_ref/raygen_material_gen.inc"
 } // namespace refcore
 
 extern "C" __attribute__((visibility("default")))
@@ -68,6 +87,50 @@ void ref_env(const float* rgba, unsigned int w, unsigned int h, const float* tra
     configConstants.EnvironmentMapColorScale = float3(scale3[0], scale3[1], scale3[2]);
     float3 c = SampleEnvironmentMap(float3(v[0], v[1], v[2]));
     out3[0] = c.x; out3[1] = c.y; out3[2] = c.z;
+}
+
+static void bind_scene(const oracle::Scene& sc, unsigned int enableNormalMaps, float time, float seed) {
+    using namespace refcore;
+    static_assert(sizeof(Material) == sizeof(TbMaterial) && sizeof(Material) == 84, "Material layout (SharedShaderStructs.h:141-161)");
+    static_assert(sizeof(TextureData) == sizeof(TbTextureData) && sizeof(TextureData) == 80, "TextureData layout (:169-190)");
+    MaterialBuffer.p = (const Material*)sc.materials.data();
+    TextureDataBuffer.p = (const TextureData*)sc.textures.data();
+    ImageTextures.images = sc.images.data();
+    configConstants.FlipTextureUVs = sc.flipTextureUVs;
+    perFrameConstants.EnableNormalMaps = enableNormalMaps;
+    perFrameConstants.Time = time;
+    g_seed = seed;
+}
+
+// GetMaterialInternal on the oracle's scene (`scene` = oracle_scene_ptr). out21 = struct Material, 84 bytes.
+extern "C" __attribute__((visibility("default")))
+void ref_material(const void* scene, float time, int materialId, const float* uv, int backside, float* seed, void* out21) {
+    using namespace refcore;
+    bind_scene(*(const oracle::Scene*)scene, 0, time, *seed);
+    Material m = GetMaterialInternal(materialId, 0u, float3(0.0f), float2(uv[0], uv[1]), backside != 0);
+    *seed = g_seed;
+    memcpy(out21, &m, sizeof(m));
+}
+
+// GetDetailNormal for the (untextured-fetch) material record `materialId`.
+extern "C" __attribute__((visibility("default")))
+void ref_detail_normal(const void* scene, unsigned int enableNormalMaps, int materialId, const float* normal, const float* tangent,
+                       const float* uv, float* out3) {
+    using namespace refcore;
+    const oracle::Scene& sc = *(const oracle::Scene*)scene;
+    bind_scene(sc, enableNormalMaps, 0.0f, 0.0f);
+    float3 n = GetDetailNormal(MaterialBuffer[materialId], float3(normal[0], normal[1], normal[2]), float3(tangent[0], tangent[1], tangent[2]),
+                               float2(uv[0], uv[1]));
+    out3[0] = n.x; out3[1] = n.y; out3[2] = n.z;
+}
+
+// GetTextureData for texture record `textureIndex` (UINT_MAX = invalid).
+extern "C" __attribute__((visibility("default")))
+void ref_texture(const void* scene, unsigned int textureIndex, const float* uv, float* out4) {
+    using namespace refcore;
+    bind_scene(*(const oracle::Scene*)scene, 0, 0.0f, 0.0f);
+    float4 t = GetTextureData(textureIndex, float2(uv[0], uv[1]));
+    out4[0] = t.x; out4[1] = t.y; out4[2] = t.z; out4[3] = t.w;
 }
 
 extern "C" __attribute__((visibility("default"))) float ref_hash13(float x, float y, float z) { return refcore::hash13(refcore::float3(x, y, z)); }

@@ -849,3 +849,79 @@ def test_intersect_and_geometry_fetch_equal_reference_text(spec, tmp_path, built
     assert (bad & ~tie).sum() == 0, "%d rays differ, first: oracle %s reference %s" % (
         (bad & ~tie).sum(), a[np.flatnonzero(bad & ~tie)[:2]], b[np.flatnonzero(bad & ~tie)[:2]])
     assert tie.sum() <= n // 1000
+
+
+@pytest.mark.parametrize("spec", ["synthetic:showcase?tris=300&seed=2", "teapot", "vwvan"])
+def test_material_and_texture_fetch_equal_reference_text(spec, tmp_path, built):
+    """GetMaterialInternal and GetDetailNormal (RayGenCommon.h:273-341) and GetTextureData with its image / checker / scale
+    / gamma / uv-flip paths (SharedRaytracing.h:55-137), compiled from the mount (oracle/_ref/libref_raygen.so), against
+    the oracle's get_material_internal / get_detail_normal / get_texture_data on the same scene: every material record x
+    random uvs (incl. negative and > 1: wrap, and the checker's int() truncation around zero) x front / back side, the
+    84 bytes of the resulting Material and the position of the rand() stream afterwards (mix materials draw one number);
+    every texture record incl. the invalid index; the detail normal with normal maps on and off. The showcase scene
+    holds every kind: mix, specular map, scale of image x checker, gamma-flagged image, normal map, emissive texture."""
+    import ctypes as C
+    import tracerboy_b200 as tb
+    from oracle import binding
+    path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_raygen.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_raygen.so not built (needs the reference mount at build time)")
+    lib = binding.load()
+    ref = C.CDLL(path)
+    if not hasattr(ref, "ref_material"):
+        pytest.skip("oracle/_ref/libref_raygen.so predates the material build")
+    fp = C.POINTER(C.c_float)
+    lib.oracle_scene_ptr.restype = C.c_void_p; lib.oracle_scene_ptr.argtypes = [C.c_void_p]
+    lib.oracle_num_materials.argtypes = [C.c_void_p]; lib.oracle_num_textures.argtypes = [C.c_void_p]
+    lib.oracle_material.argtypes = [C.c_void_p, C.c_float, C.c_int, fp, C.c_int, fp, C.c_void_p]; lib.oracle_material.restype = None
+    ref.ref_material.argtypes = [C.c_void_p, C.c_float, C.c_int, fp, C.c_int, fp, C.c_void_p]; ref.ref_material.restype = None
+    lib.oracle_detail_normal.argtypes = [C.c_void_p, C.c_uint32, C.c_int, fp, fp, fp, fp]; lib.oracle_detail_normal.restype = None
+    ref.ref_detail_normal.argtypes = [C.c_void_p, C.c_uint32, C.c_int, fp, fp, fp, fp]; ref.ref_detail_normal.restype = None
+    lib.oracle_texture.argtypes = [C.c_void_p, C.c_uint32, fp, fp]; lib.oracle_texture.restype = None
+    ref.ref_texture.argtypes = [C.c_void_p, C.c_uint32, fp, fp]; ref.ref_texture.restype = None
+    if spec in NAMED:
+        scene = scene_path(NAMED[spec])
+        if scene is None:
+            pytest.skip("scene cache missing")
+    else:
+        scene = str(tmp_path / "s.tbscene")
+        tb.convert_scene(spec, scene)
+    o = binding.Oracle(); o.LoadScene(scene, 0)
+    sp = lib.oracle_scene_ptr(o.h)
+    nm, nt = lib.oracle_num_materials(o.h), lib.oracle_num_textures(o.h)
+    rng = np.random.default_rng(3)
+
+    def p(a):
+        return a.ctypes.data_as(fp)
+
+    def same(a, b):
+        return ((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all()
+
+    per = max(20, 3000 // max(nm, 1))
+    for m in range(nm):
+        for i in range(per):
+            uv = (rng.uniform(-2.5, 3.5, 2) if i % 3 else rng.uniform(0, 1, 2)).astype(np.float32)
+            if i % 17 == 0: uv[:] = [0.0, -0.0]
+            back = i & 1
+            s1 = np.array([rng.integers(0, 4000)], np.float32); s2 = s1.copy()
+            a, b = np.zeros(21, np.float32), np.zeros(21, np.float32)
+            lib.oracle_material(o.h, np.float32(0.25 * (i % 4)), m, p(uv), back, p(s1), a.ctypes.data_as(C.c_void_p))
+            ref.ref_material(sp, np.float32(0.25 * (i % 4)), m, p(uv), back, p(s2), b.ctypes.data_as(C.c_void_p))
+            assert s1[0] == s2[0], "rand() stream position differs (material %d)" % m
+            assert same(a, b), (m, uv, a, b)
+            nrm = rng.normal(0, 1, 3).astype(np.float32); nrm /= np.linalg.norm(nrm)
+            tan = np.cross(nrm, rng.normal(0, 1, 3)).astype(np.float32); tan /= np.linalg.norm(tan)
+            for on in (0, 1):
+                x, y = np.zeros(3, np.float32), np.zeros(3, np.float32)
+                lib.oracle_detail_normal(o.h, on, m, p(nrm), p(tan), p(uv), p(x))
+                ref.ref_detail_normal(sp, on, m, p(nrm), p(tan), p(uv), p(y))
+                assert same(x, y), (m, on, x, y)
+    for t in list(range(nt)) + [0xffffffff]:
+        for i in range(300 if nt else 3):
+            uv = (rng.uniform(-2.5, 3.5, 2) if i % 3 else rng.uniform(0, 1, 2)).astype(np.float32)
+            x, y = np.zeros(4, np.float32), np.zeros(4, np.float32)
+            lib.oracle_texture(o.h, t, p(uv), p(x))
+            ref.ref_texture(sp, t, p(uv), p(y))
+            assert same(x, y), (t, uv, x, y)
+    if spec.startswith("synthetic:showcase"):
+        assert nm >= 8 and nt >= 5
