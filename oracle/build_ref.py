@@ -68,6 +68,37 @@ def build_post(force=False):
     return target
 
 
+ENTRY = "/root/reference/TracerBoy/SoftwareRayTraceCS.hlsl"
+
+
+def frame_lib_path():
+    return os.path.join(OUT, "libref_frame.so")
+
+
+def build_frame(force=False):
+    """oracle/_ref/libref_frame.so: the per-pixel wrapper (GetBlueNoise, AOV writers, RayTraceCommon, the entry point's
+    per-pixel part) as host C++, PathTrace = the synthetic stand-in."""
+    target = frame_lib_path()
+    raygen = "/root/reference/TracerBoy/RayGenCommon.h"
+    if not (os.path.exists(raygen) and os.path.exists(ENTRY)):
+        return target if os.path.exists(target) else None
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_frame.cpp", "synthetic_tracer.h")] + \
+           [raygen, ENTRY, os.path.join(HERE, "glue.h"), os.path.join(HERE, "liboracle.so")]
+    if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs):
+        return target
+    sys.path.insert(0, os.path.join(HERE, "ref"))
+    import prepass
+    prepass.run_frame(raygen, ENTRY, os.path.join(OUT, "frame_gen.inc"))
+    cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma", "-ffp-contract=off", "-fsingle-precision-constant", "-fno-fast-math",
+           "-fvisibility=hidden", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + HERE, os.path.join(HERE, "ref", "ref_frame.cpp"),
+           "-o", target, "-L" + HERE, "-loracle", "-Wl,-rpath,$ORIGIN/.."]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref frame wrapper build failed:\n" + r.stdout)
+    return target
+
+
 GENHIST = "/root/reference/TracerBoy/GenerateHistogramCS.hlsl"
 AVGLUM = "/root/reference/TracerBoy/CalculateAveragedLuminanceCS.hlsl"
 
@@ -310,6 +341,7 @@ def build_raygen(force=False):
 
 if __name__ == "__main__":
     print(build_temporal(force="--force" in sys.argv))
+    print(build_frame(force="--force" in sys.argv))
     print(build_hist(force="--force" in sys.argv))
     print(build_raygen(force="--force" in sys.argv))
     print(build_boxes(force="--force" in sys.argv))

@@ -8,6 +8,7 @@
 #include "../tracerboy_b200/csrc/common/tb_vec.h"
 #include "oracle.h"
 #include "glue.h"
+#include "ref/synthetic_tracer.h"
 
 using namespace oracle;
 
@@ -224,6 +225,36 @@ ORACLE_API void oracle_texture(OracleHandle* h, uint32_t textureIndex, const flo
     tbm::f4 t = get_texture_data(h->scene, textureIndex, tbm::mk2(uv[0], uv[1]));
     out4[0] = t.x; out4[1] = t.y; out4[2] = t.z; out4[3] = t.w;
 }
+// test hook for the pin of the per-pixel wrapper (RayTraceCommon, AOV writers, GetBlueNoise): render_frame driven by the
+// synthetic stand-in for PathTrace that oracle/ref/ref_frame.cpp drives the reference text with.
+namespace {
+struct CtxSink {
+    Ctx& c;
+    float rand() { return c.rand(); }
+    void blue_noise(float o[8]) {
+        BlueNoiseData d = get_blue_noise(c);
+        o[0] = d.PrimaryJitter.x; o[1] = d.PrimaryJitter.y; o[2] = d.SecondaryRayDirection.x; o[3] = d.SecondaryRayDirection.y;
+        o[4] = d.AreaLightJitter.x; o[5] = d.AreaLightJitter.y; o[6] = d.DOFJitter.x; o[7] = d.DOFJitter.y;
+    }
+    // the writers as core.cpp's path_trace performs them on the pixel context
+    void albedo(const float* a, float) { c.aovAlbedo = tbm::mk4(a[0], a[1], a[2], 1.0f); }
+    void normal(const float* n) { c.aovNormal = tbm::mk4(n[0], n[1], n[2], 1.0f); }
+    void world_position(const float* p, float d) { c.worldPosition += tbm::mk3(p[0], p[1], p[2]); c.distanceToNeighbor += d; }
+    void distance(float D) {
+        c.aovDepth = tbm::saturate(D / c.rp.settings.MaxZ); c.wroteDepth = true;
+        if (c.selected()) { c.statDistance = D; c.wroteStats = true; }
+    }
+    void material(int id) { if (c.selected()) { c.statMaterial = id; c.wroteStats = true; } }
+    void emissive(const float* e) { c.aovEmissive = tbm::mk4(e[0], e[1], e[2], 1.0f); c.wroteEmissive = true; }
+};
+tbm::f4 synthetic_override(Ctx& c, tbm::f2 pixelCoord) {
+    CtxSink s{c};
+    float out[4];
+    synthetic_path(s, pixelCoord.x, pixelCoord.y, c.rp.frame, out);
+    return tbm::mk4(out[0], out[1], out[2], out[3]);
+}
+} // namespace
+ORACLE_API void oracle_enable_synthetic_tracer(int on) { set_path_trace_override(on ? synthetic_override : nullptr); }
 ORACLE_API uint32_t oracle_morton(const float* centroid, const float* smin, const float* smax) {
     return oracle::morton_public(centroid, smin, smax);
 }

@@ -22,7 +22,9 @@
 //       the ray query LOOP itself (Traverse, SoftwareRayQuery, TestLeafNodeIntersections, the node / primitive readers:
 //       ref_traverse_loop.cpp) on the oracle's own BVH bytes: every field of every hit record incl. both counters -> PINNED;
 //       IntersectWithMaxDistance + the SharedHitGroup.h geometry fetch (same file): t, material, normal, tangent, uv -> PINNED;
-//  (ii) the builder's resource-bound glue and the rest of the RayGenCommon/SharedHitGroup/SharedRaytracing glue are
+//       the per-pixel wrapper (GetBlueNoise, AOV writers, RayTraceCommon, the entry point's per-pixel part: ref_frame.cpp,
+//       driven by the synthetic stand-in for PathTrace of ref/synthetic_tracer.h) -> PINNED;
+//  (ii) the builder's resource-bound glue and the camera accessors are
 //       HLSL that cannot be compiled here: restated, checked by the fallback layer's own
 //       validator invariants, analytic known answers and independent numpy restatements
 //       -> "parity unpinned" by reference outputs for these parts.

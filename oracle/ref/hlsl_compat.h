@@ -54,6 +54,9 @@ struct float4 {
     float2 xy() const { return float2(x, y); }
     float3 xyz() const { return float3(x, y, z); }
     float3 rgb() const { return float3(x, y, z); }
+#ifdef RC_FRAME
+    float2 zw() const { return float2(z, w); }                       // BlueNoise0Texture[...].zw (RayGenCommon.h:116)
+#endif
 #ifdef RC_MATERIAL
     void set_rgb(float3 v) { x = v.x; y = v.y; z = v.z; }           // `data.rgb = ...` (SharedRaytracing.h:110)
 #endif

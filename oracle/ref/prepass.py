@@ -278,5 +278,47 @@ def run_material(structs_h, tonemap_h, sharedrt_h, raygen_h, dst):
     open(dst, "w").write(text)
 
 
+def run_frame(raygen_h, entry_hlsl, dst):
+    """The per-pixel wrapper around PathTrace: Halton / Halton23, struct BlueNoiseData, ApplyLDSToNoise, the
+    Resolution / DispatchIndex accessors and GetBlueNoise (RayGenCommon.h:48-122), the AOV writers OutputPrimaryAlbedo,
+    OutputPrimaryEmissive, OutputRayStats, OutputPrimaryNormal, OutputPrimaryWorldPosition (with its statics),
+    IsSelectedPixel, OutputDistanceToFirstHit, OutputMaterial, ClearAOVs (:524-654), hash13 (:662-667), RayTraceCommon
+    (:690-728) and the per-pixel part of SoftwareRayTraceCS.hlsl's main() (ClearAOVs ... RayTraceCommon, :37-51)."""
+    t = open(raygen_h).read()
+
+    def between(a, b):
+        i = t.index(a)
+        return t[i:t.index(b, i)]
+    parts = [between("float Halton(int b, int i)", "float GetRotationFactor()") if "float GetRotationFactor()" in t[t.index("float Halton(int b, int i)"):t.index("BlueNoiseData GetBlueNoise()")] else between("float Halton(int b, int i)", "float4 GetMouse()"),
+             between("BlueNoiseData GetBlueNoise()", "\n}\n") + "\n}\n"]
+    defs = t.index("void OutputPrimaryAlbedo(float3 albedo, float DiffuseContribution)\n{")
+    tail = t[defs:]
+
+    def fn(sig, src=tail):
+        i = src.index(sig)
+        return src[i:src.index("\n}\n", i) + 3]
+    for sig in ("void OutputPrimaryAlbedo(float3 albedo, float DiffuseContribution)", "void OutputPrimaryEmissive(float3 emissive)",
+                "void OutputRayStats(uint TrianglesTested, uint BoxesTested)", "void OutputPrimaryNormal(float3 normal)"):
+        parts.append(fn(sig))
+    parts.append(between("static float3 WorldPosition;", "bool IsSelectedPixel()"))
+    for sig in ("bool IsSelectedPixel()", "void OutputDistanceToFirstHit(float Distance)", "void OutputMaterial(int MaterialID)", "void ClearAOVs()"):
+        parts.append(fn(sig))
+    parts.append(between("float hash13(vec3 p3)", "bool ShouldSkipRay()"))
+    parts.append(t[t.index("void RayTraceCommon()"):])
+    e = open(entry_hlsl).read()
+    body = e[e.index("\tClearAOVs();"):e.index("\tRayTraceCommon();") + len("\tRayTraceCommon();")]
+    parts.append("\nstatic void pixel_main()\n{\n" + body + "\n}\n")
+    text = "\n".join(parts)
+    # the four float2(rand(), rand()) of GetBlueNoise: DXC evaluates arguments left to right, g++ right to left
+    # (SURVEY 8c trap 17); a braced initialiser list is sequenced left to right by the language
+    if text.count("float2(rand(), rand())") != 4:
+        raise SystemExit("prepass: expected four float2(rand(), rand()) in GetBlueNoise")
+    text = text.replace("float2(rand(), rand())", "float2{rand(), rand()}")
+    if re.search(r"\([^()]*rand\(\)[^()]*rand\(\)[^()]*\)", text):
+        raise SystemExit("prepass: an unsequenced pair of rand() calls is left in one argument list")
+    text = re.sub(r"\.(xyz|rgb|xy|zw|yzx)\b(?!\s*\()", r".\1()", text)
+    open(dst, "w").write(text)
+
+
 if __name__ == "__main__":
     run(sys.argv[1], sys.argv[2])

@@ -925,3 +925,67 @@ def test_material_and_texture_fetch_equal_reference_text(spec, tmp_path, built):
             assert same(x, y), (t, uv, x, y)
     if spec.startswith("synthetic:showcase"):
         assert nm >= 8 and nt >= 5
+
+
+@pytest.mark.parametrize("blue_noise,realtime", [(1, 0), (0, 0), (1, 1)])
+def test_frame_wrapper_equals_reference_text(blue_noise, realtime, cornell, built):
+    """The per-pixel wrapper around PathTrace — GetBlueNoise with ApplyLDSToNoise / Halton23 (RayGenCommon.h:48-122), the
+    AOV writers (:524-654), RayTraceCommon (:690-728: NaN samples dropped whole, world-position ping-pong by frame parity,
+    "frame 0 overwrites" accumulation, the jittered half-buffer and its rand() coin, real-time mode) and the entry point's
+    per-pixel part (ClearAOVs, seed = hash13(x, y, frame)) — compiled from the mount (oracle/_ref/libref_frame.so) against
+    the oracle's render_frame, both driven by the same deterministic stand-in for PathTrace (oracle/ref/synthetic_tracer.h:
+    a varying number of rand() draws, blue-noise lookups, NaN / negative samples, pixels with all, some and no AOV writes).
+    After 5 frames every buffer must be bit-identical: accumulation, jittered, normals, both world-position buffers'
+    latest, albedo, emissive, depth, and the selected pixel's statistics."""
+    import ctypes as C
+    import tracerboy_b200 as tb
+    from oracle import binding
+    path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_frame.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_frame.so not built (needs the reference mount at build time)")
+    lib = binding.load()
+    ref = C.CDLL(path)
+    lib.oracle_scene_ptr.restype = C.c_void_p; lib.oracle_scene_ptr.argtypes = [C.c_void_p]
+    lib.oracle_enable_synthetic_tracer.argtypes = [C.c_int]; lib.oracle_enable_synthetic_tracer.restype = None
+    ref.ref_render_synthetic.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_float] + [C.c_void_p] * 9
+    W, H, frames = 300, 37, 5          # wider than the 256-texel blue-noise tile, odd height
+    s = tb.get_default_output_settings()
+    s.EnableBlueNoise = blue_noise
+    s.RenderMode = 1 if realtime else 0
+    s.MaxZ = 40.0                      # some synthetic distances saturate the depth AOV
+    K = tb.BufferKind
+    o = binding.Oracle(); o.LoadScene(cornell, 0); o.Resize(W, H)
+    o.SelectPixel(7, 5)
+    try:
+        lib.oracle_enable_synthetic_tracer(1)
+        o.Render(s, frames, 0.25)
+    finally:
+        lib.oracle_enable_synthetic_tracer(0)
+    bufs = {k: np.zeros((H, W, 4), np.float32) for k in ("accum", "jit", "nrm", "wp0", "wp1", "alb", "emi")}
+    depth = np.zeros((H, W), np.float32)
+    stats = np.zeros(4, np.uint32)
+    rc = ref.ref_render_synthetic(lib.oracle_scene_ptr(o.h), C.byref(s), W, H, 0, frames, 7, 5, np.float32(0.25),
+                                  *[bufs[k].ctypes.data_as(C.c_void_p) for k in ("accum", "jit", "nrm", "wp0", "wp1", "alb", "emi")],
+                                  depth.ctypes.data_as(C.c_void_p), stats.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+
+    def same(a, b):
+        return ((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b)))
+    last = (frames - 1) % 2
+    pairs = [("accum", K.ACCUM_RGBW), ("jit", K.JITTERED_RGBW), ("nrm", K.AOV_NORMAL), ("wp%d" % last, K.AOV_WORLDPOS),
+             ("alb", K.AOV_ALBEDO), ("emi", K.AOV_EMISSIVE)]
+    for name, kind in pairs:
+        got = o.Readback(kind).reshape(H, W, 4)
+        ok = same(got, bufs[name])
+        assert ok.all(), "%s differs at %d values, first %s: oracle %s reference %s" % (
+            name, (~ok).sum(), np.argwhere(~ok)[0], got[tuple(np.argwhere(~ok)[0])], bufs[name][tuple(np.argwhere(~ok)[0])])
+    assert same(o.Readback(K.AOV_DEPTH).reshape(H, W), depth).all()
+    st = o.GetReadbackStats()
+    assert np.float32(st.SelectedPixelDistance).view(np.uint32) == stats[2] and st.SelectedMaterialID == stats[3]
+    # the run really exercised the rules: some samples were dropped, the jittered buffer holds about half of the frames
+    acc = bufs["accum"]
+    if realtime:   # every frame overwrites, the jittered buffer is never written
+        assert acc[..., 3].max() == 1 and (acc[..., 3] == 0).any() and not bufs["jit"].any()
+    else:
+        assert acc[..., 3].max() == frames and (acc[..., 3] < frames).any() and (bufs["jit"][..., 3] < acc[..., 3]).any()
+    assert (depth == 1.0).any() and (bufs["emi"][..., 3] == 0).any() and (bufs["emi"][..., 3] == 1).any()
