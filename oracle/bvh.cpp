@@ -349,6 +349,7 @@ bool build_bvh(Scene& s, int treeletPasses, std::string& err) {
             minTris *= 2;
         }
     }
+    s.hierarchy.assign((const uint32_t*)H.data(), (const uint32_t*)H.data() + 3 * (size_t)total);
     // PrepareForComputeAABBs + ComputeAABBs (ComputeAABBs.hlsli:69-172)
     const uint32_t offBoxes = 16;
     const uint32_t offPrims = offBoxes + 32 * total;

@@ -58,6 +58,11 @@ ORACLE_API int oracle_get_bvh(OracleHandle* h, void* dst, uint64_t bytes) {
     memcpy(dst, h->scene.bvh.data(), h->scene.bvh.size());
     return 0;
 }
+ORACLE_API int oracle_get_hierarchy(OracleHandle* h, uint32_t* dst, uint64_t words) { // test hook (ComputeAABBs pin)
+    if (words < h->scene.hierarchy.size()) return -1;
+    memcpy(dst, h->scene.hierarchy.data(), 4 * h->scene.hierarchy.size());
+    return 0;
+}
 ORACLE_API uint32_t oracle_max_treelet_climb(OracleHandle* h) { return h->scene.maxTreeletClimb; }
 ORACLE_API uint32_t oracle_num_triangles(OracleHandle* h) { return h->scene.numPrims; }
 ORACLE_API int oracle_trace_rays(OracleHandle* h, const TbRay* rays, uint64_t n, TbHit* hits) {

@@ -24,7 +24,9 @@
 //       IntersectWithMaxDistance + the SharedHitGroup.h geometry fetch (same file): t, material, normal, tangent, uv -> PINNED;
 //       the per-pixel wrapper (GetBlueNoise, AOV writers, RayTraceCommon, the entry point's per-pixel part: ref_frame.cpp,
 //       driven by the synthetic stand-in for PathTrace of ref/synthetic_tracer.h) -> PINNED;
-//  (ii) the builder's resource-bound glue and the camera accessors are
+//       the builder's last stage (PrepareForComputeAABBs + ComputeAABBs: node encoding, bottom-up climb; ref_refit.cpp) -> PINNED
+//       (child order at equal subtree sizes is arrival-order dependent in the reference: deviation D1, asserted by the test);
+//  (ii) the front of the builder (primitive load, scene AABB, sort order, treelet roots / climb order) and the camera accessors are
 //       HLSL that cannot be compiled here: restated, checked by the fallback layer's own
 //       validator invariants, analytic known answers and independent numpy restatements
 //       -> "parity unpinned" by reference outputs for these parts.
@@ -60,6 +62,7 @@ struct Scene {
     std::vector<uint8_t> bvh;
     uint32_t numPrims = 0;
     uint32_t maxTreeletClimb = 0; // longest base-treelet -> root chain (reference caps at 33)
+    std::vector<uint32_t> hierarchy; // test hook: the HierarchyNode array (parent, left, right per node) handed to ComputeAABBs
 };
 
 bool load_tbscene(Scene& s, const std::string& path, std::string& err);

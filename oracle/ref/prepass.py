@@ -278,6 +278,33 @@ def run_material(structs_h, tonemap_h, sharedrt_h, raygen_h, dst):
     open(dst, "w").write(text)
 
 
+def run_refit(helper_hlsli, prepare_hlsl, bottom_hlsl, compute_hlsli, dst_prepare, dst_compute):
+    """The last builder stage: main() of BottomLevelPrepareForComputeAABBs.hlsl (header offsets, the thread -> node map,
+    counter clear) into one file; RayTracingHelper.hlsli's helpers (AABB_Min_Padding ... GetBoxFromChildBoxes), ComputeLeafAABB of
+    BottomLevelComputeAABBs.hlsl and the whole ComputeAABBs.hlsli (node encoding, the bottom-up climb with its
+    InterlockedAdd hand-over and the smaller-subtree-left rule) into another."""
+    h = open(helper_hlsli).read()
+    helper = h[h.index("#define AABB_Min_Padding 0.001"):h.index("float Determinant(in AffineMatrix transform)")]
+    p = open(prepare_hlsl).read()
+    prep = p[p.index("[numthreads(THREAD_GROUP_1D_WIDTH, 1, 1)]"):]
+    prep = prep.replace("[numthreads(THREAD_GROUP_1D_WIDTH, 1, 1)]", "").replace("void main(uint3 DTid : SV_DispatchThreadID)", "static void prepare_main(uint3 DTid)")
+    b = open(bottom_hlsl).read()
+    leaf = b[b.index("BoundingBox ComputeLeafAABB("):b.index("#define BOTTOM_LEVEL 1")]
+    c = open(compute_hlsli).read()
+    comp = c[c.index("uint DivideAndRoundUp("):]
+    comp = comp.replace("[numthreads(THREAD_GROUP_1D_WIDTH, 1, 1)]", "").replace("void main(uint3 DTid : SV_DispatchThreadID)", "static void compute_main(uint3 DTid)")
+    if "static void compute_main(uint3 DTid)" not in comp or "static void prepare_main(uint3 DTid)" not in prep:
+        raise SystemExit("prepass: entry points not found")
+
+    def fix(text):
+        text = text.replace("[unroll]", "")
+        text = re.sub(r"\b(?:inout|out)\s+([A-Za-z_]\w*)\s+([A-Za-z_]\w*)", r"\1& \2", text)
+        text = re.sub(r"\.(xyz|rgb|xy|zw)\b(?!\s*\()", r".\1()", text)
+        return text
+    open(dst_prepare, "w").write(fix(prep))
+    open(dst_compute, "w").write(fix(helper + "\n" + leaf + "\n" + comp))
+
+
 def run_frame(raygen_h, entry_hlsl, dst):
     """The per-pixel wrapper around PathTrace: Halton / Halton23, struct BlueNoiseData, ApplyLDSToNoise, the
     Resolution / DispatchIndex accessors and GetBlueNoise (RayGenCommon.h:48-122), the AOV writers OutputPrimaryAlbedo,

@@ -989,3 +989,77 @@ def test_frame_wrapper_equals_reference_text(blue_noise, realtime, cornell, buil
     else:
         assert acc[..., 3].max() == frames and (acc[..., 3] < frames).any() and (bufs["jit"][..., 3] < acc[..., 3]).any()
     assert (depth == 1.0).any() and (bufs["emi"][..., 3] == 0).any() and (bufs["emi"][..., 3] == 1).any()
+
+
+@pytest.mark.parametrize("spec,passes", [("cornell", 3), ("teapot", 3), ("synthetic:blobs?copies=8&tris=1000&seed=7", 1),
+                                         ("synthetic:showcase?tris=300&seed=2", 0)])
+def test_node_encoding_and_refit_equal_reference_text(spec, passes, tmp_path, built):
+    """The builder's last stage — BottomLevelPrepareForComputeAABBs.hlsl (header offsets, thread -> node map) and
+    ComputeAABBs.hlsli with ComputeLeafAABB (leaf / internal node encoding, the bottom-up climb where the second thread to
+    arrive continues, smaller subtree left) — compiled from the mount (oracle/_ref/libref_refit.so) and run on the oracle's
+    own sorted primitives and final hierarchy, under the two sequential schedules a barrier-free kernel allows (threads
+    ascending / descending). Against the oracle's BVH bytes: header, primitives and metadata untouched, every leaf node
+    and every internal node's box bit-identical under both schedules, child references identical wherever the two
+    subtrees differ in size; at equal sizes the reference's order depends on which thread arrives second (the two
+    schedules disagree with each other there), and the oracle keeps the hierarchy's order — deviation D1, asserted."""
+    import ctypes as C
+    import tracerboy_b200 as tb
+    from oracle import binding
+    path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_refit.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_refit.so not built (needs the reference mount at build time)")
+    ref = C.CDLL(path)
+    ref.ref_refit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
+    lib = binding.load()
+    lib.oracle_get_hierarchy.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    if spec in NAMED:
+        scene = scene_path(NAMED[spec])
+        if scene is None:
+            pytest.skip("scene cache missing")
+    else:
+        scene = str(tmp_path / "s.tbscene")
+        tb.convert_scene(spec, scene)
+    o = binding.Oracle(); o.LoadScene(scene, passes)
+    B = np.ascontiguousarray(o.GetBVH())
+    n = (B.size + 16) // 116
+    total, nint = 2 * n - 1, n - 1
+    H = np.zeros(3 * total, np.uint32)
+    assert lib.oracle_get_hierarchy(o.h, H.ctypes.data_as(C.c_void_p), H.size) == 0
+    H = H.reshape(total, 3)
+    off_prims = 16 + 32 * total
+    nodes_o = B[16:off_prims].view(np.uint32).reshape(total, 8)
+    # subtree sizes from the hierarchy (children before parents, explicit stack)
+    count = np.zeros(total, np.int64); count[nint:] = 1
+    stack, order = [0], []
+    while stack:
+        i = stack.pop()
+        if i < nint:
+            order.append(i); stack.append(int(H[i, 1])); stack.append(int(H[i, 2]))
+    for i in reversed(order):
+        count[i] = count[H[i, 1]] + count[H[i, 2]]
+    results = []
+    for descending in (0, 1):
+        R = B.copy()
+        R[:off_prims] = 0          # header and nodes are what the stage writes
+        assert ref.ref_refit(R.ctypes.data_as(C.c_void_p), np.ascontiguousarray(H).ctypes.data_as(C.c_void_p), n, descending) == 0
+        assert np.array_equal(R[:16], B[:16]), "BVHOffsets header"
+        assert np.array_equal(R[off_prims:], B[off_prims:])
+        results.append(R[16:off_prims].view(np.uint32).reshape(total, 8))
+    ties = 0
+    for nodes_r in results:
+        assert np.array_equal(nodes_r[nint:], nodes_o[nint:]), "leaf nodes"
+        assert np.array_equal(nodes_r[:nint][:, [0, 1, 2, 4, 5, 6]], nodes_o[:nint][:, [0, 1, 2, 4, 5, 6]]), "internal boxes"
+    lo, ro = nodes_o[:nint, 3].astype(np.int64), nodes_o[:nint, 7].astype(np.int64)
+    hl, hr = H[:nint, 1].astype(np.int64), H[:nint, 2].astype(np.int64)
+    tie = count[hl] == count[hr]
+    for nodes_r in results:
+        lr, rr = nodes_r[:nint, 3].astype(np.int64), nodes_r[:nint, 7].astype(np.int64)
+        assert np.array_equal(lr[~tie], lo[~tie]) and np.array_equal(rr[~tie], ro[~tie]), "child order where sizes differ"
+        assert np.array_equal(np.minimum(lr, rr), np.minimum(lo, ro)) and np.array_equal(np.maximum(lr, rr), np.maximum(lo, ro))
+        assert (count[lr[~tie]] < count[rr[~tie]]).all(), "smaller subtree left"
+    # D1: at equal sizes the oracle keeps the hierarchy's order; the two schedules of the reference pick opposite orders
+    assert np.array_equal(lo[tie], hl[tie]) and np.array_equal(ro[tie], hr[tie])
+    if tie.any():
+        a, b = results[0][:nint, 3][tie], results[1][:nint, 3][tie]
+        assert (a != b).any(), "the two schedules should disagree on some equal-size node"
+    assert tie.sum() > 0 or n < 8

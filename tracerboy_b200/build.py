@@ -205,6 +205,7 @@ def build_all(force=False, verbose=False):
     build_ref.build_temporal(force)
     build_ref.build_hist(force)
     build_ref.build_frame(force)
+    build_ref.build_refit(force)
 
 
 if __name__ == "__main__":
