@@ -68,6 +68,33 @@ def build_post(force=False):
     return target
 
 
+def treelet_pass_lib_path():
+    return os.path.join(OUT, "libref_treelet_pass.so")
+
+
+def build_treelet_pass(force=False):
+    """oracle/_ref/libref_treelet_pass.so: ClearBuffers + FindTreelets + the whole TreeletReorder.hlsl as host C++."""
+    src = "/root/reference/D3D12RaytracingFallback/src/"
+    files = [src + f for f in ("TreeletReorderBindings.h", "TreeletReorder.hlsl", "ClearBuffers.hlsl", "FindTreelets.hlsl",
+                               "RayTracingHelper.hlsli", "RayTracingHlslCompat.h")]
+    target = treelet_pass_lib_path()
+    if not all(os.path.exists(f) for f in files):
+        return target if os.path.exists(target) else None
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_treelet_pass.cpp")] + files
+    if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs):
+        return target
+    sys.path.insert(0, os.path.join(HERE, "ref"))
+    import prepass
+    prepass.run_treelet_pass(*files, os.path.join(OUT, "treelet_pass_gen.inc"))
+    cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-mfma", "-ffp-contract=off", "-fsingle-precision-constant", "-fno-fast-math",
+           "-fvisibility=hidden", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + HERE, os.path.join(HERE, "ref", "ref_treelet_pass.cpp"), "-o", target]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref treelet pass build failed:\n" + r.stdout)
+    return target
+
+
 def refit_lib_path():
     return os.path.join(OUT, "libref_refit.so")
 
@@ -369,6 +396,7 @@ if __name__ == "__main__":
     print(build_temporal(force="--force" in sys.argv))
     print(build_frame(force="--force" in sys.argv))
     print(build_refit(force="--force" in sys.argv))
+    print(build_treelet_pass(force="--force" in sys.argv))
     print(build_hist(force="--force" in sys.argv))
     print(build_raygen(force="--force" in sys.argv))
     print(build_boxes(force="--force" in sys.argv))

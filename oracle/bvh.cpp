@@ -263,6 +263,19 @@ void treelet_public(uint32_t* H3, float* aabb6, uint32_t n, uint32_t root) {
     }
 }
 
+// test hook: one whole treelet pass (ClearBuffers + FindTreelets + TreeletReorder) on a caller-provided hierarchy and the
+// sorted primitives (40 bytes each)
+void treelet_pass_public(uint32_t* H3, const void* prims40, uint32_t n, uint32_t minTris, uint32_t* maxClimb) {
+    const uint32_t total = 2 * n - 1;
+    std::vector<HNode> H(total);
+    memcpy(H.data(), H3, sizeof(HNode) * total);
+    std::vector<Prim> prims((const Prim*)prims40, (const Prim*)prims40 + n);
+    uint32_t climb = 0;
+    treelet_pass(H, prims, n, minTris, climb);
+    memcpy(H3, H.data(), sizeof(HNode) * total);
+    if (maxClimb) *maxClimb = climb;
+}
+
 // test hooks: the two box constructors of the node writer (leaf from a triangle, parent from two children)
 void leaf_box_public(const float* v9, float* c3, float* h3) {
     Prim p; p.type = 1; memcpy(p.v, v9, 36);

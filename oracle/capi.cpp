@@ -139,6 +139,9 @@ ORACLE_API void oracle_math_eval(int fn, const float* x, const float* y, float* 
 }
 ORACLE_API void oracle_karras(const uint32_t* codes, uint32_t n, uint32_t* out3) { oracle::karras_public(codes, n, out3); }
 ORACLE_API void oracle_treelet(uint32_t* H3, float* aabb6, uint32_t n, uint32_t root) { oracle::treelet_public(H3, aabb6, n, root); }
+ORACLE_API void oracle_treelet_pass(uint32_t* H3, const void* prims40, uint32_t n, uint32_t minTris, uint32_t* maxClimb) {
+    oracle::treelet_pass_public(H3, prims40, n, minTris, maxClimb);
+}
 ORACLE_API void oracle_leaf_box(const float* v9, float* c3, float* h3) { oracle::leaf_box_public(v9, c3, h3); }
 ORACLE_API void oracle_parent_box(const float* ac, const float* ah, const float* bc, const float* bh, float* c3, float* h3) { oracle::parent_box_public(ac, ah, bc, bh, c3, h3); }
 // test hooks for oracle/ref/ref_raygen.cpp: the restated light sampling and environment lookup on caller-provided data

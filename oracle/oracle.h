@@ -26,7 +26,9 @@
 //       driven by the synthetic stand-in for PathTrace of ref/synthetic_tracer.h) -> PINNED;
 //       the builder's last stage (PrepareForComputeAABBs + ComputeAABBs: node encoding, bottom-up climb; ref_refit.cpp) -> PINNED
 //       (child order at equal subtree sizes is arrival-order dependent in the reference: deviation D1, asserted by the test);
-//  (ii) the front of the builder (primitive load, scene AABB, sort order, treelet roots / climb order) and the camera accessors are
+//       one whole treelet pass (ClearBuffers + FindTreelets + all of TreeletReorder.hlsl incl. the climb; ref_treelet_pass.cpp),
+//       chained over the three passes: every hierarchy word -> PINNED (climbs within the reference's cap of 33);
+//  (ii) the front of the builder (primitive load, scene AABB, sort order, rearrange) and the camera accessors are
 //       HLSL that cannot be compiled here: restated, checked by the fallback layer's own
 //       validator invariants, analytic known answers and independent numpy restatements
 //       -> "parity unpinned" by reference outputs for these parts.
@@ -104,6 +106,7 @@ float hash13_public(float x, float y, float z);
 float halton_public(int b, int i);
 uint32_t morton_public(const float* centroid, const float* smin, const float* smax);
 void karras_public(const uint32_t* sortedCodes, uint32_t n, uint32_t* parentLeftRight);
+void treelet_pass_public(uint32_t* H3, const void* prims40, uint32_t n, uint32_t minTris, uint32_t* maxClimb);
 void leaf_box_public(const float* v9, float* c3, float* h3);
 void parent_box_public(const float* ac, const float* ah, const float* bc, const float* bh, float* c3, float* h3);
 void treelet_public(uint32_t* parentLeftRight, float* aabbMinMax, uint32_t n, uint32_t root);

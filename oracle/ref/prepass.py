@@ -305,6 +305,48 @@ def run_refit(helper_hlsli, prepare_hlsl, bottom_hlsl, compute_hlsli, dst_prepar
     open(dst_compute, "w").write(fix(helper + "\n" + leaf + "\n" + comp))
 
 
+def run_treelet_pass(bindings_h, treelet_hlsl, clear_hlsl, find_hlsl, helper_hlsli, compat_h, dst):
+    """One whole treelet-reorder pass: TreeletReorderBindings.h tables and helpers, RawDataToTriangle / GetTriangle
+    (RayTracingHlslCompat.h), the box helpers of RayTracingHelper.hlsli, ClearBuffers.hlsl main(), FindTreelets.hlsl
+    (ComputeLeafAABB + main()) and ALL of TreeletReorder.hlsl from CalculateCost to the end: FormTreelet,
+    FindOptimalPartitions, ReformTree, TraverseToParent and main() with its 33-iteration loop."""
+    b = open(bindings_h).read()
+    b0 = "static const uint FullTreeletSize = 7;\n"
+    assert b0 in b
+    a1 = b.index("#define BIT(x) (1 << (x))")
+    bind = b0 + b[a1:b.index("#endif", a1)]
+    c = open(compat_h).read()
+    tri = c[c.index("Triangle RawDataToTriangle(uint4 a, uint4 b, uint c)"):c.index("void TriangleToRawData(")]
+    gt = c[c.index("Triangle GetTriangle(Primitive prim)"):c.index("AABB GetProceduralPrimitiveAABB(Primitive prim)")]
+    h = open(helper_hlsli).read()
+    helper = h[h.index("#define AABB_Min_Padding 0.001"):h.index("float Determinant(in AffineMatrix transform)")]
+    cl = open(clear_hlsl).read()
+    clear = cl[cl.index("[numthreads(THREAD_GROUP_1D_WIDTH, 1, 1)]"):]
+    f = open(find_hlsl).read()
+    find = f[f.index("AABB ComputeLeafAABB(uint triangleIndex)"):]
+    t = open(treelet_hlsl).read()
+    reorder = t[t.index("static const float CostOfRayBoxIntersection"):]
+    marker = "    AABB nodeAABB = AABBBuffer[nodeIndex];"
+    assert reorder.count(marker) == 1   # wave lockstep made explicit, as in run_treelet
+    reorder = reorder.replace(marker, "    GroupMemoryBarrierWithGroupSync(); /* wave lockstep made explicit */\n" + marker)
+    for old, new, where in (("void main(uint3 DTid : SV_DispatchThreadID)", "static void clear_main(uint3 DTid)", "clear"),
+                            ("void main(uint3 DTid : SV_DispatchThreadID)", "static void find_main(uint3 DTid)", "find"),
+                            ("void main(uint3 Gid : SV_GroupID, uint3 GTid : SV_GroupThreadId)", "static void reorder_main(uint3 Gid, uint3 GTid)", "reorder")):
+        src = {"clear": clear, "find": find, "reorder": reorder}[where]
+        if old not in src:
+            raise SystemExit("prepass: entry point not found in " + where)
+        src = src.replace(old, new)
+        if where == "clear": clear = src
+        elif where == "find": find = src
+        else: reorder = src
+    text = bind + "\n" + helper + "\n" + tri + "\n" + gt + "\n" + clear + "\n" + find + "\n" + reorder
+    text = text.replace("[numthreads(THREAD_GROUP_1D_WIDTH, 1, 1)]", "").replace("[numthreads(NumThreadsInGroup, 1, 1)]", "").replace("[unroll]", "")
+    text = re.sub(r"\b(?:inout|out)\s+([A-Za-z_]\w*)\s+([A-Za-z_]\w*)", r"\1& \2", text)
+    text = re.sub(r"([(,]\s*)in[ \t]+([A-Za-z_]\w*)[ \t]+([A-Za-z_]\w*)", r"\1\2 \3", text)   # parameter lists only (comments say "in", too)
+    text = re.sub(r"\.(xyz|rgb|xy|zw)\b(?!\s*\()", r".\1()", text)
+    open(dst, "w").write(text)
+
+
 def run_frame(raygen_h, entry_hlsl, dst):
     """The per-pixel wrapper around PathTrace: Halton / Halton23, struct BlueNoiseData, ApplyLDSToNoise, the
     Resolution / DispatchIndex accessors and GetBlueNoise (RayGenCommon.h:48-122), the AOV writers OutputPrimaryAlbedo,

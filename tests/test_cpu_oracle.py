@@ -1063,3 +1063,62 @@ def test_node_encoding_and_refit_equal_reference_text(spec, passes, tmp_path, bu
         a, b = results[0][:nint, 3][tie], results[1][:nint, 3][tie]
         assert (a != b).any(), "the two schedules should disagree on some equal-size node"
     assert tie.sum() > 0 or n < 8
+
+
+@pytest.mark.parametrize("spec", ["cornell", "synthetic:showcase?tris=300&seed=2", "synthetic:blobs?copies=8&tris=1000&seed=7"])
+def test_whole_treelet_pass_equals_reference_text(spec, tmp_path, built):
+    """One whole treelet-reorder pass of the reference — ClearBuffers, FindTreelets (bottom-up boxes, triangle counts, which
+    nodes are base treelet roots) and ALL of TreeletReorder.hlsl (FormTreelet, FindOptimalPartitions, ReformTree,
+    TraverseToParent and main() with its 33-iteration climb) — compiled from the mount (oracle/_ref/libref_treelet_pass.so;
+    a group = 32 host threads with a real barrier, groups one after another) against the oracle's treelet_pass, chained
+    over the three passes of PREFER_FAST_TRACE (7, 14, 28 triangles per treelet) starting from the Karras hierarchy of the
+    oracle's sorted primitives: all 3 (2N-1) parent / left / right words identical after every pass, as long as the
+    longest climb stays within the reference's cap (deviation D2 is about longer ones); and the chain ends in the
+    hierarchy a PREFER_FAST_TRACE build of the oracle hands to ComputeAABBs."""
+    import ctypes as C
+    import tracerboy_b200 as tb
+    from oracle import binding
+    path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_treelet_pass.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_treelet_pass.so not built (needs the reference mount at build time)")
+    ref = C.CDLL(path)
+    ref.ref_treelet_pass.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    lib = binding.load()
+    lib.oracle_get_hierarchy.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.oracle_treelet_pass.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.oracle_treelet_pass.restype = None
+    if spec in NAMED:
+        scene = scene_path(NAMED[spec])
+        if scene is None:
+            pytest.skip("scene cache missing")
+    else:
+        scene = str(tmp_path / "s.tbscene")
+        tb.convert_scene(spec, scene)
+
+    def hierarchy(passes):
+        o = binding.Oracle(); o.LoadScene(scene, passes)
+        B = np.ascontiguousarray(o.GetBVH())
+        n = (B.size + 16) // 116
+        H = np.zeros(3 * (2 * n - 1), np.uint32)
+        assert lib.oracle_get_hierarchy(o.h, H.ctypes.data_as(C.c_void_p), H.size) == 0
+        return H, B, n
+    H, B, n = hierarchy(0)                                   # FAST_BUILD: the Karras hierarchy, no treelet pass
+    prims = np.ascontiguousarray(B[16 + 32 * (2 * n - 1):16 + 32 * (2 * n - 1) + 40 * n])
+    compared = 0
+    for min_tris in (7, 14, 28):
+        if min_tris > n:
+            break
+        Ho, Hr = H.copy(), H.copy()
+        climb = C.c_uint32(0)
+        lib.oracle_treelet_pass(Ho.ctypes.data_as(C.c_void_p), prims.ctypes.data_as(C.c_void_p), n, min_tris, C.byref(climb))
+        groups = ref.ref_treelet_pass(Hr.ctypes.data_as(C.c_void_p), prims.ctypes.data_as(C.c_void_p), n, min_tris)
+        assert groups >= 1
+        assert climb.value <= 32, "pick a scene whose climbs stay within the reference's cap (%d)" % climb.value
+        diff = np.flatnonzero(Ho != Hr)
+        assert diff.size == 0, "pass with %d triangles per treelet: %d words differ, first at node %d" % (min_tris, diff.size, diff[0] // 3)
+        assert (Ho != H).any() or n < 8, "the pass changed nothing"
+        H = Ho
+        compared += 1
+    assert compared >= 1
+    Hfull, _, _ = hierarchy(3)
+    assert np.array_equal(H, Hfull)
