@@ -293,6 +293,30 @@ uint32_t morton_public(const float* c, const float* mn, const float* mx) {
     return morton_code(mk3(c[0], c[1], c[2]), mk3(mn[0], mn[1], mn[2]), mk3(mx[0], mx[1], mx[2]));
 }
 
+// CalculateSceneAABBFromPrimitives.hlsl:16-40 (the reduction tree of SceneAABBCalculator.cpp:36-84 is min / max: order free)
+static void scene_box(const Prim* prims, uint32_t n, f3& smin, f3& smax) {
+    smin = mk3(FLT_MAX); smax = mk3(-FLT_MAX);
+    for (uint32_t i = 0; i < n; i++) {
+        const Prim& p = prims[i];
+        smin = min3(min3(min3(pv(p, 0), smin), pv(p, 1)), pv(p, 2));
+        smax = max3(max3(max3(pv(p, 0), smax), pv(p, 1)), pv(p, 2));
+    }
+}
+// GetCentroid, CalculateMortonCodesForPrimitives.hlsl:17-24
+static f3 centroid(const Prim& p) { return ((pv(p, 0) + pv(p, 1)) + pv(p, 2)) / 3.0f; }
+// the order the sort produces: ascending by (code, index) (BitonicSortCommon.hlsli:37-47 with NullItem = 0xffffffff)
+static bool sorts_before(uint32_t codeA, uint32_t indexA, uint32_t codeB, uint32_t indexB) {
+    return codeA != codeB ? codeA < codeB : indexA < indexB;
+}
+// test hooks
+void scene_box_public(const void* prims40, uint32_t n, float* out6) {
+    f3 a, b;
+    scene_box((const Prim*)prims40, n, a, b);
+    out6[0] = a.x; out6[1] = a.y; out6[2] = a.z; out6[3] = b.x; out6[4] = b.y; out6[5] = b.z;
+}
+void centroid_public(const void* prim40, float* out3) { f3 c = centroid(*(const Prim*)prim40); out3[0] = c.x; out3[1] = c.y; out3[2] = c.z; }
+int sorts_before_public(uint32_t codeA, uint32_t indexA, uint32_t codeB, uint32_t indexB) { return sorts_before(codeA, indexA, codeB, indexB) ? 1 : 0; }
+
 bool build_bvh(Scene& s, int treeletPasses, std::string& err) {
     // LoadPrimitives (LoadPrimitivesPass.cpp:56-169, BottomLevelLoadTriangles.hlsli:88-126)
     std::vector<Prim> prims;
@@ -318,20 +342,16 @@ bool build_bvh(Scene& s, int treeletPasses, std::string& err) {
     // up to 2^30 nodes (needed by the 20 M-triangle config).
     if (2ull * n - 1 > (1ull << 30)) { err = "too many triangles for 30-bit node indices"; return false; }
     // CalculateSceneAABBFromPrimitives.hlsl:16-40
-    f3 smin = mk3(FLT_MAX), smax = mk3(-FLT_MAX);
-    for (const Prim& p : prims) {
-        smin = min3(min3(min3(pv(p, 0), smin), pv(p, 1)), pv(p, 2));
-        smax = max3(max3(max3(pv(p, 0), smax), pv(p, 1)), pv(p, 2));
-    }
+    f3 smin, smax;
+    scene_box(prims.data(), n, smin, smax);
     // Morton codes (CalculateMortonCodesForPrimitives.hlsl:17-24)
     std::vector<uint32_t> codes(n), order(n);
     for (uint32_t i = 0; i < n; i++) {
-        f3 c = ((pv(prims[i], 0) + pv(prims[i], 1)) + pv(prims[i], 2)) / 3.0f;
-        codes[i] = morton_code(c, smin, smax);
+        codes[i] = morton_code(centroid(prims[i]), smin, smax);
         order[i] = i;
     }
     // Bitonic sort == stable sort by (code, index) (BitonicSortCommon.hlsli:37-47)
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return codes[a] < codes[b]; });
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return sorts_before(codes[a], a, codes[b], b); });
     // RearrangeTriangles.hlsl:29-36
     std::vector<Prim> sp(n);
     std::vector<Meta> sm(n);

@@ -9,6 +9,7 @@ into the repository) into text a C++ compiler accepts against hlsl_compat.h:
 
 The output goes to oracle/_ref/ (git-ignored) and is compiled there; nothing is written anywhere else.
 """
+import os
 import re
 import subprocess
 import sys
@@ -339,7 +340,19 @@ def run_treelet_pass(bindings_h, treelet_hlsl, clear_hlsl, find_hlsl, helper_hls
         if where == "clear": clear = src
         elif where == "find": find = src
         else: reorder = src
-    text = bind + "\n" + helper + "\n" + tri + "\n" + gt + "\n" + clear + "\n" + find + "\n" + reorder
+    # the builder's front, riding along because this translation unit has the shims: the sort's comparator, the
+    # centroid the Morton code is taken of, and the per-thread part of the scene box
+    srcdir = os.path.dirname(find_hlsl)
+    bs = open(os.path.join(srcdir, "BitonicSortCommon.hlsli")).read()
+    swap = bs[bs.index("bool ShouldSwap(uint A, uint B, uint indexA, uint indexB)"):]
+    swap = swap[:swap.index("\n}\n") + 3]
+    mc = open(os.path.join(srcdir, "CalculateMortonCodesForPrimitives.hlsl")).read()
+    cen = mc[mc.index("float3 GetCentroid(uint elementIndex)"):]
+    cen = cen[:cen.index("\n}\n") + 3]
+    sa = open(os.path.join(srcdir, "CalculateSceneAABBFromPrimitives.hlsl")).read()
+    box = sa[sa.index("AABB CalculateSceneAABB(uint baseElementIndex)"):]
+    box = box[:box.index("\n}\n") + 3]
+    text = bind + "\n" + helper + "\n" + tri + "\n" + gt + "\n" + clear + "\n" + find + "\n" + reorder + "\n" + swap + "\n" + cen + "\n" + box
     text = text.replace("[numthreads(THREAD_GROUP_1D_WIDTH, 1, 1)]", "").replace("[numthreads(NumThreadsInGroup, 1, 1)]", "").replace("[unroll]", "")
     text = re.sub(r"\b(?:inout|out)\s+([A-Za-z_]\w*)\s+([A-Za-z_]\w*)", r"\1& \2", text)
     text = re.sub(r"([(,]\s*)in[ \t]+([A-Za-z_]\w*)[ \t]+([A-Za-z_]\w*)", r"\1\2 \3", text)   # parameter lists only (comments say "in", too)

@@ -83,6 +83,10 @@ inline void GroupMemoryBarrierWithGroupSync() { pthread_barrier_wait(&g_barrier)
 inline void DeviceMemoryBarrierWithGroupSync() { pthread_barrier_wait(&g_barrier); }
 inline void DeviceMemoryBarrier() {}
 #define groupshared static
+static uint NullItem;                    // BitonicSortCommon.hlsli:18-21 (cbuffer): 0xffffffff = ascending (BitonicSort.cpp:87)
+#define ElementsSummedPerThread 8        // CalculateSceneAABBBindings.h:20
+inline float3 min(float3 a, float3 b);   // hlsl_compat.h
+inline float3 max(float3 a, float3 b);
 
 #include "../_ref/treelet_pass_gen.inc"
 
@@ -115,4 +119,34 @@ int ref_treelet_pass(uint32_t* H3, const void* prims40, uint32_t n, uint32_t min
     for (auto& th : pool) th.join();
     pthread_barrier_destroy(&g_barrier);
     return (int)groups;
+}
+
+// ---- the builder's front (same translation unit for its shims)
+// ShouldSwap of the bitonic network, ascending as GpuBVH2Builder.cpp:316-322 asks for it
+extern "C" __attribute__((visibility("default")))
+int ref_should_swap(uint32_t A, uint32_t B, uint32_t indexA, uint32_t indexB) {
+    refcore::NullItem = 0xffffffffu;
+    return refcore::ShouldSwap(A, B, indexA, indexB) ? 1 : 0;
+}
+extern "C" __attribute__((visibility("default")))
+void ref_centroid(const void* prim40, float* out3) {
+    using namespace refcore;
+    InputBuffer = (Primitive*)prim40;
+    float3 c = GetCentroid(0);
+    out3[0] = c.x; out3[1] = c.y; out3[2] = c.z;
+}
+// CalculateSceneAABB per thread (8 primitives each, CalculateSceneAABBFromPrimitives.hlsl), then the min / max of the
+// per-thread boxes, which is what the further reduction passes of SceneAABBCalculator.cpp:36-84 compute
+extern "C" __attribute__((visibility("default")))
+void ref_scene_box(const void* prims40, uint32_t n, float* out6) {
+    using namespace refcore;
+    InputBuffer = (Primitive*)prims40;
+    Constants.NumberOfElements = n;
+    AABB total;
+    total.min = float3(FLT_MAX, FLT_MAX, FLT_MAX); total.max = float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    for (uint32_t base = 0; base < n; base += ElementsSummedPerThread) {
+        AABB t = CalculateSceneAABB(base);
+        total.min = min(total.min, t.min); total.max = max(total.max, t.max);
+    }
+    out6[0] = total.min.x; out6[1] = total.min.y; out6[2] = total.min.z; out6[3] = total.max.x; out6[4] = total.max.y; out6[5] = total.max.z;
 }

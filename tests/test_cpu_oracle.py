@@ -1122,3 +1122,60 @@ def test_whole_treelet_pass_equals_reference_text(spec, tmp_path, built):
     assert compared >= 1
     Hfull, _, _ = hierarchy(3)
     assert np.array_equal(H, Hfull)
+
+
+def test_builder_front_equals_reference_text(built):
+    """The builder's front against the reference text compiled from the mount (oracle/_ref/libref_treelet_pass.so): the
+    bitonic network's comparator ShouldSwap (BitonicSortCommon.hlsli:37-47, ascending as GpuBVH2Builder.cpp:316-322 asks)
+    defines exactly the order the oracle sorts by — ascending (code, index), what a stable sort by code produces;
+    GetCentroid (CalculateMortonCodesForPrimitives.hlsl:17-24), whose rounding decides Morton codes; and the scene box
+    (CalculateSceneAABBFromPrimitives.hlsl per thread of 8 primitives + min / max reduction), bit for bit."""
+    import ctypes as C
+    from oracle import binding
+    path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_treelet_pass.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_treelet_pass.so not built (needs the reference mount at build time)")
+    ref = C.CDLL(path)
+    if not hasattr(ref, "ref_should_swap"):
+        pytest.skip("oracle/_ref/libref_treelet_pass.so predates the builder-front build")
+    lib = binding.load()
+    u32 = C.c_uint32
+    ref.ref_should_swap.argtypes = [u32] * 4; lib.oracle_sorts_before.argtypes = [u32] * 4
+    ref.ref_centroid.argtypes = [C.c_void_p, C.c_void_p]; lib.oracle_centroid.argtypes = [C.c_void_p, C.c_void_p]
+    ref.ref_scene_box.argtypes = [C.c_void_p, u32, C.c_void_p]; lib.oracle_scene_box.argtypes = [C.c_void_p, u32, C.c_void_p]
+    for f in (ref.ref_centroid, lib.oracle_centroid, ref.ref_scene_box, lib.oracle_scene_box):
+        f.restype = None
+    rng = np.random.default_rng(8)
+    # comparator: a swap of (A at the lower position, B at the higher) is wanted iff B's element sorts before A's
+    codes = rng.integers(0, 40, 20000).astype(np.uint32)          # many equal codes
+    codes[:2000] = rng.integers(0, 2 ** 30, 2000)
+    idx = rng.permutation(20000).astype(np.uint32)
+    for i in range(0, 19998, 2):
+        a, b, ia, ib = int(codes[i]), int(codes[i + 1]), int(idx[i]), int(idx[i + 1])
+        assert ref.ref_should_swap(a, b, ia, ib) == lib.oracle_sorts_before(b, ib, a, ia), (a, b, ia, ib)
+    assert ref.ref_should_swap(5, 5, 3, 3) == 0 and lib.oracle_sorts_before(5, 3, 5, 3) == 0
+    # a whole sort with the reference's comparator (odd-even transposition network: only adjacent compare-exchanges)
+    keys, vals = codes[:300].copy(), np.arange(300, dtype=np.uint32)
+    for rnd in range(300):
+        for j in range(rnd & 1, 299, 2):
+            if ref.ref_should_swap(int(keys[j]), int(keys[j + 1]), int(vals[j]), int(vals[j + 1])):
+                keys[j], keys[j + 1] = keys[j + 1], keys[j]; vals[j], vals[j + 1] = vals[j + 1], vals[j]
+    assert np.array_equal(vals, np.argsort(codes[:300], kind="stable").astype(np.uint32))
+    # centroid and scene box on primitives (type word + 9 floats = 40 bytes)
+    n = 1003                                                    # not a multiple of the 8 primitives a thread sums
+    prims = np.zeros((n, 10), np.float32)
+    prims.view(np.uint32)[:, 0] = 1
+    prims[:, 1:] = (rng.normal(0, 1, (n, 9)) * np.exp(rng.normal(0, 4, (n, 1)))).astype(np.float32)
+    prims[7, 1:4] = np.nan                                      # HLSL min / max drop a NaN operand
+    for i in range(n):
+        a, b = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        row = np.ascontiguousarray(prims[i])
+        lib.oracle_centroid(row.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p))
+        ref.ref_centroid(row.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+        assert ((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all(), (i, a, b)
+    for m in (1, 7, 8, 9, n):
+        a, b = np.zeros(6, np.float32), np.zeros(6, np.float32)
+        sub = np.ascontiguousarray(prims[:m])
+        lib.oracle_scene_box(sub.ctypes.data_as(C.c_void_p), m, a.ctypes.data_as(C.c_void_p))
+        ref.ref_scene_box(sub.ctypes.data_as(C.c_void_p), m, b.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (m, a, b)
