@@ -389,3 +389,107 @@ def test_camera_update_follows_tracerboy_update(built):
     lib = tb.load_library()
     assert lib.tb_camera_update(None, last, 0, 0, 0, 0, None, 0.0, None, None, None) != 0
     assert lib.tb_update(None, 0, 0, None, 0.0, None, None) != 0
+
+
+MATERIALS_PBRT = """LookAt 0 0 8  0 0 0  0 1 0
+Camera "perspective" "float fov" [40]
+WorldBegin
+Material "disney" "rgb color" [0.9 0.5 0.5] "float roughness" 0.3 "float eta" 1.4 "float metallic" 0.8
+Shape "trianglemesh" "point P" [0 0 0  1 0 0  0 1 0] "integer indices" [0 1 2]
+Material "disney" "rgb color" [0.5 0.6 0.7] "float spectrans" 0.5 "float roughness" 0.4 "float eta" 1.2
+Shape "trianglemesh" "point P" [0 0 1  1 0 1  0 1 1] "integer indices" [0 1 2]
+Material "uber" "rgb Kd" [0.1 0.2 0.3] "float roughness" 0.25 "rgb opacity" [0.5 0.5 0.5] "float index" 1.33 "rgb Kt" [0.2 0.3 0.4]
+Shape "trianglemesh" "point P" [0 0 2  1 0 2  0 1 2] "integer indices" [0 1 2]
+Material "uber" "rgb Kd" [0.3 0.2 0.1] "float roughness" 0.25 "float uroughness" 0.1 "float vroughness" 0.1
+Shape "trianglemesh" "point P" [0 0 3  1 0 3  0 1 3] "integer indices" [0 1 2]
+Material "mirror" "rgb Kr" [0.9 0.8 0.7]
+Shape "trianglemesh" "point P" [0 0 4  1 0 4  0 1 4] "integer indices" [0 1 2]
+Material "metal" "rgb eta" [0.2 0.9 1.1] "float uroughness" 0.05 "float vroughness" 0.05
+Shape "trianglemesh" "point P" [0 0 5  1 0 5  0 1 5] "integer indices" [0 1 2]
+Material "substrate" "rgb Kd" [0.4 0.5 0.6] "rgb Ks" [0.04 0.04 0.04] "float uroughness" 0.1 "float vroughness" 0.1
+Shape "trianglemesh" "point P" [0 0 6  1 0 6  0 1 6] "integer indices" [0 1 2]
+Material "glass" "float index" 1.7
+Shape "trianglemesh" "point P" [0 0 7  1 0 7  0 1 7] "integer indices" [0 1 2]
+Material "matte" "rgb Kd" [0.7 0.6 0.5] "float sigma" 20
+Shape "trianglemesh" "point P" [0 0 8  1 0 8  0 1 8] "integer indices" [0 1 2]
+Material "plastic" "rgb Kd" [0.2 0.4 0.6] "rgb Ks" [0.25 0.25 0.25] "float roughness" 0.15
+Shape "trianglemesh" "point P" [0 0 9  1 0 9  0 1 9] "integer indices" [0 1 2]
+Material "translucent" "rgb Kd" [0.2 0.2 0.2]
+Shape "trianglemesh" "point P" [0 0 10  1 0 10  0 1 10] "integer indices" [0 1 2]
+Material "hair"
+Shape "trianglemesh" "point P" [0 0 11  1 0 11  0 1 11] "integer indices" [0 1 2]
+MakeNamedMaterial "a" "string type" "matte" "rgb Kd" [0.1 0.1 0.1]
+MakeNamedMaterial "b" "string type" "mirror" "rgb Kr" [1 1 1]
+MakeNamedMaterial "m" "string type" "mix" "string namedmaterial1" "a" "string namedmaterial2" "b" "rgb amount" [0.3 0.3 0.3]
+NamedMaterial "m"
+Shape "trianglemesh" "point P" [0 0 12  1 0 12  0 1 12] "integer indices" [0 1 2]
+AttributeBegin
+AreaLightSource "diffuse" "rgb L" [5 4 3]
+Material "matte" "rgb Kd" [0.5 0.5 0.5]
+Shape "trianglemesh" "point P" [0 0 13  1 0 13  0 1 13] "integer indices" [0 1 2]
+AttributeEnd
+WorldEnd
+"""
+
+
+def test_create_material_rules(tmp_path, built):
+    """CreateMaterial (TracerBoy.cpp:273-505) through the PBRT importer, one shape per rule: disney (albedo.x >
+    0.7 forced to 0.2, metallic > 0.5, specTrans => subsurface with roughness 0), uber (uroughness wins, opacity < 1 =>
+    subsurface + single-sided with IOR = index and absorption = Kt), mirror, metal (white albedo, IOR = average eta),
+    substrate / plastic (IOR = (sqrt(ks) + 1) / (1 - sqrt(ks)), SpecularCoef = ks), glass, matte (NO_SPECULAR, sigma as
+    roughness), translucent without a map, an unsupported type (default brown), mix (sub-material indices and amount in
+    albedo, +2 materials), the LIGHT flag from an area light's emission, and NO_ALPHA everywhere (no alpha textures)."""
+    import struct
+    import tracerboy_b200 as tb
+    from tracerboy_b200 import build
+    if not os.path.exists(os.path.join(build.LIB, "libtb_pbrtimport.so")):
+        pytest.skip("PBRT importer not built (needs the reference mount at build time)")
+    src, dst = str(tmp_path / "m.pbrt"), str(tmp_path / "m.tbscene")
+    open(src, "w").write(MATERIALS_PBRT)
+    tb.convert_scene(src, dst)
+    raw = open(dst, "rb").read()
+    magic, version, flip, ng, nv, ni, nm, nl, nt, nimg, env = struct.unpack_from("<8sII7Ii", raw, 0)
+    off = 8 + 4 + 4 + 7 * 4 + 4 + 14 * 4 + 3 * 16 + 12 + 8 * 4
+    geoms = np.frombuffer(raw, np.uint32, ng * 8, off).reshape(ng, 8)
+    off += ng * 32 + nv * 12 + nv * 32 + ni * 4
+    M = np.dtype([("albedo", "3f4"), ("albedoIndex", "u4"), ("alphaIndex", "u4"), ("normalMapIndex", "u4"), ("emissiveIndex", "u4"),
+                  ("specularMapIndex", "u4"), ("IOR", "f4"), ("absorption", "3f4"), ("roughness", "f4"), ("scattering", "3f4"),
+                  ("emissive", "3f4"), ("Flags", "i4"), ("SpecularCoef", "f4")])
+    assert M.itemsize == 84
+    mats = np.frombuffer(raw, M, nm, off)
+    assert ng == 14 and nm == 16 and nt == 0           # 13 materials + 2 sub-materials of the mix + the emissive matte
+    METAL, SSS, NOSPEC, MIX, LIGHT, NOALPHA, SINGLE = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x80
+    f = np.float32
+
+    def ior(ks):
+        return f((np.sqrt(ks) + 1.0) / (1.0 - np.sqrt(ks)))
+    # per shape, in file order: albedo, IOR, roughness, flags, SpecularCoef, absorption
+    want = [((0.2, 0.2, 0.2), 1.4, 0.3, METAL | NOALPHA, 0.0, (0, 0, 0)),                      # disney, bright and metallic
+            ((0.5, 0.6, 0.7), 1.2, 0.0, SSS | NOALPHA, 0.0, (0, 0, 0)),                        # disney, specTrans
+            ((0.1, 0.2, 0.3), 1.33, 0.25, SSS | SINGLE | NOALPHA, 0.0, (0.2, 0.3, 0.4)),       # uber, opacity 0.5
+            ((0.3, 0.2, 0.1), 1.5, 0.1, NOALPHA, 0.0, (0, 0, 0)),                              # uber, uroughness
+            ((0.9, 0.8, 0.7), 1.5, 0.0, METAL | NOALPHA, 1.0, (0, 0, 0)),                      # mirror
+            ((1.0, 1.0, 1.0), f((0.2 + 0.9 + 1.1) / 3.0), 0.05, METAL | NOALPHA, 0.0, (0, 0, 0)),   # metal
+            ((0.4, 0.5, 0.6), ior(0.04), 0.1, NOALPHA, 0.04, (0, 0, 0)),                       # substrate
+            ((0.0, 0.0, 0.0), 1.7, 0.0, SSS | NOALPHA, 0.0, (0, 0, 0)),                        # glass
+            ((0.7, 0.6, 0.5), 1.5, 20.0, NOSPEC | NOALPHA, 0.0, (0, 0, 0)),                    # matte
+            ((0.2, 0.4, 0.6), ior(0.25), 0.15, NOALPHA, 0.25, (0, 0, 0)),                      # plastic
+            ((0.0, 0.0, 0.0), 1.5, 0.0, SSS | NOALPHA, 0.0, (0.001, 0.001, 0.001)),            # translucent, no map
+            ((153.0 / 255.0, 102.0 / 255.0, 58.0 / 255.0), 1.5, 0.2, NOALPHA, 0.0, (0, 0, 0))]  # unsupported type
+    for shape, (alb, io, rough, flags, spec, absorb) in enumerate(want):
+        m = mats[geoms[shape][0]]
+        assert np.allclose(m["albedo"], np.array(alb, f), rtol=0, atol=1e-7), (shape, m["albedo"])
+        assert np.isclose(m["IOR"], f(io), rtol=1e-6) and np.isclose(m["roughness"], f(rough), rtol=1e-6), (shape, m["IOR"], m["roughness"])
+        assert m["Flags"] == flags, (shape, hex(m["Flags"]))
+        assert np.isclose(m["SpecularCoef"], f(spec), rtol=1e-6) and np.allclose(m["absorption"], np.array(absorb, f)), shape
+        assert not m["emissive"].any() and not m["scattering"].any()
+        for k in ("albedoIndex", "alphaIndex", "normalMapIndex", "emissiveIndex", "specularMapIndex"):
+            assert m[k] == 0xffffffff
+    mix = mats[geoms[12][0]]
+    assert mix["Flags"] == MIX | NOALPHA and np.isclose(mix["albedo"][2], f(0.3))
+    a, b = mats[int(mix["albedo"][0])], mats[int(mix["albedo"][1])]
+    assert np.allclose(a["albedo"], f(0.1)) and a["Flags"] == NOSPEC | NOALPHA
+    assert np.allclose(b["albedo"], 1.0) and b["Flags"] == METAL | NOALPHA and b["SpecularCoef"] == 1.0
+    light = mats[geoms[13][0]]
+    assert light["Flags"] == LIGHT | NOSPEC | NOALPHA and light["emissive"].tolist() == [5.0, 4.0, 3.0]
+    assert nl == 1                                      # its one triangle is the scene's one light (TracerBoy.cpp:1780-1835)
