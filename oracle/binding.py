@@ -181,6 +181,7 @@ def load():
         lib.oracle_select_pixel.argtypes = [C.c_void_p, C.c_int, C.c_int]
         lib.oracle_set_samples.argtypes = [C.c_void_p, C.c_uint32]
         lib.oracle_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        lib.oracle_set_row_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         lib.oracle_math_eval.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         lib.oracle_math_eval.restype = None
         lib.oracle_morton.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -275,6 +276,9 @@ class Oracle:
 
     def SetFrameShard(self, offset, stride):
         self._ck(self.lib.oracle_set_shard(self.h, offset, stride))
+
+    def SetRowShard(self, offset, stride):
+        self._ck(self.lib.oracle_set_row_shard(self.h, offset, stride))
 
     def SetSamples(self, n):
         self.lib.oracle_set_samples(self.h, n)

@@ -20,6 +20,7 @@ struct OracleHandle {
     uint32_t samples = 0;
     uint32_t shardOffset = 0, shardStride = 1; // frame f = offset + local * stride (multi-process sharding tests)
     int selX = -1, selY = -1;
+    uint32_t rowOffset = 0, rowStride = 1;
 };
 
 #define ORACLE_API extern "C" __attribute__((visibility("default")))
@@ -105,6 +106,7 @@ ORACLE_API int oracle_render(OracleHandle* h, const TbOutputSettings* s, uint32_
         p.settings = *s; p.camera = h->camera; p.time = time; p.frame = h->shardOffset + h->samples * h->shardStride;
         p.clearAccum = h->samples == 0;
         p.selectedX = h->selX; p.selectedY = h->selY;
+        p.rowOffset = h->rowOffset; p.rowStride = h->rowStride;
         render_frame(h->scene, p, h->fb, threads);
         h->samples++;
     }
@@ -117,6 +119,11 @@ ORACLE_API void oracle_set_literal_mode(int mask) { oracle::set_literal_mode(mas
 ORACLE_API int oracle_set_shard(OracleHandle* h, uint32_t offset, uint32_t stride) {
     if (stride == 0 || offset >= stride) return -1;
     h->shardOffset = offset; h->shardStride = stride; h->samples = 0;
+    return 0;
+}
+ORACLE_API int oracle_set_row_shard(OracleHandle* h, uint32_t offset, uint32_t stride) { // tb_set_row_shard
+    if (stride == 0 || offset >= stride) return -1;
+    h->rowOffset = offset; h->rowStride = stride; h->samples = 0;
     return 0;
 }
 // pinned intrinsics and noise functions, exposed so tests can pin them against independent numpy restatements

@@ -645,6 +645,7 @@ void render_frame(const Scene& s, const RenderParams& p, FrameBuffers& fb, int n
 #endif
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : rays, tris, boxes)
     for (int64_t y = 0; y < (int64_t)H; y++) {
+        if (((uint32_t)y / 8u) % p.rowStride != p.rowOffset) continue; // another shard's band: its pixels stay untouched (zero)
         for (uint32_t x = 0; x < W; x++) {
             Ctx c(s, p);
             c.W = W; c.H = H; c.px = x; c.py = (uint32_t)y;

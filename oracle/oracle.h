@@ -98,6 +98,7 @@ struct RenderParams {
     uint32_t frame = 0; // GlobalFrameCount
     bool clearAccum = true; // first frame after an invalidate (== frame 0 unless sample-sharded)
     int selectedX = -1, selectedY = -1;
+    uint32_t rowOffset = 0, rowStride = 1; // row-band sharding (partitioning 1): bands of 8 rows, band b on shard b mod rowStride
 };
 
 // One SoftwareRayTraceCS dispatch (SoftwareRayTraceCS.hlsl:9-51): one sample per pixel.

@@ -159,6 +159,44 @@ def test_sample_sharding_world_size_2_gloo(cornell, tmp_path):
     assert "SHARD_OK" in outs[0]
 
 
+ROW_SHARD_SCRIPT = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+import tracerboy_b200 as tb
+from oracle.binding import Oracle
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+s = tb.get_default_output_settings(); s.MaxBounces = 3
+o = Oracle(); o.LoadScene(%(scene)r, 3); o.Resize(40, 44)      # 5.5 bands of 8 rows
+o.SetRowShard(rank, 2)              # band b on rank b mod N, as bench.py --shard rows / tb_set_row_shard do
+o.Render(s, 4, 0.0)                 # all 4 frames, this rank's bands only
+acc = torch.from_numpy(o.Readback(0).copy())
+own = ((np.arange(44) // 8) %% 2) == rank
+assert not acc.numpy()[~own].any() and acc.numpy()[own][..., 3].all()
+dist.all_reduce(acc)                # the path's one exchange step: every pixel is non-zero on exactly one rank
+if rank == 0:
+    ref = Oracle(); ref.LoadScene(%(scene)r, 3); ref.Resize(40, 44); ref.Render(s, 4, 0.0)
+    want = ref.Readback(0)
+    assert np.array_equal(acc.numpy().view(np.uint32), want.view(np.uint32))   # x + 0 = x: bit-identical to one process
+    print("ROW_SHARD_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_row_band_sharding_world_size_2_gloo(cornell, tmp_path):
+    """The other partitioning of SURVEY 8e: bands of 8 rows interleaved over the ranks, one all-reduce of the accumulation
+    buffer; every pixel is computed entirely by one rank, so the sum is bit-identical to the single-process image.
+    Two processes over gloo on the CPU (the GPU version of this property is test_row_band_sharding_is_bit_identical)."""
+    script = tmp_path / "rows.py"
+    script.write_text(ROW_SHARD_SCRIPT % {"root": ROOT, "port": 31000 + os.getpid() % 2000, "scene": cornell})
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "ROW_SHARD_OK" in outs[0]
+
+
 CURVES_PBRT = """LookAt 0 0 8  1.5 0.5 0  0 1 0
 Camera "perspective" "float fov" [40]
 WorldBegin
