@@ -381,6 +381,40 @@ def test_api_state_errors_and_materials(cornell):
     assert st.SelectedPixelDistance > 0 and 0 <= st.SelectedMaterialID < 8
 
 
+def test_load_status_is_published_to_a_polling_thread(teapot, tmp_path):
+    """The threading contract of the boundary: LoadScene runs on a worker thread (D3D12App.cpp:53-67) while
+    another thread polls the SceneLoadStatus (TracerBoy.h:114-128). States only move forward, the load ends in
+    LoadFinished with every instance counted, the scene renders afterwards; a failing load ends in LoadFailed."""
+    import threading
+    import tracerboy_b200 as tb
+    if teapot is None:
+        pytest.skip("scene cache missing")
+    IDLE, LOADING_PBRT, LOADING_HOST, RECORDING, WAITING, FINISHED, FAILED = range(7)   # TbSceneLoadState
+    g = tb.TracerBoy(0)
+    assert g.GetSceneLoadStatus().State == IDLE
+    seen, done = [], threading.Event()
+
+    def worker():
+        try:
+            g.LoadScene(teapot)          # ctypes releases the GIL for the duration of the call
+        finally:
+            done.set()
+    t = threading.Thread(target=worker)
+    t.start()
+    while not done.is_set():
+        seen.append(g.GetSceneLoadStatus().State)
+    t.join()
+    last = g.GetSceneLoadStatus()
+    seen.append(last.State)
+    assert all(a <= b for a, b in zip(seen, seen[1:])), "states went backwards: %s" % sorted(set(seen))
+    assert last.State == FINISHED and last.InstancesLoaded == last.TotalInstances == g.GetSceneInfo().NumGeometries
+    g.Resize(32, 32)
+    g.Render(tb.get_default_output_settings(), 1, 0.0)
+    with pytest.raises(tb.TracerBoyError):
+        g.LoadScene(str(tmp_path / "missing.tbscene"))
+    assert g.GetSceneLoadStatus().State == FAILED
+
+
 def test_update_moves_the_camera_and_invalidates_history(cornell):
     """TracerBoy::Update on a handle: an idle call changes nothing and keeps the history; W moves Position and LookAt
     along the view direction, invalidates the history, and the next render is the one tb_set_camera gives for that
