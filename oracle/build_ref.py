@@ -95,6 +95,32 @@ def build_treelet_pass(force=False):
     return target
 
 
+def load_lib_path():
+    return os.path.join(OUT, "libref_load.so")
+
+
+def build_load(force=False):
+    """oracle/_ref/libref_load.so: BottomLevelLoadTriangles.hlsli (three index-format variants) as host C++."""
+    src = "/root/reference/D3D12RaytracingFallback/src/"
+    files = [src + f for f in ("BottomLevelLoadTriangles.hlsli", "LoadPrimitivesBindings.h", "RayTracingHlslCompat.h")]
+    target = load_lib_path()
+    if not all(os.path.exists(f) for f in files):
+        return target if os.path.exists(target) else None
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_load.cpp")] + files
+    if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs):
+        return target
+    sys.path.insert(0, os.path.join(HERE, "ref"))
+    import prepass
+    prepass.run_load(files[0], files[1], files[2], os.path.join(OUT, "load_common_gen.inc"), os.path.join(OUT, "load_variant_gen.inc"))
+    cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma", "-ffp-contract=off", "-fsingle-precision-constant", "-fno-fast-math",
+           "-fvisibility=hidden", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + HERE, os.path.join(HERE, "ref", "ref_load.cpp"), "-o", target]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref load build failed:\n" + r.stdout)
+    return target
+
+
 def refit_lib_path():
     return os.path.join(OUT, "libref_refit.so")
 
@@ -396,6 +422,7 @@ if __name__ == "__main__":
     print(build_temporal(force="--force" in sys.argv))
     print(build_frame(force="--force" in sys.argv))
     print(build_refit(force="--force" in sys.argv))
+    print(build_load(force="--force" in sys.argv))
     print(build_treelet_pass(force="--force" in sys.argv))
     print(build_hist(force="--force" in sys.argv))
     print(build_raygen(force="--force" in sys.argv))

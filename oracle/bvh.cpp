@@ -293,6 +293,28 @@ uint32_t morton_public(const float* c, const float* mn, const float* mx) {
     return morton_code(mk3(c[0], c[1], c[2]), mk3(mn[0], mn[1], mn[2]), mk3(mx[0], mx[1], mx[2]));
 }
 
+// LoadPrimitives (LoadPrimitivesPass.cpp:56-169, BottomLevelLoadTriangles.hlsli:88-126): triangle soup in geometry order
+static void load_primitives(const Scene& s, std::vector<Prim>& prims, std::vector<Meta>& meta) {
+    for (size_t g = 0; g < s.geoms.size(); g++) {
+        const TbGeometryRecord& G = s.geoms[g];
+        for (uint32_t t = 0; t < G.IndexCount / 3; t++) {
+            Prim p;
+            p.type = 1;
+            for (int k = 0; k < 3; k++) {
+                const TbFloat3& v = s.positions[G.VertexFirst + s.indices[G.IndexFirst + 3 * t + k]];
+                p.v[3 * k] = v.x; p.v[3 * k + 1] = v.y; p.v[3 * k + 2] = v.z;
+            }
+            prims.push_back(p);
+            meta.push_back({(uint32_t)g, t, G.GeometryFlags});
+        }
+    }
+}
+void load_primitives_public(const Scene& s, void* prims40, void* meta12) { // test hook
+    std::vector<Prim> prims; std::vector<Meta> meta;
+    load_primitives(s, prims, meta);
+    memcpy(prims40, prims.data(), sizeof(Prim) * prims.size());
+    memcpy(meta12, meta.data(), sizeof(Meta) * meta.size());
+}
 // CalculateSceneAABBFromPrimitives.hlsl:16-40 (the reduction tree of SceneAABBCalculator.cpp:36-84 is min / max: order free)
 static void scene_box(const Prim* prims, uint32_t n, f3& smin, f3& smax) {
     smin = mk3(FLT_MAX); smax = mk3(-FLT_MAX);
@@ -318,22 +340,9 @@ void centroid_public(const void* prim40, float* out3) { f3 c = centroid(*(const 
 int sorts_before_public(uint32_t codeA, uint32_t indexA, uint32_t codeB, uint32_t indexB) { return sorts_before(codeA, indexA, codeB, indexB) ? 1 : 0; }
 
 bool build_bvh(Scene& s, int treeletPasses, std::string& err) {
-    // LoadPrimitives (LoadPrimitivesPass.cpp:56-169, BottomLevelLoadTriangles.hlsli:88-126)
     std::vector<Prim> prims;
     std::vector<Meta> meta;
-    for (size_t g = 0; g < s.geoms.size(); g++) {
-        const TbGeometryRecord& G = s.geoms[g];
-        for (uint32_t t = 0; t < G.IndexCount / 3; t++) {
-            Prim p;
-            p.type = 1;
-            for (int k = 0; k < 3; k++) {
-                const TbFloat3& v = s.positions[G.VertexFirst + s.indices[G.IndexFirst + 3 * t + k]];
-                p.v[3 * k] = v.x; p.v[3 * k + 1] = v.y; p.v[3 * k + 2] = v.z;
-            }
-            prims.push_back(p);
-            meta.push_back({(uint32_t)g, t, G.GeometryFlags});
-        }
-    }
+    load_primitives(s, prims, meta);
     const uint32_t n = (uint32_t)prims.size();
     if (n == 0) { err = "scene has no triangles"; return false; }
     // The reference keeps 24-bit child / leaf indices (RayTracingHelper.hlsli:97-103), which

@@ -28,8 +28,8 @@
 //       (child order at equal subtree sizes is arrival-order dependent in the reference: deviation D1, asserted by the test);
 //       one whole treelet pass (ClearBuffers + FindTreelets + all of TreeletReorder.hlsl incl. the climb; ref_treelet_pass.cpp),
 //       chained over the three passes: every hierarchy word -> PINNED (climbs within the reference's cap of 33);
-//       the builder's front: scene box, centroid, the bitonic comparator ShouldSwap (same library) -> PINNED;
-//  (ii) data movement of the builder (triangle load, bitonic exchange schedule, rearrange copy) and the camera accessors are
+//       the builder's front: primitive load (ref_load.cpp), scene box, centroid, the bitonic comparator ShouldSwap -> PINNED;
+//  (ii) the bitonic exchange schedule, the rearrange copy, host dispatch loops and the camera accessors are
 //       HLSL that cannot be compiled here: restated, checked by the fallback layer's own
 //       validator invariants, analytic known answers and independent numpy restatements
 //       -> "parity unpinned" by reference outputs for these parts.
@@ -108,6 +108,7 @@ float hash13_public(float x, float y, float z);
 float halton_public(int b, int i);
 uint32_t morton_public(const float* centroid, const float* smin, const float* smax);
 void karras_public(const uint32_t* sortedCodes, uint32_t n, uint32_t* parentLeftRight);
+void load_primitives_public(const Scene& s, void* prims40, void* meta12);
 void scene_box_public(const void* prims40, uint32_t n, float* out6);
 void centroid_public(const void* prim40, float* out3);
 int sorts_before_public(uint32_t codeA, uint32_t indexA, uint32_t codeB, uint32_t indexB);

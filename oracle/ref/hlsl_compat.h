@@ -39,6 +39,9 @@ struct float3 {
     float3 xyz() const { return *this; }
     float3 rgb() const { return *this; }
     float3 yzx() const { return float3(y, z, x); }
+#ifdef RC_LOAD
+    float2 yz() const { return float2(y, z); }                        // tri.v1.yz (RayTracingHlslCompat.h:113)
+#endif
 #ifdef RC_TRAVERSE
     float3(float x_, float2 yz) : x(x_), y(yz.x), z(yz.y) {}          // float3(a.w, b.xy) (RayTracingHelper.hlsli:223)
     void set_xy(float2 v) { x = v.x; y = v.y; }                      // `A.xy = ...` (TraverseFunction.hlsli:257-259)
@@ -51,6 +54,9 @@ struct float4 {
     float4(float s) : x(s), y(s), z(s), w(s) {}
     float4(float x_, float y_, float z_, float w_) : x(x_), y(y_), z(z_), w(w_) {}
     float4(float3 v, float w_) : x(v.x), y(v.y), z(v.z), w(w_) {}
+#ifdef RC_LOAD
+    float4(float2 a, float2 b) : x(a.x), y(a.y), z(b.x), w(b.y) {}  // float4(tri.v1.yz, tri.v2.xy) (RayTracingHlslCompat.h:113)
+#endif
     float2 xy() const { return float2(x, y); }
     float3 xyz() const { return float3(x, y, z); }
     float3 rgb() const { return float3(x, y, z); }

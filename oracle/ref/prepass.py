@@ -360,6 +360,37 @@ def run_treelet_pass(bindings_h, treelet_hlsl, clear_hlsl, find_hlsl, helper_hls
     open(dst, "w").write(text)
 
 
+def run_load(load_hlsli, bindings_h, compat_h, dst_common, dst_variant):
+    """The builder's first stage, BottomLevelLoadTriangles.hlsli: the index readers (32-bit, 16-bit with its 2-byte-aligned
+    start, none), GetVertex, TransformVertex and main(); GetOutputIndex / StorePrimitiveMetadata of
+    LoadPrimitivesBindings.h; TriangleToRawData / NullPrimitive / CreateTrianglePrimitive of RayTracingHlslCompat.h.
+    dst_common holds what does not depend on the index format; dst_variant holds GetIndex + main(), which the three
+    LoadTriangles*.hlsl files compile with INDEX_BUFFER_32_BIT / INDEX_BUFFER_16_BIT / NO_INDEX_BUFFER."""
+    c = open(compat_h).read()
+    raw = c[c.index("void TriangleToRawData("):c.index("#else", c.index("void TriangleToRawData("))]
+    nullp = c[c.index("Primitive NullPrimitive()"):c.index("Primitive CreateProceduralGeometryPrimitive(AABB aabb)")]
+    create = c[c.index("Primitive CreateTrianglePrimitive(Triangle tri)"):c.index("Triangle GetTriangle(Primitive prim)")]
+    b = open(bindings_h).read()
+    bind = b[b.index("uint GetOutputIndex(uint inputIndex)"):b.rindex("#endif")]
+    t = open(load_hlsli).read()
+    readers = t[t.index("uint3 GetUint32Index3("):t.index("uint3 GetIndex(uint threadIndex)")]
+    rest = t[t.index("float3 GetVertex(ByteAddressBuffer VertexBuffer, uint index, uint stride)"):t.index("[numthreads(THREAD_GROUP_1D_WIDTH, 1, 1)]")]
+    getindex = t[t.index("uint3 GetIndex(uint threadIndex)"):t.index("float3 GetVertex(ByteAddressBuffer VertexBuffer, uint index, uint stride)")]
+    main = t[t.index("[numthreads(THREAD_GROUP_1D_WIDTH, 1, 1)]"):]
+    main = main.replace("[numthreads(THREAD_GROUP_1D_WIDTH, 1, 1)]", "")
+    if "void main( uint3 DTid : SV_DispatchThreadID )" not in main:
+        raise SystemExit("prepass: load entry point not found")
+    main = main.replace("void main( uint3 DTid : SV_DispatchThreadID )", "static void load_main(uint3 DTid)")
+
+    def fix(text):
+        text = re.sub(r"([(,]\s*)(?:inout|out)\s+([A-Za-z_]\w*)\s+([A-Za-z_]\w*)", r"\1\2& \3", text)
+        text = re.sub(r"([(,]\s*)in[ \t]+([A-Za-z_]\w*)[ \t]+([A-Za-z_]\w*)", r"\1\2 \3", text)
+        text = re.sub(r"\.(xyz|rgb|xy|zw|yz)\b(?!\s*\()", r".\1()", text)
+        return text
+    open(dst_common, "w").write(fix(raw + "\n" + nullp + "\n" + create + "\n" + bind + "\n" + readers + "\n" + rest))
+    open(dst_variant, "w").write(fix(getindex + "\n" + main))
+
+
 def run_frame(raygen_h, entry_hlsl, dst):
     """The per-pixel wrapper around PathTrace: Halton / Halton23, struct BlueNoiseData, ApplyLDSToNoise, the
     Resolution / DispatchIndex accessors and GetBlueNoise (RayGenCommon.h:48-122), the AOV writers OutputPrimaryAlbedo,

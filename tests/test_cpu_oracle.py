@@ -1179,3 +1179,77 @@ def test_builder_front_equals_reference_text(built):
         lib.oracle_scene_box(sub.ctypes.data_as(C.c_void_p), m, a.ctypes.data_as(C.c_void_p))
         ref.ref_scene_box(sub.ctypes.data_as(C.c_void_p), m, b.ctypes.data_as(C.c_void_p))
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (m, a, b)
+
+
+def test_primitive_load_equals_reference_text(tmp_path, built):
+    """The builder's first stage — BottomLevelLoadTriangles.hlsli (index readers for 32-bit, 16-bit incl. a 2-byte-aligned
+    start, and absent index buffers; GetVertex; main()) with StorePrimitiveMetadata and CreateTrianglePrimitive, driven by
+    the restated dispatch loop of LoadPrimitivesPass.cpp:70-166 — compiled from the mount (oracle/_ref/libref_load.so),
+    against the oracle's primitive / metadata lists on whole scenes (40-byte primitives and 12-byte metadata, byte for
+    byte: geometry order, GeometryContributionToHitGroupIndex = geometry index, PrimitiveIndex local to the geometry) and
+    against numpy for the index formats and the per-geometry transform the oracle's .tbscene path never sees."""
+    import ctypes as C
+    import tracerboy_b200 as tb
+    from oracle import binding
+    path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_load.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_load.so not built (needs the reference mount at build time)")
+    ref = C.CDLL(path)
+
+    class Desc(C.Structure):
+        _fields_ = [("positions", C.c_void_p), ("strideBytes", C.c_uint32), ("vertexCount", C.c_uint32), ("indices", C.c_void_p),
+                    ("indexFormat", C.c_uint32), ("indexCount", C.c_uint32), ("transform3x4", C.c_void_p), ("geometryFlags", C.c_uint32)]
+    ref.ref_load_primitives.argtypes = [C.POINTER(Desc), C.c_uint32, C.c_void_p, C.c_void_p]
+    lib = binding.load()
+    lib.oracle_scene_arrays.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.oracle_scene_positions.restype = C.c_void_p; lib.oracle_scene_positions.argtypes = [C.c_void_p]
+    lib.oracle_load_primitives.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]; lib.oracle_load_primitives.restype = None
+    lib.oracle_num_triangles.argtypes = [C.c_void_p]
+    # 1) whole scenes: the descs a maintainer would pass for the oracle's pooled arrays
+    for spec in ("cornell", "synthetic:showcase?tris=300&seed=2", "synthetic:blobs?copies=8&tris=500&seed=4"):
+        scene = scene_path(NAMED[spec]) if spec in NAMED else str(tmp_path / "s.tbscene")
+        if spec not in NAMED:
+            tb.convert_scene(spec, scene)
+        o = binding.Oracle(); o.LoadScene(scene, 0)
+        n = lib.oracle_num_triangles(o.h)
+        geoms, ng, idx, vtx = C.c_void_p(), C.c_uint32(), C.c_void_p(), C.c_void_p()
+        lib.oracle_scene_arrays(o.h, C.byref(geoms), C.byref(ng), C.byref(idx), C.byref(vtx))
+        G = np.ctypeslib.as_array(C.cast(geoms, C.POINTER(C.c_uint32)), (ng.value, 8))   # TbGeometryRecord: material, VertexFirst, VertexCount, IndexFirst, IndexCount, flags, index, pad
+        pos = lib.oracle_scene_positions(o.h)
+        descs = (Desc * ng.value)()
+        for g in range(ng.value):
+            descs[g] = Desc(pos + 12 * int(G[g, 1]), 12, int(G[g, 2]), idx.value + 4 * int(G[g, 3]), 4, int(G[g, 4]), None, int(G[g, 5]))
+        p_o, m_o = np.zeros((n, 10), np.uint32), np.zeros((n, 3), np.uint32)
+        p_r, m_r = np.zeros((n, 10), np.uint32), np.zeros((n, 3), np.uint32)
+        lib.oracle_load_primitives(o.h, p_o.ctypes.data_as(C.c_void_p), m_o.ctypes.data_as(C.c_void_p))
+        assert ref.ref_load_primitives(descs, ng.value, p_r.ctypes.data_as(C.c_void_p), m_r.ctypes.data_as(C.c_void_p)) == n
+        assert np.array_equal(p_o, p_r) and np.array_equal(m_o, m_r), spec
+        assert (p_r[:, 0] == 1).all() and len(np.unique(m_r[:, 0])) == ng.value
+    # 2) index formats and the transform, against numpy
+    rng = np.random.default_rng(2)
+    verts = rng.normal(0, 3, (50, 4)).astype(np.float32)              # stride 16: DXGI_FORMAT_R32G32B32A32_FLOAT is allowed
+    tris = rng.integers(0, 50, (7, 3))                                  # an odd number of triangles: 21 indices
+    raw = np.zeros(64, np.uint16)
+    cases = []
+    for start in (0, 1):                                                # a 4-byte aligned and a 2-byte aligned 16-bit index buffer
+        buf = raw.copy(); buf[start:start + 21] = tris.ravel()
+        cases.append(("u16@%d" % (2 * start), buf, buf.ctypes.data + 2 * start, 2, 21, tris))
+    i32 = np.ascontiguousarray(tris.ravel().astype(np.uint32))
+    cases.append(("u32", i32, i32.ctypes.data, 4, 21, tris))
+    cases.append(("none", None, None, 0, 0, np.arange(48).reshape(16, 3)))   # 50 vertices -> 16 triangles, two vertices ignored
+    M = rng.normal(0, 1, (3, 4)).astype(np.float32)
+    for name, keep, iptr, fmt, icount, want_idx in cases:
+        for xf in (None, M):
+            d = (Desc * 1)(Desc(verts.ctypes.data, 16, 50, iptr, fmt, icount, xf.ctypes.data if xf is not None else None, 3))
+            nt = want_idx.shape[0]
+            p, m = np.zeros((nt, 10), np.float32), np.zeros((nt, 3), np.uint32)
+            assert ref.ref_load_primitives(d, 1, p.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p)) == nt, name
+            v = verts[want_idx.ravel(), :3]
+            if xf is not None:
+                x, y, z = v[:, 0:1], v[:, 1:2], v[:, 2:3]
+                v = ((xf[None, :, 0] * x + xf[None, :, 1] * y) + xf[None, :, 2] * z) + xf[None, :, 3]   # float32, left to right
+            assert np.array_equal(p[:, 1:].view(np.uint32), v.reshape(nt, 9).astype(np.float32).view(np.uint32)), name
+            assert (p.view(np.uint32)[:, 0] == 1).all() and (m[:, 0] == 0).all() and np.array_equal(m[:, 1], np.arange(nt)) and (m[:, 2] == 3).all()
+    # 3) E_INVALIDARG: an index format without an index buffer (LoadPrimitivesPass.cpp:77-80)
+    bad = (Desc * 1)(Desc(verts.ctypes.data, 16, 50, None, 4, 21, None, 0))
+    assert ref.ref_load_primitives(bad, 1, p.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p)) == -1

@@ -206,6 +206,7 @@ def build_all(force=False, verbose=False):
     build_ref.build_hist(force)
     build_ref.build_frame(force)
     build_ref.build_refit(force)
+    build_ref.build_load(force)
     build_ref.build_treelet_pass(force)
 
 
