@@ -267,7 +267,9 @@ typedef enum TbBufferKind {
     /* written by tb_postprocess */
     TB_BUF_POSTPROCESS_RGBA = 10,   /* float4: PostProcessCS output before the back-buffer format conversion (PostProcessCS.hlsl:195) */
     TB_BUF_BACKBUFFER_RGBA8 = 11,   /* uchar4: the same after the UNORM8 store, i.e. what lands in m_pPostProcessOutput */
-    TB_BUF_LUMINANCE_HISTOGRAM = 12 /* uint32[256] LuminanceHistogram + 1 float AveragedLuminance (1028 bytes) */
+    TB_BUF_LUMINANCE_HISTOGRAM = 12,/* uint32[256] LuminanceHistogram + 1 float AveragedLuminance (1028 bytes) */
+    /* multi-GPU: this rank's own accumulation buffer (kinds 0-2 serve the job-wide image once a communicator is attached) */
+    TB_BUF_LOCAL_ACCUM_RGBW = 13
 } TbBufferKind;
 
 /* ----------------------------------------------------------- SW-RT boundary */
@@ -291,11 +293,15 @@ typedef enum TbBvhBuildFlags {
     TB_BVH_BUILD_PREFER_FAST_BUILD = 0x8  /* 0 treelet passes */
 } TbBvhBuildFlags;
 
-/* GetRaytracingAccelerationStructurePrebuildInfo (D3D12RaytracingFallback.h:134-136) */
+/* GetRaytracingAccelerationStructurePrebuildInfo (D3D12RaytracingFallback.h:134-136). The caller allocates
+ * ResultDataMaxSizeInBytes for `dst` and ScratchDataSizeInBytes for `scratch` of tb_bvh_build_device, both
+ * 256-byte aligned device memory. The result starts with the reference layout (116 N - 16 bytes,
+ * GpuBVH2Builder.cpp:459 = ReferenceLayoutSizeInBytes) and continues with this library's traversal layout. */
 typedef struct TbPrebuildInfo {
-    uint64_t ResultDataMaxSizeInBytes; /* 116*N - 16, GpuBVH2Builder.cpp:459 */
+    uint64_t ResultDataMaxSizeInBytes;
     uint64_t ScratchDataSizeInBytes;
     uint64_t UpdateScratchDataSizeInBytes;
+    uint64_t ReferenceLayoutSizeInBytes; /* 116*N - 16 */
 } TbPrebuildInfo;
 
 /* RayDesc as consumed by SoftwareRayQuery::TraceRayInline (TraverseFunction.hlsli:39-132) */
@@ -336,6 +342,18 @@ typedef struct TbRenderStats {
     double ResumeMilliseconds;
 } TbRenderStats;
 
+/* Multi-GPU: how the frame is partitioned over the ranks of a communicator. */
+#define TB_SHARD_SAMPLES 1u /* rank r renders frames r, r+N, ...; reduction = all-gather + sum in fixed rank order */
+#define TB_SHARD_ROWS 2u    /* bands of 8 rows, band b on rank b mod N; reduction = gather of the owned bands (bit-identical to one GPU) */
+#define TB_COMM_ID_BYTES 128 /* sizeof(ncclUniqueId) */
+
+typedef struct TbCommInfo {
+    uint32_t Rank, NumRanks, ShardMode, NcclVersion;
+    uint64_t Reductions;                 /* tb_comm_reduce calls so far */
+    uint64_t BytesReceivedPerReduction;  /* over NVLink, per rank */
+    double LastReductionMilliseconds;    /* CUDA events around pack + all-gather + combine */
+} TbCommInfo;
+
 typedef struct TbHandle TbHandle; /* opaque; owns all device memory */
 
 /* ---------------------------------------------------------------- lifecycle */
@@ -345,6 +363,10 @@ TB_API int tb_create(int device, TbHandle** out);
 TB_API void tb_destroy(TbHandle* h);
 TB_API const char* tb_last_error(TbHandle* h); /* h may be NULL: last create error */
 TB_API const char* tb_version(void);
+/* Largest triangle count of one acceleration structure (37 025 580): the reference layout stores 32-bit byte
+ * offsets (RayTracingHlslCompat.h:344-398), so its 116 N - 16 bytes must stay below 4 GiB. Larger inputs are
+ * rejected with TB_ERR_INVALID_ARG by tb_load_scene / tb_bvh_build / tb_bvh_prebuild_info. */
+TB_API uint64_t tb_max_triangles(void);
 
 /* ------------------------------------------------------------- scene + bvh */
 /* TracerBoy::LoadScene (TracerBoy.cpp:1065-2161). Accepts
@@ -421,6 +443,25 @@ TB_API int tb_set_shadow_mode(TbHandle* h, int mode);
 TB_API int tb_set_ray_sort(TbHandle* h, int mode);
 TB_API int tb_synchronize(TbHandle* h);
 
+/* --------------------------------------------------------------- multi-GPU */
+/* One process per GPU, one handle per process (the reference has no multi-GPU path; SURVEY §8b asks for "one CUDA
+ * stream per device + one NCCL communicator" behind the boundary). Rank 0 obtains an id (ncclGetUniqueId) and hands
+ * its TB_COMM_ID_BYTES bytes to the other processes by whatever means the host has (MPI, torch.distributed, a file);
+ * every process then calls tb_comm_init on its handle (ncclCommInitRank on the handle's device), which also sets the
+ * handle's shard (tb_set_frame_shard / tb_set_row_shard) to (rank, nranks). Scene and BVH are replicated: every rank
+ * loads the same scene; the build is deterministic. NCCL is loaded at run time (libnccl.so.2; TB_NCCL_LIB overrides). */
+TB_API int tb_comm_get_unique_id(void* id, uint64_t bytes);
+TB_API int tb_comm_init(TbHandle* h, const void* id, int rank, int nranks, uint32_t shardMode);
+TB_API int tb_comm_destroy(TbHandle* h);
+TB_API int tb_comm_info(TbHandle* h, TbCommInfo* out);
+/* The path's only exchange step, COLLECTIVE (every rank calls it): combines the ranks' float4 accumulation buffers
+ * (OutputTexture and JitteredOutputTexture) into the job-wide image on every rank, deterministically (see
+ * TB_SHARD_*). Afterwards tb_readback / tb_device_buffer / tb_save_image of TB_BUF_ACCUM_RGBW, TB_BUF_JITTERED_RGBW
+ * and TB_BUF_RESOLVED_RGB, and tb_postprocess of the Lit output, serve the job-wide image. On a handle with a
+ * communicator those calls run the reduction themselves when frames were rendered since the last one, which makes
+ * THEM collective too. */
+TB_API int tb_comm_reduce(TbHandle* h);
+
 /* ------------------------------------------------------------ post-process */
 /* The step right after the path: auto exposure (GenerateHistogramCS.hlsl,
  * CalculateAveragedLuminanceCS.hlsl; host side TracerBoy.cpp:2948-3039) and PostProcessCS.hlsl
@@ -467,6 +508,25 @@ TB_API int tb_bvh_prebuild_info(const TbGeometryDesc* geoms, uint32_t n, TbPrebu
 TB_API int tb_bvh_build(TbHandle* h, const TbGeometryDesc* geoms, uint32_t n, uint32_t bvhBuildFlags);
 /* SoftwareRayQuery::TraceRayInline + Proceed for n rays (host arrays). */
 TB_API int tb_trace_rays(TbHandle* h, const TbRay* rays, uint64_t n, TbHit* hits);
+/* The same two calls with the reference's ownership model (D3D12RaytracingFallback.h:83-84, 134-136:
+ * BuildRaytracingAccelerationStructure(desc) with caller-allocated DestAccelerationStructureData and
+ * ScratchAccelerationStructureData GPU VAs). Every pointer inside `geoms` (Positions, Indices, Transform3x4) is a
+ * DEVICE pointer on the handle's device; `dst` / `scratch` are caller-owned device memory sized by
+ * tb_bvh_prebuild_info (scratch may be NULL: the library then allocates its own for the duration of the call);
+ * `cudaStream` is a cudaStream_t (NULL = the handle's stream). The build runs on that stream and the call returns
+ * when it has completed. The handle's scene is not touched. Indices are not range-checked (as in the reference). */
+TB_API int tb_bvh_build_device(TbHandle* h, const TbGeometryDesc* geoms, uint32_t n, uint32_t bvhBuildFlags, void* dst,
+                               uint64_t dstBytes, void* scratch, uint64_t scratchBytes, void* cudaStream);
+/* n ray queries against a caller-owned acceleration structure (`as` = a dst of tb_bvh_build_device, also one built
+ * by another handle on the same device; NULL = the handle's scene), rays and hits in DEVICE memory. Enqueued on
+ * `cudaStream` and NOT synchronised: it orders with the caller's other work on that stream like a dispatch. */
+TB_API int tb_trace_rays_device(TbHandle* h, const void* as, uint64_t asBytes, const TbRay* dRays, uint64_t n, TbHit* dHits,
+                                void* cudaStream);
+/* Drop the handle's cached description of a caller-owned acceleration structure (call before freeing / reusing dst). */
+TB_API int tb_bvh_forget_device(TbHandle* h, const void* as);
+/* Height of the scene's BVH (0 = a single leaf). The traversal keeps at most one waiting node per level; a tree deeper
+ * than its 96-entry stack is rejected at build time (TB_ERR_NOT_IMPL) rather than traversed lossily. */
+TB_API int tb_get_bvh_depth(TbHandle* h, uint32_t* depth);
 
 #ifdef __cplusplus
 }

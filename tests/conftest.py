@@ -13,6 +13,7 @@ CACHE = os.path.join(ROOT, "scenes", "_cache")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: minutes of CPU oracle work (runs with TB_RUN_SLOW=1)")
 
 
 def scene_path(name):

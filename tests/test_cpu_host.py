@@ -68,7 +68,9 @@ def test_product_does_not_reference_the_oracle():
 
 
 def test_prebuild_info(built):
-    """GetRaytracingAccelerationStructurePrebuildInfo: result size 116 N - 16 (GpuBVH2Builder.cpp:459)."""
+    """GetRaytracingAccelerationStructurePrebuildInfo: the reference layout is 116 N - 16 bytes (GpuBVH2Builder.cpp:459);
+    the result buffer a caller allocates also holds the traversal layout (64 (N-1) + 48 N) behind it, and the scratch
+    size is what the builder really carves its temporaries from."""
     import tracerboy_b200 as tb
     from tracerboy_b200.api import GeometryDesc, PrebuildInfo
     lib = tb.load_library()
@@ -80,7 +82,16 @@ def test_prebuild_info(built):
     d[1].Positions = pos.ctypes.data; d[1].PositionStrideBytes = 12; d[1].VertexCount = 12  # non-indexed: 4 tris
     info = PrebuildInfo()
     assert lib.tb_bvh_prebuild_info(d, 2, C.byref(info)) == 0
-    assert info.ResultDataMaxSizeInBytes == 116 * 7 - 16 and info.ScratchDataSizeInBytes > 0
+    assert info.ReferenceLayoutSizeInBytes == 116 * 7 - 16 and info.ScratchDataSizeInBytes > 7 * (40 + 12 + 16)
+    assert info.ResultDataMaxSizeInBytes >= 116 * 7 - 16 + 64 * 6 + 48 * 7 and info.ResultDataMaxSizeInBytes % 16 == 0
+    # the layout's byte offsets are 32 bit: 116 N - 16 must stay below 4 GiB, larger inputs are E_INVALIDARG
+    limit = lib.tb_max_triangles()
+    assert 116 * limit - 16 < 2 ** 32 <= 116 * (limit + 1) - 16
+    big = (GeometryDesc * 1)()
+    big[0].Positions = pos.ctypes.data; big[0].PositionStrideBytes = 12; big[0].VertexCount = 4000000000  # non-indexed
+    assert lib.tb_bvh_prebuild_info(big, 1, C.byref(info)) == -1
+    big[0].VertexCount = 3 * limit
+    assert lib.tb_bvh_prebuild_info(big, 1, C.byref(info)) == 0 and info.ReferenceLayoutSizeInBytes == 116 * limit - 16
     d[1].IndexFormat = 4  # "If the index buffer is null, the index format must be UNKNOWN" (LoadPrimitivesPass.cpp:73-76)
     assert lib.tb_bvh_prebuild_info(d, 2, C.byref(info)) == -1
 
@@ -103,6 +114,53 @@ def test_tbscene_roundtrip_and_validation(tmp_path, built):
     with pytest.raises(tb.TracerBoyError) as e:
         tb.convert_scene("scene.fbx", b)  # AssimpImporter slot: not available
     assert e.value.code == -2
+
+
+def test_tbscene_loader_rejects_every_dangling_index(tmp_path, built):
+    """The kernels index materials -> textures -> images (and mix-material ids, the environment image) without bounds
+    checks; the reference leans on D3D12 robust buffer access. A stale or malformed cache must be refused on the host:
+    each case below flips one field of a valid file and expects TB_ERR_IO, not a device fault later."""
+    import struct
+    import tracerboy_b200 as tb
+    src = str(tmp_path / "ok.tbscene")
+    tb.convert_scene("synthetic:showcase?tris=60&seed=3", src)   # has image / checker / scale textures, mix materials, env image
+    raw = bytearray(open(src, "rb").read())
+    hdr = struct.unpack_from("<8sII7Ii", raw, 0)
+    ng, nv, ni, nm, nl, nt, nimg, env = hdr[3:]
+    assert nm > 3 and nt > 2 and nimg > 0
+    off_geoms = 8 + 4 + 4 + 7 * 4 + 4 + 56 + 48 + 12 + 32
+    off_mats = off_geoms + ng * 32 + nv * 12 + nv * 32 + ni * 4
+    off_lights = off_mats + nm * 84
+    off_tex = off_lights + nl * 104
+
+    def mutated(offset, fmt, value):
+        b = bytearray(raw)
+        struct.pack_into(fmt, b, offset, value)
+        p = str(tmp_path / "bad.tbscene")
+        open(p, "wb").write(b)
+        return p
+
+    def rejected(p):
+        with pytest.raises(tb.TracerBoyError) as e:
+            tb.convert_scene(p, str(tmp_path / "out.tbscene"))
+        return e.value.code == -3
+    tb.convert_scene(mutated(off_mats + 0, "<f", struct.unpack_from("<f", raw, off_mats)[0]), str(tmp_path / "out.tbscene"))  # identity: still loads
+    assert rejected(mutated(off_mats + 12, "<I", nt + 5))            # albedoIndex
+    assert rejected(mutated(off_mats + 20, "<I", 0x7fffffff))        # normalMapIndex
+    assert rejected(mutated(off_mats + 28, "<I", nt))                # specularMapIndex == count
+    mats = np.frombuffer(bytes(raw[off_mats:off_mats + nm * 84]), np.uint32).reshape(nm, 21)
+    mix = int(np.flatnonzero(mats[:, 19] & 0x8)[0])
+    assert rejected(mutated(off_mats + mix * 84 + 0, "<f", float(nm)))   # mix material id in albedo.x
+    assert rejected(mutated(off_mats + mix * 84 + 4, "<f", -1.0))        # ... albedo.y
+    tex = np.frombuffer(bytes(raw[off_tex:off_tex + nt * 80]), np.uint32).reshape(nt, 20)
+    img_tex = int(np.flatnonzero(tex[:, 0] == 0)[0])
+    assert rejected(mutated(off_tex + img_tex * 80 + 4, "<I", nimg))     # DescriptorHeapIndex
+    scale_tex = int(np.flatnonzero(tex[:, 0] == 2)[0])
+    assert rejected(mutated(off_tex + scale_tex * 80 + 48, "<I", nt + 1))  # TextureIndex1
+    assert rejected(mutated(8 + 4 + 4 + 7 * 4, "<i", nimg))              # envImage
+    assert rejected(mutated(8 + 4 + 4, "<I", 0x40000000))                # numGeoms far beyond the file size: no giant resize
+    off_img0 = off_tex + nt * 80 + nm * 64
+    assert rejected(mutated(off_img0, "<I", struct.unpack_from("<I", raw, off_img0)[0] + 1))  # image width vs its pixel bytes
 
 
 def test_cornell_flatten_matches_reference_scene(cornell):

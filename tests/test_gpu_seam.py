@@ -1,0 +1,165 @@
+"""The SW-RT seam with the reference's ownership model (D3D12RaytracingFallback.h:83-84, 134-136):
+GetRaytracingAccelerationStructurePrebuildInfo sizes caller-allocated device memory,
+BuildRaytracingAccelerationStructure builds into it from caller-owned device vertex / index buffers, and ray queries
+run against that caller-owned structure on the caller's stream. Device memory and streams come from PyTorch (plumbing);
+every call goes through the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _mesh(rng, nv, nt):
+    pos = rng.uniform(-1, 1, (nv, 3)).astype(np.float32)
+    idx = rng.integers(0, nv, (nt, 3)).astype(np.uint32)
+    return pos, idx
+
+
+def _descs(geoms, keep):
+    """geoms: list of dicts(pos [V,k>=3] float32 strided, idx or None, transform or None) -> (GeometryDesc * n) with
+    DEVICE pointers (torch tensors kept alive in `keep`)."""
+    import torch
+    from tracerboy_b200.api import GeometryDesc
+    d = (GeometryDesc * len(geoms))()
+    for i, g in enumerate(geoms):
+        tp = torch.from_numpy(np.ascontiguousarray(g["pos"])).cuda()
+        keep.append(tp)
+        d[i].Positions = tp.data_ptr(); d[i].PositionStrideBytes = g["pos"].shape[1] * 4; d[i].VertexCount = g["pos"].shape[0]
+        d[i].GeometryFlags = 1
+        if g.get("idx") is not None:
+            raw = np.ascontiguousarray(g["idx"]).reshape(-1)
+            ti = torch.from_numpy(raw.view(np.uint8)).cuda()
+            keep.append(ti)
+            d[i].Indices = ti.data_ptr(); d[i].IndexFormat = raw.dtype.itemsize; d[i].IndexCount = raw.size
+        if g.get("transform") is not None:
+            tt = torch.from_numpy(np.ascontiguousarray(g["transform"], np.float32)).cuda()
+            keep.append(tt)
+            d[i].Transform3x4 = tt.data_ptr()
+    return d
+
+
+def _host_list(geoms):
+    """The same geometry for the host-pointer path (tb_bvh_build), transforms applied with the pinned arithmetic there."""
+    out = []
+    for g in geoms:
+        out.append((np.ascontiguousarray(g["pos"][:, :3]), g.get("idx")))
+    return out
+
+
+@pytest.mark.parametrize("case", ["u32", "u16_strided_transform", "nonindexed_mixed"])
+def test_build_into_caller_memory_and_trace_on_caller_stream(case, built):
+    import torch
+    import tracerboy_b200 as tb
+    from tracerboy_b200.api import RAY_DTYPE, HIT_DTYPE
+    rng = np.random.default_rng(7)
+    if case == "u32":
+        p, i = _mesh(rng, 3000, 9000)
+        geoms = [dict(pos=p, idx=i)]
+    elif case == "u16_strided_transform":
+        p, i = _mesh(rng, 2000, 5000)
+        p5 = np.concatenate([p, rng.uniform(0, 1, (2000, 2)).astype(np.float32)], 1)  # stride 20: uv after the position
+        m = np.array([[1.5, 0.1, 0, 0.3], [0, 0.8, -0.2, -1.0], [0.05, 0, 1.1, 2.0]], np.float32)
+        geoms = [dict(pos=p5, idx=i.astype(np.uint16), transform=m), dict(pos=p, idx=i[:1000])]
+    else:
+        p, i = _mesh(rng, 999, 10)
+        q, j = _mesh(rng, 500, 700)
+        geoms = [dict(pos=p, idx=None), dict(pos=q, idx=j.astype(np.uint16)), dict(pos=q + 3, idx=j)]
+    keep = []
+    d = _descs(geoms, keep)
+    info = tb.prebuild_info(d, len(geoms))
+    ntri = sum((g["idx"].size if g.get("idx") is not None else g["pos"].shape[0]) // 3 for g in geoms)
+    assert info.ReferenceLayoutSizeInBytes == 116 * ntri - 16
+    assert info.ResultDataMaxSizeInBytes >= info.ReferenceLayoutSizeInBytes + 112 * ntri - 64 and info.ScratchDataSizeInBytes > 100 * ntri
+    dst = torch.zeros(info.ResultDataMaxSizeInBytes, dtype=torch.uint8, device="cuda")
+    scratch = torch.empty(info.ScratchDataSizeInBytes, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.Stream()
+    g = tb.TracerBoy(0)
+    g.BuildRaytracingAccelerationStructureDevice(d, len(geoms), dst.data_ptr(), dst.numel(), scratch.data_ptr(), scratch.numel(),
+                                                 stream.cuda_stream)
+    ref_bytes = dst[:info.ReferenceLayoutSizeInBytes].cpu().numpy()
+
+    # the same geometry through the host-pointer path of a second handle (which the oracle tests pin): identical bytes
+    h = tb.TracerBoy(0)
+    host = []
+    for gd in geoms:
+        pos = np.ascontiguousarray(gd["pos"][:, :3])
+        if gd.get("transform") is not None:
+            m = gd["transform"]
+            x, y, z = pos[:, 0], pos[:, 1], pos[:, 2]
+            pos = np.stack([((m[r, 0] * x + m[r, 1] * y) + m[r, 2] * z) + m[r, 3] for r in range(3)], 1).astype(np.float32)
+        host.append((pos, gd.get("idx")))
+    h.BuildRaytracingAccelerationStructure(host)
+    assert np.array_equal(ref_bytes, h.GetBVH())
+
+    # ray queries against the caller-owned structure, device rays / hits, on the caller's stream
+    rays = np.zeros(50000, RAY_DTYPE)
+    rays["Origin"] = rng.uniform(-3, 3, (50000, 3)); rays["Direction"] = rng.normal(0, 1, (50000, 3))
+    rays["TMin"] = 0.001; rays["TMax"] = 999999.0
+    d_rays = torch.from_numpy(rays.view(np.uint8)).cuda()
+    d_hits = torch.zeros(50000 * 32, dtype=torch.uint8, device="cuda")
+    with torch.cuda.stream(stream):
+        g.TraceRaysDevice(dst.data_ptr(), dst.numel(), d_rays.data_ptr(), 50000, d_hits.data_ptr(), stream.cuda_stream)
+    stream.synchronize()
+    got = d_hits.cpu().numpy().view(HIT_DTYPE)
+    want = h.TraceRays(rays)
+    for f in got.dtype.names:
+        assert np.array_equal(got[f].view(np.uint32), want[f].view(np.uint32)), f
+    assert (got["t"] > 0).sum() > 1000
+
+    # another handle recognises the structure from its own trailer (no shared host state)
+    k = tb.TracerBoy(0)
+    d_hits.zero_()
+    k.TraceRaysDevice(dst.data_ptr(), dst.numel(), d_rays.data_ptr(), 50000, d_hits.data_ptr(), None)
+    k.Synchronize()
+    assert np.array_equal(d_hits.cpu().numpy().view(HIT_DTYPE)["t"].view(np.uint32), want["t"].view(np.uint32))
+
+    # library-owned scratch (NULL) gives the same bytes; wrong sizes are E_INVALIDARG
+    dst2 = torch.zeros_like(dst)
+    g.BuildRaytracingAccelerationStructureDevice(d, len(geoms), dst2.data_ptr(), dst2.numel(), None, 0, None)
+    assert torch.equal(dst2[:info.ReferenceLayoutSizeInBytes], dst[:info.ReferenceLayoutSizeInBytes])
+    with pytest.raises(tb.TracerBoyError):
+        g.BuildRaytracingAccelerationStructureDevice(d, len(geoms), dst.data_ptr(), info.ReferenceLayoutSizeInBytes, None, 0, None)
+    with pytest.raises(tb.TracerBoyError):
+        g.BuildRaytracingAccelerationStructureDevice(d, len(geoms), dst.data_ptr(), dst.numel(), scratch.data_ptr(), 1024, None)
+    g.ForgetAccelerationStructure(dst.data_ptr())
+
+
+def test_trace_rays_device_on_the_handles_scene(cornell):
+    import torch
+    import tracerboy_b200 as tb
+    from tracerboy_b200.api import RAY_DTYPE, HIT_DTYPE
+    g = tb.TracerBoy(0)
+    g.LoadScene(cornell)
+    rng = np.random.default_rng(3)
+    rays = np.zeros(4096, RAY_DTYPE)
+    rays["Origin"] = rng.uniform(-0.5, 0.5, (4096, 3)) + np.array([0, 1, 3]); rays["Direction"] = rng.normal(0, 1, (4096, 3))
+    rays["TMin"] = 0.001; rays["TMax"] = 999999.0
+    d_rays = torch.from_numpy(rays.view(np.uint8)).cuda()
+    d_hits = torch.zeros(4096 * 32, dtype=torch.uint8, device="cuda")
+    g.TraceRaysDevice(None, 0, d_rays.data_ptr(), 4096, d_hits.data_ptr(), None)
+    g.Synchronize()
+    want = g.TraceRays(rays)
+    got = d_hits.cpu().numpy().view(HIT_DTYPE)
+    for f in got.dtype.names:
+        assert np.array_equal(got[f].view(np.uint32), want[f].view(np.uint32)), f
+
+
+def test_set_material_rejects_dangling_indices(cornell):
+    """tb_set_material validates what the kernels index unchecked (the reference leans on D3D robust buffer access)."""
+    import tracerboy_b200 as tb
+    g = tb.TracerBoy(0)
+    g.LoadScene(cornell)
+    m, _ = g.GetMaterial(0)
+    m.albedoIndex = 12345
+    with pytest.raises(tb.TracerBoyError) as e:
+        g.SetMaterial(0, m)
+    assert e.value.code == -1
+    m, _ = g.GetMaterial(0)
+    m.Flags |= 0x8  # mix material whose ids (albedo.x / .y) point nowhere
+    m.albedo.x = 99.0
+    with pytest.raises(tb.TracerBoyError):
+        g.SetMaterial(0, m)
+    g.Resize(16, 16)
+    g.Render(tb.get_default_output_settings(), 1, 0.0)  # the device scene is still the valid one

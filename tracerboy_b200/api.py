@@ -120,15 +120,24 @@ class GeometryDesc(C.Structure):
 
 class PrebuildInfo(C.Structure):
     _fields_ = [("ResultDataMaxSizeInBytes", C.c_uint64), ("ScratchDataSizeInBytes", C.c_uint64),
-                ("UpdateScratchDataSizeInBytes", C.c_uint64)]
+                ("UpdateScratchDataSizeInBytes", C.c_uint64), ("ReferenceLayoutSizeInBytes", C.c_uint64)]
+
+
+class CommInfo(C.Structure):
+    _fields_ = [("Rank", C.c_uint32), ("NumRanks", C.c_uint32), ("ShardMode", C.c_uint32), ("NcclVersion", C.c_uint32),
+                ("Reductions", C.c_uint64), ("BytesReceivedPerReduction", C.c_uint64), ("LastReductionMilliseconds", C.c_double)]
+
+
+SHARD_SAMPLES, SHARD_ROWS = 1, 2
+COMM_ID_BYTES = 128
 
 
 class BufferKind:
     ACCUM_RGBW, JITTERED_RGBW, RESOLVED_RGB, AOV_NORMAL, AOV_WORLDPOS, AOV_DEPTH, AOV_ALBEDO, AOV_EMISSIVE, \
-        PRIMARY_HIT_IDS, RAY_COUNTERS, POSTPROCESS_RGBA, BACKBUFFER_RGBA8, LUMINANCE_HISTOGRAM = range(13)
+        PRIMARY_HIT_IDS, RAY_COUNTERS, POSTPROCESS_RGBA, BACKBUFFER_RGBA8, LUMINANCE_HISTOGRAM, LOCAL_ACCUM_RGBW = range(14)
     _shape = {0: (np.float32, 4), 1: (np.float32, 4), 2: (np.float32, 3), 3: (np.float32, 4), 4: (np.float32, 4),
               5: (np.float32, 1), 6: (np.float32, 4), 7: (np.float32, 4), 8: (np.uint32, 2), 9: (np.uint32, 2),
-              10: (np.float32, 4), 11: (np.uint8, 4)}
+              10: (np.float32, 4), 11: (np.uint8, 4), 13: (np.float32, 4)}
 
 
 BVH_BUILD_PREFER_FAST_TRACE = 0x4
@@ -156,6 +165,8 @@ def load_library():
     lib.tb_version.restype = C.c_char_p
     lib.tb_destroy.restype = None
     lib.tb_destroy.argtypes = [C.c_void_p]
+    lib.tb_max_triangles.restype = C.c_uint64
+    lib.tb_max_triangles.argtypes = []
     vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
     sig = {
         "tb_create": [i32, C.POINTER(vp)], "tb_load_scene": [vp, C.c_char_p], "tb_load_scene_ex": [vp, C.c_char_p, u32],
@@ -177,6 +188,11 @@ def load_library():
         "tb_set_material": [vp, i32, C.POINTER(Material)],
         "tb_bvh_prebuild_info": [C.POINTER(GeometryDesc), u32, C.POINTER(PrebuildInfo)],
         "tb_bvh_build": [vp, C.POINTER(GeometryDesc), u32, u32], "tb_trace_rays": [vp, vp, u64, vp],
+        "tb_bvh_build_device": [vp, C.POINTER(GeometryDesc), u32, u32, vp, u64, vp, u64, vp],
+        "tb_trace_rays_device": [vp, vp, u64, vp, u64, vp, vp], "tb_bvh_forget_device": [vp, vp],
+        "tb_get_bvh_depth": [vp, C.POINTER(u32)],
+        "tb_comm_get_unique_id": [vp, u64], "tb_comm_init": [vp, vp, i32, i32, u32], "tb_comm_destroy": [vp],
+        "tb_comm_info": [vp, C.POINTER(CommInfo)], "tb_comm_reduce": [vp],
         "tb_get_default_postprocess_settings": [C.POINTER(PostProcessSettings)],
         "tb_postprocess": [vp, u32, C.POINTER(PostProcessSettings)],
         "tb_temporal_accumulate_image": [vp, C.POINTER(TemporalAccumulationParams), u32, u32, vp, vp, vp, vp, vp, vp, vp, vp],
@@ -200,7 +216,9 @@ EXPORTED_SYMBOLS = ["tb_create", "tb_destroy", "tb_last_error", "tb_version", "t
                     "tb_get_render_stats", "tb_reset_render_stats", "tb_set_profiling", "tb_set_frames_in_flight", "tb_set_shadow_mode", "tb_synchronize", "tb_is_material_id_valid",
                     "tb_get_material", "tb_set_material", "tb_bvh_prebuild_info", "tb_bvh_build", "tb_trace_rays",
                     "tb_get_default_postprocess_settings", "tb_postprocess", "tb_postprocess_image",
-                    "tb_temporal_accumulate_image", "tb_save_image", "tb_write_image", "tb_update", "tb_camera_update", "tb_set_ray_sort"]
+                    "tb_temporal_accumulate_image", "tb_save_image", "tb_write_image", "tb_update", "tb_camera_update", "tb_set_ray_sort",
+                    "tb_max_triangles", "tb_bvh_build_device", "tb_trace_rays_device", "tb_bvh_forget_device", "tb_get_bvh_depth",
+                    "tb_comm_get_unique_id", "tb_comm_init", "tb_comm_destroy", "tb_comm_info", "tb_comm_reduce"]
 
 
 def _key_table(keyboardInput):
@@ -252,6 +270,25 @@ def write_image(path, pixels):
     rc = load_library().tb_write_image(str(path).encode(), a.ctypes.data, a.shape[1], a.shape[0], a.shape[2], a.dtype.itemsize, err, 512)
     if rc != 0:
         raise TracerBoyError(rc, err.value.decode())
+
+
+def comm_get_unique_id():
+    """ncclGetUniqueId: called by one process, the bytes go to every rank's CommInit by whatever means the host has."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    lib = load_library()
+    rc = lib.tb_comm_get_unique_id(buf, COMM_ID_BYTES)
+    if rc != 0:
+        raise TracerBoyError(rc, lib.tb_last_error(None).decode())
+    return buf.raw
+
+
+def prebuild_info(descs, n):
+    """GetRaytracingAccelerationStructurePrebuildInfo on a (GeometryDesc * n) array."""
+    info = PrebuildInfo()
+    rc = load_library().tb_bvh_prebuild_info(descs, n, C.byref(info))
+    if rc != 0:
+        raise TracerBoyError(rc, "tb_bvh_prebuild_info")
+    return info
 
 
 def convert_scene(src, dst):
@@ -348,6 +385,42 @@ class TracerBoy:
                 descs[i].IndexFormat = idx.dtype.itemsize
                 descs[i].IndexCount = idx.size
         self._ck(self._lib.tb_bvh_build(self._h, descs, len(geometries), flags))
+
+    def GetBVHDepth(self):
+        d = C.c_uint32()
+        self._ck(self._lib.tb_get_bvh_depth(self._h, C.byref(d)))
+        return d.value
+
+    def BuildRaytracingAccelerationStructureDevice(self, descs, n, dst, dst_bytes, scratch=None, scratch_bytes=0, stream=None,
+                                                   flags=BVH_BUILD_PREFER_FAST_TRACE):
+        """BuildRaytracingAccelerationStructure with caller-allocated dest + scratch device memory; `descs` is a
+        (GeometryDesc * n) array whose pointers are DEVICE pointers (D3D12RaytracingFallback.h:83-84)."""
+        self._ck(self._lib.tb_bvh_build_device(self._h, descs, n, flags, dst, dst_bytes, scratch, scratch_bytes, stream))
+
+    def TraceRaysDevice(self, accel, accel_bytes, d_rays, n, d_hits, stream=None):
+        """n ray queries against a caller-owned acceleration structure (None: the handle's scene); device pointers,
+        enqueued on `stream` without synchronising."""
+        self._ck(self._lib.tb_trace_rays_device(self._h, accel, accel_bytes, d_rays, n, d_hits, stream))
+
+    def ForgetAccelerationStructure(self, accel):
+        self._ck(self._lib.tb_bvh_forget_device(self._h, accel))
+
+    # --- multi-GPU -------------------------------------------------------
+    def CommInit(self, unique_id, rank, nranks, shard_mode=SHARD_SAMPLES):
+        """ncclCommInitRank on this handle's device; also sets the handle's shard to (rank, nranks)."""
+        self._ck(self._lib.tb_comm_init(self._h, unique_id, int(rank), int(nranks), int(shard_mode)))
+
+    def CommDestroy(self):
+        self._ck(self._lib.tb_comm_destroy(self._h))
+
+    def CommReduce(self):
+        """Collective: the job-wide accumulation image on every rank (deterministic; see TB_SHARD_*)."""
+        self._ck(self._lib.tb_comm_reduce(self._h))
+
+    def CommInfo(self):
+        s = CommInfo()
+        self._ck(self._lib.tb_comm_info(self._h, C.byref(s)))
+        return s
 
     def TraceRays(self, rays):
         rays = np.ascontiguousarray(rays, RAY_DTYPE)

@@ -28,9 +28,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",
               "-I" + os.path.join(ROOT, "include"), "-ccbin", GXX]
 
-CUDA_SRCS = ["csrc/cuda/bvh_build.cu", "csrc/cuda/pathtrace.cu", "csrc/cuda/postprocess.cu"]
-HOST_SRCS = ["csrc/host/api.cpp", "csrc/host/scene.cpp", "csrc/host/image_io.cpp"]
-HEADERS = ["csrc/cuda/device_types.h", "csrc/cuda/pathtrace.h", "csrc/cuda/traverse.cuh", "csrc/cuda/launch.h", "csrc/cuda/postprocess.h",
+CUDA_SRCS = ["csrc/cuda/bvh_build.cu", "csrc/cuda/pathtrace.cu", "csrc/cuda/postprocess.cu", "csrc/cuda/reduce.cu"]
+HOST_SRCS = ["csrc/host/api.cpp", "csrc/host/comm.cpp", "csrc/host/scene.cpp", "csrc/host/image_io.cpp"]
+HEADERS = ["csrc/cuda/device_types.h", "csrc/cuda/pathtrace.h", "csrc/cuda/traverse.cuh", "csrc/cuda/launch.h", "csrc/cuda/postprocess.h", "csrc/cuda/reduce.h", "csrc/host/handle.h",
            "csrc/common/tb_math.h", "csrc/common/tb_vec.h", "csrc/host/scene.h", "../include/tracerboy_b200.h"]
 
 
@@ -132,6 +132,7 @@ BUNDLED_SCENES = {
     "cornell-box": "Scenes/cornell-box/scene.pbrt",
     "teapot": "Scenes/Teapot/scene.pbrt",
     "vw-van": "variant:vw-van",
+    "dragon": "variant:dragon",
 }
 
 
@@ -156,6 +157,102 @@ def _vw_van_variant(tmp):
     return out
 
 
+def _write_ply(path, pos, nrm, uv, faces):
+    """Binary little-endian PLY with the vertex layout of the scene's own meshes (x y z nx ny nz u v; uint8-counted int faces)."""
+    import numpy as np
+    v = np.concatenate([pos, nrm, uv], axis=1).astype("<f4")
+    f = np.zeros(faces.shape[0], dtype=[("n", "u1"), ("i", "<i4", 3)])
+    f["n"] = 3
+    f["i"] = faces
+    with open(path, "wb") as out:
+        out.write(("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+                   "property float nx\nproperty float ny\nproperty float nz\nproperty float u\nproperty float v\n"
+                   "element face %d\nproperty list uint8 int vertex_indices\nend_header\n" % (v.shape[0], f.shape[0])).encode())
+        out.write(v.tobytes())
+        out.write(f.tobytes())
+
+
+def _grid_surface(point_fn, nu, nv, closed_u=True):
+    """Triangulated (nu x nv) parametric surface with smooth normals from the grid's own tangents."""
+    import numpy as np
+    u = np.arange(nu + (0 if closed_u else 1), dtype=np.float64) / nu
+    v = np.arange(nv + 1, dtype=np.float64) / nv
+    U, V = np.meshgrid(u, v, indexing="ij")
+    P = point_fn(U, V)
+    cols = P.shape[0]
+    du = (np.roll(P, -1, 0) - np.roll(P, 1, 0)) if closed_u else np.gradient(P, axis=0)
+    dv = np.gradient(P, axis=1)
+    N = np.cross(dv, du)
+    ln = np.linalg.norm(N, axis=2, keepdims=True)
+    radial = P - P.reshape(-1, 3).mean(0)
+    radial /= np.maximum(np.linalg.norm(radial, axis=2, keepdims=True), 1e-20)
+    N = np.where(ln > 1e-12, N / np.maximum(ln, 1e-20), radial)
+    N = np.where((N * radial).sum(2, keepdims=True) < 0, -N, N)
+    idx = np.arange(cols * (nv + 1)).reshape(cols, nv + 1)
+    a = idx[:-1 if not closed_u else None, :-1]
+    b = (np.roll(idx, -1, 0) if closed_u else idx[1:])[: a.shape[0], :-1]
+    c = (np.roll(idx, -1, 0) if closed_u else idx[1:])[: a.shape[0], 1:]
+    d = idx[: a.shape[0], 1:]
+    faces = np.concatenate([np.stack([a, b, c], -1).reshape(-1, 3), np.stack([a, c, d], -1).reshape(-1, 3)])
+    return P.reshape(-1, 3), N.reshape(-1, 3), np.stack([U, V], -1).reshape(-1, 2), faces
+
+
+def _dragon_variant(tmp):
+    """BASELINE.json configs[2]: the mount holds Scenes/dragon/scene.pbrt, its environment map and 12 of
+    its 16 meshes (51 140 triangles); the four missing ones are the two ground pieces (Mesh012 GroundInner, Mesh007
+    GroundOuter) and the dragon's body (Mesh008, Mesh013). The variant is the reference's own scene.pbrt, read from
+    the mount at build time and left untouched -- same camera, same nine matte materials, lit only by textures/envmap.hdr
+    -- with the four missing .ply files generated here: a deterministic high-poly body of multi-scale bumps where the
+    dragon stands (819 200 + 32 768 triangles, so the whole scene is the ~0.9 M-triangle, all-diffuse, environment-lit
+    workload the config names) and two small ground pieces. Nothing is written into the repo except the flattened
+    scenes/_cache/dragon.tbscene (git-ignored)."""
+    import numpy as np
+    src = os.path.join(REF, "Scenes/dragon")
+    if not os.path.exists(os.path.join(src, "scene.pbrt")):
+        return None
+    os.makedirs(os.path.join(tmp, "models"))
+    os.symlink(os.path.join(src, "textures"), os.path.join(tmp, "textures"))
+    for f in os.listdir(os.path.join(src, "models")):
+        os.symlink(os.path.join(src, "models", f), os.path.join(tmp, "models", f))
+    shutil.copy(os.path.join(src, "scene.pbrt"), os.path.join(tmp, "scene.pbrt"))
+    tau = 2.0 * np.pi
+
+    def body(U, V):  # closed lat-long surface around (0, 5.6, -1.2): lobes, ridges and fine "scales"
+        th, ph = tau * U, np.pi * V
+        r = 1.0 + 0.18 * np.sin(3 * th + 0.7) * np.sin(2 * ph) + 0.10 * np.sin(7 * th) * np.sin(5 * ph + 0.3) \
+            + 0.035 * np.sin(29 * th + 1.1) * np.sin(23 * ph) + 0.008 * np.sin(131 * th) * np.sin(113 * ph + 0.5)
+        x = 4.2 * r * np.sin(ph) * np.cos(th)
+        y = 5.6 + 5.0 * r * np.cos(ph)
+        z = -1.2 + 5.2 * r * np.sin(ph) * np.sin(th)
+        return np.stack([x, y, z], -1)
+
+    def tail(U, V):  # a tapering tube coiled around the pedestal
+        t = V
+        ang = tau * (1.35 * t + 0.1)
+        rad = 7.6 - 1.8 * t
+        cx, cy, cz = rad * np.cos(ang), 0.9 + 2.4 * t * t, -1.2 + rad * np.sin(ang)
+        w = 0.75 * (1.0 - 0.85 * t) * (1.0 + 0.06 * np.sin(40 * tau * t) )
+        a = tau * U
+        # frame: radial (outwards from the pedestal axis) and up
+        ox, oz = np.cos(ang), np.sin(ang)
+        x = cx + w * np.cos(a) * ox
+        y = cy + w * np.sin(a)
+        z = cz + w * np.cos(a) * oz
+        return np.stack([x, y, z], -1)
+
+    def disc(r0, r1, height):
+        def f(U, V):
+            r = r0 + (r1 - r0) * V
+            return np.stack([r * np.cos(tau * U), np.full_like(U, height) + 0.02 * np.sin(9 * tau * U) * (r / r1), r * np.sin(tau * U)], -1)
+        return f
+
+    _write_ply(os.path.join(tmp, "models", "Mesh008.ply"), *_grid_surface(body, 640, 640))
+    _write_ply(os.path.join(tmp, "models", "Mesh013.ply"), *_grid_surface(tail, 32, 512))
+    _write_ply(os.path.join(tmp, "models", "Mesh012.ply"), *_grid_surface(disc(0.0, 9.0, 0.24), 64, 16))
+    _write_ply(os.path.join(tmp, "models", "Mesh007.ply"), *_grid_surface(disc(9.0, 13.0, 0.1), 64, 8))
+    return os.path.join(tmp, "scene.pbrt")
+
+
 def build_scene_cache(force=False):
     """Flatten the reference's bundled scenes into scenes/_cache/*.tbscene (needs the mount)."""
     cache = os.path.join(ROOT, "scenes", "_cache")
@@ -172,7 +269,7 @@ def build_scene_cache(force=False):
         tmp = None
         if rel.startswith("variant:"):
             tmp = tempfile.mkdtemp(prefix="tb_variant_")
-            src = _vw_van_variant(tmp)
+            src = _dragon_variant(tmp) if rel == "variant:dragon" else _vw_van_variant(tmp)
             if not src:
                 shutil.rmtree(tmp, ignore_errors=True)
                 continue

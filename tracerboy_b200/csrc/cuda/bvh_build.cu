@@ -47,9 +47,11 @@ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
 }
 
 // ---------------------------------------------------------------- load + AABB
-__global__ void k_load_prims(const TbGeometryRecord* __restrict__ geoms, const uint32_t* __restrict__ triPrefix,
-                             uint32_t numGeoms, const float* __restrict__ positions,
-                             const uint32_t* __restrict__ indices, uint32_t n, Prim* __restrict__ prims,
+// BottomLevelLoadTriangles.hlsli:14-126 in its three index-format variants (none / 16 bit / 32 bit), with the optional
+// 3x4 transform (TransformVertex :83-86: mul(float3x4, float4(v, 1)), one dot product per row, left to right) and a
+// vertex stride, straight from the caller's device buffers (D3D12_RAYTRACING_GEOMETRY_TRIANGLES_DESC).
+__global__ void k_load_prims(const BuildGeometry* __restrict__ geoms, const uint32_t* __restrict__ triPrefix,
+                             uint32_t numGeoms, uint32_t n, Prim* __restrict__ prims,
                              Meta* __restrict__ meta, uint32_t* __restrict__ sceneBox /*6 ordered uints*/) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     f3 mn = mk3(FLT_MAX), mx = mk3(-FLT_MAX);
@@ -57,14 +59,24 @@ __global__ void k_load_prims(const TbGeometryRecord* __restrict__ geoms, const u
         // geometry lookup: last g with triPrefix[g] <= i
         uint32_t lo = 0, hi = numGeoms;
         while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (triPrefix[mid] <= i) lo = mid; else hi = mid; }
-        TbGeometryRecord G = geoms[lo];
+        const BuildGeometry G = geoms[lo];
         uint32_t t = i - triPrefix[lo];
         Prim p;
         p.type = 1;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            uint32_t vi = G.VertexFirst + indices[G.IndexFirst + 3 * t + k];
-            float x = positions[3 * (size_t)vi], y = positions[3 * (size_t)vi + 1], z = positions[3 * (size_t)vi + 2];
+            uint32_t vi = 3 * t + k;
+            if (G.indexFormat == 4) vi = ((const uint32_t*)G.indices)[vi];
+            else if (G.indexFormat == 2) vi = ((const uint16_t*)G.indices)[vi];
+            const float* pv = (const float*)(G.positions + (size_t)vi * G.strideBytes);
+            float x = pv[0], y = pv[1], z = pv[2];
+            if (G.transform) {
+                const float* m = G.transform;
+                float tx = ((m[0] * x + m[1] * y) + m[2] * z) + m[3];
+                float ty = ((m[4] * x + m[5] * y) + m[6] * z) + m[7];
+                float tz = ((m[8] * x + m[9] * y) + m[10] * z) + m[11];
+                x = tx; y = ty; z = tz;
+            }
             p.v[3 * k] = x; p.v[3 * k + 1] = y; p.v[3 * k + 2] = z;
             mn = min3(mn, mk3(x, y, z));
             mx = max3(mx, mk3(x, y, z));
@@ -73,7 +85,7 @@ __global__ void k_load_prims(const TbGeometryRecord* __restrict__ geoms, const u
         const uint32_t* src = (const uint32_t*)&p;
 #pragma unroll
         for (int k = 0; k < 10; k++) dst[k] = src[k];
-        Meta m = {lo, t, G.GeometryFlags};
+        Meta m = {lo, t, G.flags};
         meta[i] = m;
     }
     // warp reduce, block reduce, then 6 atomics per block (min/max are order independent => deterministic). One set of
@@ -343,9 +355,26 @@ __global__ void k_find_treelets(const Prim* __restrict__ prims, uint32_t n, uint
     }
 }
 
-// masks 1..127 ordered by popcount (2..7 used), built at compile time into constant memory
-__constant__ uint8_t c_masksBySize[128];
-__constant__ uint8_t c_sizeStart[9];
+// masks 0..127 ordered by popcount (sizes 2..7 used), built at compile time: the tables are part of the module image,
+// so every device that loads the module has them (a run-time cudaMemcpyToSymbol only writes the current device's copy).
+struct MaskTables { uint8_t bySize[128]; uint8_t sizeStart[9]; };
+constexpr MaskTables make_mask_tables() {
+    MaskTables t{};
+    uint32_t k = 0;
+    for (uint32_t s = 0; s <= 7; s++) {
+        t.sizeStart[s] = (uint8_t)k;
+        for (uint32_t m = 0; m < 128; m++) {
+            uint32_t bits = 0;
+            for (uint32_t b = 0; b < 7; b++) bits += (m >> b) & 1u;
+            if (bits == s) t.bySize[k++] = (uint8_t)m;
+        }
+    }
+    t.sizeStart[8] = (uint8_t)k;
+    return t;
+}
+__constant__ const MaskTables c_maskTables = make_mask_tables();
+#define c_masksBySize c_maskTables.bySize
+#define c_sizeStart c_maskTables.sizeStart
 
 // TreeletReorder.hlsl:38-312 — one OCTET (8 lanes) per base treelet root, climbing to the BVH root; the four
 // octets of a warp run in lock step, each on its own treelet.
@@ -595,19 +624,27 @@ __global__ void __launch_bounds__(128, 8) k_treelet_reorder(uint32_t n, HNode* H
 
 // --------------------------------------------------------------------- refit
 // ComputeAABBs.hlsli:69-172 (+ PrepareForComputeAABBs header)
-__global__ void k_refit(uint32_t n, const HNode* H, uint8_t* bvh, uint32_t* counter) {
+// The climb also carries the subtree height (count in the low word of the 64-bit arrival counter, height in the
+// high word: the value the first arrival leaves is exactly what the second one reads back), so the depth of the
+// finished tree is known when the root is written. The traversal keeps at most one waiting far child per level,
+// so `depth` bounds the stack it needs: the host rejects a tree deeper than TB_STACK_DEPTH instead of the traversal
+// dropping children silently.
+__global__ void k_refit(uint32_t n, const HNode* H, uint8_t* bvh, unsigned long long* counter, uint32_t* depthOut) {
     uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= n) return;
     const uint32_t nInternal = n - 1, total = 2 * n - 1;
-    const uint32_t offPrims = 16 + 32 * total;
+    // 64-bit addressing throughout; the header's four words are the reference's 32-bit byte offsets
+    // (RayTracingHlslCompat.h:344-398), which the host guarantees to fit (tb_max_triangles: 116 N - 16 < 4 GiB)
+    const size_t offPrims = 16 + 32 * (size_t)total;
     if (tid == 0) {
         uint32_t* hd = (uint32_t*)bvh;
-        hd[0] = 16; hd[1] = offPrims; hd[2] = offPrims + 40 * n; hd[3] = offPrims + 40 * n + 12 * n;
+        hd[0] = 16; hd[1] = (uint32_t)offPrims; hd[2] = (uint32_t)(offPrims + 40 * (size_t)n); hd[3] = (uint32_t)(offPrims + 52 * (size_t)n);
+        if (n == 1) *depthOut = 0;
     }
     float* nodes = (float*)(bvh + 16);
     const Prim* prims = (const Prim*)(bvh + offPrims);
     uint32_t node = total - tid - 1;
-    uint32_t count = 1;
+    uint32_t count = 1, height = 0;
     {
         f3 c, h;
         leaf_box(prims, node - nInternal, c, h);
@@ -618,7 +655,8 @@ __global__ void k_refit(uint32_t n, const HNode* H, uint8_t* bvh, uint32_t* coun
     while (node != 0) {
         uint32_t parent = ld_u(&H[node].parent);
         __threadfence();
-        uint32_t other = atomicAdd(&counter[parent], count);
+        const unsigned long long arrived = atomicAdd(&counter[parent], ((unsigned long long)height << 32) | count);
+        const uint32_t other = (uint32_t)arrived, otherHeight = (uint32_t)(arrived >> 32);
         if (other == 0) return;
         __threadfence();
         uint32_t l = ld_u(&H[parent].left), r = ld_u(&H[parent].right);
@@ -637,6 +675,8 @@ __global__ void k_refit(uint32_t n, const HNode* H, uint8_t* bvh, uint32_t* coun
         __stcg(nd + 1, make_float4(h.x, h.y, h.z, __uint_as_float(r)));
         node = parent;
         count += other;
+        height = (height > otherHeight ? height : otherHeight) + 1;
+        if (node == 0) *depthOut = height;
     }
 }
 
@@ -671,59 +711,70 @@ __global__ void k_widen(uint32_t n, const uint8_t* __restrict__ bvh, PairNode* _
     }
 }
 
-void init_mask_tables() {
-    static bool done = false;
-    if (done) return;
-    uint8_t masks[128] = {0}, start[9] = {0};
-    uint32_t k = 0;
-    for (uint32_t s = 0; s <= 7; s++) {
-        start[s] = (uint8_t)k;
-        for (uint32_t m = 0; m < 128; m++)
-            if ((uint32_t)__builtin_popcount(m) == s) masks[k++] = (uint8_t)m;
-    }
-    start[8] = (uint8_t)k;
-    cudaMemcpyToSymbol(c_masksBySize, masks, sizeof(masks));
-    cudaMemcpyToSymbol(c_sizeStart, start, sizeof(start));
-    done = true;
-}
-
 } // namespace
 
 uint64_t bvh_ref_bytes(uint32_t n) { return 16ull + 32ull * (2ull * n - 1) + 40ull * n + 12ull * n; }
 
-// Builds dst (reference layout) + wide layout. All temporaries are allocated and freed
-// here (cudaMallocAsync on the stream); returns cudaSuccess or the first error.
-cudaError_t build_bvh(const TbGeometryRecord* d_geoms, const uint32_t* d_triPrefix, uint32_t numGeoms,
-                      const float* d_positions, const uint32_t* d_indices, uint32_t n, int treeletPasses,
-                      DeviceBvh& out, cudaStream_t stream, LaunchCounter& lc) {
-    init_mask_tables();
+// The builder's temporaries, carved out of ONE scratch allocation (the caller's, as in
+// BuildRaytracingAccelerationStructure's ScratchAccelerationStructureData, or the library's own).
+namespace {
+struct ScratchLayout {
+    size_t prims, meta, codes, order, codesAlt, orderAlt, sceneBox, numTris, baseCount, baseRoots, H, aabb, radixHist, arrive, depth, end;
+    uint32_t sortBlocks;
+};
+ScratchLayout scratch_layout(uint32_t n) {
+    ScratchLayout L;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t at = off; off += (bytes + 255) & ~(size_t)255; return at; };
+    const size_t total = 2 * (size_t)n - 1;
+    L.sortBlocks = (n + RS_TILE - 1) / RS_TILE;
+    L.prims = take(sizeof(Prim) * (size_t)n);
+    L.meta = take(sizeof(Meta) * (size_t)n);
+    L.codes = take(4 * (size_t)n); L.order = take(4 * (size_t)n);
+    L.codesAlt = take(4 * (size_t)n); L.orderAlt = take(4 * (size_t)n);
+    L.sceneBox = take(6 * 4);
+    L.numTris = take(4 * (size_t)n);
+    L.baseCount = take(4);
+    L.baseRoots = take(4 * ((size_t)n / 7 + 1));
+    L.H = take(sizeof(HNode) * total);
+    L.aabb = take(32 * total);
+    L.radixHist = take(4 * 256 * ((size_t)L.sortBlocks + 1));
+    L.arrive = take(8 * (size_t)n);
+    L.depth = take(4);
+    L.end = off;
+    return L;
+}
+} // namespace
+
+uint64_t bvh_scratch_bytes(uint32_t n) { return n ? scratch_layout(n).end : 0; }
+
+// Builds the reference layout into out.ref and the traversal layout into out.pairs / out.tris. `scratch` holds at
+// least bvh_scratch_bytes(n) bytes (256-byte aligned). No allocation happens in here; the stream is synchronised
+// once at the end (the root box and the tree depth come back to the host).
+cudaError_t build_bvh(const BuildGeometry* d_geoms, const uint32_t* d_triPrefix, uint32_t numGeoms, uint32_t n, int treeletPasses,
+                      DeviceBvh& out, void* scratch, cudaStream_t stream, LaunchCounter& lc) {
     const uint32_t total = 2 * n - 1, nInternal = n - 1;
     const uint32_t T = 256;
     auto grid = [&](uint32_t c) { return (c + T - 1) / T; };
     cudaError_t err;
 #define CK(x) do { err = (x); if (err != cudaSuccess) return err; } while (0)
-    Prim* prims; Meta* meta; uint32_t *codes, *order, *codesAlt, *orderAlt, *sceneBox, *numTris, *baseCount, *baseRoots;
-    HNode* H; float* aabb; 
-    CK(cudaMallocAsync(&prims, sizeof(Prim) * (size_t)n, stream));
-    CK(cudaMallocAsync(&meta, sizeof(Meta) * (size_t)n, stream));
-    CK(cudaMallocAsync(&codes, 4 * (size_t)n, stream));
-    CK(cudaMallocAsync(&order, 4 * (size_t)n, stream));
-    CK(cudaMallocAsync(&codesAlt, 4 * (size_t)n, stream));
-    CK(cudaMallocAsync(&orderAlt, 4 * (size_t)n, stream));
-    CK(cudaMallocAsync(&sceneBox, 6 * 4, stream));
-    CK(cudaMallocAsync(&numTris, 4 * (size_t)(nInternal + 1), stream));
-    CK(cudaMallocAsync(&baseCount, 4, stream));
-    CK(cudaMallocAsync(&baseRoots, 4 * (size_t)(n / 7 + 1), stream));
-    CK(cudaMallocAsync(&H, sizeof(HNode) * (size_t)total, stream));
-    CK(cudaMallocAsync(&aabb, 32 * (size_t)total, stream));
-    const uint32_t sortBlocks = (n + RS_TILE - 1) / RS_TILE;
-    uint32_t* radixHist;
-    CK(cudaMallocAsync(&radixHist, 4 * 256 * ((size_t)sortBlocks + 1), stream));
+    const ScratchLayout L = scratch_layout(n);
+    uint8_t* base = (uint8_t*)scratch;
+    Prim* prims = (Prim*)(base + L.prims); Meta* meta = (Meta*)(base + L.meta);
+    uint32_t *codes = (uint32_t*)(base + L.codes), *order = (uint32_t*)(base + L.order);
+    uint32_t *codesAlt = (uint32_t*)(base + L.codesAlt), *orderAlt = (uint32_t*)(base + L.orderAlt);
+    uint32_t *sceneBox = (uint32_t*)(base + L.sceneBox), *numTris = (uint32_t*)(base + L.numTris);
+    uint32_t *baseCount = (uint32_t*)(base + L.baseCount), *baseRoots = (uint32_t*)(base + L.baseRoots);
+    HNode* H = (HNode*)(base + L.H); float* aabb = (float*)(base + L.aabb);
+    const uint32_t sortBlocks = L.sortBlocks;
+    uint32_t* radixHist = (uint32_t*)(base + L.radixHist);
     uint32_t* radixDigitStart = radixHist + 256 * (size_t)sortBlocks;
+    unsigned long long* arrive = (unsigned long long*)(base + L.arrive);
+    uint32_t* depthDev = (uint32_t*)(base + L.depth);
 
     uint32_t boxInit[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     CK(cudaMemcpyAsync(sceneBox, boxInit, sizeof(boxInit), cudaMemcpyHostToDevice, stream));
-    k_load_prims<<<grid(n), T, 0, stream>>>(d_geoms, d_triPrefix, numGeoms, d_positions, d_indices, n, prims, meta, sceneBox); lc.count++;
+    k_load_prims<<<grid(n), T, 0, stream>>>(d_geoms, d_triPrefix, numGeoms, n, prims, meta, sceneBox); lc.count++;
     k_morton<<<grid(n), T, 0, stream>>>(prims, n, sceneBox, codes, order); lc.count++;
     uint32_t *kIn = codes, *vIn = order, *kOut = codesAlt, *vOut = orderAlt;
     for (int shift = 0; shift < 30; shift += 8) {
@@ -752,15 +803,12 @@ cudaError_t build_bvh(const TbGeometryRecord* d_geoms, const uint32_t* d_triPref
             minTris *= 2;
         }
     }
-    CK(cudaMemsetAsync(numTris, 0, 4 * (size_t)(nInternal + 1), stream));
-    k_refit<<<grid(n), T, 0, stream>>>(n, H, bvh, numTris); lc.count++;
+    CK(cudaMemsetAsync(arrive, 0, 8 * (size_t)n, stream));
+    k_refit<<<grid(n), T, 0, stream>>>(n, H, bvh, arrive, depthDev); lc.count++;
     k_widen<<<grid(n), T, 0, stream>>>(n, bvh, out.pairs, out.tris); lc.count++;
     CK(cudaMemcpyAsync(&out.root, bvh + 16, sizeof(RefNode), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(&out.depth, depthDev, 4, cudaMemcpyDeviceToHost, stream));
     CK(cudaGetLastError());
-    cudaFreeAsync(prims, stream); cudaFreeAsync(meta, stream); cudaFreeAsync(codes, stream); cudaFreeAsync(order, stream);
-    cudaFreeAsync(codesAlt, stream); cudaFreeAsync(orderAlt, stream); cudaFreeAsync(sceneBox, stream); cudaFreeAsync(numTris, stream);
-    cudaFreeAsync(baseCount, stream); cudaFreeAsync(baseRoots, stream); cudaFreeAsync(H, stream); cudaFreeAsync(aabb, stream);
-    cudaFreeAsync(radixHist, stream);
     CK(cudaStreamSynchronize(stream));
     out.numPrims = n;
 #undef CK

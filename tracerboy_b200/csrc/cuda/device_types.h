@@ -26,6 +26,10 @@ struct PairNode {
 };
 struct WideTri { float4 v0, v1, v2; };
 
+// Entries of the per-ray traversal stack. A near-first BVH2 traversal keeps at most one waiting far child per tree
+// level, so a tree of depth <= TB_STACK_DEPTH can never overflow it; deeper trees are rejected after the build.
+#define TB_STACK_DEPTH 96
+
 struct DeviceBvh {
     uint8_t* ref = nullptr;      // reference-layout bytes
     uint64_t refBytes = 0;
@@ -33,6 +37,19 @@ struct DeviceBvh {
     WideTri* tris = nullptr;     // numPrims entries
     RefNode root;                // root node copy (box for the initial test; leaf flag if N==1)
     uint32_t numPrims = 0;
+    uint32_t depth = 0;          // height of the tree (0 = a single leaf): bounds the traversal stack
+};
+
+// One geometry of a build as the load kernel reads it: the caller's device buffers
+// (D3D12_RAYTRACING_GEOMETRY_TRIANGLES_DESC: vertex buffer + stride, optional 16 / 32 bit indices, optional 3x4 transform).
+struct BuildGeometry {
+    const uint8_t* positions;  // first vertex; float3 at every strideBytes
+    const void* indices;       // nullptr when indexFormat == 0
+    const float* transform;    // 12 floats, row-major 3x4, or nullptr
+    uint32_t strideBytes;
+    uint32_t indexFormat;      // 0 none, 2 uint16, 4 uint32
+    uint32_t flags;            // D3D12_RAYTRACING_GEOMETRY_FLAGS
+    uint32_t pad;
 };
 
 struct DeviceScene {
@@ -63,6 +80,7 @@ struct FrameConstants {
     int32_t selectedX, selectedY;
     float halton2, halton3; // Halton23(frame), RayGenCommon.h:79-82 (per-frame constant)
     uint32_t rowOffset, rowStride; // row-band shard: bands of 8 rows, band b is rendered iff b % rowStride == rowOffset
+    uint32_t worldPosSlot;  // which of the two world-position buffers this frame writes (local sample index & 1)
     uint32_t aovMask;       // AOV_FULL / AOV_WORLDPOS ownership of this frame (frames run concurrently)
     uint32_t clearAccum;    // 1 on the first frame this handle renders after an invalidate. Equals
                             // (GlobalFrameCount == 0) on one GPU; differs only under sample sharding.

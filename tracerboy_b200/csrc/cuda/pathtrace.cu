@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(256) k_raygen(DeviceScene sc, const FrameConst
         st.primaryHit[pi] = make_uint2(0xffffffffu, 0xffffffffu);
         st.counters[pi] = make_uint2(0, 0);
     }
-    if (fc.aovMask & AOV_WORLDPOS) st.aovWorldPos[fc.frame & 1][pi] = make_float4(0, 0, 0, 0);
+    if (fc.aovMask & AOV_WORLDPOS) st.aovWorldPos[fc.worldPosSlot][pi] = make_float4(0, 0, 0, 0);
     // per-frame staging of the two AOVs that persist when a frame does not write them
     st.stEmissive[pi] = make_float4(0, 0, 0, 0);
     st.stDepth[pi] = -1.0f;
@@ -827,7 +827,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, 
                         f3 nrp = mk3(nb.x, nb.y, nb.z) + mk3(nd.x, nd.y, nd.z) * h4.x;
                         f3 wp = mk3(0.0f) + RayPoint;
                         float dn = 0.0f + length(nrp - RayPoint);
-                        st.aovWorldPos[fc.frame & 1][pi] = make_float4(wp.x, wp.y, wp.z, dn);
+                        st.aovWorldPos[fc.worldPosSlot][pi] = make_float4(wp.x, wp.y, wp.z, dn);
                     }
                     if (fc.aovMask & AOV_FULL) st.aovNormal[pi] = make_float4(detailNormal.x, detailNormal.y, detailNormal.z, 1.0f);
                     st.stDepth[pi] = saturate(h4.x / S.MaxZ);
@@ -1279,11 +1279,6 @@ __global__ void k_trace_rays(DeviceBvh bvh, const TbRay* __restrict__ rays, uint
 } // namespace
 
 // ------------------------------------------------------------------ launchers
-static int g_numSMs = 0;
-static int num_sms() {
-    if (!g_numSMs) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_numSMs, cudaDevAttrMultiProcessorCount, dev); if (g_numSMs <= 0) g_numSMs = 148; }
-    return g_numSMs;
-}
 
 // Per-frame constants live in device memory (one copy per frame slot) so that the frame's kernel sequence can be
 // captured once into a CUDA graph and replayed: nothing baked into the graph changes from frame to frame.
@@ -1301,7 +1296,7 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
     cudaMemsetAsync(st.susCount, 0, 16, stream);
     k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(sc, fcDev, st); launches++;
     // persistent grids: a multiple of the SM count, capped by the work available
-    const uint32_t sms = (uint32_t)num_sms();
+    const uint32_t sms = (uint32_t)(opts.numSMs > 0 ? opts.numSMs : 148);
     const uint32_t maxBlocks = sms * 16;
     uint32_t blocks = (n + 127) / 128;
     if (blocks > maxBlocks) blocks = maxBlocks;
@@ -1410,7 +1405,6 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
                            opts.sceneHasSSS ? 1u : 0u, opts.suspendRays ? 1u : 0u, (uint32_t)opts.sortRays};
     if (!graph->exec || memcmp(&key, &graph->key, sizeof(key)) != 0) {
         graph->reset();
-        (void)num_sms(); // device query outside the capture
         cudaGraph_t g = nullptr;
         cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
         if (e != cudaSuccess) return e;
@@ -1440,9 +1434,9 @@ cudaError_t resolve_rgb(const float4* accum, float* rgb, uint32_t n, cudaStream_
     return cudaGetLastError();
 }
 
-cudaError_t trace_rays(const DeviceBvh& bvh, const TbRay* d_rays, uint64_t n, TbHit* d_hits, cudaStream_t stream, LaunchCounter& lc) {
+cudaError_t trace_rays(const DeviceBvh& bvh, const TbRay* d_rays, uint64_t n, TbHit* d_hits, int numSMs, cudaStream_t stream, LaunchCounter& lc) {
     uint64_t blocks = (n + 127) / 128;
-    uint64_t cap = (uint64_t)num_sms() * 16;
+    uint64_t cap = (uint64_t)(numSMs > 0 ? numSMs : 148) * 16;
     if (blocks > cap) blocks = cap;
     if (blocks == 0) return cudaSuccess;
     k_trace_rays<<<(uint32_t)blocks, 128, 0, stream>>>(bvh, d_rays, n, d_hits); lc.count++;

@@ -97,13 +97,14 @@ struct RenderOptions {
     int walkRounds = 1; // glass / subsurface walk: wavefront rounds (k_extend<EXT_WALK> + k_walk_step) before the persistent tail kernel
     bool suspendRays = true; // park rays over budget and resume them in k_extend_resume rounds (set by the host: on with fewer than 8 frames in flight)
     int sortRays = 2;   // spatial sort of the ray queues before traversal: 0 off, bit 0 bounce queue, bit 1 shadow queue (1 or 3), 2 automatic (3 for scenes whose BVH is far beyond L2)
+    int numSMs = 148;   // of the handle's device (persistent grids are sized from it)
     bool sceneHasSSS = true; // any material with the subsurface flag (selects the k_shade variant with the inline random walk)
 };
 
 uint64_t bvh_ref_bytes(uint32_t numPrims);
-cudaError_t build_bvh(const TbGeometryRecord* d_geoms, const uint32_t* d_triPrefix, uint32_t numGeoms,
-                      const float* d_positions, const uint32_t* d_indices, uint32_t numPrims, int treeletPasses,
-                      DeviceBvh& out, cudaStream_t stream, LaunchCounter& lc);
+uint64_t bvh_scratch_bytes(uint32_t numPrims);
+cudaError_t build_bvh(const BuildGeometry* d_geoms, const uint32_t* d_triPrefix, uint32_t numGeoms, uint32_t numPrims, int treeletPasses,
+                      DeviceBvh& out, void* scratch, cudaStream_t stream, LaunchCounter& lc);
 // The captured kernel sequence of one frame on one frame slot (see render_frame).
 struct FrameGraph {
     struct Key { uint32_t epoch, width, height, maxBounces, heat, nee, shadowMode, walkRounds, sss, suspend, sort; }; // no padding: compared with memcmp
@@ -116,6 +117,6 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
                          cudaStream_t stream, LaunchCounter& lc, KernelTimers* timers, const RenderOptions& opts, FrameGraph* graph);
 cudaError_t accumulate_frame(const FrameConstants& fc, PathState& st, cudaStream_t stream, LaunchCounter& lc);
 cudaError_t resolve_rgb(const float4* accum, float* rgb, uint32_t n, cudaStream_t stream, LaunchCounter& lc);
-cudaError_t trace_rays(const DeviceBvh& bvh, const TbRay* d_rays, uint64_t n, TbHit* d_hits, cudaStream_t stream, LaunchCounter& lc);
+cudaError_t trace_rays(const DeviceBvh& bvh, const TbRay* d_rays, uint64_t n, TbHit* d_hits, int numSMs, cudaStream_t stream, LaunchCounter& lc);
 
 } // namespace tbd

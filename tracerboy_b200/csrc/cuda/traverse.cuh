@@ -23,7 +23,8 @@ struct HitRec {
     uint32_t tris, boxes;
 };
 
-#define TB_STACK_DEPTH 96
+// TB_STACK_DEPTH (device_types.h) bounds the waiting far children: at most one per level of the tree, and the host
+// refuses to hand out a BVH deeper than that (DeviceBvh::depth, measured by the builder), so a push never overflows.
 // The memory stack is `uint32_t stack[TB_STACK_WORDS]`: word 0 is a sentinel (TB_NO_NODE, written by
 // begin()/resume()), words 1..depth are the waiting far children. Popping the sentinel ends the traversal,
 // so pop is one unconditional load with no emptiness test.
@@ -201,7 +202,7 @@ struct Traversal {
         const bool takeRight = rh && (!lh || rt < lt); // both hit: right only when strictly nearer (:754-765)
         const uint32_t nearRef = takeRight ? rref : lref;
         const uint32_t farRef = takeRight ? lref : rref;
-        if (both && sp < TB_STACK_DEPTH) { ++sp; stack[sp] = farRef; }
+        if (both) { ++sp; stack[sp] = farRef; } // never overflows: sp <= tree depth <= TB_STACK_DEPTH (checked by the host after the build)
         cur = nearRef;
         if (!(lh || rh)) pop(stack);
     }

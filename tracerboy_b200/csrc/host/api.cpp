@@ -8,75 +8,19 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
 #include "../cuda/pathtrace.h"
 #include "../cuda/postprocess.h"
-#include "scene.h"
-#include "tracerboy_b200.h"
+#include "handle.h"
 
 using namespace tbd;
 
-struct TbHandle {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    std::string err;
-    tb::Scene scene;
-    bool sceneLoaded = false;
-    // device scene
-    DeviceScene dscene;
-    std::vector<void*> sceneAllocs;
-    DeviceBvh bvh;
-    double bvhBuildMs = 0.0;
-    // render state
-    PathState st;                   // shared buffers (+ slot 0's private ones)
-    // Frames in flight: each slot owns private path state + staging and its own stream, so the
-    // long tail of one frame's traversal kernels overlaps the next frames' work. h->stream is
-    // the accumulate stream: k_accumulate runs there in frame order.
-    struct Slot { PathState st; cudaStream_t stream = nullptr; cudaEvent_t frameDone = nullptr, accDone = nullptr;
-                  FrameConstants* fcDev = nullptr; FrameGraph graph; };
-    std::vector<Slot> slots;
-    uint32_t framesInFlight = 0;    // 0 = automatic (memory budget), see tb_resize
-    uint64_t framesIssued = 0;
-    std::vector<void*> frameAllocs;
-    float* resolved = nullptr;
-    float4* post = nullptr;         // PostProcessCS output (float4) ...
-    uchar4* post8 = nullptr;        // ... and after the UNORM8 back-buffer store
-    uint32_t* lumHist = nullptr;    // LuminanceHistogram[256] + AveragedLuminance
-    int numSMs = 148;
-    uint32_t width = 0, height = 0;
-    TbCamera camera{};
-    uint32_t samplesRendered = 0; // local samples since the last invalidate
-    uint32_t shardOffset = 0, shardStride = 1;
-    uint32_t rowOffset = 0, rowStride = 1;
-    int selX = -1, selY = -1;
-    uint32_t lastMouse[2] = {0, 0}; // m_mouseX, m_mouseY (TracerBoy.cpp:511-512)
-    LaunchCounter lc;
-    double deviceMs = 0.0;
-    uint64_t pathsStarted = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::chrono::steady_clock::time_point renderStart;
-    bool timing = false;
-    std::mutex statusLock;
-    TbSceneLoadStatus status{TB_LOAD_IDLE, 0, 0};
-    std::vector<uint8_t> blueNoiseHost;
-    bool profiling = false;
-    RenderOptions options;
-    KernelTimers timers;
-    double extendMs = 0.0, shadeMs = 0.0, resumeMs = 0.0;
-    uint64_t extendLaunches = 0;
-};
-
-static std::string g_createError;
 static std::string g_libDir;
-
-static int fail(TbHandle* h, int code, const std::string& msg) {
-    if (h) h->err = msg; else g_createError = msg;
-    return code;
-}
-#define CUDA_OK(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(h, TB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
+namespace tbh { std::string& create_error() { static std::string e; return e; } }
 
 static std::string lib_dir() {
     if (!g_libDir.empty()) return g_libDir;
@@ -122,6 +66,7 @@ static void free_frame(TbHandle* h) {
         if (sl.accDone) cudaEventDestroy(sl.accDone);
     }
     h->slots.clear();
+    tbh::comm_release_buffers(h);
     free_list(h->frameAllocs);
     h->st = PathState();
     h->resolved = nullptr;
@@ -145,13 +90,49 @@ static void set_status(TbHandle* h, uint32_t state, uint32_t loaded, uint32_t to
     h->status.State = state; h->status.InstancesLoaded = loaded; h->status.TotalInstances = total;
 }
 
+static bool scene_has_sss(const tb::Scene& s) {
+    // subsurface / glass materials reachable from the geometry (directly or through a mix material)
+    for (const TbGeometryRecord& g : s.geoms) {
+        const TbMaterial& m = s.materials[g.MaterialIndex];
+        uint32_t ids[3] = {g.MaterialIndex, g.MaterialIndex, g.MaterialIndex};
+        if (m.Flags & TB_MIX_MATERIAL_FLAG) { ids[1] = (uint32_t)m.albedo.x; ids[2] = (uint32_t)m.albedo.y; }
+        for (uint32_t id : ids)
+            if (id < s.materials.size() && (s.materials[id].Flags & TB_SUBSURFACE_SCATTER_MATERIAL_FLAG)) return true;
+    }
+    return false;
+}
+
+// One build on caller-described device geometry into caller-provided (or library-owned) memory. Shared by the scene
+// path (upload_and_build) and the SW-RT seam (tb_bvh_build_device).
+static int run_build(TbHandle* h, const std::vector<BuildGeometry>& descs, const std::vector<uint32_t>& prefix, uint32_t n,
+                     uint32_t flags, DeviceBvh& out, void* scratch, cudaStream_t stream) {
+    void* owned[3] = {nullptr, nullptr, nullptr};
+    struct Guard { void** p; ~Guard() { for (int i = 0; i < 3; i++) if (p[i]) cudaFree(p[i]); } } guard{owned};
+    CUDA_OK(h, cudaMalloc(&owned[0], sizeof(BuildGeometry) * descs.size()));
+    CUDA_OK(h, cudaMalloc(&owned[1], 4 * prefix.size()));
+    CUDA_OK(h, cudaMemcpyAsync(owned[0], descs.data(), sizeof(BuildGeometry) * descs.size(), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(h, cudaMemcpyAsync(owned[1], prefix.data(), 4 * prefix.size(), cudaMemcpyHostToDevice, stream));
+    if (!scratch) { // no caller scratch: one allocation of the library's own, released after the build
+        CUDA_OK(h, cudaMalloc(&owned[2], bvh_scratch_bytes(n)));
+        scratch = owned[2];
+    }
+    int passes = (flags & TB_BVH_BUILD_PREFER_FAST_BUILD) ? 0 : ((flags & TB_BVH_BUILD_PREFER_FAST_TRACE) ? 3 : 1); // TreeletReorder.cpp:63-78
+    CUDA_OK(h, build_bvh((const BuildGeometry*)owned[0], (const uint32_t*)owned[1], (uint32_t)descs.size(), n, passes, out, scratch, stream, h->lc));
+    if (out.depth > TB_STACK_DEPTH)
+        return fail(h, TB_ERR_NOT_IMPL, "the built BVH is " + std::to_string(out.depth) + " levels deep; the traversal stack holds " +
+                                         std::to_string(TB_STACK_DEPTH) + " waiting nodes (no ray is ever dropped silently)");
+    return TB_OK;
+}
+
 // Uploads h->scene and builds the BVH.
 static int upload_and_build(TbHandle* h, uint32_t flags) {
     tb::Scene& s = h->scene;
-    if (s.numTriangles() == 0) return fail(h, TB_ERR_INVALID_ARG, "scene has no triangles");
-    if (2ull * s.numTriangles() - 1 > (1ull << 30)) return fail(h, TB_ERR_INVALID_ARG, "too many triangles (30-bit node indices)");
     CUDA_OK(h, cudaSetDevice(h->device));
-    free_scene(h);
+    free_scene(h); // whatever happens below, the previous device scene is gone (sceneLoaded = false)
+    if (s.numTriangles() == 0) return fail(h, TB_ERR_INVALID_ARG, "scene has no triangles");
+    if (s.numTriangles() > tb_max_triangles()) return fail(h, TB_ERR_INVALID_ARG, "too many triangles (the reference BVH layout has 32-bit byte offsets: 116 N - 16 must stay below 4 GiB)");
+    std::string why;
+    if (!tb::validate_scene(s, why)) return fail(h, TB_ERR_INVALID_ARG, "invalid scene: " + why);
     set_status(h, TB_RECORDING_DEVICE_WORK, (uint32_t)s.geoms.size(), (uint32_t)s.geoms.size());
     DeviceScene& d = h->dscene;
     CUDA_OK(h, upload(h, h->sceneAllocs, s.geoms.data(), s.geoms.size(), &d.geoms));
@@ -174,36 +155,40 @@ static int upload_and_build(TbHandle* h, uint32_t flags) {
     d.envImage = s.envImage; d.flipTextureUVs = s.flipTextureUVs;
     for (int r = 0; r < 3; r++) { d.envTransform[r][0] = s.envTransform[r].x; d.envTransform[r][1] = s.envTransform[r].y; d.envTransform[r][2] = s.envTransform[r].z; d.envTransform[r][3] = s.envTransform[r].w; }
     d.envColorScale[0] = s.envColorScale.x; d.envColorScale[1] = s.envColorScale.y; d.envColorScale[2] = s.envColorScale.z;
-    // per-geometry triangle prefix (LoadPrimitivesPass.cpp:70-166 walks the descs in order)
+    // per-geometry triangle prefix (LoadPrimitivesPass.cpp:70-166 walks the descs in order); the pooled arrays are
+    // described to the builder the way a D3D12 caller describes its vertex / index buffers
     std::vector<uint32_t> prefix(s.geoms.size());
+    std::vector<BuildGeometry> descs(s.geoms.size());
     uint32_t n = 0;
-    for (size_t g = 0; g < s.geoms.size(); g++) { prefix[g] = n; n += s.geoms[g].IndexCount / 3; }
-    const uint32_t* dPrefix = nullptr;
-    CUDA_OK(h, upload(h, h->sceneAllocs, prefix.data(), prefix.size(), &dPrefix));
+    for (size_t g = 0; g < s.geoms.size(); g++) {
+        const TbGeometryRecord& G = s.geoms[g];
+        prefix[g] = n; n += G.IndexCount / 3;
+        descs[g] = {(const uint8_t*)(d.positions + 3 * (size_t)G.VertexFirst), d.indices + G.IndexFirst, nullptr, 12u, 4u, G.GeometryFlags, 0u};
+    }
     h->bvh.refBytes = bvh_ref_bytes(n);
     CUDA_OK(h, cudaMalloc((void**)&h->bvh.ref, h->bvh.refBytes));
     CUDA_OK(h, cudaMalloc((void**)&h->bvh.pairs, sizeof(PairNode) * (size_t)(n > 1 ? n - 1 : 1)));
     CUDA_OK(h, cudaMalloc((void**)&h->bvh.tris, sizeof(WideTri) * (size_t)n));
-    int passes = (flags & TB_BVH_BUILD_PREFER_FAST_BUILD) ? 0 : ((flags & TB_BVH_BUILD_PREFER_FAST_TRACE) ? 3 : 1); // TreeletReorder.cpp:63-78
+    // the builder's scratch is kept between builds of the same handle (reloading a scene of the same size reuses it)
+    const uint64_t need = bvh_scratch_bytes(n);
+    if (h->buildScratchBytes < need) {
+        if (h->buildScratch) cudaFree(h->buildScratch);
+        h->buildScratch = nullptr; h->buildScratchBytes = 0;
+        CUDA_OK(h, cudaMalloc(&h->buildScratch, need));
+        h->buildScratchBytes = need;
+    }
     set_status(h, TB_WAITING_ON_GPU, (uint32_t)s.geoms.size(), (uint32_t)s.geoms.size());
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     CUDA_OK(h, cudaEventRecord(h->ev0, h->stream));
-    CUDA_OK(h, build_bvh(d.geoms, dPrefix, d.numGeoms, d.positions, d.indices, n, passes, h->bvh, h->stream, h->lc));
+    int rc = run_build(h, descs, prefix, n, flags, h->bvh, h->buildScratch, h->stream);
+    if (rc != TB_OK) return rc;
     CUDA_OK(h, cudaEventRecord(h->ev1, h->stream));
     CUDA_OK(h, cudaEventSynchronize(h->ev1));
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->bvhBuildMs = ms;
     h->camera = s.camera;
-    // subsurface / glass materials reachable from the geometry (directly or through a mix material)
-    h->options.sceneHasSSS = false;
-    for (const TbGeometryRecord& g : s.geoms) {
-        const TbMaterial& m = s.materials[g.MaterialIndex];
-        uint32_t ids[3] = {g.MaterialIndex, g.MaterialIndex, g.MaterialIndex};
-        if (m.Flags & TB_MIX_MATERIAL_FLAG) { ids[1] = (uint32_t)m.albedo.x; ids[2] = (uint32_t)m.albedo.y; }
-        for (uint32_t id : ids)
-            if (id < s.materials.size() && (s.materials[id].Flags & TB_SUBSURFACE_SCATTER_MATERIAL_FLAG)) h->options.sceneHasSSS = true;
-    }
+    h->options.sceneHasSSS = scene_has_sss(s);
     h->sceneLoaded = true;
     h->samplesRendered = 0;
     set_status(h, TB_LOAD_FINISHED, (uint32_t)s.geoms.size(), (uint32_t)s.geoms.size());
@@ -212,9 +197,14 @@ static int upload_and_build(TbHandle* h, uint32_t flags) {
 
 extern "C" {
 
+// Largest triangle count one acceleration structure can hold: the reference layout's header and leaf records carry
+// 32-bit byte offsets (RayTracingHlslCompat.h:344-398), so 116 N - 16 must stay below 4 GiB (and 2N - 1 nodes below
+// the 30-bit node index, which is the weaker bound).
+TB_API uint64_t tb_max_triangles(void) { return ((1ull << 32) - 1 + 16) / 116; }
+
 TB_API const char* tb_version(void) { return "tracerboy_b200 0.1 (sm_100a)"; }
 
-TB_API const char* tb_last_error(TbHandle* h) { return h ? h->err.c_str() : g_createError.c_str(); }
+TB_API const char* tb_last_error(TbHandle* h) { return h ? h->err.c_str() : tbh::create_error().c_str(); }
 
 TB_API int tb_create(int device, TbHandle** out) {
     if (!out) return fail(nullptr, TB_ERR_INVALID_ARG, "out is null");
@@ -229,11 +219,19 @@ TB_API int tb_create(int device, TbHandle** out) {
     if (device < 0 || device >= count) return fail(nullptr, TB_ERR_INVALID_ARG, "device ordinal out of range");
     TbHandle* h = new TbHandle();
     h->device = device;
+    auto abandon = [&]() {
+        if (h->ev0) cudaEventDestroy(h->ev0);
+        if (h->ev1) cudaEventDestroy(h->ev1);
+        if (h->stream) cudaStreamDestroy(h->stream);
+        delete h;
+    };
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
-        delete h;
+        abandon();
         return fail(nullptr, TB_ERR_CUDA, "cannot initialise CUDA stream/events");
     }
+    if (cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->numSMs <= 0) h->numSMs = 148;
+    h->options.numSMs = h->numSMs;
     // The builder's temporaries come from the device's default stream-ordered pool; keep up to 16 GiB of it
     // mapped between builds instead of handing it back to the driver at every synchronise.
     {
@@ -250,8 +248,7 @@ TB_API int tb_create(int device, TbHandle** out) {
     FILE* f = fopen(bn.c_str(), "rb");
     if (!f || fread(h->blueNoiseHost.data(), 1, h->blueNoiseHost.size(), f) != h->blueNoiseHost.size()) {
         if (f) fclose(f);
-        cudaStreamDestroy(h->stream);
-        delete h;
+        abandon();
         return fail(nullptr, TB_ERR_IO, "cannot read blue-noise table " + bn);
     }
     fclose(f);
@@ -263,8 +260,10 @@ TB_API void tb_destroy(TbHandle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    tbh::comm_destroy(h);
     free_frame(h);
     free_scene(h);
+    if (h->buildScratch) cudaFree(h->buildScratch);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);
@@ -297,8 +296,10 @@ static int load_host_scene(TbHandle* h, tb::Scene& s, const char* path) {
 TB_API int tb_load_scene_ex(TbHandle* h, const char* path, uint32_t flags) {
     if (!h || !path) return fail(h, TB_ERR_INVALID_ARG, "null argument");
     set_status(h, TB_LOADING_PBRT, 0, 0);
-    int rc = load_host_scene(h, h->scene, path);
+    tb::Scene incoming; // a failed import leaves the handle's current scene (host mirror and device copy) untouched
+    int rc = load_host_scene(h, incoming, path);
     if (rc != TB_OK) { set_status(h, TB_LOAD_FAILED, 0, 0); return rc; }
+    h->scene = std::move(incoming);
     set_status(h, TB_LOADING_HOST, 0, (uint32_t)h->scene.geoms.size());
     rc = upload_and_build(h, flags);
     if (rc != TB_OK) set_status(h, TB_LOAD_FAILED, 0, 0);
@@ -542,8 +543,6 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
     CUDA_OK(h, alloc((void**)&h->resolved, 12 * n));
     CUDA_OK(h, alloc((void**)&h->post, 16 * n)); CUDA_OK(h, alloc((void**)&h->post8, 4 * n));
     CUDA_OK(h, alloc((void**)&h->lumHist, 257 * sizeof(uint32_t)));
-    cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, h->device);
-    if (h->numSMs <= 0) h->numSMs = 148;
     CUDA_OK(h, cudaStreamSynchronize(h->stream)); // memsets done before the slot streams touch the buffers
     h->width = w; h->height = hh;
     h->samplesRendered = 0;
@@ -581,6 +580,7 @@ TB_API int tb_render(TbHandle* h, const TbOutputSettings* s, uint32_t nSamples, 
         uint32_t left = (int)h->samplesRendered >= s->SampleLimit ? 0u : (uint32_t)s->SampleLimit - h->samplesRendered;
         if (todo > left) todo = left;
     }
+    if (h->comm && todo) h->comm->valid = false; // the job-wide image is stale from here on
     const bool timeLimited = s->TimeLimitInSeconds > 0.0f;
     const bool serial = timeLimited || h->profiling;
     CUDA_OK(h, cudaEventRecord(h->ev0, h->stream));
@@ -603,6 +603,9 @@ TB_API int tb_render(TbHandle* h, const TbOutputSettings* s, uint32_t nSamples, 
         fc.rowOffset = h->rowOffset; fc.rowStride = h->rowStride;
         const bool last = serial || i + 1 == todo;
         fc.aovMask = last ? 3u : (i + 2 == todo ? 2u : 0u);
+        // world-position ping-pong by the LOCAL sample index: under sample sharding the global frame index advances
+        // by the stride, whose parity may never change (the last two frames would then share a buffer)
+        fc.worldPosSlot = h->samplesRendered & 1u;
         TbHandle::Slot& sl = h->slots[serial ? 0 : h->framesIssued % h->slots.size()];
         // the slot's previous frame must have been consumed by its k_accumulate
         CUDA_OK(h, cudaStreamWaitEvent(sl.stream, sl.accDone, 0));
@@ -644,6 +647,7 @@ TB_API int tb_set_frame_shard(TbHandle* h, uint32_t offset, uint32_t stride) {
     if (!h || stride == 0 || offset >= stride) return fail(h, TB_ERR_INVALID_ARG, "need offset < stride");
     h->shardOffset = offset; h->shardStride = stride;
     h->samplesRendered = 0;
+    if (h->comm) h->comm->valid = false;
     return TB_OK;
 }
 
@@ -651,6 +655,7 @@ TB_API int tb_set_row_shard(TbHandle* h, uint32_t offset, uint32_t stride) {
     if (!h || stride == 0 || offset >= stride) return fail(h, TB_ERR_INVALID_ARG, "need offset < stride");
     h->rowOffset = offset; h->rowStride = stride;
     h->samplesRendered = 0;
+    if (h->comm) h->comm->valid = false;
     if (h->width) { // pixels of other shards must read as zero
         CUDA_OK(h, cudaSetDevice(h->device));
         size_t n = (size_t)h->width * h->height;
@@ -661,16 +666,24 @@ TB_API int tb_set_row_shard(TbHandle* h, uint32_t offset, uint32_t stride) {
     return TB_OK;
 }
 
+// With a communicator the accumulation buffers a caller sees are the job-wide ones; the reduction (collective) runs
+// here when frames were rendered since the last one.
+static int job_wide_current(TbHandle* h) {
+    if (h->comm && !h->comm->valid) return tb_comm_reduce(h);
+    return TB_OK;
+}
+static const float4* accum_view(TbHandle* h) { return h->comm ? h->comm->reducedAccum : h->st.accum; }
+
 static int buffer_info(TbHandle* h, uint32_t kind, void** p, uint64_t* bytes) {
     size_t n = (size_t)h->width * h->height;
     PathState& st = h->st;
     switch (kind) {
-    case TB_BUF_ACCUM_RGBW: *p = st.accum; *bytes = 16 * n; break;
-    case TB_BUF_JITTERED_RGBW: *p = st.jittered; *bytes = 16 * n; break;
+    case TB_BUF_ACCUM_RGBW: *p = h->comm ? h->comm->reducedAccum : st.accum; *bytes = 16 * n; break;
+    case TB_BUF_JITTERED_RGBW: *p = h->comm ? h->comm->reducedJittered : st.jittered; *bytes = 16 * n; break;
     case TB_BUF_RESOLVED_RGB: *p = h->resolved; *bytes = 12 * n; break;
     case TB_BUF_AOV_NORMAL: *p = st.aovNormal; *bytes = 16 * n; break;
     case TB_BUF_AOV_WORLDPOS: {
-        uint32_t last = h->shardOffset + (h->samplesRendered ? h->samplesRendered - 1 : 0) * h->shardStride;
+        uint32_t last = h->samplesRendered ? h->samplesRendered - 1 : 0;
         *p = st.aovWorldPos[last & 1]; *bytes = 16 * n; break;
     }
     case TB_BUF_AOV_DEPTH: *p = st.aovDepth; *bytes = 4 * n; break;
@@ -681,6 +694,7 @@ static int buffer_info(TbHandle* h, uint32_t kind, void** p, uint64_t* bytes) {
     case TB_BUF_POSTPROCESS_RGBA: *p = h->post; *bytes = 16 * n; break;
     case TB_BUF_BACKBUFFER_RGBA8: *p = h->post8; *bytes = 4 * n; break;
     case TB_BUF_LUMINANCE_HISTOGRAM: *p = h->lumHist; *bytes = 257 * sizeof(uint32_t); break;
+    case TB_BUF_LOCAL_ACCUM_RGBW: *p = st.accum; *bytes = 16 * n; break;
     default: return fail(h, TB_ERR_INVALID_ARG, "unknown buffer kind");
     }
     return TB_OK;
@@ -696,10 +710,11 @@ TB_API int tb_buffer_size(TbHandle* h, uint32_t kind, uint64_t* bytes) {
 TB_API int tb_device_buffer(TbHandle* h, uint32_t kind, void** devPtr, uint64_t* bytes) {
     if (!h || !devPtr || !bytes) return fail(h, TB_ERR_INVALID_ARG, "null argument");
     if (!h->width) return fail(h, TB_ERR_STATE, "no frame buffers (tb_resize)");
+    if (kind <= TB_BUF_RESOLVED_RGB) { int rr = job_wide_current(h); if (rr != TB_OK) return rr; }
     int rc = buffer_info(h, kind, devPtr, bytes);
     if (rc == TB_OK && kind == TB_BUF_RESOLVED_RGB) {
         CUDA_OK(h, cudaSetDevice(h->device));
-        CUDA_OK(h, resolve_rgb(h->st.accum, h->resolved, h->width * h->height, h->stream, h->lc));
+        CUDA_OK(h, resolve_rgb(accum_view(h), h->resolved, h->width * h->height, h->stream, h->lc));
         CUDA_OK(h, cudaStreamSynchronize(h->stream));
     }
     return rc;
@@ -709,11 +724,12 @@ TB_API int tb_readback(TbHandle* h, uint32_t kind, void* dst, uint64_t bytes) {
     if (!h || !dst) return fail(h, TB_ERR_INVALID_ARG, "null argument");
     if (!h->width) return fail(h, TB_ERR_STATE, "no frame buffers (tb_resize)");
     void* p; uint64_t need;
+    if (kind <= TB_BUF_RESOLVED_RGB) { int rr = job_wide_current(h); if (rr != TB_OK) return rr; }
     int rc = buffer_info(h, kind, &p, &need);
     if (rc != TB_OK) return rc;
     if (bytes < need) return fail(h, TB_ERR_INVALID_ARG, "destination too small");
     CUDA_OK(h, cudaSetDevice(h->device));
-    if (kind == TB_BUF_RESOLVED_RGB) CUDA_OK(h, resolve_rgb(h->st.accum, h->resolved, h->width * h->height, h->stream, h->lc));
+    if (kind == TB_BUF_RESOLVED_RGB) CUDA_OK(h, resolve_rgb(accum_view(h), h->resolved, h->width * h->height, h->stream, h->lc));
     CUDA_OK(h, cudaMemcpyAsync(dst, p, need, cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     return TB_OK;
@@ -733,7 +749,12 @@ TB_API int tb_postprocess(TbHandle* h, uint32_t outputType, const TbPostProcessS
     const void* in = nullptr;
     bool scalar = false;
     switch (outputType) { // GetOutputSRV, TracerBoy.cpp:2354-2383
-    case TB_OUTPUT_LIT: case TB_OUTPUT_LUMINANCE: case TB_OUTPUT_LIVE_WAVES: in = h->st.accum; break;
+    case TB_OUTPUT_LIT: case TB_OUTPUT_LUMINANCE: case TB_OUTPUT_LIVE_WAVES: {
+        int rr = job_wide_current(h);
+        if (rr != TB_OK) return rr;
+        in = accum_view(h);
+        break;
+    }
     case TB_OUTPUT_ALBEDO: case TB_OUTPUT_LIVE_PIXELS: case TB_OUTPUT_HEATMAP: in = h->st.aovAlbedo; break;
     case TB_OUTPUT_NORMALS: in = h->st.aovNormal; break;
     case TB_OUTPUT_DEPTH: in = h->st.aovDepth; scalar = true; break;
@@ -915,8 +936,10 @@ TB_API int tb_get_material(TbHandle* h, int id, TbMaterial* out, char* name, uin
 TB_API int tb_set_material(TbHandle* h, int id, const TbMaterial* m) {
     if (!h || !m) return fail(h, TB_ERR_INVALID_ARG, "null argument");
     if (!tb_is_material_id_valid(h, id)) return fail(h, TB_ERR_INVALID_ARG, "invalid material id");
+    std::string why;
+    if (!tb::validate_material(h->scene, *m, why)) return fail(h, TB_ERR_INVALID_ARG, why); // the kernels index textures / mixed materials unchecked
     h->scene.materials[id] = *m;
-    if (m->Flags & TB_SUBSURFACE_SCATTER_MATERIAL_FLAG) h->options.sceneHasSSS = true;
+    h->options.sceneHasSSS = scene_has_sss(h->scene); // also through mix materials that reference the edited one
     CUDA_OK(h, cudaSetDevice(h->device));
     CUDA_OK(h, cudaMemcpyAsync((void*)(h->dscene.materials + id), m, sizeof(*m), cudaMemcpyHostToDevice, h->stream));
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
@@ -924,19 +947,134 @@ TB_API int tb_set_material(TbHandle* h, int id, const TbMaterial* m) {
     return TB_OK;
 }
 
+// ---- SW-RT seam. A caller-owned acceleration structure (`dst` of tb_bvh_build_device) is laid out as
+//   [0, 116 N - 16)          the reference layout (RayTracingHlslCompat.h:344-398)
+//   [A, A + 256)             AsTrailer, A = the reference layout's size rounded up to 256
+//   [A + 256, ...)           PairNode[max(N - 1, 1)], then (256-aligned) WideTri[N]: the traversal layout
+// so the buffer is self-describing: any handle can trace against it.
+namespace {
+struct AsTrailer { char magic[8]; uint32_t numPrims, depth; RefNode root; };
+inline uint64_t up256(uint64_t v) { return (v + 255) & ~255ull; }
+struct AsLayout { uint64_t trailer, pairs, tris, end; };
+AsLayout as_layout(uint32_t n) {
+    AsLayout L;
+    L.trailer = up256(bvh_ref_bytes(n));
+    L.pairs = L.trailer + 256;
+    L.tris = up256(L.pairs + sizeof(PairNode) * (uint64_t)(n > 1 ? n - 1 : 1));
+    L.end = L.tris + sizeof(WideTri) * (uint64_t)n;
+    return L;
+}
+int count_triangles(const TbGeometryDesc* geoms, uint32_t n, uint64_t* tris) {
+    *tris = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (geoms[i].Indices == nullptr && geoms[i].IndexFormat != 0) return TB_ERR_INVALID_ARG; // LoadPrimitivesPass.cpp:73-76
+        if (geoms[i].IndexFormat != 0 && geoms[i].IndexFormat != 2 && geoms[i].IndexFormat != 4) return TB_ERR_INVALID_ARG;
+        uint32_t vc = geoms[i].IndexFormat == 0 ? geoms[i].VertexCount : geoms[i].IndexCount;
+        *tris += vc / 3;
+    }
+    return TB_OK;
+}
+} // namespace
+
 TB_API int tb_bvh_prebuild_info(const TbGeometryDesc* geoms, uint32_t n, TbPrebuildInfo* out) {
     if (!geoms || !out) return TB_ERR_INVALID_ARG;
     uint64_t tris = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        if (geoms[i].Indices == nullptr && geoms[i].IndexFormat != 0) return TB_ERR_INVALID_ARG; // LoadPrimitivesPass.cpp:73-76
-        uint32_t vc = geoms[i].IndexFormat == 0 ? geoms[i].VertexCount : geoms[i].IndexCount;
-        tris += vc / 3;
-    }
-    if (tris == 0) { memset(out, 0, sizeof(*out)); return TB_OK; }
-    out->ResultDataMaxSizeInBytes = bvh_ref_bytes((uint32_t)tris);
-    // scratch: unsorted prims+meta, codes/order double buffers, hierarchy, AABBs, counters
-    out->ScratchDataSizeInBytes = tris * (40 + 12 + 16 + 4 + 4) + (2 * tris) * (12 + 24);
+    int rc = count_triangles(geoms, n, &tris);
+    if (rc != TB_OK) return rc;
+    memset(out, 0, sizeof(*out));
+    if (tris == 0) return TB_OK;
+    if (tris > tb_max_triangles()) return TB_ERR_INVALID_ARG; // E_INVALIDARG: the result would not fit the layout's 32-bit offsets
+    out->ReferenceLayoutSizeInBytes = bvh_ref_bytes((uint32_t)tris);
+    out->ResultDataMaxSizeInBytes = as_layout((uint32_t)tris).end;
+    out->ScratchDataSizeInBytes = bvh_scratch_bytes((uint32_t)tris);
     out->UpdateScratchDataSizeInBytes = 0;
+    return TB_OK;
+}
+
+TB_API int tb_bvh_build_device(TbHandle* h, const TbGeometryDesc* geoms, uint32_t n, uint32_t flags, void* dst, uint64_t dstBytes,
+                               void* scratch, uint64_t scratchBytes, void* cudaStream) {
+    if (!h || !geoms || n == 0 || !dst) return fail(h, TB_ERR_INVALID_ARG, "null/empty argument");
+    uint64_t tris = 0;
+    if (count_triangles(geoms, n, &tris) != TB_OK) return fail(h, TB_ERR_INVALID_ARG, "bad index format (If the index buffer is null, the index format must be 0)");
+    if (tris == 0) return fail(h, TB_ERR_INVALID_ARG, "no triangles");
+    if (tris > tb_max_triangles()) return fail(h, TB_ERR_INVALID_ARG, "too many triangles");
+    const uint32_t N = (uint32_t)tris;
+    const AsLayout L = as_layout(N);
+    if (dstBytes < L.end) return fail(h, TB_ERR_INVALID_ARG, "destination smaller than ResultDataMaxSizeInBytes");
+    if (scratch && scratchBytes < bvh_scratch_bytes(N)) return fail(h, TB_ERR_INVALID_ARG, "scratch smaller than ScratchDataSizeInBytes");
+    if (((uintptr_t)dst & 255) || ((uintptr_t)scratch & 255)) return fail(h, TB_ERR_INVALID_ARG, "dst and scratch must be 256-byte aligned (D3D12_RAYTRACING_ACCELERATION_STRUCTURE_BYTE_ALIGNMENT)");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    cudaStream_t stream = cudaStream ? (cudaStream_t)cudaStream : h->stream;
+    std::vector<BuildGeometry> descs(n);
+    std::vector<uint32_t> prefix(n);
+    uint32_t at = 0;
+    for (uint32_t g = 0; g < n; g++) {
+        const TbGeometryDesc& G = geoms[g];
+        if (!G.Positions || G.PositionStrideBytes < 12 || G.PositionStrideBytes % 4) return fail(h, TB_ERR_INVALID_ARG, "bad vertex buffer");
+        prefix[g] = at;
+        at += (G.IndexFormat == 0 ? G.VertexCount : G.IndexCount) / 3;
+        descs[g] = {(const uint8_t*)G.Positions, G.Indices, G.Transform3x4, G.PositionStrideBytes, G.IndexFormat, G.GeometryFlags, 0u};
+    }
+    DeviceBvh b;
+    b.ref = (uint8_t*)dst; b.refBytes = bvh_ref_bytes(N);
+    b.pairs = (PairNode*)((uint8_t*)dst + L.pairs); b.tris = (WideTri*)((uint8_t*)dst + L.tris);
+    int rc = run_build(h, descs, prefix, N, flags, b, scratch, stream);
+    if (rc != TB_OK) return rc;
+    AsTrailer t;
+    memset(&t, 0, sizeof(t));
+    memcpy(t.magic, "TBAS0001", 8);
+    t.numPrims = N; t.depth = b.depth; t.root = b.root;
+    CUDA_OK(h, cudaMemcpyAsync((uint8_t*)dst + L.trailer, &t, sizeof(t), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(h, cudaStreamSynchronize(stream));
+    h->deviceBuilds[dst] = b;
+    return TB_OK;
+}
+
+TB_API int tb_trace_rays_device(TbHandle* h, const void* as, uint64_t asBytes, const TbRay* dRays, uint64_t n, TbHit* dHits, void* cudaStream) {
+    if (!h || (n && (!dRays || !dHits))) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    cudaStream_t stream = cudaStream ? (cudaStream_t)cudaStream : h->stream;
+    DeviceBvh b;
+    if (!as) {
+        if (!h->sceneLoaded) return fail(h, TB_ERR_STATE, "no acceleration structure");
+        b = h->bvh;
+    } else {
+        auto it = h->deviceBuilds.find(as);
+        if (it != h->deviceBuilds.end()) b = it->second;
+        else { // built by another handle (or copied): read the structure's own trailer. The first four words of the
+               // reference layout give its size: offsetToPrimitiveMetaData + 12 N == 116 N - 16.
+            uint32_t hd[4];
+            CUDA_OK(h, cudaMemcpyAsync(hd, as, sizeof(hd), cudaMemcpyDeviceToHost, stream));
+            CUDA_OK(h, cudaStreamSynchronize(stream));
+            if (hd[0] != 16 || hd[3] < 100 || (hd[3] + 16ull) % 116) return fail(h, TB_ERR_INVALID_ARG, "not an acceleration structure built by tb_bvh_build_device");
+            const uint32_t N = (uint32_t)((hd[3] + 16ull) / 116);
+            const AsLayout L = as_layout(N);
+            if (asBytes < L.end) return fail(h, TB_ERR_INVALID_ARG, "acceleration structure buffer too small");
+            AsTrailer t;
+            CUDA_OK(h, cudaMemcpyAsync(&t, (const uint8_t*)as + L.trailer, sizeof(t), cudaMemcpyDeviceToHost, stream));
+            CUDA_OK(h, cudaStreamSynchronize(stream));
+            if (memcmp(t.magic, "TBAS0001", 8) != 0 || t.numPrims != N || t.depth > TB_STACK_DEPTH) return fail(h, TB_ERR_INVALID_ARG, "acceleration structure trailer is missing or corrupt");
+            b.ref = (uint8_t*)as; b.refBytes = bvh_ref_bytes(N);
+            b.pairs = (PairNode*)((uint8_t*)as + L.pairs); b.tris = (WideTri*)((uint8_t*)as + L.tris);
+            b.root = t.root; b.numPrims = N; b.depth = t.depth;
+            h->deviceBuilds[as] = b;
+        }
+    }
+    if (n == 0) return TB_OK;
+    CUDA_OK(h, trace_rays(b, dRays, n, dHits, h->numSMs, stream, h->lc)); // asynchronous on `stream`, like a dispatch
+    return TB_OK;
+}
+
+TB_API int tb_bvh_forget_device(TbHandle* h, const void* as) {
+    if (!h) return TB_ERR_INVALID_ARG;
+    h->deviceBuilds.erase(as);
+    return TB_OK;
+}
+
+TB_API int tb_get_bvh_depth(TbHandle* h, uint32_t* depth) {
+    if (!h || !depth) return fail(h, TB_ERR_INVALID_ARG, "null argument");
+    if (!h->sceneLoaded) return fail(h, TB_ERR_STATE, "no scene loaded");
+    *depth = h->bvh.depth;
     return TB_OK;
 }
 
@@ -990,7 +1128,7 @@ TB_API int tb_trace_rays(TbHandle* h, const TbRay* rays, uint64_t n, TbHit* hits
     cudaError_t e = cudaMalloc((void**)&dh, sizeof(TbHit) * n);
     if (e != cudaSuccess) { cudaFree(dr); return fail(h, TB_ERR_OOM, cudaGetErrorString(e)); }
     e = cudaMemcpyAsync(dr, rays, sizeof(TbRay) * n, cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) e = trace_rays(h->bvh, dr, n, dh, h->stream, h->lc);
+    if (e == cudaSuccess) e = trace_rays(h->bvh, dr, n, dh, h->numSMs, h->stream, h->lc);
     if (e == cudaSuccess) e = cudaMemcpyAsync(hits, dh, sizeof(TbHit) * n, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(dr); cudaFree(dh);

@@ -158,6 +158,50 @@ bool save_tbscene(const Scene& s, const std::string& path, std::string& err) {
     return ok;
 }
 
+// Every index the kernels dereference without a bounds check. The reference leans on D3D12's robust buffer access
+// (out-of-range reads return 0); here a stale or malformed file would be an illegal-address fault that poisons the
+// CUDA context of the whole process, so it is rejected on the host instead.
+bool validate_material(const Scene& s, const TbMaterial& m, std::string& err) {
+    const uint32_t nt = (uint32_t)s.textures.size();
+    const uint32_t tex[5] = {m.albedoIndex, m.alphaIndex, m.normalMapIndex, m.emissiveIndex, m.specularMapIndex};
+    for (uint32_t t : tex)
+        if (t != TB_INVALID_TEXTURE && t >= nt) { err = "material references a texture that does not exist"; return false; }
+    if (m.Flags & TB_MIX_MATERIAL_FLAG) { // the two mixed material ids travel in albedo.x / albedo.y (TracerBoy.cpp:452-470)
+        const float n = (float)s.materials.size();
+        if (!(m.albedo.x >= 0.0f && m.albedo.x < n) || !(m.albedo.y >= 0.0f && m.albedo.y < n)) {
+            err = "mix material references a material that does not exist"; return false;
+        }
+    }
+    return true;
+}
+
+bool validate_scene(const Scene& s, std::string& err) {
+    if (s.vertices.size() != s.positions.size()) { err = "vertex attribute count differs from position count"; return false; }
+    for (const auto& g : s.geoms) {
+        if ((uint64_t)g.VertexFirst + g.VertexCount > s.positions.size() ||
+            (uint64_t)g.IndexFirst + g.IndexCount > s.indices.size() || g.IndexCount % 3 ||
+            g.MaterialIndex >= s.materials.size()) { err = "geometry range or material index out of range"; return false; }
+        for (uint32_t i = 0; i < g.IndexCount; i++)
+            if (s.indices[g.IndexFirst + i] >= g.VertexCount) { err = "vertex index out of range"; return false; }
+    }
+    for (const auto& m : s.materials)
+        if (!validate_material(s, m, err)) return false;
+    for (const auto& t : s.textures) {
+        if (t.TextureType == TB_IMAGE_TEXTURE_TYPE && t.DescriptorHeapIndex >= s.images.size()) { err = "texture references an image that does not exist"; return false; }
+        if (t.TextureType == TB_SCALE_TEXTURE_TYPE && (t.TextureIndex1 >= s.textures.size() || t.TextureIndex2 >= s.textures.size())) {
+            err = "scale texture references a texture that does not exist"; return false;
+        }
+    }
+    if (s.envImage < -1 || s.envImage >= (int64_t)s.images.size()) { err = "environment image index out of range"; return false; }
+    for (const auto& im : s.images) {
+        const uint64_t bpp = im.format == 0 ? 16 : 4;
+        if (im.format > 1 || im.width == 0 || im.height == 0 || (uint64_t)im.width * im.height * bpp != im.data.size()) {
+            err = "image size does not match its pixel data"; return false;
+        }
+    }
+    return true;
+}
+
 bool load_tbscene(Scene& s, const std::string& path, std::string& err) {
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) { err = "cannot open: " + path; return false; }
@@ -167,6 +211,15 @@ bool load_tbscene(Scene& s, const std::string& path, std::string& err) {
         err = "not a .tbscene v1 file: " + path;
         return false;
     }
+    // the counts drive the allocations below: bound them by what the file can hold before resizing anything
+    fseek(f, 0, SEEK_END);
+    const uint64_t fileBytes = (uint64_t)ftell(f);
+    fseek(f, (long)sizeof(FileHeader), SEEK_SET);
+    const uint64_t declared = sizeof(FileHeader) + (uint64_t)h.numGeoms * sizeof(TbGeometryRecord) +
+                              (uint64_t)h.numVerts * (sizeof(TbFloat3) + sizeof(TbVertex)) + (uint64_t)h.numIndices * 4 +
+                              (uint64_t)h.numMaterials * (sizeof(TbMaterial) + 64) + (uint64_t)h.numLights * sizeof(TbLight) +
+                              (uint64_t)h.numTextures * sizeof(TbTextureData) + (uint64_t)h.numImages * 16;
+    if (declared > fileBytes) { fclose(f); err = "corrupt .tbscene (header counts exceed the file size): " + path; return false; }
     s.clear();
     s.flipTextureUVs = h.flipTextureUVs;
     s.envImage = h.envImage;
@@ -195,6 +248,7 @@ bool load_tbscene(Scene& s, const std::string& path, std::string& err) {
         uint32_t ih[4];
         ok = rd(f, ih, 4);
         if (!ok) break;
+        if ((uint64_t)ih[3] > fileBytes) { ok = false; break; }
         s.images[i].width = ih[0];
         s.images[i].height = ih[1];
         s.images[i].format = ih[2];
@@ -202,19 +256,10 @@ bool load_tbscene(Scene& s, const std::string& path, std::string& err) {
         ok = rd(f, s.images[i].data.data(), ih[3]);
     }
     fclose(f);
-    if (ok) {
-        // structural validation: every index must stay inside its geometry
-        for (auto& g : s.geoms) {
-            if ((uint64_t)g.VertexFirst + g.VertexCount > s.positions.size() ||
-                (uint64_t)g.IndexFirst + g.IndexCount > s.indices.size() || g.IndexCount % 3 ||
-                g.MaterialIndex >= s.materials.size()) { ok = false; break; }
-            for (uint32_t i = 0; i < g.IndexCount; i++)
-                if (s.indices[g.IndexFirst + i] >= g.VertexCount) { ok = false; break; }
-            if (!ok) break;
-        }
-        if (!ok) err = "corrupt .tbscene (index out of range): " + path;
-    } else err = "short read: " + path;
-    return ok;
+    if (!ok) { err = "short read: " + path; return false; }
+    std::string why;
+    if (!validate_scene(s, why)) { err = "corrupt .tbscene (" + why + "): " + path; return false; }
+    return true;
 }
 
 // ------------------------------------------------------------------- .hdr

@@ -40,6 +40,10 @@ struct Scene {
 // Layout is documented in DESIGN.md; little-endian, 8-byte magic "TBSCENE1".
 bool save_tbscene(const Scene& s, const std::string& path, std::string& err);
 bool load_tbscene(Scene& s, const std::string& path, std::string& err);
+// Structural validation of everything the kernels index without a bounds check (geometry ranges, vertex indices,
+// material -> texture, texture -> image / texture, mix-material ids, environment image, image byte sizes).
+bool validate_scene(const Scene& s, std::string& err);
+bool validate_material(const Scene& s, const TbMaterial& m, std::string& err);
 
 // Radiance .hdr (RGBE) -> float4 image, as DirectXTex LoadFromHDRFile gives the reference.
 bool load_hdr(const std::string& path, Image& img, std::string& err);
