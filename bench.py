@@ -1,21 +1,25 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the path-tracing hot path (contract in the task brief).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME] [--shard samples|rows]
+                  [--scaling weak|strong]
 
-One "step" = one pass of the hot path over one batch: `--spp` samples per pixel of the
-workload scene at 1920x1080 (default: Teapot, 64 spp, BASELINE.json configs[1]) through
-tb_render. Prints ONE JSON line on rank 0.
+One "step" = one pass of the hot path over one batch: `--spp` samples per pixel of the workload scene
+(default: Teapot 1920x1080, 64 spp, 6 bounces = BASELINE.json configs[1]) through tb_render. ONE JSON line on rank 0.
 
-  value     Mrays/s, whole job (all ranks), inputs resident in HBM, CUDA-event timed
-  e2e       same metric through the public API with host buffers: every step does the
-            host->device copy of the per-frame inputs (settings + camera, pinned) and the
-            device->host read of the resolved image, inside the timed region
-  roofline  dominant kernel (k_extend): algorithmic bytes / summed CUDA-event launch time
-  cpu_baseline  the CPU oracle timed on this box's host cores on a bounded sample (N=1 only)
+  value     Mrays/s, whole job (all ranks), inputs resident in HBM. Time = device time of every step, CUDA events
+            recorded by the library on its own stream around the frames of tb_render and around the reduction
+            (tb_comm_reduce), max over ranks; the same clock for every N.
+  e2e       same metric through the public API with host buffers: every step does the host->device copy of the
+            per-frame inputs (settings + camera, pinned) and the device->host read of the resolved JOB-WIDE image
+            (for N > 1 that read runs the NCCL reduction), wall clock bracketed by barriers + synchronisation
+  roofline  the dominant kernel (k_extend): algorithmic bytes over its time in the timed mode; what binds it per ncu
+  cpu_baseline  the CPU oracle timed on this box's host cores on a bounded sample (N = 1 only)
 
-N>1 (torchrun): sample-index sharding (frame f on rank f mod N), one NCCL all-reduce of the
-float4 accumulation buffer per step (the path's only exchange step); weak scaling.
+N > 1 (torchrun): one process per GPU, one TbHandle each, joined by the library's own communicator (tb_comm_init: NCCL
+over NVLink; the id is broadcast with torch.distributed, which is plumbing only). --shard samples: frame f on rank
+f mod N, reduction = all-gather + fixed rank-order sum; --shard rows: bands of 8 rows, bit-identical to one GPU.
+--scaling weak (default): every GPU renders `spp` frames per step (or all frames of its bands); strong: `spp` in total.
 --impl reference: the reference's CPU implementation of the path (CPU oracle / oracle/_ref).
 """
 import argparse
@@ -34,11 +38,12 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (scene spec, width, height, spp, max bounces)
-    "teapot": ("teapot", 1920, 1080, 64, 6),
-    "cornell": ("cornell-box", 512, 512, 16, 4),
-    "dragon": ("synthetic:blobs?copies=1&tris=871000&seed=1", 1920, 1080, 256, 8),
-    "vwvan": ("vw-van", 3840, 2160, 128, 6),  # configs[3], variant scene (tracerboy_b200/build.py)
-    "blobs20m": ("synthetic:blobs?copies=20000&tris=1000&seed=1", 1920, 1080, 1024, 6),
+    "teapot": ("teapot", 1920, 1080, 64, 6),                   # configs[1]
+    "cornell": ("cornell-box", 512, 512, 16, 4),               # configs[0]
+    "dragon": ("dragon", 1920, 1080, 256, 8),                  # configs[2]: the reference's scene.pbrt, variant (tracerboy_b200/build.py)
+    "vwvan": ("vw-van", 3840, 2160, 128, 6),                   # configs[3], variant scene (tracerboy_b200/build.py)
+    "blobs20m": ("synthetic:blobs?copies=20000&tris=1000&seed=1", 1920, 1080, 1024, 6),   # configs[4]
+    "blobs871k": ("synthetic:blobs?copies=1&tris=871000&seed=1", 1920, 1080, 256, 8),     # round-1 stand-in: area light, glass, metal
 }
 
 
@@ -54,11 +59,12 @@ def scene_arg(spec):
 
 def tbscene_for_oracle(spec):
     """The oracle only reads .tbscene; synthetic specs are converted through the host-only C ABI call."""
+    import hashlib
+    import tempfile
     import tracerboy_b200 as tb
     if not spec.startswith("synthetic:"):
         return scene_arg(spec)
-    out = os.path.join(ROOT, "scenes", "_cache", "bench_synth_%08x.tbscene" % (hash(spec) & 0xffffffff))
-    os.makedirs(os.path.dirname(out), exist_ok=True)
+    out = os.path.join(tempfile.gettempdir(), "tb_bench_synth_%s.tbscene" % hashlib.sha1(spec.encode()).hexdigest()[:10])
     if not os.path.exists(out):
         tb.convert_scene(spec, out)
     return out
@@ -118,15 +124,22 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per k_extend launch from the committed ncu --set full summary, if any."""
-    p = os.path.join(ROOT, "profiles", "extend_dram_traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p))
-        except Exception:
-            return None
-    return None
+def ncu_units(workload):
+    """What binds k_extend on this workload according to the committed `ncu --set full` capture of the same command
+    (profiles/r2_ncu_units.json, written by tools/ncu_units.py from the raw CSV): per-unit utilisation, DRAM / L2 bytes."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_units.json")
+    try:
+        return json.load(open(p)).get(workload)
+    except Exception:
+        return None
+
+
+def cpu_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+CPU_PARTS = {"core (PathTrace / Trace / BRDFs / material model)": "reference text: TracerBoy/kernel.glsl compiled from the mount as host C++ (oracle/_ref/libref_core.so)",
+             "ray query, BVH builder, ray-generation glue": "hand restatement (oracle/*.cpp), each stage pinned bit-exact against the reference's own shader text compiled from the mount (tests/test_cpu_oracle.py)"}
 
 
 def run_reference(args, rank, world):
@@ -148,8 +161,7 @@ def run_reference(args, rank, world):
     o.Resize(w, h)
     s = tb.get_default_output_settings()
     s.MaxBounces = bounces
-    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = cpu_cores()  # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
     sample_spp = max(1, args.ref_spp)
     for _ in range(args.warmup):
         o.Render(s, 1, 0.0, threads=cores)
@@ -164,9 +176,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic camera/seeds on the bundled scene",
-        "config": {"workload": "%s %dx%d, %d bounces, CPU sample of %d spp per step" % (args.workload, w, h, bounces, sample_spp)},
+        "config": {"workload": "%s %dx%d, %d bounces, CPU sample of %d spp per step (a rate metric: Mrays/s does not depend on the sample count)" % (
+            args.workload, w, h, bounces, sample_spp)},
         "samples_per_s": w * h * sample_spp * args.steps / t,
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind,
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "parts": CPU_PARTS if kind == "reference" else None,
                          "sample": "%d spp of the %dx%d %s workload per step, OpenMP over pixels" % (sample_spp, w, h, args.workload)},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -186,8 +199,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fif", type=int, default=0, help="frames in flight (0: the library's automatic policy)")
     ap.add_argument("--shard", default="samples", choices=["samples", "rows"],
-                    help="N>1: 'samples' = frame f on rank f mod N (weak scaling, default); 'rows' = interleaved bands of 8 rows, "
-                         "every rank renders all frames of its bands (strong scaling, bit-identical to one GPU)")
+                    help="N>1: 'samples' = frame f on rank f mod N (fixed rank-order sum); 'rows' = interleaved bands of 8 rows "
+                         "(bit-identical to one GPU)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = every GPU renders `spp` frames per step; strong = `spp` frames per step in total")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -217,25 +232,33 @@ def main():
     g = tb.TracerBoy(local_rank)
     g.LoadScene(scene_arg(spec))
     load_s = time.time() - t_load
-    build_first_ms = g.GetBVHBuildMilliseconds()  # includes the first-use costs: module load, growth of the memory pool
+    build_first_ms = g.GetBVHBuildMilliseconds()  # includes the first-use costs: module load, first touch of the scratch
     g.LoadScene(scene_arg(spec))                  # the same build again: the steady-state builder time
     g.Resize(w, h)
     if args.fif:
         g.SetFramesInFlight(args.fif)
-    if args.shard == "rows":
-        g.SetRowShard(rank, world)    # bands of 8 rows, band b on rank b mod N
+    rows = args.shard == "rows"
+    if world > 1:
+        # the product's own communicator; torch.distributed only carries the 128-byte id to the other processes
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(tb.comm_get_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        g.CommInit(bytes(uid.cpu().numpy().tobytes()), rank, world, tb.SHARD_ROWS if rows else tb.SHARD_SAMPLES)
+    # frames this rank renders per step
+    if rows:
+        spp_rank = spp                                   # all frames of its own bands: strong scaling by construction
+        frames_job = spp
+    elif args.scaling == "strong":
+        spp_rank = max(1, spp // world)
+        frames_job = spp_rank * world
     else:
-        g.SetFrameShard(rank, world)  # frame f rendered on rank f mod N
+        spp_rank = spp
+        frames_job = spp * world
+    strong = world > 1 and (rows or args.scaling == "strong")
     s = tb.get_default_output_settings()
     s.MaxBounces = bounces
     info = g.GetSceneInfo()
-
-    acc_ptr, acc_bytes = g.DeviceBuffer(tb.BufferKind.ACCUM_RGBW)
-
-    class _Holder:  # zero-copy torch view of the library's float4 accumulation buffer
-        __cuda_array_interface__ = {"shape": (h, w, 4), "typestr": "<f4", "data": (acc_ptr, False), "version": 2}
-    acc_t = torch.as_tensor(_Holder(), device=torch.device("cuda", local_rank))
-    reduced = torch.empty_like(acc_t) if world > 1 else None
 
     # pinned host buffers for the e2e leg
     host_img = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
@@ -244,10 +267,9 @@ def main():
 
     def step_resident():
         g.InvalidateHistory()
-        g.Render(s, spp, 0.0)
-        if world > 1:  # the path's one exchange step: sum of the per-rank accumulation buffers
-            reduced.copy_(acc_t)
-            dist.all_reduce(reduced)
+        g.Render(s, spp_rank, 0.0)
+        if world > 1:
+            g.CommReduce()  # the path's one exchange step (collective): job-wide accumulation buffers on every rank
 
     def step_e2e():
         # host -> device: this step's inputs (PerFrameConstants sources) from pinned memory
@@ -256,11 +278,8 @@ def main():
         s_in = tb.OutputSettings.from_address(host_in.data_ptr())
         cam_in = tb.Camera.from_address(host_in.data_ptr() + ctypes.sizeof(s))
         g.SetCamera(cam_in)  # also invalidates history, like TracerBoy::Update
-        g.Render(s_in, spp, 0.0)
-        if world > 1:
-            reduced.copy_(acc_t)
-            dist.all_reduce(reduced)
-        # device -> host: the resolved image (rgb / w), read by the caller
+        g.Render(s_in, spp_rank, 0.0)
+        # device -> host: the resolved image (rgb / w) of the WHOLE JOB (runs the reduction when N > 1), read by the caller
         g.Readback(tb.BufferKind.RESOLVED_RGB, out=host_img.numpy())
 
     def barrier():
@@ -270,92 +289,138 @@ def main():
 
     def timed(fn, steps):
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g.ResetRenderStats()
         g.Synchronize()
+        red0 = g.CommInfo().TotalReductionMilliseconds if world > 1 else 0.0
         t0 = time.perf_counter()
-        e0.record()
         for _ in range(steps):
             fn()
         g.Synchronize()
-        e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         barrier()
         st = g.GetRenderStats()
-        # device time of the library's own stream (CUDA events recorded by tb_render) ...
-        dev_ms = st.DeviceMilliseconds
-        # ... and the wall clock bracketed by synchronisations (includes copies / collectives)
-        return st, dev_ms, wall
+        red_ms = (g.CommInfo().TotalReductionMilliseconds - red0) if world > 1 else 0.0
+        # device time: the library's CUDA events around the frames of every tb_render + around every reduction
+        return st, st.DeviceMilliseconds + red_ms, wall, red_ms
 
     for _ in range(max(3, args.warmup)):
         step_resident()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    st, dev_ms, wall = timed(step_resident, args.steps)
+    st, dev_ms, wall, red_ms = timed(step_resident, args.steps)
     clocks = sampler.stop()
-    # value: whole-step time on the device (max over ranks); tb_render's events bracket the
-    # kernels, the wall clock additionally covers the all-reduce when N > 1
-    t_step = wall if world > 1 else dev_ms / 1e3
-    vals = torch.tensor([t_step, float(st.RaysTraced), float(st.KernelLaunches)], dtype=torch.float64, device="cuda")
+    vals = torch.tensor([dev_ms / 1e3, wall, red_ms / 1e3], dtype=torch.float64, device="cuda")
+    sums = torch.tensor([float(st.RaysTraced), float(st.KernelLaunches), float(st.BoxesTested), float(st.TrianglesTested)] +
+                        [float(x) for x in st.RaysByBounce], dtype=torch.float64, device="cuda")
     if world > 1:
-        tmax = vals.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = vals.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        t_step, rays_total, launches = tmax[0].item(), tsum[1].item(), tsum[2].item()
-    else:
-        rays_total, launches = float(st.RaysTraced), float(st.KernelLaunches)
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    t_step, wall, red_s = vals[0].item(), vals[1].item(), vals[2].item()
+    rays_total, launches, boxes_total, tris_total = (sums[i].item() for i in range(4))
+    rays_by_bounce = [sums[4 + b].item() for b in range(32)]
     value = rays_total / t_step / 1e6
+
+    # the same step with primary rays only (MaxBounces = 1: camera ray + its shadow ray): the difference is what the
+    # incoherent bounces cost in the timed mode, frames in flight and all
+    incoherent = None
+    if bounces > 1:
+        s1 = tb.get_default_output_settings()
+        s1.MaxBounces = 1
+
+        def step_primary():
+            g.InvalidateHistory()
+            g.Render(s1, spp_rank, 0.0)
+        step_primary()
+        st1, dev1_ms, _, _ = timed(step_primary, args.steps)
+        v1 = torch.tensor([dev1_ms / 1e3], dtype=torch.float64, device="cuda")
+        r1 = torch.tensor([float(st1.RaysTraced)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(v1, op=dist.ReduceOp.MAX)
+            dist.all_reduce(r1, op=dist.ReduceOp.SUM)
+        t_render = t_step - red_s
+        if t_render > v1[0].item() and rays_total > r1[0].item():
+            incoherent = {"mrays_per_s": (rays_total - r1[0].item()) / (t_render - v1[0].item()) / 1e6,
+                          "primary_only_mrays_per_s": r1[0].item() / v1[0].item() / 1e6,
+                          "rays_share": (rays_total - r1[0].item()) / rays_total,
+                          "how": "(rays(all bounces) - rays(MaxBounces=1)) / (device time(all bounces) - device time(MaxBounces=1)), same timed mode"}
 
     # e2e leg
     for _ in range(2):
         step_e2e()
-    st_e, _, wall_e = timed(step_e2e, args.steps)
-    ve = torch.tensor([wall_e, float(st_e.RaysTraced)], dtype=torch.float64, device="cuda")
+    st_e, _, wall_e, _ = timed(step_e2e, args.steps)
+    ve = torch.tensor([wall_e], dtype=torch.float64, device="cuda")
+    re_ = torch.tensor([float(st_e.RaysTraced)], dtype=torch.float64, device="cuda")
     if world > 1:
-        a = ve.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
-        b = ve.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
-        wall_e, rays_e = a[0].item(), b[1].item()
-    else:
-        rays_e = float(st_e.RaysTraced)
+        dist.all_reduce(ve, op=dist.ReduceOp.MAX)
+        dist.all_reduce(re_, op=dist.ReduceOp.SUM)
+    wall_e, rays_e = ve[0].item(), re_[0].item()
     e2e_value = rays_e / wall_e / 1e6
 
-    # roofline of the dominant kernel, measured live with per-launch CUDA events (profiling mode)
-    g.SetProfiling(True)
+    # ---- roofline of the dominant kernel
+    # (a) shares in the timed mode: per-launch CUDA events on each frame slot's own stream while the frames overlap as
+    #     in the timed region (profiling mode 2, no graph replay)
+    g.SetProfiling(2)
     g.ResetRenderStats()
     g.InvalidateHistory()
-    g.Render(s, min(spp, 16), 0.0)
+    g.Render(s, spp_rank, 0.0)
+    cst = g.GetRenderStats()
+    # (b) exclusive times: one frame at a time (profiling mode 1), also per bounce
+    g.SetProfiling(1)
+    g.ResetRenderStats()
+    g.InvalidateHistory()
+    g.Render(s, min(spp_rank, 16), 0.0)
     pst = g.GetRenderStats()
-    g.SetProfiling(False)
-    # rays that finish inside k_extend (the rest are suspended and finish in k_extend_resume, timed separately)
-    alg_bytes = 32.0 * pst.ExtendBoxesTested + 40.0 * pst.ExtendTrianglesTested + 64.0 * pst.ExtendRays
+    g.SetProfiling(0)
     peak, peak_src = measured_peak_gbs()
-    ext_s = pst.ExtendMilliseconds / 1e3
-    achieved = alg_bytes / ext_s / 1e9 if ext_s > 0 else 0.0
-    # DRAM bytes per launch from the committed ncu --set full capture (Teapot only: the capture is of that workload).
-    # The captured launch is a bounce-0 launch; scaled by rays to the average launch `achieved` is quoted on.
-    traffic = ncu_traffic() if args.workload == "teapot" else None
-    traffic_per_launch = None
-    if traffic:
-        cap = traffic.get("launches", [{}])[0]
-        if cap.get("rays"):
-            per_ray = (cap["dram_read"] + cap["dram_write"]) / cap["rays"]
-            traffic_per_launch = per_ray * pst.ExtendRays / max(1, pst.ExtendLaunches)
-        else:
-            traffic_per_launch = traffic["dram_bytes_per_launch"]
+    # k_extend's share of the step: from the exclusive per-launch times (the same definition as the serialised ncu launch
+    # list in profiles/); the per-stream elapsed times under concurrency (mode 2) are reported beside it -- they inflate
+    # short kernels, which wait for the SMs the persistent traversal kernels of other frames hold
+    share = pst.ExtendMilliseconds / max(1e-9, pst.ExtendMilliseconds + pst.ShadeMilliseconds + pst.ResumeMilliseconds)
+    share_concurrent = cst.ExtendMilliseconds / max(1e-9, cst.ExtendMilliseconds + cst.ShadeMilliseconds + cst.ResumeMilliseconds)
+    frames_rank_timed = spp_rank * args.steps
+    # rays that finish inside k_extend<EXT_MAIN> during the timed region (the rest are shadow / walk / resumed rays)
+    alg_bytes_timed = 32.0 * st.ExtendBoxesTested + 40.0 * st.ExtendTrianglesTested + 64.0 * st.ExtendRays  # SURVEY §8(d), this rank
+    launches_timed = frames_rank_timed * bounces
+    t_render_rank = st.DeviceMilliseconds / 1e3
+    ext_s = share * t_render_rank           # k_extend's part of the timed region
+    achieved = alg_bytes_timed / ext_s / 1e9 if ext_s > 0 else 0.0
+    units = ncu_units(args.workload)
+    bound = "unknown (no ncu capture of this workload in profiles/r2_ncu_units.json)"
+    if units:
+        pct = {"issue": units.get("issue_active_pct") or 0.0, "l1": units.get("l1tex_throughput_pct") or 0.0,
+               "l2": units.get("lts_throughput_pct") or 0.0, "hbm": units.get("dram_throughput_pct") or 0.0}
+        bound = max(pct, key=pct.get)
+    serial_alg = 32.0 * pst.ExtendBoxesTested + 40.0 * pst.ExtendTrianglesTested + 64.0 * pst.ExtendRays
+    per_bounce = []
+    for b in range(min(bounces, 32)):
+        if pst.RaysByBounce[b]:
+            per_bounce.append({"bounce": b, "rays": int(pst.RaysByBounce[b]), "ms": pst.BounceMilliseconds[b],
+                               "mrays_per_s": pst.RaysByBounce[b] / max(1e-9, pst.BounceMilliseconds[b]) / 1e3,
+                               "extend_ms": pst.BounceExtendMilliseconds[b]})
     roofline = {
-        "bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic_per_launch,
-        "traffic_source": traffic["source"] if traffic else None,
-        "algorithmic_bytes_per_launch": alg_bytes / max(1, pst.ExtendLaunches),
-        "avg_launch_ms": pst.ExtendMilliseconds / max(1, pst.ExtendLaunches), "launches": pst.ExtendLaunches,
-        "kernel_share_of_step": pst.ExtendMilliseconds / max(1e-9, pst.ExtendMilliseconds + pst.ShadeMilliseconds + pst.ResumeMilliseconds),
-        "resume_rounds": {"rays": pst.ResumeRays, "ms": pst.ResumeMilliseconds,
-                          "algorithmic_bytes": 32.0 * pst.ResumeBoxesTested + 40.0 * pst.ResumeTrianglesTested + 64.0 * pst.ResumeRays},
+        "bound": bound, "kernel": "k_extend<EXT_MAIN>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak,
+        "traffic": (units or {}).get("dram_bytes_per_launch"),
+        "traffic_source": (units or {}).get("source"),
+        "algorithmic_bytes_per_launch": alg_bytes_timed / max(1, launches_timed),
+        "avg_launch_ms": 1e3 * ext_s / max(1, launches_timed), "launches": launches_timed,
+        "kernel_share_of_step": share, "kernel_share_of_stream_time_under_concurrency": share_concurrent,
+        "how": "timed mode: achieved = algorithmic bytes of the rays finished by k_extend<EXT_MAIN> in the timed region / (share x device "
+               "time of the region); share = k_extend's part of the exclusive per-launch CUDA-event times of one frame at a time "
+               "(profiling mode 1, measured in this run; the definition the serialised ncu launch list uses); avg_launch_ms = share x "
+               "time / launches, i.e. what a launch costs with the other frames in flight filling its tail",
+        "units_pct_of_peak": units,
+        "exclusive": {  # one frame at a time: what the kernel costs alone on the GPU
+            "achieved": serial_alg / max(1e-9, pst.ExtendMilliseconds / 1e3) / 1e9, "avg_launch_ms": pst.ExtendMilliseconds / max(1, pst.ExtendLaunches),
+            "launches": pst.ExtendLaunches, "kernel_share_of_step": pst.ExtendMilliseconds / max(1e-9, pst.ExtendMilliseconds + pst.ShadeMilliseconds + pst.ResumeMilliseconds),
+            "resume_rounds": {"rays": pst.ResumeRays, "ms": pst.ResumeMilliseconds}},
         # all rays of the timed region (every kernel, frames in flight overlapped) over the whole step time
-        "whole_step_algorithmic_GBps": world * (32.0 * st.BoxesTested + 40.0 * st.TrianglesTested + 64.0 * st.RaysTraced) / t_step / 1e9,
+        "whole_step_algorithmic_GBps": (32.0 * boxes_total + 40.0 * tris_total + 64.0 * rays_total) / t_step / 1e9,
         "peak_source": peak_src,
-        "note": "algorithmic bytes = 32 B x BoxesTested + 40 B x TrianglesTested + 64 B ray/hit (reference BVH2 layout); "
-                "a BVH that fits the 126 MB L2 is served from L2, so frac can exceed DRAM-only expectations",
+        "note": "algorithmic bytes = 32 B x BoxesTested + 40 B x TrianglesTested + 64 B ray/hit on the reference BVH2 layout (SURVEY 8d). "
+                "`peak` is the measured HBM copy bandwidth; a BVH that fits the 126 MB L2 is served from L1/L2, so `bound` names the unit "
+                "ncu shows closest to its own peak and frac is NOT a DRAM utilisation there",
     }
 
     cpu_baseline = None
@@ -369,34 +434,45 @@ def main():
         o = Oracle()
         o.LoadScene(tbscene_for_oracle(spec), 3)
         o.Resize(w, h)
-        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        cores = cpu_cores()
         o.Render(s, 1, 0.0, threads=cores)
         c0 = o.Counts()
         sec = o.Render(s, args.cpu_baseline_spp, 0.0, threads=cores)
         c1 = o.Counts()
         cpu_baseline = {"value": (c1["rays"] - c0["rays"]) / sec / 1e6, "unit": "Mrays/s", "cores": cores,
-                        "kind": kind, "sample": "%d spp of the %dx%d %s workload (%.1f s), OpenMP over pixels" % (
+                        "kind": kind, "parts": CPU_PARTS if kind == "reference" else None,
+                        "sample": "%d spp of the %dx%d %s workload (%.1f s), OpenMP over pixels" % (
                             args.cpu_baseline_spp, w, h, args.workload, sec)}
 
     if rank == 0:
+        comm = g.CommInfo() if world > 1 else None
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": 1e3 * t_step / args.steps, "higher_is_better": True,
-            "scaling": "strong" if (args.shard == "rows" and world > 1) else "weak", "vs_baseline": None, "dtype": "f32",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic camera/seeds on the bundled scene",
-            "config": {"workload": "%s %dx%d, %d spp per step per GPU, %d bounces, NEE on, blue noise on, Time=0" % (
-                           args.workload, w, h, spp, bounces),
-                       "triangles": info.NumTriangles, "sharding": ("bands of 8 rows, band b on rank b mod N" if args.shard == "rows" else "frame f on rank f mod N") +
-                                   "; all-reduce of the accumulation buffer per step",
+            "config": {"workload": "%s %dx%d, %d spp per step %s, %d bounces, NEE on, blue noise on, Time=0" % (
+                           args.workload, w, h, frames_job, "in total" if strong else "per GPU" if world > 1 else "", bounces),
+                       "triangles": info.NumTriangles, "bvh_depth": g.GetBVHDepth(),
+                       "sharding": None if world == 1 else (("bands of 8 rows, band b on rank b mod N; NCCL all-gather of the owned bands (bit-identical to one GPU)" if rows else
+                                                            "frame f on rank f mod N; NCCL all-gather + fixed rank-order sum") + ", inside the library (tb_comm_reduce), once per step"),
                        "l2": "inputs exceed L2: %d MB of path state + accumulation buffers are rewritten every sample" % (
                            (w * h * 16 * 14) >> 20),
-                       "frames_in_flight": args.fif if args.fif else "auto (memory budget, <= 32)"},
-            "samples_per_s": (1 if args.shard == "rows" else world) * w * h * spp * args.steps / t_step,
+                       "frames_in_flight": args.fif if args.fif else "auto (memory budget, <= 32)",
+                       "timing": "device: CUDA events of tb_render + tb_comm_reduce on the library's stream, max over ranks"},
+            "samples_per_s": w * h * frames_job * args.steps / t_step,
             "rays_per_step": rays_total / args.steps,
+            "wall_ms_per_step": 1e3 * wall / args.steps,
+            "reduce_ms_per_step": 1e3 * red_s / args.steps if world > 1 else None,
+            "comm": None if comm is None else {"nccl_version": comm.NcclVersion, "bytes_received_per_reduction": comm.BytesReceivedPerReduction},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(host_in.numel()),
-                    "d2h_bytes_per_step": int(host_img.numel() * 4), "ms_per_step": 1e3 * wall_e / args.steps},
+                    "d2h_bytes_per_step": int(host_img.numel() * 4), "ms_per_step": 1e3 * wall_e / args.steps,
+                    "image": "resolved rgb of the whole job (after the reduction)" if world > 1 else "resolved rgb"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "rays_by_bounce": [int(x) for x in rays_by_bounce[:bounces]],
+            "incoherent": incoherent,
+            "per_bounce_exclusive": per_bounce,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "bvh_build_ms": g.GetBVHBuildMilliseconds(), "bvh_build_first_call_ms": build_first_ms,
@@ -404,6 +480,7 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        g.CommDestroy()
         dist.destroy_process_group()
 
 

@@ -340,6 +340,12 @@ typedef struct TbRenderStats {
     /* rays that were suspended and finished in a k_extend_resume round */
     uint64_t ResumeRays, ResumeBoxesTested, ResumeTrianglesTested;
     double ResumeMilliseconds;
+    /* every Intersect call by the bounce index of its path (extension, shadow and walk rays of bounce b; 31 = 31 and
+     * above): bounce 0 holds the coherent camera rays, the others are the incoherent ones */
+    uint64_t RaysByBounce[32];
+    /* profiling mode only: device time of all stages of bounce b, and of its k_extend launch alone */
+    double BounceMilliseconds[32];
+    double BounceExtendMilliseconds[32];
 } TbRenderStats;
 
 /* Multi-GPU: how the frame is partitioned over the ranks of a communicator. */
@@ -352,6 +358,7 @@ typedef struct TbCommInfo {
     uint64_t Reductions;                 /* tb_comm_reduce calls so far */
     uint64_t BytesReceivedPerReduction;  /* over NVLink, per rank */
     double LastReductionMilliseconds;    /* CUDA events around pack + all-gather + combine */
+    double TotalReductionMilliseconds;   /* the same, summed over all reductions */
 } TbCommInfo;
 
 typedef struct TbHandle TbHandle; /* opaque; owns all device memory */
@@ -428,7 +435,10 @@ TB_API int tb_device_buffer(TbHandle* h, uint32_t kind, void** devPtr, uint64_t*
 TB_API int tb_get_render_stats(TbHandle* h, TbRenderStats* out);
 TB_API int tb_reset_render_stats(TbHandle* h);
 /* Profiling mode: record CUDA events around every traversal / shading launch (small
- * overhead; off by default). Results appear in TbRenderStats.Extend/ShadeMilliseconds. */
+ * overhead; off by default). Results appear in TbRenderStats.Extend/ShadeMilliseconds.
+ *   1  one frame at a time: exclusive device time of every launch (what a kernel costs alone)
+ *   2  frames in flight as in a normal render (no graph replay): each launch's elapsed time on its own stream while
+ *      the other frames' kernels share the GPU, i.e. the kernels' SHARES of the step as it is really run */
 TB_API int tb_set_profiling(TbHandle* h, int enable);
 /* Number of frames (samples) kept in flight on independent CUDA streams (0 = automatic:
  * as many as fit a third of the free device memory, between 4 and 16). The result does not depend on it: samples are added to the accumulation buffer in frame order. */

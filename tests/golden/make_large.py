@@ -37,8 +37,8 @@ def main():
     from oracle.binding import Oracle
     from test_gpu_parity import _random_rays
     from test_gpu_scale import _tree_depth
-    path = os.path.join(ROOT, "scenes", "_cache", "blobs20m.tbscene")
-    os.makedirs(os.path.dirname(path), exist_ok=True)
+    import tempfile
+    path = os.path.join(tempfile.gettempdir(), "tb_blobs20m.tbscene")  # 770 MB: kept out of the repo tree
     if not os.path.exists(path):
         tb.convert_scene(SPEC, path)
     o = Oracle()

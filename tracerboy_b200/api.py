@@ -95,7 +95,8 @@ class RenderStats(C.Structure):
                 ("ExtendRays", C.c_uint64), ("ExtendBoxesTested", C.c_uint64), ("ExtendTrianglesTested", C.c_uint64),
                 ("ExtendLaunches", C.c_uint64), ("ExtendMilliseconds", C.c_double), ("ShadeMilliseconds", C.c_double),
                 ("ResumeRays", C.c_uint64), ("ResumeBoxesTested", C.c_uint64), ("ResumeTrianglesTested", C.c_uint64),
-                ("ResumeMilliseconds", C.c_double)]
+                ("ResumeMilliseconds", C.c_double), ("RaysByBounce", C.c_uint64 * 32),
+                ("BounceMilliseconds", C.c_double * 32), ("BounceExtendMilliseconds", C.c_double * 32)]
 
 
 class SceneInfo(C.Structure):
@@ -125,7 +126,8 @@ class PrebuildInfo(C.Structure):
 
 class CommInfo(C.Structure):
     _fields_ = [("Rank", C.c_uint32), ("NumRanks", C.c_uint32), ("ShardMode", C.c_uint32), ("NcclVersion", C.c_uint32),
-                ("Reductions", C.c_uint64), ("BytesReceivedPerReduction", C.c_uint64), ("LastReductionMilliseconds", C.c_double)]
+                ("Reductions", C.c_uint64), ("BytesReceivedPerReduction", C.c_uint64), ("LastReductionMilliseconds", C.c_double),
+                ("TotalReductionMilliseconds", C.c_double)]
 
 
 SHARD_SAMPLES, SHARD_ROWS = 1, 2
@@ -555,7 +557,7 @@ class TracerBoy:
         self._ck(self._lib.tb_set_ray_sort(self._h, int(mode)))
 
     def SetProfiling(self, enable):
-        self._ck(self._lib.tb_set_profiling(self._h, int(bool(enable))))
+        self._ck(self._lib.tb_set_profiling(self._h, int(enable)))
 
     def Synchronize(self):
         self._ck(self._lib.tb_synchronize(self._h))

@@ -519,12 +519,15 @@ __device__ __forceinline__ void push_sorted(PathState& st, int qi, uint32_t pi, 
     (hit ? st.hitQueue : st.missQueue)[slot] = pi;
 }
 
-__device__ __forceinline__ void flush_stats(PathState& st, int slot, uint32_t rays, uint32_t ntris, uint32_t nboxes) {
+// stats layout (TB_STATS_WORDS 64-bit words): [0..2] rays / boxes / tris finished in k_extend<EXT_MAIN>, [3..5] in the
+// shadow / walk / inline traversals, [6..8] in k_extend_resume, [16 + b] rays of bounce b of any kind (b clamped to 31)
+__device__ __forceinline__ void flush_stats(PathState& st, int slot, int bounce, uint32_t rays, uint32_t ntris, uint32_t nboxes) {
     for (int o = 16; o > 0; o >>= 1) {
         rays += __shfl_xor_sync(0xffffffffu, rays, o); ntris += __shfl_xor_sync(0xffffffffu, ntris, o); nboxes += __shfl_xor_sync(0xffffffffu, nboxes, o);
     }
     if ((threadIdx.x & 31) == 0 && rays) {
         atomicAdd(&st.stats[slot], (unsigned long long)rays); atomicAdd(&st.stats[slot + 1], (unsigned long long)nboxes); atomicAdd(&st.stats[slot + 2], (unsigned long long)ntris);
+        atomicAdd(&st.stats[16 + (bounce < 31 ? bounce : 31)], (unsigned long long)rays);
     }
 }
 
@@ -544,8 +547,9 @@ __device__ __forceinline__ bool try_suspend(PathState& st, int round, const Trav
 #define EXT_SHADOW 1
 #define EXT_WALK 2
 template <int KIND>
-__global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh, PathState st, int qi, int bounceIsZero, uint32_t outputHeatmap, const FrameConstants* __restrict__ fcp, uint32_t budgetMain, uint32_t refillBelow) {
+__global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh, PathState st, int qi, int bounce, uint32_t outputHeatmap, const FrameConstants* __restrict__ fcp, uint32_t budgetMain, uint32_t refillBelow) {
     const uint32_t aovMask = fcp->aovMask;
+    const int bounceIsZero = bounce == 0;
     const uint32_t count = KIND == EXT_SHADOW ? st.queueCount[4] : KIND == EXT_WALK ? st.queueCount[10 + qi] : st.queueCount[qi];
     if (KIND == EXT_MAIN && blockIdx.x == 0 && threadIdx.x == 0) {
         st.queueCount[qi ^ 1] = 0;                       // next queue starts empty (consumed by k_shade)
@@ -645,13 +649,14 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
             }
         }
     }
-    flush_stats(st, KIND == EXT_MAIN ? 0 : 3, rays, ntris, nboxes);
+    flush_stats(st, KIND == EXT_MAIN ? 0 : 3, bounce, rays, ntris, nboxes);
 }
 
 // Resume round `round` (1-based): continues the rays parked by round-1; the last round has no budget.
-__global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState st, int qi, int round, uint32_t budget, int bounceIsZero,
+__global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState st, int qi, int round, uint32_t budget, int bounce,
                                                        uint32_t outputHeatmap, const FrameConstants* __restrict__ fcp) {
     const uint32_t aovMask = fcp->aovMask;
+    const int bounceIsZero = bounce == 0;
     const uint32_t count = min(st.susCount[round - 1], st.susCapacity);
     const float4* __restrict__ pairs = (const float4*)bvh.pairs;
     const float4* __restrict__ tris = (const float4*)bvh.tris;
@@ -671,7 +676,7 @@ __global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState 
             tr.step(stack, pairs, tris);
         }
     }
-    flush_stats(st, 6, rays, ntris, nboxes);
+    flush_stats(st, 6, bounce, rays, ntris, nboxes);
 }
 
 // ------------------------------------------------------------------ ray sort
@@ -772,7 +777,7 @@ __device__ __forceinline__ void finish_path(const FrameConstants& fc, PathState&
 //          without them (checked on the host) get a kernel with no traversal code at all in stages
 //          0, 1 and 3: fewer registers, no local-memory stack.
 template <int STAGE, bool SSS>
-__global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, DeviceScene sc, const FrameConstants* __restrict__ fcp, PathState st, int qi) {
+__global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, DeviceScene sc, const FrameConstants* __restrict__ fcp, PathState st, int qi, int bounceIndex) {
     const FrameConstants& fc = *fcp;
     const uint32_t count = STAGE == 1 ? st.queueCount[4] : st.queueCount[6 + 2 * qi];
     const uint32_t* __restrict__ inQueue = STAGE == 1 ? st.shadowQueue : st.hitQueue;
@@ -1023,6 +1028,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, 
     }
     if ((threadIdx.x & 31) == 0 && rays) { // slots 3..5: rays traced inside the shading stage (shadow feelers, SSS walk)
         atomicAdd(&st.stats[3], (unsigned long long)rays); atomicAdd(&st.stats[4], (unsigned long long)boxes); atomicAdd(&st.stats[5], (unsigned long long)tris);
+        atomicAdd(&st.stats[16 + (bounceIndex < 31 ? bounceIndex : 31)], (unsigned long long)rays);
     }
 }
 
@@ -1150,7 +1156,7 @@ __global__ void __launch_bounds__(256) k_walk_step(DeviceScene sc, const FrameCo
 // a walker, the traversal phase steps all lanes' rays together (one code path per iteration), and the service phase
 // runs walk_step for the lanes whose ray has finished, then either starts the walker's next ray or ends its bounce
 // and takes a new walker from queue `wr`.
-__global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, const FrameConstants* __restrict__ fcp, PathState st, int qi, int wr) {
+__global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, const FrameConstants* __restrict__ fcp, PathState st, int qi, int wr, int bounce) {
     const FrameConstants& fc = *fcp;
     const uint32_t count = st.queueCount[10 + wr];
     uint32_t* __restrict__ next = &st.queueCount[12 + wr];
@@ -1209,7 +1215,7 @@ __global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, 
             }
         }
     }
-    flush_stats(st, 3, rays, ntris, nboxes);
+    flush_stats(st, 3, bounce, rays, ntris, nboxes);
 }
 
 // Paths whose extension ray left the scene (kernel.glsl:1328-1343): radiance += throughput * environment,
@@ -1304,7 +1310,7 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
     const uint32_t heat = fc.settings.OutputType == TB_OUTPUT_HEATMAP;
     for (int b = 0; b < maxBounces; b++) {
         int qi = b & 1;
-        if (timers) cudaEventRecord(timers->next(KernelTimers::EXTEND), stream);
+        if (timers) cudaEventRecord(timers->next(KernelTimers::EXTEND, b), stream);
         static int suspendEnv = -2;
         static uint32_t budgetMain = EXTEND_BUDGET_MAIN, budgets[EXTEND_RESUME_ROUNDS] = {384u, 1536u, 0u}, refillBelow = REFILL_THRESHOLD;
         if (suspendEnv == -2) { // tuning knobs (results never depend on them)
@@ -1331,17 +1337,17 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
             sort_queue(st.queue[qi], &st.queueCount[qi], st.rayO);
             stx.queue[qi] = st.sortTmp;
         }
-        k_extend<EXT_MAIN><<<blocks, 128, 0, stream>>>(bvh, stx, qi, b == 0, heat, fcDev, suspendMode ? budgetMain : 0xffffffffu, refillBelow); launches++;
+        k_extend<EXT_MAIN><<<blocks, 128, 0, stream>>>(bvh, stx, qi, b, heat, fcDev, suspendMode ? budgetMain : 0xffffffffu, refillBelow); launches++;
         if (suspendMode) {
             uint32_t rblocks = (st.susCapacity + 127) / 128;
             if (rblocks > sms * 4) rblocks = sms * 4;
-            if (timers) cudaEventRecord(timers->next(KernelTimers::RESUME), stream);
+            if (timers) cudaEventRecord(timers->next(KernelTimers::RESUME, b), stream);
             for (int r = 1; r <= EXTEND_RESUME_ROUNDS; r++) {
-                k_extend_resume<<<rblocks, 128, 0, stream>>>(bvh, st, qi, r, budgets[r - 1], b == 0, heat, fcDev); launches++;
+                k_extend_resume<<<rblocks, 128, 0, stream>>>(bvh, st, qi, r, budgets[r - 1], b, heat, fcDev); launches++;
                 rblocks = (rblocks + 3) / 4 > sms ? (rblocks + 3) / 4 : sms;
             }
         }
-        if (timers) cudaEventRecord(timers->next(KernelTimers::SHADE), stream);
+        if (timers) cudaEventRecord(timers->next(KernelTimers::SHADE, b), stream);
         k_shade_miss<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(sc, fcDev, st, qi); launches++;
         // next-event shadow rays exist only with lights and NEE on; then shading runs as two stages
         // around a traversal kernel for the shadow queue
@@ -1351,8 +1357,8 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
         // (measured: 874 k triangles +9 %, 36 triangles -26 %)
         const int shadowMode = opts.shadowMode == 2 ? (bvh.numPrims >= 32768u ? 1 : 0) : opts.shadowMode;
         const bool sss = opts.sceneHasSSS;
-#define TB_LAUNCH_SHADE(STG) do { if (sss) k_shade<STG, true><<<blocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi); \
-                                  else k_shade<STG, false><<<blocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi); launches++; } while (0)
+#define TB_LAUNCH_SHADE(STG) do { if (sss) k_shade<STG, true><<<blocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi, b); \
+                                  else k_shade<STG, false><<<blocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi, b); launches++; } while (0)
         if (nee && shadowMode) {
             TB_LAUNCH_SHADE(0);
             PathState sts = st; // what k_extend<EXT_SHADOW> reads its queue from
@@ -1360,7 +1366,7 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
                 sort_queue(st.shadowQueue, &st.queueCount[4], st.shRayO);
                 sts.shadowQueue = st.sortTmp;
             }
-            k_extend<EXT_SHADOW><<<blocks, 128, 0, stream>>>(bvh, sts, qi, 0, 0, fcDev, 0xffffffffu, refillBelow); launches++;
+            k_extend<EXT_SHADOW><<<blocks, 128, 0, stream>>>(bvh, sts, qi, b, 0, fcDev, 0xffffffffu, refillBelow); launches++;
             TB_LAUNCH_SHADE(1);
         } else if (nee) {
             TB_LAUNCH_SHADE(2);
@@ -1373,13 +1379,13 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
             if (roundsEnv == -2) { const char* e = getenv("TB_WALK_ROUNDS"); roundsEnv = e ? atoi(e) : -1; }
             const int rounds = roundsEnv >= 0 ? roundsEnv : opts.walkRounds; // wavefront rounds before the persistent tail (which reads queue rounds & 1)
             for (int r = 0; r < rounds; r++) {
-                k_extend<EXT_WALK><<<blocks, 128, 0, stream>>>(bvh, st, r & 1, 0, 0, fcDev, 0xffffffffu, REFILL_THRESHOLD); launches++;
+                k_extend<EXT_WALK><<<blocks, 128, 0, stream>>>(bvh, st, r & 1, b, 0, fcDev, 0xffffffffu, REFILL_THRESHOLD); launches++;
                 k_walk_step<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(sc, fcDev, st, qi, r & 1); launches++;
             }
             uint32_t wblocks = blocks > sms * 4 ? sms * 4 : blocks;
-            k_walk<<<wblocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi, rounds & 1); launches++;
+            k_walk<<<wblocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi, rounds & 1, b); launches++;
         }
-        if (timers) cudaEventRecord(timers->next(KernelTimers::END), stream);
+        if (timers) cudaEventRecord(timers->next(KernelTimers::END, b), stream);
     }
     return cudaGetLastError();
 }

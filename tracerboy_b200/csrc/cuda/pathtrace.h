@@ -65,23 +65,29 @@ struct PathState {
 // around every k_extend / k_shade launch; resolved by the caller after a stream sync.
 struct KernelTimers {
     enum Tag { EXTEND = 0, SHADE = 1, END = 2, RESUME = 3 };
+    KernelTimers() = default;
+    KernelTimers(const KernelTimers&) = delete;            // owns its events
+    KernelTimers& operator=(const KernelTimers&) = delete;
+    KernelTimers(KernelTimers&& o) noexcept : events(std::move(o.events)), tags(std::move(o.tags)), used(o.used) { o.events.clear(); o.used = 0; }
     std::vector<cudaEvent_t> events;
-    std::vector<int> tags;
+    std::vector<int> tags;   // Tag | bounce << 8
     size_t used = 0;
-    cudaEvent_t next(Tag t) {
+    cudaEvent_t next(Tag t, int bounce) {
         if (used == events.size()) { cudaEvent_t e; cudaEventCreate(&e); events.push_back(e); tags.push_back(0); }
-        tags[used] = (int)t;
+        tags[used] = (int)t | ((bounce < 31 ? bounce : 31) << 8);
         return events[used++];
     }
-    // adds elapsed ms per tag, returns number of (extend, shade) launch pairs
-    void resolve(double& extendMs, double& shadeMs, double& resumeMs, uint64_t& extendLaunches) {
+    // adds elapsed ms per tag (and per bounce: every stage of bounce b, extend to walk), counts the extend launches
+    void resolve(double& extendMs, double& shadeMs, double& resumeMs, uint64_t& extendLaunches, double* bounceMs /*[32]*/, double* bounceExtendMs /*[32]*/) {
         for (size_t i = 0; i + 1 < used; i++) {
-            if (tags[i] == END) continue;
+            const int tag = tags[i] & 0xff, bounce = tags[i] >> 8;
+            if (tag == END) continue;
             float ms = 0;
             cudaEventElapsedTime(&ms, events[i], events[i + 1]);
-            if (tags[i] == EXTEND) { extendMs += ms; extendLaunches++; }
-            else if (tags[i] == RESUME) resumeMs += ms;
+            if (tag == EXTEND) { extendMs += ms; extendLaunches++; bounceExtendMs[bounce] += ms; }
+            else if (tag == RESUME) resumeMs += ms;
             else shadeMs += ms;
+            bounceMs[bounce] += ms;
         }
         used = 0;
     }
@@ -89,6 +95,7 @@ struct KernelTimers {
 };
 
 // scheduling knobs; none of them changes a result
+#define TB_STATS_WORDS 64    // 64-bit words of PathState::stats (layout: flush_stats in pathtrace.cu)
 #define TB_SORT_CELLS 32768u // 5 bits per axis of the ray origin inside the scene box
 
 struct RenderOptions {

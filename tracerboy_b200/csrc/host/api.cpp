@@ -497,7 +497,7 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
     CUDA_OK(h, alloc((void**)&st.aovWorldPos[0], 16 * n)); CUDA_OK(h, alloc((void**)&st.aovWorldPos[1], 16 * n));
     CUDA_OK(h, alloc((void**)&st.aovDepth, 4 * n));
     CUDA_OK(h, alloc((void**)&st.primaryHit, 8 * n)); CUDA_OK(h, alloc((void**)&st.counters, 8 * n));
-    CUDA_OK(h, alloc((void**)&st.stats, 128)); CUDA_OK(h, alloc((void**)&st.readbackStats, sizeof(TbReadbackStats)));
+    CUDA_OK(h, alloc((void**)&st.stats, 8 * TB_STATS_WORDS)); CUDA_OK(h, alloc((void**)&st.readbackStats, sizeof(TbReadbackStats)));
     {
         // private state per slot: 5 float4 + hitGeom + 2 float4 + 2 queues + staging (float4+float+float4+float)
         // + walk state + 2 suspension buffers. Automatic policy: as many slots as fit a third of the free device
@@ -582,7 +582,7 @@ TB_API int tb_render(TbHandle* h, const TbOutputSettings* s, uint32_t nSamples, 
     }
     if (h->comm && todo) h->comm->valid = false; // the job-wide image is stale from here on
     const bool timeLimited = s->TimeLimitInSeconds > 0.0f;
-    const bool serial = timeLimited || h->profiling;
+    const bool serial = timeLimited || h->profiling == 1;
     CUDA_OK(h, cudaEventRecord(h->ev0, h->stream));
     for (auto& sl : h->slots) CUDA_OK(h, cudaStreamWaitEvent(sl.stream, h->ev0, 0)); // slot streams start after ev0
     h->options.suspendRays = serial || h->slots.size() < 8;
@@ -609,7 +609,7 @@ TB_API int tb_render(TbHandle* h, const TbOutputSettings* s, uint32_t nSamples, 
         TbHandle::Slot& sl = h->slots[serial ? 0 : h->framesIssued % h->slots.size()];
         // the slot's previous frame must have been consumed by its k_accumulate
         CUDA_OK(h, cudaStreamWaitEvent(sl.stream, sl.accDone, 0));
-        CUDA_OK(h, render_frame(h->bvh, h->dscene, fc, sl.fcDev, sl.st, sl.stream, h->lc, h->profiling ? &h->timers : nullptr, h->options,
+        CUDA_OK(h, render_frame(h->bvh, h->dscene, fc, sl.fcDev, sl.st, sl.stream, h->lc, h->profiling ? &sl.timers : nullptr, h->options,
                                 serial ? nullptr : &sl.graph));
         CUDA_OK(h, cudaEventRecord(sl.frameDone, sl.stream));
         CUDA_OK(h, cudaStreamWaitEvent(h->stream, sl.frameDone, 0));
@@ -618,9 +618,9 @@ TB_API int tb_render(TbHandle* h, const TbOutputSettings* s, uint32_t nSamples, 
         h->framesIssued++;
         h->samplesRendered++;
         h->pathsStarted += (uint64_t)h->width * h->height;
-        if (h->profiling && h->timers.used > 4096) { // bound the number of live events
+        if (h->profiling && sl.timers.used > 4096) { // bound the number of live events
             CUDA_OK(h, cudaStreamSynchronize(h->stream));
-            h->timers.resolve(h->extendMs, h->shadeMs, h->resumeMs, h->extendLaunches);
+            sl.timers.resolve(h->extendMs, h->shadeMs, h->resumeMs, h->extendLaunches, h->bounceMs, h->bounceExtendMs);
         }
     }
     CUDA_OK(h, cudaEventRecord(h->ev1, h->stream));
@@ -628,7 +628,9 @@ TB_API int tb_render(TbHandle* h, const TbOutputSettings* s, uint32_t nSamples, 
     float ms = 0;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     h->deviceMs += ms;
-    if (h->profiling) h->timers.resolve(h->extendMs, h->shadeMs, h->resumeMs, h->extendLaunches);
+    if (h->profiling) {
+        for (auto& sl : h->slots) { CUDA_OK(h, cudaStreamSynchronize(sl.stream)); sl.timers.resolve(h->extendMs, h->shadeMs, h->resumeMs, h->extendLaunches, h->bounceMs, h->bounceExtendMs); }
+    }
     CUDA_OK(h, cudaGetLastError());
     return TB_OK;
 }
@@ -869,14 +871,16 @@ TB_API int tb_get_render_stats(TbHandle* h, TbRenderStats* out) {
     if (!h || !out) return fail(h, TB_ERR_INVALID_ARG, "null argument");
     memset(out, 0, sizeof(*out));
     if (h->st.stats) {
-        unsigned long long s[9];
+        unsigned long long s[TB_STATS_WORDS];
         CUDA_OK(h, cudaSetDevice(h->device));
         CUDA_OK(h, cudaMemcpyAsync(s, h->st.stats, sizeof(s), cudaMemcpyDeviceToHost, h->stream));
         CUDA_OK(h, cudaStreamSynchronize(h->stream));
         out->RaysTraced = s[0] + s[3] + s[6]; out->BoxesTested = s[1] + s[4] + s[7]; out->TrianglesTested = s[2] + s[5] + s[8];
         out->ExtendRays = s[0]; out->ExtendBoxesTested = s[1]; out->ExtendTrianglesTested = s[2];
         out->ResumeRays = s[6]; out->ResumeBoxesTested = s[7]; out->ResumeTrianglesTested = s[8];
+        for (int b = 0; b < 32; b++) out->RaysByBounce[b] = s[16 + b];
     }
+    for (int b = 0; b < 32; b++) { out->BounceMilliseconds[b] = h->bounceMs[b]; out->BounceExtendMilliseconds[b] = h->bounceExtendMs[b]; }
     out->ExtendLaunches = h->extendLaunches; out->ExtendMilliseconds = h->extendMs; out->ShadeMilliseconds = h->shadeMs; out->ResumeMilliseconds = h->resumeMs;
     out->PathsStarted = h->pathsStarted;
     out->KernelLaunches = h->lc.count;
@@ -885,7 +889,8 @@ TB_API int tb_get_render_stats(TbHandle* h, TbRenderStats* out) {
 }
 TB_API int tb_reset_render_stats(TbHandle* h) {
     if (!h) return TB_ERR_INVALID_ARG;
-    if (h->st.stats) { CUDA_OK(h, cudaSetDevice(h->device)); CUDA_OK(h, cudaMemsetAsync(h->st.stats, 0, 128, h->stream)); }
+    if (h->st.stats) { CUDA_OK(h, cudaSetDevice(h->device)); CUDA_OK(h, cudaMemsetAsync(h->st.stats, 0, 8 * TB_STATS_WORDS, h->stream)); }
+    memset(h->bounceMs, 0, sizeof(h->bounceMs)); memset(h->bounceExtendMs, 0, sizeof(h->bounceExtendMs));
     h->pathsStarted = 0; h->lc.count = 0; h->deviceMs = 0.0;
     h->extendMs = h->shadeMs = h->resumeMs = 0.0; h->extendLaunches = 0;
     return TB_OK;
@@ -915,7 +920,8 @@ TB_API int tb_set_ray_sort(TbHandle* h, int mode) {
 }
 TB_API int tb_set_profiling(TbHandle* h, int enable) {
     if (!h) return TB_ERR_INVALID_ARG;
-    h->profiling = enable != 0;
+    if (enable < 0 || enable > 2) return fail(h, TB_ERR_INVALID_ARG, "profiling mode must be 0, 1 or 2");
+    h->profiling = enable;
     return TB_OK;
 }
 TB_API int tb_synchronize(TbHandle* h) {

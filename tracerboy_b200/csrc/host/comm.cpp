@@ -125,7 +125,7 @@ TB_API int tb_comm_info(TbHandle* h, TbCommInfo* out) {
     if (!h->comm) return TB_OK;
     out->Rank = (uint32_t)h->comm->rank; out->NumRanks = (uint32_t)h->comm->nranks; out->ShardMode = h->comm->mode;
     out->Reductions = h->comm->reductions; out->BytesReceivedPerReduction = h->comm->bytesPerReduction;
-    out->LastReductionMilliseconds = h->comm->lastMs;
+    out->LastReductionMilliseconds = h->comm->lastMs; out->TotalReductionMilliseconds = h->comm->totalMs;
     if (nccl().ok) { int v = 0; if (nccl().GetVersion(&v) == ncclSuccess) out->NcclVersion = (uint32_t)v; }
     return TB_OK;
 }
@@ -176,6 +176,7 @@ TB_API int tb_comm_reduce(TbHandle* h) {
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     c->lastMs = ms;
+    c->totalMs += ms;
     c->reductions++;
     c->valid = true;
     return TB_OK;

@@ -26,7 +26,7 @@ struct Comm {
     bool valid = false;              // the reduced buffers reflect everything rendered so far
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t reductions = 0, bytesPerReduction = 0;
-    double lastMs = 0.0;
+    double lastMs = 0.0, totalMs = 0.0;
 };
 void comm_release_buffers(TbHandle* h);
 void comm_destroy(TbHandle* h);
@@ -50,7 +50,7 @@ struct TbHandle {
     // long tail of one frame's traversal kernels overlaps the next frames' work. h->stream is
     // the accumulate stream: k_accumulate runs there in frame order.
     struct Slot { PathState st; cudaStream_t stream = nullptr; cudaEvent_t frameDone = nullptr, accDone = nullptr;
-                  FrameConstants* fcDev = nullptr; FrameGraph graph; };
+                  FrameConstants* fcDev = nullptr; FrameGraph graph; KernelTimers timers; };
     std::vector<Slot> slots;
     uint32_t framesInFlight = 0;    // 0 = automatic (memory budget), see tb_resize
     uint64_t framesIssued = 0;
@@ -76,13 +76,13 @@ struct TbHandle {
     std::mutex statusLock;
     TbSceneLoadStatus status{TB_LOAD_IDLE, 0, 0};
     std::vector<uint8_t> blueNoiseHost;
-    bool profiling = false;
+    int profiling = 0;              // 0 off, 1 one frame at a time (exclusive kernel times), 2 frames in flight (in-situ shares)
     void* buildScratch = nullptr;   // the builder's temporaries, kept between builds
     uint64_t buildScratchBytes = 0;
     std::map<const void*, DeviceBvh> deviceBuilds; // acceleration structures built into caller memory (tb_bvh_build_device)
     RenderOptions options;
-    KernelTimers timers;
     double extendMs = 0.0, shadeMs = 0.0, resumeMs = 0.0;
+    double bounceMs[32] = {}, bounceExtendMs[32] = {};
     uint64_t extendLaunches = 0;
     tbh::Comm* comm = nullptr;      // multi-GPU: NCCL communicator + reduction buffers (comm.cpp), nullptr on one GPU
 };
