@@ -373,25 +373,22 @@ def main():
     pst = g.GetRenderStats()
     g.SetProfiling(0)
     peak, peak_src = measured_peak_gbs()
-    # k_extend's share of the step: from the exclusive per-launch times (the same definition as the serialised ncu launch
-    # list in profiles/); the per-stream elapsed times under concurrency (mode 2) are reported beside it -- they inflate
-    # short kernels, which wait for the SMs the persistent traversal kernels of other frames hold
+    # The dominant kernel's launch duration is well defined only when it has the GPU to itself: one frame at a time
+    # (profiling mode 1), CUDA events around every k_extend<EXT_MAIN> launch. That is `achieved`. In the timed mode 32
+    # frames overlap and fill each other's tails, so the step is ~2x shorter than the sum of its exclusive launches;
+    # what traversal achieves there is reported as `in_situ` (all rays of the timed region over the whole device time,
+    # shading included: a lower bound of the traversal rate).
     share = pst.ExtendMilliseconds / max(1e-9, pst.ExtendMilliseconds + pst.ShadeMilliseconds + pst.ResumeMilliseconds)
     share_concurrent = cst.ExtendMilliseconds / max(1e-9, cst.ExtendMilliseconds + cst.ShadeMilliseconds + cst.ResumeMilliseconds)
-    frames_rank_timed = spp_rank * args.steps
-    # rays that finish inside k_extend<EXT_MAIN> during the timed region (the rest are shadow / walk / resumed rays)
-    alg_bytes_timed = 32.0 * st.ExtendBoxesTested + 40.0 * st.ExtendTrianglesTested + 64.0 * st.ExtendRays  # SURVEY §8(d), this rank
-    launches_timed = frames_rank_timed * bounces
-    t_render_rank = st.DeviceMilliseconds / 1e3
-    ext_s = share * t_render_rank           # k_extend's part of the timed region
-    achieved = alg_bytes_timed / ext_s / 1e9 if ext_s > 0 else 0.0
+    serial_alg = 32.0 * pst.ExtendBoxesTested + 40.0 * pst.ExtendTrianglesTested + 64.0 * pst.ExtendRays  # SURVEY §8(d)
+    achieved = serial_alg / max(1e-9, pst.ExtendMilliseconds / 1e3) / 1e9
+    in_situ_gbs = (32.0 * boxes_total + 40.0 * tris_total + 64.0 * rays_total) / t_step / 1e9
     units = ncu_units(args.workload)
     bound = "unknown (no ncu capture of this workload in profiles/r2_ncu_units.json)"
     if units:
         pct = {"issue": units.get("issue_active_pct") or 0.0, "l1": units.get("l1tex_throughput_pct") or 0.0,
                "l2": units.get("lts_throughput_pct") or 0.0, "hbm": units.get("dram_throughput_pct") or 0.0}
         bound = max(pct, key=pct.get)
-    serial_alg = 32.0 * pst.ExtendBoxesTested + 40.0 * pst.ExtendTrianglesTested + 64.0 * pst.ExtendRays
     per_bounce = []
     for b in range(min(bounces, 32)):
         if pst.RaysByBounce[b]:
@@ -403,24 +400,23 @@ def main():
         "frac": achieved / peak,
         "traffic": (units or {}).get("dram_bytes_per_launch"),
         "traffic_source": (units or {}).get("source"),
-        "algorithmic_bytes_per_launch": alg_bytes_timed / max(1, launches_timed),
-        "avg_launch_ms": 1e3 * ext_s / max(1, launches_timed), "launches": launches_timed,
-        "kernel_share_of_step": share, "kernel_share_of_stream_time_under_concurrency": share_concurrent,
-        "how": "timed mode: achieved = algorithmic bytes of the rays finished by k_extend<EXT_MAIN> in the timed region / (share x device "
-               "time of the region); share = k_extend's part of the exclusive per-launch CUDA-event times of one frame at a time "
-               "(profiling mode 1, measured in this run; the definition the serialised ncu launch list uses); avg_launch_ms = share x "
-               "time / launches, i.e. what a launch costs with the other frames in flight filling its tail",
+        "algorithmic_bytes_per_launch": serial_alg / max(1, pst.ExtendLaunches),
+        "avg_launch_ms": pst.ExtendMilliseconds / max(1, pst.ExtendLaunches), "launches": pst.ExtendLaunches,
+        "kernel_share_of_step": share,
+        "how": "per-launch CUDA events around k_extend<EXT_MAIN> on its launching stream, one frame at a time (the kernel alone on the GPU), "
+               "%d frames of the workload measured in this run; share = its part of the exclusive time of all launches of a frame "
+               "(the definition the serialised ncu launch list in profiles/ uses)" % min(spp_rank, 16),
         "units_pct_of_peak": units,
-        "exclusive": {  # one frame at a time: what the kernel costs alone on the GPU
-            "achieved": serial_alg / max(1e-9, pst.ExtendMilliseconds / 1e3) / 1e9, "avg_launch_ms": pst.ExtendMilliseconds / max(1, pst.ExtendLaunches),
-            "launches": pst.ExtendLaunches, "kernel_share_of_step": pst.ExtendMilliseconds / max(1e-9, pst.ExtendMilliseconds + pst.ShadeMilliseconds + pst.ResumeMilliseconds),
-            "resume_rounds": {"rays": pst.ResumeRays, "ms": pst.ResumeMilliseconds}},
-        # all rays of the timed region (every kernel, frames in flight overlapped) over the whole step time
-        "whole_step_algorithmic_GBps": (32.0 * boxes_total + 40.0 * tris_total + 64.0 * rays_total) / t_step / 1e9,
+        "resume_rounds": {"rays": pst.ResumeRays, "ms": pst.ResumeMilliseconds},
+        # the timed mode itself: frames in flight overlap, every kernel included
+        "in_situ": {"algorithmic_GBps": in_situ_gbs, "frac": in_situ_gbs / peak,
+                    "what": "algorithmic bytes of ALL rays of the timed region (extension, shadow, walk) / whole device time of the region, "
+                            "shading and accumulation included",
+                    "kernel_share_of_stream_time_under_concurrency": share_concurrent},
         "peak_source": peak_src,
         "note": "algorithmic bytes = 32 B x BoxesTested + 40 B x TrianglesTested + 64 B ray/hit on the reference BVH2 layout (SURVEY 8d). "
                 "`peak` is the measured HBM copy bandwidth; a BVH that fits the 126 MB L2 is served from L1/L2, so `bound` names the unit "
-                "ncu shows closest to its own peak and frac is NOT a DRAM utilisation there",
+                "ncu shows closest to its own peak (units_pct_of_peak) and frac is NOT a DRAM utilisation there",
     }
 
     cpu_baseline = None

@@ -451,6 +451,10 @@ TB_API int tb_set_shadow_mode(TbHandle* h, int mode);
  * 1 = the bounce queue, 3 = bounce and shadow queues, 4 = automatic (default: 3 for scenes whose traversal BVH is
  * beyond 256 MB, i.e. far outside L2, else 0). Scheduling only: results are identical. */
 TB_API int tb_set_ray_sort(TbHandle* h, int mode);
+/* Hit queue of the shading stage grouped by material class (the material's flag bits + "albedo is textured") so that a
+ * warp shades hits that take the same branches: 0 = off, 1 = on, 2 = automatic (default: on when the scene's reachable
+ * materials span more than one class). Scheduling only: results are identical. */
+TB_API int tb_set_material_sort(TbHandle* h, int mode);
 TB_API int tb_synchronize(TbHandle* h);
 
 /* --------------------------------------------------------------- multi-GPU */
@@ -490,6 +494,12 @@ TB_API int tb_postprocess(TbHandle* h, uint32_t outputType, const TbPostProcessS
  * ".exr" (OpenEXR scanline, uncompressed, 32-bit float) and ".pfm" write a float buffer: TB_BUF_RESOLVED_RGB,
  * TB_BUF_POSTPROCESS_RGBA, TB_BUF_ACCUM_RGBW or an AOV (float4 kinds keep their 4th channel as A in .exr). */
 TB_API int tb_save_image(TbHandle* h, uint32_t kind, const char* path);
+/* Host-only: decode a texture file the way the reference's loaders hand it to the GPU (TracerBoy::InitializeTexture,
+ * TracerBoy.cpp:2186-2246; format rules of DirectXTex's WIC / TGA / HDR loaders): .png, .tga, .hdr. *format: 0 = float4
+ * (16 bytes per pixel), 1 = RGBA8 UNORM, 2 = RGBA8 UNORM sRGB (4 bytes per pixel). pixels may be NULL to query the size;
+ * otherwise capBytes must cover width * height * bytes per pixel. *hasAlpha = !IsAlphaAllOpaque(). */
+TB_API int tb_load_image_file(const char* path, uint32_t* width, uint32_t* height, uint32_t* format, int* hasAlpha,
+                              void* pixels, uint64_t capBytes, char* err, size_t errCap);
 /* Host-only: the same writers on a caller-provided image (top row first; 4 x 8 bit for .png, 3 or 4 x float for .exr / .pfm). */
 TB_API int tb_write_image(const char* path, const void* pixels, uint32_t width, uint32_t height, uint32_t channels,
                           uint32_t bytesPerChannel, char* err, size_t errCap);

@@ -43,13 +43,17 @@ void FrameBuffers::resize(uint32_t w, uint32_t h) {
 
 
 // ---------------------------------------------------------------- textures
+// The sampler's sRGB -> linear conversion of an _SRGB format (D3D11.3 functional spec 7.2.1.2), pinned intrinsics.
+inline float srgb_to_linear(float c) { return c <= 0.04045f ? c / 12.92f : pow_((c + 0.055f) / 1.055f, 2.4f); }
 f4 fetch_texel(const Image& im, int x, int y) {
     if (im.format == 0) {
         const float* p = (const float*)im.data.data() + 4 * ((size_t)y * im.width + x);
         return mk4(p[0], p[1], p[2], p[3]);
     }
     const uint8_t* p = im.data.data() + 4 * ((size_t)y * im.width + x);
-    return mk4((float)p[0] / 255.0f, (float)p[1] / 255.0f, (float)p[2] / 255.0f, (float)p[3] / 255.0f);
+    f4 c = mk4((float)p[0] / 255.0f, (float)p[1] / 255.0f, (float)p[2] / 255.0f, (float)p[3] / 255.0f);
+    if (im.format == 2) { c.x = srgb_to_linear(c.x); c.y = srgb_to_linear(c.y); c.z = srgb_to_linear(c.z); } // R8G8B8A8_UNORM_SRGB: per texel, before filtering
+    return c;
 }
 inline int wrapi(int i, int n) { i %= n; return i < 0 ? i + n : i; }
 inline f4 lerp4(f4 a, f4 b, float s) { return mk4(lerp(a.x, b.x, s), lerp(a.y, b.y, s), lerp(a.z, b.z, s), lerp(a.w, b.w, s)); }

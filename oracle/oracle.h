@@ -42,7 +42,7 @@
 namespace oracle {
 
 struct Image {
-    uint32_t width = 0, height = 0, format = 0; // 0 float4, 1 unorm8x4
+    uint32_t width = 0, height = 0, format = 0; // 0 float4, 1 unorm8x4, 2 unorm8x4 sRGB (linearised per texel by the sampler)
     std::vector<uint8_t> data;
 };
 

@@ -195,6 +195,24 @@ def test_curves_scene_bit_exact(tmp_path, built):
     assert (g.Readback(tb.BufferKind.PRIMARY_HIT_IDS)[..., 0] < 2).sum() > 100  # the tubes are visible
 
 
+def test_png_and_tga_albedo_maps_bit_exact(tmp_path, built):
+    """Image textures other than .hdr (TracerBoy.cpp:2186-2246): a PBRT scene with PNG (sRGB and linear RGBA) and TGA
+    albedo maps through the importer; the sRGB image is linearised per texel by the sampler (R8G8B8A8_UNORM_SRGB) and
+    gamma-corrected again by the shader, as in the reference. Every buffer equals the oracle's."""
+    import tracerboy_b200 as tb
+    from tracerboy_b200 import build
+    from test_cpu_images import write_textured_scene
+    if not os.path.exists(os.path.join(build.LIB, "libtb_pbrtimport.so")):
+        pytest.skip("PBRT importer not built (needs the reference mount at build time)")
+    dst = str(tmp_path / "t.tbscene")
+    tb.convert_scene(write_textured_scene(str(tmp_path)), dst)
+    g, o = _pair(dst, 160, 120)
+    s = tb.get_default_output_settings()
+    _compare_render(g, o, s, 3)
+    alb = g.Readback(tb.BufferKind.AOV_ALBEDO)[..., :3]
+    assert len(np.unique(alb.reshape(-1, 3), axis=0)) > 200   # the maps are really sampled
+
+
 def test_full_size_properties_vwvan_4k(vwvan):
     """configs[3] at its full 3840x2160: progressive accumulation is exact (3 + 5 == 8 samples), the weight
     channel counts the samples, radiance is finite, and frames in flight do not change a bit."""
@@ -261,6 +279,25 @@ def test_ray_sort_changes_nothing(tmp_path, built):
         _compare_render(g, o, s, 2) # both sides keep accumulating: frames 0-1, 2-3, 4-5
     with pytest.raises(tb.TracerBoyError):
         g.SetRaySort(2)
+
+
+def test_material_sort_changes_nothing(tmp_path, built):
+    """The shading stage's hit queue grouped by material class (north star (4): "sorted by material to cut divergence";
+    automatic whenever the scene's materials span more than one class) is scheduling only: forced on and off, with the
+    shadow rays inline and as their own stage, with and without ray suspension (one frame in flight), a scene with
+    every material class still equals the oracle bit for bit, counters included."""
+    import tracerboy_b200 as tb
+    path = _tbscene("synthetic:showcase?tris=400&seed=7", tmp_path)
+    s = tb.get_default_output_settings()
+    s.MaxBounces = 6
+    for mode, shadow, fif in ((1, 1, 0), (0, 1, 0), (1, 0, 0), (1, 1, 1), (2, 2, 0)):
+        g, o = _pair(path, 120, 80)
+        g.SetMaterialSort(mode)
+        g.SetShadowMode(shadow)
+        g.SetFramesInFlight(fif)
+        _compare_render(g, o, s, 2)
+    with pytest.raises(tb.TracerBoyError):
+        g.SetMaterialSort(3)
 
 
 @pytest.mark.parametrize("shadow_mode", [0, 1])

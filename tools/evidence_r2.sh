@@ -23,7 +23,13 @@ for w in teapot dragon blobs20m; do
 done
 TB_FIF=1 timeout 900 ncu --set full $EXTRA --import-source on --clock-control none -k regex:k_walk -s 8 -c 3 -o $out/${tag}_walk_blobs20m python tools/profile_run.py blobs20m 2 > $out/${tag}_ncu_walk_blobs20m.log 2>&1
 TB_FIF=1 timeout 900 ncu --set full $EXTRA --import-source on --clock-control none -k regex:k_shade -s 12 -c 4 -o $out/${tag}_shade_vwvan python tools/profile_run.py vwvan 2 > $out/${tag}_ncu_shade_vwvan.log 2>&1
-for f in $out/${tag}_*.ncu-rep; do ncu -i $f --page raw --csv > ${f%.ncu-rep}_raw.csv 2>/dev/null; done
+# raw metric pages + the source page (SASS / source line counters) as text; the .ncu-rep files themselves (10-20 MB each)
+# stay on the box: gpurun_out/ is capped at 64 MiB
+for f in $out/${tag}_*.ncu-rep; do
+  ncu -i $f --page raw --csv > ${f%.ncu-rep}_raw.csv 2>/dev/null
+  ncu -i $f --page source --csv --print-source sass 2>/dev/null | head -c 3000000 > ${f%.ncu-rep}_source_sass.csv
+  rm -f $f
+done
 for f in teapot cornell dragon vwvan blobs20m blobs871k; do python - <<PY
 import json
 try:

@@ -185,7 +185,7 @@ def load_library():
         "tb_render": [vp, C.POINTER(OutputSettings), u32, C.c_float], "tb_samples_rendered": [vp, C.POINTER(u32)],
         "tb_invalidate_history": [vp], "tb_set_frame_shard": [vp, u32, u32], "tb_set_row_shard": [vp, u32, u32], "tb_buffer_size": [vp, u32, C.POINTER(u64)],
         "tb_readback": [vp, u32, vp, u64], "tb_device_buffer": [vp, u32, C.POINTER(vp), C.POINTER(u64)],
-        "tb_get_render_stats": [vp, C.POINTER(RenderStats)], "tb_reset_render_stats": [vp], "tb_synchronize": [vp], "tb_set_profiling": [vp, i32], "tb_set_frames_in_flight": [vp, u32], "tb_set_shadow_mode": [vp, i32], "tb_set_ray_sort": [vp, i32],
+        "tb_get_render_stats": [vp, C.POINTER(RenderStats)], "tb_reset_render_stats": [vp], "tb_synchronize": [vp], "tb_set_profiling": [vp, i32], "tb_set_frames_in_flight": [vp, u32], "tb_set_shadow_mode": [vp, i32], "tb_set_ray_sort": [vp, i32], "tb_set_material_sort": [vp, i32],
         "tb_is_material_id_valid": [vp, i32], "tb_get_material": [vp, i32, C.POINTER(Material), C.c_char_p, u32],
         "tb_set_material": [vp, i32, C.POINTER(Material)],
         "tb_bvh_prebuild_info": [C.POINTER(GeometryDesc), u32, C.POINTER(PrebuildInfo)],
@@ -200,6 +200,7 @@ def load_library():
         "tb_temporal_accumulate_image": [vp, C.POINTER(TemporalAccumulationParams), u32, u32, vp, vp, vp, vp, vp, vp, vp, vp],
         "tb_save_image": [vp, u32, C.c_char_p],
         "tb_write_image": [C.c_char_p, vp, u32, u32, u32, u32, C.c_char_p, C.c_size_t],
+        "tb_load_image_file": [C.c_char_p, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_int), vp, u64, C.c_char_p, C.c_size_t],
         "tb_postprocess_image": [vp, vp, vp, u32, u32, u32, C.POINTER(PostProcessSettings), vp, vp, vp, C.POINTER(C.c_float)],
     }
     for name, args in sig.items():
@@ -219,7 +220,7 @@ EXPORTED_SYMBOLS = ["tb_create", "tb_destroy", "tb_last_error", "tb_version", "t
                     "tb_get_material", "tb_set_material", "tb_bvh_prebuild_info", "tb_bvh_build", "tb_trace_rays",
                     "tb_get_default_postprocess_settings", "tb_postprocess", "tb_postprocess_image",
                     "tb_temporal_accumulate_image", "tb_save_image", "tb_write_image", "tb_update", "tb_camera_update", "tb_set_ray_sort",
-                    "tb_max_triangles", "tb_bvh_build_device", "tb_trace_rays_device", "tb_bvh_forget_device", "tb_get_bvh_depth",
+                    "tb_set_material_sort", "tb_load_image_file", "tb_max_triangles", "tb_bvh_build_device", "tb_trace_rays_device", "tb_bvh_forget_device", "tb_get_bvh_depth",
                     "tb_comm_get_unique_id", "tb_comm_init", "tb_comm_destroy", "tb_comm_info", "tb_comm_reduce"]
 
 
@@ -291,6 +292,22 @@ def prebuild_info(descs, n):
     if rc != 0:
         raise TracerBoyError(rc, "tb_bvh_prebuild_info")
     return info
+
+
+def load_image_file(path):
+    """Host-only: decode a .png / .tga / .hdr texture as the reference's loaders would hand it to the GPU.
+    Returns (pixels, format, has_alpha): float32 [h, w, 4] for format 0, uint8 [h, w, 4] for 1 (UNORM) and 2 (UNORM sRGB)."""
+    lib = load_library()
+    w, h, fmt, alpha = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_int()
+    err = C.create_string_buffer(512)
+    rc = lib.tb_load_image_file(str(path).encode(), C.byref(w), C.byref(h), C.byref(fmt), C.byref(alpha), None, 0, err, 512)
+    if rc != 0:
+        raise TracerBoyError(rc, err.value.decode())
+    out = np.empty((h.value, w.value, 4), np.float32 if fmt.value == 0 else np.uint8)
+    rc = lib.tb_load_image_file(str(path).encode(), C.byref(w), C.byref(h), C.byref(fmt), C.byref(alpha), out.ctypes.data, out.nbytes, err, 512)
+    if rc != 0:
+        raise TracerBoyError(rc, err.value.decode())
+    return out, fmt.value, bool(alpha.value)
 
 
 def convert_scene(src, dst):
@@ -555,6 +572,10 @@ class TracerBoy:
     def SetRaySort(self, mode):
         """0 off, 1 bounce queue, 3 bounce + shadow queues, 4 automatic (scheduling only, results are identical)."""
         self._ck(self._lib.tb_set_ray_sort(self._h, int(mode)))
+
+    def SetMaterialSort(self, mode):
+        """0 off, 1 on, 2 automatic: the shading stage's hit queue grouped by material class (scheduling only)."""
+        self._ck(self._lib.tb_set_material_sort(self._h, int(mode)))
 
     def SetProfiling(self, enable):
         self._ck(self._lib.tb_set_profiling(self._h, int(enable)))

@@ -29,7 +29,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-I" + os.path.join(ROOT, "include"), "-ccbin", GXX]
 
 CUDA_SRCS = ["csrc/cuda/bvh_build.cu", "csrc/cuda/pathtrace.cu", "csrc/cuda/postprocess.cu", "csrc/cuda/reduce.cu"]
-HOST_SRCS = ["csrc/host/api.cpp", "csrc/host/comm.cpp", "csrc/host/scene.cpp", "csrc/host/image_io.cpp"]
+HOST_SRCS = ["csrc/host/api.cpp", "csrc/host/comm.cpp", "csrc/host/scene.cpp", "csrc/host/image_io.cpp", "csrc/host/image_decode.cpp"]
 HEADERS = ["csrc/cuda/device_types.h", "csrc/cuda/pathtrace.h", "csrc/cuda/traverse.cuh", "csrc/cuda/launch.h", "csrc/cuda/postprocess.h", "csrc/cuda/reduce.h", "csrc/host/handle.h",
            "csrc/common/tb_math.h", "csrc/common/tb_vec.h", "csrc/host/scene.h", "../include/tracerboy_b200.h"]
 
@@ -92,7 +92,7 @@ def build_pbrt_import(force=False):
     if not os.path.isdir(parser):
         return target if os.path.exists(target) else None
     mine = [os.path.join(PKG, "csrc/host/pbrt_import.cpp"), os.path.join(PKG, "csrc/host/scene.cpp"),
-            os.path.join(PKG, "csrc/host/scene.h")]
+            os.path.join(PKG, "csrc/host/image_decode.cpp"), os.path.join(PKG, "csrc/host/scene.h")]
     stamp = _stamp(mine)
     if not force and _up_to_date(target, stamp):
         return target
@@ -115,7 +115,7 @@ def build_pbrt_import(force=False):
     _run([GXX.replace("g++", "gcc"), "-O2", "-fPIC", "-w", "-c", os.path.join(parser, "impl/3rdParty/rply.c"), "-o", rply])
     _run([GXX, "-O2", "-std=c++14", "-fPIC", "-shared", "-fvisibility=hidden", "-w", "-include", "cstdint", "-mfma",
           "-ffp-contract=off", "-I" + os.path.join(parser, "include"), "-I" + os.path.join(ROOT, "include"),
-          "-I" + os.path.join(PKG, "csrc/host"), mine[0], mine[1]] + objs + [rply, "-o", target])
+          "-I" + os.path.join(PKG, "csrc/host"), mine[0], mine[1], mine[2]] + objs + [rply, "-o", target])
     _write_stamp(target, stamp)
     return target
 

@@ -74,10 +74,14 @@ struct Rng {
 };
 
 // ------------------------------------------------------------------ textures
+// The sampler's sRGB -> linear conversion of an _SRGB format (D3D11.3 functional spec 7.2.1.2), pinned intrinsics.
+__device__ __forceinline__ float srgb_to_linear(float c) { return c <= 0.04045f ? c / 12.92f : pow_((c + 0.055f) / 1.055f, 2.4f); }
 __device__ __forceinline__ f4 fetch_texel(const DeviceScene::ImageRef& im, int x, int y) {
     if (im.format == 0) return *((const f4*)im.data + ((size_t)y * im.width + x));
     uchar4 c = *((const uchar4*)im.data + ((size_t)y * im.width + x));
-    return mk4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
+    f4 v = mk4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
+    if (im.format == 2) { v.x = srgb_to_linear(v.x); v.y = srgb_to_linear(v.y); v.z = srgb_to_linear(v.z); } // R8G8B8A8_UNORM_SRGB: per texel, before filtering
+    return v;
 }
 __device__ __forceinline__ int wrapi(int i, int n) { i %= n; return i < 0 ? i + n : i; }
 __device__ __forceinline__ f4 lerp4(f4 a, f4 b, float s) { return mk4(lerp(a.x, b.x, s), lerp(a.y, b.y, s), lerp(a.z, b.z, s), lerp(a.w, b.w, s)); }
@@ -513,10 +517,28 @@ __device__ __forceinline__ bool write_hit(PathState& st, const Traversal& tr, ui
     return h.t >= 0.0f;
 }
 
+// Material class of a hit: the key of the shading stage's queue (north star: "hit queues ... sorted by material to cut
+// divergence"). The divergent code of the bounce is selected by the material's flags (kernel.glsl:1394-1417 lobe
+// choice, :1519-1697 specular / subsurface / diffuse branches; RayGenCommon.h:298-341 mix and textured fetch), so
+// the key is those flag bits plus "albedo comes from a texture": 6 bits, 64 classes.
+#define TB_CLASS_BITS 6
+#define TB_CLASS_SHIFT 26            // a queue entry is pixel | class << 26 (tb_resize caps the image at 2^26 pixels)
+#define TB_PIXEL_MASK 0x03ffffffu
+#define TB_CLASS_COUNT_BASE 16       // queueCount[16 .. 79]: hits per class of the current bounce, [80 .. 143]: scatter cursors
+__device__ __forceinline__ uint32_t material_class(const TbGeometryRecord* __restrict__ geoms, const TbMaterial* __restrict__ mats, uint32_t geom) {
+    const uint32_t mi = __ldg(&geoms[geom].MaterialIndex);
+    const uint32_t* m = (const uint32_t*)(mats + mi);
+    const uint32_t flags = __ldg(m + 19), albedoIndex = __ldg(m + 3);
+    return (flags & 0x1fu) | (albedoIndex != TB_INVALID_TEXTURE ? 0x20u : 0u); // METALLIC 1, SSS 2, NO_SPECULAR 4, MIX 8, LIGHT 16, textured 32
+}
+
 // hit / miss queues of the bounce: counters [6 + 2*qi] (hits) and [7 + 2*qi] (misses)
-__device__ __forceinline__ void push_sorted(PathState& st, int qi, uint32_t pi, bool hit) {
+__device__ __forceinline__ void push_sorted(PathState& st, int qi, uint32_t pi, bool hit, uint32_t cls, bool classSort) {
     uint32_t slot = atomicAdd(&st.queueCount[6 + 2 * qi + (hit ? 0 : 1)], 1u);
-    (hit ? st.hitQueue : st.missQueue)[slot] = pi;
+    if (hit) {
+        st.hitQueue[slot] = pi | (cls << TB_CLASS_SHIFT);
+        if (classSort) atomicAdd(&st.queueCount[TB_CLASS_COUNT_BASE + cls], 1u);
+    } else st.missQueue[slot] = pi;
 }
 
 // stats layout (TB_STATS_WORDS 64-bit words): [0..2] rays / boxes / tris finished in k_extend<EXT_MAIN>, [3..5] in the
@@ -547,7 +569,9 @@ __device__ __forceinline__ bool try_suspend(PathState& st, int round, const Trav
 #define EXT_SHADOW 1
 #define EXT_WALK 2
 template <int KIND>
-__global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh, PathState st, int qi, int bounce, uint32_t outputHeatmap, const FrameConstants* __restrict__ fcp, uint32_t budgetMain, uint32_t refillBelow) {
+__global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh, PathState st, int qi, int bounce, uint32_t outputHeatmap, const FrameConstants* __restrict__ fcp, uint32_t budgetMain, uint32_t refillBelow,
+                                                                   const TbGeometryRecord* __restrict__ classGeoms, const TbMaterial* __restrict__ classMats) {
+    const bool classSort = KIND == EXT_MAIN && classGeoms != nullptr; // hits carry their material class and are counted per class
     const uint32_t aovMask = fcp->aovMask;
     const int bounceIsZero = bounce == 0;
     const uint32_t count = KIND == EXT_SHADOW ? st.queueCount[4] : KIND == EXT_WALK ? st.queueCount[10 + qi] : st.queueCount[qi];
@@ -595,6 +619,12 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
         }
         if (KIND == EXT_MAIN) { // sort retired paths into the hit / miss queues (material-class split of the shading stage)
             uint32_t mh = __ballot_sync(0xffffffffu, retired && retiredHit), mm = __ballot_sync(0xffffffffu, retired && !retiredHit);
+            uint32_t cls = 0;
+            if (classSort && retired && retiredHit) { // one counter update per distinct class per warp
+                cls = material_class(classGeoms, classMats, tr.hitGeom);
+                const uint32_t peers = __match_any_sync(mh, cls);
+                if (lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&st.queueCount[TB_CLASS_COUNT_BASE + cls], (uint32_t)__popc(peers));
+            }
             if (mh | mm) {
                 uint32_t bh = 0, bm = 0;
                 if (lane == 0) {
@@ -603,7 +633,7 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
                 }
                 bh = __shfl_sync(0xffffffffu, bh, 0); bm = __shfl_sync(0xffffffffu, bm, 0);
                 const uint32_t below = (1u << lane) - 1u;
-                if (retired && retiredHit) st.hitQueue[bh + __popc(mh & below)] = pi;
+                if (retired && retiredHit) st.hitQueue[bh + __popc(mh & below)] = pi | (cls << TB_CLASS_SHIFT);
                 if (retired && !retiredHit) st.missQueue[bm + __popc(mm & below)] = pi;
             }
         }
@@ -654,7 +684,9 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
 
 // Resume round `round` (1-based): continues the rays parked by round-1; the last round has no budget.
 __global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState st, int qi, int round, uint32_t budget, int bounce,
-                                                       uint32_t outputHeatmap, const FrameConstants* __restrict__ fcp) {
+                                                       uint32_t outputHeatmap, const FrameConstants* __restrict__ fcp,
+                                                       const TbGeometryRecord* __restrict__ classGeoms, const TbMaterial* __restrict__ classMats) {
+    const bool classSort = classGeoms != nullptr;
     const uint32_t aovMask = fcp->aovMask;
     const int bounceIsZero = bounce == 0;
     const uint32_t count = min(st.susCount[round - 1], st.susCapacity);
@@ -668,7 +700,11 @@ __global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState 
         uint32_t pi = tr.resume(bvh, in + (size_t)i * Traversal::kRecordWords, stack, st.rayO, st.rayD, MIN_T, FAR_T);
         uint32_t suspendAt = tr.steps() + budget;
         while (true) {
-            if (tr.done()) { push_sorted(st, qi, pi, write_hit(st, tr, pi, bounceIsZero, outputHeatmap, aovMask, rays, ntris, nboxes)); break; }
+            if (tr.done()) {
+                const bool hit = write_hit(st, tr, pi, bounceIsZero, outputHeatmap, aovMask, rays, ntris, nboxes);
+                push_sorted(st, qi, pi, hit, (hit && classSort) ? material_class(classGeoms, classMats, tr.hitGeom) : 0u, classSort);
+                break;
+            }
             if (budget && tr.steps() >= suspendAt) {
                 if (try_suspend(st, round, tr, stack, pi)) break;
                 suspendAt += budget;
@@ -754,6 +790,34 @@ __global__ void __launch_bounds__(256) k_sort_scatter(PathState st, const uint32
     }
 }
 
+// Counting sort of the bounce's hit queue by material class: the histogram was filled by k_extend as the rays
+// retired, so one pass is left (every block derives the class offsets from the 64 counters itself). A warp of the
+// shading stage then works on hits of ONE class: the same branch of the lobe choice / specular / subsurface /
+// diffuse code, the same texture path. Order inside a class is arbitrary (every path is independent).
+__global__ void __launch_bounds__(256) k_class_scatter(PathState st, int qi) {
+    __shared__ uint32_t s_start[1u << TB_CLASS_BITS];
+    const uint32_t count = st.queueCount[6 + 2 * qi];
+    if (threadIdx.x < (1u << TB_CLASS_BITS)) {
+        uint32_t run = 0;
+        for (uint32_t c = 0; c < threadIdx.x; c++) run += st.queueCount[TB_CLASS_COUNT_BASE + c];
+        s_start[threadIdx.x] = run;
+    }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t* __restrict__ cursor = st.queueCount + TB_CLASS_COUNT_BASE + (1u << TB_CLASS_BITS);
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < count; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + lane;
+        const uint32_t e = i < count ? st.hitQueue[i] : 0xffffffffu;
+        const uint32_t key = i < count ? (e >> TB_CLASS_SHIFT) : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+        uint32_t pos = 0;
+        if (i < count && lane == leader) pos = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+        pos = __shfl_sync(0xffffffffu, pos, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        if (i < count) st.hitSorted[s_start[key] + pos] = e & TB_PIXEL_MASK;
+    }
+}
+
 // ----------------------------------------------------------------------- shade
 // End of a path: firefly clamp + filter weight (kernel.glsl:1907-1920) and NaN rejection
 // (RayGenCommon.h:704-707). The sample and the path's rand() seed are staged per frame;
@@ -777,14 +841,17 @@ __device__ __forceinline__ void finish_path(const FrameConstants& fc, PathState&
 //          without them (checked on the host) get a kernel with no traversal code at all in stages
 //          0, 1 and 3: fewer registers, no local-memory stack.
 template <int STAGE, bool SSS>
-__global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, DeviceScene sc, const FrameConstants* __restrict__ fcp, PathState st, int qi, int bounceIndex) {
+__global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, DeviceScene sc, const FrameConstants* __restrict__ fcp, PathState st, int qi, int bounceIndex, int sortedHits) {
     const FrameConstants& fc = *fcp;
     const uint32_t count = STAGE == 1 ? st.queueCount[4] : st.queueCount[6 + 2 * qi];
-    const uint32_t* __restrict__ inQueue = STAGE == 1 ? st.shadowQueue : st.hitQueue;
-    if (STAGE != 1 && blockIdx.x == 0 && threadIdx.x == 0) {
-        st.queueCount[2 + (qi ^ 1)] = 0; // work counter of the next k_extend
-        st.queueCount[6 + 2 * (qi ^ 1)] = 0; st.queueCount[7 + 2 * (qi ^ 1)] = 0; // hit / miss queues of the next bounce
-        for (int r = 0; r < 4; r++) st.susCount[r] = 0; // suspension counters of the next bounce
+    const uint32_t* __restrict__ inQueue = STAGE == 1 ? st.shadowQueue : (sortedHits ? st.hitSorted : st.hitQueue);
+    if (STAGE != 1 && blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            st.queueCount[2 + (qi ^ 1)] = 0; // work counter of the next k_extend
+            st.queueCount[6 + 2 * (qi ^ 1)] = 0; st.queueCount[7 + 2 * (qi ^ 1)] = 0; // hit / miss queues of the next bounce
+            for (int r = 0; r < 4; r++) st.susCount[r] = 0; // suspension counters of the next bounce
+        }
+        st.queueCount[TB_CLASS_COUNT_BASE + threadIdx.x] = 0; // 128 threads: class counters + scatter cursors of the next bounce
     }
     const TbOutputSettings& S = fc.settings;
     const int MaxBounces = S.MaxBounces;
@@ -798,7 +865,7 @@ __global__ void __launch_bounds__(128, SHADE_MIN_BLOCKS) k_shade(DeviceBvh bvh, 
         bool walker = false, walkerPerfectSpec = false; // entered a subsurface / glass medium: continues in k_walk
         uint32_t pi = 0;
         if (i < count) {
-            pi = inQueue[i];
+            pi = inQueue[i] & TB_PIXEL_MASK; // (hit-queue entries carry the material class in their top bits)
             float4 o4 = st.rayO[pi], d4 = st.rayD[pi], t4 = st.thr[pi], c4 = st.col[pi], h4 = st.hit[pi];
             Rng rng; rng.seed = o4.w; rng.time = fc.time;
             uint32_t sw = __float_as_uint(d4.w);
@@ -1298,7 +1365,7 @@ static bool sort_pays(const DeviceBvh& bvh) { return (uint64_t)bvh.numPrims * 11
 static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, const FrameConstants& fc, const FrameConstants* fcDev,
                                 PathState& st, cudaStream_t stream, uint64_t& launches, KernelTimers* timers, const RenderOptions& opts) {
     const uint32_t n = fc.width * fc.height;
-    cudaMemsetAsync(st.queueCount, 0, 64, stream);
+    cudaMemsetAsync(st.queueCount, 0, 4 * TB_QUEUE_COUNT_WORDS, stream);
     cudaMemsetAsync(st.susCount, 0, 16, stream);
     k_raygen<<<(n + 255) / 256, 256, 0, stream>>>(sc, fcDev, st); launches++;
     // persistent grids: a multiple of the SM count, capped by the work available
@@ -1337,18 +1404,25 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
             sort_queue(st.queue[qi], &st.queueCount[qi], st.rayO);
             stx.queue[qi] = st.sortTmp;
         }
-        k_extend<EXT_MAIN><<<blocks, 128, 0, stream>>>(bvh, stx, qi, b, heat, fcDev, suspendMode ? budgetMain : 0xffffffffu, refillBelow); launches++;
+        // hits are binned by material class when the scene's reachable materials span more than one class
+        static int classEnv = -2; // tuning knob (results never depend on it)
+        if (classEnv == -2) { const char* e = getenv("TB_CLASS_SORT"); classEnv = e ? atoi(e) : -1; }
+        const bool classSort = classEnv >= 0 ? classEnv != 0 : (opts.materialSort == 2 ? opts.sceneMaterialClasses > 1 : opts.materialSort != 0);
+        const TbGeometryRecord* classGeoms = classSort ? sc.geoms : nullptr;
+        const TbMaterial* classMats = classSort ? sc.materials : nullptr;
+        k_extend<EXT_MAIN><<<blocks, 128, 0, stream>>>(bvh, stx, qi, b, heat, fcDev, suspendMode ? budgetMain : 0xffffffffu, refillBelow, classGeoms, classMats); launches++;
         if (suspendMode) {
             uint32_t rblocks = (st.susCapacity + 127) / 128;
             if (rblocks > sms * 4) rblocks = sms * 4;
             if (timers) cudaEventRecord(timers->next(KernelTimers::RESUME, b), stream);
             for (int r = 1; r <= EXTEND_RESUME_ROUNDS; r++) {
-                k_extend_resume<<<rblocks, 128, 0, stream>>>(bvh, st, qi, r, budgets[r - 1], b, heat, fcDev); launches++;
+                k_extend_resume<<<rblocks, 128, 0, stream>>>(bvh, st, qi, r, budgets[r - 1], b, heat, fcDev, classGeoms, classMats); launches++;
                 rblocks = (rblocks + 3) / 4 > sms ? (rblocks + 3) / 4 : sms;
             }
         }
         if (timers) cudaEventRecord(timers->next(KernelTimers::SHADE, b), stream);
         k_shade_miss<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(sc, fcDev, st, qi); launches++;
+        if (classSort) { k_class_scatter<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(st, qi); launches++; }
         // next-event shadow rays exist only with lights and NEE on; then shading runs as two stages
         // around a traversal kernel for the shadow queue
         const bool nee = sc.numLights > 0 && fc.settings.EnableNextEventEstimation;
@@ -1357,8 +1431,8 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
         // (measured: 874 k triangles +9 %, 36 triangles -26 %)
         const int shadowMode = opts.shadowMode == 2 ? (bvh.numPrims >= 32768u ? 1 : 0) : opts.shadowMode;
         const bool sss = opts.sceneHasSSS;
-#define TB_LAUNCH_SHADE(STG) do { if (sss) k_shade<STG, true><<<blocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi, b); \
-                                  else k_shade<STG, false><<<blocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi, b); launches++; } while (0)
+#define TB_LAUNCH_SHADE(STG) do { if (sss) k_shade<STG, true><<<blocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi, b, classSort ? 1 : 0); \
+                                  else k_shade<STG, false><<<blocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi, b, classSort ? 1 : 0); launches++; } while (0)
         if (nee && shadowMode) {
             TB_LAUNCH_SHADE(0);
             PathState sts = st; // what k_extend<EXT_SHADOW> reads its queue from
@@ -1366,7 +1440,7 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
                 sort_queue(st.shadowQueue, &st.queueCount[4], st.shRayO);
                 sts.shadowQueue = st.sortTmp;
             }
-            k_extend<EXT_SHADOW><<<blocks, 128, 0, stream>>>(bvh, sts, qi, b, 0, fcDev, 0xffffffffu, refillBelow); launches++;
+            k_extend<EXT_SHADOW><<<blocks, 128, 0, stream>>>(bvh, sts, qi, b, 0, fcDev, 0xffffffffu, refillBelow, nullptr, nullptr); launches++;
             TB_LAUNCH_SHADE(1);
         } else if (nee) {
             TB_LAUNCH_SHADE(2);
@@ -1379,7 +1453,7 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
             if (roundsEnv == -2) { const char* e = getenv("TB_WALK_ROUNDS"); roundsEnv = e ? atoi(e) : -1; }
             const int rounds = roundsEnv >= 0 ? roundsEnv : opts.walkRounds; // wavefront rounds before the persistent tail (which reads queue rounds & 1)
             for (int r = 0; r < rounds; r++) {
-                k_extend<EXT_WALK><<<blocks, 128, 0, stream>>>(bvh, st, r & 1, b, 0, fcDev, 0xffffffffu, REFILL_THRESHOLD); launches++;
+                k_extend<EXT_WALK><<<blocks, 128, 0, stream>>>(bvh, st, r & 1, b, 0, fcDev, 0xffffffffu, REFILL_THRESHOLD, nullptr, nullptr); launches++;
                 k_walk_step<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(sc, fcDev, st, qi, r & 1); launches++;
             }
             uint32_t wblocks = blocks > sms * 4 ? sms * 4 : blocks;
@@ -1408,7 +1482,8 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
     if (!graph || timers || !useGraphs) return launch_frame(bvh, sc, fc, fcDev, st, stream, lc.count, timers, opts);
     FrameGraph::Key key = {opts.epoch, fc.width, fc.height, (uint32_t)fc.settings.MaxBounces, fc.settings.OutputType == TB_OUTPUT_HEATMAP ? 1u : 0u,
                            fc.settings.EnableNextEventEstimation ? 1u : 0u, (uint32_t)opts.shadowMode, (uint32_t)opts.walkRounds,
-                           opts.sceneHasSSS ? 1u : 0u, opts.suspendRays ? 1u : 0u, (uint32_t)opts.sortRays};
+                           opts.sceneHasSSS ? 1u : 0u, opts.suspendRays ? 1u : 0u, (uint32_t)opts.sortRays,
+                           (uint32_t)opts.materialSort * 256u + opts.sceneMaterialClasses};
     if (!graph->exec || memcmp(&key, &graph->key, sizeof(key)) != 0) {
         graph->reset();
         cudaGraph_t g = nullptr;

@@ -18,9 +18,10 @@ struct PathState {
     float4* neighbor = nullptr;    // neighbour camera ray origin (bounce 0 only)
     float4* neighborDir = nullptr; // neighbour camera ray direction
     uint32_t* queue[2] = {nullptr, nullptr};
-    uint32_t* queueCount = nullptr; // [0..1] queue sizes, [2..3] k_extend work counters, [4] shadow queue size, [5] its work counter, [6..9] hit/miss queue sizes, [10..11] walk queue sizes, [12..13] their work counters
+    uint32_t* queueCount = nullptr; // TB_QUEUE_COUNT_WORDS words: [16..79] hits per material class, [80..143] the class sort's cursors, [0..1] queue sizes, [2..3] k_extend work counters, [4] shadow queue size, [5] its work counter, [6..9] hit/miss queue sizes, [10..11] walk queue sizes, [12..13] their work counters
     // the bounce's paths sorted by k_extend into "hit something" / "left the scene"; counters [6..9] by queue parity
-    uint32_t* hitQueue = nullptr;
+    uint32_t* hitQueue = nullptr;   // entries: pixel | material class << 26
+    uint32_t* hitSorted = nullptr;  // the hit queue grouped by material class (k_class_scatter), plain pixels
     uint32_t* missQueue = nullptr;
     // next-event shadow rays: queued by k_shade<0>, traced by k_extend<true>, consumed by k_shade<1>
     uint32_t* shadowQueue = nullptr;
@@ -95,6 +96,7 @@ struct KernelTimers {
 };
 
 // scheduling knobs; none of them changes a result
+#define TB_QUEUE_COUNT_WORDS 144
 #define TB_STATS_WORDS 64    // 64-bit words of PathState::stats (layout: flush_stats in pathtrace.cu)
 #define TB_SORT_CELLS 32768u // 5 bits per axis of the ray origin inside the scene box
 
@@ -104,6 +106,8 @@ struct RenderOptions {
     int walkRounds = 1; // glass / subsurface walk: wavefront rounds (k_extend<EXT_WALK> + k_walk_step) before the persistent tail kernel
     bool suspendRays = true; // park rays over budget and resume them in k_extend_resume rounds (set by the host: on with fewer than 8 frames in flight)
     int sortRays = 2;   // spatial sort of the ray queues before traversal: 0 off, bit 0 bounce queue, bit 1 shadow queue (1 or 3), 2 automatic (3 for scenes whose BVH is far beyond L2)
+    int materialSort = 2; // hit queue grouped by material class before shading: 0 off, 1 on, 2 automatic (on when the scene's reachable materials span more than one class)
+    uint32_t sceneMaterialClasses = 1; // distinct material classes reachable from the geometry (host-side count)
     int numSMs = 148;   // of the handle's device (persistent grids are sized from it)
     bool sceneHasSSS = true; // any material with the subsurface flag (selects the k_shade variant with the inline random walk)
 };
@@ -114,7 +118,7 @@ cudaError_t build_bvh(const BuildGeometry* d_geoms, const uint32_t* d_triPrefix,
                       DeviceBvh& out, void* scratch, cudaStream_t stream, LaunchCounter& lc);
 // The captured kernel sequence of one frame on one frame slot (see render_frame).
 struct FrameGraph {
-    struct Key { uint32_t epoch, width, height, maxBounces, heat, nee, shadowMode, walkRounds, sss, suspend, sort; }; // no padding: compared with memcmp
+    struct Key { uint32_t epoch, width, height, maxBounces, heat, nee, shadowMode, walkRounds, sss, suspend, sort, classSort; }; // no padding: compared with memcmp
     Key key{};
     cudaGraphExec_t exec = nullptr;
     uint64_t launches = 0; // kernels inside the graph

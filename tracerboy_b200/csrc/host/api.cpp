@@ -102,6 +102,17 @@ static bool scene_has_sss(const tb::Scene& s) {
     return false;
 }
 
+// distinct material classes (the key of the shading stage's queue, material_class() in pathtrace.cu) among the
+// materials the geometry references
+static uint32_t scene_material_classes(const tb::Scene& s) {
+    uint64_t seen = 0;
+    for (const TbGeometryRecord& g : s.geoms) {
+        const TbMaterial& m = s.materials[g.MaterialIndex];
+        seen |= 1ull << (((uint32_t)m.Flags & 0x1fu) | (m.albedoIndex != TB_INVALID_TEXTURE ? 0x20u : 0u));
+    }
+    return (uint32_t)__builtin_popcountll(seen);
+}
+
 // One build on caller-described device geometry into caller-provided (or library-owned) memory. Shared by the scene
 // path (upload_and_build) and the SW-RT seam (tb_bvh_build_device).
 static int run_build(TbHandle* h, const std::vector<BuildGeometry>& descs, const std::vector<uint32_t>& prefix, uint32_t n,
@@ -189,6 +200,7 @@ static int upload_and_build(TbHandle* h, uint32_t flags) {
     h->bvhBuildMs = ms;
     h->camera = s.camera;
     h->options.sceneHasSSS = scene_has_sss(s);
+    h->options.sceneMaterialClasses = scene_material_classes(s);
     h->sceneLoaded = true;
     h->samplesRendered = 0;
     set_status(h, TB_LOAD_FINISHED, (uint32_t)s.geoms.size(), (uint32_t)s.geoms.size());
@@ -479,7 +491,7 @@ TB_API int tb_update(TbHandle* h, int mouseX, int mouseY, const uint8_t* keys, f
 }
 
 TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
-    if (!h || w == 0 || hh == 0 || (uint64_t)w * hh > (1ull << 28)) return fail(h, TB_ERR_INVALID_ARG, "bad resolution");
+    if (!h || w == 0 || hh == 0 || (uint64_t)w * hh > (1ull << 26)) return fail(h, TB_ERR_INVALID_ARG, "bad resolution (at most 2^26 pixels: queue entries keep 6 bits for the material class)");
     CUDA_OK(h, cudaSetDevice(h->device));
     if (w == h->width && hh == h->height) return TB_OK;
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
@@ -524,8 +536,8 @@ TB_API int tb_resize(TbHandle* h, uint32_t w, uint32_t hh) {
         CUDA_OK(h, alloc((void**)&p.hit, 16 * n)); CUDA_OK(h, alloc((void**)&p.hitGeom, 4 * n));
         CUDA_OK(h, alloc((void**)&p.neighbor, 16 * n)); CUDA_OK(h, alloc((void**)&p.neighborDir, 16 * n));
         CUDA_OK(h, alloc((void**)&p.queue[0], 4 * n)); CUDA_OK(h, alloc((void**)&p.queue[1], 4 * n));
-        CUDA_OK(h, alloc((void**)&p.queueCount, 64));
-        CUDA_OK(h, alloc((void**)&p.hitQueue, 4 * n)); CUDA_OK(h, alloc((void**)&p.missQueue, 4 * n));
+        CUDA_OK(h, alloc((void**)&p.queueCount, 4 * TB_QUEUE_COUNT_WORDS));
+        CUDA_OK(h, alloc((void**)&p.hitQueue, 4 * n)); CUDA_OK(h, alloc((void**)&p.hitSorted, 4 * n)); CUDA_OK(h, alloc((void**)&p.missQueue, 4 * n));
         CUDA_OK(h, alloc((void**)&p.sortKeys, 4 * n)); CUDA_OK(h, alloc((void**)&p.sortTmp, 4 * n)); CUDA_OK(h, alloc((void**)&p.sortHist, 4 * (TB_SORT_CELLS + 1)));
         CUDA_OK(h, alloc((void**)&p.shadowQueue, 4 * n)); CUDA_OK(h, alloc((void**)&p.shRayO, 16 * n)); CUDA_OK(h, alloc((void**)&p.shRayD, 16 * n));
         CUDA_OK(h, alloc((void**)&p.shHit, 16 * n)); CUDA_OK(h, alloc((void**)&p.shHitGeom, 4 * n));
@@ -801,6 +813,23 @@ TB_API int tb_postprocess_image(TbHandle* h, const float* inRGBA, const float* a
 }
 
 // host-only: no device needed
+TB_API int tb_load_image_file(const char* path, uint32_t* width, uint32_t* height, uint32_t* format, int* hasAlpha, void* pixels,
+                              uint64_t capBytes, char* err, size_t errCap) {
+    auto bad = [&](int code, const std::string& m) { if (err && errCap) { strncpy(err, m.c_str(), errCap - 1); err[errCap - 1] = 0; } return code; };
+    if (!path || !width || !height || !format) return bad(TB_ERR_INVALID_ARG, "null argument");
+    tb::Image img;
+    std::string e;
+    bool alpha = false;
+    if (!tb::load_image_file(path, img, &alpha, e)) return bad(e.find("unsupported texture format") != std::string::npos ? TB_ERR_NOT_IMPL : TB_ERR_IO, e);
+    *width = img.width; *height = img.height; *format = img.format;
+    if (hasAlpha) *hasAlpha = alpha ? 1 : 0;
+    if (pixels) {
+        if (capBytes < img.data.size()) return bad(TB_ERR_INVALID_ARG, "destination too small");
+        memcpy(pixels, img.data.data(), img.data.size());
+    }
+    return TB_OK;
+}
+
 TB_API int tb_write_image(const char* path, const void* pixels, uint32_t width, uint32_t height, uint32_t channels,
                           uint32_t bytesPerChannel, char* err, size_t errCap) {
     auto bad = [&](int code, const std::string& m) { if (err && errCap) { strncpy(err, m.c_str(), errCap - 1); err[errCap - 1] = 0; } return code; };
@@ -918,6 +947,11 @@ TB_API int tb_set_ray_sort(TbHandle* h, int mode) {
     h->options.sortRays = mode == 4 ? 2 : mode;
     return TB_OK;
 }
+TB_API int tb_set_material_sort(TbHandle* h, int mode) {
+    if (!h || mode < 0 || mode > 2) return fail(h, TB_ERR_INVALID_ARG, "material sort must be 0 (off), 1 (on) or 2 (auto)");
+    h->options.materialSort = mode;
+    return TB_OK;
+}
 TB_API int tb_set_profiling(TbHandle* h, int enable) {
     if (!h) return TB_ERR_INVALID_ARG;
     if (enable < 0 || enable > 2) return fail(h, TB_ERR_INVALID_ARG, "profiling mode must be 0, 1 or 2");
@@ -946,6 +980,7 @@ TB_API int tb_set_material(TbHandle* h, int id, const TbMaterial* m) {
     if (!tb::validate_material(h->scene, *m, why)) return fail(h, TB_ERR_INVALID_ARG, why); // the kernels index textures / mixed materials unchecked
     h->scene.materials[id] = *m;
     h->options.sceneHasSSS = scene_has_sss(h->scene); // also through mix materials that reference the edited one
+    h->options.sceneMaterialClasses = scene_material_classes(h->scene);
     CUDA_OK(h, cudaSetDevice(h->device));
     CUDA_OK(h, cudaMemcpyAsync((void*)(h->dscene.materials + id), m, sizeof(*m), cudaMemcpyHostToDevice, h->stream));
     CUDA_OK(h, cudaStreamSynchronize(h->stream));

@@ -38,16 +38,16 @@ struct Importer {
     }
 
     uint32_t load_image(const std::string& fileName, bool* hasAlpha) {
-        // InitializeTexture, TracerBoy.cpp:2186-2246. Only Radiance .hdr (and the .pfm ->
-        // .hdr rename) is implemented; other formats went through DirectXTex/WIC.
+        // InitializeTexture, TracerBoy.cpp:2186-2246: .pfm is renamed to .hdr; .hdr / .tga have their own loaders,
+        // everything else goes through WIC (PNG here; image_decode.cpp follows the loaders' format rules)
         std::string full = dir + fileName;
         std::string ext = full.size() >= 4 ? full.substr(full.size() - 4) : "";
-        if (ext == ".pfm") { full = full.substr(0, full.size() - 4) + ".hdr"; ext = ".hdr"; }
-        if (ext != ".hdr") throw std::runtime_error("unsupported texture format (only .hdr): " + fileName);
+        if (ext == ".pfm") full = full.substr(0, full.size() - 4) + ".hdr";
         Image img;
         std::string err;
-        if (!load_hdr(full, img, err)) throw std::runtime_error(err);
-        if (hasAlpha) *hasAlpha = false;
+        bool alpha = false;
+        if (!load_image_file(full, img, &alpha, err)) throw std::runtime_error(err);
+        if (hasAlpha) *hasAlpha = alpha;
         out.images.push_back(std::move(img));
         return (uint32_t)out.images.size() - 1;
     }
@@ -63,7 +63,12 @@ struct Importer {
         if (img) {
             t.TextureType = TB_IMAGE_TEXTURE_TYPE;
             t.DescriptorHeapIndex = load_image(img->fileName, hasAlpha);
-            t.TextureFlags = 0; // float formats are not "normalized" => no gamma flag (:205-209)
+            // NEEDS_GAMMA_CORRECTION only for "normalized" formats (IsNormalizedFormat, :128-160, :205-209): the 8-bit
+            // ones, sRGB included (the sampler's own sRGB decode and the shader's pow 2.2 then both apply, as in the
+            // reference), and R16G16B16A16_UNORM (16-bit PNG, stored as float here); never the float .hdr
+            t.TextureFlags = 0;
+            const Image& loaded = out.images[t.DescriptorHeapIndex];
+            if (gammaCorrect && (loaded.format != 0 || loaded.unorm16)) t.TextureFlags |= TB_NEEDS_GAMMA_CORRECTION_TEXTURE_FLAG;
         } else if (chk) {
             t.TextureType = TB_CHECKER_TEXTURE_TYPE;
             t.UScale = chk->uScale;
@@ -311,6 +316,9 @@ struct Importer {
             auto inf = std::dynamic_pointer_cast<pbrt::InfiniteLightSource>(ls);
             auto dist = std::dynamic_pointer_cast<pbrt::DistantLightSource>(ls);
             if (inf) {
+                // the reference takes the last four characters of the map name unconditionally (TracerBoy.cpp:1903-1904,
+                // 2200): an infinite light without a map is an out_of_range exception there, an error here
+                if (inf->mapName.size() < 4) throw std::runtime_error("infinite light source without a \"mapname\" is not supported (TracerBoy.cpp:1903)");
                 out.envImage = (int32_t)load_image(inf->mapName, nullptr);
                 auto& l = inf->transform.l;
                 out.envTransform[0] = {l.vx.x, l.vx.y, l.vx.z, 0};

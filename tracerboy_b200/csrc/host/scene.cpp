@@ -195,7 +195,7 @@ bool validate_scene(const Scene& s, std::string& err) {
     if (s.envImage < -1 || s.envImage >= (int64_t)s.images.size()) { err = "environment image index out of range"; return false; }
     for (const auto& im : s.images) {
         const uint64_t bpp = im.format == 0 ? 16 : 4;
-        if (im.format > 1 || im.width == 0 || im.height == 0 || (uint64_t)im.width * im.height * bpp != im.data.size()) {
+        if (im.format > 2 || im.width == 0 || im.height == 0 || (uint64_t)im.width * im.height * bpp != im.data.size()) {
             err = "image size does not match its pixel data"; return false;
         }
     }

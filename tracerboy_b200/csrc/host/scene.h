@@ -11,7 +11,8 @@ namespace tb {
 
 struct Image {
     uint32_t width = 0, height = 0;
-    uint32_t format = 0; // 0 = float4, 1 = unorm8 x4
+    uint32_t format = 0; // 0 = float4, 1 = unorm8 x4, 2 = unorm8 x4 sRGB (R8G8B8A8_UNORM_SRGB: the sampler linearises every texel before filtering)
+    bool unorm16 = false; // import-time only: a float4 image that came from a 16-bit UNORM file ("normalized" for the gamma flag)
     std::vector<uint8_t> data;
 };
 
@@ -47,6 +48,8 @@ bool validate_material(const Scene& s, const TbMaterial& m, std::string& err);
 
 // Radiance .hdr (RGBE) -> float4 image, as DirectXTex LoadFromHDRFile gives the reference.
 bool load_hdr(const std::string& path, Image& img, std::string& err);
+// Any supported texture file by extension: .hdr, .png, .tga (image_decode.cpp; the formats follow DirectXTex's loaders).
+bool load_image_file(const std::string& path, Image& img, bool* hasAlpha, std::string& err);
 
 // Built-in procedural scenes: "synthetic:<name>?key=value&..." (SURVEY §8d C5 and the
 // dragon / vw-van stand-ins). Integer-only generator, no libm, deterministic.
