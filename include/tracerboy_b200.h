@@ -542,6 +542,14 @@ TB_API int tb_bvh_build_device(TbHandle* h, const TbGeometryDesc* geoms, uint32_
  * `cudaStream` and NOT synchronised: it orders with the caller's other work on that stream like a dispatch. */
 TB_API int tb_trace_rays_device(TbHandle* h, const void* as, uint64_t asBytes, const TbRay* dRays, uint64_t n, TbHit* dHits,
                                 void* cudaStream);
+/* BuildRaytracingAccelerationStructure with PERFORM_UPDATE (GpuBVH2Builder.cpp:165-234; SURVEY 8f rank 4: animated
+ * geometry): `dst` is an acceleration structure built by tb_bvh_build_device, `geoms` describes the same geometries
+ * (same triangle counts, same index topology) with moved vertices. The hierarchy is kept, the triangles are reloaded
+ * into their sorted slots and every box is refitted bottom-up, in place; scratch is UpdateScratchDataSizeInBytes of
+ * tb_bvh_prebuild_info (NULL: library-owned for the call). No ALLOW_UPDATE flag is needed at build time: the slot of a
+ * triangle is recovered from the structure's own metadata instead of the reference's sort cache. */
+TB_API int tb_bvh_update_device(TbHandle* h, const TbGeometryDesc* geoms, uint32_t n, void* dst, uint64_t dstBytes,
+                                void* scratch, uint64_t scratchBytes, void* cudaStream);
 /* Drop the handle's cached description of a caller-owned acceleration structure (call before freeing / reusing dst). */
 TB_API int tb_bvh_forget_device(TbHandle* h, const void* as);
 /* Height of the scene's BVH (0 = a single leaf). The traversal keeps at most one waiting node per level; a tree deeper

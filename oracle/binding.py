@@ -245,6 +245,19 @@ class Oracle:
         self._ck(self.lib.oracle_get_bvh(self.h, buf.ctypes.data, n))
         return buf
 
+    def ScenePositions(self):
+        """The scene's pooled vertex positions [V, 3] (a copy)."""
+        self.lib.oracle_scene_positions.restype = C.c_void_p
+        self.lib.oracle_scene_num_positions.restype = C.c_uint64
+        n = self.lib.oracle_scene_num_positions(self.h)
+        p = self.lib.oracle_scene_positions(self.h)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n, 3)).copy()
+
+    def UpdateBVH(self, positions):
+        """PERFORM_UPDATE: new vertex positions (same count), hierarchy kept, boxes refitted."""
+        positions = np.ascontiguousarray(positions, np.float32)
+        self._ck(self.lib.oracle_update_bvh(self.h, positions.ctypes.data_as(C.c_void_p), C.c_uint64(positions.shape[0])))
+
     def MaxTreeletClimb(self):
         return self.lib.oracle_max_treelet_climb(self.h)
 

@@ -446,4 +446,58 @@ bool build_bvh(Scene& s, int treeletPasses, std::string& err) {
     return true;
 }
 
+// BuildRaytracingAccelerationStructure with PERFORM_UPDATE (GpuBVH2Builder.cpp:165-234): the hierarchy is kept, the
+// primitives are reloaded straight into their sorted slots and ComputeAABBs refits every box bottom-up reading the
+// child indices from the node flags (ComputeAABBs.hlsli:39-67: GetLeftNodeIndex / GetRightNodeIndex of the stored node).
+// The reference finds a primitive's slot through the sort cache it wrote at build time; the slot's own metadata
+// (geometry, primitive index) names the same triangle, which is what is used here. `s.positions` holds the moved vertices.
+bool update_bvh(Scene& s, std::string& err) {
+    const uint32_t n = s.numPrims;
+    if (n == 0 || s.bvh.empty()) { err = "no acceleration structure to update"; return false; }
+    const uint32_t nInternal = n - 1, total = 2 * n - 1;
+    const uint32_t* header = (const uint32_t*)s.bvh.data();
+    AABBNode* nodes = (AABBNode*)(s.bvh.data() + header[0]);
+    Prim* sp = (Prim*)(s.bvh.data() + header[1]);
+    const Meta* sm = (const Meta*)(s.bvh.data() + header[2]);
+    for (uint32_t i = 0; i < n; i++) {
+        const TbGeometryRecord& G = s.geoms[sm[i].geom];
+        Prim p;
+        p.type = 1;
+        for (int k = 0; k < 3; k++) {
+            const TbFloat3& v = s.positions[G.VertexFirst + s.indices[G.IndexFirst + 3 * sm[i].prim + k]];
+            p.v[3 * k] = v.x; p.v[3 * k + 1] = v.y; p.v[3 * k + 2] = v.z;
+        }
+        sp[i] = p;
+        f3 c, h;
+        leaf_box(p, c, h);
+        AABBNode& nd = nodes[nInternal + i];
+        nd.c[0] = c.x; nd.c[1] = c.y; nd.c[2] = c.z;
+        nd.h[0] = h.x; nd.h[1] = h.y; nd.h[2] = h.z;
+    }
+    if (n > 1) { // post-order over the stored topology; flags and child order stay as built
+        std::vector<std::pair<uint32_t, int>> st;
+        st.push_back({0, 0});
+        while (!st.empty()) {
+            auto& top = st.back();
+            const uint32_t node = top.first;
+            if (node >= nInternal) { st.pop_back(); continue; }
+            const uint32_t l = nodes[node].flags & 0x3fffffffu, r = nodes[node].right;
+            if (top.second == 0) { top.second = 1; st.push_back({l, 0}); }
+            else if (top.second == 1) { top.second = 2; st.push_back({r, 0}); }
+            else {
+                const AABBNode& A = nodes[l];
+                const AABBNode& B = nodes[r];
+                f3 c, h;
+                parent_box(mk3(A.c[0], A.c[1], A.c[2]), mk3(A.h[0], A.h[1], A.h[2]), mk3(B.c[0], B.c[1], B.c[2]), mk3(B.h[0], B.h[1], B.h[2]), c, h);
+                AABBNode& nd = nodes[node];
+                nd.c[0] = c.x; nd.c[1] = c.y; nd.c[2] = c.z;
+                nd.h[0] = h.x; nd.h[1] = h.y; nd.h[2] = h.z;
+                st.pop_back();
+            }
+        }
+    }
+    (void)total;
+    return true;
+}
+
 } // namespace oracle

@@ -148,6 +148,13 @@ ORACLE_API void oracle_karras(const uint32_t* codes, uint32_t n, uint32_t* out3)
 ORACLE_API void oracle_treelet(uint32_t* H3, float* aabb6, uint32_t n, uint32_t root) { oracle::treelet_public(H3, aabb6, n, root); }
 ORACLE_API void oracle_load_primitives(OracleHandle* h, void* prims40, void* meta12) { oracle::load_primitives_public(h->scene, prims40, meta12); }
 ORACLE_API const void* oracle_scene_positions(OracleHandle* h) { return h->scene.positions.data(); }
+ORACLE_API uint64_t oracle_scene_num_positions(OracleHandle* h) { return h->scene.positions.size(); }
+// PERFORM_UPDATE: replace the scene's vertex positions (same count) and refit the acceleration structure
+ORACLE_API int oracle_update_bvh(OracleHandle* h, const float* positions, uint64_t count) {
+    if (!positions || count != h->scene.positions.size()) { h->err = "position count differs from the scene's"; return -1; }
+    memcpy(h->scene.positions.data(), positions, sizeof(TbFloat3) * count);
+    return oracle::update_bvh(h->scene, h->err) ? 0 : -1;
+}
 ORACLE_API void oracle_scene_box(const void* prims40, uint32_t n, float* out6) { oracle::scene_box_public(prims40, n, out6); }
 ORACLE_API void oracle_centroid(const void* prim40, float* out3) { oracle::centroid_public(prim40, out3); }
 ORACLE_API int oracle_sorts_before(uint32_t codeA, uint32_t indexA, uint32_t codeB, uint32_t indexB) { return oracle::sorts_before_public(codeA, indexA, codeB, indexB); }

@@ -72,6 +72,9 @@ bool load_tbscene(Scene& s, const std::string& path, std::string& err);
 
 // BVH build (GpuBVH2Builder.cpp:167-356). passes: 3 = PREFER_FAST_TRACE, 1 = default, 0 = FAST_BUILD.
 bool build_bvh(Scene& s, int treeletPasses, std::string& err);
+// PERFORM_UPDATE (GpuBVH2Builder.cpp:165-234, ComputeAABBs.hlsli:39-67): same hierarchy, primitives reloaded from the
+// (moved) s.positions, every box refitted bottom-up.
+bool update_bvh(Scene& s, std::string& err);
 
 // SoftwareRayQuery::TraceRayInline + Proceed (TraverseFunction.hlsli:537-785), FAST_PATH.
 void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit);

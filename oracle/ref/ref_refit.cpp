@@ -81,3 +81,19 @@ int ref_refit(uint8_t* bvh, const uint32_t* H3, uint32_t n, int descending) {
     for (uint32_t k = 0; k < n; k++) compute_main(uint3(descending ? n - 1 - k : k, 0, 0));
     return 0;
 }
+
+// The same kernel with PERFORM_UPDATE (GpuBVH2Builder.cpp:165-234): bvh is a finished acceleration structure whose
+// sorted primitives have been replaced by the moved ones; child indices come from the stored node flags and parents
+// from `parents` (the aabbParentBuffer a PREPARE_UPDATE build leaves behind: parents[child] = node).
+extern "C" __attribute__((visibility("default")))
+int ref_refit_update(uint8_t* bvh, const uint32_t* parents, uint32_t n, int descending) {
+    using namespace refcore;
+    std::vector<uint32_t> scratch(n), counters(n ? n : 1);
+    std::vector<uint32_t> par(parents, parents + (2 * (size_t)n - 1));
+    outputBVH.bytes = bvh; scratchMemory.bytes = (uint8_t*)scratch.data(); childNodesProcessedCounter.bytes = (uint8_t*)counters.data();
+    hierarchyBuffer = nullptr; aabbParentBuffer = par.data();
+    Constants.NumberOfElements = n; Constants.UpdateFlags = PERFORM_UPDATE_FLAG;
+    for (uint32_t t = 0; t < n; t++) prepare_main(uint3(t, 0, 0));
+    for (uint32_t k = 0; k < n; k++) compute_main(uint3(descending ? n - 1 - k : k, 0, 0));
+    return 0;
+}

@@ -1253,3 +1253,78 @@ def test_primitive_load_equals_reference_text(tmp_path, built):
     # 3) E_INVALIDARG: an index format without an index buffer (LoadPrimitivesPass.cpp:77-80)
     bad = (Desc * 1)(Desc(verts.ctypes.data, 16, 50, None, 4, 21, None, 0))
     assert ref.ref_load_primitives(bad, 1, p.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p)) == -1
+
+
+@pytest.mark.parametrize("spec,passes", [("cornell", 3), ("synthetic:blobs?copies=8&tris=1000&seed=7", 3), ("synthetic:showcase?tris=300&seed=2", 1)])
+def test_bvh_update_equals_reference_text(spec, passes, tmp_path, built):
+    """BuildRaytracingAccelerationStructure with PERFORM_UPDATE (GpuBVH2Builder.cpp:165-234): the hierarchy
+    is kept, the moved primitives go straight into their sorted slots, ComputeAABBs refits every box bottom-up reading the
+    children from the stored node flags and the parents from the aabbParentBuffer (ComputeAABBs.hlsli:39-67). The oracle's
+    update_bvh against that kernel compiled from the mount with PERFORM_UPDATE set, under both sequential schedules:
+    header, metadata and leaf encoding untouched, the sorted primitives are the moved triangles, every box bit-identical;
+    child order identical wherever the subtree sizes differ (equal sizes: the reference's arrival-order rule, D1).
+    An update with unmoved vertices reproduces the built structure byte for byte."""
+    import ctypes as C
+    import tracerboy_b200 as tb
+    from oracle import binding
+    path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_refit.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_refit.so not built (needs the reference mount at build time)")
+    ref = C.CDLL(path)
+    if not hasattr(ref, "ref_refit_update"):
+        pytest.skip("oracle/_ref/libref_refit.so predates the update entry point")
+    ref.ref_refit_update.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
+    if spec in NAMED:
+        scene = scene_path(NAMED[spec])
+    else:
+        scene = str(tmp_path / "s.tbscene")
+        tb.convert_scene(spec, scene)
+    o = binding.Oracle(); o.LoadScene(scene, passes)
+    built_bytes = np.ascontiguousarray(o.GetBVH())
+    n = (built_bytes.size + 16) // 116
+    total, nint = 2 * n - 1, n - 1
+    off_prims, off_meta = 16 + 32 * total, 16 + 32 * total + 40 * n
+    pos = o.ScenePositions()
+    o.UpdateBVH(pos)
+    assert np.array_equal(o.GetBVH(), built_bytes), "an update with unmoved vertices must reproduce the build"
+    rng = np.random.default_rng(5)
+    moved = (pos + rng.normal(0, 0.05, pos.shape) * (np.abs(pos).max() * 0.02 + 0.01)).astype(np.float32)
+    o.UpdateBVH(moved)
+    U = np.ascontiguousarray(o.GetBVH())
+    assert np.array_equal(U[:16], built_bytes[:16]) and np.array_equal(U[off_meta:], built_bytes[off_meta:])
+    # the sorted primitives are the moved triangles named by each slot's metadata
+    P, M = np.empty((n, 10), np.uint32), np.empty((n, 3), np.uint32)
+    lib = binding.load()
+    lib.oracle_load_primitives(o.h, P.ctypes.data_as(C.c_void_p), M.ctypes.data_as(C.c_void_p))   # moved scene, geometry order
+    meta_sorted = U[off_meta:].view(np.uint32).reshape(n, 3)
+    key = {(int(g), int(p)): i for i, (g, p, _) in enumerate(M)}
+    src = np.array([key[(int(g), int(p))] for g, p, _ in meta_sorted])
+    assert np.array_equal(U[off_prims:off_meta].view(np.uint32).reshape(n, 10), P[src])
+    nodes_b = built_bytes[16:off_prims].view(np.uint32).reshape(total, 8)
+    nodes_u = U[16:off_prims].view(np.uint32).reshape(total, 8)
+    assert np.array_equal(nodes_u[:, [3, 7]], nodes_b[:, [3, 7]]), "the oracle's update keeps every child reference"
+    assert not np.array_equal(nodes_u, nodes_b)
+    # parents (what a PREPARE_UPDATE build records) and subtree sizes from the stored topology
+    parents = np.zeros(total, np.uint32)
+    left, right = (nodes_b[:nint, 3] & 0x3fffffff).astype(np.int64), nodes_b[:nint, 7].astype(np.int64)
+    parents[left] = np.arange(nint); parents[right] = np.arange(nint)
+    count = np.zeros(total, np.int64); count[nint:] = 1
+    stack, order = [0], []
+    while stack:
+        i = stack.pop()
+        if i < nint:
+            order.append(i); stack.append(int(left[i])); stack.append(int(right[i]))
+    for i in reversed(order):
+        count[i] = count[left[i]] + count[right[i]]
+    tie = count[left] == count[right]
+    for descending in (0, 1):
+        R = built_bytes.copy()
+        R[off_prims:off_meta] = U[off_prims:off_meta]      # LoadBVHElements wrote the moved primitives straight to the output
+        assert ref.ref_refit_update(R.ctypes.data_as(C.c_void_p), parents.ctypes.data_as(C.c_void_p), n, descending) == 0
+        assert np.array_equal(R[:16], U[:16]) and np.array_equal(R[off_prims:], U[off_prims:])
+        nodes_r = R[16:off_prims].view(np.uint32).reshape(total, 8)
+        assert np.array_equal(nodes_r[nint:], nodes_u[nint:]), "leaf nodes"
+        assert np.array_equal(nodes_r[:nint][:, [0, 1, 2, 4, 5, 6]], nodes_u[:nint][:, [0, 1, 2, 4, 5, 6]]), "internal boxes"
+        lr, rr = (nodes_r[:nint, 3] & 0x3fffffff).astype(np.int64), nodes_r[:nint, 7].astype(np.int64)
+        assert np.array_equal(lr[~tie], left[~tie]) and np.array_equal(rr[~tie], right[~tie]), "child order where sizes differ"
+        assert np.array_equal(np.minimum(lr, rr), np.minimum(left, right)) and np.array_equal(np.maximum(lr, rr), np.maximum(left, right))

@@ -163,3 +163,74 @@ def test_set_material_rejects_dangling_indices(cornell):
         g.SetMaterial(0, m)
     g.Resize(16, 16)
     g.Render(tb.get_default_output_settings(), 1, 0.0)  # the device scene is still the valid one
+
+
+def test_update_in_place_equals_the_oracles_update(tmp_path, built):
+    """PERFORM_UPDATE (GpuBVH2Builder.cpp:165-234): a caller-owned acceleration structure refitted to
+    moved vertices, in place, on caller scratch. Bytes of the reference layout and ray queries equal the oracle's
+    update (which is pinned against ComputeAABBs.hlsli compiled from the mount with PERFORM_UPDATE); an update with
+    unmoved vertices reproduces the build; a different triangle count is E_INVALIDARG."""
+    import torch
+    import tracerboy_b200 as tb
+    from oracle.binding import Oracle
+    from tracerboy_b200.api import RAY_DTYPE, HIT_DTYPE
+    rng = np.random.default_rng(17)
+    # a wavy grid: coherent geometry, so that the refitted tree is still a sensible one
+    nx = 70
+    gx, gy = np.meshgrid(np.linspace(-1, 1, nx), np.linspace(-1, 1, nx), indexing="ij")
+    pos = np.stack([gx, gy, 0.2 * np.sin(4 * gx) * np.cos(3 * gy)], -1).reshape(-1, 3).astype(np.float32)
+    idx = np.arange(nx * nx).reshape(nx, nx)
+    quads = np.stack([idx[:-1, :-1], idx[1:, :-1], idx[1:, 1:], idx[:-1, :-1], idx[1:, 1:], idx[:-1, 1:]], -1).reshape(-1, 3).astype(np.uint32)
+    # the oracle's view of the same geometry: through the host-pointer build + .tbscene
+    h = tb.TracerBoy(0)
+    h.BuildRaytracingAccelerationStructure([(pos, quads)])
+    path = str(tmp_path / "grid.tbscene")
+    h.SaveScene(path)
+    o = Oracle(); o.LoadScene(path, 3)
+    keep = []
+    d = _descs([dict(pos=pos, idx=quads)], keep)
+    info = tb.prebuild_info(d, 1)
+    assert info.UpdateScratchDataSizeInBytes > 4 * 3 * quads.shape[0]
+    dst = torch.zeros(info.ResultDataMaxSizeInBytes, dtype=torch.uint8, device="cuda")
+    scratch = torch.empty(max(info.ScratchDataSizeInBytes, info.UpdateScratchDataSizeInBytes), dtype=torch.uint8, device="cuda")
+    g = tb.TracerBoy(0)
+    g.BuildRaytracingAccelerationStructureDevice(d, 1, dst.data_ptr(), dst.numel(), scratch.data_ptr(), scratch.numel(), None)
+    nref = info.ReferenceLayoutSizeInBytes
+    built_bytes = dst[:nref].cpu().numpy()
+    assert np.array_equal(built_bytes, o.GetBVH())
+    # unmoved: identical bytes
+    g.UpdateRaytracingAccelerationStructureDevice(d, 1, dst.data_ptr(), dst.numel(), scratch.data_ptr(), scratch.numel(), None)
+    assert np.array_equal(dst[:nref].cpu().numpy(), built_bytes)
+    # moved vertices (the caller overwrites its own vertex buffer, as an animation would)
+    moved = pos.copy()
+    moved[:, 2] = 0.2 * np.sin(4 * gx.reshape(-1) + 0.7) * np.cos(3 * gy.reshape(-1) - 0.4) + rng.normal(0, 0.01, pos.shape[0]).astype(np.float32)
+    keep[0].copy_(torch.from_numpy(moved))
+    g.UpdateRaytracingAccelerationStructureDevice(d, 1, dst.data_ptr(), dst.numel(), None, 0, None)   # library-owned scratch
+    o.UpdateBVH(moved)
+    want = o.GetBVH()
+    got = dst[:nref].cpu().numpy()
+    diff = np.flatnonzero(got != want)
+    assert diff.size == 0, "updated BVH differs at %d bytes, first at %d" % (diff.size, diff[0])
+    assert not np.array_equal(got, built_bytes)
+    rays = np.zeros(40000, RAY_DTYPE)
+    rays["Origin"] = rng.uniform(-1, 1, (40000, 3)) * [1.2, 1.2, 0.2] + [0, 0, 1.5]
+    rays["Direction"] = rng.normal(0, 0.3, (40000, 3)) + [0, 0, -1]
+    rays["TMin"] = 0.001; rays["TMax"] = 999999.0
+    d_rays = torch.from_numpy(rays.view(np.uint8)).cuda()
+    d_hits = torch.zeros(40000 * 32, dtype=torch.uint8, device="cuda")
+    g.TraceRaysDevice(dst.data_ptr(), dst.numel(), d_rays.data_ptr(), 40000, d_hits.data_ptr(), None)
+    g.Synchronize()
+    hg, ho = d_hits.cpu().numpy().view(HIT_DTYPE), o.TraceRays(rays)
+    for f in hg.dtype.names:
+        assert np.array_equal(hg[f].view(np.uint32), ho[f].view(np.uint32)), f
+    assert (hg["t"] > 0).mean() > 0.5
+    # every hit lies on the MOVED surface
+    hit = hg["t"] > 0
+    p = rays["Origin"][hit] + rays["Direction"][hit] * hg["t"][hit][:, None]
+    tri = moved[quads[hg["PrimitiveIndex"][hit]]]
+    nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    dist = np.abs(((p - tri[:, 0]) * nrm).sum(1)) / np.maximum(np.linalg.norm(nrm, axis=1), 1e-12)
+    assert dist.max() < 1e-4
+    with pytest.raises(tb.TracerBoyError):
+        d2 = _descs([dict(pos=pos, idx=quads[:-5])], keep)
+        g.UpdateRaytracingAccelerationStructureDevice(d2, 1, dst.data_ptr(), dst.numel(), None, 0, None)

@@ -192,6 +192,7 @@ def load_library():
         "tb_bvh_build": [vp, C.POINTER(GeometryDesc), u32, u32], "tb_trace_rays": [vp, vp, u64, vp],
         "tb_bvh_build_device": [vp, C.POINTER(GeometryDesc), u32, u32, vp, u64, vp, u64, vp],
         "tb_trace_rays_device": [vp, vp, u64, vp, u64, vp, vp], "tb_bvh_forget_device": [vp, vp],
+        "tb_bvh_update_device": [vp, C.POINTER(GeometryDesc), u32, vp, u64, vp, u64, vp],
         "tb_get_bvh_depth": [vp, C.POINTER(u32)],
         "tb_comm_get_unique_id": [vp, u64], "tb_comm_init": [vp, vp, i32, i32, u32], "tb_comm_destroy": [vp],
         "tb_comm_info": [vp, C.POINTER(CommInfo)], "tb_comm_reduce": [vp],
@@ -220,7 +221,7 @@ EXPORTED_SYMBOLS = ["tb_create", "tb_destroy", "tb_last_error", "tb_version", "t
                     "tb_get_material", "tb_set_material", "tb_bvh_prebuild_info", "tb_bvh_build", "tb_trace_rays",
                     "tb_get_default_postprocess_settings", "tb_postprocess", "tb_postprocess_image",
                     "tb_temporal_accumulate_image", "tb_save_image", "tb_write_image", "tb_update", "tb_camera_update", "tb_set_ray_sort",
-                    "tb_set_material_sort", "tb_load_image_file", "tb_max_triangles", "tb_bvh_build_device", "tb_trace_rays_device", "tb_bvh_forget_device", "tb_get_bvh_depth",
+                    "tb_set_material_sort", "tb_load_image_file", "tb_max_triangles", "tb_bvh_build_device", "tb_trace_rays_device", "tb_bvh_forget_device", "tb_bvh_update_device", "tb_get_bvh_depth",
                     "tb_comm_get_unique_id", "tb_comm_init", "tb_comm_destroy", "tb_comm_info", "tb_comm_reduce"]
 
 
@@ -415,6 +416,10 @@ class TracerBoy:
         """BuildRaytracingAccelerationStructure with caller-allocated dest + scratch device memory; `descs` is a
         (GeometryDesc * n) array whose pointers are DEVICE pointers (D3D12RaytracingFallback.h:83-84)."""
         self._ck(self._lib.tb_bvh_build_device(self._h, descs, n, flags, dst, dst_bytes, scratch, scratch_bytes, stream))
+
+    def UpdateRaytracingAccelerationStructureDevice(self, descs, n, dst, dst_bytes, scratch=None, scratch_bytes=0, stream=None):
+        """PERFORM_UPDATE: refit a caller-owned acceleration structure to moved vertices (same topology), in place."""
+        self._ck(self._lib.tb_bvh_update_device(self._h, descs, n, dst, dst_bytes, scratch, scratch_bytes, stream))
 
     def TraceRaysDevice(self, accel, accel_bytes, d_rays, n, d_hits, stream=None):
         """n ray queries against a caller-owned acceleration structure (None: the handle's scene); device pointers,

@@ -50,6 +50,26 @@ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
 // BottomLevelLoadTriangles.hlsli:14-126 in its three index-format variants (none / 16 bit / 32 bit), with the optional
 // 3x4 transform (TransformVertex :83-86: mul(float3x4, float4(v, 1)), one dot product per row, left to right) and a
 // vertex stride, straight from the caller's device buffers (D3D12_RAYTRACING_GEOMETRY_TRIANGLES_DESC).
+__device__ __forceinline__ void load_triangle(const BuildGeometry& G, uint32_t t, Prim& p) {
+    p.type = 1;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        uint32_t vi = 3 * t + k;
+        if (G.indexFormat == 4) vi = ((const uint32_t*)G.indices)[vi];
+        else if (G.indexFormat == 2) vi = ((const uint16_t*)G.indices)[vi];
+        const float* pv = (const float*)(G.positions + (size_t)vi * G.strideBytes);
+        float x = pv[0], y = pv[1], z = pv[2];
+        if (G.transform) {
+            const float* m = G.transform;
+            float tx = ((m[0] * x + m[1] * y) + m[2] * z) + m[3];
+            float ty = ((m[4] * x + m[5] * y) + m[6] * z) + m[7];
+            float tz = ((m[8] * x + m[9] * y) + m[10] * z) + m[11];
+            x = tx; y = ty; z = tz;
+        }
+        p.v[3 * k] = x; p.v[3 * k + 1] = y; p.v[3 * k + 2] = z;
+    }
+}
+
 __global__ void k_load_prims(const BuildGeometry* __restrict__ geoms, const uint32_t* __restrict__ triPrefix,
                              uint32_t numGeoms, uint32_t n, Prim* __restrict__ prims,
                              Meta* __restrict__ meta, uint32_t* __restrict__ sceneBox /*6 ordered uints*/) {
@@ -62,24 +82,11 @@ __global__ void k_load_prims(const BuildGeometry* __restrict__ geoms, const uint
         const BuildGeometry G = geoms[lo];
         uint32_t t = i - triPrefix[lo];
         Prim p;
-        p.type = 1;
+        load_triangle(G, t, p);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            uint32_t vi = 3 * t + k;
-            if (G.indexFormat == 4) vi = ((const uint32_t*)G.indices)[vi];
-            else if (G.indexFormat == 2) vi = ((const uint16_t*)G.indices)[vi];
-            const float* pv = (const float*)(G.positions + (size_t)vi * G.strideBytes);
-            float x = pv[0], y = pv[1], z = pv[2];
-            if (G.transform) {
-                const float* m = G.transform;
-                float tx = ((m[0] * x + m[1] * y) + m[2] * z) + m[3];
-                float ty = ((m[4] * x + m[5] * y) + m[6] * z) + m[7];
-                float tz = ((m[8] * x + m[9] * y) + m[10] * z) + m[11];
-                x = tx; y = ty; z = tz;
-            }
-            p.v[3 * k] = x; p.v[3 * k + 1] = y; p.v[3 * k + 2] = z;
-            mn = min3(mn, mk3(x, y, z));
-            mx = max3(mx, mk3(x, y, z));
+            mn = min3(mn, mk3(p.v[3 * k], p.v[3 * k + 1], p.v[3 * k + 2]));
+            mx = max3(mx, mk3(p.v[3 * k], p.v[3 * k + 1], p.v[3 * k + 2]));
         }
         uint32_t* dst = (uint32_t*)(prims + i);
         const uint32_t* src = (const uint32_t*)&p;
@@ -680,6 +687,69 @@ __global__ void k_refit(uint32_t n, const HNode* H, uint8_t* bvh, unsigned long 
     }
 }
 
+// -------------------------------------------------------------------- update
+// BuildRaytracingAccelerationStructure with PERFORM_UPDATE (GpuBVH2Builder.cpp:165-234): the hierarchy stays, the moved
+// triangles go straight into their sorted slots and every box is refitted bottom-up (ComputeAABBs.hlsli:39-67 reads the
+// children from the stored node flags and the parents from the aabbParentBuffer). The reference finds a triangle's slot
+// through a sort cache written at build time; a slot's own metadata (geometry, primitive index) names the same triangle,
+// so no cache is kept: one thread per SLOT reloads its triangle. Parents are derived from the stored child indices.
+__global__ void k_update_prims(const BuildGeometry* __restrict__ geoms, uint32_t n, uint8_t* bvh) {
+    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n) return;
+    const size_t offPrims = 16 + 32 * (2 * (size_t)n - 1);
+    Prim* prims = (Prim*)(bvh + offPrims);
+    const Meta m = ((const Meta*)(bvh + offPrims + 40 * (size_t)n))[slot];
+    Prim p;
+    load_triangle(geoms[m.geom], m.prim, p);
+    uint32_t* dst = (uint32_t*)(prims + slot);
+    const uint32_t* src = (const uint32_t*)&p;
+#pragma unroll
+    for (int k = 0; k < 10; k++) dst[k] = src[k];
+}
+__global__ void k_update_parents(uint32_t n, const uint8_t* __restrict__ bvh, uint32_t* __restrict__ parent) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const RefNode* nodes = (const RefNode*)(bvh + 16);
+    parent[nodes[i].flags & 0x3fffffffu] = i;
+    parent[nodes[i].right] = i;
+    if (i == 0) parent[0] = 0xffffffffu;
+}
+__global__ void k_update_refit(uint32_t n, uint8_t* bvh, const uint32_t* __restrict__ parent, uint32_t* arrive) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n) return;
+    const uint32_t nInternal = n - 1, total = 2 * n - 1;
+    float* nodes = (float*)(bvh + 16);
+    const Prim* prims = (const Prim*)(bvh + 16 + 32 * (size_t)total);
+    uint32_t node = total - tid - 1;
+    {
+        f3 c, h;
+        leaf_box(prims, node - nInternal, c, h);
+        float4* nd = (float4*)(nodes + 8 * (size_t)node);
+        __stcg(nd, make_float4(c.x, c.y, c.z, __uint_as_float((node - nInternal) | 0x80000000u)));
+        __stcg(nd + 1, make_float4(h.x, h.y, h.z, __uint_as_float(1u)));
+    }
+    while (node != 0) {
+        const uint32_t up = parent[node];
+        __threadfence();
+        if (atomicAdd(&arrive[up], 1u) == 0) return; // the second arrival continues
+        __threadfence();
+        float4* nd = (float4*)(nodes + 8 * (size_t)up);
+        const float4 p0 = __ldcg(nd), p1 = __ldcg(nd + 1);        // keeps its child references (w lanes)
+        const uint32_t l = __float_as_uint(p0.w) & 0x3fffffffu, r = __float_as_uint(p1.w);
+        const float4* A = (const float4*)(nodes + 8 * (size_t)l);
+        const float4* B = (const float4*)(nodes + 8 * (size_t)r);
+        const float4 a0 = __ldcg(A), a1 = __ldcg(A + 1), b0 = __ldcg(B), b1 = __ldcg(B + 1);
+        f3 ac = mk3(a0.x, a0.y, a0.z), ah = mk3(a1.x, a1.y, a1.z);
+        f3 bc = mk3(b0.x, b0.y, b0.z), bh = mk3(b1.x, b1.y, b1.z);
+        f3 mn = min3(ac - ah, bc - bh), mx = max3(ac + ah, bc + bh);
+        f3 c = (mn + mx) * 0.5f;
+        f3 h = mx - c;
+        __stcg(nd, make_float4(c.x, c.y, c.z, p0.w));
+        __stcg(nd + 1, make_float4(h.x, h.y, h.z, p1.w));
+        node = up;
+    }
+}
+
 // ---------------------------------------------------------------------- widen
 __global__ void k_widen(uint32_t n, const uint8_t* __restrict__ bvh, PairNode* __restrict__ pairs, WideTri* __restrict__ tris) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -747,6 +817,24 @@ ScratchLayout scratch_layout(uint32_t n) {
 } // namespace
 
 uint64_t bvh_scratch_bytes(uint32_t n) { return n ? scratch_layout(n).end : 0; }
+// update: parent of every node + one arrival counter per internal node
+uint64_t bvh_update_scratch_bytes(uint32_t n) { return n ? 4 * (2 * (uint64_t)n - 1) + 256 + 4 * (uint64_t)n : 0; }
+
+cudaError_t update_bvh(const BuildGeometry* d_geoms, uint32_t n, DeviceBvh& bvh, void* scratch, cudaStream_t stream, LaunchCounter& lc) {
+    const uint32_t T = 256;
+    auto grid = [&](uint32_t c) { return (c + T - 1) / T; };
+    cudaError_t err;
+    uint32_t* parent = (uint32_t*)scratch;
+    uint32_t* arrive = (uint32_t*)((uint8_t*)scratch + ((4 * (2 * (size_t)n - 1) + 255) & ~(size_t)255));
+    k_update_prims<<<grid(n), T, 0, stream>>>(d_geoms, n, bvh.ref); lc.count++;
+    if (n > 1) { k_update_parents<<<grid(n - 1), T, 0, stream>>>(n, bvh.ref, parent); lc.count++; }
+    if ((err = cudaMemsetAsync(arrive, 0, 4 * (size_t)n, stream)) != cudaSuccess) return err;
+    k_update_refit<<<grid(n), T, 0, stream>>>(n, bvh.ref, parent, arrive); lc.count++;
+    k_widen<<<grid(n), T, 0, stream>>>(n, bvh.ref, bvh.pairs, bvh.tris); lc.count++;
+    if ((err = cudaMemcpyAsync(&bvh.root, bvh.ref + 16, sizeof(RefNode), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return err;
+    if ((err = cudaGetLastError()) != cudaSuccess) return err;
+    return cudaStreamSynchronize(stream);
+}
 
 // Builds the reference layout into out.ref and the traversal layout into out.pairs / out.tris. `scratch` holds at
 // least bvh_scratch_bytes(n) bytes (256-byte aligned). No allocation happens in here; the stream is synchronised

@@ -572,6 +572,13 @@ template <int KIND>
 __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh, PathState st, int qi, int bounce, uint32_t outputHeatmap, const FrameConstants* __restrict__ fcp, uint32_t budgetMain, uint32_t refillBelow,
                                                                    const TbGeometryRecord* __restrict__ classGeoms, const TbMaterial* __restrict__ classMats) {
     const bool classSort = KIND == EXT_MAIN && classGeoms != nullptr; // hits carry their material class and are counted per class
+    // per-block class histogram: the scene's hits fall into a handful of classes, so counting them in global memory would
+    // be millions of same-address atomics per bounce (measured: -13 % on Teapot); shared counters, flushed once per block
+    __shared__ uint32_t s_classCount[KIND == EXT_MAIN ? (1u << TB_CLASS_BITS) : 1u];
+    if (classSort) {
+        if (threadIdx.x < (1u << TB_CLASS_BITS)) s_classCount[threadIdx.x] = 0;
+        __syncthreads();
+    }
     const uint32_t aovMask = fcp->aovMask;
     const int bounceIsZero = bounce == 0;
     const uint32_t count = KIND == EXT_SHADOW ? st.queueCount[4] : KIND == EXT_WALK ? st.queueCount[10 + qi] : st.queueCount[qi];
@@ -623,7 +630,7 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
             if (classSort && retired && retiredHit) { // one counter update per distinct class per warp
                 cls = material_class(classGeoms, classMats, tr.hitGeom);
                 const uint32_t peers = __match_any_sync(mh, cls);
-                if (lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&st.queueCount[TB_CLASS_COUNT_BASE + cls], (uint32_t)__popc(peers));
+                if (lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_classCount[cls], (uint32_t)__popc(peers));
             }
             if (mh | mm) {
                 uint32_t bh = 0, bm = 0;
@@ -680,6 +687,10 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
         }
     }
     flush_stats(st, KIND == EXT_MAIN ? 0 : 3, bounce, rays, ntris, nboxes);
+    if (classSort) {
+        __syncthreads();
+        if (threadIdx.x < (1u << TB_CLASS_BITS) && s_classCount[threadIdx.x]) atomicAdd(&st.queueCount[TB_CLASS_COUNT_BASE + threadIdx.x], s_classCount[threadIdx.x]);
+    }
 }
 
 // Resume round `round` (1-based): continues the rays parked by round-1; the last round has no budget.
@@ -794,27 +805,52 @@ __global__ void __launch_bounds__(256) k_sort_scatter(PathState st, const uint32
 // retired, so one pass is left (every block derives the class offsets from the 64 counters itself). A warp of the
 // shading stage then works on hits of ONE class: the same branch of the lobe choice / specular / subsurface /
 // diffuse code, the same texture path. Order inside a class is arbitrary (every path is independent).
+#define CS_ITEMS 8 // queue entries per thread: a block of 256 threads sorts a chunk of 2048
 __global__ void __launch_bounds__(256) k_class_scatter(PathState st, int qi) {
-    __shared__ uint32_t s_start[1u << TB_CLASS_BITS];
+    __shared__ uint32_t s_start[1u << TB_CLASS_BITS]; // first slot of the class in the sorted queue
+    __shared__ uint32_t s_count[1u << TB_CLASS_BITS]; // this chunk's entries per class, then the chunk's cursor inside the class
+    __shared__ uint32_t s_base[1u << TB_CLASS_BITS];  // where this chunk's entries of the class start (one global atomic per class per block)
     const uint32_t count = st.queueCount[6 + 2 * qi];
+    uint32_t* __restrict__ cursor = st.queueCount + TB_CLASS_COUNT_BASE + (1u << TB_CLASS_BITS);
+    const uint32_t chunk = 256u * CS_ITEMS;
     if (threadIdx.x < (1u << TB_CLASS_BITS)) {
         uint32_t run = 0;
         for (uint32_t c = 0; c < threadIdx.x; c++) run += st.queueCount[TB_CLASS_COUNT_BASE + c];
         s_start[threadIdx.x] = run;
     }
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31;
-    uint32_t* __restrict__ cursor = st.queueCount + TB_CLASS_COUNT_BASE + (1u << TB_CLASS_BITS);
-    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < count; base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + lane;
-        const uint32_t e = i < count ? st.hitQueue[i] : 0xffffffffu;
-        const uint32_t key = i < count ? (e >> TB_CLASS_SHIFT) : 0xffffffffu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, key);
-        const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
-        uint32_t pos = 0;
-        if (i < count && lane == leader) pos = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
-        pos = __shfl_sync(0xffffffffu, pos, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-        if (i < count) st.hitSorted[s_start[key] + pos] = e & TB_PIXEL_MASK;
+    for (uint32_t first = blockIdx.x * chunk; first < count; first += gridDim.x * chunk) {
+        if (threadIdx.x < (1u << TB_CLASS_BITS)) s_count[threadIdx.x] = 0;
+        __syncthreads();
+        // one shared-memory atomic per distinct class per warp (a warp's 32 entries fall into one or two classes)
+        const uint32_t lane = threadIdx.x & 31;
+        uint32_t e[CS_ITEMS];
+#pragma unroll
+        for (int k = 0; k < CS_ITEMS; k++) {
+            const uint32_t i = first + k * 256u + threadIdx.x;
+            e[k] = i < count ? st.hitQueue[i] : 0xffffffffu;
+            const uint32_t key = i < count ? (e[k] >> TB_CLASS_SHIFT) : 0xffffffffu;
+            const uint32_t peers = __match_any_sync(0xffffffffu, key);
+            if (i < count && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_count[key], (uint32_t)__popc(peers));
+        }
+        __syncthreads();
+        if (threadIdx.x < (1u << TB_CLASS_BITS)) {
+            const uint32_t c = s_count[threadIdx.x];
+            s_base[threadIdx.x] = c ? atomicAdd(&cursor[threadIdx.x], c) : 0u;
+            s_count[threadIdx.x] = 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < CS_ITEMS; k++) {
+            const uint32_t i = first + k * 256u + threadIdx.x;
+            const uint32_t key = i < count ? (e[k] >> TB_CLASS_SHIFT) : 0xffffffffu;
+            const uint32_t peers = __match_any_sync(0xffffffffu, key);
+            const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+            uint32_t pos = 0;
+            if (i < count && lane == leader) pos = atomicAdd(&s_count[key], (uint32_t)__popc(peers));
+            pos = __shfl_sync(0xffffffffu, pos, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            if (i < count) st.hitSorted[s_start[key] + s_base[key] + pos] = e[k] & TB_PIXEL_MASK;
+        }
+        __syncthreads();
     }
 }
 
@@ -1422,7 +1458,7 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
         }
         if (timers) cudaEventRecord(timers->next(KernelTimers::SHADE, b), stream);
         k_shade_miss<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(sc, fcDev, st, qi); launches++;
-        if (classSort) { k_class_scatter<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(st, qi); launches++; }
+        if (classSort) { k_class_scatter<<<(n + 2047) / 2048 < sms * 8 ? (n + 2047) / 2048 : sms * 8, 256, 0, stream>>>(st, qi); launches++; }
         // next-event shadow rays exist only with lights and NEE on; then shading runs as two stages
         // around a traversal kernel for the shadow queue
         const bool nee = sc.numLights > 0 && fc.settings.EnableNextEventEstimation;

@@ -1028,7 +1028,7 @@ TB_API int tb_bvh_prebuild_info(const TbGeometryDesc* geoms, uint32_t n, TbPrebu
     out->ReferenceLayoutSizeInBytes = bvh_ref_bytes((uint32_t)tris);
     out->ResultDataMaxSizeInBytes = as_layout((uint32_t)tris).end;
     out->ScratchDataSizeInBytes = bvh_scratch_bytes((uint32_t)tris);
-    out->UpdateScratchDataSizeInBytes = 0;
+    out->UpdateScratchDataSizeInBytes = bvh_update_scratch_bytes((uint32_t)tris);
     return TB_OK;
 }
 
@@ -1071,6 +1071,29 @@ TB_API int tb_bvh_build_device(TbHandle* h, const TbGeometryDesc* geoms, uint32_
     return TB_OK;
 }
 
+// resolves a caller-owned acceleration structure to its DeviceBvh (cached, else from the structure's own trailer)
+static int resolve_as(TbHandle* h, const void* as, uint64_t asBytes, cudaStream_t stream, DeviceBvh& b) {
+    auto it = h->deviceBuilds.find(as);
+    if (it != h->deviceBuilds.end()) { b = it->second; return TB_OK; }
+    uint32_t hd[4];
+    CUDA_OK(h, cudaMemcpyAsync(hd, as, sizeof(hd), cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(h, cudaStreamSynchronize(stream));
+    // the first four words of the reference layout give its size: offsetToPrimitiveMetaData + 12 N == 116 N - 16
+    if (hd[0] != 16 || hd[3] < 100 || (hd[3] + 16ull) % 116) return fail(h, TB_ERR_INVALID_ARG, "not an acceleration structure built by tb_bvh_build_device");
+    const uint32_t N = (uint32_t)((hd[3] + 16ull) / 116);
+    const AsLayout L = as_layout(N);
+    if (asBytes < L.end) return fail(h, TB_ERR_INVALID_ARG, "acceleration structure buffer too small");
+    AsTrailer t;
+    CUDA_OK(h, cudaMemcpyAsync(&t, (const uint8_t*)as + L.trailer, sizeof(t), cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(h, cudaStreamSynchronize(stream));
+    if (memcmp(t.magic, "TBAS0001", 8) != 0 || t.numPrims != N || t.depth > TB_STACK_DEPTH) return fail(h, TB_ERR_INVALID_ARG, "acceleration structure trailer is missing or corrupt");
+    b.ref = (uint8_t*)as; b.refBytes = bvh_ref_bytes(N);
+    b.pairs = (PairNode*)((uint8_t*)as + L.pairs); b.tris = (WideTri*)((uint8_t*)as + L.tris);
+    b.root = t.root; b.numPrims = N; b.depth = t.depth;
+    h->deviceBuilds[as] = b;
+    return TB_OK;
+}
+
 TB_API int tb_trace_rays_device(TbHandle* h, const void* as, uint64_t asBytes, const TbRay* dRays, uint64_t n, TbHit* dHits, void* cudaStream) {
     if (!h || (n && (!dRays || !dHits))) return fail(h, TB_ERR_INVALID_ARG, "null argument");
     CUDA_OK(h, cudaSetDevice(h->device));
@@ -1080,29 +1103,46 @@ TB_API int tb_trace_rays_device(TbHandle* h, const void* as, uint64_t asBytes, c
         if (!h->sceneLoaded) return fail(h, TB_ERR_STATE, "no acceleration structure");
         b = h->bvh;
     } else {
-        auto it = h->deviceBuilds.find(as);
-        if (it != h->deviceBuilds.end()) b = it->second;
-        else { // built by another handle (or copied): read the structure's own trailer. The first four words of the
-               // reference layout give its size: offsetToPrimitiveMetaData + 12 N == 116 N - 16.
-            uint32_t hd[4];
-            CUDA_OK(h, cudaMemcpyAsync(hd, as, sizeof(hd), cudaMemcpyDeviceToHost, stream));
-            CUDA_OK(h, cudaStreamSynchronize(stream));
-            if (hd[0] != 16 || hd[3] < 100 || (hd[3] + 16ull) % 116) return fail(h, TB_ERR_INVALID_ARG, "not an acceleration structure built by tb_bvh_build_device");
-            const uint32_t N = (uint32_t)((hd[3] + 16ull) / 116);
-            const AsLayout L = as_layout(N);
-            if (asBytes < L.end) return fail(h, TB_ERR_INVALID_ARG, "acceleration structure buffer too small");
-            AsTrailer t;
-            CUDA_OK(h, cudaMemcpyAsync(&t, (const uint8_t*)as + L.trailer, sizeof(t), cudaMemcpyDeviceToHost, stream));
-            CUDA_OK(h, cudaStreamSynchronize(stream));
-            if (memcmp(t.magic, "TBAS0001", 8) != 0 || t.numPrims != N || t.depth > TB_STACK_DEPTH) return fail(h, TB_ERR_INVALID_ARG, "acceleration structure trailer is missing or corrupt");
-            b.ref = (uint8_t*)as; b.refBytes = bvh_ref_bytes(N);
-            b.pairs = (PairNode*)((uint8_t*)as + L.pairs); b.tris = (WideTri*)((uint8_t*)as + L.tris);
-            b.root = t.root; b.numPrims = N; b.depth = t.depth;
-            h->deviceBuilds[as] = b;
-        }
+        int rc = resolve_as(h, as, asBytes, stream, b);
+        if (rc != TB_OK) return rc;
     }
     if (n == 0) return TB_OK;
     CUDA_OK(h, trace_rays(b, dRays, n, dHits, h->numSMs, stream, h->lc)); // asynchronous on `stream`, like a dispatch
+    return TB_OK;
+}
+
+TB_API int tb_bvh_update_device(TbHandle* h, const TbGeometryDesc* geoms, uint32_t n, void* dst, uint64_t dstBytes,
+                                void* scratch, uint64_t scratchBytes, void* cudaStream) {
+    if (!h || !geoms || n == 0 || !dst) return fail(h, TB_ERR_INVALID_ARG, "null/empty argument");
+    uint64_t tris = 0;
+    if (count_triangles(geoms, n, &tris) != TB_OK) return fail(h, TB_ERR_INVALID_ARG, "bad index format");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    cudaStream_t stream = cudaStream ? (cudaStream_t)cudaStream : h->stream;
+    DeviceBvh b;
+    int rc = resolve_as(h, dst, dstBytes, stream, b);
+    if (rc != TB_OK) return rc;
+    // "the geometry descs of an update must match the build's: same counts, same index buffers' topology" (D3D12 spec)
+    if (tris != b.numPrims) return fail(h, TB_ERR_INVALID_ARG, "an update needs the triangle count of the original build");
+    if (scratch && scratchBytes < bvh_update_scratch_bytes(b.numPrims)) return fail(h, TB_ERR_INVALID_ARG, "scratch smaller than UpdateScratchDataSizeInBytes");
+    std::vector<BuildGeometry> descs(n);
+    for (uint32_t g = 0; g < n; g++) {
+        const TbGeometryDesc& G = geoms[g];
+        if (!G.Positions || G.PositionStrideBytes < 12 || G.PositionStrideBytes % 4) return fail(h, TB_ERR_INVALID_ARG, "bad vertex buffer");
+        descs[g] = {(const uint8_t*)G.Positions, G.Indices, G.Transform3x4, G.PositionStrideBytes, G.IndexFormat, G.GeometryFlags, 0u};
+    }
+    void* owned[2] = {nullptr, nullptr};
+    struct Guard { void** p; ~Guard() { for (int i = 0; i < 2; i++) if (p[i]) cudaFree(p[i]); } } guard{owned};
+    CUDA_OK(h, cudaMalloc(&owned[0], sizeof(BuildGeometry) * descs.size()));
+    CUDA_OK(h, cudaMemcpyAsync(owned[0], descs.data(), sizeof(BuildGeometry) * descs.size(), cudaMemcpyHostToDevice, stream));
+    if (!scratch) { CUDA_OK(h, cudaMalloc(&owned[1], bvh_update_scratch_bytes(b.numPrims))); scratch = owned[1]; }
+    CUDA_OK(h, update_bvh((const BuildGeometry*)owned[0], b.numPrims, b, scratch, stream, h->lc));
+    AsTrailer t;
+    memset(&t, 0, sizeof(t));
+    memcpy(t.magic, "TBAS0001", 8);
+    t.numPrims = b.numPrims; t.depth = b.depth; t.root = b.root;
+    CUDA_OK(h, cudaMemcpyAsync((uint8_t*)dst + as_layout(b.numPrims).trailer, &t, sizeof(t), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(h, cudaStreamSynchronize(stream));
+    h->deviceBuilds[dst] = b;
     return TB_OK;
 }
 
