@@ -373,16 +373,20 @@ def main():
     pst = g.GetRenderStats()
     g.SetProfiling(0)
     peak, peak_src = measured_peak_gbs()
-    # The dominant kernel's launch duration is well defined only when it has the GPU to itself: one frame at a time
-    # (profiling mode 1), CUDA events around every k_extend<EXT_MAIN> launch. That is `achieved`. In the timed mode 32
-    # frames overlap and fill each other's tails, so the step is ~2x shorter than the sum of its exclusive launches;
-    # what traversal achieves there is reported as `in_situ` (all rays of the timed region over the whole device time,
-    # shading included: a lower bound of the traversal rate).
+    # `achieved`: what the traversal stage achieves in the TIMED mode -- the algorithmic bytes of every ray of the timed
+    # region (extension, shadow and walk rays; all k_extend kinds, k_extend_resume, k_walk) over the whole device time of
+    # the region, shading and accumulation included: a lower bound of the traversal rate that needs no attribution of
+    # overlapped kernels. With 32 frames in flight the launches of different frames overlap and fill each other's tails
+    # (the step is ~2x shorter than the sum of its launches timed alone), so a per-launch duration only exists for a
+    # launch that has the GPU to itself: that is measured too (profiling mode 1, one frame at a time, CUDA events around
+    # every k_extend<EXT_MAIN> launch) and reported as `exclusive`, with the kernel's share of the step for the
+    # cross-check against the serialised ncu launch list in profiles/.
     share = pst.ExtendMilliseconds / max(1e-9, pst.ExtendMilliseconds + pst.ShadeMilliseconds + pst.ResumeMilliseconds)
     share_concurrent = cst.ExtendMilliseconds / max(1e-9, cst.ExtendMilliseconds + cst.ShadeMilliseconds + cst.ResumeMilliseconds)
     serial_alg = 32.0 * pst.ExtendBoxesTested + 40.0 * pst.ExtendTrianglesTested + 64.0 * pst.ExtendRays
-    achieved = serial_alg / max(1e-9, pst.ExtendMilliseconds / 1e3) / 1e9
-    in_situ_gbs = (32.0 * boxes_total + 40.0 * tris_total + 64.0 * rays_total) / t_step / 1e9
+    exclusive_gbs = serial_alg / max(1e-9, pst.ExtendMilliseconds / 1e3) / 1e9
+    alg_step = (32.0 * boxes_total + 40.0 * tris_total + 64.0 * rays_total) / args.steps   # whole job, per step
+    achieved = alg_step / (t_step / args.steps) / 1e9 / world                                # per GPU
     units = ncu_units(args.workload)
     bound = "unknown (no ncu capture of this workload in profiles/r2_ncu_units.json)"
     if units:
@@ -396,27 +400,27 @@ def main():
                                "mrays_per_s": pst.RaysByBounce[b] / max(1e-9, pst.BounceMilliseconds[b]) / 1e3,
                                "extend_ms": pst.BounceExtendMilliseconds[b]})
     roofline = {
-        "bound": bound, "kernel": "k_extend<EXT_MAIN>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak,
+        "bound": bound, "kernel": "traversal stage (k_extend<MAIN|SHADOW|WALK>, k_extend_resume, k_walk)", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": achieved / peak,
         "traffic": (units or {}).get("dram_bytes_per_launch"),
         "traffic_source": (units or {}).get("source"),
-        "algorithmic_bytes_per_launch": serial_alg / max(1, pst.ExtendLaunches),
-        "avg_launch_ms": pst.ExtendMilliseconds / max(1, pst.ExtendLaunches), "launches": pst.ExtendLaunches,
+        "algorithmic_bytes_per_step": alg_step / world, "ms_per_step": 1e3 * t_step / args.steps,
+        "how": "timed mode, per GPU: (32 B x BoxesTested + 40 B x TrianglesTested + 64 B x rays) of ALL rays of the timed region / device time "
+               "of the region (the same CUDA events as `value`), shading included; no attribution of overlapped launches is needed",
         "kernel_share_of_step": share,
-        "how": "per-launch CUDA events around k_extend<EXT_MAIN> on its launching stream, one frame at a time (the kernel alone on the GPU), "
-               "%d frames of the workload measured in this run; share = its part of the exclusive time of all launches of a frame "
-               "(the definition the serialised ncu launch list in profiles/ uses)" % min(spp_rank, 16),
         "units_pct_of_peak": units,
-        "resume_rounds": {"rays": pst.ResumeRays, "ms": pst.ResumeMilliseconds},
-        # the timed mode itself: frames in flight overlap, every kernel included
-        "in_situ": {"algorithmic_GBps": in_situ_gbs, "frac": in_situ_gbs / peak,
-                    "what": "algorithmic bytes of ALL rays of the timed region (extension, shadow, walk) / whole device time of the region, "
-                            "shading and accumulation included",
-                    "kernel_share_of_stream_time_under_concurrency": share_concurrent},
+        "exclusive": {  # k_extend<EXT_MAIN> alone on the GPU: one frame at a time, CUDA events around every launch on its stream
+            "kernel": "k_extend<EXT_MAIN>", "achieved": exclusive_gbs, "frac": exclusive_gbs / peak,
+            "algorithmic_bytes_per_launch": serial_alg / max(1, pst.ExtendLaunches),
+            "avg_launch_ms": pst.ExtendMilliseconds / max(1, pst.ExtendLaunches), "launches": pst.ExtendLaunches,
+            "frames": min(spp_rank, 16), "kernel_share_of_step": share,
+            "resume_rounds": {"rays": pst.ResumeRays, "ms": pst.ResumeMilliseconds},
+            "note": "includes each launch's tail (a few rays with thousands of node visits), which the timed mode hides behind other frames"},
+        "kernel_share_of_stream_time_under_concurrency": share_concurrent,
         "peak_source": peak_src,
-        "note": "algorithmic bytes = 32 B x BoxesTested + 40 B x TrianglesTested + 64 B ray/hit on the reference BVH2 layout (SURVEY 8d). "
-                "`peak` is the measured HBM copy bandwidth; a BVH that fits the 126 MB L2 is served from L1/L2, so `bound` names the unit "
-                "ncu shows closest to its own peak (units_pct_of_peak) and frac is NOT a DRAM utilisation there",
+        "note": "algorithmic bytes on the reference BVH2 layout (SURVEY 8d). `peak` is the measured HBM copy bandwidth; a BVH that fits the "
+                "126 MB L2 is served from L1/L2, so `bound` names the unit ncu shows closest to its own peak (units_pct_of_peak) and frac "
+                "is NOT a DRAM utilisation there",
     }
 
     cpu_baseline = None

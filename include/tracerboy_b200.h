@@ -453,7 +453,7 @@ TB_API int tb_set_shadow_mode(TbHandle* h, int mode);
 TB_API int tb_set_ray_sort(TbHandle* h, int mode);
 /* Hit queue of the shading stage grouped by material class (the material's flag bits + "albedo is textured") so that a
  * warp shades hits that take the same branches: 0 = off, 1 = on, 2 = automatic (default: on when the scene's reachable
- * materials span more than one class). Scheduling only: results are identical. */
+ * materials span four or more classes, where it was measured to pay). Scheduling only: results are identical. */
 TB_API int tb_set_material_sort(TbHandle* h, int mode);
 TB_API int tb_synchronize(TbHandle* h);
 

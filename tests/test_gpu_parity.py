@@ -283,7 +283,7 @@ def test_ray_sort_changes_nothing(tmp_path, built):
 
 def test_material_sort_changes_nothing(tmp_path, built):
     """The shading stage's hit queue grouped by material class (north star (4): "sorted by material to cut divergence";
-    automatic whenever the scene's materials span more than one class) is scheduling only: forced on and off, with the
+    automatic from four material classes on) is scheduling only: forced on and off, with the
     shadow rays inline and as their own stage, with and without ray suspension (one frame in flight), a scene with
     every material class still equals the oracle bit for bit, counters included."""
     import tracerboy_b200 as tb

@@ -63,6 +63,7 @@ struct DeviceScene {
     // images: table of {ptr, w, h, format}
     struct ImageRef { const void* data; uint32_t width, height, format; };
     const ImageRef* images = nullptr;
+    const uint8_t* geomClass = nullptr; // per geometry: material class of the shading stage's queue (pathtrace.cu: material_class)
     const uint8_t* blueNoise = nullptr; // 2 x 256 x 256 x RGBA8
     uint32_t numGeoms = 0, numMaterials = 0, numLights = 0, numTextures = 0, numImages = 0;
     int32_t envImage = -1;

@@ -525,12 +525,11 @@ __device__ __forceinline__ bool write_hit(PathState& st, const Traversal& tr, ui
 #define TB_CLASS_SHIFT 26            // a queue entry is pixel | class << 26 (tb_resize caps the image at 2^26 pixels)
 #define TB_PIXEL_MASK 0x03ffffffu
 #define TB_CLASS_COUNT_BASE 16       // queueCount[16 .. 79]: hits per class of the current bounce, [80 .. 143]: scatter cursors
-__device__ __forceinline__ uint32_t material_class(const TbGeometryRecord* __restrict__ geoms, const TbMaterial* __restrict__ mats, uint32_t geom) {
-    const uint32_t mi = __ldg(&geoms[geom].MaterialIndex);
-    const uint32_t* m = (const uint32_t*)(mats + mi);
-    const uint32_t flags = __ldg(m + 19), albedoIndex = __ldg(m + 3);
-    return (flags & 0x1fu) | (albedoIndex != TB_INVALID_TEXTURE ? 0x20u : 0u); // METALLIC 1, SSS 2, NO_SPECULAR 4, MIX 8, LIGHT 16, textured 32
-}
+// The class of every geometry is tabulated by the host when the scene (or a material) changes: (Flags & 0x1f) |
+// (albedo textured ? 0x20 : 0) of the geometry's material, i.e. METALLIC 1, SUBSURFACE 2, NO_SPECULAR 4, MIX 8, LIGHT 16,
+// textured 32. One byte load from a table that lives in L1 (two dependent loads through the geometry and material
+// records stalled the whole warp's service phase).
+__device__ __forceinline__ uint32_t material_class(const uint8_t* __restrict__ classOfGeom, uint32_t geom) { return __ldg(classOfGeom + geom); }
 
 // hit / miss queues of the bounce: counters [6 + 2*qi] (hits) and [7 + 2*qi] (misses)
 __device__ __forceinline__ void push_sorted(PathState& st, int qi, uint32_t pi, bool hit, uint32_t cls, bool classSort) {
@@ -570,8 +569,8 @@ __device__ __forceinline__ bool try_suspend(PathState& st, int round, const Trav
 #define EXT_WALK 2
 template <int KIND>
 __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh, PathState st, int qi, int bounce, uint32_t outputHeatmap, const FrameConstants* __restrict__ fcp, uint32_t budgetMain, uint32_t refillBelow,
-                                                                   const TbGeometryRecord* __restrict__ classGeoms, const TbMaterial* __restrict__ classMats) {
-    const bool classSort = KIND == EXT_MAIN && classGeoms != nullptr; // hits carry their material class and are counted per class
+                                                                   const uint8_t* __restrict__ classOfGeom) {
+    const bool classSort = KIND == EXT_MAIN && classOfGeom != nullptr; // hits carry their material class and are counted per class
     // per-block class histogram: the scene's hits fall into a handful of classes, so counting them in global memory would
     // be millions of same-address atomics per bounce (measured: -13 % on Teapot); shared counters, flushed once per block
     __shared__ uint32_t s_classCount[KIND == EXT_MAIN ? (1u << TB_CLASS_BITS) : 1u];
@@ -628,7 +627,7 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
             uint32_t mh = __ballot_sync(0xffffffffu, retired && retiredHit), mm = __ballot_sync(0xffffffffu, retired && !retiredHit);
             uint32_t cls = 0;
             if (classSort && retired && retiredHit) { // one counter update per distinct class per warp
-                cls = material_class(classGeoms, classMats, tr.hitGeom);
+                cls = material_class(classOfGeom, tr.hitGeom);
                 const uint32_t peers = __match_any_sync(mh, cls);
                 if (lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_classCount[cls], (uint32_t)__popc(peers));
             }
@@ -696,8 +695,8 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
 // Resume round `round` (1-based): continues the rays parked by round-1; the last round has no budget.
 __global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState st, int qi, int round, uint32_t budget, int bounce,
                                                        uint32_t outputHeatmap, const FrameConstants* __restrict__ fcp,
-                                                       const TbGeometryRecord* __restrict__ classGeoms, const TbMaterial* __restrict__ classMats) {
-    const bool classSort = classGeoms != nullptr;
+                                                       const uint8_t* __restrict__ classOfGeom) {
+    const bool classSort = classOfGeom != nullptr;
     const uint32_t aovMask = fcp->aovMask;
     const int bounceIsZero = bounce == 0;
     const uint32_t count = min(st.susCount[round - 1], st.susCapacity);
@@ -713,7 +712,7 @@ __global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState 
         while (true) {
             if (tr.done()) {
                 const bool hit = write_hit(st, tr, pi, bounceIsZero, outputHeatmap, aovMask, rays, ntris, nboxes);
-                push_sorted(st, qi, pi, hit, (hit && classSort) ? material_class(classGeoms, classMats, tr.hitGeom) : 0u, classSort);
+                push_sorted(st, qi, pi, hit, (hit && classSort) ? material_class(classOfGeom, tr.hitGeom) : 0u, classSort);
                 break;
             }
             if (budget && tr.steps() >= suspendAt) {
@@ -1443,16 +1442,18 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
         // hits are binned by material class when the scene's reachable materials span more than one class
         static int classEnv = -2; // tuning knob (results never depend on it)
         if (classEnv == -2) { const char* e = getenv("TB_CLASS_SORT"); classEnv = e ? atoi(e) : -1; }
-        const bool classSort = classEnv >= 0 ? classEnv != 0 : (opts.materialSort == 2 ? opts.sceneMaterialClasses > 1 : opts.materialSort != 0);
-        const TbGeometryRecord* classGeoms = classSort ? sc.geoms : nullptr;
-        const TbMaterial* classMats = classSort ? sc.materials : nullptr;
-        k_extend<EXT_MAIN><<<blocks, 128, 0, stream>>>(bvh, stx, qi, b, heat, fcDev, suspendMode ? budgetMain : 0xffffffffu, refillBelow, classGeoms, classMats); launches++;
+        // automatic: from four classes on. Measured on B200 (profiles/r2_class_sort_sweep.log): vw-van (glass, metal, mix,
+        // textured, matte) +3 %, 20.8 M triangles +2 %, Teapot +0.4 %; scenes with two classes lose 3-4 % to the extra
+        // launch per bounce (dragon, cornell)
+        const bool classSort = classEnv >= 0 ? classEnv != 0 : (opts.materialSort == 2 ? opts.sceneMaterialClasses >= 4 : opts.materialSort != 0);
+        const uint8_t* classOfGeom = classSort ? sc.geomClass : nullptr;
+        k_extend<EXT_MAIN><<<blocks, 128, 0, stream>>>(bvh, stx, qi, b, heat, fcDev, suspendMode ? budgetMain : 0xffffffffu, refillBelow, classOfGeom); launches++;
         if (suspendMode) {
             uint32_t rblocks = (st.susCapacity + 127) / 128;
             if (rblocks > sms * 4) rblocks = sms * 4;
             if (timers) cudaEventRecord(timers->next(KernelTimers::RESUME, b), stream);
             for (int r = 1; r <= EXTEND_RESUME_ROUNDS; r++) {
-                k_extend_resume<<<rblocks, 128, 0, stream>>>(bvh, st, qi, r, budgets[r - 1], b, heat, fcDev, classGeoms, classMats); launches++;
+                k_extend_resume<<<rblocks, 128, 0, stream>>>(bvh, st, qi, r, budgets[r - 1], b, heat, fcDev, classOfGeom); launches++;
                 rblocks = (rblocks + 3) / 4 > sms ? (rblocks + 3) / 4 : sms;
             }
         }
@@ -1476,7 +1477,7 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
                 sort_queue(st.shadowQueue, &st.queueCount[4], st.shRayO);
                 sts.shadowQueue = st.sortTmp;
             }
-            k_extend<EXT_SHADOW><<<blocks, 128, 0, stream>>>(bvh, sts, qi, b, 0, fcDev, 0xffffffffu, refillBelow, nullptr, nullptr); launches++;
+            k_extend<EXT_SHADOW><<<blocks, 128, 0, stream>>>(bvh, sts, qi, b, 0, fcDev, 0xffffffffu, refillBelow, nullptr); launches++;
             TB_LAUNCH_SHADE(1);
         } else if (nee) {
             TB_LAUNCH_SHADE(2);
@@ -1489,7 +1490,7 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
             if (roundsEnv == -2) { const char* e = getenv("TB_WALK_ROUNDS"); roundsEnv = e ? atoi(e) : -1; }
             const int rounds = roundsEnv >= 0 ? roundsEnv : opts.walkRounds; // wavefront rounds before the persistent tail (which reads queue rounds & 1)
             for (int r = 0; r < rounds; r++) {
-                k_extend<EXT_WALK><<<blocks, 128, 0, stream>>>(bvh, st, r & 1, b, 0, fcDev, 0xffffffffu, REFILL_THRESHOLD, nullptr, nullptr); launches++;
+                k_extend<EXT_WALK><<<blocks, 128, 0, stream>>>(bvh, st, r & 1, b, 0, fcDev, 0xffffffffu, REFILL_THRESHOLD, nullptr); launches++;
                 k_walk_step<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(sc, fcDev, st, qi, r & 1); launches++;
             }
             uint32_t wblocks = blocks > sms * 4 ? sms * 4 : blocks;

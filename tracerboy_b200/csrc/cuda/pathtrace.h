@@ -106,7 +106,7 @@ struct RenderOptions {
     int walkRounds = 1; // glass / subsurface walk: wavefront rounds (k_extend<EXT_WALK> + k_walk_step) before the persistent tail kernel
     bool suspendRays = true; // park rays over budget and resume them in k_extend_resume rounds (set by the host: on with fewer than 8 frames in flight)
     int sortRays = 2;   // spatial sort of the ray queues before traversal: 0 off, bit 0 bounce queue, bit 1 shadow queue (1 or 3), 2 automatic (3 for scenes whose BVH is far beyond L2)
-    int materialSort = 2; // hit queue grouped by material class before shading: 0 off, 1 on, 2 automatic (on when the scene's reachable materials span more than one class)
+    int materialSort = 2; // hit queue grouped by material class before shading: 0 off, 1 on, 2 automatic (on from four material classes)
     uint32_t sceneMaterialClasses = 1; // distinct material classes reachable from the geometry (host-side count)
     int numSMs = 148;   // of the handle's device (persistent grids are sized from it)
     bool sceneHasSSS = true; // any material with the subsurface flag (selects the k_shade variant with the inline random walk)

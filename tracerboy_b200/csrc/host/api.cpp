@@ -104,13 +104,22 @@ static bool scene_has_sss(const tb::Scene& s) {
 
 // distinct material classes (the key of the shading stage's queue, material_class() in pathtrace.cu) among the
 // materials the geometry references
+static uint8_t geometry_class(const tb::Scene& s, const TbGeometryRecord& g) {
+    const TbMaterial& m = s.materials[g.MaterialIndex];
+    return (uint8_t)(((uint32_t)m.Flags & 0x1fu) | (m.albedoIndex != TB_INVALID_TEXTURE ? 0x20u : 0u));
+}
 static uint32_t scene_material_classes(const tb::Scene& s) {
     uint64_t seen = 0;
-    for (const TbGeometryRecord& g : s.geoms) {
-        const TbMaterial& m = s.materials[g.MaterialIndex];
-        seen |= 1ull << (((uint32_t)m.Flags & 0x1fu) | (m.albedoIndex != TB_INVALID_TEXTURE ? 0x20u : 0u));
-    }
+    for (const TbGeometryRecord& g : s.geoms) seen |= 1ull << geometry_class(s, g);
     return (uint32_t)__builtin_popcountll(seen);
+}
+// (re)writes the device table of per-geometry classes; the allocation is made once per scene upload
+static int upload_geometry_classes(TbHandle* h) {
+    std::vector<uint8_t> cls(h->scene.geoms.size());
+    for (size_t g = 0; g < cls.size(); g++) cls[g] = geometry_class(h->scene, h->scene.geoms[g]);
+    CUDA_OK(h, cudaMemcpyAsync((void*)h->dscene.geomClass, cls.data(), cls.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return TB_OK;
 }
 
 // One build on caller-described device geometry into caller-provided (or library-owned) memory. Shared by the scene
@@ -161,6 +170,14 @@ static int upload_and_build(TbHandle* h, uint32_t flags) {
     }
     CUDA_OK(h, upload(h, h->sceneAllocs, refs.data(), refs.size(), &d.images));
     CUDA_OK(h, upload(h, h->sceneAllocs, h->blueNoiseHost.data(), h->blueNoiseHost.size(), &d.blueNoise));
+    {
+        void* p = nullptr;
+        CUDA_OK(h, cudaMalloc(&p, s.geoms.size() ? s.geoms.size() : 1));
+        h->sceneAllocs.push_back(p);
+        d.geomClass = (const uint8_t*)p;
+        int rc = upload_geometry_classes(h);
+        if (rc != TB_OK) return rc;
+    }
     d.numGeoms = (uint32_t)s.geoms.size(); d.numMaterials = (uint32_t)s.materials.size();
     d.numLights = (uint32_t)s.lights.size(); d.numTextures = (uint32_t)s.textures.size(); d.numImages = (uint32_t)s.images.size();
     d.envImage = s.envImage; d.flipTextureUVs = s.flipTextureUVs;
@@ -982,6 +999,7 @@ TB_API int tb_set_material(TbHandle* h, int id, const TbMaterial* m) {
     h->options.sceneHasSSS = scene_has_sss(h->scene); // also through mix materials that reference the edited one
     h->options.sceneMaterialClasses = scene_material_classes(h->scene);
     CUDA_OK(h, cudaSetDevice(h->device));
+    { int rc = upload_geometry_classes(h); if (rc != TB_OK) return rc; }
     CUDA_OK(h, cudaMemcpyAsync((void*)(h->dscene.materials + id), m, sizeof(*m), cudaMemcpyHostToDevice, h->stream));
     CUDA_OK(h, cudaStreamSynchronize(h->stream));
     h->samplesRendered = 0;
