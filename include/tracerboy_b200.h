@@ -304,6 +304,14 @@ typedef struct TbPrebuildInfo {
     uint64_t ReferenceLayoutSizeInBytes; /* 116*N - 16 */
 } TbPrebuildInfo;
 
+/* D3D12_RAYTRACING_INSTANCE_DESC (64 bytes; RayTracingHlslCompat.h:217-224 reads it as RaytracingInstanceDesc). */
+typedef struct TbInstanceDesc {
+    float Transform[12];                                   /* object to world, row-major 3x4 */
+    uint32_t InstanceIDAndMask;                            /* InstanceID : 24 | InstanceMask << 24 (mask 0 = never hit) */
+    uint32_t InstanceContributionToHitGroupIndexAndFlags;  /* contribution : 24 | D3D12_RAYTRACING_INSTANCE_FLAGS << 24 */
+    uint64_t AccelerationStructure;                        /* device address of a bottom-level structure (dst of tb_bvh_build_device) */
+} TbInstanceDesc;
+
 /* RayDesc as consumed by SoftwareRayQuery::TraceRayInline (TraverseFunction.hlsli:39-132) */
 typedef struct TbRay {
     float Origin[3];
@@ -563,6 +571,7 @@ static_assert(sizeof(TbLight) == 104, "Light must be 104 bytes");
 static_assert(sizeof(TbTextureData) == 80, "TextureData must be 80 bytes");
 static_assert(sizeof(TbVertex) == 32, "Vertex must be 32 bytes");
 static_assert(sizeof(TbRay) == 32, "Ray must be 32 bytes");
+static_assert(sizeof(TbInstanceDesc) == 64, "D3D12_RAYTRACING_INSTANCE_DESC is 64 bytes");
 static_assert(sizeof(TbHit) == 32, "Hit must be 32 bytes");
 #endif
 #endif /* TRACERBOY_B200_H */

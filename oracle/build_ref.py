@@ -147,6 +147,31 @@ def build_refit(force=False):
     return target
 
 
+def tlas_lib_path():
+    return os.path.join(OUT, "libref_tlas.so")
+
+
+def build_tlas(force=False):
+    """oracle/_ref/libref_tlas.so: the arithmetic of the top-level instance load (inverse transform, transformed box) as host C++."""
+    helper = "/root/reference/D3D12RaytracingFallback/src/RayTracingHelper.hlsli"
+    target = tlas_lib_path()
+    if not os.path.exists(helper):
+        return target if os.path.exists(target) else None
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_tlas.cpp")] + [helper]
+    if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs):
+        return target
+    sys.path.insert(0, os.path.join(HERE, "ref"))
+    import prepass
+    prepass.run_tlas(helper, os.path.join(OUT, "tlas_gen.inc"))
+    cmd = [GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma", "-ffp-contract=off", "-fsingle-precision-constant", "-fno-fast-math",
+           "-fvisibility=hidden", "-w", "-I" + os.path.join(ROOT, "include"), "-I" + HERE, os.path.join(HERE, "ref", "ref_tlas.cpp"), "-o", target]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref tlas build failed:\n" + r.stdout)
+    return target
+
+
 ENTRY = "/root/reference/TracerBoy/SoftwareRayTraceCS.hlsl"
 
 

@@ -500,4 +500,165 @@ bool update_bvh(Scene& s, std::string& err) {
     return true;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Top-level acceleration structure: BuildRaytracingAccelerationStructure for
+// D3D12_RAYTRACING_ACCELERATION_STRUCTURE_TYPE_TOP_LEVEL (GpuBVH2Builder.cpp:116-146, SceneType::BottomLevelBVHs).
+//   load        TopLevelLoadAABBs.hlsli:58-100: per instance, the bottom-level root box transformed to world space
+//               (TransformAABB, RayTracingHelper.hlsli:318-344: the 8 corners through ObjectToWorld), the desc's
+//               transform replaced by its inverse (InverseAffineTransform :297-316), ObjectToWorld kept beside it
+//   scene box   CalculateSceneAABBFromBVHs.hlsl (min / max of the instance boxes, read back as centre -+ half)
+//   morton      CalculateMortonCodesForAABBs.hlsl: GetCentroid = the stored box centre
+//   sort, rearrange (RearrangeBVHs.hlsl), Karras hierarchy: as for triangles; NO treelet pass (GpuBVH2Builder.cpp:343)
+//   boxes       TopLevelComputeAABBs.hlsl: a leaf's box is recomputed from its instance's bottom-level root box and
+//               ObjectToWorld; internal nodes as for triangles (smaller subtree left, D1 on ties)
+// Layout: 16-byte header {offsetToBoxes = 16, 0, offsetToLeafNodeMetaData, totalSize} (TopLevelPrepareForComputeAABBs.hlsl
+// stores three of the four words), 32-byte nodes (internal [0, N-1), leaves [N-1, 2N-1)), 116-byte BVHMetadata per sorted
+// leaf (RayTracingHlslCompat.h:217-236: the instance desc with WorldToObject, ObjectToWorld, the original instance index).
+namespace {
+struct Mat34 { float m[3][4]; };
+// mul(float3x4, float4): one dot product per row, left to right (the pin of the primitive load's transform)
+inline f3 mul_point(const Mat34& a, f3 p, float w) {
+    return mk3(((a.m[0][0] * p.x + a.m[0][1] * p.y) + a.m[0][2] * p.z) + a.m[0][3] * w,
+               ((a.m[1][0] * p.x + a.m[1][1] * p.y) + a.m[1][2] * p.z) + a.m[1][3] * w,
+               ((a.m[2][0] * p.x + a.m[2][1] * p.y) + a.m[2][2] * p.z) + a.m[2][3] * w);
+}
+// Determinant, RayTracingHelper.hlsli:287-295 (left to right)
+inline float determinant(const Mat34& t) {
+    return ((((t.m[0][0] * t.m[1][1] * t.m[2][2] -
+               t.m[0][0] * t.m[2][1] * t.m[1][2]) -
+              t.m[1][0] * t.m[0][1] * t.m[2][2]) +
+             t.m[1][0] * t.m[2][1] * t.m[0][2]) +
+            t.m[2][0] * t.m[0][1] * t.m[1][2]) -
+           t.m[2][0] * t.m[1][1] * t.m[0][2];
+}
+// InverseAffineTransform, RayTracingHelper.hlsli:297-316, term by term (the 0.0f / 1.0f factors of the implicit fourth
+// row stay in the text: they only matter for the sign of zeros and for non-finite entries)
+inline Mat34 inverse_affine(const Mat34& a) {
+    const float (*t)[4] = a.m;
+    const float invDet = 1.0f / determinant(a);
+    Mat34 r;
+    r.m[0][0] = invDet * ((t[1][1] * (t[2][2] * 1.0f - 0.0f * t[2][3]) + t[2][1] * (0.0f * t[1][3] - t[1][2] * 1.0f)) + 0.0f * (t[1][2] * t[2][3] - t[2][2] * t[1][3]));
+    r.m[1][0] = invDet * ((t[1][2] * (t[2][0] * 1.0f - 0.0f * t[2][3]) + t[2][2] * (0.0f * t[1][3] - t[1][0] * 1.0f)) + 0.0f * (t[1][0] * t[2][3] - t[2][0] * t[1][3]));
+    r.m[2][0] = invDet * ((t[1][3] * (t[2][0] * 0.0f - 0.0f * t[2][1]) + t[2][3] * (0.0f * t[1][1] - t[1][0] * 0.0f)) + 1.0f * (t[1][0] * t[2][1] - t[2][0] * t[1][1]));
+    r.m[0][1] = invDet * ((t[2][1] * (t[0][2] * 1.0f - 0.0f * t[0][3]) + 0.0f * (t[2][2] * t[0][3] - t[0][2] * t[2][3])) + t[0][1] * (0.0f * t[2][3] - t[2][2] * 1.0f));
+    r.m[1][1] = invDet * ((t[2][2] * (t[0][0] * 1.0f - 0.0f * t[0][3]) + 0.0f * (t[2][0] * t[0][3] - t[0][0] * t[2][3])) + t[0][2] * (0.0f * t[2][3] - t[2][0] * 1.0f));
+    r.m[2][1] = invDet * ((t[2][3] * (t[0][0] * 0.0f - 0.0f * t[0][1]) + 1.0f * (t[2][0] * t[0][1] - t[0][0] * t[2][1])) + t[0][3] * (0.0f * t[2][1] - t[2][0] * 0.0f));
+    r.m[0][2] = invDet * ((0.0f * (t[0][2] * t[1][3] - t[1][2] * t[0][3]) + t[0][1] * (t[1][2] * 1.0f - 0.0f * t[1][3])) + t[1][1] * (0.0f * t[0][3] - t[0][2] * 1.0f));
+    r.m[1][2] = invDet * ((0.0f * (t[0][0] * t[1][3] - t[1][0] * t[0][3]) + t[0][2] * (t[1][0] * 1.0f - 0.0f * t[1][3])) + t[1][2] * (0.0f * t[0][3] - t[0][0] * 1.0f));
+    r.m[2][2] = invDet * ((1.0f * (t[0][0] * t[1][1] - t[1][0] * t[0][1]) + t[0][3] * (t[1][0] * 0.0f - 0.0f * t[1][1])) + t[1][3] * (0.0f * t[0][1] - t[0][0] * 0.0f));
+    r.m[0][3] = invDet * ((t[0][1] * (t[2][2] * t[1][3] - t[1][2] * t[2][3]) + t[1][1] * (t[0][2] * t[2][3] - t[2][2] * t[0][3])) + t[2][1] * (t[1][2] * t[0][3] - t[0][2] * t[1][3]));
+    r.m[1][3] = invDet * ((t[0][2] * (t[2][0] * t[1][3] - t[1][0] * t[2][3]) + t[1][2] * (t[0][0] * t[2][3] - t[2][0] * t[0][3])) + t[2][2] * (t[1][0] * t[0][3] - t[0][0] * t[1][3]));
+    r.m[2][3] = invDet * ((t[0][3] * (t[2][0] * t[1][1] - t[1][0] * t[2][1]) + t[1][3] * (t[0][0] * t[2][1] - t[2][0] * t[0][1])) + t[2][3] * (t[1][0] * t[0][1] - t[0][0] * t[1][1]));
+    return r;
+}
+// TransformAABB, RayTracingHelper.hlsli:318-344 (min / max are order independent)
+inline Box transform_aabb(const Box& b, const Mat34& m) {
+    Box r{mk3(FLT_MAX), mk3(-FLT_MAX)};
+    for (int i = 0; i < 8; i++) {
+        f3 v = mul_point(m, mk3((i & 4) ? b.mx.x : b.mn.x, (i & 2) ? b.mx.y : b.mn.y, (i & 1) ? b.mx.z : b.mn.z), 1.0f);
+        r.mn = min3(r.mn, v); r.mx = max3(r.mx, v);
+    }
+    return r;
+}
+// the world-space box of an instance: bottom-level root (centre / half -> min / max), transformed, back to centre / half
+inline void instance_box(const uint8_t* blas, const Mat34& objectToWorld, f3& c, f3& h) {
+    const AABBNode& root = *(const AABBNode*)(blas + 16);
+    f3 rc = mk3(root.c[0], root.c[1], root.c[2]), rh = mk3(root.h[0], root.h[1], root.h[2]);
+    Box w = transform_aabb(Box{rc - rh, rc + rh}, objectToWorld); // BoundingBoxToAABB :237-243
+    c = (w.mn + w.mx) * 0.5f;                                     // AABBtoBoundingBox :229-235
+    h = w.mx - c;
+}
+} // namespace
+
+bool build_tlas(const TbInstanceDesc* inst, uint32_t n, const std::vector<const uint8_t*>& blas, std::vector<uint8_t>& out, std::string& err) {
+    if (n == 0) { err = "no instances"; return false; }
+    struct MetaRec { float worldToObject[12]; uint32_t idAndMask, contribAndFlags, asLo, asHi; float objectToWorld[12]; uint32_t instanceIndex; };
+    static_assert(sizeof(MetaRec) == 116, "BVHMetadata is 116 bytes");
+    std::vector<AABBNode> leaf(n);
+    std::vector<MetaRec> meta(n);
+    for (uint32_t i = 0; i < n; i++) {
+        if (inst[i].AccelerationStructure >= blas.size()) { err = "instance references a bottom-level structure that does not exist"; return false; }
+        Mat34 o2w;
+        memcpy(o2w.m, inst[i].Transform, 48);
+        Mat34 w2o = inverse_affine(o2w);
+        f3 c, h;
+        instance_box(blas[inst[i].AccelerationStructure], o2w, c, h);
+        leaf[i] = AABBNode{{c.x, c.y, c.z}, kLeafFlag | i, {h.x, h.y, h.z}, 0};
+        MetaRec& m = meta[i];
+        memcpy(m.worldToObject, w2o.m, 48);
+        m.idAndMask = inst[i].InstanceIDAndMask; m.contribAndFlags = inst[i].InstanceContributionToHitGroupIndexAndFlags;
+        m.asLo = (uint32_t)inst[i].AccelerationStructure; m.asHi = (uint32_t)(inst[i].AccelerationStructure >> 32);
+        memcpy(m.objectToWorld, o2w.m, 48);
+        m.instanceIndex = i;
+    }
+    f3 smin = mk3(FLT_MAX), smax = mk3(-FLT_MAX);
+    for (uint32_t i = 0; i < n; i++) { // CalculateSceneAABBFromBVHs.hlsl: RawDataToAABB of the stored box
+        f3 c = mk3(leaf[i].c[0], leaf[i].c[1], leaf[i].c[2]), h = mk3(leaf[i].h[0], leaf[i].h[1], leaf[i].h[2]);
+        smin = min3(c - h, smin); smax = max3(c + h, smax);
+    }
+    std::vector<uint32_t> codes(n), order(n);
+    for (uint32_t i = 0; i < n; i++) { codes[i] = morton_code(mk3(leaf[i].c[0], leaf[i].c[1], leaf[i].c[2]), smin, smax); order[i] = i; }
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return sorts_before(codes[a], a, codes[b], b); });
+    std::vector<uint32_t> sc(n);
+    std::vector<MetaRec> sm(n);
+    for (uint32_t i = 0; i < n; i++) { sc[i] = codes[order[i]]; sm[i] = meta[order[i]]; }
+    const uint32_t nInternal = n - 1, total = 2 * n - 1;
+    std::vector<HNode> H(total, HNode{0xffffffffu, 0, 0});
+    if (n > 1) {
+        Karras K{sc.data(), n};
+        for (uint32_t idx = 0; idx < nInternal; idx++) {
+            uint32_t first, last;
+            K.range(idx, first, last);
+            uint32_t split = K.split(first, last);
+            uint32_t a = (split == first) ? nInternal + split : split;
+            uint32_t b = (split + 1 == last) ? nInternal + split + 1 : split + 1;
+            H[idx].left = a; H[idx].right = b; H[a].parent = idx; H[b].parent = idx;
+        }
+    }
+    const uint32_t offBoxes = 16, offMeta = offBoxes + 32 * total, totalSize = offMeta + 116 * n;
+    out.assign(totalSize, 0);
+    uint32_t header[4] = {offBoxes, 0, offMeta, totalSize};
+    memcpy(out.data(), header, 16);
+    AABBNode* nodes = (AABBNode*)(out.data() + offBoxes);
+    memcpy(out.data() + offMeta, sm.data(), 116ull * n);
+    for (uint32_t i = 0; i < n; i++) { // TopLevelComputeAABBs.hlsl ComputeLeafAABB: from the metadata of the sorted leaf
+        Mat34 o2w;
+        memcpy(o2w.m, sm[i].objectToWorld, 48);
+        f3 c, h;
+        instance_box(blas[sm[i].asLo], o2w, c, h);
+        nodes[nInternal + i] = AABBNode{{c.x, c.y, c.z}, i | kLeafFlag, {h.x, h.y, h.z}, 1};
+    }
+    if (n > 1) {
+        std::vector<uint32_t> cnt(total, 1);
+        std::vector<std::pair<uint32_t, int>> st;
+        st.push_back({0, 0});
+        while (!st.empty()) {
+            auto& top = st.back();
+            uint32_t node = top.first;
+            if (node >= nInternal) { st.pop_back(); continue; }
+            if (top.second == 0) { top.second = 1; st.push_back({H[node].left, 0}); }
+            else if (top.second == 1) { top.second = 2; st.push_back({H[node].right, 0}); }
+            else {
+                uint32_t l = H[node].left, r = H[node].right;
+                if (cnt[l] > cnt[r]) std::swap(l, r);
+                cnt[node] = cnt[l] + cnt[r];
+                f3 c, h;
+                parent_box(mk3(nodes[l].c[0], nodes[l].c[1], nodes[l].c[2]), mk3(nodes[l].h[0], nodes[l].h[1], nodes[l].h[2]),
+                           mk3(nodes[r].c[0], nodes[r].c[1], nodes[r].c[2]), mk3(nodes[r].h[0], nodes[r].h[1], nodes[r].h[2]), c, h);
+                nodes[node] = AABBNode{{c.x, c.y, c.z}, l & 0x3fffffffu, {h.x, h.y, h.z}, r};
+                st.pop_back();
+            }
+        }
+    }
+    return true;
+}
+// test hooks: the pure functions of the instance load
+void inverse_affine_public(const float* m12, float* out12) { Mat34 a; memcpy(a.m, m12, 48); Mat34 r = inverse_affine(a); memcpy(out12, r.m, 48); }
+void transform_aabb_public(const float* mn, const float* mx, const float* m12, float* out6) {
+    Mat34 a; memcpy(a.m, m12, 48);
+    Box r = transform_aabb(Box{mk3(mn[0], mn[1], mn[2]), mk3(mx[0], mx[1], mx[2])}, a);
+    out6[0] = r.mn.x; out6[1] = r.mn.y; out6[2] = r.mn.z; out6[3] = r.mx.x; out6[4] = r.mx.y; out6[5] = r.mx.z;
+}
+
 } // namespace oracle

@@ -149,6 +149,24 @@ ORACLE_API void oracle_treelet(uint32_t* H3, float* aabb6, uint32_t n, uint32_t 
 ORACLE_API void oracle_load_primitives(OracleHandle* h, void* prims40, void* meta12) { oracle::load_primitives_public(h->scene, prims40, meta12); }
 ORACLE_API const void* oracle_scene_positions(OracleHandle* h) { return h->scene.positions.data(); }
 ORACLE_API uint64_t oracle_scene_num_positions(OracleHandle* h) { return h->scene.positions.size(); }
+// Top-level structure over reference-layout bottom-level byte buffers: blas[i] / blasBytes[i]; instance desc field
+// AccelerationStructure = index into that list. Two calls: size query (out == nullptr), then the bytes.
+ORACLE_API int64_t oracle_build_tlas(const TbInstanceDesc* inst, uint32_t n, const uint8_t* const* blas, uint32_t numBlas, uint8_t* out, uint64_t cap) {
+    std::vector<const uint8_t*> list(blas, blas + numBlas);
+    std::vector<uint8_t> bytes;
+    std::string err;
+    if (!oracle::build_tlas(inst, n, list, bytes, err)) return -1;
+    if (out) { if (cap < bytes.size()) return -2; memcpy(out, bytes.data(), bytes.size()); }
+    return (int64_t)bytes.size();
+}
+ORACLE_API int oracle_trace_rays_tlas(const uint8_t* tlas, const uint8_t* const* blas, uint32_t numBlas, const TbRay* rays, uint64_t n, TbHit* hits) {
+    std::vector<const uint8_t*> list(blas, blas + numBlas);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < (int64_t)n; i++) oracle::trace_ray_tlas(tlas, list, rays[i], hits[i]);
+    return 0;
+}
+ORACLE_API void oracle_inverse_affine(const float* m12, float* out12) { oracle::inverse_affine_public(m12, out12); }
+ORACLE_API void oracle_transform_aabb(const float* mn, const float* mx, const float* m12, float* out6) { oracle::transform_aabb_public(mn, mx, m12, out6); }
 // PERFORM_UPDATE: replace the scene's vertex positions (same count) and refit the acceleration structure
 ORACLE_API int oracle_update_bvh(OracleHandle* h, const float* positions, uint64_t count) {
     if (!positions || count != h->scene.positions.size()) { h->err = "position count differs from the scene's"; return -1; }

@@ -78,6 +78,12 @@ bool update_bvh(Scene& s, std::string& err);
 
 // SoftwareRayQuery::TraceRayInline + Proceed (TraverseFunction.hlsli:537-785), FAST_PATH.
 void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit);
+// Top-level acceleration structure over instances of bottom-level structures (reference-layout bytes; an instance's
+// AccelerationStructure field is an index into `blas`) and the two-level query (FAST_PATH 0).
+bool build_tlas(const TbInstanceDesc* inst, uint32_t n, const std::vector<const uint8_t*>& blas, std::vector<uint8_t>& out, std::string& err);
+void trace_ray_tlas(const uint8_t* tlas, const std::vector<const uint8_t*>& blas, const TbRay& ray, TbHit& hit);
+void inverse_affine_public(const float* m12, float* out12);
+void transform_aabb_public(const float* mn, const float* mx, const float* m12, float* out6);
 // test hook: evaluate GetRayData's rcp literally (inf for zero components) instead of the clamped form
 void set_visit_log(std::vector<uint8_t>* log); // analysis hook: per-thread log of node visits (0 internal, 1 leaf)
 void set_literal_rcp(bool on);

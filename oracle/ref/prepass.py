@@ -306,6 +306,22 @@ def run_refit(helper_hlsli, prepare_hlsl, bottom_hlsl, compute_hlsli, dst_prepar
     open(dst_compute, "w").write(fix(helper + "\n" + leaf + "\n" + comp))
 
 
+def run_tlas(helper_hlsli, dst):
+    """The arithmetic of the top-level instance load (RayTracingHelper.hlsli): AABBtoBoundingBox, BoundingBoxToAABB,
+    Determinant, InverseAffineTransform, TransformAABB. float4(...) constructors become make4(...) overloads."""
+    h = open(helper_hlsli).read()
+    boxes = h[h.index("BoundingBox AABBtoBoundingBox(AABB aabb)"):h.index("AABB RawDataToAABB(int4 a, int4 b)")]
+    affine = h[h.index("float Determinant(in AffineMatrix transform)"):h.index("static const uint OffsetToAnyHitStateId")]
+    text = boxes + "\n" + affine
+    text = re.sub(r"\bin\s+([A-Za-z_]\w*)\s+([A-Za-z_]\w*)", r"\1 \2", text)
+    text = re.sub(r"\.(xyz|xy|yz)\b(?!\s*\()", r".\1()", text)
+    text = text.replace("float4 boxVertices[verticesPerAABB];", "@@DECL@@")
+    text = re.sub(r"\bfloat4\(", "make4(", text).replace("@@DECL@@", "float4 boxVertices[verticesPerAABB];")
+    if "InverseAffineTransform" not in text or "TransformAABB" not in text:
+        raise SystemExit("prepass: top-level helpers not found")
+    open(dst, "w").write(text)
+
+
 def run_treelet_pass(bindings_h, treelet_hlsl, clear_hlsl, find_hlsl, helper_hlsli, compat_h, dst):
     """One whole treelet-reorder pass: TreeletReorderBindings.h tables and helpers, RawDataToTriangle / GetTriangle
     (RayTracingHlslCompat.h), the box helpers of RayTracingHelper.hlsli, ClearBuffers.hlsl main(), FindTreelets.hlsl

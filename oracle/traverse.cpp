@@ -178,6 +178,119 @@ void trace_ray(const Scene& s, const TbRay& ray, TbHit& hit) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Two-level ray query: Traverse with FAST_PATH 0 (TraverseFunction.hlsli:537-785). The top-level tree is walked with the
+// world-space ray; at an instance leaf (:603-638) whose mask passes, the ray is taken to object space with the stored
+// WorldToObject (origin as a point, direction as a vector: t keeps its meaning), GetRayData is redone for it, and the
+// instance's bottom-level tree is walked from its root WITHOUT a root box test (the instance's world box stood for it)
+// until it is exhausted; then the walk returns to the top level with the world-space ray data (:770-774). One
+// committed t, both counters run across the levels. D3 extends to (instance, geometry, primitive): on exactly equal t
+// the lower triple wins. D6 / D7 apply to each level's ray as in the single-level query.
+namespace {
+struct RayData { f3 org, inv, oinv, shear; int kx, ky, kz, zmask; };
+inline RayData ray_data(f3 org, f3 dir) {
+    RayData r;
+    r.org = org;
+    r.inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+    r.zmask = g_literalRcp ? 0 : ((dir.x == 0.0f ? 1 : 0) | (dir.y == 0.0f ? 2 : 0) | (dir.z == 0.0f ? 4 : 0));
+    r.oinv = org * r.inv;
+    f3 ad = abs3(dir);
+    r.kz = (ad.x > ad.y && ad.x > ad.z) ? 0 : (ad.y > ad.z ? 1 : 2);
+    r.kx = (r.kz + 1) % 3; r.ky = (r.kz + 2) % 3;
+    if (comp(dir, r.kz) < 0.0f) { int t = r.kx; r.kx = r.ky; r.ky = t; }
+    r.shear = mk3(comp(dir, r.kx) / comp(dir, r.kz), comp(dir, r.ky) / comp(dir, r.kz), 1.0f / comp(dir, r.kz));
+    return r;
+}
+inline bool is_nan3(f3 v) { return v.x != v.x || v.y != v.y || v.z != v.z; }
+struct TlasMeta { float worldToObject[12]; uint32_t idAndMask, contribAndFlags, asLo, asHi; float objectToWorld[12]; uint32_t instanceIndex; };
+} // namespace
+
+void trace_ray_tlas(const uint8_t* tlas, const std::vector<const uint8_t*>& blasList, const TbRay& ray, TbHit& hit) {
+    uint32_t th[4];
+    memcpy(th, tlas, 16);
+    const AABBNode* tnodes = (const AABBNode*)(tlas + th[0]);
+    const uint8_t* tmeta = tlas + th[2];
+    f3 worg = mk3(ray.Origin[0], ray.Origin[1], ray.Origin[2]), wdir = mk3(ray.Direction[0], ray.Direction[1], ray.Direction[2]);
+    hit.TrianglesTested = hit.BoxesTested = 0; hit.InstanceIndex = 0;
+    hit.t = -1.0f; hit.b1 = hit.b2 = 0; hit.PrimitiveIndex = hit.GeometryIndex = 0xffffffffu;
+    if (!g_literalNaN && (is_nan3(worg) || is_nan3(wdir))) return; // D7
+    const RayData W = ray_data(worg, wdir);
+    float committedT = ray.TMax;
+    bool haveHit = false;
+    uint32_t hitInst = 0, hitGeom = 0, hitPrim = 0;
+    float hb1 = 0, hb2 = 0;
+    uint32_t trisTested = 0, boxesTested = 0;
+    std::vector<uint32_t> tstack, bstack;
+    float unusedT;
+    if (ray_box(unusedT, committedT, W.org, W.zmask, W.oinv, W.inv, tnodes[0])) tstack.push_back(0);
+    while (!tstack.empty()) {
+        const uint32_t ni = tstack.back();
+        tstack.pop_back();
+        const AABBNode& nd = tnodes[ni];
+        if (nd.flags & 0x80000000u) {
+            TlasMeta m;
+            memcpy(&m, tmeta + 116 * (size_t)(nd.flags & 0x3fffffffu), 116);
+            if (((m.idAndMask >> 24) & 0xffu) == 0) continue; // GetInstanceMask & InstanceInclusionMask (~0)
+            const float* w = m.worldToObject;
+            f3 oorg = mk3(((w[0] * worg.x + w[1] * worg.y) + w[2] * worg.z) + w[3] * 1.0f,
+                          ((w[4] * worg.x + w[5] * worg.y) + w[6] * worg.z) + w[7] * 1.0f,
+                          ((w[8] * worg.x + w[9] * worg.y) + w[10] * worg.z) + w[11] * 1.0f);
+            f3 odir = mk3(((w[0] * wdir.x + w[1] * wdir.y) + w[2] * wdir.z) + w[3] * 0.0f,
+                          ((w[4] * wdir.x + w[5] * wdir.y) + w[6] * wdir.z) + w[7] * 0.0f,
+                          ((w[8] * wdir.x + w[9] * wdir.y) + w[10] * wdir.z) + w[11] * 0.0f);
+            if (!g_literalNaN && (is_nan3(oorg) || is_nan3(odir))) continue; // D7 for the object-space ray
+            const RayData O = ray_data(oorg, odir);
+            const uint8_t* blas = blasList[m.asLo];
+            uint32_t bh[4];
+            memcpy(bh, blas, 16);
+            const AABBNode* nodes = (const AABBNode*)(blas + bh[0]);
+            const uint8_t* prims = blas + bh[1];
+            const uint32_t* meta = (const uint32_t*)(blas + bh[2]);
+            bstack.clear();
+            bstack.push_back(0); // :621 StackPush(0): no box test of the bottom-level root
+            while (!bstack.empty()) {
+                const uint32_t bi = bstack.back();
+                bstack.pop_back();
+                const AABBNode& bn = nodes[bi];
+                if (bn.flags & 0x80000000u) {
+                    const uint32_t leaf = bn.flags & 0x3fffffffu;
+                    const uint32_t* pm = meta + 3 * (size_t)leaf;
+                    trisTested++;
+                    float t0 = committedT, b1, b2;
+                    const bool ok = ray_tri(t0, b1, b2, O.org, O.kx, O.ky, O.kz, O.shear, (const float*)(prims + 40 * (size_t)leaf + 4));
+                    const bool closer = t0 < committedT;
+                    const bool lower = m.instanceIndex < hitInst || (m.instanceIndex == hitInst && (pm[0] < hitGeom || (pm[0] == hitGeom && pm[1] < hitPrim)));
+                    const bool tie = haveHit && t0 == committedT && lower;
+                    if (ok && (closer || tie) && t0 > ray.TMin) {
+                        committedT = t0; hb1 = b1; hb2 = b2; hitInst = m.instanceIndex; hitGeom = pm[0]; hitPrim = pm[1]; haveHit = true;
+                    }
+                } else {
+                    const uint32_t l = bn.flags & 0x3fffffffu, r = bn.right;
+                    float lt, rt;
+                    const bool lh = ray_box(lt, committedT, O.org, O.zmask, O.oinv, O.inv, nodes[l]);
+                    const bool rh = ray_box(rt, committedT, O.org, O.zmask, O.oinv, O.inv, nodes[r]);
+                    boxesTested += 2;
+                    if (lh && rh) { const bool rightFirst = rt < lt; bstack.push_back(rightFirst ? l : r); bstack.push_back(rightFirst ? r : l); }
+                    else if (lh || rh) bstack.push_back(rh ? r : l);
+                }
+            }
+        } else {
+            const uint32_t l = nd.flags & 0x3fffffffu, r = nd.right;
+            float lt, rt;
+            const bool lh = ray_box(lt, committedT, W.org, W.zmask, W.oinv, W.inv, tnodes[l]);
+            const bool rh = ray_box(rt, committedT, W.org, W.zmask, W.oinv, W.inv, tnodes[r]);
+            boxesTested += 2;
+            if (lh && rh) { const bool rightFirst = rt < lt; tstack.push_back(rightFirst ? l : r); tstack.push_back(rightFirst ? r : l); }
+            else if (lh || rh) tstack.push_back(rh ? r : l);
+        }
+    }
+    hit.TrianglesTested = trisTested;
+    hit.BoxesTested = boxesTested;
+    if (haveHit && committedT < ray.TMax) {
+        hit.t = committedT; hit.b1 = hb1; hit.b2 = hb2; hit.PrimitiveIndex = hitPrim; hit.GeometryIndex = hitGeom; hit.InstanceIndex = hitInst;
+    }
+}
+
 } // namespace oracle
 
 // ---- test hooks: the three pure functions of the ray query, so that tests can compare them with the reference's

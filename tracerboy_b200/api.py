@@ -119,6 +119,12 @@ class GeometryDesc(C.Structure):
                 ("Transform3x4", C.c_void_p), ("GeometryFlags", C.c_uint32)]
 
 
+class InstanceDesc(C.Structure):
+    """D3D12_RAYTRACING_INSTANCE_DESC (64 bytes)."""
+    _fields_ = [("Transform", C.c_float * 12), ("InstanceIDAndMask", C.c_uint32),
+                ("InstanceContributionToHitGroupIndexAndFlags", C.c_uint32), ("AccelerationStructure", C.c_uint64)]
+
+
 class PrebuildInfo(C.Structure):
     _fields_ = [("ResultDataMaxSizeInBytes", C.c_uint64), ("ScratchDataSizeInBytes", C.c_uint64),
                 ("UpdateScratchDataSizeInBytes", C.c_uint64), ("ReferenceLayoutSizeInBytes", C.c_uint64)]

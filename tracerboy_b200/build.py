@@ -305,6 +305,7 @@ def build_all(force=False, verbose=False):
     build_ref.build_refit(force)
     build_ref.build_load(force)
     build_ref.build_treelet_pass(force)
+    build_ref.build_tlas(force)
 
 
 if __name__ == "__main__":
