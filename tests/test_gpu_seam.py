@@ -234,3 +234,92 @@ def test_update_in_place_equals_the_oracles_update(tmp_path, built):
     with pytest.raises(tb.TracerBoyError):
         d2 = _descs([dict(pos=pos, idx=quads[:-5])], keep)
         g.UpdateRaytracingAccelerationStructureDevice(d2, 1, dst.data_ptr(), dst.numel(), None, 0, None)
+
+
+def test_two_level_structure_and_query_equal_the_oracle(tmp_path, built):
+    """Top-level acceleration structure over instances of three caller-owned bottom-level structures:
+    the reference-layout bytes of the top level (header, nodes, 116-byte BVHMetadata per sorted leaf: inverse transform,
+    object-to-world, original index) equal the oracle's, except for the 8-byte AccelerationStructure field (a device
+    address here, an index there); 100 k two-level ray queries equal the oracle's in every field, InstanceIndex and both
+    counters included. Mirrored / scaled / rotated instances, one instance masked out, one bottom level of a single triangle."""
+    import torch
+    import tracerboy_b200 as tb
+    from oracle.binding import Oracle
+    from tracerboy_b200.api import RAY_DTYPE, HIT_DTYPE, InstanceDesc
+    from test_cpu_tlas import _rand_affine, oracle_tlas, oracle_trace_tlas
+    rng = np.random.default_rng(31)
+    g = tb.TracerBoy(0)
+    meshes = []
+    for k, (nv, nt) in enumerate(((400, 900), (150, 260), (3, 1))):
+        pos = rng.uniform(-1, 1, (nv, 3)).astype(np.float32) * (1.0 + k)
+        idx = rng.integers(0, nv, (nt, 3)).astype(np.uint32) if nt > 1 else np.array([[0, 1, 2]], np.uint32)
+        meshes.append((pos, idx))
+    keep, blas_dev, blas_bytes = [], [], []
+    for k, (pos, idx) in enumerate(meshes):
+        # oracle's bytes of the same bottom level: host-pointer build + .tbscene + oracle build
+        h = tb.TracerBoy(0)
+        h.BuildRaytracingAccelerationStructure([(pos, idx)])
+        p = str(tmp_path / ("b%d.tbscene" % k))
+        h.SaveScene(p)
+        o = Oracle(); o.LoadScene(p, 3)
+        blas_bytes.append(np.ascontiguousarray(o.GetBVH()))
+        d = _descs([dict(pos=pos, idx=idx)], keep)
+        info = tb.prebuild_info(d, 1)
+        dst = torch.zeros(info.ResultDataMaxSizeInBytes, dtype=torch.uint8, device="cuda")
+        g.BuildRaytracingAccelerationStructureDevice(d, 1, dst.data_ptr(), dst.numel(), None, 0, None)
+        assert np.array_equal(dst[:info.ReferenceLayoutSizeInBytes].cpu().numpy(), blas_bytes[-1])
+        blas_dev.append(dst)
+    n = 60
+    mats = _rand_affine(rng, n)
+    mats[:, :, 3] = rng.uniform(-25, 25, (n, 3))
+    inst_gpu, inst_cpu = (InstanceDesc * n)(), (InstanceDesc * n)()
+    for i in range(n):
+        for arr in (inst_gpu, inst_cpu):
+            for j in range(12):
+                arr[i].Transform[j] = float(mats[i].reshape(-1)[j])
+            arr[i].InstanceIDAndMask = (500 + i) | ((0 if i == 11 else 0xff) << 24)
+            arr[i].InstanceContributionToHitGroupIndexAndFlags = 2 * i
+        inst_gpu[i].AccelerationStructure = blas_dev[i % 3].data_ptr()
+        inst_cpu[i].AccelerationStructure = i % 3
+    tinfo = tb.tlas_prebuild_info(n)
+    assert tinfo.ReferenceLayoutSizeInBytes == 16 + 32 * (2 * n - 1) + 116 * n and tinfo.ScratchDataSizeInBytes == 0
+    tlas = torch.zeros(tinfo.ResultDataMaxSizeInBytes, dtype=torch.uint8, device="cuda")
+    g.BuildTopLevelAccelerationStructureDevice(inst_gpu, n, tlas.data_ptr(), tlas.numel(), None)
+    want, arr = oracle_tlas(blas_bytes, inst_cpu, n)
+    got = tlas[:tinfo.ReferenceLayoutSizeInBytes].cpu().numpy()
+    off_meta = 16 + 32 * (2 * n - 1)
+    gm, wm = got[off_meta:].reshape(n, 116).copy(), want[off_meta:].reshape(n, 116).copy()
+    ptrs = gm[:, 56:64].copy().view(np.uint64).reshape(-1)
+    assert [int(p) for p in ptrs] == [blas_dev[int(i) % 3].data_ptr() for i in gm[:, 112:116].view(np.uint32).reshape(-1)]
+    gm[:, 56:64] = 0; wm[:, 56:64] = 0
+    assert np.array_equal(got[:off_meta], want[:off_meta]), "header / nodes"
+    assert np.array_equal(gm, wm), "instance metadata"
+    R = 100000
+    rays = np.zeros(R, RAY_DTYPE)
+    rays["Origin"] = rng.uniform(-40, 40, (R, 3))
+    tgt = mats[rng.integers(0, n, R), :, 3] + rng.normal(0, 1.5, (R, 3))
+    dd = tgt - rays["Origin"]
+    rays["Direction"] = dd / np.linalg.norm(dd, axis=1, keepdims=True)
+    rays["Direction"][::97, 1] = 0.0           # exactly-zero components (D6) ...
+    rays["Direction"][5::1013] = np.nan        # ... and NaN rays (D7)
+    rays["TMin"] = 0.001; rays["TMax"] = 999999.0
+    rays["TMax"][::50] = 20.0
+    d_rays = torch.from_numpy(rays.view(np.uint8)).cuda()
+    d_hits = torch.zeros(R * 32, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.Stream()
+    g.TraceRaysTopLevelDevice(tlas.data_ptr(), tlas.numel(), d_rays.data_ptr(), R, d_hits.data_ptr(), stream.cuda_stream)
+    stream.synchronize()
+    hg, ho = d_hits.cpu().numpy().view(HIT_DTYPE), oracle_trace_tlas(want, arr, 3, rays)
+    for f in hg.dtype.names:
+        same = hg[f].view(np.uint32) == ho[f].view(np.uint32)
+        assert same.all(), "field %s differs for %d rays, first %d" % (f, (~same).sum(), np.flatnonzero(~same)[0])
+    hit = hg["t"] > 0
+    assert hit.mean() > 0.2 and len(np.unique(hg["InstanceIndex"][hit])) > 30 and not (hg["InstanceIndex"][hit] == 11).any()
+    # another handle recognises the structure from its own bytes
+    k = tb.TracerBoy(0)
+    d_hits.zero_()
+    k.TraceRaysTopLevelDevice(tlas.data_ptr(), tlas.numel(), d_rays.data_ptr(), R, d_hits.data_ptr(), None)
+    k.Synchronize()
+    assert np.array_equal(d_hits.cpu().numpy().view(HIT_DTYPE)["t"].view(np.uint32), ho["t"].view(np.uint32))
+    with pytest.raises(tb.TracerBoyError):
+        g.BuildTopLevelAccelerationStructureDevice(inst_gpu, n, tlas.data_ptr(), 1000, None)

@@ -199,6 +199,8 @@ def load_library():
         "tb_bvh_build_device": [vp, C.POINTER(GeometryDesc), u32, u32, vp, u64, vp, u64, vp],
         "tb_trace_rays_device": [vp, vp, u64, vp, u64, vp, vp], "tb_bvh_forget_device": [vp, vp],
         "tb_bvh_update_device": [vp, C.POINTER(GeometryDesc), u32, vp, u64, vp, u64, vp],
+        "tb_tlas_prebuild_info": [u32, C.POINTER(PrebuildInfo)], "tb_tlas_build_device": [vp, C.POINTER(InstanceDesc), u32, u32, vp, u64, vp],
+        "tb_trace_rays_tlas_device": [vp, vp, u64, vp, u64, vp, vp],
         "tb_get_bvh_depth": [vp, C.POINTER(u32)],
         "tb_comm_get_unique_id": [vp, u64], "tb_comm_init": [vp, vp, i32, i32, u32], "tb_comm_destroy": [vp],
         "tb_comm_info": [vp, C.POINTER(CommInfo)], "tb_comm_reduce": [vp],
@@ -227,7 +229,7 @@ EXPORTED_SYMBOLS = ["tb_create", "tb_destroy", "tb_last_error", "tb_version", "t
                     "tb_get_material", "tb_set_material", "tb_bvh_prebuild_info", "tb_bvh_build", "tb_trace_rays",
                     "tb_get_default_postprocess_settings", "tb_postprocess", "tb_postprocess_image",
                     "tb_temporal_accumulate_image", "tb_save_image", "tb_write_image", "tb_update", "tb_camera_update", "tb_set_ray_sort",
-                    "tb_set_material_sort", "tb_load_image_file", "tb_max_triangles", "tb_bvh_build_device", "tb_trace_rays_device", "tb_bvh_forget_device", "tb_bvh_update_device", "tb_get_bvh_depth",
+                    "tb_set_material_sort", "tb_load_image_file", "tb_max_triangles", "tb_bvh_build_device", "tb_trace_rays_device", "tb_bvh_forget_device", "tb_bvh_update_device", "tb_tlas_prebuild_info", "tb_tlas_build_device", "tb_trace_rays_tlas_device", "tb_get_bvh_depth",
                     "tb_comm_get_unique_id", "tb_comm_init", "tb_comm_destroy", "tb_comm_info", "tb_comm_reduce"]
 
 
@@ -315,6 +317,14 @@ def load_image_file(path):
     if rc != 0:
         raise TracerBoyError(rc, err.value.decode())
     return out, fmt.value, bool(alpha.value)
+
+
+def tlas_prebuild_info(n):
+    info = PrebuildInfo()
+    rc = load_library().tb_tlas_prebuild_info(n, C.byref(info))
+    if rc != 0:
+        raise TracerBoyError(rc, "tb_tlas_prebuild_info")
+    return info
 
 
 def convert_scene(src, dst):
@@ -426,6 +436,14 @@ class TracerBoy:
     def UpdateRaytracingAccelerationStructureDevice(self, descs, n, dst, dst_bytes, scratch=None, scratch_bytes=0, stream=None):
         """PERFORM_UPDATE: refit a caller-owned acceleration structure to moved vertices (same topology), in place."""
         self._ck(self._lib.tb_bvh_update_device(self._h, descs, n, dst, dst_bytes, scratch, scratch_bytes, stream))
+
+    def BuildTopLevelAccelerationStructureDevice(self, instances, n, dst, dst_bytes, stream=None, flags=0):
+        """TYPE_TOP_LEVEL build over a host (InstanceDesc * n) array whose AccelerationStructure fields are device
+        addresses of bottom-level structures; dst = caller-owned device memory sized by tlas_prebuild_info."""
+        self._ck(self._lib.tb_tlas_build_device(self._h, instances, n, flags, dst, dst_bytes, stream))
+
+    def TraceRaysTopLevelDevice(self, tlas, tlas_bytes, d_rays, n, d_hits, stream=None):
+        self._ck(self._lib.tb_trace_rays_tlas_device(self._h, tlas, tlas_bytes, d_rays, n, d_hits, stream))
 
     def TraceRaysDevice(self, accel, accel_bytes, d_rays, n, d_hits, stream=None):
         """n ray queries against a caller-owned acceleration structure (None: the handle's scene); device pointers,

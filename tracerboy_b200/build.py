@@ -29,7 +29,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-I" + os.path.join(ROOT, "include"), "-ccbin", GXX]
 
 CUDA_SRCS = ["csrc/cuda/bvh_build.cu", "csrc/cuda/pathtrace.cu", "csrc/cuda/postprocess.cu", "csrc/cuda/reduce.cu"]
-HOST_SRCS = ["csrc/host/api.cpp", "csrc/host/comm.cpp", "csrc/host/scene.cpp", "csrc/host/image_io.cpp", "csrc/host/image_decode.cpp"]
+HOST_SRCS = ["csrc/host/api.cpp", "csrc/host/comm.cpp", "csrc/host/scene.cpp", "csrc/host/image_io.cpp", "csrc/host/image_decode.cpp", "csrc/host/tlas.cpp"]
 HEADERS = ["csrc/cuda/device_types.h", "csrc/cuda/pathtrace.h", "csrc/cuda/traverse.cuh", "csrc/cuda/launch.h", "csrc/cuda/postprocess.h", "csrc/cuda/reduce.h", "csrc/host/handle.h",
            "csrc/common/tb_math.h", "csrc/common/tb_vec.h", "csrc/host/scene.h", "../include/tracerboy_b200.h"]
 

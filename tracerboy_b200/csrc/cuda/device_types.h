@@ -40,6 +40,18 @@ struct DeviceBvh {
     uint32_t depth = 0;          // height of the tree (0 = a single leaf): bounds the traversal stack
 };
 
+// Two-level query: one record per SORTED leaf of a top-level structure (tlas.cpp writes them behind the reference bytes)
+#define TB_TLAS_STACK_DEPTH 64
+struct TlasInstanceRecord {
+    float worldToObject[12];   // row-major 3x4 (the inverted instance transform)
+    const PairNode* pairs;     // the instance's bottom-level structure, traversal layout
+    const WideTri* tris;
+    uint32_t rootRef;          // 0 (internal root) or 0x80000000 | slot (a single-triangle bottom level)
+    uint32_t instanceIndex;    // index of the instance in the caller's array (SoftwareHitData::InstanceIndex)
+    uint32_t mask;             // InstanceMask (8 bit): 0 = never hit
+    uint32_t pad;
+};
+
 // One geometry of a build as the load kernel reads it: the caller's device buffers
 // (D3D12_RAYTRACING_GEOMETRY_TRIANGLES_DESC: vertex buffer + stride, optional 16 / 32 bit indices, optional 3x4 transform).
 struct BuildGeometry {

@@ -1384,6 +1384,81 @@ __global__ void k_trace_rays(DeviceBvh bvh, const TbRay* __restrict__ rays, uint
     }
 }
 
+// Two-level ray query (TraverseFunction.hlsli:537-785 with FAST_PATH 0), one thread per ray: the
+// top-level tree is walked on the reference's own 32-byte nodes with the world-space ray; at an instance leaf whose mask
+// passes, the ray goes to object space (origin as a point, direction as a vector, so t keeps its meaning), and the
+// instance's bottom level is walked on the traversal layout from its root without a root box test, with the t committed
+// so far. One committed t and both counters run across the levels; on exactly equal t the lower (instance, geometry,
+// primitive) triple wins (D3 extended).
+__global__ void __launch_bounds__(128) k_trace_rays_tlas(const uint8_t* __restrict__ tlas, const TlasInstanceRecord* __restrict__ records,
+                                                         const TbRay* __restrict__ rays, uint64_t n, TbHit* __restrict__ hits) {
+    const RefNode* __restrict__ tnodes = (const RefNode*)(tlas + 16);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const TbRay r = rays[i];
+        const f3 worg = mk3(r.Origin[0], r.Origin[1], r.Origin[2]), wdir = mk3(r.Direction[0], r.Direction[1], r.Direction[2]);
+        TbHit o;
+        o.t = -1.0f; o.b1 = o.b2 = 0.0f; o.PrimitiveIndex = o.GeometryIndex = 0xffffffffu; o.InstanceIndex = 0; o.TrianglesTested = o.BoxesTested = 0;
+        const bool nanRay = worg.x != worg.x || worg.y != worg.y || worg.z != worg.z || wdir.x != wdir.x || wdir.y != wdir.y || wdir.z != wdir.z;
+        if (!nanRay) { // D7
+            const f3 inv = mk3(1.0f / wdir.x, 1.0f / wdir.y, 1.0f / wdir.z), oinv = worg * inv, ainv = abs3(inv);
+            const int zmask = (wdir.x == 0.0f ? 1 : 0) | (wdir.y == 0.0f ? 2 : 0) | (wdir.z == 0.0f ? 4 : 0); // D6
+            auto box = [&](const RefNode& b, float closest) {
+                return zmask ? slab_zero(closest, worg, zmask, oinv, inv, ainv, b.c[0], b.c[1], b.c[2], b.h[0], b.h[1], b.h[2])
+                             : slab(closest, oinv, inv, ainv, b.c[0], b.c[1], b.c[2], b.h[0], b.h[1], b.h[2]);
+            };
+            float committedT = r.TMax, hb1 = 0.0f, hb2 = 0.0f;
+            bool haveHit = false;
+            uint32_t hitInst = 0, hitGeom = 0, hitPrim = 0, tris = 0, boxes = 0;
+            uint32_t tstack[TB_TLAS_STACK_DEPTH + 1];
+            int tsp = 0;
+            { const RefNode root = tnodes[0]; const SlabRange rr = box(root, committedT); if (rr.enter < rr.exit) tstack[tsp++] = 0; }
+            uint32_t stack[TB_STACK_WORDS];
+            while (tsp > 0) {
+                const RefNode nd = tnodes[tstack[--tsp]];
+                if (nd.flags & 0x80000000u) {
+                    const TlasInstanceRecord rec = records[nd.flags & 0x3fffffffu];
+                    if (rec.mask == 0) continue; // GetInstanceMask & InstanceInclusionMask
+                    const float* w = rec.worldToObject;
+                    const f3 oorg = mk3(((w[0] * worg.x + w[1] * worg.y) + w[2] * worg.z) + w[3] * 1.0f,
+                                        ((w[4] * worg.x + w[5] * worg.y) + w[6] * worg.z) + w[7] * 1.0f,
+                                        ((w[8] * worg.x + w[9] * worg.y) + w[10] * worg.z) + w[11] * 1.0f);
+                    const f3 odir = mk3(((w[0] * wdir.x + w[1] * wdir.y) + w[2] * wdir.z) + w[3] * 0.0f,
+                                        ((w[4] * wdir.x + w[5] * wdir.y) + w[6] * wdir.z) + w[7] * 0.0f,
+                                        ((w[8] * wdir.x + w[9] * wdir.y) + w[10] * wdir.z) + w[11] * 0.0f);
+                    // what an equal-t hit inside this instance has to beat: the committed triple if it is this instance's,
+                    // anything if this instance's index is lower than the committed one, nothing if it is higher
+                    uint32_t seedGeom = hitGeom, seedPrim = hitPrim;
+                    if (haveHit && rec.instanceIndex < hitInst) seedGeom = seedPrim = 0xffffffffu;
+                    else if (haveHit && rec.instanceIndex > hitInst) seedGeom = seedPrim = 0u;
+                    DeviceBvh blas;
+                    blas.root.c[0] = blas.root.c[1] = blas.root.c[2] = 0.0f; blas.root.h[0] = blas.root.h[1] = blas.root.h[2] = 0.0f; blas.root.flags = 0; blas.root.right = 0;
+                    Traversal tr;
+                    tr.begin_bottom_level(blas, rec.rootRef, stack, oorg, odir, r.TMin, r.TMax, committedT, haveHit, seedGeom, seedPrim);
+                    const float tBefore = committedT;
+                    const float4* __restrict__ pairs = (const float4*)rec.pairs;
+                    const float4* __restrict__ btris = (const float4*)rec.tris;
+                    while (!tr.done()) tr.step(stack, pairs, btris);
+                    tris += tr.trisTested; boxes += tr.boxes_tested();
+                    if (tr.haveHit && (tr.committedT != tBefore || tr.hitGeom != seedGeom || tr.hitPrim != seedPrim || !haveHit)) {
+                        committedT = tr.committedT; hb1 = tr.hb1; hb2 = tr.hb2; hitGeom = tr.hitGeom; hitPrim = tr.hitPrim; hitInst = rec.instanceIndex; haveHit = true;
+                    }
+                } else {
+                    const uint32_t l = nd.flags & 0x3fffffffu, rr = nd.right;
+                    const RefNode L = tnodes[l], R = tnodes[rr];
+                    const SlabRange a = box(L, committedT), b = box(R, committedT);
+                    boxes += 2;
+                    const bool lh = a.enter < a.exit, rh = b.enter < b.exit;
+                    if (lh && rh) { const bool rightFirst = b.enter < a.enter; tstack[tsp++] = rightFirst ? l : rr; tstack[tsp++] = rightFirst ? rr : l; }
+                    else if (lh || rh) tstack[tsp++] = rh ? rr : l;
+                }
+            }
+            o.TrianglesTested = tris; o.BoxesTested = boxes;
+            if (haveHit && committedT < r.TMax) { o.t = committedT; o.b1 = hb1; o.b2 = hb2; o.PrimitiveIndex = hitPrim; o.GeometryIndex = hitGeom; o.InstanceIndex = hitInst; }
+        }
+        hits[i] = o;
+    }
+}
+
 } // namespace
 
 // ------------------------------------------------------------------ launchers
@@ -1558,6 +1633,16 @@ cudaError_t trace_rays(const DeviceBvh& bvh, const TbRay* d_rays, uint64_t n, Tb
     if (blocks > cap) blocks = cap;
     if (blocks == 0) return cudaSuccess;
     k_trace_rays<<<(uint32_t)blocks, 128, 0, stream>>>(bvh, d_rays, n, d_hits); lc.count++;
+    return cudaGetLastError();
+}
+
+cudaError_t trace_rays_tlas(const uint8_t* tlasRef, const TlasInstanceRecord* records, uint32_t numInstances, const TbRay* d_rays, uint64_t n,
+                            TbHit* d_hits, int numSMs, cudaStream_t stream, LaunchCounter& lc) {
+    (void)numInstances;
+    uint64_t blocks = (n + 127) / 128, cap = (uint64_t)(numSMs > 0 ? numSMs : 148) * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) return cudaSuccess;
+    k_trace_rays_tlas<<<(uint32_t)blocks, 128, 0, stream>>>(tlasRef, records, d_rays, n, d_hits); lc.count++;
     return cudaGetLastError();
 }
 

@@ -132,6 +132,16 @@ struct Traversal {
         if (rootHit && !nanRay)
             cur = (bvh.root.flags & 0x80000000u) ? (0x80000000u | (bvh.root.flags & 0x3fffffffu)) : 0u;
     }
+    // The bottom level of a two-level query (TraverseFunction.hlsli:621): the walk starts at the instance's root
+    // WITHOUT a root box test (the instance's world box stood for it), with the t committed so far and the id triple
+    // `seedGeom / seedPrim` that an equal-t hit has to beat (0xffffffff: any hit wins the tie, 0 / 0: none does).
+    __device__ __forceinline__ void begin_bottom_level(const DeviceBvh& unusedRootBox, uint32_t rootRef, uint32_t* stack, tbm::f3 o, tbm::f3 dir,
+                                                       float tmin_, float tmax_, float committedSoFar, bool haveHitSoFar, uint32_t seedGeom, uint32_t seedPrim) {
+        begin(unusedRootBox, stack, o, dir, tmin_, tmax_);
+        const bool nanRay = o.x != o.x || o.y != o.y || o.z != o.z || dir.x != dir.x || dir.y != dir.y || dir.z != dir.z;
+        cur = nanRay ? TB_NO_NODE : rootRef;
+        committedT = committedSoFar; haveHit = haveHitSoFar; hitGeom = seedGeom; hitPrim = seedPrim;
+    }
     __device__ __forceinline__ bool done() const { return cur == TB_NO_NODE; }
     __device__ __forceinline__ bool at_leaf() const { return (cur & 0x80000000u) != 0; }
     __device__ __forceinline__ void pop(const uint32_t* stack) { cur = stack[sp]; --sp; } // the sentinel ends the traversal

@@ -1129,6 +1129,14 @@ TB_API int tb_trace_rays_device(TbHandle* h, const void* as, uint64_t asBytes, c
     return TB_OK;
 }
 
+namespace tbh {
+// a bottom-level structure named by an instance desc: the handle's cache, else the structure's own trailer
+int resolve_bottom_level(TbHandle* h, const void* as, cudaStream_t stream, DeviceBvh& out) {
+    if (!as) return fail(h, TB_ERR_INVALID_ARG, "instance without a bottom-level acceleration structure");
+    return resolve_as(h, as, ~0ull, stream, out);
+}
+} // namespace tbh
+
 TB_API int tb_bvh_update_device(TbHandle* h, const TbGeometryDesc* geoms, uint32_t n, void* dst, uint64_t dstBytes,
                                 void* scratch, uint64_t scratchBytes, void* cudaStream) {
     if (!h || !geoms || n == 0 || !dst) return fail(h, TB_ERR_INVALID_ARG, "null/empty argument");
@@ -1167,6 +1175,7 @@ TB_API int tb_bvh_update_device(TbHandle* h, const TbGeometryDesc* geoms, uint32
 TB_API int tb_bvh_forget_device(TbHandle* h, const void* as) {
     if (!h) return TB_ERR_INVALID_ARG;
     h->deviceBuilds.erase(as);
+    h->topLevelBuilds.erase(as);
     return TB_OK;
 }
 

@@ -80,6 +80,7 @@ struct TbHandle {
     void* buildScratch = nullptr;   // the builder's temporaries, kept between builds
     uint64_t buildScratchBytes = 0;
     std::map<const void*, DeviceBvh> deviceBuilds; // acceleration structures built into caller memory (tb_bvh_build_device)
+    std::map<const void*, uint32_t> topLevelBuilds; // top-level structures in caller memory -> number of instances
     RenderOptions options;
     double extendMs = 0.0, shadeMs = 0.0, resumeMs = 0.0;
     double bounceMs[32] = {}, bounceExtendMs[32] = {};
