@@ -1129,6 +1129,7 @@ TB_API int tb_trace_rays_device(TbHandle* h, const void* as, uint64_t asBytes, c
     return TB_OK;
 }
 
+extern "C++" {
 namespace tbh {
 // a bottom-level structure named by an instance desc: the handle's cache, else the structure's own trailer
 int resolve_bottom_level(TbHandle* h, const void* as, cudaStream_t stream, DeviceBvh& out) {
@@ -1136,6 +1137,7 @@ int resolve_bottom_level(TbHandle* h, const void* as, cudaStream_t stream, Devic
     return resolve_as(h, as, ~0ull, stream, out);
 }
 } // namespace tbh
+} // extern "C++"
 
 TB_API int tb_bvh_update_device(TbHandle* h, const TbGeometryDesc* geoms, uint32_t n, void* dst, uint64_t dstBytes,
                                 void* scratch, uint64_t scratchBytes, void* cudaStream) {

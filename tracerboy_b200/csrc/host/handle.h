@@ -28,6 +28,7 @@ struct Comm {
     uint64_t reductions = 0, bytesPerReduction = 0;
     double lastMs = 0.0, totalMs = 0.0;
 };
+int resolve_bottom_level(TbHandle* h, const void* as, cudaStream_t stream, tbd::DeviceBvh& out); // api.cpp
 void comm_release_buffers(TbHandle* h);
 void comm_destroy(TbHandle* h);
 }

@@ -124,8 +124,6 @@ TlasLayout tlas_layout(uint32_t n) {
 
 } // namespace
 
-namespace tbh { int resolve_bottom_level(TbHandle* h, const void* as, cudaStream_t stream, DeviceBvh& out); }
-
 extern "C" {
 
 TB_API int tb_tlas_prebuild_info(uint32_t numInstances, TbPrebuildInfo* out) {
