@@ -277,7 +277,7 @@ def build_traverse(force=False):
         return target if os.path.exists(target) else None
     os.makedirs(OUT, exist_ok=True)
     srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "hlsl_compat.h", "ref_traverse_box.cpp", "ref_traverse_rest.cpp",
-                                                     "ref_traverse_loop.cpp")] + [TRAVERSE, HELPER]
+                                                     "ref_traverse_loop.cpp", "ref_traverse_loop2.cpp")] + [TRAVERSE, HELPER]
     if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs):
         return target
     sys.path.insert(0, os.path.join(HERE, "ref"))
@@ -288,17 +288,21 @@ def build_traverse(force=False):
                           "/root/reference/TracerBoy/RayGenCommon.h", os.path.join(OUT, "intersect_gen.inc"))
     common = [GXX, "-O2", "-std=c++17", "-fPIC", "-mfma", "-fsingle-precision-constant", "-fno-fast-math", "-fvisibility=hidden", "-w",
               "-I" + os.path.join(ROOT, "include"), "-I" + HERE, "-c"]
+    prepass.run_instance_desc("/root/reference/D3D12RaytracingFallback/src/RayTracingHlslCompat.h", os.path.join(OUT, "instance_desc_gen.inc"))
     objs = []
-    for name, contract in (("ref_traverse_box", "fast"), ("ref_traverse_rest", "off"), ("ref_traverse_loop", "off")):
+    for name, contract in (("ref_traverse_box", "fast"), ("ref_traverse_rest", "off"), ("ref_traverse_loop", "off"), ("ref_traverse_loop2", "off")):
         obj = os.path.join(OUT, name + ".o")
         r = subprocess.run(common + ["-fopenmp", "-ffp-contract=" + contract, os.path.join(HERE, "ref", name + ".cpp"), "-o", obj],
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError("oracle/_ref traversal build failed:\n" + r.stdout)
         objs.append(obj)
-    r = subprocess.run([GXX, "-shared", "-fopenmp", "-o", target] + objs, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("oracle/_ref traversal link failed:\n" + r.stdout)
+    # two libraries from the same objects: the single-level loop (FAST_PATH 1, TracerBoy's configuration) and the two-level
+    # loop (FAST_PATH 0) define the same functions, so each is linked with the three pure functions on its own
+    for out, mine in ((target, objs[:3]), (os.path.join(OUT, "libref_traverse2.so"), objs[:2] + objs[3:])):
+        r = subprocess.run([GXX, "-shared", "-fopenmp", "-o", out] + mine, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("oracle/_ref traversal link failed:\n" + r.stdout)
     return target
 
 

@@ -512,8 +512,8 @@ bool update_bvh(Scene& s, std::string& err) {
 //   sort, rearrange (RearrangeBVHs.hlsl), Karras hierarchy: as for triangles; NO treelet pass (GpuBVH2Builder.cpp:343)
 //   boxes       TopLevelComputeAABBs.hlsl: a leaf's box is recomputed from its instance's bottom-level root box and
 //               ObjectToWorld; internal nodes as for triangles (smaller subtree left, D1 on ties)
-// Layout: 16-byte header {offsetToBoxes = 16, 0, offsetToLeafNodeMetaData, totalSize} (TopLevelPrepareForComputeAABBs.hlsl
-// stores three of the four words), 32-byte nodes (internal [0, N-1), leaves [N-1, 2N-1)), 116-byte BVHMetadata per sorted
+// Layout: 16-byte header {offsetToBoxes = 16, offsetToLeafNodeMetaData, 0, totalSize} (TopLevelPrepareForComputeAABBs.hlsl
+// stores three of the four words; OffsetToLeafNodeMetaDataOffset = 4, RayTracingHelper.hlsli:46), 32-byte nodes (internal [0, N-1), leaves [N-1, 2N-1)), 116-byte BVHMetadata per sorted
 // leaf (RayTracingHlslCompat.h:217-236: the instance desc with WorldToObject, ObjectToWorld, the original instance index).
 namespace {
 struct Mat34 { float m[3][4]; };
@@ -618,7 +618,7 @@ bool build_tlas(const TbInstanceDesc* inst, uint32_t n, const std::vector<const 
     }
     const uint32_t offBoxes = 16, offMeta = offBoxes + 32 * total, totalSize = offMeta + 116 * n;
     out.assign(totalSize, 0);
-    uint32_t header[4] = {offBoxes, 0, offMeta, totalSize};
+    uint32_t header[4] = {offBoxes, offMeta, 0, totalSize}; // OffsetToLeafNodeMetaDataOffset = 4 (RayTracingHelper.hlsli:46), word 2 is not written
     memcpy(out.data(), header, 16);
     AABBNode* nodes = (AABBNode*)(out.data() + offBoxes);
     memcpy(out.data() + offMeta, sm.data(), 116ull * n);

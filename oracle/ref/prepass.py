@@ -306,6 +306,23 @@ def run_refit(helper_hlsli, prepare_hlsl, bottom_hlsl, compute_hlsli, dst_prepar
     open(dst_compute, "w").write(fix(helper + "\n" + leaf + "\n" + comp))
 
 
+def run_instance_desc(compat_h, dst):
+    """The instance-desc readers the two-level walk uses (RayTracingHlslCompat.h): CreateMatrix, struct
+    RaytracingInstanceDesc, struct BVHMetadata, RawDataToRaytracingInstanceDesc, LoadBVHMetadata and the Get* accessors."""
+    c = open(compat_h).read()
+    create = c[c.index("AffineMatrix CreateMatrix(float4 rows[3])"):c.index("static const uint D3D12_RAYTRACING_INSTANCE_FLAG_NONE")]
+    structs = c[c.index("struct RaytracingInstanceDesc"):c.index("#define Store4StrideInBytes 16")]
+    readers = c[c.index("RaytracingInstanceDesc RawDataToRaytracingInstanceDesc("):c.index("RaytracingInstanceDesc LoadRaytracingInstanceDesc(RWByteAddressBuffer buffer, uint offset)")]
+    getters = c[c.index("uint GetInstanceContributionToHitGroupIndex(RaytracingInstanceDesc desc)"):c.index("#else\nstatic_assert(sizeof(BVHMetadata) == SizeOfBVHMetadata")]
+    text = create + "\n" + structs + "\n" + readers + "\n" + getters
+    # the slices cut through the header's #ifdef HLSL / #else / #endif bracketing: resolve it for HLSL by hand
+    text = re.sub(r"#ifdef HLSL\n(.*?)#else\n.*?#endif\s*\n", r"\1", text, flags=re.S)
+    text = "\n".join(ln for ln in text.split("\n") if ln.strip() not in ("#endif", "#ifdef HLSL"))
+    text = text.replace("[unroll]", "")
+    text = re.sub(r"\.(zw)\b(?!\s*\()", r".\1()", text)
+    open(dst, "w").write(text)
+
+
 def run_tlas(helper_hlsli, dst):
     """The arithmetic of the top-level instance load (RayTracingHelper.hlsli): AABBtoBoundingBox, BoundingBoxToAABB,
     Determinant, InverseAffineTransform, TransformAABB. float4(...) constructors become make4(...) overloads."""

@@ -209,7 +209,7 @@ void trace_ray_tlas(const uint8_t* tlas, const std::vector<const uint8_t*>& blas
     uint32_t th[4];
     memcpy(th, tlas, 16);
     const AABBNode* tnodes = (const AABBNode*)(tlas + th[0]);
-    const uint8_t* tmeta = tlas + th[2];
+    const uint8_t* tmeta = tlas + th[1]; // GetOffsetToInstanceDesc: OffsetToLeafNodeMetaDataOffset = 4
     f3 worg = mk3(ray.Origin[0], ray.Origin[1], ray.Origin[2]), wdir = mk3(ray.Direction[0], ray.Direction[1], ray.Direction[2]);
     hit.TrianglesTested = hit.BoxesTested = 0; hit.InstanceIndex = 0;
     hit.t = -1.0f; hit.b1 = hit.b2 = 0; hit.PrimitiveIndex = hit.GeometryIndex = 0xffffffffu;

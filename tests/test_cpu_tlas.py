@@ -111,7 +111,7 @@ def test_two_level_query_against_brute_force(tmp_path, built):
     tlas, arr = oracle_tlas(blas, inst, n)
     hdr = tlas[:16].view(np.uint32)
     total = 2 * n - 1
-    assert hdr.tolist() == [16, 0, 16 + 32 * total, 16 + 32 * total + 116 * n]
+    assert hdr.tolist() == [16, 16 + 32 * total, 0, 16 + 32 * total + 116 * n]   # OffsetToLeafNodeMetaDataOffset = 4
     nodes = tlas[16:16 + 32 * total].view(np.float32).reshape(total, 8)
     flags = nodes.view(np.uint32)
     meta = tlas[16 + 32 * total:].reshape(n, 116)
@@ -171,3 +171,49 @@ def test_two_level_query_against_brute_force(tmp_path, built):
             assert (int(hits["InstanceIndex"][k]), int(hits["GeometryIndex"][k]), int(hits["PrimitiveIndex"][k])) == tuple(int(x) for x in I[best]), k
             checked += 1
     assert checked > 200
+
+
+def test_two_level_loop_equals_reference_text(tmp_path, built):
+    """The two-level walk itself against the reference's own text: TraverseFunction.hlsli compiled from the mount with
+    FAST_PATH 0 (oracle/ref/ref_traverse_loop2.cpp -> oracle/_ref/libref_traverse2.so: instance leaves :603-638, object-space
+    ray, return to the top level :770-774, with the instance-desc readers of RayTracingHlslCompat.h) run on the oracle's
+    top-level bytes and the three bottom-level structures. oracle::trace_ray_tlas in its literal mode (D6 / D7 off)
+    must give bit-identical hit records -- t, barycentrics, primitive / geometry / INSTANCE index and both counters --
+    for 40 000 rays incl. exactly-zero direction components, NaN rays, short TMax; the only tolerated difference is D3
+    (ids on exactly equal t)."""
+    from tracerboy_b200.api import RAY_DTYPE, HIT_DTYPE
+    path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_traverse2.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_traverse2.so not built (needs the reference mount at build time)")
+    ref = C.CDLL(path)
+    ref.ref_trace_rays_tlas.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    n = 50
+    blas, scenes, inst, mats = make_two_level_scene(tmp_path, seed=4, n_inst=n)
+    tlas, arr = oracle_tlas(blas, inst, n)
+    rng = np.random.default_rng(2)
+    R = 40000
+    rays = np.zeros(R, RAY_DTYPE)
+    rays["Origin"] = rng.uniform(-60, 60, (R, 3))
+    tgt = mats[rng.integers(0, n, R), :, 3] + rng.normal(0, 2.0, (R, 3))
+    d = tgt - rays["Origin"]
+    rays["Direction"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays["Direction"][::89, 0] = 0.0
+    rays["Direction"][3::977] = np.nan
+    rays["TMin"] = 0.001; rays["TMax"] = 999999.0
+    rays["TMax"][::40] = 30.0
+    lib = binding.load()
+    lib.oracle_set_literal_mode(3)
+    try:
+        got = oracle_trace_tlas(tlas, arr, len(blas), rays)
+    finally:
+        lib.oracle_set_literal_mode(0)
+    want = np.zeros(R, HIT_DTYPE)
+    assert ref.ref_trace_rays_tlas(tlas.ctypes.data, arr, rays.ctypes.data, R, want.ctypes.data) == 0
+    assert (want["t"] > 0).mean() > 0.3 and len(np.unique(want["InstanceIndex"][want["t"] > 0])) > 20
+    for f in ("t", "b1", "b2", "TrianglesTested", "BoxesTested"):
+        same = got[f].view(np.uint32) == want[f].view(np.uint32)
+        if f in ("b1", "b2"):   # D3: on exactly equal t the ids (and with them the barycentrics) may be another triangle's
+            same |= (got["PrimitiveIndex"] != want["PrimitiveIndex"]) | (got["InstanceIndex"] != want["InstanceIndex"]) | (got["GeometryIndex"] != want["GeometryIndex"])
+        assert same.all(), "%s differs for %d rays, first %d" % (f, (~same).sum(), np.flatnonzero(~same)[0])
+    ids_differ = (got["PrimitiveIndex"] != want["PrimitiveIndex"]) | (got["InstanceIndex"] != want["InstanceIndex"]) | (got["GeometryIndex"] != want["GeometryIndex"])
+    assert ids_differ.mean() < 0.002, ids_differ.sum()    # equal-t ties only (coincident triangles of the blob meshes)

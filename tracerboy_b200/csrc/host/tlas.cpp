@@ -183,7 +183,7 @@ TB_API int tb_tlas_build_device(TbHandle* h, const TbInstanceDesc* instances, ui
     for (uint32_t i = 0; i < nInternal; i++) K.node(i, left[i], right[i]);
     std::vector<uint8_t> bytes(L.end, 0);
     const uint32_t offBoxes = 16, offMeta = offBoxes + 32 * total, totalSize = offMeta + 116 * n;
-    const uint32_t header[4] = {offBoxes, 0, offMeta, totalSize};
+    const uint32_t header[4] = {offBoxes, offMeta, 0, totalSize}; // OffsetToLeafNodeMetaDataOffset = 4 (RayTracingHelper.hlsli:46); word 2 is not written
     memcpy(bytes.data(), header, 16);
     RefNodeH* nodes = (RefNodeH*)(bytes.data() + offBoxes);
     MetaRec* sm = (MetaRec*)(bytes.data() + offMeta);
@@ -253,7 +253,7 @@ TB_API int tb_trace_rays_tlas_device(TbHandle* h, const void* tlas, uint64_t tla
         uint32_t hd[4];
         CUDA_OK(h, cudaMemcpyAsync(hd, tlas, sizeof(hd), cudaMemcpyDeviceToHost, stream));
         CUDA_OK(h, cudaStreamSynchronize(stream));
-        if (hd[0] != 16 || hd[1] != 0 || hd[3] < 164 || (hd[3] + 16ull) % 180) return fail(h, TB_ERR_INVALID_ARG, "not a top-level structure built by tb_tlas_build_device");
+        if (hd[0] != 16 || hd[2] != 0 || hd[3] < 164 || (hd[3] + 16ull) % 180 || hd[1] + 116ull * ((hd[3] + 16ull) / 180) != hd[3]) return fail(h, TB_ERR_INVALID_ARG, "not a top-level structure built by tb_tlas_build_device");
         numInstances = (uint32_t)((hd[3] + 16ull) / 180);
         const TlasLayout L = tlas_layout(numInstances);
         if (tlasBytes < L.end) return fail(h, TB_ERR_INVALID_ARG, "top-level structure buffer too small");
