@@ -147,6 +147,37 @@ def build_refit(force=False):
     return target
 
 
+def flatten_lib_path():
+    return os.path.join(OUT, "libref_flatten.so")
+
+
+def build_flatten(force=False):
+    """oracle/_ref/libref_flatten.so: CreateMaterial, MaterialTracker and the area-light rule of LoadScene compiled from the
+    mount, linked against the vendored pbrt-parser objects the importer build leaves in build/pbrt."""
+    cpp, hdr, structs = ("/root/reference/TracerBoy/TracerBoy.cpp", "/root/reference/TracerBoy/TracerBoy.h", "/root/reference/TracerBoy/SharedShaderStructs.h")
+    target = flatten_lib_path()
+    parser = "/root/reference/PBRTParser"
+    objdir = os.path.join(ROOT, "build", "pbrt")
+    if not all(os.path.exists(f) for f in (cpp, hdr, structs)) or not os.path.isdir(objdir):
+        return target if os.path.exists(target) else None
+    objs = [os.path.join(objdir, f) for f in sorted(os.listdir(objdir)) if f.endswith(".o")]
+    if not objs:
+        return target if os.path.exists(target) else None
+    os.makedirs(OUT, exist_ok=True)
+    srcs = [os.path.join(HERE, "ref", f) for f in ("prepass.py", "ref_flatten.cpp")] + [cpp, hdr, structs]
+    if not force and os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(s) for s in srcs):
+        return target
+    sys.path.insert(0, os.path.join(HERE, "ref"))
+    import prepass
+    prepass.run_flatten(cpp, hdr, structs, os.path.join(OUT, "flatten_gen.inc"), os.path.join(OUT, "flatten_light_gen.inc"))
+    cmd = [GXX, "-O2", "-std=c++14", "-fPIC", "-shared", "-mfma", "-ffp-contract=off", "-fno-fast-math", "-fvisibility=hidden", "-w", "-include", "cstdint",
+           "-I" + os.path.join(parser, "include"), "-I" + HERE, os.path.join(HERE, "ref", "ref_flatten.cpp")] + objs + ["-o", target]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle/_ref flatten build failed:\n" + r.stdout)
+    return target
+
+
 def tlas_lib_path():
     return os.path.join(OUT, "libref_tlas.so")
 

@@ -306,6 +306,28 @@ def run_refit(helper_hlsli, prepare_hlsl, bottom_hlsl, compute_hlsli, dst_prepar
     open(dst_compute, "w").write(fix(helper + "\n" + leaf + "\n" + comp))
 
 
+def run_flatten(tracerboy_cpp, tracerboy_h, structs_h, dst, dst_light):
+    """The scene flatten's material and light rules: struct Light ... struct Material with the flag constants
+    (SharedShaderStructs.h), struct MaterialTracker (TracerBoy.h), ConvertFloat3, ChannelAverage, ConvertSpecularToIOR,
+    GetAreaLightColor, reciprocol and CreateMaterial (TracerBoy.cpp) into one file; the per-triangle body of LoadScene's
+    area-light loop (from `Light light = {};` to `lightList.push_back(light);`) into another."""
+    sh = open(structs_h).read()
+    structs = sh[sh.index("struct Light\n"):sh.index("#define IMAGE_TEXTURE_TYPE 0")]
+    structs = re.sub(r"#ifdef HLSL\n.*?#endif\n", "", structs, flags=re.S)
+    th = open(tracerboy_h).read()
+    tracker = th[th.index("struct MaterialTracker"):th.index("class TracerBoy\n")]
+    cpp = open(tracerboy_cpp).read()
+    conv3 = cpp[cpp.index("float3 ConvertFloat3(const pbrt::vec3f& v)"):cpp.index("float4 ConvertFloat4(")]
+    avg = cpp[cpp.index("float ChannelAverage(const pbrt::vec3f& v)"):cpp.index("bool IsNormalizedFormat(DXGI_FORMAT format)")]
+    light = cpp[cpp.index("pbrt::vec3f GetAreaLightColor(pbrt::AreaLight::SP pAreaLight)"):cpp.index("Material CreateMaterial(")]
+    a = cpp.index("Material CreateMaterial(")
+    create = cpp[a:cpp.index("TracerBoy::TracerBoy(", a)]
+    open(dst, "w").write("\n".join([structs, tracker, conv3, avg, light, create]))
+    b = cpp.index("\t\t\t\t\tLight light = {};")
+    body = cpp[b:cpp.index("lightList.push_back(light);", b) + len("lightList.push_back(light);")]
+    open(dst_light, "w").write(body + "\n")
+
+
 def run_instance_desc(compat_h, dst):
     """The instance-desc readers the two-level walk uses (RayTracingHlslCompat.h): CreateMatrix, struct
     RaytracingInstanceDesc, struct BVHMetadata, RawDataToRaytracingInstanceDesc, LoadBVHMetadata and the Get* accessors."""

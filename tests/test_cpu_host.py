@@ -589,3 +589,62 @@ def test_create_material_rules(tmp_path, built):
     light = mats[geoms[13][0]]
     assert light["Flags"] == LIGHT | NOSPEC | NOALPHA and light["emissive"].tolist() == [5.0, 4.0, 3.0]
     assert nl == 1                                      # its one triangle is the scene's one light (TracerBoy.cpp:1780-1835)
+
+
+def _tbscene_arrays(path):
+    """materials [nm, 21] u32, per-geometry material index, lights [nl, 26] u32, texture count of a .tbscene."""
+    import struct
+    raw = open(path, "rb").read()
+    magic, version, flip, ng, nv, ni, nm, nl, nt, nimg, env = struct.unpack_from("<8sII7Ii", raw, 0)
+    geoms = np.frombuffer(raw, np.uint32, ng * 8, 196).reshape(ng, 8)
+    off = 196 + ng * 32 + nv * 12 + nv * 32 + ni * 4
+    mats = np.frombuffer(raw, np.uint32, nm * 21, off).reshape(nm, 21)
+    off += nm * 84
+    lights = np.frombuffer(raw, np.uint32, nl * 26, off).reshape(nl, 26)
+    return mats, geoms[:, 0].copy(), lights, nt
+
+
+@pytest.mark.parametrize("which", ["materials", "textured", "cornell", "teapot"])
+def test_flatten_equals_the_reference_rules_compiled_from_the_mount(which, tmp_path, built):
+    """An independent check of the scene flatten: CreateMaterial, MaterialTracker and the per-triangle
+    area-light rule of LoadScene compiled from the reference's own TracerBoy.cpp / TracerBoy.h / SharedShaderStructs.h
+    (oracle/ref/ref_flatten.cpp -> oracle/_ref/libref_flatten.so, linked against the vendored pbrt-parser) against what
+    the product's importer wrote into the .tbscene: every 84-byte Material in tracker order (mix sub-materials
+    included), the material index of every shape, every 104-byte Light, the number of textures created."""
+    import ctypes as C
+    import tracerboy_b200 as tb
+    from tracerboy_b200 import build
+    from oracle import binding
+    lib_path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_flatten.so")
+    if not os.path.exists(lib_path) or not os.path.exists(os.path.join(build.LIB, "libtb_pbrtimport.so")):
+        pytest.skip("oracle/_ref/libref_flatten.so or the PBRT importer not built (need the reference mount at build time)")
+    if which == "materials":
+        src = str(tmp_path / "m.pbrt"); open(src, "w").write(MATERIALS_PBRT)
+    elif which == "textured":
+        from test_cpu_images import write_textured_scene
+        src = write_textured_scene(str(tmp_path))
+    else:
+        src = "/root/reference/Scenes/%s/scene.pbrt" % {"cornell": "cornell-box", "teapot": "Teapot"}[which]
+        if not os.path.exists(src):
+            pytest.skip("reference mount not present")
+    dst = str(tmp_path / "s.tbscene")
+    tb.convert_scene(src, dst)
+    mats, shape_mat, lights, ntex = _tbscene_arrays(dst)
+    ref = C.CDLL(lib_path)
+    ref.ref_flatten.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    rm, rs, rl, counts = np.zeros((4096, 21), np.uint32), np.zeros(65536, np.int32), np.zeros((1 << 16, 26), np.uint32), np.zeros(4, np.int32)
+    assert ref.ref_flatten(src.encode(), rm.ctypes.data, 4096, rs.ctypes.data, 65536, rl.ctypes.data, 1 << 16, counts.ctypes.data) == 0
+    nm, ns, nl, nt = (int(x) for x in counts)
+    assert nm == mats.shape[0], (nm, mats.shape[0])
+    want = rm[:nm].copy()
+    # the stand-in texture allocator cannot look into image files: it reports "no alpha" for every map, so NO_ALPHA
+    # (0x20) of materials with an albedo map is left to test_pbrt_scene_with_png_and_tga_albedo_maps_flattens
+    textured = mats[:, 3] != 0xffffffff
+    want[textured, 19] = (want[textured, 19] & ~np.uint32(0x20)) | (mats[textured, 19] & np.uint32(0x20))
+    bad = np.argwhere(want != mats)
+    assert bad.shape[0] == 0, "material %d word %d: reference %#x, importer %#x" % (bad[0][0], bad[0][1], want[bad[0][0], bad[0][1]], mats[bad[0][0], bad[0][1]])
+    meshes = rs[:ns][rs[:ns] >= 0]
+    assert np.array_equal(meshes, shape_mat.astype(np.int32)), "per-shape material index"
+    area = lights[lights[:, 0] == 0]    # LIGHT_TYPE_AREA; directional lights come from LoadScene's light-source loop (:1896-1917)
+    assert nl == area.shape[0] and np.array_equal(rl[:nl], area), "area lights"
+    assert nt == ntex

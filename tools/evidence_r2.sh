@@ -17,17 +17,19 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --
 for w in teapot dragon blobs20m; do
   TB_FIF=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $out/${tag}_launches_${w}.csv python tools/profile_run.py $w 4 > $out/${tag}_prof_${w}.log 2>&1
 done
-# ncu --set full: the bounce-0 and a mid-bounce launch of k_extend<0> on each workload; shadow + walk kernels on the 20 M scene
+# ncu --set full of the traversal kernels at BOUNCE 0 of the second rendered frame (one frame at a time: every bounce is
+# k_extend<0> + three resume rounds [+ k_extend<1> shadow + k_extend<2> walk on scenes with lights / glass])
+skip_teapot=24; skip_dragon=32; skip_blobs20m=36
 for w in teapot dragon blobs20m; do
-  TB_FIF=1 timeout 900 ncu --set full $EXTRA --import-source on --clock-control none -k regex:k_extend -s 24 -c 4 -o $out/${tag}_extend_${w} python tools/profile_run.py $w 2 > $out/${tag}_ncu_extend_${w}.log 2>&1
+  eval s=\$skip_$w
+  TB_FIF=1 timeout 900 ncu --set full $EXTRA --import-source on --clock-control none -k regex:k_extend -s $s -c 6 -o $out/${tag}_extend_${w} python tools/profile_run.py $w 2 > $out/${tag}_ncu_extend_${w}.log 2>&1
 done
-TB_FIF=1 timeout 900 ncu --set full $EXTRA --import-source on --clock-control none -k regex:k_walk -s 8 -c 3 -o $out/${tag}_walk_blobs20m python tools/profile_run.py blobs20m 2 > $out/${tag}_ncu_walk_blobs20m.log 2>&1
+TB_FIF=1 timeout 900 ncu --set full $EXTRA --import-source on --clock-control none -k regex:k_walk -s 12 -c 3 -o $out/${tag}_walk_blobs20m python tools/profile_run.py blobs20m 2 > $out/${tag}_ncu_walk_blobs20m.log 2>&1
 TB_FIF=1 timeout 900 ncu --set full $EXTRA --import-source on --clock-control none -k regex:k_shade -s 12 -c 4 -o $out/${tag}_shade_vwvan python tools/profile_run.py vwvan 2 > $out/${tag}_ncu_shade_vwvan.log 2>&1
 # raw metric pages + the source page (SASS / source line counters) as text; the .ncu-rep files themselves (10-20 MB each)
 # stay on the box: gpurun_out/ is capped at 64 MiB
 for f in $out/${tag}_*.ncu-rep; do
   ncu -i $f --page raw --csv > ${f%.ncu-rep}_raw.csv 2>/dev/null
-  ncu -i $f --page source --csv --print-source sass 2>/dev/null | head -c 3000000 > ${f%.ncu-rep}_source_sass.csv
   rm -f $f
 done
 for f in teapot cornell dragon vwvan blobs20m blobs871k; do python - <<PY

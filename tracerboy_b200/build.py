@@ -306,6 +306,7 @@ def build_all(force=False, verbose=False):
     build_ref.build_load(force)
     build_ref.build_treelet_pass(force)
     build_ref.build_tlas(force)
+    build_ref.build_flatten(force)
 
 
 if __name__ == "__main__":
