@@ -477,6 +477,14 @@ def main():
             "cpu_baseline": cpu_baseline,
             "bvh_build_ms": g.GetBVHBuildMilliseconds(), "bvh_build_first_call_ms": build_first_ms,
             "bvh_build_mtris_per_s": g.GetSceneInfo().NumTriangles / max(1e-9, g.GetBVHBuildMilliseconds()) / 1e3, "scene_load_s": load_s,
+            # the builder against the HBM roofline: compulsory traffic of its stages per triangle: load 48 + 52,
+            # Morton 40 + 8, four radix passes 4 x 32, rearrange 108, Karras ~24, three treelet passes ~3 x 100, refit 96 + 32,
+            # traversal layout 116 + 112 = 1064 B
+            "bvh_build_roofline": {"bound": "hbm", "algorithmic_bytes_per_triangle": 1064,
+                                   "achieved": 1064.0 * info.NumTriangles / max(1e-9, g.GetBVHBuildMilliseconds() / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": 1064.0 * info.NumTriangles / max(1e-9, g.GetBVHBuildMilliseconds() / 1e3) / 1e9 / peak,
+                                   "note": "small scenes are bound by the serial climb at the top of the tree (launch / latency), large ones by the "
+                                           "treelet search's shared-memory traffic (profiles/r1c_treelet_octets_20m_ncu_full_raw.csv)"},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
