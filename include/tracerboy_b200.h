@@ -459,14 +459,6 @@ TB_API int tb_set_shadow_mode(TbHandle* h, int mode);
  * 1 = the bounce queue, 3 = bounce and shadow queues, 4 = automatic (default: 3 for scenes whose traversal BVH is
  * beyond 256 MB, i.e. far outside L2, else 0). Scheduling only: results are identical. */
 TB_API int tb_set_ray_sort(TbHandle* h, int mode);
-/* Node layout the wavefront's traversal kernels walk: 0 = pairs (default: one 64-byte node per BVH2 internal node, the
- * reference's visit order, so TrianglesTested / BoxesTested in TbRenderStats and TB_BUF_RAY_COUNTERS are the reference's
- * numbers bit for bit), 1 = 4-wide (128-byte nodes holding a node's four grandchildren: two BVH2 levels per dependent
- * fetch, same boxes, same slab and triangle arithmetic, closest hit with the same id tie-break). With layout 1 the two
- * counters count this layout's own tests; hit ids, t and radiance are expected to stay identical (every box decision is
- * the BVH2 walk's own; see DESIGN.md §4 for the one theoretical caveat) and the tests require it on every test scene.
- * tb_trace_rays*, the heat-map output's meaning and the inline queries of the shading stage always use the pair layout. */
-TB_API int tb_set_traversal_layout(TbHandle* h, int layout);
 /* Hit queue of the shading stage grouped by material class (the material's flag bits + "albedo is textured") so that a
  * warp shades hits that take the same branches: 0 = off, 1 = on, 2 = automatic (default: on when the scene's reachable
  * materials span four or more classes, where it was measured to pay). Scheduling only: results are identical. */

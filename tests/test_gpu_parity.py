@@ -281,44 +281,6 @@ def test_ray_sort_changes_nothing(tmp_path, built):
         g.SetRaySort(2)
 
 
-@pytest.mark.parametrize("scene", ["cornell", "teapot", "showcase", "blobs", "vwvan"])
-def test_wide_traversal_layout_keeps_hits_and_radiance(scene, tmp_path, built):
-    """tb_set_traversal_layout(1): the wavefront's traversal kernels walk 4-wide nodes (two BVH2 levels per fetch, the very
-    same boxes and arithmetic). Primary-hit ids, every radiance and AOV buffer and the ray count still equal the oracle
-    bit for bit -- with frames in flight and with one frame at a time (ray suspension + resume rounds); only the two
-    traversal counters are this layout's own."""
-    import tracerboy_b200 as tb
-    if scene == "cornell":
-        path, w, h, bounces = scene_path("cornell-box"), 160, 160, 4
-    elif scene == "teapot":
-        path, w, h, bounces = scene_path("teapot"), 256, 144, 6
-    elif scene == "vwvan":
-        path, w, h, bounces = scene_path("vw-van"), 192, 108, 6
-    elif scene == "showcase":
-        path, w, h, bounces = _tbscene("synthetic:showcase?tris=400&seed=9", tmp_path), 160, 90, 8
-    else:
-        path, w, h, bounces = _tbscene("synthetic:blobs?copies=27&tris=300&seed=3", tmp_path), 160, 90, 8
-    if path is None:
-        pytest.skip("scene cache missing")
-    s = tb.get_default_output_settings()
-    s.MaxBounces = bounces
-    for fif in (0, 1):
-        g, o = _pair(path, w, h)
-        g.SetTraversalLayout(1)
-        g.SetFramesInFlight(fif)
-        g.Render(s, 3, 0.0)
-        o.Render(s, 3, 0.0)
-        for k in (0, 1, 3, 4, 5, 6, 7, 8):
-            a, b = g.Readback(k), o.Readback(k)
-            same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b)) if a.dtype == np.float32 else a == b
-            assert same.all(), "buffer kind %d differs at %d elements (frames in flight %d)" % (k, (~same).sum(), fif)
-        assert g.GetRenderStats().RaysTraced == o.Counts()["rays"]
-    g.SetTraversalLayout(0)   # back to the pair layout: counters are the reference's again
-    g.InvalidateHistory()
-    o2 = _pair(path, w, h)[1]
-    _compare_render(g, o2, s, 2)
-
-
 def test_material_sort_changes_nothing(tmp_path, built):
     """The shading stage's hit queue grouped by material class (north star (4): "sorted by material to cut divergence";
     automatic from four material classes on) is scheduling only: forced on and off, with the

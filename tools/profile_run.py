@@ -12,8 +12,6 @@ spec, w, h, _, bounces = bench.WORKLOADS[wl]
 g = tb.TracerBoy(0)
 g.LoadScene(bench.scene_arg(spec))
 g.Resize(w, h)
-if os.environ.get("TB_WIDE"):
-    g.SetTraversalLayout(int(os.environ["TB_WIDE"]))
 if os.environ.get("TB_FIF"):
     g.SetFramesInFlight(int(os.environ["TB_FIF"]))
 s = tb.get_default_output_settings()

@@ -191,7 +191,7 @@ def load_library():
         "tb_render": [vp, C.POINTER(OutputSettings), u32, C.c_float], "tb_samples_rendered": [vp, C.POINTER(u32)],
         "tb_invalidate_history": [vp], "tb_set_frame_shard": [vp, u32, u32], "tb_set_row_shard": [vp, u32, u32], "tb_buffer_size": [vp, u32, C.POINTER(u64)],
         "tb_readback": [vp, u32, vp, u64], "tb_device_buffer": [vp, u32, C.POINTER(vp), C.POINTER(u64)],
-        "tb_get_render_stats": [vp, C.POINTER(RenderStats)], "tb_reset_render_stats": [vp], "tb_synchronize": [vp], "tb_set_profiling": [vp, i32], "tb_set_frames_in_flight": [vp, u32], "tb_set_shadow_mode": [vp, i32], "tb_set_ray_sort": [vp, i32], "tb_set_material_sort": [vp, i32], "tb_set_traversal_layout": [vp, i32],
+        "tb_get_render_stats": [vp, C.POINTER(RenderStats)], "tb_reset_render_stats": [vp], "tb_synchronize": [vp], "tb_set_profiling": [vp, i32], "tb_set_frames_in_flight": [vp, u32], "tb_set_shadow_mode": [vp, i32], "tb_set_ray_sort": [vp, i32], "tb_set_material_sort": [vp, i32],
         "tb_is_material_id_valid": [vp, i32], "tb_get_material": [vp, i32, C.POINTER(Material), C.c_char_p, u32],
         "tb_set_material": [vp, i32, C.POINTER(Material)],
         "tb_bvh_prebuild_info": [C.POINTER(GeometryDesc), u32, C.POINTER(PrebuildInfo)],
@@ -229,7 +229,7 @@ EXPORTED_SYMBOLS = ["tb_create", "tb_destroy", "tb_last_error", "tb_version", "t
                     "tb_get_material", "tb_set_material", "tb_bvh_prebuild_info", "tb_bvh_build", "tb_trace_rays",
                     "tb_get_default_postprocess_settings", "tb_postprocess", "tb_postprocess_image",
                     "tb_temporal_accumulate_image", "tb_save_image", "tb_write_image", "tb_update", "tb_camera_update", "tb_set_ray_sort",
-                    "tb_set_material_sort", "tb_set_traversal_layout", "tb_load_image_file", "tb_max_triangles", "tb_bvh_build_device", "tb_trace_rays_device", "tb_bvh_forget_device", "tb_bvh_update_device", "tb_tlas_prebuild_info", "tb_tlas_build_device", "tb_trace_rays_tlas_device", "tb_get_bvh_depth",
+                    "tb_set_material_sort", "tb_load_image_file", "tb_max_triangles", "tb_bvh_build_device", "tb_trace_rays_device", "tb_bvh_forget_device", "tb_bvh_update_device", "tb_tlas_prebuild_info", "tb_tlas_build_device", "tb_trace_rays_tlas_device", "tb_get_bvh_depth",
                     "tb_comm_get_unique_id", "tb_comm_init", "tb_comm_destroy", "tb_comm_info", "tb_comm_reduce"]
 
 
@@ -601,10 +601,6 @@ class TracerBoy:
     def SetRaySort(self, mode):
         """0 off, 1 bounce queue, 3 bounce + shadow queues, 4 automatic (scheduling only, results are identical)."""
         self._ck(self._lib.tb_set_ray_sort(self._h, int(mode)))
-
-    def SetTraversalLayout(self, layout):
-        """0 = pairs (reference visit order, exact counters; default), 1 = 4-wide nodes (counters are the layout's own)."""
-        self._ck(self._lib.tb_set_traversal_layout(self._h, int(layout)))
 
     def SetMaterialSort(self, mode):
         """0 off, 1 on, 2 automatic: the shading stage's hit queue grouped by material class (scheduling only)."""

@@ -783,38 +783,6 @@ __global__ void k_widen(uint32_t n, const uint8_t* __restrict__ bvh, PairNode* _
 
 } // namespace
 
-// 4-wide layout from the pair layout: node X keeps the boxes and references of X's grandchildren (a leaf child stands
-// for itself). Every node is independent of the others: one thread per BVH2 internal node.
-__global__ void k_collapse4(uint32_t nInternal, const PairNode* __restrict__ pairs, WideNode* __restrict__ wide) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nInternal) return;
-    float c[4][3], h[4][3];
-    uint32_t ref[4];
-    int k = 0;
-#pragma unroll
-    for (int e = 0; e < 4; e++) { ref[e] = 0x7fffffffu; c[e][0] = c[e][1] = c[e][2] = 0.0f; h[e][0] = h[e][1] = h[e][2] = 0.0f; }
-    const PairNode p = pairs[i];
-    auto put = [&](const float4& cc, const float4& hh, uint32_t r) { c[k][0] = cc.x; c[k][1] = cc.y; c[k][2] = cc.z; h[k][0] = hh.x; h[k][1] = hh.y; h[k][2] = hh.z; ref[k] = r; k++; };
-    const uint32_t lref = __float_as_uint(p.lc.w), rref = __float_as_uint(p.lh.w);
-    if (lref & 0x80000000u) put(p.lc, p.lh, lref);
-    else { const PairNode q = pairs[lref]; put(q.lc, q.lh, __float_as_uint(q.lc.w)); put(q.rc, q.rh, __float_as_uint(q.lh.w)); }
-    if (rref & 0x80000000u) put(p.rc, p.rh, rref);
-    else { const PairNode q = pairs[rref]; put(q.lc, q.lh, __float_as_uint(q.lc.w)); put(q.rc, q.rh, __float_as_uint(q.lh.w)); }
-    WideNode w;
-    w.cx = make_float4(c[0][0], c[1][0], c[2][0], c[3][0]); w.cy = make_float4(c[0][1], c[1][1], c[2][1], c[3][1]); w.cz = make_float4(c[0][2], c[1][2], c[2][2], c[3][2]);
-    w.hx = make_float4(h[0][0], h[1][0], h[2][0], h[3][0]); w.hy = make_float4(h[0][1], h[1][1], h[2][1], h[3][1]); w.hz = make_float4(h[0][2], h[1][2], h[2][2], h[3][2]);
-    w.ref = make_uint4(ref[0], ref[1], ref[2], ref[3]);
-    w.pad = make_uint4(0, 0, 0, 0);
-    wide[i] = w;
-}
-
-cudaError_t build_wide_layout(DeviceBvh& bvh, cudaStream_t stream, LaunchCounter& lc) {
-    if (bvh.numPrims < 2 || !bvh.wide) return cudaSuccess;
-    const uint32_t nInternal = bvh.numPrims - 1;
-    k_collapse4<<<(nInternal + 255) / 256, 256, 0, stream>>>(nInternal, bvh.pairs, bvh.wide); lc.count++;
-    return cudaGetLastError();
-}
-
 uint64_t bvh_ref_bytes(uint32_t n) { return 16ull + 32ull * (2ull * n - 1) + 40ull * n + 12ull * n; }
 
 // The builder's temporaries, carved out of ONE scratch allocation (the caller's, as in

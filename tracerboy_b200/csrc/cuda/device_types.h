@@ -25,10 +25,6 @@ struct PairNode {
     float4 rh;  // right half xyz,   w unused
 };
 struct WideTri { float4 v0, v1, v2; };
-// Optional 4-wide traversal layout (tb_set_traversal_layout): one 128-byte node per BVH2 internal node X holding X's up
-// to four GRANDCHILDREN (a leaf child of X stands for itself), SoA so that the four slab tests run on the same
-// arithmetic as the pair test: the very same boxes, two BVH2 levels per dependent fetch. ref = TB_NO_NODE for unused entries.
-struct WideNode { float4 cx, cy, cz, hx, hy, hz; uint4 ref; uint4 pad; };
 
 // Entries of the per-ray traversal stack. A near-first BVH2 traversal keeps at most one waiting far child per tree
 // level, so a tree of depth <= TB_STACK_DEPTH can never overflow it; deeper trees are rejected after the build.
@@ -39,7 +35,6 @@ struct DeviceBvh {
     uint64_t refBytes = 0;
     PairNode* pairs = nullptr;   // numPrims-1 entries (>=1 allocated)
     WideTri* tris = nullptr;     // numPrims entries
-    WideNode* wide = nullptr;    // numPrims-1 entries, only when the 4-wide layout was requested (owned by the handle)
     RefNode root;                // root node copy (box for the initial test; leaf flag if N==1)
     uint32_t numPrims = 0;
     uint32_t depth = 0;          // height of the tree (0 = a single leaf): bounds the traversal stack

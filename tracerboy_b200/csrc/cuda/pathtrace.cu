@@ -567,7 +567,7 @@ __device__ __forceinline__ bool try_suspend(PathState& st, int round, const Trav
 #define EXT_MAIN 0
 #define EXT_SHADOW 1
 #define EXT_WALK 2
-template <int KIND, bool WIDE>
+template <int KIND>
 __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh, PathState st, int qi, int bounce, uint32_t outputHeatmap, const FrameConstants* __restrict__ fcp, uint32_t budgetMain, uint32_t refillBelow,
                                                                    const uint8_t* __restrict__ classOfGeom) {
     const bool classSort = KIND == EXT_MAIN && classOfGeom != nullptr; // hits carry their material class and are counted per class
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
     const uint32_t* __restrict__ queue = KIND == EXT_SHADOW ? st.shadowQueue : KIND == EXT_WALK ? st.walkQueue[qi] : st.queue[qi];
     const float4* __restrict__ rayO = KIND == EXT_SHADOW ? st.shRayO : st.rayO;
     const float4* __restrict__ rayD = KIND == EXT_SHADOW ? st.shRayD : st.rayD;
-    const float4* __restrict__ pairs = WIDE ? (const float4*)bvh.wide : (const float4*)bvh.pairs;
+    const float4* __restrict__ pairs = (const float4*)bvh.pairs;
     const float4* __restrict__ tris = (const float4*)bvh.tris;
     const uint32_t lane = threadIdx.x & 31;
     uint32_t rays = 0, ntris = 0, nboxes = 0;
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
             if (2 * nL > nB) {
                 if (wantLeaf) tr.step_leaf(stack, tris);
             } else {
-                if (busy && !wantLeaf) { if (WIDE) tr.step_wide(stack, pairs); else tr.step_internal(stack, pairs); }
+                if (busy && !wantLeaf) tr.step_internal(stack, pairs);
             }
         }
     }
@@ -693,7 +693,6 @@ __global__ void __launch_bounds__(128, EXTEND_MIN_BLOCKS) k_extend(DeviceBvh bvh
 }
 
 // Resume round `round` (1-based): continues the rays parked by round-1; the last round has no budget.
-template <bool WIDE>
 __global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState st, int qi, int round, uint32_t budget, int bounce,
                                                        uint32_t outputHeatmap, const FrameConstants* __restrict__ fcp,
                                                        const uint8_t* __restrict__ classOfGeom) {
@@ -701,7 +700,7 @@ __global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState 
     const uint32_t aovMask = fcp->aovMask;
     const int bounceIsZero = bounce == 0;
     const uint32_t count = min(st.susCount[round - 1], st.susCapacity);
-    const float4* __restrict__ pairs = WIDE ? (const float4*)bvh.wide : (const float4*)bvh.pairs;
+    const float4* __restrict__ pairs = (const float4*)bvh.pairs;
     const float4* __restrict__ tris = (const float4*)bvh.tris;
     const uint32_t* __restrict__ in = st.susBuf[(round - 1) & 1];
     uint32_t rays = 0, ntris = 0, nboxes = 0;
@@ -720,7 +719,7 @@ __global__ void __launch_bounds__(128) k_extend_resume(DeviceBvh bvh, PathState 
                 if (try_suspend(st, round, tr, stack, pi)) break;
                 suspendAt += budget;
             }
-            if (tr.at_leaf()) tr.step_leaf(stack, tris); else if (WIDE) tr.step_wide(stack, pairs); else tr.step_internal(stack, pairs);
+            tr.step(stack, pairs, tris);
         }
     }
     flush_stats(st, 6, bounce, rays, ntris, nboxes);
@@ -1523,18 +1522,13 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
         // launch per bounce (dragon, cornell)
         const bool classSort = classEnv >= 0 ? classEnv != 0 : (opts.materialSort == 2 ? opts.sceneMaterialClasses >= 4 : opts.materialSort != 0);
         const uint8_t* classOfGeom = classSort ? sc.geomClass : nullptr;
-        const bool wide = opts.wideNodes && bvh.wide != nullptr;
-        if (wide) k_extend<EXT_MAIN, true><<<blocks, 128, 0, stream>>>(bvh, stx, qi, b, heat, fcDev, suspendMode ? budgetMain : 0xffffffffu, refillBelow, classOfGeom);
-        else k_extend<EXT_MAIN, false><<<blocks, 128, 0, stream>>>(bvh, stx, qi, b, heat, fcDev, suspendMode ? budgetMain : 0xffffffffu, refillBelow, classOfGeom);
-        launches++;
+        k_extend<EXT_MAIN><<<blocks, 128, 0, stream>>>(bvh, stx, qi, b, heat, fcDev, suspendMode ? budgetMain : 0xffffffffu, refillBelow, classOfGeom); launches++;
         if (suspendMode) {
             uint32_t rblocks = (st.susCapacity + 127) / 128;
             if (rblocks > sms * 4) rblocks = sms * 4;
             if (timers) cudaEventRecord(timers->next(KernelTimers::RESUME, b), stream);
             for (int r = 1; r <= EXTEND_RESUME_ROUNDS; r++) {
-                if (wide) k_extend_resume<true><<<rblocks, 128, 0, stream>>>(bvh, st, qi, r, budgets[r - 1], b, heat, fcDev, classOfGeom);
-                else k_extend_resume<false><<<rblocks, 128, 0, stream>>>(bvh, st, qi, r, budgets[r - 1], b, heat, fcDev, classOfGeom);
-                launches++;
+                k_extend_resume<<<rblocks, 128, 0, stream>>>(bvh, st, qi, r, budgets[r - 1], b, heat, fcDev, classOfGeom); launches++;
                 rblocks = (rblocks + 3) / 4 > sms ? (rblocks + 3) / 4 : sms;
             }
         }
@@ -1558,9 +1552,7 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
                 sort_queue(st.shadowQueue, &st.queueCount[4], st.shRayO);
                 sts.shadowQueue = st.sortTmp;
             }
-            if (wide) k_extend<EXT_SHADOW, true><<<blocks, 128, 0, stream>>>(bvh, sts, qi, b, 0, fcDev, 0xffffffffu, refillBelow, nullptr);
-            else k_extend<EXT_SHADOW, false><<<blocks, 128, 0, stream>>>(bvh, sts, qi, b, 0, fcDev, 0xffffffffu, refillBelow, nullptr);
-            launches++;
+            k_extend<EXT_SHADOW><<<blocks, 128, 0, stream>>>(bvh, sts, qi, b, 0, fcDev, 0xffffffffu, refillBelow, nullptr); launches++;
             TB_LAUNCH_SHADE(1);
         } else if (nee) {
             TB_LAUNCH_SHADE(2);
@@ -1573,9 +1565,7 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
             if (roundsEnv == -2) { const char* e = getenv("TB_WALK_ROUNDS"); roundsEnv = e ? atoi(e) : -1; }
             const int rounds = roundsEnv >= 0 ? roundsEnv : opts.walkRounds; // wavefront rounds before the persistent tail (which reads queue rounds & 1)
             for (int r = 0; r < rounds; r++) {
-                if (wide) k_extend<EXT_WALK, true><<<blocks, 128, 0, stream>>>(bvh, st, r & 1, b, 0, fcDev, 0xffffffffu, REFILL_THRESHOLD, nullptr);
-                else k_extend<EXT_WALK, false><<<blocks, 128, 0, stream>>>(bvh, st, r & 1, b, 0, fcDev, 0xffffffffu, REFILL_THRESHOLD, nullptr);
-                launches++;
+                k_extend<EXT_WALK><<<blocks, 128, 0, stream>>>(bvh, st, r & 1, b, 0, fcDev, 0xffffffffu, REFILL_THRESHOLD, nullptr); launches++;
                 k_walk_step<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(sc, fcDev, st, qi, r & 1); launches++;
             }
             uint32_t wblocks = blocks > sms * 4 ? sms * 4 : blocks;
@@ -1605,7 +1595,7 @@ cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const Fram
     FrameGraph::Key key = {opts.epoch, fc.width, fc.height, (uint32_t)fc.settings.MaxBounces, fc.settings.OutputType == TB_OUTPUT_HEATMAP ? 1u : 0u,
                            fc.settings.EnableNextEventEstimation ? 1u : 0u, (uint32_t)opts.shadowMode, (uint32_t)opts.walkRounds,
                            opts.sceneHasSSS ? 1u : 0u, opts.suspendRays ? 1u : 0u, (uint32_t)opts.sortRays,
-                           (uint32_t)opts.materialSort * 256u + opts.sceneMaterialClasses, (opts.wideNodes && bvh.wide) ? 1u : 0u};
+                           (uint32_t)opts.materialSort * 256u + opts.sceneMaterialClasses};
     if (!graph->exec || memcmp(&key, &graph->key, sizeof(key)) != 0) {
         graph->reset();
         cudaGraph_t g = nullptr;

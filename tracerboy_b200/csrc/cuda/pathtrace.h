@@ -108,15 +108,12 @@ struct RenderOptions {
     int sortRays = 2;   // spatial sort of the ray queues before traversal: 0 off, bit 0 bounce queue, bit 1 shadow queue (1 or 3), 2 automatic (3 for scenes whose BVH is far beyond L2)
     int materialSort = 2; // hit queue grouped by material class before shading: 0 off, 1 on, 2 automatic (on from four material classes)
     uint32_t sceneMaterialClasses = 1; // distinct material classes reachable from the geometry (host-side count)
-    bool wideNodes = false; // traverse the 4-wide layout in k_extend / k_extend_resume (set by the host when DeviceBvh::wide is built)
     int numSMs = 148;   // of the handle's device (persistent grids are sized from it)
     bool sceneHasSSS = true; // any material with the subsurface flag (selects the k_shade variant with the inline random walk)
 };
 
 uint64_t bvh_ref_bytes(uint32_t numPrims);
 uint64_t bvh_scratch_bytes(uint32_t numPrims);
-// fills bvh.wide (allocated by the caller: numPrims - 1 WideNode) from bvh.pairs
-cudaError_t build_wide_layout(DeviceBvh& bvh, cudaStream_t stream, LaunchCounter& lc);
 uint64_t bvh_update_scratch_bytes(uint32_t numPrims);
 // PERFORM_UPDATE: same hierarchy, triangles reloaded from the (moved) geometry into their sorted slots, boxes refitted
 cudaError_t update_bvh(const BuildGeometry* d_geoms, uint32_t numPrims, DeviceBvh& bvh, void* scratch, cudaStream_t stream, LaunchCounter& lc);
@@ -124,7 +121,7 @@ cudaError_t build_bvh(const BuildGeometry* d_geoms, const uint32_t* d_triPrefix,
                       DeviceBvh& out, void* scratch, cudaStream_t stream, LaunchCounter& lc);
 // The captured kernel sequence of one frame on one frame slot (see render_frame).
 struct FrameGraph {
-    struct Key { uint32_t epoch, width, height, maxBounces, heat, nee, shadowMode, walkRounds, sss, suspend, sort, classSort, wide; }; // no padding: compared with memcmp
+    struct Key { uint32_t epoch, width, height, maxBounces, heat, nee, shadowMode, walkRounds, sss, suspend, sort, classSort; }; // no padding: compared with memcmp
     Key key{};
     cudaGraphExec_t exec = nullptr;
     uint64_t launches = 0; // kernels inside the graph

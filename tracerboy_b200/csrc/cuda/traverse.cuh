@@ -216,45 +216,6 @@ struct Traversal {
         cur = nearRef;
         if (!(lh || rh)) pop(stack);
     }
-    // cur is an internal node, 4-wide layout: the four grandchildren's boxes with the SAME slab arithmetic as the pair test
-    // (so every single box decision equals the BVH2 walk's), nearest first, the other hits wait on the stack sorted so
-    // that the nearer one is popped first. Hits do not depend on the order (closest hit + id tie-break); the two traversal
-    // counters do: in this mode BoxesTested counts four boxes per visit and is not the reference's number.
-    __device__ __forceinline__ void step_wide(uint32_t* stack, const float4* __restrict__ wide) {
-        using namespace tbm;
-        const float4* nd = wide + 8 * (size_t)cur;
-        float4 cx, cy, cz, hx, hy, hz, rf, pad;
-        ldg256(nd, cx, cy); ldg256(nd + 2, cz, hx); ldg256(nd + 4, hy, hz); ldg256(nd + 6, rf, pad);
-        const f3 ainv = abs3(inv);
-        SlabRange r0, r1, r2, r3;
-        if (zmask) {
-            r0 = slab_zero(committedT, org, zmask, oinv, inv, ainv, cx.x, cy.x, cz.x, hx.x, hy.x, hz.x);
-            r1 = slab_zero(committedT, org, zmask, oinv, inv, ainv, cx.y, cy.y, cz.y, hx.y, hy.y, hz.y);
-            r2 = slab_zero(committedT, org, zmask, oinv, inv, ainv, cx.z, cy.z, cz.z, hx.z, hy.z, hz.z);
-            r3 = slab_zero(committedT, org, zmask, oinv, inv, ainv, cx.w, cy.w, cz.w, hx.w, hy.w, hz.w);
-        } else {
-            r0 = slab(committedT, oinv, inv, ainv, cx.x, cy.x, cz.x, hx.x, hy.x, hz.x);
-            r1 = slab(committedT, oinv, inv, ainv, cx.y, cy.y, cz.y, hx.y, hy.y, hz.y);
-            r2 = slab(committedT, oinv, inv, ainv, cx.z, cy.z, cz.z, hx.z, hy.z, hz.z);
-            r3 = slab(committedT, oinv, inv, ainv, cx.w, cy.w, cz.w, hx.w, hy.w, hz.w);
-        }
-        pairsTested += 2;
-        const float inf = __uint_as_float(0x7f800000u);
-        uint32_t e0 = __float_as_uint(rf.x), e1 = __float_as_uint(rf.y), e2 = __float_as_uint(rf.z), e3 = __float_as_uint(rf.w);
-        float d0 = (r0.enter < r0.exit && e0 != TB_NO_NODE) ? r0.enter : inf;
-        float d1 = (r1.enter < r1.exit && e1 != TB_NO_NODE) ? r1.enter : inf;
-        float d2 = (r2.enter < r2.exit && e2 != TB_NO_NODE) ? r2.enter : inf;
-        float d3 = (r3.enter < r3.exit && e3 != TB_NO_NODE) ? r3.enter : inf;
-        // sorting network for four (5 compare-exchanges), ascending by entry distance
-#define TB_CE(da, ea, db, eb) { const bool sw = db < da; const float td = sw ? db : da; const uint32_t te = sw ? eb : ea; db = sw ? da : db; eb = sw ? ea : eb; da = td; ea = te; }
-        TB_CE(d0, e0, d1, e1) TB_CE(d2, e2, d3, e3) TB_CE(d0, e0, d2, e2) TB_CE(d1, e1, d3, e3) TB_CE(d1, e1, d2, e2)
-#undef TB_CE
-        if (d3 < inf) { ++sp; stack[sp] = e3; }
-        if (d2 < inf) { ++sp; stack[sp] = e2; }
-        if (d1 < inf) { ++sp; stack[sp] = e1; }
-        cur = e0;
-        if (!(d0 < inf)) pop(stack);
-    }
     __device__ __forceinline__ void step(uint32_t* stack, const float4* __restrict__ pairs, const float4* __restrict__ tris) {
         if (at_leaf()) step_leaf(stack, tris); else step_internal(stack, pairs);
     }

@@ -53,7 +53,6 @@ static void free_scene(TbHandle* h) {
     if (h->bvh.ref) cudaFree(h->bvh.ref);
     if (h->bvh.pairs) cudaFree(h->bvh.pairs);
     if (h->bvh.tris) cudaFree(h->bvh.tris);
-    if (h->bvh.wide) cudaFree(h->bvh.wide);
     h->bvh = DeviceBvh();
     h->dscene = DeviceScene();
     h->sceneLoaded = false;
@@ -145,23 +144,6 @@ static int run_build(TbHandle* h, const std::vector<BuildGeometry>& descs, const
     return TB_OK;
 }
 
-// The optional 4-wide traversal layout of the handle's scene (tb_set_traversal_layout): built from the pair layout when
-// requested and when the wider pushes (up to three per visit, two BVH2 levels per visit) provably fit the stack.
-static int ensure_wide_layout(TbHandle* h) {
-    h->options.wideNodes = false;
-    if (!h->wantWideNodes || !h->sceneLoaded || h->bvh.numPrims < 2) return TB_OK;
-    if (3u * (h->bvh.depth / 2u + 1u) > TB_STACK_DEPTH) return TB_OK; // stays on the pair layout
-    if (!h->bvh.wide) {
-        CUDA_OK(h, cudaSetDevice(h->device));
-        CUDA_OK(h, cudaMalloc((void**)&h->bvh.wide, sizeof(WideNode) * (size_t)(h->bvh.numPrims - 1)));
-        CUDA_OK(h, build_wide_layout(h->bvh, h->stream, h->lc));
-        CUDA_OK(h, cudaStreamSynchronize(h->stream));
-        h->options.epoch++; // a device pointer baked into captured frame graphs changed
-    }
-    h->options.wideNodes = true;
-    return TB_OK;
-}
-
 // Uploads h->scene and builds the BVH.
 static int upload_and_build(TbHandle* h, uint32_t flags) {
     tb::Scene& s = h->scene;
@@ -238,7 +220,6 @@ static int upload_and_build(TbHandle* h, uint32_t flags) {
     h->options.sceneMaterialClasses = scene_material_classes(s);
     h->sceneLoaded = true;
     h->samplesRendered = 0;
-    { int rcw = ensure_wide_layout(h); if (rcw != TB_OK) return rcw; }
     set_status(h, TB_LOAD_FINISHED, (uint32_t)s.geoms.size(), (uint32_t)s.geoms.size());
     return TB_OK;
 }
@@ -982,11 +963,6 @@ TB_API int tb_set_ray_sort(TbHandle* h, int mode) {
     if (!h || mode < 0 || mode > 4 || mode == 2) return fail(h, TB_ERR_INVALID_ARG, "ray sort must be 0 (off), 1 (bounce queue), 3 (bounce + shadow queues) or 4 (auto)");
     h->options.sortRays = mode == 4 ? 2 : mode;
     return TB_OK;
-}
-TB_API int tb_set_traversal_layout(TbHandle* h, int layout) {
-    if (!h || layout < 0 || layout > 1) return fail(h, TB_ERR_INVALID_ARG, "traversal layout must be 0 (pairs) or 1 (4-wide)");
-    h->wantWideNodes = layout == 1;
-    return ensure_wide_layout(h);
 }
 TB_API int tb_set_material_sort(TbHandle* h, int mode) {
     if (!h || mode < 0 || mode > 2) return fail(h, TB_ERR_INVALID_ARG, "material sort must be 0 (off), 1 (on) or 2 (auto)");

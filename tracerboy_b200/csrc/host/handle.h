@@ -77,7 +77,6 @@ struct TbHandle {
     std::mutex statusLock;
     TbSceneLoadStatus status{TB_LOAD_IDLE, 0, 0};
     std::vector<uint8_t> blueNoiseHost;
-    bool wantWideNodes = false;     // tb_set_traversal_layout(1)
     int profiling = 0;              // 0 off, 1 one frame at a time (exclusive kernel times), 2 frames in flight (in-situ shares)
     void* buildScratch = nullptr;   // the builder's temporaries, kept between builds
     uint64_t buildScratchBytes = 0;
