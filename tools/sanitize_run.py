@@ -24,6 +24,7 @@ for spec, w, h, shadow in (("tests/golden/cornell-box.tbscene", 96, 64, 2), ("sy
     g.Resize(w, h)
     g.SetShadowMode(shadow)
     g.SetRaySort(3 if shadow == 1 else 4)  # the queue sort kernels on two of the scenes
+    g.SetMaterialSort(1)                   # material-class hit queues (k_class_scatter)
     s.MaxBounces = 5
     s.EnableNormalMaps = 1
     g.Render(s, 3, 0.0)          # frame graphs captured here
@@ -46,4 +47,35 @@ p = tb.TemporalAccumulationParams()
 p.Camera = g.GetCamera(); p.PrevCamera = g.GetCamera()
 p.HistoryWeight, p.IgnoreHistory, p.OutputMomentInformation = 0.95, 0, 1
 g.TemporalAccumulateImage(p, img, img, img, img, img, img)
+# the SW-RT seam on caller-owned device memory: build, update in place, top level, single- and two-level queries
+import ctypes as C
+import torch
+from tracerboy_b200.api import GeometryDesc, InstanceDesc
+rng = np.random.default_rng(2)
+pos = torch.from_numpy(rng.uniform(-1, 1, (300, 3)).astype(np.float32)).cuda()
+idx = torch.from_numpy(rng.integers(0, 300, 900).astype(np.uint16).view(np.uint8)).cuda()
+d = (GeometryDesc * 1)()
+d[0].Positions = pos.data_ptr(); d[0].PositionStrideBytes = 12; d[0].VertexCount = 300
+d[0].Indices = idx.data_ptr(); d[0].IndexFormat = 2; d[0].IndexCount = 900; d[0].GeometryFlags = 1
+info = tb.prebuild_info(d, 1)
+dst = torch.zeros(info.ResultDataMaxSizeInBytes, dtype=torch.uint8, device="cuda")
+scratch = torch.empty(info.ScratchDataSizeInBytes, dtype=torch.uint8, device="cuda")
+g.BuildRaytracingAccelerationStructureDevice(d, 1, dst.data_ptr(), dst.numel(), scratch.data_ptr(), scratch.numel(), None)
+pos += 0.01
+g.UpdateRaytracingAccelerationStructureDevice(d, 1, dst.data_ptr(), dst.numel(), scratch.data_ptr(), scratch.numel(), None)
+inst = (InstanceDesc * 5)()
+for i in range(5):
+    for j, v in enumerate((1, 0, 0, 3.0 * i, 0, 1, 0, 0, 0, 0, 1, 0)):
+        inst[i].Transform[j] = float(v)
+    inst[i].InstanceIDAndMask = i | (0xff << 24); inst[i].AccelerationStructure = dst.data_ptr()
+tinfo = tb.tlas_prebuild_info(5)
+tlas = torch.zeros(tinfo.ResultDataMaxSizeInBytes, dtype=torch.uint8, device="cuda")
+g.BuildTopLevelAccelerationStructureDevice(inst, 5, tlas.data_ptr(), tlas.numel(), None)
+rays = np.zeros(2000, tb.api.RAY_DTYPE)
+rays["Origin"] = rng.uniform(-2, 14, (2000, 3)) * [1, 0.2, 0.2]; rays["Direction"] = rng.normal(0, 1, (2000, 3)); rays["TMin"] = 0.001; rays["TMax"] = 1e6
+d_rays = torch.from_numpy(rays.view(np.uint8)).cuda()
+d_hits = torch.zeros(2000 * 32, dtype=torch.uint8, device="cuda")
+g.TraceRaysDevice(dst.data_ptr(), dst.numel(), d_rays.data_ptr(), 2000, d_hits.data_ptr(), None)
+g.TraceRaysTopLevelDevice(tlas.data_ptr(), tlas.numel(), d_rays.data_ptr(), 2000, d_hits.data_ptr(), None)
+g.Synchronize()
 print("sanitize_run ok")
