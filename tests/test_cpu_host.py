@@ -648,3 +648,40 @@ def test_flatten_equals_the_reference_rules_compiled_from_the_mount(which, tmp_p
     area = lights[lights[:, 0] == 0]    # LIGHT_TYPE_AREA; directional lights come from LoadScene's light-source loop (:1896-1917)
     assert nl == area.shape[0] and np.array_equal(rl[:nl], area), "area lights"
     assert nt == ntex
+
+
+def test_seam_size_queries_and_argument_checks_without_a_device(built):
+    """Host-only parts of the SW-RT seam and of the communicator: size queries are pure arithmetic, bad arguments are
+    E_INVALIDARG, and nothing here needs (or silently replaces) a GPU."""
+    import tracerboy_b200 as tb
+    from tracerboy_b200.api import GeometryDesc, PrebuildInfo
+    lib = tb.load_library()
+    # top level: 16-byte header + 32-byte nodes (2N - 1) + 116-byte BVHMetadata per instance; no scratch (built on the host)
+    for n in (1, 2, 7, 20000):
+        info = tb.tlas_prebuild_info(n)
+        assert info.ReferenceLayoutSizeInBytes == 16 + 32 * (2 * n - 1) + 116 * n
+        assert info.ResultDataMaxSizeInBytes >= info.ReferenceLayoutSizeInBytes + 256 + 80 * n and info.ScratchDataSizeInBytes == 0
+    assert tb.tlas_prebuild_info(0).ResultDataMaxSizeInBytes == 0
+    info = PrebuildInfo()
+    assert lib.tb_tlas_prebuild_info((1 << 24) + 1, C.byref(info)) == -1      # InstanceID / hit-group contribution are 24 bit
+    # bottom level: scratch and update scratch grow linearly and are 256-byte granular
+    pos = np.zeros((3, 3), np.float32)
+    d = (GeometryDesc * 1)()
+    d[0].Positions = pos.ctypes.data; d[0].PositionStrideBytes = 12
+    sizes = []
+    for tris in (1, 1000, 1000000):
+        d[0].VertexCount = 3 * tris
+        assert lib.tb_bvh_prebuild_info(d, 1, C.byref(info)) == 0
+        assert info.UpdateScratchDataSizeInBytes >= 12 * tris - 4 and info.ScratchDataSizeInBytes >= 150 * tris
+        sizes.append(info.ScratchDataSizeInBytes)
+    assert sizes[0] < sizes[1] < sizes[2] < 200 * 1000000 + (1 << 20)
+    d[0].IndexFormat = 3                                                        # only none / uint16 / uint32
+    d[0].Indices = pos.ctypes.data
+    assert lib.tb_bvh_prebuild_info(d, 1, C.byref(info)) == -1
+    # communicator: the id is 128 bytes (ncclUniqueId); calls on a null handle are errors, not crashes
+    buf = C.create_string_buffer(64)
+    assert lib.tb_comm_get_unique_id(buf, 64) == -1
+    assert lib.tb_comm_init(None, buf, 0, 1, 1) == -1 and lib.tb_comm_reduce(None) == -1 and lib.tb_comm_destroy(None) == -1
+    assert lib.tb_bvh_build_device(None, d, 1, 0, None, 0, None, 0, None) == -1
+    assert lib.tb_tlas_build_device(None, None, 1, 0, None, 0, None) == -1
+    assert lib.tb_set_material_sort(None, 1) == -1
