@@ -326,6 +326,16 @@ def run_flatten(tracerboy_cpp, tracerboy_h, structs_h, dst, dst_light):
     b = cpp.index("\t\t\t\t\tLight light = {};")
     body = cpp[b:cpp.index("lightList.push_back(light);", b) + len("lightList.push_back(light);")]
     open(dst_light, "w").write(body + "\n")
+    # the two geometry loops of LoadScene: per-vertex attributes (:1638-1661) and indices + flat normals (:1704-1730)
+    v0 = cpp.index("for (UINT v = 0; v < pTriangleMesh->vertex.size(); v++)")
+    v1 = cpp.index("auto SRVIndexIter = ResourceToSRVIndex.find(pVertexBuffer->GetGPUVirtualAddress());", v0)
+    i0 = cpp.index("for (UINT i = 0; i < pTriangleMesh->index.size(); i++)", v1)
+    i1 = cpp.index("auto SRVIndexIter = ResourceToSRVIndex.find(pIndexBuffer->GetGPUVirtualAddress());", i0)
+    vertex_struct = sh[sh.index("struct Vertex\n"):sh.index("struct Light\n")]
+    base = os.path.dirname(dst)
+    open(os.path.join(base, "flatten_vertex_struct_gen.inc"), "w").write(vertex_struct)
+    open(os.path.join(base, "flatten_vertices_gen.inc"), "w").write(cpp[v0:v1] + "\n")
+    open(os.path.join(base, "flatten_indices_gen.inc"), "w").write(cpp[i0:i1] + "\n")
 
 
 def run_instance_desc(compat_h, dst):

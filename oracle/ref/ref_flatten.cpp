@@ -37,9 +37,34 @@ struct TextureAllocator {
     }
 };
 
+#include "../_ref/flatten_vertex_struct_gen.inc"
 #include "../_ref/flatten_gen.inc"
 
-static_assert(sizeof(Material) == 84 && sizeof(Light) == 104, "SharedShaderStructs.h layout");
+static_assert(sizeof(Material) == 84 && sizeof(Light) == 104 && sizeof(Vertex) == 32, "SharedShaderStructs.h layout");
+typedef uint32_t UINT32;
+
+// The geometry of shape `shapeIndex` exactly as LoadScene writes it into its upload buffers: the per-vertex loop
+// (positions, normals, uvs, tangents; TracerBoy.cpp:1638-1661) and the index loop with its flat-normal rule for meshes
+// without normals (:1704-1730), both compiled from the mount; top-level shapes are baked with the identity transform (:1360).
+extern "C" __attribute__((visibility("default")))
+int ref_flatten_geometry(const char* pbrtPath, int shapeIndex, float* positions3, Vertex* vertices, uint32_t* indices, int capVerts, int capIndices, int* counts) {
+    using pbrt::math::normalize; using pbrt::math::xfmNormal;
+    pbrt::Scene::SP pScene;
+    try { pScene = pbrt::importPBRT(pbrtPath); } catch (...) { return -1; }
+    if (!pScene || !pScene->world || shapeIndex < 0 || shapeIndex >= (int)pScene->world->shapes.size()) return -1;
+    pbrt::TriangleMesh::SP pTriangleMesh = std::dynamic_pointer_cast<pbrt::TriangleMesh>(pScene->world->shapes[shapeIndex]);
+    if (!pTriangleMesh) return -2;
+    if ((int)pTriangleMesh->vertex.size() > capVerts || (int)pTriangleMesh->index.size() * 3 > capIndices) return -1;
+    pbrt::affine3f vertexBufferTransform = pbrt::affine3f::identity();
+    bool bNormalsProvided = pTriangleMesh->normal.size();
+    Vertex* pVertexBufferData = vertices;
+    float3* pPositionBufferData = (float3*)positions3;
+    UINT32* pIndexBufferData = indices;
+#include "../_ref/flatten_vertices_gen.inc"
+#include "../_ref/flatten_indices_gen.inc"
+    counts[0] = (int)pTriangleMesh->vertex.size(); counts[1] = (int)pTriangleMesh->index.size() * 3;
+    return 0;
+}
 
 // out: materials in MaterialTracker order, one material index per world->shapes entry that is a triangle mesh (-1 otherwise),
 // the area lights in creation order. Returns 0, or -1 when a capacity is too small / the scene cannot be read.

@@ -685,3 +685,54 @@ def test_seam_size_queries_and_argument_checks_without_a_device(built):
     assert lib.tb_bvh_build_device(None, d, 1, 0, None, 0, None, 0, None) == -1
     assert lib.tb_tlas_build_device(None, None, 1, 0, None, 0, None) == -1
     assert lib.tb_set_material_sort(None, 1) == -1
+
+
+@pytest.mark.parametrize("which", ["cornell", "teapot", "textured", "materials"])
+def test_geometry_flatten_equals_the_reference_loops_compiled_from_the_mount(which, tmp_path, built):
+    """The geometry half of the flatten: LoadScene's per-vertex loop (positions, normalised normals, uvs,
+    tangents with the (0,0,1) default; TracerBoy.cpp:1638-1661) and its index loop with the flat-normal rule for meshes
+    without normals (last face to touch a vertex wins, degenerate faces get (0,1,0); :1704-1730), both compiled from the
+    mount, against the product importer's pooled arrays in the .tbscene: every position, every 32-byte Vertex, every
+    index of every shape, bit for bit."""
+    import ctypes as C
+    import struct
+    import tracerboy_b200 as tb
+    from tracerboy_b200 import build
+    from oracle import binding
+    lib_path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_flatten.so")
+    if not os.path.exists(lib_path) or not os.path.exists(os.path.join(build.LIB, "libtb_pbrtimport.so")):
+        pytest.skip("oracle/_ref/libref_flatten.so or the PBRT importer not built (need the reference mount at build time)")
+    ref = C.CDLL(lib_path)
+    if not hasattr(ref, "ref_flatten_geometry"):
+        pytest.skip("oracle/_ref/libref_flatten.so predates the geometry entry point")
+    if which == "materials":
+        src = str(tmp_path / "m.pbrt"); open(src, "w").write(MATERIALS_PBRT)
+    elif which == "textured":
+        from test_cpu_images import write_textured_scene
+        src = write_textured_scene(str(tmp_path))
+    else:
+        src = "/root/reference/Scenes/%s/scene.pbrt" % {"cornell": "cornell-box", "teapot": "Teapot"}[which]
+        if not os.path.exists(src):
+            pytest.skip("reference mount not present")
+    dst = str(tmp_path / "s.tbscene")
+    tb.convert_scene(src, dst)
+    raw = open(dst, "rb").read()
+    magic, version, flip, ng, nv, ni, nm, nl, nt, nimg, env = struct.unpack_from("<8sII7Ii", raw, 0)
+    geoms = np.frombuffer(raw, np.uint32, ng * 8, 196).reshape(ng, 8)
+    off = 196 + ng * 32
+    positions = np.frombuffer(raw, np.uint32, nv * 3, off).reshape(nv, 3); off += nv * 12
+    vertices = np.frombuffer(raw, np.uint32, nv * 8, off).reshape(nv, 8); off += nv * 32
+    indices = np.frombuffer(raw, np.uint32, ni, off)
+    ref.ref_flatten_geometry.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    checked = 0
+    for g in range(ng):
+        mat, vfirst, vcount, ifirst, icount = (int(x) for x in geoms[g][:5])
+        P, V, I, counts = np.zeros((vcount, 3), np.uint32), np.zeros((vcount, 8), np.uint32), np.zeros(icount, np.uint32), np.zeros(2, np.int32)
+        assert ref.ref_flatten_geometry(src.encode(), g, P.ctypes.data, V.ctypes.data, I.ctypes.data, vcount, icount, counts.ctypes.data) == 0, g
+        assert counts.tolist() == [vcount, icount]
+        assert np.array_equal(P, positions[vfirst:vfirst + vcount]), "positions of shape %d" % g
+        assert np.array_equal(I, indices[ifirst:ifirst + icount]), "indices of shape %d" % g
+        bad = np.argwhere(V != vertices[vfirst:vfirst + vcount])
+        assert bad.shape[0] == 0, "shape %d vertex %d word %d (normal 0-2, uv 3-4, tangent 5-7)" % (g, bad[0][0], bad[0][1])
+        checked += vcount
+    assert checked == nv

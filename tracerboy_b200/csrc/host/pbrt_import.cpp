@@ -294,21 +294,32 @@ struct Importer {
                 TbMaterial m = create_material(mesh->material, at != mesh->textures.end() ? &at->second : nullptr, emissive);
                 matId = add_material(mesh->material.get(), m);
             }
-            // normals: normalize(xfmNormal(identity, n)) (:1647-1650)
-            std::vector<TbFloat3> nrm, tan;
-            std::vector<TbFloat2> uv;
+            // The reference pushes every position through `vertexBufferTransform * v` and every normal and tangent
+            // through normalize(xfmNormal(vertexBufferTransform, n)) with the transform at identity
+            // (TracerBoy.cpp:1636-1650). The identity products are kept literally: they turn -0 into +0.
+            const pbrt::affine3f vertexBufferTransform = pbrt::affine3f::identity();
             size_t nv = mesh->vertex.size();
-            if (N) {
-                nrm.resize(nv);
-                for (size_t v = 0; v < nv; v++) nrm[v] = cv3(pbrt::math::normalize(mesh->normal[v]));
-            }
-            tan.resize(nv);
-            uv.resize(nv);
+            std::vector<TbFloat3> pos(nv), nrm(nv), tan(nv);
+            std::vector<TbFloat2> uv(nv);
             for (size_t v = 0; v < nv; v++) {
-                tan[v] = v < mesh->tangents.size() ? cv3(pbrt::math::normalize(mesh->tangents[v])) : TbFloat3{0, 0, 1};
+                pos[v] = cv3(vertexBufferTransform * mesh->vertex[v]);
+                nrm[v] = N ? cv3(pbrt::math::normalize(pbrt::math::xfmNormal(vertexBufferTransform, mesh->normal[v]))) : TbFloat3{0, 1, 0};
+                tan[v] = v < mesh->tangents.size() ? cv3(pbrt::math::normalize(pbrt::math::xfmNormal(vertexBufferTransform, mesh->tangents[v]))) : TbFloat3{0, 0, 1};
                 uv[v] = v < mesh->texcoord.size() ? TbFloat2{mesh->texcoord[v].x, mesh->texcoord[v].y} : TbFloat2{0, 0};
             }
-            append_geometry(out, P, N ? nrm.data() : nullptr, uv.data(), tan.data(), (uint32_t)nv, idx.data(),
+            if (!N) {
+                // flat normals from the untransformed positions, written into the shared vertices, last face wins (:1710-1729)
+                for (size_t i = 0; i < mesh->index.size(); i++) {
+                    auto t = mesh->index[i];
+                    pbrt::vec3f edge1 = mesh->vertex[t.z] - mesh->vertex[t.x];
+                    pbrt::vec3f edge2 = mesh->vertex[t.z] - mesh->vertex[t.y];
+                    pbrt::vec3f n = pbrt::math::cross(edge1, edge2);
+                    if (pbrt::math::dot(n, n) <= 0.0000000001f) n = pbrt::vec3f(0, 1, 0);
+                    else n = pbrt::math::normalize(pbrt::math::xfmNormal(vertexBufferTransform, n));
+                    nrm[t.x] = nrm[t.y] = nrm[t.z] = cv3(n);
+                }
+            }
+            append_geometry(out, pos.data(), nrm.data(), uv.data(), tan.data(), (uint32_t)nv, idx.data(),
                             (uint32_t)idx.size(), matId);
         }
         // lights / environment, TracerBoy.cpp:1896-1934
