@@ -391,10 +391,22 @@ TB_API uint64_t tb_max_triangles(void);
  * then builds the BVH on the device (PREFER_FAST_TRACE, TracerBoy.cpp:1970). */
 TB_API int tb_load_scene(TbHandle* h, const char* path);
 TB_API int tb_load_scene_ex(TbHandle* h, const char* path, uint32_t bvhBuildFlags);
+/* What the PBRT import does with object instances (`ObjectInstance` directives). LoadScene has a switch for it,
+ * bInsertInstancesIntoBLAS (TracerBoy.cpp:1355), compiled as false: instances get a bottom-level structure each and
+ * a top-level entry (:2031-2050) that the software path then never traverses (it renders BLASList[0], :2862).
+ *   TB_INSTANCES_SKIP              the reference build's software path: instances are not rendered (default)
+ *   TB_INSTANCES_INSERT_INTO_BLAS  the switch set: every instance joins the global bottom-level structure as the
+ *                                  first shape of its object, its transform baked into the vertex data (:1367-1376,
+ *                                  1623-1651)
+ * Takes effect at the next tb_load_scene of a .pbrt / .pbf path. */
+#define TB_INSTANCES_SKIP 0u
+#define TB_INSTANCES_INSERT_INTO_BLAS 1u
+TB_API int tb_set_instance_mode(TbHandle* h, uint32_t mode);
 TB_API int tb_get_load_status(TbHandle* h, TbSceneLoadStatus* out);
 TB_API int tb_save_scene(TbHandle* h, const char* tbscenePath); /* .pbf-cache role, TracerBoy.cpp:1200-1223 */
 /* Host-only: import any supported scene path and write the .tbscene cache (no device needed). */
 TB_API int tb_convert_scene(const char* inPath, const char* outTbscenePath, char* err, size_t errCap);
+TB_API int tb_convert_scene_ex(const char* inPath, const char* outTbscenePath, uint32_t instanceMode, char* err, size_t errCap);
 TB_API int tb_get_scene_info(TbHandle* h, TbSceneInfo* out);
 TB_API int tb_get_bvh_size(TbHandle* h, uint64_t* bytes);
 /* Copies the BVH in the reference's byte layout (RayTracingHlslCompat.h:344-398). */

@@ -336,6 +336,14 @@ def run_flatten(tracerboy_cpp, tracerboy_h, structs_h, dst, dst_light):
     open(os.path.join(base, "flatten_vertex_struct_gen.inc"), "w").write(vertex_struct)
     open(os.path.join(base, "flatten_vertices_gen.inc"), "w").write(cpp[v0:v1] + "\n")
     open(os.path.join(base, "flatten_indices_gen.inc"), "w").write(cpp[i0:i1] + "\n")
+    # which geometry and transform loop iteration i of LoadScene takes (top-level shape or object instance, :1358-1376)
+    # and whether the transform is baked into the vertex data (:1623-1624)
+    s0 = cpp.index("std::shared_ptr<pbrt::Object> pObject;")
+    s1 = cpp.index("bool bNeedToCreateGlobalBLAS = bInsertIntoGlobalBLAS && !GlobalBLASKey;", s0)
+    k0 = cpp.index("bool bBakeTransformIntoVertexBuffer = bInsertIntoGlobalBLAS;")
+    k1 = cpp.index("bool bNormalsProvided = pTriangleMesh->normal.size();", k0)
+    open(os.path.join(base, "flatten_select_gen.inc"), "w").write(cpp[s0:s1] + "\n")
+    open(os.path.join(base, "flatten_bake_gen.inc"), "w").write(cpp[k0:k1] + "\n")
 
 
 def run_instance_desc(compat_h, dst):

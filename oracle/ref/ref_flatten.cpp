@@ -43,19 +43,25 @@ struct TextureAllocator {
 static_assert(sizeof(Material) == 84 && sizeof(Light) == 104 && sizeof(Vertex) == 32, "SharedShaderStructs.h layout");
 typedef uint32_t UINT32;
 
-// The geometry of shape `shapeIndex` exactly as LoadScene writes it into its upload buffers: the per-vertex loop
-// (positions, normals, uvs, tangents; TracerBoy.cpp:1638-1661) and the index loop with its flat-normal rule for meshes
-// without normals (:1704-1730), both compiled from the mount; top-level shapes are baked with the identity transform (:1360).
+// The geometry of LoadScene's loop iteration `shapeIndex` (top-level shapes first, then the object instances)
+// exactly as it is written into the upload buffers: which shape and transform the iteration takes (:1358-1376), whether
+// the transform is baked (:1623-1624), the per-vertex loop (positions, normals, uvs, tangents; :1638-1661) and the index
+// loop with its flat-normal rule for meshes without normals (:1704-1730), all compiled from the mount.
+// `insertInstancesIntoBLAS` is LoadScene's local switch of that name (:1355; the reference build has it false).
 extern "C" __attribute__((visibility("default")))
-int ref_flatten_geometry(const char* pbrtPath, int shapeIndex, float* positions3, Vertex* vertices, uint32_t* indices, int capVerts, int capIndices, int* counts) {
+int ref_flatten_geometry(const char* pbrtPath, int shapeIndex, float* positions3, Vertex* vertices, uint32_t* indices, int capVerts, int capIndices, int* counts,
+                         int insertInstancesIntoBLAS) {
     using pbrt::math::normalize; using pbrt::math::xfmNormal;
     pbrt::Scene::SP pScene;
     try { pScene = pbrt::importPBRT(pbrtPath); } catch (...) { return -1; }
-    if (!pScene || !pScene->world || shapeIndex < 0 || shapeIndex >= (int)pScene->world->shapes.size()) return -1;
-    pbrt::TriangleMesh::SP pTriangleMesh = std::dynamic_pointer_cast<pbrt::TriangleMesh>(pScene->world->shapes[shapeIndex]);
+    if (!pScene || !pScene->world || shapeIndex < 0 || shapeIndex >= (int)(pScene->world->shapes.size() + pScene->world->instances.size())) return -1;
+    const UINT i = (UINT)shapeIndex;
+    const bool bInsertInstancesIntoBLAS = insertInstancesIntoBLAS != 0;
+#include "../_ref/flatten_select_gen.inc"
+    pbrt::TriangleMesh::SP pTriangleMesh = std::dynamic_pointer_cast<pbrt::TriangleMesh>(pGeometry);
     if (!pTriangleMesh) return -2;
     if ((int)pTriangleMesh->vertex.size() > capVerts || (int)pTriangleMesh->index.size() * 3 > capIndices) return -1;
-    pbrt::affine3f vertexBufferTransform = pbrt::affine3f::identity();
+#include "../_ref/flatten_bake_gen.inc"
     bool bNormalsProvided = pTriangleMesh->normal.size();
     Vertex* pVertexBufferData = vertices;
     float3* pPositionBufferData = (float3*)positions3;
@@ -69,7 +75,8 @@ int ref_flatten_geometry(const char* pbrtPath, int shapeIndex, float* positions3
 // out: materials in MaterialTracker order, one material index per world->shapes entry that is a triangle mesh (-1 otherwise),
 // the area lights in creation order. Returns 0, or -1 when a capacity is too small / the scene cannot be read.
 extern "C" __attribute__((visibility("default")))
-int ref_flatten(const char* pbrtPath, Material* mats, int capMats, int* shapeMaterial, int capShapes, Light* lights, int capLights, int* counts) {
+int ref_flatten(const char* pbrtPath, Material* mats, int capMats, int* shapeMaterial, int capShapes, Light* lights, int capLights, int* counts,
+                int insertInstancesIntoBLAS) {
     pbrt::Scene::SP pScene;
     try { pScene = pbrt::importPBRT(pbrtPath); } catch (...) { return -1; }
     if (!pScene || !pScene->world) return -1;
@@ -77,9 +84,12 @@ int ref_flatten(const char* pbrtPath, Material* mats, int capMats, int* shapeMat
     TextureAllocator textureAllocator;
     std::vector<Light> lightList;
     int nShapes = 0;
-    for (size_t s = 0; s < pScene->world->shapes.size(); s++) {
+    const bool bInsertInstancesIntoBLAS = insertInstancesIntoBLAS != 0;
+    const UINT totalSceneInstances = pScene->world->shapes.size() + (bInsertInstancesIntoBLAS ? pScene->world->instances.size() : 0);
+    for (UINT i = 0; i < totalSceneInstances; i++) {
         if (nShapes >= capShapes) return -1;
-        pbrt::TriangleMesh::SP pTriangleMesh = std::dynamic_pointer_cast<pbrt::TriangleMesh>(pScene->world->shapes[s]);
+#include "../_ref/flatten_select_gen.inc"
+        pbrt::TriangleMesh::SP pTriangleMesh = std::dynamic_pointer_cast<pbrt::TriangleMesh>(pGeometry);
         if (!pTriangleMesh) { shapeMaterial[nShapes++] = -1; continue; }
         pbrt::vec3f emissive(0.0f);
         if (pTriangleMesh->areaLight) {

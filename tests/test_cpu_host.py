@@ -591,6 +591,22 @@ def test_create_material_rules(tmp_path, built):
     assert nl == 1                                      # its one triangle is the scene's one light (TracerBoy.cpp:1780-1835)
 
 
+def _flatten_case(which, tmp_path):
+    """(scene path, insert-instances flag) of a flatten test case."""
+    if which == "materials":
+        src = str(tmp_path / "m.pbrt"); open(src, "w").write(MATERIALS_PBRT)
+    elif which == "instanced":
+        src = str(tmp_path / "i.pbrt"); open(src, "w").write(INSTANCED_PBRT)
+    elif which == "textured":
+        from test_cpu_images import write_textured_scene
+        src = write_textured_scene(str(tmp_path))
+    else:
+        src = "/root/reference/Scenes/%s/scene.pbrt" % {"cornell": "cornell-box", "teapot": "Teapot"}[which]
+        if not os.path.exists(src):
+            pytest.skip("reference mount not present")
+    return src, 1 if which == "instanced" else 0
+
+
 def _tbscene_arrays(path):
     """materials [nm, 21] u32, per-geometry material index, lights [nl, 26] u32, texture count of a .tbscene."""
     import struct
@@ -604,7 +620,59 @@ def _tbscene_arrays(path):
     return mats, geoms[:, 0].copy(), lights, nt
 
 
-@pytest.mark.parametrize("which", ["materials", "textured", "cornell", "teapot"])
+INSTANCED_PBRT = """
+LookAt 0 2 -12  0 0 0  0 1 0
+Camera "perspective" "float fov" [40]
+Film "image" "integer xresolution" [64] "integer yresolution" [48]
+WorldBegin
+MakeNamedMaterial "red" "string type" ["matte"] "rgb Kd" [0.8 0.1 0.1]
+MakeNamedMaterial "steel" "string type" ["metal"] "float roughness" [0.2]
+# object a: a smooth-shaded quad followed by a second shape that LoadScene ignores (it instantiates shapes[0] only)
+ObjectBegin "a"
+  NamedMaterial "red"
+  Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-1 0 -1  1 0 -1  1 0.5 1  -1 0.5 1]
+        "normal N" [0 1 0  0 1 0  0.3 0.9 0.1  -0.3 0.9 0.1] "float uv" [0 0 1 0 1 1 0 1]
+  Shape "trianglemesh" "integer indices" [0 1 2] "point P" [5 5 5  6 5 5  5 6 5]
+ObjectEnd
+# object b: no normals (flat-normal rule under a rotation and a non-uniform scale), one degenerate face
+ObjectBegin "b"
+  NamedMaterial "steel"
+  Shape "trianglemesh" "integer indices" [0 1 2 0 2 3 0 0 1] "point P" [-1 -1 0  1 -1 0  1 1 0.25  -1 1 0]
+ObjectEnd
+# object c: an emissive triangle (its light is built from the UNtransformed vertices, TracerBoy.cpp:1538-1540)
+ObjectBegin "c"
+  AreaLightSource "diffuse" "rgb L" [4 3 2]
+  NamedMaterial "red"
+  Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0  1 0 0  0 0 1]
+ObjectEnd
+NamedMaterial "red"
+Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-20 -2 -20  20 -2 -20  20 -2 20  -20 -2 20]
+AttributeBegin
+  Translate 3 0.5 0
+  ObjectInstance "a"
+AttributeEnd
+AttributeBegin
+  Translate -3 1 2
+  Rotate 37 0.3 1 0.2
+  Scale 1.5 0.5 2
+  ObjectInstance "a"
+AttributeEnd
+AttributeBegin
+  Rotate -70 1 0 0
+  Scale 2 1 3
+  Translate 0.5 0 -1
+  ObjectInstance "b"
+AttributeEnd
+AttributeBegin
+  Translate 0 6 0
+  Rotate 180 1 0 0
+  ObjectInstance "c"
+AttributeEnd
+WorldEnd
+"""
+
+
+@pytest.mark.parametrize("which", ["materials", "textured", "cornell", "teapot", "instanced"])
 def test_flatten_equals_the_reference_rules_compiled_from_the_mount(which, tmp_path, built):
     """An independent check of the scene flatten: CreateMaterial, MaterialTracker and the per-triangle
     area-light rule of LoadScene compiled from the reference's own TracerBoy.cpp / TracerBoy.h / SharedShaderStructs.h
@@ -618,22 +686,16 @@ def test_flatten_equals_the_reference_rules_compiled_from_the_mount(which, tmp_p
     lib_path = os.path.join(os.path.dirname(binding.ref_traverse_lib_path()), "libref_flatten.so")
     if not os.path.exists(lib_path) or not os.path.exists(os.path.join(build.LIB, "libtb_pbrtimport.so")):
         pytest.skip("oracle/_ref/libref_flatten.so or the PBRT importer not built (need the reference mount at build time)")
-    if which == "materials":
-        src = str(tmp_path / "m.pbrt"); open(src, "w").write(MATERIALS_PBRT)
-    elif which == "textured":
-        from test_cpu_images import write_textured_scene
-        src = write_textured_scene(str(tmp_path))
-    else:
-        src = "/root/reference/Scenes/%s/scene.pbrt" % {"cornell": "cornell-box", "teapot": "Teapot"}[which]
-        if not os.path.exists(src):
-            pytest.skip("reference mount not present")
+    src, insert = _flatten_case(which, tmp_path)
     dst = str(tmp_path / "s.tbscene")
-    tb.convert_scene(src, dst)
+    tb.convert_scene(src, dst, tb.INSTANCES_INSERT_INTO_BLAS if insert else tb.INSTANCES_SKIP)
     mats, shape_mat, lights, ntex = _tbscene_arrays(dst)
     ref = C.CDLL(lib_path)
-    ref.ref_flatten.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    ref.ref_flatten.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     rm, rs, rl, counts = np.zeros((4096, 21), np.uint32), np.zeros(65536, np.int32), np.zeros((1 << 16, 26), np.uint32), np.zeros(4, np.int32)
-    assert ref.ref_flatten(src.encode(), rm.ctypes.data, 4096, rs.ctypes.data, 65536, rl.ctypes.data, 1 << 16, counts.ctypes.data) == 0
+    assert ref.ref_flatten(src.encode(), rm.ctypes.data, 4096, rs.ctypes.data, 65536, rl.ctypes.data, 1 << 16, counts.ctypes.data, insert) == 0
+    if which == "instanced":
+        assert counts[1] == 5 and shape_mat.shape[0] == 5   # the floor + four instances, one geometry each
     nm, ns, nl, nt = (int(x) for x in counts)
     assert nm == mats.shape[0], (nm, mats.shape[0])
     want = rm[:nm].copy()
@@ -687,7 +749,7 @@ def test_seam_size_queries_and_argument_checks_without_a_device(built):
     assert lib.tb_set_material_sort(None, 1) == -1
 
 
-@pytest.mark.parametrize("which", ["cornell", "teapot", "textured", "materials"])
+@pytest.mark.parametrize("which", ["cornell", "teapot", "textured", "materials", "instanced"])
 def test_geometry_flatten_equals_the_reference_loops_compiled_from_the_mount(which, tmp_path, built):
     """The geometry half of the flatten: LoadScene's per-vertex loop (positions, normalised normals, uvs,
     tangents with the (0,0,1) default; TracerBoy.cpp:1638-1661) and its index loop with the flat-normal rule for meshes
@@ -705,17 +767,9 @@ def test_geometry_flatten_equals_the_reference_loops_compiled_from_the_mount(whi
     ref = C.CDLL(lib_path)
     if not hasattr(ref, "ref_flatten_geometry"):
         pytest.skip("oracle/_ref/libref_flatten.so predates the geometry entry point")
-    if which == "materials":
-        src = str(tmp_path / "m.pbrt"); open(src, "w").write(MATERIALS_PBRT)
-    elif which == "textured":
-        from test_cpu_images import write_textured_scene
-        src = write_textured_scene(str(tmp_path))
-    else:
-        src = "/root/reference/Scenes/%s/scene.pbrt" % {"cornell": "cornell-box", "teapot": "Teapot"}[which]
-        if not os.path.exists(src):
-            pytest.skip("reference mount not present")
+    src, insert = _flatten_case(which, tmp_path)
     dst = str(tmp_path / "s.tbscene")
-    tb.convert_scene(src, dst)
+    tb.convert_scene(src, dst, tb.INSTANCES_INSERT_INTO_BLAS if insert else tb.INSTANCES_SKIP)
     raw = open(dst, "rb").read()
     magic, version, flip, ng, nv, ni, nm, nl, nt, nimg, env = struct.unpack_from("<8sII7Ii", raw, 0)
     geoms = np.frombuffer(raw, np.uint32, ng * 8, 196).reshape(ng, 8)
@@ -723,12 +777,12 @@ def test_geometry_flatten_equals_the_reference_loops_compiled_from_the_mount(whi
     positions = np.frombuffer(raw, np.uint32, nv * 3, off).reshape(nv, 3); off += nv * 12
     vertices = np.frombuffer(raw, np.uint32, nv * 8, off).reshape(nv, 8); off += nv * 32
     indices = np.frombuffer(raw, np.uint32, ni, off)
-    ref.ref_flatten_geometry.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    ref.ref_flatten_geometry.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
     checked = 0
     for g in range(ng):
         mat, vfirst, vcount, ifirst, icount = (int(x) for x in geoms[g][:5])
         P, V, I, counts = np.zeros((vcount, 3), np.uint32), np.zeros((vcount, 8), np.uint32), np.zeros(icount, np.uint32), np.zeros(2, np.int32)
-        assert ref.ref_flatten_geometry(src.encode(), g, P.ctypes.data, V.ctypes.data, I.ctypes.data, vcount, icount, counts.ctypes.data) == 0, g
+        assert ref.ref_flatten_geometry(src.encode(), g, P.ctypes.data, V.ctypes.data, I.ctypes.data, vcount, icount, counts.ctypes.data, insert) == 0, g
         assert counts.tolist() == [vcount, icount]
         assert np.array_equal(P, positions[vfirst:vfirst + vcount]), "positions of shape %d" % g
         assert np.array_equal(I, indices[ifirst:ifirst + icount]), "indices of shape %d" % g
@@ -736,3 +790,6 @@ def test_geometry_flatten_equals_the_reference_loops_compiled_from_the_mount(whi
         assert bad.shape[0] == 0, "shape %d vertex %d word %d (normal 0-2, uv 3-4, tangent 5-7)" % (g, bad[0][0], bad[0][1])
         checked += vcount
     assert checked == nv
+    if which == "instanced":   # instances dropped (the reference build's software path) leaves the floor alone
+        tb.convert_scene(src, dst)
+        assert struct.unpack_from("<8sII7Ii", open(dst, "rb").read(), 0)[3] == 1

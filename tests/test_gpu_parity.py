@@ -213,6 +213,36 @@ def test_png_and_tga_albedo_maps_bit_exact(tmp_path, built):
     assert len(np.unique(alb.reshape(-1, 3), axis=0)) > 200   # the maps are really sampled
 
 
+def test_object_instances_inserted_into_the_bottom_level_bit_exact(tmp_path, built):
+    """LoadScene's bInsertInstancesIntoBLAS mode (TracerBoy.cpp:1355, 1367-1376, 1623-1651) through LoadScene on the .pbrt
+    itself: four instances of three objects under translations, rotations and non-uniform scales join the floor in the
+    one bottom-level structure. BVH bytes and every render buffer equal the oracle's; with the reference build's
+    setting (instances dropped) only the floor is left."""
+    import tracerboy_b200 as tb
+    from tracerboy_b200 import build
+    from oracle import binding
+    from test_cpu_host import INSTANCED_PBRT
+    if not os.path.exists(os.path.join(build.LIB, "libtb_pbrtimport.so")):
+        pytest.skip("PBRT importer not built (needs the reference mount at build time)")
+    src = str(tmp_path / "i.pbrt"); open(src, "w").write(INSTANCED_PBRT)
+    dst = str(tmp_path / "i.tbscene")
+    tb.convert_scene(src, dst, tb.INSTANCES_INSERT_INTO_BLAS)
+    g = tb.TracerBoy(0)
+    g.SetInstanceMode(tb.INSTANCES_INSERT_INTO_BLAS)
+    g.LoadScene(src)
+    assert g.GetSceneInfo().NumGeometries == 5 and g.GetSceneInfo().NumLights == 1
+    g.Resize(160, 120)
+    o = binding.Oracle(); o.LoadScene(dst, 3); o.Resize(160, 120)
+    assert np.array_equal(g.GetBVH(), o.GetBVH())
+    s = tb.get_default_output_settings()
+    _compare_render(g, o, s, 3)
+    geoms = np.unique(g.Readback(tb.BufferKind.PRIMARY_HIT_IDS)[..., 0])
+    assert set(geoms.tolist()) >= {0, 1, 2, 3}            # the floor and the instances are all visible
+    g.SetInstanceMode(tb.INSTANCES_SKIP)
+    g.LoadScene(src)
+    assert g.GetSceneInfo().NumGeometries == 1
+
+
 def test_full_size_properties_vwvan_4k(vwvan):
     """configs[3] at its full 3840x2160: progressive accumulation is exact (3 + 5 == 8 samples), the weight
     channel counts the samples, radiance is finite, and frames in flight do not change a bit."""

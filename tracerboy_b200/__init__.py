@@ -14,10 +14,12 @@ from .api import (TracerBoy, TracerBoyError, OutputSettings, Camera, Material, R
                   SceneInfo, BufferKind, lib_path, load_library, convert_scene, get_default_output_settings,
                   PostProcessSettings, OutputType, TonemapType, get_default_postprocess_settings,
                   TemporalAccumulationParams, write_image, ControllerState, CameraSettings, camera_update,
-                  comm_get_unique_id, prebuild_info, tlas_prebuild_info, InstanceDesc, load_image_file, SHARD_SAMPLES, SHARD_ROWS, GeometryDesc, PrebuildInfo)
+                  comm_get_unique_id, prebuild_info, tlas_prebuild_info, InstanceDesc, load_image_file, SHARD_SAMPLES, SHARD_ROWS, GeometryDesc, PrebuildInfo,
+                  INSTANCES_SKIP, INSTANCES_INSERT_INTO_BLAS)
 
 __all__ = ["TracerBoy", "TracerBoyError", "OutputSettings", "Camera", "Material", "Ray", "Hit", "RenderStats",
            "SceneInfo", "BufferKind", "lib_path", "load_library", "convert_scene", "get_default_output_settings",
            "PostProcessSettings", "OutputType", "TonemapType", "get_default_postprocess_settings",
            "TemporalAccumulationParams", "write_image", "ControllerState", "CameraSettings", "camera_update",
-           "comm_get_unique_id", "prebuild_info", "tlas_prebuild_info", "InstanceDesc", "load_image_file", "SHARD_SAMPLES", "SHARD_ROWS", "GeometryDesc", "PrebuildInfo"]
+           "comm_get_unique_id", "prebuild_info", "tlas_prebuild_info", "InstanceDesc", "load_image_file", "SHARD_SAMPLES", "SHARD_ROWS", "GeometryDesc", "PrebuildInfo",
+           "INSTANCES_SKIP", "INSTANCES_INSERT_INTO_BLAS"]

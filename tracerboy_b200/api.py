@@ -180,6 +180,7 @@ def load_library():
         "tb_create": [i32, C.POINTER(vp)], "tb_load_scene": [vp, C.c_char_p], "tb_load_scene_ex": [vp, C.c_char_p, u32],
         "tb_get_load_status": [vp, C.POINTER(LoadStatus)], "tb_save_scene": [vp, C.c_char_p],
         "tb_convert_scene": [C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t],
+        "tb_convert_scene_ex": [C.c_char_p, C.c_char_p, u32, C.c_char_p, C.c_size_t], "tb_set_instance_mode": [vp, u32],
         "tb_get_scene_info": [vp, C.POINTER(SceneInfo)], "tb_get_bvh_size": [vp, C.POINTER(u64)],
         "tb_get_bvh": [vp, vp, u64], "tb_get_bvh_build_ms": [vp, C.POINTER(C.c_double)],
         "tb_get_default_settings": [C.POINTER(OutputSettings)], "tb_get_camera": [vp, C.POINTER(Camera)],
@@ -221,7 +222,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ["tb_create", "tb_destroy", "tb_last_error", "tb_version", "tb_load_scene", "tb_load_scene_ex",
-                    "tb_get_load_status", "tb_save_scene", "tb_convert_scene", "tb_get_scene_info", "tb_get_bvh_size",
+                    "tb_get_load_status", "tb_save_scene", "tb_convert_scene", "tb_convert_scene_ex", "tb_set_instance_mode", "tb_get_scene_info", "tb_get_bvh_size",
                     "tb_get_bvh", "tb_get_bvh_build_ms", "tb_get_default_settings", "tb_get_camera", "tb_set_camera",
                     "tb_resize", "tb_select_pixel", "tb_get_stats", "tb_render", "tb_samples_rendered",
                     "tb_invalidate_history", "tb_set_frame_shard", "tb_set_row_shard", "tb_buffer_size", "tb_readback", "tb_device_buffer",
@@ -327,10 +328,13 @@ def tlas_prebuild_info(n):
     return info
 
 
-def convert_scene(src, dst):
+INSTANCES_SKIP, INSTANCES_INSERT_INTO_BLAS = 0, 1
+
+
+def convert_scene(src, dst, instance_mode=INSTANCES_SKIP):
     """Host-only: import a scene (.pbrt/.pbf/.tbscene/synthetic:) and write the .tbscene cache."""
     err = C.create_string_buffer(1024)
-    rc = load_library().tb_convert_scene(src.encode(), dst.encode(), err, 1024)
+    rc = load_library().tb_convert_scene_ex(src.encode(), dst.encode(), instance_mode, err, 1024)
     if rc != 0:
         raise TracerBoyError(rc, err.value.decode())
 
@@ -371,6 +375,10 @@ class TracerBoy:
     # --- scene -----------------------------------------------------------
     def LoadScene(self, path, bvh_build_flags=BVH_BUILD_PREFER_FAST_TRACE):
         self._ck(self._lib.tb_load_scene_ex(self._h, path.encode(), bvh_build_flags))
+
+    def SetInstanceMode(self, mode):
+        """INSTANCES_SKIP (the reference's software path) or INSTANCES_INSERT_INTO_BLAS (LoadScene's bInsertInstancesIntoBLAS)."""
+        self._ck(self._lib.tb_set_instance_mode(self._h, mode))
 
     def SaveScene(self, path):
         self._ck(self._lib.tb_save_scene(self._h, path.encode()))

@@ -311,10 +311,10 @@ static int load_host_scene(TbHandle* h, tb::Scene& s, const char* path) {
         std::string so = lib_dir() + "/libtb_pbrtimport.so";
         void* lib = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
         if (!lib) return fail(h, TB_ERR_NOT_IMPL, "PBRT import needs " + so + " (built only when the pbrt-parser sources are available)");
-        typedef int (*ImportFn)(const char*, void*, char*, size_t);
-        ImportFn fn = (ImportFn)dlsym(lib, "tb_pbrt_import");
+        typedef int (*ImportFn)(const char*, uint32_t, void*, char*, size_t);
+        ImportFn fn = (ImportFn)dlsym(lib, "tb_pbrt_import_ex");
         char buf[1024] = {0};
-        if (!fn || fn(path, &s, buf, sizeof(buf)) != 0) return fail(h, TB_ERR_IO, std::string("pbrt import failed: ") + buf);
+        if (!fn || fn(path, h->instanceMode, &s, buf, sizeof(buf)) != 0) return fail(h, TB_ERR_IO, std::string("pbrt import failed: ") + buf);
     } else {
         // AssimpImporter (fbx/obj/...) links a Windows-only binary in the reference; not available
         return fail(h, TB_ERR_NOT_IMPL, "unsupported scene type: " + p);
@@ -336,8 +336,19 @@ TB_API int tb_load_scene_ex(TbHandle* h, const char* path, uint32_t flags) {
 }
 TB_API int tb_load_scene(TbHandle* h, const char* path) { return tb_load_scene_ex(h, path, TB_BVH_BUILD_PREFER_FAST_TRACE); }
 
+TB_API int tb_set_instance_mode(TbHandle* h, uint32_t mode) {
+    if (!h) return TB_ERR_INVALID_ARG;
+    if (mode > TB_INSTANCES_INSERT_INTO_BLAS) return fail(h, TB_ERR_INVALID_ARG, "instance mode must be TB_INSTANCES_SKIP or TB_INSTANCES_INSERT_INTO_BLAS");
+    h->instanceMode = mode;
+    return TB_OK;
+}
+
 TB_API int tb_convert_scene(const char* inPath, const char* outTbscene, char* err, size_t errCap) {
+    return tb_convert_scene_ex(inPath, outTbscene, TB_INSTANCES_SKIP, err, errCap);
+}
+TB_API int tb_convert_scene_ex(const char* inPath, const char* outTbscene, uint32_t instanceMode, char* err, size_t errCap) {
     TbHandle tmp; // host-only use
+    tmp.instanceMode = instanceMode;
     tb::Scene s;
     int rc = load_host_scene(&tmp, s, inPath);
     std::string e = tmp.err;

@@ -40,6 +40,7 @@ struct TbHandle {
     std::string err;
     tb::Scene scene;
     bool sceneLoaded = false;
+    uint32_t instanceMode = 0;      // TB_INSTANCES_*: what the PBRT import does with object instances
     // device scene
     DeviceScene dscene;
     std::vector<void*> sceneAllocs;

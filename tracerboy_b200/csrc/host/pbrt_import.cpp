@@ -27,7 +27,8 @@ struct Importer {
     Scene& out;
     std::string dir;
     std::unordered_map<pbrt::Material*, uint32_t> matIndex; // MaterialTracker, TracerBoy.h:130-156
-    Importer(Scene& s, const std::string& d) : out(s), dir(d) {}
+    bool insertInstancesIntoBLAS; // LoadScene's bInsertInstancesIntoBLAS (TracerBoy.cpp:1355; false in the reference build)
+    Importer(Scene& s, const std::string& d, bool insertInstances) : out(s), dir(d), insertInstancesIntoBLAS(insertInstances) {}
 
     uint32_t add_material(pbrt::Material* key, const TbMaterial& m) {
         uint32_t i = (uint32_t)out.materials.size();
@@ -266,12 +267,27 @@ struct Importer {
         out.camera.Right = cv3(right);
         out.camera.Up = cv3(up);
 
-        // shapes: every top-level shape goes into the one global BLAS (:1361-1366). The SW
-        // path renders only that BLAS (TracerBoy.cpp:2862), so instances are not emitted.
+        // shapes: every top-level shape goes into the one global BLAS (:1361-1366). The SW path renders only that BLAS
+        // (TracerBoy.cpp:2862), so object instances are dropped unless the caller asks for LoadScene's other mode
+        // (bInsertInstancesIntoBLAS, :1355, 1367-1376): then every instance joins the global BLAS as the FIRST shape of
+        // its object with the instance transform baked into positions, normals and tangents (:1623-1624).
         auto& world = scene->world;
-        for (size_t si = 0; si < world->shapes.size(); si++) {
-            auto mesh = std::dynamic_pointer_cast<pbrt::TriangleMesh>(world->shapes[si]);
-            if (auto curve = std::dynamic_pointer_cast<pbrt::Curve>(world->shapes[si])) mesh = tessellate_curves(world->shapes, si, curve);
+        const size_t topLevelShapes = world->shapes.size();
+        const size_t totalSceneInstances = topLevelShapes + (insertInstancesIntoBLAS ? world->instances.size() : 0);
+        for (size_t si = 0; si < totalSceneInstances; si++) {
+            pbrt::Shape::SP geometry;
+            pbrt::affine3f transform = pbrt::affine3f::identity();
+            if (si < topLevelShapes) geometry = world->shapes[si];
+            else {
+                auto& instance = world->instances[si - topLevelShapes];
+                // the reference indexes object->shapes[0] unconditionally; an object without shapes (instances of instances) has nothing to insert
+                if (!instance || !instance->object || instance->object->shapes.empty()) continue;
+                transform = instance->xfm;
+                geometry = instance->object->shapes[0];
+            }
+            auto mesh = std::dynamic_pointer_cast<pbrt::TriangleMesh>(geometry);
+            // (an instanced curve never merges: its loop index is past the top-level shapes, :1437-1438)
+            if (auto curve = std::dynamic_pointer_cast<pbrt::Curve>(geometry)) mesh = tessellate_curves(world->shapes, si, curve);
             if (!mesh) continue; // spheres, disks, ...: skipped as in the reference
             pbrt::vec3f emissive(0.f);
             std::vector<uint32_t> idx(mesh->index.size() * 3);
@@ -296,8 +312,9 @@ struct Importer {
             }
             // The reference pushes every position through `vertexBufferTransform * v` and every normal and tangent
             // through normalize(xfmNormal(vertexBufferTransform, n)) with the transform at identity
-            // (TracerBoy.cpp:1636-1650). The identity products are kept literally: they turn -0 into +0.
-            const pbrt::affine3f vertexBufferTransform = pbrt::affine3f::identity();
+            // (TracerBoy.cpp:1636-1650); an inserted instance carries its own transform. The identity products are kept
+            // literally: they turn -0 into +0. (Area lights above read the UNtransformed vertices, as :1538-1540 does.)
+            const pbrt::affine3f vertexBufferTransform = transform;
             size_t nv = mesh->vertex.size();
             std::vector<TbFloat3> pos(nv), nrm(nv), tan(nv);
             std::vector<TbFloat2> uv(nv);
@@ -352,7 +369,7 @@ struct Importer {
 } // namespace
 
 extern "C" __attribute__((visibility("default")))
-int tb_pbrt_import(const char* path, void* sceneOut, char* err, size_t errCap) {
+int tb_pbrt_import_ex(const char* path, uint32_t instanceMode, void* sceneOut, char* err, size_t errCap) {
     Scene& s = *(Scene*)sceneOut;
     try {
         std::string p(path);
@@ -364,7 +381,7 @@ int tb_pbrt_import(const char* path, void* sceneOut, char* err, size_t errCap) {
         size_t slash = p.find_last_of('/');
         std::string dir = slash == std::string::npos ? "" : p.substr(0, slash + 1);
         s.clear();
-        Importer imp(s, dir);
+        Importer imp(s, dir, instanceMode == TB_INSTANCES_INSERT_INTO_BLAS);
         imp.run(scene);
         return 0;
     } catch (const std::exception& e) {
@@ -372,6 +389,9 @@ int tb_pbrt_import(const char* path, void* sceneOut, char* err, size_t errCap) {
         return -3;
     }
 }
+
+extern "C" __attribute__((visibility("default")))
+int tb_pbrt_import(const char* path, void* sceneOut, char* err, size_t errCap) { return tb_pbrt_import_ex(path, TB_INSTANCES_SKIP, sceneOut, err, errCap); }
 
 // Import + write the .tbscene cache in one call (used by the build step that converts the
 // bundled scenes, and by tb_load_scene when it wants to cache).
