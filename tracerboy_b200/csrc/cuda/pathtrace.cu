@@ -1258,7 +1258,7 @@ __global__ void __launch_bounds__(256) k_walk_step(DeviceScene sc, const FrameCo
 // a walker, the traversal phase steps all lanes' rays together (one code path per iteration), and the service phase
 // runs walk_step for the lanes whose ray has finished, then either starts the walker's next ray or ends its bounce
 // and takes a new walker from queue `wr`.
-__global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, const FrameConstants* __restrict__ fcp, PathState st, int qi, int wr, int bounce) {
+__global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, const FrameConstants* __restrict__ fcp, PathState st, int qi, int wr, int bounce, uint32_t serviceAt) {
     const FrameConstants& fc = *fcp;
     const uint32_t count = st.queueCount[10 + wr];
     uint32_t* __restrict__ next = &st.queueCount[12 + wr];
@@ -1309,7 +1309,7 @@ __global__ void __launch_bounds__(128, 4) k_walk(DeviceBvh bvh, DeviceScene sc, 
             uint32_t mB = __ballot_sync(0xffffffffu, busy), mL = __ballot_sync(0xffffffffu, wantLeaf);
             uint32_t nB = __popc(mB), nL = __popc(mL);
             uint32_t nHave = __popc(__ballot_sync(0xffffffffu, have));
-            if (nB == 0 || nHave - nB >= 8u) break; // enough finished rays to make a walk step (and a refill) worthwhile
+            if (nB == 0 || nHave - nB >= serviceAt) break; // enough finished rays to make a walk step (and a refill) worthwhile
             if (2 * nL > nB) {
                 if (wantLeaf) tr.step_leaf(stack, tris);
             } else {
@@ -1569,7 +1569,13 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
                 k_walk_step<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(sc, fcDev, st, qi, r & 1); launches++;
             }
             uint32_t wblocks = blocks > sms * 4 ? sms * 4 : blocks;
-            k_walk<<<wblocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi, rounds & 1, b); launches++;
+            static int serviceEnv = -2; // tuning knob (results never depend on it)
+            if (serviceEnv == -2) { const char* e = getenv("TB_WALK_SERVICE"); serviceEnv = e ? atoi(e) : -1; }
+            // finished rays that end a traversal phase: a walk step is long divergent code, so on a cache-resident tree
+            // (cheap traversal) it pays to batch more of them; on an HBM-resident tree idle lanes cost more than that.
+            // Measured (profiles/r2_walk_service_sweep.log): vw-van 8 -> 24 +3.8 %, 20.8 M triangles 8 -> 16 -5 %
+            const uint32_t serviceAt = serviceEnv > 0 ? (uint32_t)serviceEnv : (bvh.numPrims < (1u << 22) ? 24u : 8u);
+            k_walk<<<wblocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi, rounds & 1, b, serviceAt); launches++;
         }
         if (timers) cudaEventRecord(timers->next(KernelTimers::END, b), stream);
     }
