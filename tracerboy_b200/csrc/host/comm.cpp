@@ -28,11 +28,8 @@ struct NcclApi {
     bool ok = false;
 };
 
-NcclApi& nccl() {
-    static NcclApi api;
-    static bool tried = false;
-    if (tried) return api;
-    tried = true;
+NcclApi load_nccl() {
+    NcclApi api;
     const char* override_ = getenv("TB_NCCL_LIB");
     void* lib = nullptr;
     if (override_) lib = dlopen(override_, RTLD_NOW | RTLD_LOCAL);
@@ -50,6 +47,10 @@ NcclApi& nccl() {
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
     api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
     api.ok = api.error.empty();
+    return api;
+}
+NcclApi& nccl() {
+    static NcclApi api = load_nccl(); // bound once, by whichever thread gets here first
     return api;
 }
 
