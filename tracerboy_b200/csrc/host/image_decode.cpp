@@ -205,6 +205,14 @@ bool decode_png(const std::vector<uint8_t>& file, Image& img, bool* hasAlpha, st
     std::vector<uint8_t> raw;
     try { inflate(idat.data(), idat.size(), raw); } catch (const std::exception& e) { err = std::string("PNG: ") + e.what(); return false; }
     const uint32_t bitsPerPixel = channels * depth, bpp = bitsPerPixel >= 8 ? bitsPerPixel / 8 : 1;
+    static const uint32_t xs[7] = {0, 4, 0, 2, 0, 1, 0}, ys[7] = {0, 0, 4, 0, 2, 0, 1}, dxs[7] = {8, 8, 4, 4, 2, 2, 1}, dys[7] = {8, 8, 8, 4, 4, 2, 2}; // Adam7
+    auto pass_width = [&](int p) { return w > xs[p] ? (w - xs[p] + dxs[p] - 1) / dxs[p] : 0u; };
+    auto pass_height = [&](int p) { return h > ys[p] ? (h - ys[p] + dys[p] - 1) / dys[p] : 0u; };
+    // the header is not trusted with an allocation: the inflated stream has to hold every scanline it announces
+    size_t expected = 0;
+    if (!interlace) expected = (size_t)h * (1 + ((size_t)w * bitsPerPixel + 7) / 8);
+    else for (int p = 0; p < 7; p++) if (pass_width(p) && pass_height(p)) expected += (size_t)pass_height(p) * (1 + ((size_t)pass_width(p) * bitsPerPixel + 7) / 8);
+    if (raw.size() < expected) { err = "PNG: image data shorter than the header's dimensions"; return false; }
     // samples[(y * w + x) * channels + c] as 16-bit values at the file's bit depth
     std::vector<uint16_t> samples((size_t)w * h * channels);
     auto unpack = [&](const std::vector<uint8_t>& rows, uint32_t pw, uint32_t ph, uint32_t x0, uint32_t y0, uint32_t dx, uint32_t dy) {
@@ -226,10 +234,9 @@ bool decode_png(const std::vector<uint8_t>& file, Image& img, bool* hasAlpha, st
             unfilter(raw.data(), raw.size(), h, ((size_t)w * bitsPerPixel + 7) / 8, bpp, rows);
             unpack(rows, w, h, 0, 0, 1, 1);
         } else { // Adam7
-            static const uint32_t xs[7] = {0, 4, 0, 2, 0, 1, 0}, ys[7] = {0, 0, 4, 0, 2, 0, 1}, dxs[7] = {8, 8, 4, 4, 2, 2, 1}, dys[7] = {8, 8, 8, 4, 4, 2, 2};
             size_t off = 0;
             for (int p = 0; p < 7; p++) {
-                const uint32_t pw = (w > xs[p]) ? (w - xs[p] + dxs[p] - 1) / dxs[p] : 0, ph = (h > ys[p]) ? (h - ys[p] + dys[p] - 1) / dys[p] : 0;
+                const uint32_t pw = pass_width(p), ph = pass_height(p);
                 if (!pw || !ph) continue;
                 off += unfilter(raw.data() + off, raw.size() - off, ph, ((size_t)pw * bitsPerPixel + 7) / 8, bpp, rows);
                 unpack(rows, pw, ph, xs[p], ys[p], dxs[p], dys[p]);
