@@ -464,7 +464,9 @@ def main():
             "rays_per_step": rays_total / args.steps,
             "wall_ms_per_step": 1e3 * wall / args.steps,
             "reduce_ms_per_step": 1e3 * red_s / args.steps if world > 1 else None,
-            "comm": None if comm is None else {"nccl_version": comm.NcclVersion, "bytes_received_per_reduction": comm.BytesReceivedPerReduction},
+            "comm": None if comm is None else {"nccl_version": comm.NcclVersion, "bytes_received_per_reduction": comm.BytesReceivedPerReduction,
+                                                   "transport": "peer memory (one kernel per rank over CUDA IPC mappings, NVLink)" if comm.Transport == 1
+                                                   else "nccl all-gather + combine kernels"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(host_in.numel()),
                     "d2h_bytes_per_step": int(host_img.numel() * 4), "ms_per_step": 1e3 * wall_e / args.steps,
                     "image": "resolved rgb of the whole job (after the reduction)" if world > 1 else "resolved rgb"},

@@ -367,7 +367,11 @@ typedef struct TbCommInfo {
     uint64_t BytesReceivedPerReduction;  /* over NVLink, per rank */
     double LastReductionMilliseconds;    /* CUDA events around pack + all-gather + combine */
     double TotalReductionMilliseconds;   /* the same, summed over all reductions */
+    uint32_t Transport;                  /* TB_COMM_TRANSPORT_* of the last reduction (NCCL until the first one) */
+    uint32_t Reserved;
 } TbCommInfo;
+#define TB_COMM_TRANSPORT_NCCL 0u /* ncclAllGather of the buffers + local combine kernels */
+#define TB_COMM_TRANSPORT_PEER 1u /* one kernel per rank over the other GPUs' memory (CUDA IPC mappings, NVLink) */
 
 typedef struct TbHandle TbHandle; /* opaque; owns all device memory */
 
@@ -483,7 +487,12 @@ TB_API int tb_synchronize(TbHandle* h);
  * its TB_COMM_ID_BYTES bytes to the other processes by whatever means the host has (MPI, torch.distributed, a file);
  * every process then calls tb_comm_init on its handle (ncclCommInitRank on the handle's device), which also sets the
  * handle's shard (tb_set_frame_shard / tb_set_row_shard) to (rank, nranks). Scene and BVH are replicated: every rank
- * loads the same scene; the build is deterministic. NCCL is loaded at run time (libnccl.so.2; TB_NCCL_LIB overrides). */
+ * loads the same scene; the build is deterministic. NCCL is loaded at run time (libnccl.so.2; TB_NCCL_LIB overrides).
+ * On one node the ranks map each other's accumulation buffers (CUDA IPC) and the reduction is one kernel per rank over
+ * peer memory (TbCommInfo::Transport == TB_COMM_TRANSPORT_PEER; TB_COMM_TRANSPORT=nccl in the environment forces the
+ * all-gather transport, which is also the fallback when a mapping cannot be opened). While buffers are mapped, the calls
+ * that free them - tb_resize, tb_set_frames_in_flight, tb_comm_destroy, tb_destroy - are COLLECTIVE as well: every rank
+ * makes them, and a rank waits (at most 10 s) for the others before it frees memory they may have open. */
 TB_API int tb_comm_get_unique_id(void* id, uint64_t bytes);
 TB_API int tb_comm_init(TbHandle* h, const void* id, int rank, int nranks, uint32_t shardMode);
 TB_API int tb_comm_destroy(TbHandle* h);

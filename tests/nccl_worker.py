@@ -41,13 +41,21 @@ def main():
     rgb = g.Readback(tb.BufferKind.RESOLVED_RGB).copy()
     info = g.CommInfo()
     assert info.Reductions == 1 and info.NumRanks == nranks and info.Rank == rank
+    want_peer = os.environ.get("TB_COMM_TRANSPORT", "peer") != "nccl" and nranks > 1
+    assert info.Transport == (tb.api.COMM_TRANSPORT_PEER if want_peer else tb.api.COMM_TRANSPORT_NCCL), info.Transport
     # progressive: more frames, then the image again
     g.Render(s, per_rank, 0.0)
     accum2 = g.Readback(tb.BufferKind.ACCUM_RGBW).copy()
     info = g.CommInfo()
     assert info.Reductions == 2
-    np.savez(os.path.join(workdir, "rank%d.npz" % rank), local=local, accum=accum, jittered=jit, rgb=rgb, accum2=accum2,
-             rays=np.array([g.GetRenderStats().RaysTraced], np.uint64),
+    rays = g.GetRenderStats().RaysTraced
+    # a resize in the middle of the job (collective while peers are mapped): buffers are unmapped, freed, mapped again
+    g.Resize(w // 2, h // 2)
+    g.Render(s, per_rank, 0.0)
+    small = g.Readback(tb.BufferKind.ACCUM_RGBW).copy()
+    small_local = g.Readback(tb.BufferKind.LOCAL_ACCUM_RGBW).copy()
+    np.savez(os.path.join(workdir, "rank%d.npz" % rank), local=local, accum=accum, jittered=jit, rgb=rgb, accum2=accum2, small=small, small_local=small_local,
+             rays=np.array([rays], np.uint64),
              comm=np.array([info.NcclVersion, info.BytesReceivedPerReduction, int(info.LastReductionMilliseconds * 1e3)], np.uint64))
     g.CommDestroy()
     g.close()

@@ -1,6 +1,6 @@
 """Multi-GPU inside the product: N processes, one GPU and one TbHandle each, joined by tb_comm_init; the
-only exchange step is the deterministic reduction of the accumulation buffers (NCCL all-gather over NVLink + the
-library's own combine kernels). Needs >= 2 GPUs (skipped on a one-GPU box; run with `gpurun --gpus 2`)."""
+only exchange step is the deterministic reduction of the accumulation buffers, over both transports: one kernel per rank
+over the other GPUs' memory (CUDA IPC mappings, NVLink), and the NCCL all-gather + the library's own combine kernels. Needs >= 2 GPUs (skipped on a one-GPU box; run with `gpurun --gpus 2`)."""
 import os
 import subprocess
 import sys
@@ -17,9 +17,10 @@ def _gpus():
     return torch.cuda.device_count()
 
 
-def _run_ranks(nranks, mode, scene, w, h, spp, bounces, workdir):
+def _run_ranks(nranks, mode, scene, w, h, spp, bounces, workdir, transport="peer"):
+    env = dict(os.environ, TB_COMM_TRANSPORT=transport)
     procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "nccl_worker.py"), str(r), str(nranks), mode, scene, str(w), str(h),
-                               str(spp), str(bounces), str(workdir)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                               str(spp), str(bounces), str(workdir)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
              for r in range(nranks)]
     outs = []
     for p in procs:
@@ -47,12 +48,25 @@ def _single(scene, w, h, spp, bounces):
     return out
 
 
+def _check_after_resize(ranks):
+    """The job-wide image rendered after a mid-job tb_resize (buffers unmapped, freed and mapped again): the fixed-order
+    sum of the ranks' local buffers (row bands: disjoint, so the sum is their union), the same bits on every rank."""
+    want = ranks[0]["small_local"].copy()
+    for d in ranks[1:]:
+        want = want + d["small_local"]
+    assert want[..., 3].min() > 0
+    for r, d in enumerate(ranks):
+        assert np.array_equal(d["small"].view(np.uint32), want.view(np.uint32)), "rank %d after the resize" % r
+
+
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("nranks", [2, 4, 8])
-def test_row_bands_over_nccl_are_bit_identical_to_one_gpu(nranks, cornell, tmp_path):
+def test_row_bands_over_nccl_are_bit_identical_to_one_gpu(nranks, transport, cornell, tmp_path):
     if _gpus() < nranks:
         pytest.skip("needs %d GPUs" % nranks)
     w, h, spp, bounces = 200, 150, 6, 4   # 19 bands of 8 rows (the last one partial): uneven over the ranks
-    ranks = _run_ranks(nranks, "rows", cornell, w, h, spp, bounces, tmp_path)
+    ranks = _run_ranks(nranks, "rows", cornell, w, h, spp, bounces, tmp_path, transport)
+    _check_after_resize(ranks)
     one = _single(cornell, w, h, spp, bounces)
     for r, d in enumerate(ranks):
         rows = (np.arange(h) // 8) % nranks == r
@@ -64,12 +78,14 @@ def test_row_bands_over_nccl_are_bit_identical_to_one_gpu(nranks, cornell, tmp_p
     assert sum(int(d["rays"][0]) for d in ranks) == one["rays"]
 
 
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("nranks", [2, 4, 8])
-def test_sample_shards_over_nccl_sum_in_rank_order(nranks, cornell, tmp_path):
+def test_sample_shards_over_nccl_sum_in_rank_order(nranks, transport, cornell, tmp_path):
     if _gpus() < nranks:
         pytest.skip("needs %d GPUs" % nranks)
     w, h, spp, bounces = 128, 96, 8 * nranks, 4
-    ranks = _run_ranks(nranks, "samples", cornell, w, h, spp, bounces, tmp_path)
+    ranks = _run_ranks(nranks, "samples", cornell, w, h, spp, bounces, tmp_path, transport)
+    _check_after_resize(ranks)
     want = ranks[0]["local"].copy()
     for d in ranks[1:]:
         want = want + d["local"]          # float32, rank order: ((r0 + r1) + r2) + ...

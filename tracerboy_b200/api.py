@@ -133,10 +133,11 @@ class PrebuildInfo(C.Structure):
 class CommInfo(C.Structure):
     _fields_ = [("Rank", C.c_uint32), ("NumRanks", C.c_uint32), ("ShardMode", C.c_uint32), ("NcclVersion", C.c_uint32),
                 ("Reductions", C.c_uint64), ("BytesReceivedPerReduction", C.c_uint64), ("LastReductionMilliseconds", C.c_double),
-                ("TotalReductionMilliseconds", C.c_double)]
+                ("TotalReductionMilliseconds", C.c_double), ("Transport", C.c_uint32), ("Reserved", C.c_uint32)]
 
 
 SHARD_SAMPLES, SHARD_ROWS = 1, 2
+COMM_TRANSPORT_NCCL, COMM_TRANSPORT_PEER = 0, 1
 COMM_ID_BYTES = 128
 
 

@@ -10,6 +10,14 @@
 //
 // All three kernels are pure HBM streams of 128-bit loads / stores: 16 B in + 16 B out per pixel (pack / unpack),
 // 16 N B in + 16 B out per pixel (sum).
+//
+// Peer-memory transport (comm.cpp maps every rank's buffers into every process with CUDA IPC): the exchange and the
+// combine are ONE kernel per rank that loads from and stores to the other GPUs' memory over NVLink.
+//   k_sum_peers      rank r owns pixels [r n/N, (r+1) n/N): it reads that slice of every rank's accumulation buffers,
+//                    adds them in the same fixed rank order and stores the sum into every rank's result buffers
+//                    (a reduce-scatter and an all-gather in one pass: 2 (N-1)/N of a buffer crosses NVLink per rank
+//                    and direction, instead of N-1 whole buffers received by the all-gather transport).
+//   k_scatter_bands_peers  row bands: a rank stores its own bands straight into every rank's result buffers.
 #include "reduce.h"
 
 namespace tbd {
@@ -46,6 +54,37 @@ __global__ void __launch_bounds__(256) k_unpack_bands(const float4* __restrict__
     }
 }
 
+// table[b * nranks + r]: buffer b of rank r as mapped into this process; b = 0 accumulation (OutputTexture), 1 jittered
+// accumulation, 2 job-wide accumulation, 3 job-wide jittered accumulation
+__global__ void __launch_bounds__(256) k_sum_peers(float4* const* __restrict__ table, uint32_t nranks, size_t first, size_t last) {
+    for (size_t i = first + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < last; i += (size_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (uint32_t b = 0; b < 2; b++) {
+            float4 a = table[b * nranks][i];
+            for (uint32_t r = 1; r < nranks; r++) { // the order of k_sum_ranks: ((r0 + r1) + r2) + ...
+                const float4 v = table[b * nranks + r][i];
+                a.x = a.x + v.x; a.y = a.y + v.y; a.z = a.z + v.z; a.w = a.w + v.w;
+            }
+            for (uint32_t r = 0; r < nranks; r++) table[(2 + b) * nranks + r][i] = a;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scatter_bands_peers(float4* const* __restrict__ table, uint32_t nranks, uint32_t rank, uint32_t width, uint32_t height,
+                                                             size_t chunkPixels) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < chunkPixels; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t row = (uint32_t)(i / width), x = (uint32_t)(i % width);
+        const uint32_t y = ((row >> 3) * nranks + rank) * 8u + (row & 7u);
+        if (y >= height) continue;
+        const size_t p = (size_t)y * width + x;
+#pragma unroll
+        for (uint32_t b = 0; b < 2; b++) {
+            const float4 v = table[b * nranks + rank][p];
+            for (uint32_t r = 0; r < nranks; r++) table[(2 + b) * nranks + r][p] = v;
+        }
+    }
+}
+
 inline uint32_t stream_grid(size_t items, int numSMs) {
     size_t blocks = (items + 255) / 256, cap = (size_t)(numSMs > 0 ? numSMs : 148) * 8; // persistent: 8 blocks of 256 per SM
     return (uint32_t)(blocks < cap ? (blocks ? blocks : 1) : cap);
@@ -71,6 +110,18 @@ cudaError_t pack_bands(const float4* src, uint32_t width, uint32_t height, uint3
 cudaError_t unpack_bands(const float4* gathered, size_t rankStridePixels, uint32_t width, uint32_t height, uint32_t stride, float4* out, int numSMs,
                          cudaStream_t stream, LaunchCounter& lc) {
     k_unpack_bands<<<stream_grid((size_t)width * height, numSMs), 256, 0, stream>>>(gathered, width, height, stride, rankStridePixels, out); lc.count++;
+    return cudaGetLastError();
+}
+
+cudaError_t sum_peers(float4* const* table, uint32_t nranks, uint32_t rank, size_t pixels, int numSMs, cudaStream_t stream, LaunchCounter& lc) {
+    const size_t slice = (pixels + nranks - 1) / nranks, first = slice * rank < pixels ? slice * rank : pixels, last = first + slice < pixels ? first + slice : pixels;
+    if (last > first) { k_sum_peers<<<stream_grid(last - first, numSMs), 256, 0, stream>>>(table, nranks, first, last); lc.count++; }
+    return cudaGetLastError();
+}
+cudaError_t scatter_bands_peers(float4* const* table, uint32_t nranks, uint32_t rank, uint32_t width, uint32_t height, int numSMs, cudaStream_t stream,
+                                LaunchCounter& lc) {
+    const size_t chunk = band_chunk_pixels(width, height, nranks);
+    k_scatter_bands_peers<<<stream_grid(chunk, numSMs), 256, 0, stream>>>(table, nranks, rank, width, height, chunk); lc.count++;
     return cudaGetLastError();
 }
 

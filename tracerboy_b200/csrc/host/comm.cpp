@@ -5,10 +5,22 @@
 // exchange step is the reduction of the float4 accumulation buffers at readback, implemented here as an NCCL
 // all-gather over NVLink followed by this library's own deterministic combine kernels (csrc/cuda/reduce.cu).
 //
+// Two transports for that step (TbCommInfo::Transport):
+//   TB_COMM_TRANSPORT_PEER   every rank maps the other ranks' buffers with CUDA IPC (same node, NVLink / NVSwitch); one
+//                            kernel per rank then reads its slice from all peers, sums in fixed rank order and stores
+//                            the result into all peers (reduce.cu: k_sum_peers / k_scatter_bands_peers). NCCL only
+//                            carries the 64-byte IPC handles at setup and a 4-byte all-gather before and after the
+//                            kernel that orders the ranks' streams.
+//   TB_COMM_TRANSPORT_NCCL   ncclAllGather of whole buffers (or packed bands) + local combine kernels; used when a
+//                            mapping cannot be opened (different nodes, IPC not permitted) or TB_COMM_TRANSPORT=nccl.
+// Both produce the same bits.
+//
 // NCCL is bound at run time (dlopen of libnccl.so.2, preferring a copy the process has already loaded, e.g. the one
 // bundled with PyTorch) so that the library has no link-time dependency on it: single-GPU users never touch it.
 #include <dlfcn.h>
 #include <cstring>
+#include <ctime>
+#include <vector>
 #include <nccl.h>
 #include "../cuda/reduce.h"
 #include "handle.h"
@@ -56,20 +68,106 @@ NcclApi& nccl() {
 
 #define NCCL_OK(h, call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) return fail(h, TB_ERR_NCCL, std::string(#call) + ": " + nccl().GetErrorString(r__)); } while (0)
 
-void release_buffers(tbh::Comm* c) {
-    for (void* p : {(void*)c->gather, (void*)c->pack, (void*)c->reducedAccum, (void*)c->reducedJittered}) if (p) cudaFree(p);
+// orders the ranks' streams: when it completes here, every rank's stream has reached it
+ncclResult_t stream_barrier(tbh::Comm* c, cudaStream_t stream) {
+    return nccl().AllGather(c->barrier + c->rank, c->barrier, 1, ncclUint32, (ncclComm_t)c->nccl, stream);
+}
+
+// COLLECTIVE when peers are mapped: nobody frees a buffer another rank still has open (undefined behaviour per the
+// CUDA IPC contract). If the other ranks do not show up within 10 s the exported buffers are leaked instead of freed.
+void release_buffers(TbHandle* h, tbh::Comm* c) {
+    bool freeExported = true;
+    if (c->peer) {
+        cudaStreamSynchronize(h->stream);
+        for (void* p : c->imported) cudaIpcCloseMemHandle(p);
+        c->imported.clear();
+        freeExported = false;
+        if (nccl().ok && c->nccl && stream_barrier(c, h->stream) == ncclSuccess) {
+            for (int ms = 0; ms < 10000 && !freeExported; ms++) {
+                if (cudaStreamQuery(h->stream) == cudaSuccess) freeExported = true;
+                else { struct timespec ts = {0, 1000000}; nanosleep(&ts, nullptr); }
+            }
+        }
+        cudaGetLastError();
+        c->peer = false;
+    }
+    for (void* p : {(void*)c->gather, (void*)c->pack, (void*)c->peerTable, (void*)c->barrier}) if (p) cudaFree(p);
+    if (freeExported) { if (c->reducedAccum) cudaFree(c->reducedAccum); if (c->reducedJittered) cudaFree(c->reducedJittered); }
     c->gather = c->pack = c->reducedAccum = c->reducedJittered = nullptr;
+    c->peerTable = nullptr; c->barrier = nullptr;
     c->pixels = 0;
     c->valid = false;
+}
+
+// all-gather of a few host bytes per rank (IPC handles, flags) through a device staging buffer
+int exchange_bytes(TbHandle* h, tbh::Comm* c, const void* mine, size_t bytes, std::vector<uint8_t>& all) {
+    const size_t N = (size_t)c->nranks;
+    all.assign(bytes * N, 0);
+    uint8_t* d = nullptr;
+    CUDA_OK(h, cudaMalloc((void**)&d, bytes * N));
+    struct Guard { uint8_t* p; ~Guard() { cudaFree(p); } } guard{d};
+    CUDA_OK(h, cudaMemcpyAsync(d + bytes * c->rank, mine, bytes, cudaMemcpyHostToDevice, h->stream));
+    NCCL_OK(h, nccl().AllGather(d + bytes * c->rank, d, bytes, ncclChar, (ncclComm_t)c->nccl, h->stream));
+    CUDA_OK(h, cudaMemcpyAsync(all.data(), d, bytes * N, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return TB_OK;
+}
+
+// Maps every rank's four buffers into this process. All ranks reach the same verdict (c->peer): one rank that cannot
+// export or open a mapping sends everybody to the NCCL transport.
+int setup_peers(TbHandle* h, tbh::Comm* c) {
+    c->peer = false;
+    const uint32_t N = (uint32_t)c->nranks;
+    if (N < 2) return TB_OK;
+    const char* t = getenv("TB_COMM_TRANSPORT");
+    struct Record { cudaIpcMemHandle_t handle[4]; uint32_t ok; uint32_t pad[15]; } mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.ok = !(t && strcmp(t, "nccl") == 0);
+    void* bufs[4] = {h->st.accum, h->st.jittered, c->reducedAccum, c->reducedJittered};
+    for (int b = 0; b < 4 && mine.ok; b++)
+        if (cudaIpcGetMemHandle(&mine.handle[b], bufs[b]) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+    std::vector<uint8_t> all;
+    int rc = exchange_bytes(h, c, &mine, sizeof(mine), all);
+    if (rc != TB_OK) return rc;
+    const Record* recs = (const Record*)all.data();
+    uint32_t opened = 1;
+    for (uint32_t r = 0; r < N; r++) opened &= recs[r].ok;
+    std::vector<float4*> table(4 * (size_t)N, nullptr);
+    if (opened)
+        for (uint32_t r = 0; r < N; r++)
+            for (int b = 0; b < 4; b++) {
+                void* p = bufs[b];
+                if (r != (uint32_t)c->rank) {
+                    p = nullptr;
+                    if (cudaIpcOpenMemHandle(&p, recs[r].handle[b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened = 0; p = nullptr; }
+                    else c->imported.push_back(p);
+                }
+                table[(size_t)b * N + r] = (float4*)p;
+            }
+    rc = exchange_bytes(h, c, &opened, sizeof(opened), all);
+    if (rc != TB_OK) return rc;
+    for (uint32_t r = 0; r < N; r++) opened &= ((const uint32_t*)all.data())[r];
+    CUDA_OK(h, cudaMalloc((void**)&c->barrier, 4 * N));
+    CUDA_OK(h, cudaMemsetAsync(c->barrier, 0, 4 * N, h->stream));
+    if (!opened) { // somebody could not: close what was opened here, once everybody is past the exchange above
+        for (void* p : c->imported) cudaIpcCloseMemHandle(p);
+        c->imported.clear();
+        return TB_OK;
+    }
+    CUDA_OK(h, cudaMalloc((void**)&c->peerTable, sizeof(float4*) * table.size()));
+    CUDA_OK(h, cudaMemcpyAsync(c->peerTable, table.data(), sizeof(float4*) * table.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream)); // `table` is a local
+    c->peer = true;
+    return TB_OK;
 }
 
 } // namespace
 
 namespace tbh {
-void comm_release_buffers(TbHandle* h) { if (h->comm) release_buffers(h->comm); }
+void comm_release_buffers(TbHandle* h) { if (h->comm) release_buffers(h, h->comm); }
 void comm_destroy(TbHandle* h) {
     if (!h->comm) return;
-    release_buffers(h->comm);
+    release_buffers(h, h->comm);
     if (h->comm->nccl && nccl().ok) nccl().CommDestroy((ncclComm_t)h->comm->nccl);
     if (h->comm->ev0) cudaEventDestroy(h->comm->ev0);
     if (h->comm->ev1) cudaEventDestroy(h->comm->ev1);
@@ -127,6 +225,7 @@ TB_API int tb_comm_info(TbHandle* h, TbCommInfo* out) {
     out->Rank = (uint32_t)h->comm->rank; out->NumRanks = (uint32_t)h->comm->nranks; out->ShardMode = h->comm->mode;
     out->Reductions = h->comm->reductions; out->BytesReceivedPerReduction = h->comm->bytesPerReduction;
     out->LastReductionMilliseconds = h->comm->lastMs; out->TotalReductionMilliseconds = h->comm->totalMs;
+    out->Transport = h->comm->peer ? TB_COMM_TRANSPORT_PEER : TB_COMM_TRANSPORT_NCCL;
     if (nccl().ok) { int v = 0; if (nccl().GetVersion(&v) == ncclSuccess) out->NcclVersion = (uint32_t)v; }
     return TB_OK;
 }
@@ -142,18 +241,32 @@ TB_API int tb_comm_reduce(TbHandle* h) {
     const size_t n = (size_t)h->width * h->height;
     const uint32_t N = (uint32_t)c->nranks;
     const size_t chunk = band_chunk_pixels(h->width, h->height, N);
-    if (c->pixels != n) { // (re)allocate for this resolution
-        release_buffers(c);
-        const size_t gatherPixels = c->mode == TB_SHARD_ROWS ? 2 * chunk * N : 2 * n * N;
-        CUDA_OK(h, cudaMalloc((void**)&c->gather, 16 * gatherPixels));
-        if (c->mode == TB_SHARD_ROWS) CUDA_OK(h, cudaMalloc((void**)&c->pack, 16 * 2 * chunk));
+    if (c->pixels != n) { // (re)allocate for this resolution; every rank takes the same branch (tb_resize is per job)
+        release_buffers(h, c);
         CUDA_OK(h, cudaMalloc((void**)&c->reducedAccum, 16 * n));
         CUDA_OK(h, cudaMalloc((void**)&c->reducedJittered, 16 * n));
+        int rc = setup_peers(h, c);
+        if (rc != TB_OK) return rc;
+        if (!c->peer) { // the all-gather transport's staging
+            const size_t gatherPixels = c->mode == TB_SHARD_ROWS ? 2 * chunk * N : 2 * n * N;
+            CUDA_OK(h, cudaMalloc((void**)&c->gather, 16 * gatherPixels));
+            if (c->mode == TB_SHARD_ROWS) CUDA_OK(h, cudaMalloc((void**)&c->pack, 16 * 2 * chunk));
+        }
         c->pixels = n;
     }
     ncclComm_t comm = (ncclComm_t)c->nccl;
     CUDA_OK(h, cudaEventRecord(c->ev0, h->stream));
-    if (c->mode == TB_SHARD_ROWS) {
+    if (c->peer) {
+        // barrier: every rank's frames are complete and nobody still reads the previous job-wide image; one kernel that
+        // loads from / stores to all peers; barrier: every rank's part has landed everywhere
+        NCCL_OK(h, stream_barrier(c, h->stream));
+        if (c->mode == TB_SHARD_ROWS) CUDA_OK(h, scatter_bands_peers(c->peerTable, N, (uint32_t)c->rank, h->width, h->height, h->numSMs, h->stream, h->lc));
+        else CUDA_OK(h, sum_peers(c->peerTable, N, (uint32_t)c->rank, n, h->numSMs, h->stream, h->lc));
+        NCCL_OK(h, stream_barrier(c, h->stream));
+        // arriving over NVLink per rank: rows: the other ranks' bands; samples: the other ranks' parts of this rank's
+        // slice (loads) + the other ranks' finished slices (their stores)
+        c->bytesPerReduction = c->mode == TB_SHARD_ROWS ? 16ull * 2 * (n - (chunk < n ? chunk : n)) : 16ull * 2 * 2 * ((n + N - 1) / N) * (N - 1);
+    } else if (c->mode == TB_SHARD_ROWS) {
         // my bands of both buffers -> one packed chunk -> all-gather -> scatter every rank's bands back into place
         CUDA_OK(h, pack_bands(h->st.accum, h->width, h->height, (uint32_t)c->rank, N, c->pack, h->numSMs, h->stream, h->lc));
         CUDA_OK(h, pack_bands(h->st.jittered, h->width, h->height, (uint32_t)c->rank, N, c->pack + chunk, h->numSMs, h->stream, h->lc));

@@ -27,6 +27,11 @@ struct Comm {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t reductions = 0, bytesPerReduction = 0;
     double lastMs = 0.0, totalMs = 0.0;
+    // peer-memory transport: every rank's accumulation and job-wide buffers mapped into this process (CUDA IPC over NVLink)
+    bool peer = false;
+    float4** peerTable = nullptr;    // device: [4][nranks] pointers (reduce.h)
+    std::vector<void*> imported;     // the other ranks' buffers as opened here (cudaIpcCloseMemHandle on release)
+    uint32_t* barrier = nullptr;     // device: nranks words, the tiny all-gather that orders the ranks' streams
 };
 int resolve_bottom_level(TbHandle* h, const void* as, cudaStream_t stream, tbd::DeviceBvh& out); // api.cpp
 void comm_release_buffers(TbHandle* h);
