@@ -1,0 +1,23 @@
+#!/bin/bash
+# Final pass of the round on one B200: the whole GPU test suite, then the bench lines of every workload + the reference arm.
+tag=${1:-r2z}; out=gpurun_out
+python -m pytest tests -m gpu -q -x 2>&1 | tail -6 > $out/${tag}_gpu_tests.log; cat $out/${tag}_gpu_tests.log
+python bench.py > $out/${tag}_bench_teapot.json 2> $out/${tag}_bench_teapot.err
+python bench.py --impl reference > $out/${tag}_bench_teapot_reference.json 2> $out/${tag}_bench_teapot_reference.err
+python bench.py --workload cornell --no-cpu-baseline > $out/${tag}_bench_cornell.json 2> $out/${tag}_bench_cornell.err
+python bench.py --workload dragon --steps 2 --no-cpu-baseline > $out/${tag}_bench_dragon.json 2> $out/${tag}_bench_dragon.err
+python bench.py --workload vwvan --steps 3 --no-cpu-baseline > $out/${tag}_bench_vwvan.json 2> $out/${tag}_bench_vwvan.err
+python bench.py --workload blobs20m --spp 32 --steps 2 --no-cpu-baseline > $out/${tag}_bench_blobs20m.json 2> $out/${tag}_bench_blobs20m.err
+python bench.py --workload blobs871k --steps 2 --no-cpu-baseline > $out/${tag}_bench_blobs871k.json 2> $out/${tag}_bench_blobs871k.err
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+for f in teapot cornell dragon vwvan blobs20m blobs871k; do python - <<PY
+import json
+try:
+    d = json.loads(open("$out/${tag}_bench_$f.json").read().strip().splitlines()[-1])
+    inc = d.get("incoherent") or {}
+    print("$f", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "incoherent", round(inc.get("mrays_per_s", 0), 1), "frac", round(d["roofline"]["frac"], 3), "build ms", round(d["bvh_build_ms"], 2))
+except Exception as e:
+    print("$f", "failed", e)
+PY
+done
+tail -c 400 $out/${tag}_bench_teapot_reference.json
