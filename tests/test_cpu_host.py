@@ -641,9 +641,11 @@ ObjectBegin "b"
 ObjectEnd
 # object c: an emissive triangle (its light is built from the UNtransformed vertices, TracerBoy.cpp:1538-1540)
 ObjectBegin "c"
-  AreaLightSource "diffuse" "rgb L" [4 3 2]
-  NamedMaterial "red"
-  Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0  1 0 0  0 0 1]
+  AttributeBegin
+    AreaLightSource "diffuse" "rgb L" [4 3 2]
+    NamedMaterial "red"
+    Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0  1 0 0  0 0 1]
+  AttributeEnd
 ObjectEnd
 NamedMaterial "red"
 Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-20 -2 -20  20 -2 -20  20 -2 20  -20 -2 20]

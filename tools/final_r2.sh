@@ -1,7 +1,7 @@
 #!/bin/bash
 # Final pass of the round on one B200: the whole GPU test suite, then the bench lines of every workload + the reference arm.
 tag=${1:-r2z}; out=gpurun_out
-python -m pytest tests -m gpu -q -x 2>&1 | tail -6 > $out/${tag}_gpu_tests.log; cat $out/${tag}_gpu_tests.log
+python -m pytest tests -m gpu -q 2>&1 | grep -v "pbrt-parser\|created object" | tail -12 > $out/${tag}_gpu_tests.log; cat $out/${tag}_gpu_tests.log
 python bench.py > $out/${tag}_bench_teapot.json 2> $out/${tag}_bench_teapot.err
 python bench.py --impl reference > $out/${tag}_bench_teapot_reference.json 2> $out/${tag}_bench_teapot_reference.err
 python bench.py --workload cornell --no-cpu-baseline > $out/${tag}_bench_cornell.json 2> $out/${tag}_bench_cornell.err
