@@ -1467,6 +1467,24 @@ __global__ void __launch_bounds__(128) k_trace_rays_tlas(const uint8_t* __restri
 // captured once into a CUDA graph and replayed: nothing baked into the graph changes from frame to frame.
 __global__ void k_set_frame(FrameConstants fc, FrameConstants* dst) { *dst = fc; }
 
+// Scheduling knobs from the environment (results never depend on them). Read once per process, by
+// whichever thread renders first; -1 = not set, the automatic policy applies.
+struct Tuning {
+    int suspend = -1, sort = -1, classSort = -1, walkRounds = -1, walkService = -1, graphs = 1;
+    uint32_t budgetMain = EXTEND_BUDGET_MAIN, budgets[EXTEND_RESUME_ROUNDS] = {384u, 1536u, 0u}, refillBelow = REFILL_THRESHOLD;
+    Tuning() {
+        auto num = [](const char* name, int unset) { const char* e = getenv(name); return e ? atoi(e) : unset; };
+        suspend = num("TB_SUSPEND", -1); sort = num("TB_SORT", -1); classSort = num("TB_CLASS_SORT", -1);
+        walkRounds = num("TB_WALK_ROUNDS", -1); walkService = num("TB_WALK_SERVICE", -1); graphs = num("TB_GRAPHS", 1);
+        if (const char* bs = getenv("TB_BUDGETS")) sscanf(bs, "%u,%u,%u", &budgetMain, &budgets[0], &budgets[1]);
+        if (const char* rs = getenv("TB_REFILL")) refillBelow = (uint32_t)atoi(rs);
+    }
+};
+const Tuning& tuning() {
+    static const Tuning t;
+    return t;
+}
+
 // Sorting the bounce queues pays when node fetches go to DRAM: traversal layout (112 B per triangle) well beyond the
 // 126 MB L2. Measured (bounce + shadow queues): 20.8 M triangles (2.3 GB) +10.6 %; 875 k triangles (98 MB) -2 %,
 // Teapot (14 MB) -5 %: when the nodes already come from L1 / L2 the three extra launches per queue are pure cost.
@@ -1488,21 +1506,15 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
     for (int b = 0; b < maxBounces; b++) {
         int qi = b & 1;
         if (timers) cudaEventRecord(timers->next(KernelTimers::EXTEND, b), stream);
-        static int suspendEnv = -2;
-        static uint32_t budgetMain = EXTEND_BUDGET_MAIN, budgets[EXTEND_RESUME_ROUNDS] = {384u, 1536u, 0u}, refillBelow = REFILL_THRESHOLD;
-        if (suspendEnv == -2) { // tuning knobs (results never depend on them)
-            const char* e = getenv("TB_SUSPEND"); suspendEnv = e ? atoi(e) : -1;
-            if (const char* bs = getenv("TB_BUDGETS")) sscanf(bs, "%u,%u,%u", &budgetMain, &budgets[0], &budgets[1]);
-            if (const char* rs = getenv("TB_REFILL")) refillBelow = (uint32_t)atoi(rs);
-        }
+        const Tuning& tune = tuning();
+        const uint32_t budgetMain = tune.budgetMain, refillBelow = tune.refillBelow;
+        const uint32_t* budgets = tune.budgets;
         // ray suspension pays when few frames are in flight (their tails have nothing to overlap with): measured with 16
         // slots it costs 1-2 % (three mostly empty launches per bounce), with one slot it is worth 2.2x on Teapot
-        const int suspendMode = suspendEnv >= 0 ? suspendEnv : (opts.suspendRays ? 1 : 0);
+        const int suspendMode = tune.suspend >= 0 ? tune.suspend : (opts.suspendRays ? 1 : 0);
         // bounce queues of large scenes are sorted by origin cell first (primary rays already come in 8x4 pixel tiles)
-        static int sortEnv = -2; // tuning knob (results never depend on it)
-        if (sortEnv == -2) { const char* e = getenv("TB_SORT"); sortEnv = e ? atoi(e) : -1; }
         // bit 0: the bounce queue, bit 1: the shadow queue
-        const int sortMode = sortEnv >= 0 ? sortEnv : (opts.sortRays == 2 ? (sort_pays(bvh) ? 3 : 0) : opts.sortRays);
+        const int sortMode = tune.sort >= 0 ? tune.sort : (opts.sortRays == 2 ? (sort_pays(bvh) ? 3 : 0) : opts.sortRays);
         PathState stx = st; // what k_extend<EXT_MAIN> reads its queue from
         auto sort_queue = [&](const uint32_t* queue, const uint32_t* countPtr, const float4* rayO) {
             cudaMemsetAsync(st.sortHist, 0, 4 * (TB_SORT_CELLS + 1), stream);
@@ -1515,12 +1527,10 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
             stx.queue[qi] = st.sortTmp;
         }
         // hits are binned by material class when the scene's reachable materials span more than one class
-        static int classEnv = -2; // tuning knob (results never depend on it)
-        if (classEnv == -2) { const char* e = getenv("TB_CLASS_SORT"); classEnv = e ? atoi(e) : -1; }
         // automatic: from four classes on. Measured on B200 (profiles/r2_class_sort_sweep.log): vw-van (glass, metal, mix,
         // textured, matte) +3 %, 20.8 M triangles +2 %, Teapot +0.4 %; scenes with two classes lose 3-4 % to the extra
         // launch per bounce (dragon, cornell)
-        const bool classSort = classEnv >= 0 ? classEnv != 0 : (opts.materialSort == 2 ? opts.sceneMaterialClasses >= 4 : opts.materialSort != 0);
+        const bool classSort = tune.classSort >= 0 ? tune.classSort != 0 : (opts.materialSort == 2 ? opts.sceneMaterialClasses >= 4 : opts.materialSort != 0);
         const uint8_t* classOfGeom = classSort ? sc.geomClass : nullptr;
         k_extend<EXT_MAIN><<<blocks, 128, 0, stream>>>(bvh, stx, qi, b, heat, fcDev, suspendMode ? budgetMain : 0xffffffffu, refillBelow, classOfGeom); launches++;
         if (suspendMode) {
@@ -1561,20 +1571,16 @@ static cudaError_t launch_frame(const DeviceBvh& bvh, const DeviceScene& sc, con
         }
 #undef TB_LAUNCH_SHADE
         if (sss) { // the bounce's glass / subsurface walkers (queued by the k_shade launches above into walk queue 0)
-            static int roundsEnv = -2; // tuning knob (results never depend on it)
-            if (roundsEnv == -2) { const char* e = getenv("TB_WALK_ROUNDS"); roundsEnv = e ? atoi(e) : -1; }
-            const int rounds = roundsEnv >= 0 ? roundsEnv : opts.walkRounds; // wavefront rounds before the persistent tail (which reads queue rounds & 1)
+            const int rounds = tune.walkRounds >= 0 ? tune.walkRounds : opts.walkRounds; // wavefront rounds before the persistent tail (which reads queue rounds & 1)
             for (int r = 0; r < rounds; r++) {
                 k_extend<EXT_WALK><<<blocks, 128, 0, stream>>>(bvh, st, r & 1, b, 0, fcDev, 0xffffffffu, REFILL_THRESHOLD, nullptr); launches++;
                 k_walk_step<<<blocks / 2 ? blocks / 2 : 1, 256, 0, stream>>>(sc, fcDev, st, qi, r & 1); launches++;
             }
             uint32_t wblocks = blocks > sms * 4 ? sms * 4 : blocks;
-            static int serviceEnv = -2; // tuning knob (results never depend on it)
-            if (serviceEnv == -2) { const char* e = getenv("TB_WALK_SERVICE"); serviceEnv = e ? atoi(e) : -1; }
             // finished rays that end a traversal phase: a walk step is long divergent code, so on a cache-resident tree
             // (cheap traversal) it pays to batch more of them; on an HBM-resident tree idle lanes cost more than that.
             // Measured (profiles/r2_walk_service_sweep.log): vw-van 8 -> 24 +3.8 %, 20.8 M triangles 8 -> 16 -5 %
-            const uint32_t serviceAt = serviceEnv > 0 ? (uint32_t)serviceEnv : (bvh.numPrims < (1u << 22) ? 24u : 8u);
+            const uint32_t serviceAt = tune.walkService > 0 ? (uint32_t)tune.walkService : (bvh.numPrims < (1u << 22) ? 24u : 8u);
             k_walk<<<wblocks, 128, 0, stream>>>(bvh, sc, fcDev, st, qi, rounds & 1, b, serviceAt); launches++;
         }
         if (timers) cudaEventRecord(timers->next(KernelTimers::END, b), stream);
@@ -1595,9 +1601,7 @@ void FrameGraph::reset() {
 cudaError_t render_frame(const DeviceBvh& bvh, const DeviceScene& sc, const FrameConstants& fc, FrameConstants* fcDev, PathState& st,
                          cudaStream_t stream, LaunchCounter& lc, KernelTimers* timers, const RenderOptions& opts, FrameGraph* graph) {
     k_set_frame<<<1, 1, 0, stream>>>(fc, fcDev); lc.count++;
-    static int useGraphs = -1;
-    if (useGraphs < 0) { const char* e = getenv("TB_GRAPHS"); useGraphs = e ? atoi(e) : 1; }
-    if (!graph || timers || !useGraphs) return launch_frame(bvh, sc, fc, fcDev, st, stream, lc.count, timers, opts);
+    if (!graph || timers || !tuning().graphs) return launch_frame(bvh, sc, fc, fcDev, st, stream, lc.count, timers, opts);
     FrameGraph::Key key = {opts.epoch, fc.width, fc.height, (uint32_t)fc.settings.MaxBounces, fc.settings.OutputType == TB_OUTPUT_HEATMAP ? 1u : 0u,
                            fc.settings.EnableNextEventEstimation ? 1u : 0u, (uint32_t)opts.shadowMode, (uint32_t)opts.walkRounds,
                            opts.sceneHasSSS ? 1u : 0u, opts.suspendRays ? 1u : 0u, (uint32_t)opts.sortRays,
