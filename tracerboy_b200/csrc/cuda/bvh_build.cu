@@ -411,12 +411,18 @@ __global__ void __launch_bounds__(128, 8) k_treelet_reorder(uint32_t n, HNode* H
     const uint32_t oct = threadIdx.x >> 3; // octet within the block
     const uint32_t nInternal = n - 1, total = 2 * n - 1;
     const uint32_t FULL = 0xffffffffu;
-    __shared__ float s_cost[TL_OCTETS][128];
-    __shared__ uint8_t s_part[TL_OCTETS][128];
+    // Cost and partition tables of the four octets of a warp are interleaved ([subset][octet]): the octets run in lock step
+    // on the same subset and partition indices, so side-by-side tables ([octet][subset]) put every access of the four on
+    // the same bank (3.2 G bank conflicts in the 20 M-triangle pass, profiles/r1c_treelet_octets_20m_ncu_full_raw.csv).
+    __shared__ float s_cost[TL_OCTETS / 4][128][4];
+    __shared__ uint8_t s_part[TL_OCTETS / 4][128][4];
     __shared__ float s_box[TL_OCTETS][7][6];
     __shared__ uint32_t s_new[TL_OCTETS][6][3]; // per new internal node: leaf subset, left child code, right child code
-    float* cost = s_cost[oct];
-    uint8_t* part = s_part[oct];
+    float (*cost4)[4] = s_cost[oct >> 2];
+    uint8_t (*part4)[4] = s_part[oct >> 2];
+    const uint32_t o4 = oct & 3u;
+#define cost(m) cost4[m][o4]
+#define part(m) part4[m][o4]
     const uint32_t numRoots = *baseCount;
     const uint32_t stride = gridDim.x * TL_OCTETS;
     uint32_t w = blockIdx.x * TL_OCTETS + oct; // next base root of this octet
@@ -486,10 +492,11 @@ __global__ void __launch_bounds__(128, 8) k_treelet_reorder(uint32_t n, HNode* H
         // ---- FindOptimalPartitions
         const float rootSA = surface_area(rb);
         {
-            // Surface area of every leaf subset: lane ol takes the 16 subsets whose leaves 4..6 are the bits of ol.
-            // Leaves 0, 1 and the union of the lane's high leaves are held in registers, so a subset costs a few
-            // register min/max pairs instead of 6 shared-memory loads per member (this loop was the larger
-            // half of the kernel's shared-memory traffic, which bounds it: profiles/).
+            // Surface area of every leaf subset: lane ol takes the 16 subsets whose leaves 0..2 are the bits of ol (the
+            // eight lanes of an octet then store to eight different banks). Leaves 5, 6 and the union of the lane's low
+            // leaves are held in registers, so a subset costs a few register min/max pairs instead of 6 shared-memory
+            // loads per member (this loop was the larger half of the kernel's shared-memory traffic, which bounds it).
+            // min / max are exact, so the order in which a subset's boxes are united does not matter.
             auto box_at = [&](uint32_t i) {
                 const float* sb = s_box[oct][i];
                 Box t; t.mn = mk3(sb[0], sb[1], sb[2]); t.mx = mk3(sb[3], sb[4], sb[5]);
@@ -497,26 +504,26 @@ __global__ void __launch_bounds__(128, 8) k_treelet_reorder(uint32_t n, HNode* H
             };
             Box base; base.mn = mk3(FLT_MAX); base.mx = mk3(-FLT_MAX);
 #pragma unroll
-            for (uint32_t i = 4; i < 7; i++)
-                if ((ol >> (i - 4)) & 1u) base = combine(base, box_at(i));
-            const Box L0 = box_at(0), L1 = box_at(1);
+            for (uint32_t i = 0; i < 3; i++)
+                if ((ol >> i) & 1u) base = combine(base, box_at(i));
+            const Box L5 = box_at(5), L6 = box_at(6);
 #pragma unroll
-            for (uint32_t hi = 0; hi < 4; hi++) { // leaves 2 and 3 (re-read per group: registers are the scarce resource)
+            for (uint32_t mid = 0; mid < 4; mid++) { // leaves 3 and 4 (re-read per group: registers are the scarce resource)
                 Box g = base;
-                if (hi & 1u) g = combine(g, box_at(2));
-                if (hi & 2u) g = combine(g, box_at(3));
+                if (mid & 1u) g = combine(g, box_at(3));
+                if (mid & 2u) g = combine(g, box_at(4));
 #pragma unroll
-                for (uint32_t lo = 0; lo < 4; lo++) {
+                for (uint32_t top = 0; top < 4; top++) {
                     Box b = g;
-                    if (lo & 1u) b = combine(b, L0);
-                    if (lo & 2u) b = combine(b, L1);
-                    const uint32_t mask = ol * 16 + hi * 4 + lo;
-                    cost[mask] = mask == 0 ? 0.0f : surface_area(b);
+                    if (top & 1u) b = combine(b, L5);
+                    if (top & 2u) b = combine(b, L6);
+                    const uint32_t mask = ol + mid * 8 + top * 32;
+                    cost(mask) = mask == 0 ? 0.0f : surface_area(b);
                 }
             }
         }
         __syncwarp();
-        if (ol < 7) cost[1u << ol] = 1.0f * surface_area(lb) / rootSA;
+        if (ol < 7) cost(1u << ol) = 1.0f * surface_area(lb) / rootSA;
         __syncwarp();
         for (uint32_t sz = 2; sz <= 6; sz++) {
             const uint32_t count = (1u << (sz - 1)) - 1u; // partitions of a subset of sz leaves (its lowest leaf stays right)
@@ -530,12 +537,12 @@ __global__ void __launch_bounds__(128, 8) k_treelet_reorder(uint32_t n, HNode* H
                 // iterations are in flight together (the loop is shared-memory latency bound)
 #pragma unroll 4
                 for (uint32_t j = 0; j < count; j++) {
-                    const float c = cost[p] + cost[mask ^ p];
+                    const float c = cost(p) + cost(mask ^ p);
                     if (c < lowest) { lowest = c; bestP = p; }
                     p = (p - delta) & mask;
                 }
-                cost[mask] = 1.0f * cost[mask] + lowest;
-                part[mask] = (uint8_t)bestP;
+                cost(mask) = 1.0f * cost(mask) + lowest;
+                part(mask) = (uint8_t)bestP;
             }
             __syncwarp();
         }
@@ -546,7 +553,7 @@ __global__ void __launch_bounds__(128, 8) k_treelet_reorder(uint32_t n, HNode* H
             uint32_t bestJ = 0xffffffffu;
             for (uint32_t j = ol; j < 63; j += 8) {
                 const uint32_t p = 2u * (j + 1u);
-                float c = cost[p] + cost[127u ^ p];
+                float c = cost(p) + cost(127u ^ p);
                 if (c < lowest) { lowest = c; bestJ = j; }
             }
 #pragma unroll
@@ -556,7 +563,7 @@ __global__ void __launch_bounds__(128, 8) k_treelet_reorder(uint32_t n, HNode* H
                 if (oc < lowest || (oc == lowest && oj < bestJ)) { lowest = oc; bestJ = oj; }
             }
             // bestJ == 0xffffffff: no partition was below FLT_MAX (NaN costs); the serial loop then leaves bestP = 0
-            if (ol == 0) part[127] = bestJ == 0xffffffffu ? (uint8_t)0 : (uint8_t)(2u * (bestJ + 1u));
+            if (ol == 0) part(127) = bestJ == 0xffffffffu ? (uint8_t)0 : (uint8_t)(2u * (bestJ + 1u));
         }
         __syncwarp();
         // ---- ReformTree. Lane 0 walks the partition table exactly like the reference's stack loop (pop an entry,
@@ -571,7 +578,7 @@ __global__ void __launch_bounds__(128, 8) k_treelet_reorder(uint32_t n, HNode* H
                 const uint32_t e = (uint32_t)(stk >> (10 * sp)) & 1023u;
                 stk &= ~(1023ull << (10 * sp));
                 const uint32_t em = e & 127u, es = e >> 7;
-                uint32_t lm = part[em];
+                uint32_t lm = part(em);
                 if (lm == 0 || (lm & ~em) != 0 || lm == em) lm = em & (0u - em); // table not meaningful (NaN costs, idle octet): stay in bounds
                 const uint32_t rm = em ^ lm;
                 uint32_t lcode, rcode;
@@ -628,6 +635,9 @@ __global__ void __launch_bounds__(128, 8) k_treelet_reorder(uint32_t n, HNode* H
         __syncwarp();
     }
 }
+
+#undef cost
+#undef part
 
 // --------------------------------------------------------------------- refit
 // ComputeAABBs.hlsli:69-172 (+ PrepareForComputeAABBs header)
