@@ -405,7 +405,10 @@ __constant__ const MaskTables c_maskTables = make_mask_tables();
 // Treelets are independent unless one is an ancestor of the other, and an ancestor only starts after both of
 // its children have arrived (atomic counter), so any schedule produces the reference's result.
 #define TL_OCTETS 16 // per 128-thread block
-__global__ void __launch_bounds__(128, 8) k_treelet_reorder(uint32_t n, HNode* H, float* aabb, uint32_t* numTris,
+#ifndef TL_MIN_BLOCKS
+#define TL_MIN_BLOCKS 8 // 9 / 10 / 12 blocks (56 / 48 / 40 registers, 40-156 B of spills) build no faster: profiles/r2_treelet_occupancy_sweep.log
+#endif
+__global__ void __launch_bounds__(128, TL_MIN_BLOCKS) k_treelet_reorder(uint32_t n, HNode* H, float* aabb, uint32_t* numTris,
                                                          const uint32_t* baseCount, const uint32_t* baseRoots) {
     const uint32_t lane = threadIdx.x & 31, ol = lane & 7u;
     const uint32_t oct = threadIdx.x >> 3; // octet within the block
