@@ -582,15 +582,16 @@ TB_API int tb_bvh_update_device(TbHandle* h, const TbGeometryDesc* geoms, uint32
 /* Top-level acceleration structures (D3D12_RAYTRACING_ACCELERATION_STRUCTURE_TYPE_TOP_LEVEL,
  * GpuBVH2Builder.cpp:116-146) over instances of bottom-level structures built by tb_bvh_build_device, and the two-level
  * ray query (TraverseFunction.hlsli with FAST_PATH 0: the ray is taken to object space at an instance leaf, :603-638).
- * `instances` is a HOST array (the reference takes a GPU address; the top level is built on the host here, from the
- * bottom-level root boxes, and uploaded); `dst` is caller-owned device memory of ResultDataMaxSizeInBytes
- * (tb_tlas_prebuild_info), 256-byte aligned; no scratch. The result starts with the reference's byte layout (header,
+ * `instances` is a HOST array (the reference takes a GPU address of an upload-heap buffer); it is uploaded and the top
+ * level is built on the GPU with the bottom level's pipeline minus the treelet pass. `dst` and `scratch` are caller-owned
+ * device memory of ResultDataMaxSizeInBytes / ScratchDataSizeInBytes (tb_tlas_prebuild_info), 256-byte aligned, as in
+ * BuildRaytracingAccelerationStructure's DestAccelerationStructureData / ScratchAccelerationStructureData. The result starts with the reference's byte layout (header,
  * 32-byte nodes, 116-byte BVHMetadata per sorted leaf: RayTracingHlslCompat.h:226-236). Hit records carry
  * InstanceIndex; instances with InstanceMask 0 are never hit; instance flags other than 0 are not interpreted (the path
  * uses RAY_FLAG_NONE and no any-hit). TracerBoy's software path itself stays single-level (FAST_PATH 1). */
 TB_API int tb_tlas_prebuild_info(uint32_t numInstances, TbPrebuildInfo* out);
 TB_API int tb_tlas_build_device(TbHandle* h, const TbInstanceDesc* instances, uint32_t n, uint32_t bvhBuildFlags, void* dst,
-                                uint64_t dstBytes, void* cudaStream);
+                                uint64_t dstBytes, void* scratch, uint64_t scratchBytes, void* cudaStream);
 TB_API int tb_trace_rays_tlas_device(TbHandle* h, const void* tlas, uint64_t tlasBytes, const TbRay* dRays, uint64_t n, TbHit* dHits,
                                      void* cudaStream);
 /* Drop the handle's cached description of a caller-owned acceleration structure (call before freeing / reusing dst). */

@@ -720,11 +720,12 @@ def test_seam_size_queries_and_argument_checks_without_a_device(built):
     import tracerboy_b200 as tb
     from tracerboy_b200.api import GeometryDesc, PrebuildInfo
     lib = tb.load_library()
-    # top level: 16-byte header + 32-byte nodes (2N - 1) + 116-byte BVHMetadata per instance; no scratch (built on the host)
+    # top level: 16-byte header + 32-byte nodes (2N - 1) + 116-byte BVHMetadata per instance; scratch grows linearly
     for n in (1, 2, 7, 20000):
         info = tb.tlas_prebuild_info(n)
         assert info.ReferenceLayoutSizeInBytes == 16 + 32 * (2 * n - 1) + 116 * n
-        assert info.ResultDataMaxSizeInBytes >= info.ReferenceLayoutSizeInBytes + 256 + 80 * n and info.ScratchDataSizeInBytes == 0
+        assert info.ResultDataMaxSizeInBytes >= info.ReferenceLayoutSizeInBytes + 256 + 80 * n
+        assert 320 * n <= info.ScratchDataSizeInBytes <= 324 * n + (1 << 13) and info.ScratchDataSizeInBytes % 256 == 0
     assert tb.tlas_prebuild_info(0).ResultDataMaxSizeInBytes == 0
     info = PrebuildInfo()
     assert lib.tb_tlas_prebuild_info((1 << 24) + 1, C.byref(info)) == -1      # InstanceID / hit-group contribution are 24 bit
@@ -747,7 +748,7 @@ def test_seam_size_queries_and_argument_checks_without_a_device(built):
     assert lib.tb_comm_get_unique_id(buf, 64) == -1
     assert lib.tb_comm_init(None, buf, 0, 1, 1) == -1 and lib.tb_comm_reduce(None) == -1 and lib.tb_comm_destroy(None) == -1
     assert lib.tb_bvh_build_device(None, d, 1, 0, None, 0, None, 0, None) == -1
-    assert lib.tb_tlas_build_device(None, None, 1, 0, None, 0, None) == -1
+    assert lib.tb_tlas_build_device(None, None, 1, 0, None, 0, None, 0, None) == -1
     assert lib.tb_set_material_sort(None, 1) == -1
 
 

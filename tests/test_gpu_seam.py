@@ -282,9 +282,10 @@ def test_two_level_structure_and_query_equal_the_oracle(tmp_path, built):
         inst_gpu[i].AccelerationStructure = blas_dev[i % 3].data_ptr()
         inst_cpu[i].AccelerationStructure = i % 3
     tinfo = tb.tlas_prebuild_info(n)
-    assert tinfo.ReferenceLayoutSizeInBytes == 16 + 32 * (2 * n - 1) + 116 * n and tinfo.ScratchDataSizeInBytes == 0
+    assert tinfo.ReferenceLayoutSizeInBytes == 16 + 32 * (2 * n - 1) + 116 * n and tinfo.ScratchDataSizeInBytes > 0
     tlas = torch.zeros(tinfo.ResultDataMaxSizeInBytes, dtype=torch.uint8, device="cuda")
-    g.BuildTopLevelAccelerationStructureDevice(inst_gpu, n, tlas.data_ptr(), tlas.numel(), None)
+    tscratch = torch.empty(tinfo.ScratchDataSizeInBytes, dtype=torch.uint8, device="cuda")
+    g.BuildTopLevelAccelerationStructureDevice(inst_gpu, n, tlas.data_ptr(), tlas.numel(), tscratch.data_ptr(), tscratch.numel(), None)
     want, arr = oracle_tlas(blas_bytes, inst_cpu, n)
     got = tlas[:tinfo.ReferenceLayoutSizeInBytes].cpu().numpy()
     off_meta = 16 + 32 * (2 * n - 1)
@@ -322,4 +323,64 @@ def test_two_level_structure_and_query_equal_the_oracle(tmp_path, built):
     k.Synchronize()
     assert np.array_equal(d_hits.cpu().numpy().view(HIT_DTYPE)["t"].view(np.uint32), ho["t"].view(np.uint32))
     with pytest.raises(tb.TracerBoyError):
-        g.BuildTopLevelAccelerationStructureDevice(inst_gpu, n, tlas.data_ptr(), 1000, None)
+        g.BuildTopLevelAccelerationStructureDevice(inst_gpu, n, tlas.data_ptr(), 1000, tscratch.data_ptr(), tscratch.numel(), None)
+    with pytest.raises(tb.TracerBoyError):
+        g.BuildTopLevelAccelerationStructureDevice(inst_gpu, n, tlas.data_ptr(), tlas.numel(), tscratch.data_ptr(), 1000, None)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 9, 5000])
+def test_top_level_bytes_equal_the_oracle_from_one_to_thousands_of_instances(n, tmp_path, built):
+    """The GPU top-level build (k_tlas_load, Morton, radix sort, Karras, k_tlas_emit, k_tlas_refit) against the oracle's
+    bytes for 1, 2, 3, 9 and 5 000 instances: a single leaf without hierarchy, the smallest trees, and a tree whose
+    instances crowd into a few Morton cells (many equal codes: the sort's tie rule and the Karras tie rule matter) plus
+    coincident instances (the same transform twice)."""
+    import torch
+    import tracerboy_b200 as tb
+    from oracle.binding import Oracle
+    from tracerboy_b200.api import InstanceDesc
+    from test_cpu_tlas import _rand_affine, oracle_tlas
+    rng = np.random.default_rng(100 + n)
+    g = tb.TracerBoy(0)
+    keep, blas_dev, blas_bytes = [], [], []
+    for k, (nv, nt) in enumerate(((60, 100), (3, 1))):
+        pos = rng.uniform(-1, 1, (nv, 3)).astype(np.float32)
+        idx = rng.integers(0, nv, (nt, 3)).astype(np.uint32) if nt > 1 else np.array([[0, 1, 2]], np.uint32)
+        h = tb.TracerBoy(0)
+        h.BuildRaytracingAccelerationStructure([(pos, idx)])
+        p = str(tmp_path / ("b%d.tbscene" % k))
+        h.SaveScene(p)
+        o = Oracle(); o.LoadScene(p, 3)
+        blas_bytes.append(np.ascontiguousarray(o.GetBVH()))
+        d = _descs([dict(pos=pos, idx=idx)], keep)
+        info = tb.prebuild_info(d, 1)
+        dst = torch.zeros(info.ResultDataMaxSizeInBytes, dtype=torch.uint8, device="cuda")
+        g.BuildRaytracingAccelerationStructureDevice(d, 1, dst.data_ptr(), dst.numel(), None, 0, None)
+        blas_dev.append(dst)
+    mats = _rand_affine(rng, n)
+    mats[:, :, 3] = rng.uniform(-25, 25, (n, 3))
+    if n >= 9:
+        mats[n // 2:, :, 3] = rng.uniform(-0.05, 0.05, (n - n // 2, 3)) + 20.0   # half of them within one Morton cell
+        mats[4] = mats[3]                                                            # coincident instances
+    inst_gpu, inst_cpu = (InstanceDesc * n)(), (InstanceDesc * n)()
+    for i in range(n):
+        for arr in (inst_gpu, inst_cpu):
+            for j in range(12):
+                arr[i].Transform[j] = float(mats[i].reshape(-1)[j])
+            arr[i].InstanceIDAndMask = i | (0xff << 24)
+            arr[i].InstanceContributionToHitGroupIndexAndFlags = i
+        inst_gpu[i].AccelerationStructure = blas_dev[i % 2].data_ptr()
+        inst_cpu[i].AccelerationStructure = i % 2
+    tinfo = tb.tlas_prebuild_info(n)
+    tlas = torch.zeros(tinfo.ResultDataMaxSizeInBytes, dtype=torch.uint8, device="cuda")
+    tscratch = torch.empty(tinfo.ScratchDataSizeInBytes, dtype=torch.uint8, device="cuda")
+    g.BuildTopLevelAccelerationStructureDevice(inst_gpu, n, tlas.data_ptr(), tlas.numel(), tscratch.data_ptr(), tscratch.numel(), None)
+    want, _ = oracle_tlas(blas_bytes, inst_cpu, n)
+    got = tlas[:tinfo.ReferenceLayoutSizeInBytes].cpu().numpy()
+    off_meta = 16 + 32 * (2 * n - 1)
+    gm, wm = got[off_meta:].reshape(n, 116).copy(), want[off_meta:].reshape(n, 116).copy()
+    gm[:, 56:64] = 0; wm[:, 56:64] = 0
+    assert np.array_equal(got[:off_meta], want[:off_meta]), "header / nodes"
+    assert np.array_equal(gm, wm), "instance metadata"
+    # and the build is repeatable into the same memory
+    g.BuildTopLevelAccelerationStructureDevice(inst_gpu, n, tlas.data_ptr(), tlas.numel(), tscratch.data_ptr(), tscratch.numel(), None)
+    assert np.array_equal(tlas[:off_meta].cpu().numpy(), got[:off_meta])

@@ -70,7 +70,8 @@ for i in range(5):
     inst[i].InstanceIDAndMask = i | (0xff << 24); inst[i].AccelerationStructure = dst.data_ptr()
 tinfo = tb.tlas_prebuild_info(5)
 tlas = torch.zeros(tinfo.ResultDataMaxSizeInBytes, dtype=torch.uint8, device="cuda")
-g.BuildTopLevelAccelerationStructureDevice(inst, 5, tlas.data_ptr(), tlas.numel(), None)
+tscratch = torch.empty(tinfo.ScratchDataSizeInBytes, dtype=torch.uint8, device="cuda")
+g.BuildTopLevelAccelerationStructureDevice(inst, 5, tlas.data_ptr(), tlas.numel(), tscratch.data_ptr(), tscratch.numel(), None)
 rays = np.zeros(2000, tb.api.RAY_DTYPE)
 rays["Origin"] = rng.uniform(-2, 14, (2000, 3)) * [1, 0.2, 0.2]; rays["Direction"] = rng.normal(0, 1, (2000, 3)); rays["TMin"] = 0.001; rays["TMax"] = 1e6
 d_rays = torch.from_numpy(rays.view(np.uint8)).cuda()

@@ -201,7 +201,7 @@ def load_library():
         "tb_bvh_build_device": [vp, C.POINTER(GeometryDesc), u32, u32, vp, u64, vp, u64, vp],
         "tb_trace_rays_device": [vp, vp, u64, vp, u64, vp, vp], "tb_bvh_forget_device": [vp, vp],
         "tb_bvh_update_device": [vp, C.POINTER(GeometryDesc), u32, vp, u64, vp, u64, vp],
-        "tb_tlas_prebuild_info": [u32, C.POINTER(PrebuildInfo)], "tb_tlas_build_device": [vp, C.POINTER(InstanceDesc), u32, u32, vp, u64, vp],
+        "tb_tlas_prebuild_info": [u32, C.POINTER(PrebuildInfo)], "tb_tlas_build_device": [vp, C.POINTER(InstanceDesc), u32, u32, vp, u64, vp, u64, vp],
         "tb_trace_rays_tlas_device": [vp, vp, u64, vp, u64, vp, vp],
         "tb_get_bvh_depth": [vp, C.POINTER(u32)],
         "tb_comm_get_unique_id": [vp, u64], "tb_comm_init": [vp, vp, i32, i32, u32], "tb_comm_destroy": [vp],
@@ -446,10 +446,10 @@ class TracerBoy:
         """PERFORM_UPDATE: refit a caller-owned acceleration structure to moved vertices (same topology), in place."""
         self._ck(self._lib.tb_bvh_update_device(self._h, descs, n, dst, dst_bytes, scratch, scratch_bytes, stream))
 
-    def BuildTopLevelAccelerationStructureDevice(self, instances, n, dst, dst_bytes, stream=None, flags=0):
+    def BuildTopLevelAccelerationStructureDevice(self, instances, n, dst, dst_bytes, scratch, scratch_bytes, stream=None, flags=0):
         """TYPE_TOP_LEVEL build over a host (InstanceDesc * n) array whose AccelerationStructure fields are device
-        addresses of bottom-level structures; dst = caller-owned device memory sized by tlas_prebuild_info."""
-        self._ck(self._lib.tb_tlas_build_device(self._h, instances, n, flags, dst, dst_bytes, stream))
+        addresses of bottom-level structures; dst / scratch = caller-owned device memory sized by tlas_prebuild_info."""
+        self._ck(self._lib.tb_tlas_build_device(self._h, instances, n, flags, dst, dst_bytes, scratch, scratch_bytes, stream))
 
     def TraceRaysTopLevelDevice(self, tlas, tlas_bytes, d_rays, n, d_hits, stream=None):
         self._ck(self._lib.tb_trace_rays_tlas_device(self._h, tlas, tlas_bytes, d_rays, n, d_hits, stream))

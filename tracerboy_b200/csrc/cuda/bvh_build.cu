@@ -798,6 +798,165 @@ __global__ void k_widen(uint32_t n, const uint8_t* __restrict__ bvh, PairNode* _
     }
 }
 
+
+// ------------------------------------------------------------------ top level
+// BuildRaytracingAccelerationStructure for TYPE_TOP_LEVEL (GpuBVH2Builder.cpp:116-146, SceneType::BottomLevelBVHs): the
+// same pipeline over instances instead of triangles, no treelet pass.
+//   k_tlas_load    TopLevelLoadAABBs.hlsli:58-100: world box = TransformAABB of the bottom-level root box, the desc's
+//                  transform replaced by InverseAffineTransform, ObjectToWorld kept (RayTracingHelper.hlsli:287-344);
+//                  scene box
+//   k_tlas_morton  Morton code of the box centre; then the radix sort by (code, index) and k_karras, shared with the
+//                  bottom level
+//   k_tlas_emit    sorted BVHMetadata records (116 B), leaf nodes, the query's per-instance records
+//   k_tlas_refit   TopLevelComputeAABBs.hlsl + ComputeAABBs.hlsli: smaller subtree left (D1), bottom-up
+struct Mat34 { float m[3][4]; };
+__device__ __forceinline__ f3 mul_point(const Mat34& a, f3 p, float w) { // mul(float3x4, float4): one dot product per row, left to right
+    return mk3(((a.m[0][0] * p.x + a.m[0][1] * p.y) + a.m[0][2] * p.z) + a.m[0][3] * w,
+               ((a.m[1][0] * p.x + a.m[1][1] * p.y) + a.m[1][2] * p.z) + a.m[1][3] * w,
+               ((a.m[2][0] * p.x + a.m[2][1] * p.y) + a.m[2][2] * p.z) + a.m[2][3] * w);
+}
+__device__ __forceinline__ float determinant(const Mat34& t) { // RayTracingHelper.hlsli:287-295
+    return ((((t.m[0][0] * t.m[1][1] * t.m[2][2] - t.m[0][0] * t.m[2][1] * t.m[1][2]) - t.m[1][0] * t.m[0][1] * t.m[2][2]) +
+             t.m[1][0] * t.m[2][1] * t.m[0][2]) + t.m[2][0] * t.m[0][1] * t.m[1][2]) - t.m[2][0] * t.m[1][1] * t.m[0][2];
+}
+__device__ Mat34 inverse_affine(const Mat34& a) { // :297-316, term by term (the constant fourth row 0 0 0 1 written out as the shader has it)
+    const float (*t)[4] = a.m;
+    const float invDet = 1.0f / determinant(a);
+    Mat34 r;
+    r.m[0][0] = invDet * ((t[1][1] * (t[2][2] * 1.0f - 0.0f * t[2][3]) + t[2][1] * (0.0f * t[1][3] - t[1][2] * 1.0f)) + 0.0f * (t[1][2] * t[2][3] - t[2][2] * t[1][3]));
+    r.m[1][0] = invDet * ((t[1][2] * (t[2][0] * 1.0f - 0.0f * t[2][3]) + t[2][2] * (0.0f * t[1][3] - t[1][0] * 1.0f)) + 0.0f * (t[1][0] * t[2][3] - t[2][0] * t[1][3]));
+    r.m[2][0] = invDet * ((t[1][3] * (t[2][0] * 0.0f - 0.0f * t[2][1]) + t[2][3] * (0.0f * t[1][1] - t[1][0] * 0.0f)) + 1.0f * (t[1][0] * t[2][1] - t[2][0] * t[1][1]));
+    r.m[0][1] = invDet * ((t[2][1] * (t[0][2] * 1.0f - 0.0f * t[0][3]) + 0.0f * (t[2][2] * t[0][3] - t[0][2] * t[2][3])) + t[0][1] * (0.0f * t[2][3] - t[2][2] * 1.0f));
+    r.m[1][1] = invDet * ((t[2][2] * (t[0][0] * 1.0f - 0.0f * t[0][3]) + 0.0f * (t[2][0] * t[0][3] - t[0][0] * t[2][3])) + t[0][2] * (0.0f * t[2][3] - t[2][0] * 1.0f));
+    r.m[2][1] = invDet * ((t[2][3] * (t[0][0] * 0.0f - 0.0f * t[0][1]) + 1.0f * (t[2][0] * t[0][1] - t[0][0] * t[2][1])) + t[0][3] * (0.0f * t[2][1] - t[2][0] * 0.0f));
+    r.m[0][2] = invDet * ((0.0f * (t[0][2] * t[1][3] - t[1][2] * t[0][3]) + t[0][1] * (t[1][2] * 1.0f - 0.0f * t[1][3])) + t[1][1] * (0.0f * t[0][3] - t[0][2] * 1.0f));
+    r.m[1][2] = invDet * ((0.0f * (t[0][0] * t[1][3] - t[1][0] * t[0][3]) + t[0][2] * (t[1][0] * 1.0f - 0.0f * t[1][3])) + t[1][2] * (0.0f * t[0][3] - t[0][0] * 1.0f));
+    r.m[2][2] = invDet * ((1.0f * (t[0][0] * t[1][1] - t[1][0] * t[0][1]) + t[0][3] * (t[1][0] * 0.0f - 0.0f * t[1][1])) + t[1][3] * (0.0f * t[0][1] - t[0][0] * 0.0f));
+    r.m[0][3] = invDet * ((t[0][1] * (t[2][2] * t[1][3] - t[1][2] * t[2][3]) + t[1][1] * (t[0][2] * t[2][3] - t[2][2] * t[0][3])) + t[2][1] * (t[1][2] * t[0][3] - t[0][2] * t[1][3]));
+    r.m[1][3] = invDet * ((t[0][2] * (t[2][0] * t[1][3] - t[1][0] * t[2][3]) + t[1][2] * (t[0][0] * t[2][3] - t[2][0] * t[0][3])) + t[2][2] * (t[1][0] * t[0][3] - t[0][0] * t[1][3]));
+    r.m[2][3] = invDet * ((t[0][3] * (t[2][0] * t[1][1] - t[1][0] * t[2][1]) + t[1][3] * (t[0][0] * t[2][1] - t[2][0] * t[0][1])) + t[2][3] * (t[1][0] * t[0][1] - t[0][0] * t[1][1]));
+    return r;
+}
+#define TLAS_META_WORDS 29 // BVHMetadata: 116 bytes
+// what k_tlas_load leaves per instance (caller order): the box, then the metadata record
+struct TlasLoaded { float4 c, h; uint32_t meta[TLAS_META_WORDS]; uint32_t pad[3]; }; // 160 bytes
+__global__ void k_tlas_load(const TbInstanceDesc* __restrict__ inst, const TlasBlasInfo* __restrict__ blas, uint32_t n, TlasLoaded* __restrict__ out,
+                            uint32_t* __restrict__ sceneBox) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const TbInstanceDesc d = inst[i];
+    Mat34 o2w;
+    for (int k = 0; k < 12; k++) o2w.m[k >> 2][k & 3] = d.Transform[k];
+    const Mat34 w2o = inverse_affine(o2w);
+    // BoundingBoxToAABB, TransformAABB over the eight corners, AABBtoBoundingBox
+    const TlasBlasInfo b = blas[i];
+    const f3 rc = mk3(b.c[0], b.c[1], b.c[2]), rh = mk3(b.h[0], b.h[1], b.h[2]);
+    const f3 bmn = rc - rh, bmx = rc + rh;
+    f3 wmn = mk3(FLT_MAX), wmx = mk3(-FLT_MAX);
+    for (int k = 0; k < 8; k++) {
+        const f3 v = mul_point(o2w, mk3((k & 4) ? bmx.x : bmn.x, (k & 2) ? bmx.y : bmn.y, (k & 1) ? bmx.z : bmn.z), 1.0f);
+        wmn = min3(wmn, v); wmx = max3(wmx, v);
+    }
+    const f3 c = (wmn + wmx) * 0.5f, h = wmx - c;
+    TlasLoaded& o = out[i];
+    o.c = make_float4(c.x, c.y, c.z, 0.0f);
+    o.h = make_float4(h.x, h.y, h.z, 0.0f);
+    for (int k = 0; k < 12; k++) { o.meta[k] = __float_as_uint(w2o.m[k >> 2][k & 3]); o.meta[16 + k] = __float_as_uint(o2w.m[k >> 2][k & 3]); }
+    o.meta[12] = d.InstanceIDAndMask; o.meta[13] = d.InstanceContributionToHitGroupIndexAndFlags;
+    o.meta[14] = (uint32_t)d.AccelerationStructure; o.meta[15] = (uint32_t)(d.AccelerationStructure >> 32);
+    o.meta[28] = i;
+    // the scene box spans the boxes as the leaves store them (centre -/+ half extent); min / max are order independent
+    const f3 lo = c - h, hi = c + h;
+    atomicMin(&sceneBox[0], float_to_ordered(lo.x)); atomicMin(&sceneBox[1], float_to_ordered(lo.y)); atomicMin(&sceneBox[2], float_to_ordered(lo.z));
+    atomicMax(&sceneBox[3], float_to_ordered(hi.x)); atomicMax(&sceneBox[4], float_to_ordered(hi.y)); atomicMax(&sceneBox[5], float_to_ordered(hi.z));
+}
+
+__global__ void k_tlas_morton(const TlasLoaded* __restrict__ loaded, uint32_t n, const uint32_t* __restrict__ sceneBox, uint32_t* __restrict__ codes,
+                              uint32_t* __restrict__ order) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const f3 smin = mk3(ordered_to_float(sceneBox[0]), ordered_to_float(sceneBox[1]), ordered_to_float(sceneBox[2]));
+    const f3 smax = mk3(ordered_to_float(sceneBox[3]), ordered_to_float(sceneBox[4]), ordered_to_float(sceneBox[5]));
+    const float4 c4 = loaded[i].c;
+    const f3 dim = max3(smax - smin, mk3(0.00001f)); // CalculateMortonCodesBindings.h:117-162
+    const f3 unit = (mk3(c4.x, c4.y, c4.z) - smin) / dim;
+    const f3 adj = min3(max3(unit * 1024.0f, mk3(0.0f)), mk3(1023.0f));
+    const uint32_t coords[3] = {(uint32_t)adj.y, (uint32_t)adj.x, (uint32_t)adj.z};
+    uint32_t code = 0;
+#pragma unroll
+    for (uint32_t bit = 0; bit < 10; bit++)
+#pragma unroll
+        for (uint32_t axis = 0; axis < 3; axis++)
+            if ((1u << bit) & coords[axis]) code |= 1u << (bit * 3 + axis);
+    codes[i] = code;
+    order[i] = i;
+}
+
+// dst: header (16 B) | 32-byte nodes (2n - 1) | 116-byte metadata (n, sorted); records: one TlasInstanceRecord per sorted leaf
+__global__ void k_tlas_emit(const TlasLoaded* __restrict__ loaded, const TlasBlasInfo* __restrict__ blas, const uint32_t* __restrict__ order, uint32_t n,
+                            uint8_t* __restrict__ dst, TlasInstanceRecord* __restrict__ records) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t nInternal = n - 1, total = 2 * n - 1;
+    const uint32_t offBoxes = 16, offMeta = offBoxes + 32 * total;
+    if (i == 0) { // OffsetToLeafNodeMetaDataOffset = 4 (RayTracingHelper.hlsli:46); word 2 is not used by a top level
+        uint32_t* hd = (uint32_t*)dst;
+        hd[0] = offBoxes; hd[1] = offMeta; hd[2] = 0; hd[3] = offMeta + 116 * n;
+    }
+    const uint32_t src = order[i];
+    const TlasLoaded& L = loaded[src];
+    uint32_t* m = (uint32_t*)(dst + offMeta + 116 * (size_t)i);
+    for (int k = 0; k < TLAS_META_WORDS; k++) m[k] = L.meta[k];
+    float4* nd = (float4*)(dst + offBoxes + 32 * (size_t)(nInternal + i));
+    nd[0] = make_float4(L.c.x, L.c.y, L.c.z, __uint_as_float(i | 0x80000000u));
+    nd[1] = make_float4(L.h.x, L.h.y, L.h.z, __uint_as_float(1u));
+    const TlasBlasInfo b = blas[src];
+    TlasInstanceRecord r;
+    for (int k = 0; k < 12; k++) r.worldToObject[k] = __uint_as_float(L.meta[k]);
+    r.pairs = b.pairs; r.tris = b.tris; r.rootRef = b.rootRef;
+    r.instanceIndex = L.meta[28];
+    r.mask = L.meta[12] >> 24;
+    r.pad = 0;
+    records[i] = r;
+}
+
+// the climb of k_refit over leaf nodes that k_tlas_emit has already written
+__global__ void k_tlas_refit(uint32_t n, const HNode* H, uint8_t* dst, unsigned long long* counter, uint32_t* depthOut) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n) return;
+    const uint32_t total = 2 * n - 1;
+    if (tid == 0 && n == 1) *depthOut = 0;
+    float* nodes = (float*)(dst + 16);
+    uint32_t node = total - tid - 1;
+    uint32_t count = 1, height = 0;
+    while (node != 0) {
+        const uint32_t parent = ld_u(&H[node].parent);
+        __threadfence();
+        const unsigned long long arrived = atomicAdd(&counter[parent], ((unsigned long long)height << 32) | count);
+        const uint32_t other = (uint32_t)arrived, otherHeight = (uint32_t)(arrived >> 32);
+        if (other == 0) return;
+        __threadfence();
+        uint32_t l = ld_u(&H[parent].left), r = ld_u(&H[parent].right);
+        const uint32_t lc = (l == node) ? count : other, rc = (l == node) ? other : count;
+        if (lc > rc) { const uint32_t t = l; l = r; r = t; } // smaller subtree left; ties keep Karras order
+        const float4* A = (const float4*)(nodes + 8 * (size_t)l);
+        const float4* B = (const float4*)(nodes + 8 * (size_t)r);
+        const float4 a0 = __ldcg(A), a1 = __ldcg(A + 1), b0 = __ldcg(B), b1 = __ldcg(B + 1);
+        const f3 ac = mk3(a0.x, a0.y, a0.z), ah = mk3(a1.x, a1.y, a1.z);
+        const f3 bc = mk3(b0.x, b0.y, b0.z), bh = mk3(b1.x, b1.y, b1.z);
+        const f3 mn = min3(ac - ah, bc - bh), mx = max3(ac + ah, bc + bh);
+        const f3 c = (mn + mx) * 0.5f;
+        const f3 h = mx - c;
+        float4* nd = (float4*)(nodes + 8 * (size_t)parent);
+        __stcg(nd, make_float4(c.x, c.y, c.z, __uint_as_float(l & 0x3fffffffu)));
+        __stcg(nd + 1, make_float4(h.x, h.y, h.z, __uint_as_float(r)));
+        node = parent;
+        count += other;
+        height = (height > otherHeight ? height : otherHeight) + 1;
+        if (node == 0) *depthOut = height;
+    }
+}
+
 } // namespace
 
 uint64_t bvh_ref_bytes(uint32_t n) { return 16ull + 32ull * (2ull * n - 1) + 40ull * n + 12ull * n; }
@@ -916,6 +1075,78 @@ cudaError_t build_bvh(const BuildGeometry* d_geoms, const uint32_t* d_triPrefix,
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(stream));
     out.numPrims = n;
+#undef CK
+    return cudaSuccess;
+}
+
+// ---- top level: scratch layout and the build
+namespace {
+struct TlasScratchLayout { size_t inst, blas, loaded, codes, order, codesAlt, orderAlt, sceneBox, H, radixHist, arrive, depth, end; uint32_t sortBlocks; };
+TlasScratchLayout tlas_scratch_layout(uint32_t n) {
+    TlasScratchLayout L;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t at = off; off += (bytes + 255) & ~(size_t)255; return at; };
+    L.sortBlocks = (n + RS_TILE - 1) / RS_TILE;
+    L.inst = take(sizeof(TbInstanceDesc) * (size_t)n);
+    L.blas = take(sizeof(TlasBlasInfo) * (size_t)n);
+    L.loaded = take(sizeof(TlasLoaded) * (size_t)n);
+    L.codes = take(4 * (size_t)n); L.order = take(4 * (size_t)n);
+    L.codesAlt = take(4 * (size_t)n); L.orderAlt = take(4 * (size_t)n);
+    L.sceneBox = take(6 * 4);
+    L.H = take(sizeof(HNode) * (2 * (size_t)n - 1));
+    L.radixHist = take(4 * 256 * ((size_t)L.sortBlocks + 1));
+    L.arrive = take(8 * (size_t)n);
+    L.depth = take(4);
+    L.end = off;
+    return L;
+}
+} // namespace
+
+uint64_t tlas_scratch_bytes(uint32_t n) { return n ? tlas_scratch_layout(n).end : 0; }
+
+// Builds the top level into `dst` (reference byte layout) and `records` (the device query's per-leaf table) from HOST
+// arrays of instance descs and resolved bottom-level infos; everything else runs on `stream`. `scratch` holds at least
+// tlas_scratch_bytes(n) bytes. One synchronisation at the end: the tree depth comes back to the host.
+cudaError_t build_tlas(const TbInstanceDesc* h_instances, const TlasBlasInfo* h_blas, uint32_t n, uint8_t* dst, TlasInstanceRecord* records,
+                       void* scratch, uint32_t* depthOut, cudaStream_t stream, LaunchCounter& lc) {
+    const uint32_t T = 256;
+    auto grid = [&](uint32_t c) { return (c + T - 1) / T; };
+    cudaError_t err;
+#define CK(x) do { err = (x); if (err != cudaSuccess) return err; } while (0)
+    const TlasScratchLayout L = tlas_scratch_layout(n);
+    uint8_t* base = (uint8_t*)scratch;
+    TbInstanceDesc* inst = (TbInstanceDesc*)(base + L.inst);
+    TlasBlasInfo* blas = (TlasBlasInfo*)(base + L.blas);
+    TlasLoaded* loaded = (TlasLoaded*)(base + L.loaded);
+    uint32_t *codes = (uint32_t*)(base + L.codes), *order = (uint32_t*)(base + L.order);
+    uint32_t *codesAlt = (uint32_t*)(base + L.codesAlt), *orderAlt = (uint32_t*)(base + L.orderAlt);
+    uint32_t* sceneBox = (uint32_t*)(base + L.sceneBox);
+    HNode* H = (HNode*)(base + L.H);
+    uint32_t* radixHist = (uint32_t*)(base + L.radixHist);
+    uint32_t* radixDigitStart = radixHist + 256 * (size_t)L.sortBlocks;
+    unsigned long long* arrive = (unsigned long long*)(base + L.arrive);
+    uint32_t* depthDev = (uint32_t*)(base + L.depth);
+    CK(cudaMemcpyAsync(inst, h_instances, sizeof(TbInstanceDesc) * (size_t)n, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(blas, h_blas, sizeof(TlasBlasInfo) * (size_t)n, cudaMemcpyHostToDevice, stream));
+    const uint32_t boxInit[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    CK(cudaMemcpyAsync(sceneBox, boxInit, sizeof(boxInit), cudaMemcpyHostToDevice, stream));
+    k_tlas_load<<<grid(n), T, 0, stream>>>(inst, blas, n, loaded, sceneBox); lc.count++;
+    k_tlas_morton<<<grid(n), T, 0, stream>>>(loaded, n, sceneBox, codes, order); lc.count++;
+    uint32_t *kIn = codes, *vIn = order, *kOut = codesAlt, *vOut = orderAlt;
+    for (int shift = 0; shift < 30; shift += 8) { // stable LSD passes: equal codes keep the caller's order
+        k_radix_hist<<<L.sortBlocks, RS_THREADS, 0, stream>>>(kIn, n, shift, L.sortBlocks, radixHist); lc.count++;
+        k_radix_scan_rows<<<256, 256, 0, stream>>>(radixHist, L.sortBlocks, radixDigitStart); lc.count++;
+        k_radix_scan_digits<<<1, 256, 0, stream>>>(radixDigitStart); lc.count++;
+        k_radix_scatter<<<L.sortBlocks, RS_THREADS, 0, stream>>>(kIn, vIn, n, shift, L.sortBlocks, radixHist, radixDigitStart, kOut, vOut); lc.count++;
+        uint32_t* t = kIn; kIn = kOut; kOut = t; t = vIn; vIn = vOut; vOut = t;
+    }
+    if (n > 1) { k_karras<<<grid(n - 1), T, 0, stream>>>(kIn, n, H); lc.count++; }
+    k_tlas_emit<<<grid(n), T, 0, stream>>>(loaded, blas, vIn, n, dst, records); lc.count++;
+    CK(cudaMemsetAsync(arrive, 0, 8 * (size_t)n, stream));
+    k_tlas_refit<<<grid(n), T, 0, stream>>>(n, H, dst, arrive, depthDev); lc.count++;
+    CK(cudaMemcpyAsync(depthOut, depthDev, 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(stream));
 #undef CK
     return cudaSuccess;
 }

@@ -52,6 +52,15 @@ struct TlasInstanceRecord {
     uint32_t pad;
 };
 
+// What the top-level build needs to know about the bottom-level structure of one instance (resolved on the host from the
+// structure's address, uploaded with the instance descs).
+struct TlasBlasInfo {
+    float c[3]; uint32_t rootRef;  // root box centre; 0 (internal root) or 0x80000000 | slot (a single-triangle bottom level)
+    float h[3]; uint32_t pad;      // root box half extent
+    const PairNode* pairs;
+    const WideTri* tris;
+};
+
 // One geometry of a build as the load kernel reads it: the caller's device buffers
 // (D3D12_RAYTRACING_GEOMETRY_TRIANGLES_DESC: vertex buffer + stride, optional 16 / 32 bit indices, optional 3x4 transform).
 struct BuildGeometry {

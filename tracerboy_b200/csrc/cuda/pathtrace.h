@@ -117,6 +117,10 @@ uint64_t bvh_scratch_bytes(uint32_t numPrims);
 uint64_t bvh_update_scratch_bytes(uint32_t numPrims);
 // PERFORM_UPDATE: same hierarchy, triangles reloaded from the (moved) geometry into their sorted slots, boxes refitted
 cudaError_t update_bvh(const BuildGeometry* d_geoms, uint32_t numPrims, DeviceBvh& bvh, void* scratch, cudaStream_t stream, LaunchCounter& lc);
+// top level over instances of bottom-level structures (bvh_build.cu); host arrays in, device structure out
+uint64_t tlas_scratch_bytes(uint32_t numInstances);
+cudaError_t build_tlas(const TbInstanceDesc* h_instances, const TlasBlasInfo* h_blas, uint32_t numInstances, uint8_t* dst, TlasInstanceRecord* records,
+                       void* scratch, uint32_t* depthOut, cudaStream_t stream, LaunchCounter& lc);
 cudaError_t build_bvh(const BuildGeometry* d_geoms, const uint32_t* d_triPrefix, uint32_t numGeoms, uint32_t numPrims, int treeletPasses,
                       DeviceBvh& out, void* scratch, cudaStream_t stream, LaunchCounter& lc);
 // The captured kernel sequence of one frame on one frame slot (see render_frame).
