@@ -646,36 +646,11 @@ __global__ void __launch_bounds__(128, TL_MIN_BLOCKS) k_treelet_reorder(uint32_t
 #undef cost
 #undef part
 
-// --------------------------------------------------------------------- refit
-// ComputeAABBs.hlsli:69-172 (+ PrepareForComputeAABBs header)
-// The climb also carries the subtree height (count in the low word of the 64-bit arrival counter, height in the
-// high word: the value the first arrival leaves is exactly what the second one reads back), so the depth of the
-// finished tree is known when the root is written. The traversal keeps at most one waiting far child per level,
-// so `depth` bounds the stack it needs: the host rejects a tree deeper than TB_STACK_DEPTH instead of the traversal
-// dropping children silently.
-__global__ void k_refit(uint32_t n, const HNode* H, uint8_t* bvh, unsigned long long* counter, uint32_t* depthOut) {
-    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= n) return;
-    const uint32_t nInternal = n - 1, total = 2 * n - 1;
-    // 64-bit addressing throughout; the header's four words are the reference's 32-bit byte offsets
-    // (RayTracingHlslCompat.h:344-398), which the host guarantees to fit (tb_max_triangles: 116 N - 16 < 4 GiB)
-    const size_t offPrims = 16 + 32 * (size_t)total;
-    if (tid == 0) {
-        uint32_t* hd = (uint32_t*)bvh;
-        hd[0] = 16; hd[1] = (uint32_t)offPrims; hd[2] = (uint32_t)(offPrims + 40 * (size_t)n); hd[3] = (uint32_t)(offPrims + 52 * (size_t)n);
-        if (n == 1) *depthOut = 0;
-    }
-    float* nodes = (float*)(bvh + 16);
-    const Prim* prims = (const Prim*)(bvh + offPrims);
-    uint32_t node = total - tid - 1;
+// The bottom-up climb shared by the bottom-level and top-level node writers (ComputeAABBs.hlsli:69-172): starts at a leaf
+// whose 32-byte node is already written; the second arrival at a parent writes the parent's node (smaller subtree
+// left, D1) and goes on. `nodes` = the structure's node array (8 floats per node).
+__device__ __forceinline__ void refit_climb(uint32_t node, const HNode* H, float* nodes, unsigned long long* counter, uint32_t* depthOut) {
     uint32_t count = 1, height = 0;
-    {
-        f3 c, h;
-        leaf_box(prims, node - nInternal, c, h);
-        float4* nd = (float4*)(nodes + 8 * (size_t)node); // 16-byte aligned: the node array starts 16 bytes into the buffer
-        __stcg(nd, make_float4(c.x, c.y, c.z, __uint_as_float((node - nInternal) | 0x80000000u)));
-        __stcg(nd + 1, make_float4(h.x, h.y, h.z, __uint_as_float(1u)));
-    }
     while (node != 0) {
         uint32_t parent = ld_u(&H[node].parent);
         __threadfence();
@@ -702,6 +677,38 @@ __global__ void k_refit(uint32_t n, const HNode* H, uint8_t* bvh, unsigned long 
         height = (height > otherHeight ? height : otherHeight) + 1;
         if (node == 0) *depthOut = height;
     }
+}
+
+// --------------------------------------------------------------------- refit
+// ComputeAABBs.hlsli:69-172 (+ PrepareForComputeAABBs header)
+// The climb also carries the subtree height (count in the low word of the 64-bit arrival counter, height in the
+// high word: the value the first arrival leaves is exactly what the second one reads back), so the depth of the
+// finished tree is known when the root is written. The traversal keeps at most one waiting far child per level,
+// so `depth` bounds the stack it needs: the host rejects a tree deeper than TB_STACK_DEPTH instead of the traversal
+// dropping children silently.
+__global__ void k_refit(uint32_t n, const HNode* H, uint8_t* bvh, unsigned long long* counter, uint32_t* depthOut) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n) return;
+    const uint32_t nInternal = n - 1, total = 2 * n - 1;
+    // 64-bit addressing throughout; the header's four words are the reference's 32-bit byte offsets
+    // (RayTracingHlslCompat.h:344-398), which the host guarantees to fit (tb_max_triangles: 116 N - 16 < 4 GiB)
+    const size_t offPrims = 16 + 32 * (size_t)total;
+    if (tid == 0) {
+        uint32_t* hd = (uint32_t*)bvh;
+        hd[0] = 16; hd[1] = (uint32_t)offPrims; hd[2] = (uint32_t)(offPrims + 40 * (size_t)n); hd[3] = (uint32_t)(offPrims + 52 * (size_t)n);
+        if (n == 1) *depthOut = 0;
+    }
+    float* nodes = (float*)(bvh + 16);
+    const Prim* prims = (const Prim*)(bvh + offPrims);
+    uint32_t node = total - tid - 1;
+    {
+        f3 c, h;
+        leaf_box(prims, node - nInternal, c, h);
+        float4* nd = (float4*)(nodes + 8 * (size_t)node); // 16-byte aligned: the node array starts 16 bytes into the buffer
+        __stcg(nd, make_float4(c.x, c.y, c.z, __uint_as_float((node - nInternal) | 0x80000000u)));
+        __stcg(nd + 1, make_float4(h.x, h.y, h.z, __uint_as_float(1u)));
+    }
+    refit_climb(node, H, nodes, counter, depthOut);
 }
 
 // -------------------------------------------------------------------- update
@@ -920,41 +927,12 @@ __global__ void k_tlas_emit(const TlasLoaded* __restrict__ loaded, const TlasBla
     records[i] = r;
 }
 
-// the climb of k_refit over leaf nodes that k_tlas_emit has already written
+// refit_climb from every leaf node (written by k_tlas_emit)
 __global__ void k_tlas_refit(uint32_t n, const HNode* H, uint8_t* dst, unsigned long long* counter, uint32_t* depthOut) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= n) return;
-    const uint32_t total = 2 * n - 1;
     if (tid == 0 && n == 1) *depthOut = 0;
-    float* nodes = (float*)(dst + 16);
-    uint32_t node = total - tid - 1;
-    uint32_t count = 1, height = 0;
-    while (node != 0) {
-        const uint32_t parent = ld_u(&H[node].parent);
-        __threadfence();
-        const unsigned long long arrived = atomicAdd(&counter[parent], ((unsigned long long)height << 32) | count);
-        const uint32_t other = (uint32_t)arrived, otherHeight = (uint32_t)(arrived >> 32);
-        if (other == 0) return;
-        __threadfence();
-        uint32_t l = ld_u(&H[parent].left), r = ld_u(&H[parent].right);
-        const uint32_t lc = (l == node) ? count : other, rc = (l == node) ? other : count;
-        if (lc > rc) { const uint32_t t = l; l = r; r = t; } // smaller subtree left; ties keep Karras order
-        const float4* A = (const float4*)(nodes + 8 * (size_t)l);
-        const float4* B = (const float4*)(nodes + 8 * (size_t)r);
-        const float4 a0 = __ldcg(A), a1 = __ldcg(A + 1), b0 = __ldcg(B), b1 = __ldcg(B + 1);
-        const f3 ac = mk3(a0.x, a0.y, a0.z), ah = mk3(a1.x, a1.y, a1.z);
-        const f3 bc = mk3(b0.x, b0.y, b0.z), bh = mk3(b1.x, b1.y, b1.z);
-        const f3 mn = min3(ac - ah, bc - bh), mx = max3(ac + ah, bc + bh);
-        const f3 c = (mn + mx) * 0.5f;
-        const f3 h = mx - c;
-        float4* nd = (float4*)(nodes + 8 * (size_t)parent);
-        __stcg(nd, make_float4(c.x, c.y, c.z, __uint_as_float(l & 0x3fffffffu)));
-        __stcg(nd + 1, make_float4(h.x, h.y, h.z, __uint_as_float(r)));
-        node = parent;
-        count += other;
-        height = (height > otherHeight ? height : otherHeight) + 1;
-        if (node == 0) *depthOut = height;
-    }
+    refit_climb(2 * n - 2 - tid, H, (float*)(dst + 16), counter, depthOut);
 }
 
 } // namespace
