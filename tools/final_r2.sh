@@ -10,6 +10,8 @@ python bench.py --workload vwvan --steps 3 --no-cpu-baseline > $out/${tag}_bench
 python bench.py --workload blobs20m --spp 32 --steps 2 --no-cpu-baseline > $out/${tag}_bench_blobs20m.json 2> $out/${tag}_bench_blobs20m.err
 python bench.py --workload blobs871k --steps 2 --no-cpu-baseline > $out/${tag}_bench_blobs871k.json 2> $out/${tag}_bench_blobs871k.err
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+# launch list of the bench command itself (per-launch durations: serialised, cold caches -> shares only)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $out/${tag}_launches_bench_teapot.csv python bench.py --steps 1 --warmup 1 --spp 8 --no-cpu-baseline > $out/${tag}_launches_bench_teapot.log 2>&1
 for f in teapot cornell dragon vwvan blobs20m blobs871k; do python - <<PY
 import json
 try:
