@@ -357,7 +357,7 @@ typedef struct TbRenderStats {
 } TbRenderStats;
 
 /* Multi-GPU: how the frame is partitioned over the ranks of a communicator. */
-#define TB_SHARD_SAMPLES 1u /* rank r renders frames r, r+N, ...; reduction = all-gather + sum in fixed rank order */
+#define TB_SHARD_SAMPLES 1u /* rank r renders frames r, r+N, ...; reduction = sum over the ranks in fixed rank order */
 #define TB_SHARD_ROWS 2u    /* bands of 8 rows, band b on rank b mod N; reduction = gather of the owned bands (bit-identical to one GPU) */
 #define TB_COMM_ID_BYTES 128 /* sizeof(ncclUniqueId) */
 
@@ -365,7 +365,7 @@ typedef struct TbCommInfo {
     uint32_t Rank, NumRanks, ShardMode, NcclVersion;
     uint64_t Reductions;                 /* tb_comm_reduce calls so far */
     uint64_t BytesReceivedPerReduction;  /* over NVLink, per rank */
-    double LastReductionMilliseconds;    /* CUDA events around pack + all-gather + combine */
+    double LastReductionMilliseconds;    /* CUDA events around the whole exchange + combine */
     double TotalReductionMilliseconds;   /* the same, summed over all reductions */
     uint32_t Transport;                  /* TB_COMM_TRANSPORT_* of the last reduction (NCCL until the first one) */
     uint32_t Reserved;
