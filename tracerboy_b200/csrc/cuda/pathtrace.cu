@@ -1409,14 +1409,16 @@ __global__ void __launch_bounds__(128) k_trace_rays_tlas(const uint8_t* __restri
             float committedT = r.TMax, hb1 = 0.0f, hb2 = 0.0f;
             bool haveHit = false;
             uint32_t hitInst = 0, hitGeom = 0, hitPrim = 0, tris = 0, boxes = 0;
-            uint32_t tstack[TB_TLAS_STACK_DEPTH + 1];
+            // A waiting top-level node is kept as its two reference words (flags | left, right): they were read with its box,
+            // so a pop goes straight to the children's boxes (or the instance record) without fetching the node again.
+            uint2 tstack[TB_TLAS_STACK_DEPTH + 1];
             int tsp = 0;
-            { const RefNode root = tnodes[0]; const SlabRange rr = box(root, committedT); if (rr.enter < rr.exit) tstack[tsp++] = 0; }
+            { const RefNode root = tnodes[0]; const SlabRange rr = box(root, committedT); if (rr.enter < rr.exit) tstack[tsp++] = make_uint2(root.flags, root.right); }
             uint32_t stack[TB_STACK_WORDS];
             while (tsp > 0) {
-                const RefNode nd = tnodes[tstack[--tsp]];
-                if (nd.flags & 0x80000000u) {
-                    const TlasInstanceRecord rec = records[nd.flags & 0x3fffffffu];
+                const uint2 nd = tstack[--tsp];
+                if (nd.x & 0x80000000u) {
+                    const TlasInstanceRecord rec = records[nd.x & 0x3fffffffu];
                     if (rec.mask == 0) continue; // GetInstanceMask & InstanceInclusionMask
                     const float* w = rec.worldToObject;
                     const f3 oorg = mk3(((w[0] * worg.x + w[1] * worg.y) + w[2] * worg.z) + w[3] * 1.0f,
@@ -1443,13 +1445,13 @@ __global__ void __launch_bounds__(128) k_trace_rays_tlas(const uint8_t* __restri
                         committedT = tr.committedT; hb1 = tr.hb1; hb2 = tr.hb2; hitGeom = tr.hitGeom; hitPrim = tr.hitPrim; hitInst = rec.instanceIndex; haveHit = true;
                     }
                 } else {
-                    const uint32_t l = nd.flags & 0x3fffffffu, rr = nd.right;
-                    const RefNode L = tnodes[l], R = tnodes[rr];
+                    const RefNode L = tnodes[nd.x & 0x3fffffffu], R = tnodes[nd.y];
                     const SlabRange a = box(L, committedT), b = box(R, committedT);
                     boxes += 2;
                     const bool lh = a.enter < a.exit, rh = b.enter < b.exit;
-                    if (lh && rh) { const bool rightFirst = b.enter < a.enter; tstack[tsp++] = rightFirst ? l : rr; tstack[tsp++] = rightFirst ? rr : l; }
-                    else if (lh || rh) tstack[tsp++] = rh ? rr : l;
+                    const uint2 le = make_uint2(L.flags, L.right), re = make_uint2(R.flags, R.right);
+                    if (lh && rh) { const bool rightFirst = b.enter < a.enter; tstack[tsp++] = rightFirst ? le : re; tstack[tsp++] = rightFirst ? re : le; }
+                    else if (lh || rh) tstack[tsp++] = rh ? re : le;
                 }
             }
             o.TrianglesTested = tris; o.BoxesTested = boxes;
