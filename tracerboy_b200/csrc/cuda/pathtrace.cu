@@ -1461,6 +1461,119 @@ __global__ void __launch_bounds__(128) k_trace_rays_tlas(const uint8_t* __restri
     }
 }
 
+
+// The same query with the warp scheduled like k_extend: every lane owns one ray and is, at any moment, waiting for one of
+// three steps - a top-level step (commit a finished instance, pop a waiting top-level node: children boxes or instance
+// entry), a bottom-level box-pair step, a bottom-level triangle step. Each iteration the whole warp executes the step
+// most lanes wait for, so the three code paths never serialise inside an iteration. Per ray the sequence of steps (and
+// with it every result and counter) is exactly k_trace_rays_tlas's.
+__global__ void __launch_bounds__(128, 4) k_trace_rays_tlas_warp(const uint8_t* __restrict__ tlas, const TlasInstanceRecord* __restrict__ records,
+                                                                 const TbRay* __restrict__ rays, uint64_t n, TbHit* __restrict__ hits) {
+    const RefNode* __restrict__ tnodes = (const RefNode*)(tlas + 16);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5), warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (uint64_t base = warp * 32; base < n; base += warps * 32) {
+        const uint64_t i = base + lane;
+        const bool valid = i < n;
+        TbRay r;
+        if (valid) r = rays[i];
+        else { r.Origin[0] = r.Origin[1] = r.Origin[2] = 0.0f; r.Direction[0] = r.Direction[1] = 0.0f; r.Direction[2] = 1.0f; r.TMin = 0.0f; r.TMax = 0.0f; }
+        const f3 worg = mk3(r.Origin[0], r.Origin[1], r.Origin[2]), wdir = mk3(r.Direction[0], r.Direction[1], r.Direction[2]);
+        const bool nanRay = worg.x != worg.x || worg.y != worg.y || worg.z != worg.z || wdir.x != wdir.x || wdir.y != wdir.y || wdir.z != wdir.z;
+        const f3 inv = mk3(1.0f / wdir.x, 1.0f / wdir.y, 1.0f / wdir.z), oinv = worg * inv, ainv = abs3(inv);
+        const int zmask = (wdir.x == 0.0f ? 1 : 0) | (wdir.y == 0.0f ? 2 : 0) | (wdir.z == 0.0f ? 4 : 0); // D6
+        auto box = [&](const RefNode& b, float closest) {
+            return zmask ? slab_zero(closest, worg, zmask, oinv, inv, ainv, b.c[0], b.c[1], b.c[2], b.h[0], b.h[1], b.h[2])
+                         : slab(closest, oinv, inv, ainv, b.c[0], b.c[1], b.c[2], b.h[0], b.h[1], b.h[2]);
+        };
+        float committedT = r.TMax, hb1 = 0.0f, hb2 = 0.0f;
+        bool haveHit = false;
+        uint32_t hitInst = 0, hitGeom = 0, hitPrim = 0, tris = 0, boxes = 0;
+        uint2 tstack[TB_TLAS_STACK_DEPTH + 1];
+        int tsp = 0;
+        if (valid && !nanRay) { // D7
+            const RefNode root = tnodes[0];
+            const SlabRange rr = box(root, committedT);
+            if (rr.enter < rr.exit) tstack[tsp++] = make_uint2(root.flags, root.right);
+        }
+        uint32_t stack[TB_STACK_WORDS];
+        Traversal tr;
+        tr.idle(stack);
+        // the instance this lane is inside of
+        bool inBlas = false;
+        uint32_t curInst = 0, seedGeom = 0, seedPrim = 0;
+        float tBefore = 0.0f;
+        const float4* __restrict__ pairs = nullptr;
+        const float4* __restrict__ btris = nullptr;
+        while (true) {
+            const bool busyBlas = inBlas && !tr.done();
+            const bool wantLeaf = busyBlas && tr.at_leaf();
+            const bool wantInt = busyBlas && !tr.at_leaf();
+            const bool wantTop = !busyBlas && (inBlas || tsp > 0);
+            const uint32_t nL = __popc(__ballot_sync(0xffffffffu, wantLeaf)), nI = __popc(__ballot_sync(0xffffffffu, wantInt));
+            const uint32_t nT = __popc(__ballot_sync(0xffffffffu, wantTop));
+            if (nL + nI + nT == 0) break;
+            if (nT >= nL && nT >= nI) {
+                if (wantTop) {
+                    if (inBlas) { // the instance's bottom level is done: commit what it found
+                        tris += tr.trisTested; boxes += tr.boxes_tested();
+                        if (tr.haveHit && (tr.committedT != tBefore || tr.hitGeom != seedGeom || tr.hitPrim != seedPrim || !haveHit)) {
+                            committedT = tr.committedT; hb1 = tr.hb1; hb2 = tr.hb2; hitGeom = tr.hitGeom; hitPrim = tr.hitPrim; hitInst = curInst; haveHit = true;
+                        }
+                        inBlas = false;
+                        tr.cur = TB_NO_NODE;
+                    }
+                    if (tsp > 0) {
+                        const uint2 nd = tstack[--tsp];
+                        if (nd.x & 0x80000000u) {
+                            const TlasInstanceRecord rec = records[nd.x & 0x3fffffffu];
+                            if (rec.mask != 0) { // GetInstanceMask & InstanceInclusionMask
+                                const float* w = rec.worldToObject;
+                                const f3 oorg = mk3(((w[0] * worg.x + w[1] * worg.y) + w[2] * worg.z) + w[3] * 1.0f,
+                                                    ((w[4] * worg.x + w[5] * worg.y) + w[6] * worg.z) + w[7] * 1.0f,
+                                                    ((w[8] * worg.x + w[9] * worg.y) + w[10] * worg.z) + w[11] * 1.0f);
+                                const f3 odir = mk3(((w[0] * wdir.x + w[1] * wdir.y) + w[2] * wdir.z) + w[3] * 0.0f,
+                                                    ((w[4] * wdir.x + w[5] * wdir.y) + w[6] * wdir.z) + w[7] * 0.0f,
+                                                    ((w[8] * wdir.x + w[9] * wdir.y) + w[10] * wdir.z) + w[11] * 0.0f);
+                                seedGeom = hitGeom; seedPrim = hitPrim; // see k_trace_rays_tlas
+                                if (haveHit && rec.instanceIndex < hitInst) seedGeom = seedPrim = 0xffffffffu;
+                                else if (haveHit && rec.instanceIndex > hitInst) seedGeom = seedPrim = 0u;
+                                DeviceBvh blas;
+                                blas.root.c[0] = blas.root.c[1] = blas.root.c[2] = 0.0f; blas.root.h[0] = blas.root.h[1] = blas.root.h[2] = 0.0f; blas.root.flags = 0; blas.root.right = 0;
+                                tr.begin_bottom_level(blas, rec.rootRef, stack, oorg, odir, r.TMin, r.TMax, committedT, haveHit, seedGeom, seedPrim);
+                                tBefore = committedT;
+                                curInst = rec.instanceIndex;
+                                pairs = (const float4*)rec.pairs;
+                                btris = (const float4*)rec.tris;
+                                inBlas = true;
+                            }
+                        } else {
+                            const RefNode L = tnodes[nd.x & 0x3fffffffu], R = tnodes[nd.y];
+                            const SlabRange a = box(L, committedT), b = box(R, committedT);
+                            boxes += 2;
+                            const bool lh = a.enter < a.exit, rh = b.enter < b.exit;
+                            const uint2 le = make_uint2(L.flags, L.right), re = make_uint2(R.flags, R.right);
+                            if (lh && rh) { const bool rightFirst = b.enter < a.enter; tstack[tsp++] = rightFirst ? le : re; tstack[tsp++] = rightFirst ? re : le; }
+                            else if (lh || rh) tstack[tsp++] = rh ? re : le;
+                        }
+                    }
+                }
+            } else if (nL >= nI) {
+                if (wantLeaf) tr.step_leaf(stack, btris);
+            } else {
+                if (wantInt) tr.step_internal(stack, pairs);
+            }
+        }
+        if (valid) {
+            TbHit o;
+            o.t = -1.0f; o.b1 = o.b2 = 0.0f; o.PrimitiveIndex = o.GeometryIndex = 0xffffffffu; o.InstanceIndex = 0;
+            o.TrianglesTested = tris; o.BoxesTested = boxes;
+            if (haveHit && committedT < r.TMax) { o.t = committedT; o.b1 = hb1; o.b2 = hb2; o.PrimitiveIndex = hitPrim; o.GeometryIndex = hitGeom; o.InstanceIndex = hitInst; }
+            hits[i] = o;
+        }
+    }
+}
+
 } // namespace
 
 // ------------------------------------------------------------------ launchers
@@ -1654,7 +1767,11 @@ cudaError_t trace_rays_tlas(const uint8_t* tlasRef, const TlasInstanceRecord* re
     uint64_t blocks = (n + 127) / 128, cap = (uint64_t)(numSMs > 0 ? numSMs : 148) * 16;
     if (blocks > cap) blocks = cap;
     if (blocks == 0) return cudaSuccess;
-    k_trace_rays_tlas<<<(uint32_t)blocks, 128, 0, stream>>>(tlasRef, records, d_rays, n, d_hits); lc.count++;
+    // TB_TLAS_QUERY=thread selects the one-thread-per-ray form (kept as the plain statement of the loop; same results)
+    static const bool perThread = [] { const char* e = getenv("TB_TLAS_QUERY"); return e && strcmp(e, "thread") == 0; }();
+    if (perThread) k_trace_rays_tlas<<<(uint32_t)blocks, 128, 0, stream>>>(tlasRef, records, d_rays, n, d_hits);
+    else k_trace_rays_tlas_warp<<<(uint32_t)blocks, 128, 0, stream>>>(tlasRef, records, d_rays, n, d_hits);
+    lc.count++;
     return cudaGetLastError();
 }
 
